@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory by RUNNING THE UNMODIFIED REFERENCE
+(/root/reference/AbDock/src, imported read-only) on seeded synthetic inputs.
+
+The reference ships no tests or golden vectors, so these fixtures --
+outputs of the reference's own code, produced in the build container -- are what pins the
+oracle (tests/test_oracle_golden.py) and, through it, the CUDA path (tests/test_gpu_*.py).
+
+    python tests/golden/make_golden.py          # rewrites tests/golden/*.npz
+
+Weights are not stored: oracle.weights.make_state_dict(seed, ...) regenerates them
+deterministically (numpy RandomState) and is loaded into the reference with strict=True.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import weights, transitions as T   # noqa: E402
+from refload import build_reference_fulldpm    # noqa: E402
+
+
+def npz(name, **arrays):
+    out = {}
+    for k, v in arrays.items():
+        out[k] = v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **out)
+    print(f'{name}: {os.path.getsize(path) / 1024:.0f} KiB')
+
+
+@torch.no_grad()
+def main():
+    torch.set_num_threads(1)          # single-thread reference: reproducible reduction order
+    # ---------------------------------------------------------------- GABlock / GAEncoder
+    seed_w, nl = 11, 2
+    W = weights.make_state_dict(seed=seed_w, num_layers=nl, flavour='abdock')
+    model, m = build_reference_fulldpm(W, num_layers=nl, obj='pred_x0')
+    inp = weights.synthetic_inputs(21, 2, 24, gen_slices=((8, 14),), ragged=True)
+    R = m['so3'].so3vec_to_rotation(inp['v'])
+    t = inp['p'] / 10.0
+    blk = model.eps_net.encoder.blocks[0]
+    x, z, mask = inp['res_feat'], inp['pair_feat'], inp['mask_res']
+    logits = blk._node_logits(x) + blk._pair_logits(z) + blk._spatial_logits(R, t, x)
+    alpha = m['ga']._alpha_from_logits(logits * np.sqrt(1 / 3), mask)
+    feat = torch.cat([blk._pair_aggregation(alpha, z), blk._node_aggregation(alpha, x),
+                      blk._spatial_aggregation(alpha, R, t, x)], -1)
+    npz('ga_block.npz', seed_w=seed_w, num_layers=nl, seed_in=21, N=2, L=24,
+        logits=logits, alpha=alpha, feat=feat, x_out=blk(R, t, x, z, mask),
+        enc_out=model.eps_net.encoder(R, t, x, z, mask))
+
+    # ---------------------------------------------------------------- EpsilonNet (AbDock flavour)
+    beta = W['trans_pos.var_sched.betas'][57].expand(2)
+    out = model.eps_net(inp['v'], t, inp['s'], x, z, beta, inp['mask_generate'], mask)
+    npz('eps_net_abdock.npz', seed_w=seed_w, num_layers=nl, seed_in=21, N=2, L=24, t=57,
+        v_next=out[0], R_next=out[1], eps_pos=out[2], c_denoised=out[3], prmsd_logits=out[4],
+        prmsd=model.prmsd.compute_prmsd(out[4]))
+
+    # ---------------------------------------------------------------- transitions, replayed noise
+    # One reverse step's three denoise calls at t = 57 (histogram branch), t = 3 (Gaussian
+    # branch: sigma <= 0.1) and t = 1 (noise switched off), N=1, L=12 so that the
+    # (N*L, 8191) exponential draw stays small enough to store.
+    sm = weights.synthetic_inputs(22, 1, 12, gen_slices=((3, 9),))
+    dpm_ref = m['dpm_full']
+    for tstep in (57, 3, 1):
+        seed_n = 1000 + tstep
+        noise = T.draw_step_noise(1, 12, torch.Generator().manual_seed(seed_n))
+        tt = torch.full((1,), tstep, dtype=torch.long)
+        v_t, p_t, s_t = sm['v'], sm['p'] / 10.0, sm['s']
+        v_net = m['so3'].rotation_to_so3vec(m['so3'].so3vec_to_rotation(sm['v'] * 0.7))
+        p_pred = p_t * 0.9 + 0.05
+        c0 = torch.softmax(sm['res_feat'][..., :20], -1)
+        torch.manual_seed(seed_n)      # the reference draws from the global generator
+        eps_p = model.trans_pos.pred_noise_from_start(p_t, p_pred, sm['mask_generate'], tt)
+        v_next = model.trans_rot.denoise(v_t, v_net, sm['mask_generate'], tt)
+        p_next = model.trans_pos.denoise(p_t, eps_p, sm['mask_generate'], tt)
+        post, s_next = model.trans_seq.denoise(s_t, c0, sm['mask_generate'], tt)
+        ppl = dpm_ref.calc_perplexity(post, sm['mask_generate'])
+        npz(f'transitions_t{tstep}.npz', seed_in=22, N=1, L=12, t=tstep, v_net=v_net, p_pred=p_pred,
+            c0=c0, eps_p=eps_p, v_next=v_next, p_next=p_next, post=post, s_next=s_next, ppl=ppl,
+            **{'noise_' + k: v for k, v in noise.items()})
+
+    # ---------------------------------------------------------------- forward noising (optimize path)
+    seed_n = 2024
+    tt = torch.full((1,), 40, dtype=torch.long)
+    noise = T.draw_step_noise(1, 12, torch.Generator().manual_seed(seed_n))
+    torch.manual_seed(seed_n)
+    v_noisy, _ = model.trans_rot.add_noise(sm['v'], sm['mask_generate'], tt)
+    p_noisy, _ = model.trans_pos.add_noise(sm['p'] / 10.0, sm['mask_generate'], tt)
+    _, s_noisy = model.trans_seq.add_noise(sm['s'], sm['mask_generate'], tt)
+    npz('add_noise_t40.npz', seed_in=22, N=1, L=12, t=40, v_noisy=v_noisy, p_noisy=p_noisy,
+        s_noisy=s_noisy, **{'noise_' + k: v for k, v in noise.items()})
+
+    # ---------------------------------------------------------------- FullDPM.sample, first steps
+    # Same-seed run of the reference; we keep the initial state and the first two reverse
+    # steps (later steps decorrelate chaotically even reference-vs-reference, SURVEY finding 4)
+    # plus the whole amino-acid trajectory of the generated residues.
+    seed_s = 4242
+    torch.manual_seed(seed_s)
+    traj = model.sample(inp['v'], inp['p'], inp['s'], x, z, inp['mask_generate'], mask)
+    keep = {}
+    for k in (100, 99, 98):
+        keep[f'v_{k}'], keep[f'p_{k}'], keep[f's_{k}'] = traj[k][0], traj[k][1], traj[k][2]
+    keep['prmsd_99'], keep['ppl_99'] = traj[99][3], traj[99][4]
+    npz('sample_first_steps.npz', seed_w=seed_w, num_layers=nl, seed_in=21, N=2, L=24, seed_s=seed_s,
+        **keep)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,144 @@
+"""Pins the CPU oracle against outputs of the UNMODIFIED reference (tests/golden/*.npz,
+produced by tests/golden/make_golden.py).  Runs anywhere (no GPU, no /root/reference)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import weights, ipa, epsnet, sampler, transitions as T, geometry as G
+
+
+def load(golden_dir, name):
+    d = np.load(os.path.join(golden_dir, name))
+    return {k: torch.from_numpy(d[k]) if d[k].ndim else d[k].item() for k in d.files}
+
+
+@pytest.fixture(scope='module')
+def case(golden_dir):
+    g = load(golden_dir, 'ga_block.npz')
+    W = weights.make_state_dict(seed=g['seed_w'], num_layers=g['num_layers'], flavour='abdock')
+    inp = weights.synthetic_inputs(g['seed_in'], g['N'], g['L'], gen_slices=((8, 14),), ragged=True)
+    return W, inp
+
+
+@pytest.mark.parametrize('materialize', [True, False])
+def test_ga_block_matches_reference(golden_dir, case, materialize):
+    g = load(golden_dir, 'ga_block.npz')
+    W, inp = case
+    R, t = G.so3_exp(inp['v']), inp['p'] / 10.0
+    out, parts = ipa.ga_block(W, 'eps_net.encoder.blocks.0.', R, t, inp['res_feat'], inp['pair_feat'],
+                              inp['mask_res'], materialize=materialize, return_parts=True)
+    torch.testing.assert_close(parts['logits'], g['logits'], rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(parts['alpha'], g['alpha'], rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(parts['feat'], g['feat'], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(out, g['x_out'], rtol=1e-4, atol=1e-5)
+    enc = ipa.ga_encoder(W, 'eps_net.encoder.', R, t, inp['res_feat'], inp['pair_feat'], inp['mask_res'],
+                         g['num_layers'], materialize)
+    torch.testing.assert_close(enc, g['enc_out'], rtol=1e-4, atol=2e-5)
+
+
+def test_masked_rows_have_zero_attention(case):
+    W, inp = case
+    R, t = G.so3_exp(inp['v']), inp['p'] / 10.0
+    _, parts = ipa.ga_block(W, 'eps_net.encoder.blocks.0.', R, t, inp['res_feat'], inp['pair_feat'],
+                            inp['mask_res'], return_parts=True)
+    a = parts['alpha']
+    assert (~inp['mask_res']).any()
+    assert a[~inp['mask_res']].abs().max() == 0
+    assert a.transpose(1, 2)[~inp['mask_res']].abs().max() == 0          # masked keys get no weight
+    torch.testing.assert_close(a[inp['mask_res']].sum(1), torch.ones_like(a[inp['mask_res']].sum(1)))
+
+
+def test_eps_net_matches_reference(golden_dir, case):
+    g = load(golden_dir, 'eps_net_abdock.npz')
+    W, inp = case
+    beta = W['trans_pos.var_sched.betas'][g['t']].expand(g['N'])
+    out = epsnet.eps_net(W, inp['v'], inp['p'] / 10.0, inp['s'], inp['res_feat'], inp['pair_feat'], beta,
+                         inp['mask_generate'], inp['mask_res'])
+    torch.testing.assert_close(out[1], g['R_next'], rtol=0, atol=2e-6)
+    torch.testing.assert_close(out[2], g['eps_pos'], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(out[3], g['c_denoised'], rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(out[4], g['prmsd_logits'], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(epsnet.prmsd_score(out[4]), g['prmsd'], rtol=1e-5, atol=1e-5)
+    # v_next goes through the ill-conditioned log map: compare as rotations
+    torch.testing.assert_close(G.so3_exp(out[0]), G.so3_exp(g['v_next']), rtol=0, atol=1e-5)
+    # context residues keep their orientation bit-for-bit
+    keep = ~inp['mask_generate']
+    assert torch.equal(out[0][keep], inp['v'][keep])
+
+
+@pytest.mark.parametrize('tstep', [57, 3, 1])
+def test_transitions_replayed_noise(golden_dir, tstep):
+    g = load(golden_dir, f'transitions_t{tstep}.npz')
+    W = T.diffusion_buffers(100)
+    sm = weights.synthetic_inputs(g['seed_in'], g['N'], g['L'], gen_slices=((3, 9),))
+    noise = {k[6:]: v for k, v in g.items() if k.startswith('noise_')}
+    tt = torch.full((g['N'],), tstep, dtype=torch.long)
+    v_t, p_t, s_t, mg = sm['v'], sm['p'] / 10.0, sm['s'], sm['mask_generate']
+    eps_p = T.pos_pred_noise_from_start(W, p_t, g['p_pred'], mg, tt)
+    torch.testing.assert_close(eps_p, g['eps_p'], rtol=1e-6, atol=1e-6)
+    v_next = T.rot_denoise(W, v_t, g['v_net'], mg, tt, noise)
+    torch.testing.assert_close(G.so3_exp(v_next), G.so3_exp(g['v_next']), rtol=0, atol=1e-5)
+    assert torch.equal(v_next[~mg], v_t[~mg])
+    p_next = T.pos_denoise(W, p_t, g['eps_p'], mg, tt, noise['z_pos'])
+    torch.testing.assert_close(p_next, g['p_next'], rtol=1e-6, atol=1e-6)
+    post, s_next = T.seq_denoise(W, s_t, g['c0'], mg, tt, noise['expo_seq'])
+    torch.testing.assert_close(post, g['post'], rtol=1e-6, atol=1e-8)
+    assert torch.equal(s_next, g['s_next'])                               # bit-exact indices
+    torch.testing.assert_close(epsnet.perplexity(post, mg), g['ppl'], rtol=1e-6, atol=1e-7)
+    if tstep == 1:      # last step adds no noise: pure network update
+        torch.testing.assert_close(G.so3_exp(v_next[mg]), G.so3_exp(g['v_net'][mg]), rtol=0, atol=1e-5)
+
+
+def test_add_noise_replayed(golden_dir):
+    g = load(golden_dir, 'add_noise_t40.npz')
+    W = T.diffusion_buffers(100)
+    sm = weights.synthetic_inputs(g['seed_in'], g['N'], g['L'], gen_slices=((3, 9),))
+    noise = {k[6:]: v for k, v in g.items() if k.startswith('noise_')}
+    tt = torch.full((g['N'],), g['t'], dtype=torch.long)
+    mg = sm['mask_generate']
+    v_noisy, _ = T.rot_add_noise(W, sm['v'], mg, tt, noise)
+    torch.testing.assert_close(G.so3_exp(v_noisy), G.so3_exp(g['v_noisy']), rtol=0, atol=1e-5)
+    torch.testing.assert_close(T.pos_add_noise(W, sm['p'] / 10.0, mg, tt, noise['z_pos']), g['p_noisy'],
+                               rtol=1e-6, atol=1e-6)
+    _, s_noisy = T.seq_add_noise(W, sm['s'], mg, tt, noise['expo_seq'])
+    assert torch.equal(s_noisy, g['s_noisy'])
+
+
+def test_multinomial_emulation_matches_torch():
+    """argmax(p / Exp(1)) IS torch.multinomial(p, 1) for the same generator state."""
+    p = torch.rand(64, 20) + 1e-3
+    a = torch.multinomial(p, 1, generator=torch.Generator().manual_seed(5)).squeeze(-1)
+    q = torch.empty(64, 20).exponential_(1, generator=torch.Generator().manual_seed(5))
+    assert torch.equal(a, T.multinomial_from_exp(p, q))
+    p = torch.rand(8, 8192)[:, :-1]                                       # non-contiguous slice, as so3.py:123
+    a = torch.multinomial(p, 1, generator=torch.Generator().manual_seed(6)).squeeze(-1)
+    q = torch.empty(8, 8191).exponential_(1, generator=torch.Generator().manual_seed(6))
+    assert torch.equal(a, T.multinomial_from_exp(p, q))
+
+
+def test_sample_same_seed_first_steps(golden_dir, case):
+    """Same seed -> same draws -> the oracle reproduces the reference's trajectory start.
+    (Relies on torch's CPU generator giving the same stream as when the fixture was made.)"""
+    g = load(golden_dir, 'sample_first_steps.npz')
+    W, inp = case
+    gen = torch.Generator().manual_seed(g['seed_s'])
+    traj = sampler.sample(W, inp['v'], inp['p'], inp['s'], inp['res_feat'], inp['pair_feat'],
+                          inp['mask_generate'], inp['mask_res'], obj='pred_x0', gen=gen, stop_at=98)
+    assert torch.equal(traj[100][2], g['s_100'])
+    torch.testing.assert_close(traj[100][1], g['p_100'], rtol=1e-6, atol=1e-5)
+    torch.testing.assert_close(G.so3_exp(traj[100][0]), G.so3_exp(g['v_100']), rtol=0, atol=1e-5)
+    for k in (99, 98):
+        assert torch.equal(traj[k][2], g[f's_{k}'])
+        torch.testing.assert_close(traj[k][1], g[f'p_{k}'], rtol=1e-4, atol=1e-3)   # Angstrom
+    torch.testing.assert_close(traj[99][3], g['prmsd_99'], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(traj[99][4], g['ppl_99'], rtol=1e-5, atol=1e-6)
+
+
+def test_schedule_properties():
+    s = T.variance_schedule(100)
+    assert s['betas'][0] == 0 and (s['betas'][1:] > 0).all() and s['betas'].max() <= 0.999
+    assert (s['alpha_bars'][1:] < s['alpha_bars'][:-1]).all()
+    assert math.isclose(s['alpha_bars'][0].item(), 1.0)
