@@ -1,0 +1,33 @@
+"""ab_opt_b200: B200-native (sm_100a) implementation of ab_opt's reverse-diffusion sampling hot
+path -- FullDPM.sample / optimize -> EpsilonNet -> GAEncoder (invariant point attention) -> SO(3) /
+R^3 / categorical transitions -- as hand-written CUDA kernels behind a C ABI
+(include/abopt_b200.h, ab_opt_b200/_lib/libabopt_b200.so) and a thin PyTorch-facing mirror of the
+reference's module interface.  There is no CPU fallback.
+"""
+from . import _capi
+from ._capi import AboptError, launch_count
+from .modules.encoders.ga import GABlock, GAEncoder
+from .modules.diffusion.dpm_full import EpsilonNet, FullDPM, FullDPMAbDesign
+from .modules.diffusion.transition import (VarianceSchedule, PositionTransition, RotationTransition,
+                                           AminoacidCategoricalTransition)
+
+__all__ = ['GABlock', 'GAEncoder', 'EpsilonNet', 'FullDPM', 'FullDPMAbDesign', 'VarianceSchedule',
+           'PositionTransition', 'RotationTransition', 'AminoacidCategoricalTransition', 'AboptError',
+           'launch_count', 'install_into_reference']
+
+
+def install_into_reference(package='src'):
+    """Swap the reference's hot-path classes for the B200 ones so that its entry points
+    (dock_pdb.py / design_pdb.py, configs/*.yml, checkpoints) run unchanged.
+
+    package = 'src' (AbDock) or 'diffab' (AbDesign); the reference package must be importable.
+    Must be called before the reference's `models/diffab.py` is imported.
+    """
+    import importlib
+    dpm = importlib.import_module(f'{package}.modules.diffusion.dpm_full')
+    ga = importlib.import_module(f'{package}.modules.encoders.ga')
+    dpm.FullDPM = FullDPM if package == 'src' else FullDPMAbDesign
+    dpm.EpsilonNet = EpsilonNet
+    ga.GAEncoder = GAEncoder
+    ga.GABlock = GABlock
+    return dpm, ga

@@ -1,0 +1,739 @@
+// C ABI of libabopt_b200 (see include/abopt_b200.h): model life cycle, weight packing, workspace and the
+// orchestration of the kernels into GABlock / GAEncoder / EpsilonNet / FullDPM.sample|optimize.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/abopt_b200.h"
+#include "kernels.h"
+
+namespace abopt {
+unsigned long long g_launches = 0;
+}
+using namespace abopt;
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return fail(ABOPT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));        \
+  } while (0)
+#define CHECK_LAUNCH() CUDA_TRY(cudaGetLastError())
+
+struct DeviceGuard {
+  int prev = -1; bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) { cudaSetDevice(dev); switched = true; }
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
+// ------------------------------------------------------------------------------------------ model
+struct HostTensor { std::vector<unsigned char> bytes; size_t numel = 0; int dtype = 0; bool set = false; };
+struct KeySpec { size_t numel; int dtype; bool required; };
+
+struct Workspace {
+  int N = 0, L = 0, Lp = 0, NB = 0;
+  size_t bytes = 0;
+  void* base = nullptr;
+  float *Rbuf, *pnorm, *xa, *xb, *proj, *feat, *S, *alpha, *prmsd_rows, *prmsd_logits, *maxprob;
+  float *v_net, *eps_pos, *c_den, *R_next;
+  int* bin_idx;
+  long long* tvec_scratch;
+};
+
+struct HostIO {       // device staging for abopt_sample_host
+  int N = 0, L = 0, T0 = 0;
+  void* base = nullptr; size_t bytes = 0;
+  float *v, *p, *res_feat, *pair_feat, *traj_v, *traj_p, *traj_prmsd, *traj_ppl;
+  long long *s, *traj_s;
+  uint8_t *mask_gen, *mask_res;
+};
+
+struct abopt_model {
+  abopt_config cfg;
+  int device = 0;
+  bool finalized = false;
+  std::map<std::string, KeySpec> spec;
+  std::map<std::string, HostTensor> sd;
+  void* wbase = nullptr; size_t wbytes = 0;
+  std::vector<BlockW> blocks;
+  std::vector<PairBiasParams> pb;
+  EpsW eps;
+  DiffW diff;
+  Workspace ws;
+  HostIO io;
+  cudaStream_t own_stream = nullptr;
+};
+
+static void add_key(abopt_model* m, const std::string& k, size_t numel, int dtype = 0, bool required = true) {
+  m->spec[k] = KeySpec{numel, dtype, required};
+}
+
+static void build_spec(abopt_model* m) {
+  const int T1 = m->cfg.num_steps + 1;
+  const int scope = m->cfg.scope;
+  if (scope != ABOPT_SCOPE_ENCODER) {
+    add_key(m, "eps_net.current_sequence_embedding.weight", 25 * F);
+    add_key(m, "eps_net.res_feat_mixer.0.weight", F * 2 * F); add_key(m, "eps_net.res_feat_mixer.0.bias", F);
+    add_key(m, "eps_net.res_feat_mixer.2.weight", F * F);     add_key(m, "eps_net.res_feat_mixer.2.bias", F);
+  }
+  for (int l = 0; l < m->cfg.num_layers; ++l) {
+    const std::string p = "eps_net.encoder.blocks." + std::to_string(l) + ".";
+    add_key(m, p + "spatial_coef", H);
+    add_key(m, p + "proj_query.weight", H * D * F); add_key(m, p + "proj_key.weight", H * D * F);
+    add_key(m, p + "proj_value.weight", H * D * F); add_key(m, p + "proj_pair_bias.weight", H * C);
+    add_key(m, p + "proj_query_point.weight", H * P * 3 * F); add_key(m, p + "proj_key_point.weight", H * P * 3 * F);
+    add_key(m, p + "proj_value_point.weight", H * P * 3 * F);
+    add_key(m, p + "out_transform.weight", F * NFEAT); add_key(m, p + "out_transform.bias", F);
+    add_key(m, p + "layer_norm_1.gamma", F); add_key(m, p + "layer_norm_1.beta", F);
+    add_key(m, p + "layer_norm_2.gamma", F); add_key(m, p + "layer_norm_2.beta", F);
+    for (int i : {0, 2, 4}) {
+      add_key(m, p + "mlp_transition." + std::to_string(i) + ".weight", F * F);
+      add_key(m, p + "mlp_transition." + std::to_string(i) + ".bias", F);
+    }
+  }
+  if (scope == ABOPT_SCOPE_ENCODER) return;
+  const char* heads[3] = {"eps_crd_net", "eps_rot_net", "eps_seq_net"};
+  const int nout[3] = {3, 3, NAA};
+  for (int hh = 0; hh < 3; ++hh) {
+    const std::string p = std::string("eps_net.") + heads[hh] + ".";
+    add_key(m, p + "0.weight", F * (F + 3)); add_key(m, p + "0.bias", F);
+    add_key(m, p + "2.weight", F * F);       add_key(m, p + "2.bias", F);
+    add_key(m, p + "4.weight", (size_t)nout[hh] * F); add_key(m, p + "4.bias", nout[hh]);
+  }
+  if (m->cfg.has_prmsd) {
+    const std::string p = "eps_net.prmsd_predictor.";
+    add_key(m, p + "layer_norm.gamma", F + 3); add_key(m, p + "layer_norm.beta", F + 3);
+    add_key(m, p + "linear_1.weight", F * (F + 3)); add_key(m, p + "linear_1.bias", F);
+    add_key(m, p + "linear_2.weight", F * F);       add_key(m, p + "linear_2.bias", F);
+    add_key(m, p + "linear_3.weight", (size_t)m->cfg.prmsd_bins * F); add_key(m, p + "linear_3.bias", m->cfg.prmsd_bins);
+    if (scope == ABOPT_SCOPE_FULL) add_key(m, "prmsd.tobin.offset", m->cfg.prmsd_bins, 0, false);
+  }
+  if (scope != ABOPT_SCOPE_FULL) return;
+  for (const char* mod : {"trans_rot", "trans_pos", "trans_seq"})
+    for (const char* k : {"betas", "alpha_bars", "alphas", "sigmas", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod"})
+      add_key(m, std::string(mod) + ".var_sched." + k, T1);
+  for (const char* tab : {"fwd", "inv"}) {
+    const std::string p = std::string("trans_rot.angular_distrib_") + tab + ".";
+    add_key(m, p + "stddevs", T1); add_key(m, p + "approx_flag", T1, 1);
+    add_key(m, p + "X", (size_t)T1 * NBINS); add_key(m, p + "Y", (size_t)T1 * NBINS);
+  }
+  add_key(m, "position_mean", 3); add_key(m, "position_scale", 1);
+  add_key(m, "_dummy", 0, 0, false); add_key(m, "trans_rot._dummy", 0, 0, false);
+}
+
+extern "C" int abopt_version(void) { return 100; }
+extern "C" const char* abopt_last_error(void) { return g_err.c_str(); }
+extern "C" uint64_t abopt_kernel_launch_count(void) { return (uint64_t)g_launches; }
+
+extern "C" int abopt_model_create(const abopt_config* cfg, int device, abopt_model** out) {
+  if (!cfg || !out) return fail(ABOPT_ERR_ARG, "null argument");
+  if (cfg->num_layers < 1 || cfg->num_layers > 64) return fail(ABOPT_ERR_ARG, "num_layers out of range");
+  if (cfg->num_steps < 2 || cfg->num_steps > 4096) return fail(ABOPT_ERR_ARG, "num_steps out of range");
+  if (cfg->scope < 0 || cfg->scope > 2) return fail(ABOPT_ERR_ARG, "bad scope");
+  if (cfg->has_prmsd && (cfg->prmsd_bins < 2 || cfg->prmsd_bins > 42)) return fail(ABOPT_ERR_ARG, "prmsd_bins must be in [2, 42]");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(ABOPT_ERR_ARG, "no such CUDA device");
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(ABOPT_ERR_CUDA, std::string("libabopt_b200 needs a B200-class GPU (sm_100); found ") + prop.name);
+  DeviceGuard g(device);
+  CUDA_TRY(linear_kernels_init());
+  CUDA_TRY(attn_kernels_init());
+  abopt_model* m = new abopt_model();
+  m->cfg = *cfg;
+  m->device = device;
+  build_spec(m);
+  CUDA_TRY(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+  *out = m;
+  return ABOPT_OK;
+}
+
+extern "C" void abopt_model_destroy(abopt_model* m) {
+  if (!m) return;
+  DeviceGuard g(m->device);
+  if (m->wbase) cudaFree(m->wbase);
+  if (m->ws.base) cudaFree(m->ws.base);
+  if (m->io.base) cudaFree(m->io.base);
+  if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  delete m;
+}
+
+extern "C" int abopt_model_set_tensor(abopt_model* m, const char* key, const void* data, size_t numel, int dtype, int on_device) {
+  if (!m || !key) return fail(ABOPT_ERR_ARG, "null argument");
+  auto it = m->spec.find(key);
+  if (it == m->spec.end()) return fail(ABOPT_ERR_KEY, std::string("unexpected state-dict key: ") + key);
+  if (it->second.numel != numel) return fail(ABOPT_ERR_KEY, std::string("size mismatch for ") + key + ": expected " +
+                                             std::to_string(it->second.numel) + " elements, got " + std::to_string(numel));
+  if (it->second.dtype != dtype) return fail(ABOPT_ERR_KEY, std::string("dtype mismatch for ") + key);
+  const size_t esz = dtype == 0 ? 4 : (dtype == 1 ? 1 : 8);
+  HostTensor& t = m->sd[key];
+  t.bytes.resize(numel * esz); t.numel = numel; t.dtype = dtype; t.set = true;
+  if (numel) {
+    if (!data) return fail(ABOPT_ERR_ARG, "null data");
+    if (on_device) { DeviceGuard g(m->device); CUDA_TRY(cudaMemcpy(t.bytes.data(), data, numel * esz, cudaMemcpyDeviceToHost)); }
+    else memcpy(t.bytes.data(), data, numel * esz);
+  }
+  m->finalized = false;
+  return ABOPT_OK;
+}
+
+// bump allocator over a host image of the packed weights
+struct Packer {
+  std::vector<unsigned char> img;
+  size_t put(const void* src, size_t bytes) {
+    size_t off = (img.size() + 255) & ~size_t(255);
+    img.resize(off + bytes);
+    memcpy(img.data() + off, src, bytes);
+    return off;
+  }
+  size_t put(const std::vector<float>& v) { return put(v.data(), v.size() * sizeof(float)); }
+};
+
+static const float* F32(abopt_model* m, const std::string& k) { return reinterpret_cast<const float*>(m->sd[k].bytes.data()); }
+static std::vector<float> transpose(const float* w, int rows, int cols, int pad_rows_to = 0) {   // [rows][cols] -> [cols][max(rows,pad)]
+  const int R = pad_rows_to > rows ? pad_rows_to : rows;
+  std::vector<float> o((size_t)cols * R, 0.f);
+  for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) o[(size_t)c * R + r] = w[(size_t)r * cols + c];
+  return o;
+}
+
+extern "C" int abopt_model_finalize(abopt_model* m) {
+  if (!m) return fail(ABOPT_ERR_ARG, "null model");
+  for (auto& kv : m->spec)
+    if (kv.second.required && !m->sd[kv.first].set) return fail(ABOPT_ERR_STATE, "missing state-dict key: " + kv.first);
+  DeviceGuard g(m->device);
+  Packer pk;
+  struct Fix { const float** slot; size_t off; };
+  std::vector<Fix> fix;
+  auto reg = [&](const float** slot, size_t off) { fix.push_back({slot, off}); };
+  const int NL = m->cfg.num_layers;
+  m->blocks.assign(NL, BlockW{});
+  m->pb.assign(NL, PairBiasParams{});
+  for (int l = 0; l < NL; ++l) {
+    const std::string p = "eps_net.encoder.blocks." + std::to_string(l) + ".";
+    BlockW& b = m->blocks[l];
+    std::vector<float> wcat((size_t)NPROJ * F);
+    size_t o = 0;
+    for (const char* nm : {"proj_query", "proj_key", "proj_value", "proj_query_point", "proj_key_point", "proj_value_point"}) {
+      const HostTensor& t = m->sd[p + nm + ".weight"];
+      memcpy(wcat.data() + o, t.bytes.data(), t.numel * 4); o += t.numel;
+    }
+    reg(&b.Wcat, pk.put(wcat));
+    const float* wb = F32(m, p + "proj_pair_bias.weight");         // [12][64]
+    std::vector<float> wbt = transpose(wb, H, C);                    // [64][12]
+    reg(&b.Wb, pk.put(wbt));
+    memcpy(m->pb[l].Wb, wbt.data(), sizeof(float) * C * H);
+    std::vector<float> coef(H);
+    const float* sc = F32(m, p + "spatial_coef");
+    for (int h = 0; h < H; ++h) {                                    // ga.py:109-111
+      const float gamma = sc[h] > 20.f ? sc[h] : log1pf(expf(sc[h]));            // F.softplus (threshold 20)
+      coef[h] = (-1.f * gamma * (float)std::sqrt(2.0 / (9.0 * P))) / 2.f;
+      m->pb[l].coef[h] = coef[h];
+    }
+    reg(&b.coef, pk.put(coef));
+    reg(&b.Wout_t, pk.put(transpose(F32(m, p + "out_transform.weight"), F, NFEAT)));
+    reg(&b.bout, pk.put(F32(m, p + "out_transform.bias"), F * 4));
+    reg(&b.ln1_g, pk.put(F32(m, p + "layer_norm_1.gamma"), F * 4)); reg(&b.ln1_b, pk.put(F32(m, p + "layer_norm_1.beta"), F * 4));
+    reg(&b.ln2_g, pk.put(F32(m, p + "layer_norm_2.gamma"), F * 4)); reg(&b.ln2_b, pk.put(F32(m, p + "layer_norm_2.beta"), F * 4));
+    reg(&b.W1_t, pk.put(transpose(F32(m, p + "mlp_transition.0.weight"), F, F))); reg(&b.b1, pk.put(F32(m, p + "mlp_transition.0.bias"), F * 4));
+    reg(&b.W2_t, pk.put(transpose(F32(m, p + "mlp_transition.2.weight"), F, F))); reg(&b.b2, pk.put(F32(m, p + "mlp_transition.2.bias"), F * 4));
+    reg(&b.W3_t, pk.put(transpose(F32(m, p + "mlp_transition.4.weight"), F, F))); reg(&b.b3, pk.put(F32(m, p + "mlp_transition.4.bias"), F * 4));
+  }
+  EpsW& e = m->eps;
+  e = EpsW{};
+  DiffW& d = m->diff;
+  d = DiffW{};
+  std::vector<size_t> flag_off(2, 0);
+  if (m->cfg.scope != ABOPT_SCOPE_ENCODER) {
+  e.has_prmsd = m->cfg.has_prmsd; e.prmsd_bins = m->cfg.prmsd_bins;
+  reg(&e.emb, pk.put(F32(m, "eps_net.current_sequence_embedding.weight"), 25 * F * 4));
+  reg(&e.Wm0_t, pk.put(transpose(F32(m, "eps_net.res_feat_mixer.0.weight"), F, 2 * F)));
+  reg(&e.bm0, pk.put(F32(m, "eps_net.res_feat_mixer.0.bias"), F * 4));
+  reg(&e.Wm2_t, pk.put(transpose(F32(m, "eps_net.res_feat_mixer.2.weight"), F, F)));
+  reg(&e.bm2, pk.put(F32(m, "eps_net.res_feat_mixer.2.bias"), F * 4));
+  auto pack_head = [&](HeadW& hw, const std::string& w0, const std::string& b0, const std::string& w2, const std::string& b2,
+                       const std::string& w4, const std::string& b4, int nout) {
+    const float* W0 = F32(m, w0);                                    // [128][131]
+    std::vector<float> w0t((size_t)F * F), w0e((size_t)3 * F);
+    for (int n = 0; n < F; ++n) {
+      for (int k = 0; k < F; ++k) w0t[(size_t)k * F + n] = W0[(size_t)n * (F + 3) + k];
+      for (int q = 0; q < 3; ++q) w0e[(size_t)q * F + n] = W0[(size_t)n * (F + 3) + F + q];
+    }
+    reg(&hw.W0_t, pk.put(w0t)); reg(&hw.W0_ext, pk.put(w0e));
+    reg(&hw.b0, pk.put(F32(m, b0), F * 4));
+    reg(&hw.W2_t, pk.put(transpose(F32(m, w2), F, F))); reg(&hw.b2, pk.put(F32(m, b2), F * 4));
+    reg(&hw.W4_t, pk.put(transpose(F32(m, w4), nout, F, F)));
+    std::vector<float> b4p(F, 0.f);
+    memcpy(b4p.data(), F32(m, b4), nout * 4);
+    reg(&hw.b4, pk.put(b4p));
+  };
+  pack_head(e.crd, "eps_net.eps_crd_net.0.weight", "eps_net.eps_crd_net.0.bias", "eps_net.eps_crd_net.2.weight",
+            "eps_net.eps_crd_net.2.bias", "eps_net.eps_crd_net.4.weight", "eps_net.eps_crd_net.4.bias", 3);
+  pack_head(e.rot, "eps_net.eps_rot_net.0.weight", "eps_net.eps_rot_net.0.bias", "eps_net.eps_rot_net.2.weight",
+            "eps_net.eps_rot_net.2.bias", "eps_net.eps_rot_net.4.weight", "eps_net.eps_rot_net.4.bias", 3);
+  pack_head(e.seq, "eps_net.eps_seq_net.0.weight", "eps_net.eps_seq_net.0.bias", "eps_net.eps_seq_net.2.weight",
+            "eps_net.eps_seq_net.2.bias", "eps_net.eps_seq_net.4.weight", "eps_net.eps_seq_net.4.bias", NAA);
+  if (m->cfg.has_prmsd) {
+    const std::string p = "eps_net.prmsd_predictor.";
+    pack_head(e.prm, p + "linear_1.weight", p + "linear_1.bias", p + "linear_2.weight", p + "linear_2.bias",
+              p + "linear_3.weight", p + "linear_3.bias", m->cfg.prmsd_bins);
+    reg(&e.prm_ln_g, pk.put(F32(m, p + "layer_norm.gamma"), (F + 3) * 4));
+    reg(&e.prm_ln_b, pk.put(F32(m, p + "layer_norm.beta"), (F + 3) * 4));
+  }
+  }
+  if (m->cfg.scope == ABOPT_SCOPE_FULL) {
+  const int T1 = m->cfg.num_steps + 1;
+  d.num_steps = m->cfg.num_steps; d.obj_pred_x0 = m->cfg.obj_pred_x0;
+  d.prmsd_min = m->cfg.prmsd_min; d.prmsd_max = m->cfg.prmsd_max;
+  memcpy(d.pos_mean, F32(m, "position_mean"), 12);
+  d.pos_scale = F32(m, "position_scale")[0];
+  reg(&d.betas, pk.put(F32(m, "trans_pos.var_sched.betas"), T1 * 4));
+  reg(&d.alpha_bars, pk.put(F32(m, "trans_pos.var_sched.alpha_bars"), T1 * 4));
+  reg(&d.alphas, pk.put(F32(m, "trans_pos.var_sched.alphas"), T1 * 4));
+  reg(&d.sigmas, pk.put(F32(m, "trans_pos.var_sched.sigmas"), T1 * 4));
+  reg(&d.sqrt_recip_ab, pk.put(F32(m, "trans_pos.var_sched.sqrt_recip_alphas_cumprod"), T1 * 4));
+  reg(&d.sqrt_recipm1_ab, pk.put(F32(m, "trans_pos.var_sched.sqrt_recipm1_alphas_cumprod"), T1 * 4));
+  reg(&d.alpha_bars_rot, pk.put(F32(m, "trans_rot.var_sched.alpha_bars"), T1 * 4));
+  reg(&d.alpha_bars_seq, pk.put(F32(m, "trans_seq.var_sched.alpha_bars"), T1 * 4));
+  for (int tab = 0; tab < 2; ++tab) {
+    const std::string p = std::string("trans_rot.angular_distrib_") + (tab == 0 ? "fwd" : "inv") + ".";
+    reg(&d.ang_X[tab], pk.put(F32(m, p + "X"), (size_t)T1 * NBINS * 4));
+    const float* Y = F32(m, p + "Y");
+    reg(&d.ang_Y[tab], pk.put(Y, (size_t)T1 * NBINS * 4));
+    std::vector<float> cdf((size_t)T1 * NBINS, 1.f);               // inverse-CDF table for fast mode
+    for (int t = 0; t < T1; ++t) {
+      double tot = 0.0;
+      for (int k = 0; k < NBINS - 1; ++k) tot += (double)Y[(size_t)t * NBINS + k];
+      double run = 0.0;
+      for (int k = 0; k < NBINS - 1; ++k) {
+        run += (double)Y[(size_t)t * NBINS + k];
+        cdf[(size_t)t * NBINS + k] = tot > 0.0 ? (float)(run / tot) : (float)(k + 1) / (float)(NBINS - 1);
+      }
+      cdf[(size_t)t * NBINS + NBINS - 2] = 2.f;                      // sentinel: search never runs past the last bin
+    }
+    reg(&d.ang_cdf[tab], pk.put(cdf));
+    reg(&d.ang_std[tab], pk.put(F32(m, p + "stddevs"), T1 * 4));
+    flag_off[tab] = pk.put(m->sd[p + "approx_flag"].bytes.data(), T1);
+  }
+  }
+  if (m->wbase) { CUDA_TRY(cudaFree(m->wbase)); m->wbase = nullptr; }
+  m->wbytes = pk.img.size();
+  CUDA_TRY(cudaMalloc(&m->wbase, m->wbytes));
+  CUDA_TRY(cudaMemcpy(m->wbase, pk.img.data(), m->wbytes, cudaMemcpyHostToDevice));
+  for (auto& f : fix) *f.slot = reinterpret_cast<const float*>(static_cast<unsigned char*>(m->wbase) + f.off);
+  if (m->cfg.scope == ABOPT_SCOPE_FULL)
+    for (int tab = 0; tab < 2; ++tab) d.ang_flag[tab] = static_cast<const uint8_t*>(m->wbase) + flag_off[tab];
+  m->finalized = true;
+  return ABOPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------ workspace
+static int chunk_size(int N, int L, int Lp) {
+  const char* env = getenv("ABOPT_CHUNK");
+  if (env && atoi(env) > 0) return atoi(env) < N ? atoi(env) : N;
+  // logits + attention weights of a chunk should stay L2 resident (126 MB on B200): budget 48 MB
+  const double per = 2.0 * H * (double)L * Lp * 4.0;
+  int nb = (int)(48.0 * 1024 * 1024 / per);
+  if (nb < 1) nb = 1;
+  return nb < N ? nb : N;
+}
+
+static int ensure_workspace(abopt_model* m, int N, int L) {
+  Workspace& w = m->ws;
+  if (w.base && w.N >= N && w.L == L) return ABOPT_OK;
+  if (w.base) { CUDA_TRY(cudaFree(w.base)); w.base = nullptr; }
+  const int Lp = (L + 3) & ~3;
+  const int NB = chunk_size(N, L, Lp);
+  const size_t M = (size_t)N * L;
+  const int bins = m->cfg.has_prmsd ? m->cfg.prmsd_bins : 1;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+  const size_t oR = take(M * 9 * 4), oP = take(M * 3 * 4), oXa = take(M * F * 4), oXb = take(M * F * 4),
+               oProj = take(M * NPROJ * 4), oFeat = take(M * NFEAT * 4), oS = take((size_t)NB * H * L * Lp * 4),
+               oAl = take((size_t)NB * H * L * Lp * 4), oPr = take(M * bins * 4), oPl = take((size_t)N * bins * 4),
+               oMp = take(M * 4), oVn = take(M * 3 * 4), oEp = take(M * 3 * 4), oCd = take(M * NAA * 4), oRn = take(M * 9 * 4),
+               oBi = take(M * 4), oTv = take((size_t)N * 8);
+  CUDA_TRY(cudaMalloc(&w.base, off));
+  unsigned char* b = static_cast<unsigned char*>(w.base);
+  w.Rbuf = (float*)(b + oR); w.pnorm = (float*)(b + oP); w.xa = (float*)(b + oXa); w.xb = (float*)(b + oXb);
+  w.proj = (float*)(b + oProj); w.feat = (float*)(b + oFeat); w.S = (float*)(b + oS); w.alpha = (float*)(b + oAl);
+  w.prmsd_rows = (float*)(b + oPr); w.prmsd_logits = (float*)(b + oPl); w.maxprob = (float*)(b + oMp);
+  w.v_net = (float*)(b + oVn); w.eps_pos = (float*)(b + oEp); w.c_den = (float*)(b + oCd); w.R_next = (float*)(b + oRn);
+  w.bin_idx = (int*)(b + oBi); w.tvec_scratch = (long long*)(b + oTv);
+  w.N = N; w.L = L; w.Lp = Lp; w.NB = NB; w.bytes = off;
+  return ABOPT_OK;
+}
+
+extern "C" size_t abopt_workspace_bytes(const abopt_model* m) { return m ? m->ws.bytes : 0; }
+
+static int check_ready(abopt_model* m, int N, int L, int need_scope = ABOPT_SCOPE_ENCODER) {
+  if (!m) return fail(ABOPT_ERR_ARG, "null model");
+  // scope order of capability: FULL (0) > EPSNET (2) > ENCODER (1)
+  const int have = m->cfg.scope;
+  const bool ok = (need_scope == ABOPT_SCOPE_ENCODER) || (need_scope == ABOPT_SCOPE_EPSNET && have != ABOPT_SCOPE_ENCODER) ||
+                  (need_scope == ABOPT_SCOPE_FULL && have == ABOPT_SCOPE_FULL);
+  if (!ok) return fail(ABOPT_ERR_STATE, "model scope does not include this operation");
+  if (!m->finalized) return fail(ABOPT_ERR_STATE, "model not finalised (call abopt_model_finalize after loading every tensor)");
+  if (N < 1 || L < 1) return fail(ABOPT_ERR_ARG, "N and L must be positive");
+  if (L > ABOPT_MAX_L) return fail(ABOPT_ERR_ARG, "L exceeds ABOPT_MAX_L (" + std::to_string(ABOPT_MAX_L) + ")");
+  if ((size_t)N * L > (size_t)1 << 30) return fail(ABOPT_ERR_ARG, "N*L too large");
+  return ABOPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------ encoder
+// one GABlock: x_in -> x_out (may not alias); feat/alpha taps optional
+static int run_block(abopt_model* m, int layer, int N, int L, const float* R, const float* t, const float* x,
+                     const float* z, const uint8_t* mask, float* x_out, float* alpha_tap, cudaStream_t st) {
+  Workspace& w = m->ws;
+  const int M = N * L;
+  const BlockW& bw = m->blocks[layer];
+  launch_proj(M, x, bw.Wcat, R, t, w.proj, st);
+  for (int b0 = 0; b0 < N; b0 += w.NB) {
+    const int nb = (N - b0 < w.NB) ? (N - b0) : w.NB;
+    launch_logits(nb, L, w.Lp, w.proj + (size_t)b0 * L * NPROJ, bw.coef, w.S, st);
+    launch_pair(nb, b0, L, w.Lp, z, mask, w.S, m->pb[layer], w.alpha, w.feat, st);
+    launch_aggr(nb, b0, L, w.Lp, w.alpha, w.proj, R, t, w.feat, st);
+    if (alpha_tap) launch_alpha_tap(nb, b0, L, w.Lp, w.alpha, alpha_tap, st);
+  }
+  if (x_out) launch_tail(M, w.feat, x, mask, bw, x_out, st);
+  CHECK_LAUNCH();
+  return ABOPT_OK;
+}
+
+extern "C" int abopt_ga_block_forward(abopt_model* m, int layer, int N, int L, const float* R, const float* t,
+                                      const float* x, const float* z, const uint8_t* mask, float* x_out, void* stream) {
+  int rc = check_ready(m, N, L); if (rc) return rc;
+  if (layer < 0 || layer >= m->cfg.num_layers) return fail(ABOPT_ERR_ARG, "layer out of range");
+  if (!R || !t || !x || !z || !mask || !x_out) return fail(ABOPT_ERR_ARG, "null tensor");
+  DeviceGuard g(m->device);
+  rc = ensure_workspace(m, N, L); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* dst = (x_out == x) ? m->ws.xa : x_out;
+  rc = run_block(m, layer, N, L, R, t, x, z, mask, dst, nullptr, st); if (rc) return rc;
+  if (dst != x_out) CUDA_TRY(cudaMemcpyAsync(x_out, dst, (size_t)N * L * F * 4, cudaMemcpyDeviceToDevice, st));
+  return ABOPT_OK;
+}
+
+extern "C" int abopt_ga_block_taps(abopt_model* m, int layer, int N, int L, const float* R, const float* t,
+                                   const float* x, const float* z, const uint8_t* mask, float* alpha, float* feat, void* stream) {
+  int rc = check_ready(m, N, L); if (rc) return rc;
+  if (layer < 0 || layer >= m->cfg.num_layers) return fail(ABOPT_ERR_ARG, "layer out of range");
+  if (!R || !t || !x || !z || !mask) return fail(ABOPT_ERR_ARG, "null tensor");
+  DeviceGuard g(m->device);
+  rc = ensure_workspace(m, N, L); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = run_block(m, layer, N, L, R, t, x, z, mask, nullptr, alpha, st); if (rc) return rc;
+  if (feat) CUDA_TRY(cudaMemcpyAsync(feat, m->ws.feat, (size_t)N * L * NFEAT * 4, cudaMemcpyDeviceToDevice, st));
+  return ABOPT_OK;
+}
+
+// all layers; result lands in *result (one of the two workspace ping-pong buffers)
+static int run_encoder(abopt_model* m, int N, int L, const float* R, const float* t, const float* x, const float* z,
+                       const uint8_t* mask, float** result, cudaStream_t st) {
+  Workspace& w = m->ws;
+  const float* cur = x;
+  float* bufs[2] = {w.xa, w.xb};
+  int which = (x == w.xa) ? 1 : 0;
+  for (int l = 0; l < m->cfg.num_layers; ++l) {
+    int rc = run_block(m, l, N, L, R, t, cur, z, mask, bufs[which], nullptr, st); if (rc) return rc;
+    cur = bufs[which]; which ^= 1;
+  }
+  *result = const_cast<float*>(cur);
+  return ABOPT_OK;
+}
+
+extern "C" int abopt_ga_encoder_forward(abopt_model* m, int N, int L, const float* R, const float* t, const float* x,
+                                        const float* z, const uint8_t* mask, float* x_out, void* stream) {
+  int rc = check_ready(m, N, L); if (rc) return rc;
+  if (!R || !t || !x || !z || !mask || !x_out) return fail(ABOPT_ERR_ARG, "null tensor");
+  DeviceGuard g(m->device);
+  rc = ensure_workspace(m, N, L); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* res = nullptr;
+  rc = run_encoder(m, N, L, R, t, x, z, mask, &res, st); if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(x_out, res, (size_t)N * L * F * 4, cudaMemcpyDeviceToDevice, st));
+  return ABOPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------ EpsilonNet
+// p_ang != null: positions arrive in Angstrom and are normalised on the fly into ws.pnorm
+static int run_eps_net(abopt_model* m, int N, int L, const float* v_t, const float* p_t, const float* p_ang,
+                       const long long* s_t, const float* res_feat, const float* pair_feat, const float* beta, int beta_stride,
+                       const uint8_t* mask_gen, const uint8_t* mask_res, float* v_next, float* R_next, float* eps_pos,
+                       float* c_den, float* prmsd_logits, cudaStream_t st) {
+  Workspace& w = m->ws;
+  const int M = N * L;
+  launch_mixer(M, res_feat, s_t, v_t, m->eps, w.xa, w.Rbuf, p_ang, w.pnorm, m->diff.pos_mean, m->diff.pos_scale, st);
+  const float* tpos = p_ang ? w.pnorm : p_t;
+  float* enc = nullptr;
+  int rc = run_encoder(m, N, L, w.Rbuf, tpos, w.xa, pair_feat, mask_res, &enc, st); if (rc) return rc;
+  launch_heads(M, L, enc, beta, beta_stride, w.Rbuf, v_t, mask_gen, m->eps, v_next, R_next, eps_pos, c_den, w.prmsd_rows,
+               m->cfg.has_prmsd ? (prmsd_logits ? prmsd_logits : w.prmsd_logits) : nullptr, st);
+  CHECK_LAUNCH();
+  return ABOPT_OK;
+}
+
+extern "C" int abopt_eps_net_forward(abopt_model* m, int N, int L, const float* v_t, const float* p_t, const int64_t* s_t,
+                                     const float* res_feat, const float* pair_feat, const float* beta,
+                                     const uint8_t* mask_generate, const uint8_t* mask_res, float* v_next, float* R_next,
+                                     float* eps_pos, float* c_denoised, float* prmsd_logits, void* stream) {
+  int rc = check_ready(m, N, L, ABOPT_SCOPE_EPSNET); if (rc) return rc;
+  if (!v_t || !p_t || !s_t || !res_feat || !pair_feat || !beta || !mask_generate || !mask_res || !v_next || !eps_pos || !c_denoised)
+    return fail(ABOPT_ERR_ARG, "null tensor");
+  DeviceGuard g(m->device);
+  rc = ensure_workspace(m, N, L); if (rc) return rc;
+  return run_eps_net(m, N, L, v_t, p_t, nullptr, (const long long*)s_t, res_feat, pair_feat, beta, 1, mask_generate, mask_res,
+                     v_next, R_next, eps_pos, c_denoised, prmsd_logits, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------ transitions
+extern "C" int abopt_rot_denoise(abopt_model* m, int N, int L, const float* v_t, const float* v_net, const uint8_t* mask_generate,
+                                 const int64_t* t, const float* u, const float* expo_ang, const float* unif_ang,
+                                 const float* gauss_ang, float* v_out, void* stream) {
+  int rc = check_ready(m, N, L, ABOPT_SCOPE_FULL); if (rc) return rc;
+  if (!v_t || !v_net || !mask_generate || !t || !u || !expo_ang || !unif_ang || !gauss_ang || !v_out) return fail(ABOPT_ERR_ARG, "null tensor");
+  DeviceGuard g(m->device);
+  rc = ensure_workspace(m, N, L); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  launch_angle_argmax(N * L, L, (const long long*)t, 0, m->diff.ang_Y[1], expo_ang, mask_generate, m->ws.bin_idx, st);
+  NoisePtrs nz{u, unif_ang, gauss_ang, nullptr, nullptr, m->ws.bin_idx};
+  launch_rot_denoise(N * L, L, v_t, v_net, mask_generate, (const long long*)t, nz, m->diff, v_out, st);
+  CHECK_LAUNCH();
+  return ABOPT_OK;
+}
+
+extern "C" int abopt_pos_pred_noise_from_start(abopt_model* m, int N, int L, const float* p_t, const float* p_0,
+                                               const uint8_t* mask_generate, const int64_t* t, float* eps_out, void* stream) {
+  int rc = check_ready(m, N, L, ABOPT_SCOPE_FULL); if (rc) return rc;
+  if (!p_t || !p_0 || !mask_generate || !t || !eps_out) return fail(ABOPT_ERR_ARG, "null tensor");
+  DeviceGuard g(m->device);
+  launch_pos(N * L, L, 0, p_t, p_0, mask_generate, (const long long*)t, nullptr, m->diff, eps_out, (cudaStream_t)stream);
+  CHECK_LAUNCH();
+  return ABOPT_OK;
+}
+
+extern "C" int abopt_pos_denoise(abopt_model* m, int N, int L, const float* p_t, const float* eps_p, const uint8_t* mask_generate,
+                                 const int64_t* t, const float* z_pos, float* p_out, void* stream) {
+  int rc = check_ready(m, N, L, ABOPT_SCOPE_FULL); if (rc) return rc;
+  if (!p_t || !eps_p || !mask_generate || !t || !z_pos || !p_out) return fail(ABOPT_ERR_ARG, "null tensor");
+  DeviceGuard g(m->device);
+  launch_pos(N * L, L, 1, p_t, eps_p, mask_generate, (const long long*)t, z_pos, m->diff, p_out, (cudaStream_t)stream);
+  CHECK_LAUNCH();
+  return ABOPT_OK;
+}
+
+extern "C" int abopt_seq_denoise(abopt_model* m, int N, int L, const int64_t* s_t, const float* c0_pred, const uint8_t* mask_generate,
+                                 const int64_t* t, const float* expo_seq, float* post, int64_t* s_out, void* stream) {
+  int rc = check_ready(m, N, L, ABOPT_SCOPE_FULL); if (rc) return rc;
+  if (!s_t || !c0_pred || !mask_generate || !t || !expo_seq || !post || !s_out) return fail(ABOPT_ERR_ARG, "null tensor");
+  DeviceGuard g(m->device);
+  launch_seq_denoise(N * L, L, (const long long*)s_t, c0_pred, mask_generate, (const long long*)t, expo_seq, m->diff, post,
+                     (long long*)s_out, (cudaStream_t)stream);
+  CHECK_LAUNCH();
+  return ABOPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------ sampling loop
+static int run_init(abopt_model* m, int N, int L, const float* v, const float* p, const long long* s, const uint8_t* mask_generate,
+                    uint32_t flags, int opt_step, uint64_t seed, const abopt_init_noise* init_noise, float* v_out, float* p_out,
+                    long long* s_out, float* prmsd_out, float* ppl_out, cudaStream_t st) {
+  Workspace& w = m->ws;
+  const int M = N * L;
+  const bool optimize = opt_step > 0;
+  const int T0 = optimize ? opt_step : m->cfg.num_steps;
+  InitArgs ia{};
+  ia.M = M; ia.L = L; ia.T0 = T0;
+  ia.sample_structure = (flags & ABOPT_SAMPLE_STRUCTURE) ? 1 : 0; ia.sample_sequence = (flags & ABOPT_SAMPLE_SEQUENCE) ? 1 : 0;
+  ia.optimize = optimize ? 1 : 0;
+  ia.has_prmsd = (m->cfg.has_prmsd && prmsd_out && ppl_out) ? 1 : 0;
+  ia.v = v; ia.p_ang = p; ia.s = s; ia.mask_gen = mask_generate;
+  ia.v_out = v_out; ia.p_out_ang = p_out; ia.s_out = s_out; ia.prmsd_out = prmsd_out; ia.ppl_out = ppl_out;
+  ia.seed = seed;
+  if (init_noise) {
+    if (!optimize) {
+      if (!init_noise->g4 || !init_noise->gp || !init_noise->s_rand) return fail(ABOPT_ERR_ARG, "init_noise for sample() needs g4, gp, s_rand");
+      ia.g4 = init_noise->g4; ia.gp = init_noise->gp; ia.s_rand = (const long long*)init_noise->s_rand;
+    } else {
+      const abopt_step_noise* a = init_noise->add;
+      if (!a || !a->u || !a->expo_ang || !a->unif_ang || !a->gauss_ang || !a->z_pos || !a->expo_seq)
+        return fail(ABOPT_ERR_ARG, "init_noise for optimize() needs a full abopt_step_noise");
+      launch_angle_argmax(M, L, nullptr, T0, m->diff.ang_Y[0], a->expo_ang, mask_generate, w.bin_idx, st);
+      ia.add = NoisePtrs{a->u, a->unif_ang, a->gauss_ang, a->z_pos, a->expo_seq, w.bin_idx};
+    }
+  }
+  launch_init(ia, m->diff, st);
+  CHECK_LAUNCH();
+  return ABOPT_OK;
+}
+
+// one iteration of the loop body: traj[t] -> traj[t-1]
+static int run_step(abopt_model* m, int N, int L, int t, bool optimize, uint32_t flags, uint64_t seed, const float* v_t,
+                    const float* p_t_ang, const long long* s_t, const float* res_feat, const float* pair_feat,
+                    const uint8_t* mask_generate, const uint8_t* mask_res, const abopt_step_noise* nz, float* v_out, float* p_out,
+                    long long* s_out, float* prmsd_out, float* ppl_out, cudaStream_t st) {
+  Workspace& w = m->ws;
+  const int M = N * L;
+  const bool prm = m->cfg.has_prmsd != 0 && prmsd_out && ppl_out;
+  int rc = run_eps_net(m, N, L, v_t, nullptr, p_t_ang, s_t, res_feat, pair_feat, m->diff.betas + t, 0, mask_generate, mask_res,
+                       w.v_net, w.R_next, w.eps_pos, w.c_den, nullptr, st);
+  if (rc) return rc;
+  StepArgs sa{};
+  sa.M = M; sa.L = L; sa.t = t;
+  sa.sample_structure = (flags & ABOPT_SAMPLE_STRUCTURE) ? 1 : 0; sa.sample_sequence = (flags & ABOPT_SAMPLE_SEQUENCE) ? 1 : 0;
+  sa.pred_x0 = (!optimize && m->cfg.obj_pred_x0) ? 1 : 0;         // optimize() ignores obj (dpm_full.py:351-356)
+  sa.masked_ppl = optimize ? 0 : 1;                               // optimize() passes no mask (dpm_full.py:357)
+  sa.v_t = v_t; sa.p_t_ang = p_t_ang; sa.s_t = s_t;
+  sa.v_net = w.v_net; sa.p_pred = w.eps_pos; sa.c_den = w.c_den; sa.mask_gen = mask_generate;
+  sa.v_out = v_out; sa.p_out_ang = p_out; sa.s_out = s_out;
+  sa.maxprob_rows = prm ? w.maxprob : nullptr;
+  sa.seed = seed;
+  if (nz) {
+    if (!nz->u || !nz->expo_ang || !nz->unif_ang || !nz->gauss_ang || !nz->z_pos || !nz->expo_seq)
+      return fail(ABOPT_ERR_ARG, "incomplete abopt_step_noise record");
+    if (sa.sample_structure) launch_angle_argmax(M, L, nullptr, t, m->diff.ang_Y[1], nz->expo_ang, mask_generate, w.bin_idx, st);
+    sa.nz = NoisePtrs{nz->u, nz->unif_ang, nz->gauss_ang, nz->z_pos, nz->expo_seq, w.bin_idx};
+  }
+  launch_step(sa, m->diff, st);
+  if (prm)
+    launch_complex_reduce(N, L, m->cfg.prmsd_bins, m->cfg.prmsd_min, m->cfg.prmsd_max, sa.masked_ppl, w.prmsd_logits, w.maxprob,
+                          mask_generate, prmsd_out, ppl_out, st);
+  CHECK_LAUNCH();
+  return ABOPT_OK;
+}
+
+extern "C" int abopt_sample_init(abopt_model* m, int N, int L, const float* v, const float* p, const int64_t* s,
+                                 const uint8_t* mask_generate, uint32_t flags, int opt_step, uint64_t seed,
+                                 const abopt_init_noise* init_noise, float* v_out, float* p_out, int64_t* s_out, void* stream) {
+  int rc = check_ready(m, N, L, ABOPT_SCOPE_FULL); if (rc) return rc;
+  if (!v || !p || !s || !mask_generate || !v_out || !p_out || !s_out) return fail(ABOPT_ERR_ARG, "null tensor");
+  if (opt_step < 0 || opt_step > m->cfg.num_steps) return fail(ABOPT_ERR_ARG, "opt_step out of range");
+  DeviceGuard g(m->device);
+  rc = ensure_workspace(m, N, L); if (rc) return rc;
+  return run_init(m, N, L, v, p, (const long long*)s, mask_generate, flags, opt_step, seed, init_noise, v_out, p_out,
+                  (long long*)s_out, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int abopt_reverse_step(abopt_model* m, int N, int L, int t, int optimize, const float* v_t, const float* p_t,
+                                  const int64_t* s_t, const float* res_feat, const float* pair_feat, const uint8_t* mask_generate,
+                                  const uint8_t* mask_res, uint32_t flags, uint64_t seed, const abopt_step_noise* noise,
+                                  float* v_out, float* p_out, int64_t* s_out, float* prmsd_out, float* ppl_out, void* stream) {
+  int rc = check_ready(m, N, L, ABOPT_SCOPE_FULL); if (rc) return rc;
+  if (!v_t || !p_t || !s_t || !res_feat || !pair_feat || !mask_generate || !mask_res || !v_out || !p_out || !s_out)
+    return fail(ABOPT_ERR_ARG, "null tensor");
+  if (t < 1 || t > m->cfg.num_steps) return fail(ABOPT_ERR_ARG, "t out of range");
+  DeviceGuard g(m->device);
+  rc = ensure_workspace(m, N, L); if (rc) return rc;
+  return run_step(m, N, L, t, optimize != 0, flags, seed, v_t, p_t, (const long long*)s_t, res_feat, pair_feat, mask_generate,
+                  mask_res, noise, v_out, p_out, (long long*)s_out, prmsd_out, ppl_out, (cudaStream_t)stream);
+}
+
+extern "C" int abopt_sample_device(abopt_model* m, int N, int L, const float* v, const float* p, const int64_t* s,
+                                   const float* res_feat, const float* pair_feat, const uint8_t* mask_generate,
+                                   const uint8_t* mask_res, uint32_t flags, int opt_step, uint64_t seed,
+                                   const abopt_init_noise* init_noise, const abopt_step_noise* noise, float* traj_v,
+                                   float* traj_p, int64_t* traj_s, float* traj_prmsd, float* traj_ppl, void* stream) {
+  int rc = check_ready(m, N, L, ABOPT_SCOPE_FULL); if (rc) return rc;
+  if (!v || !p || !s || !res_feat || !pair_feat || !mask_generate || !mask_res || !traj_v || !traj_p || !traj_s)
+    return fail(ABOPT_ERR_ARG, "null tensor");
+  if (m->cfg.has_prmsd && (!traj_prmsd || !traj_ppl)) return fail(ABOPT_ERR_ARG, "traj_prmsd / traj_ppl required for pRMSD models");
+  if (opt_step < 0 || opt_step > m->cfg.num_steps) return fail(ABOPT_ERR_ARG, "opt_step out of range");
+  if ((noise == nullptr) != (init_noise == nullptr)) return fail(ABOPT_ERR_ARG, "noise and init_noise must be given together");
+  DeviceGuard g(m->device);
+  rc = ensure_workspace(m, N, L); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t M = (size_t)N * L;
+  const bool optimize = opt_step > 0;
+  const int T0 = optimize ? opt_step : m->cfg.num_steps;
+  const bool keep = (flags & ABOPT_KEEP_TRAJECTORY) != 0;
+  const bool prm = m->cfg.has_prmsd != 0;
+  // Slot addressing: with the full trajectory every step has its own slot; otherwise intermediate steps
+  // ping-pong between slots 1 and 2 and only slots T0 and 0 are meaningful to the caller.
+  if (!keep && T0 < 3) return fail(ABOPT_ERR_ARG, "opt_step < 3 requires ABOPT_KEEP_TRAJECTORY");
+  auto slot_of = [&](int t) -> int { return (keep || t == T0 || t == 0) ? t : 1 + (t & 1); };
+  auto V = [&](int t) { return traj_v + (size_t)slot_of(t) * M * 3; };
+  auto Pp = [&](int t) { return traj_p + (size_t)slot_of(t) * M * 3; };
+  auto S = [&](int t) { return (long long*)traj_s + (size_t)slot_of(t) * M; };
+  auto PR = [&](int t) { return prm ? traj_prmsd + (size_t)slot_of(t) * N : nullptr; };
+  auto PL = [&](int t) { return prm ? traj_ppl + (size_t)slot_of(t) * N : nullptr; };
+
+  rc = run_init(m, N, L, v, p, (const long long*)s, mask_generate, flags, opt_step, seed, init_noise, V(T0), Pp(T0), S(T0),
+                PR(T0), PL(T0), st);
+  if (rc) return rc;
+  for (int t = T0; t >= 1; --t) {
+    rc = run_step(m, N, L, t, optimize, flags, seed, V(t), Pp(t), S(t), res_feat, pair_feat, mask_generate, mask_res,
+                  noise ? &noise[T0 - t] : nullptr, V(t - 1), Pp(t - 1), S(t - 1), PR(t - 1), PL(t - 1), st);
+    if (rc) return rc;
+  }
+  return ABOPT_OK;
+}
+
+static int ensure_hostio(abopt_model* m, int N, int L, int T0) {
+  HostIO& io = m->io;
+  if (io.base && io.N == N && io.L == L && io.T0 == T0) return ABOPT_OK;
+  if (io.base) { CUDA_TRY(cudaFree(io.base)); io.base = nullptr; }
+  const size_t M = (size_t)N * L, S1 = (size_t)T0 + 1;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+  const size_t ov = take(M * 12), op = take(M * 12), os = take(M * 8), orf = take(M * F * 4), opf = take(M * L * C * 4),
+               omg = take(M), omr = take(M), otv = take(S1 * M * 12), otp = take(S1 * M * 12), ots = take(S1 * M * 8),
+               opr = take(S1 * N * 4), opl = take(S1 * N * 4);
+  CUDA_TRY(cudaMalloc(&io.base, off));
+  unsigned char* b = static_cast<unsigned char*>(io.base);
+  io.v = (float*)(b + ov); io.p = (float*)(b + op); io.s = (long long*)(b + os); io.res_feat = (float*)(b + orf);
+  io.pair_feat = (float*)(b + opf); io.mask_gen = b + omg; io.mask_res = b + omr; io.traj_v = (float*)(b + otv);
+  io.traj_p = (float*)(b + otp); io.traj_s = (long long*)(b + ots); io.traj_prmsd = (float*)(b + opr); io.traj_ppl = (float*)(b + opl);
+  io.N = N; io.L = L; io.T0 = T0; io.bytes = off;
+  return ABOPT_OK;
+}
+
+extern "C" int abopt_sample_host(abopt_model* m, int N, int L, const float* v, const float* p, const int64_t* s,
+                                 const float* res_feat, const float* pair_feat, const uint8_t* mask_generate,
+                                 const uint8_t* mask_res, uint32_t flags, int opt_step, uint64_t seed, float* traj_v,
+                                 float* traj_p, int64_t* traj_s, float* traj_prmsd, float* traj_ppl) {
+  int rc = check_ready(m, N, L, ABOPT_SCOPE_FULL); if (rc) return rc;
+  if (!v || !p || !s || !res_feat || !pair_feat || !mask_generate || !mask_res || !traj_v || !traj_p || !traj_s)
+    return fail(ABOPT_ERR_ARG, "null tensor");
+  if (opt_step < 0 || opt_step > m->cfg.num_steps) return fail(ABOPT_ERR_ARG, "opt_step out of range");
+  DeviceGuard g(m->device);
+  const int T0 = opt_step > 0 ? opt_step : m->cfg.num_steps;
+  rc = ensure_hostio(m, N, L, T0); if (rc) return rc;
+  HostIO& io = m->io;
+  cudaStream_t st = m->own_stream;
+  const size_t M = (size_t)N * L;
+  CUDA_TRY(cudaMemcpyAsync(io.v, v, M * 12, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(io.p, p, M * 12, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(io.s, s, M * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(io.res_feat, res_feat, M * F * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(io.mask_gen, mask_generate, M, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(io.mask_res, mask_res, M, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(io.pair_feat, pair_feat, M * L * C * 4, cudaMemcpyHostToDevice, st));
+  rc = abopt_sample_device(m, N, L, io.v, io.p, (const int64_t*)io.s, io.res_feat, io.pair_feat, io.mask_gen, io.mask_res, flags,
+                           opt_step, seed, nullptr, nullptr, io.traj_v, io.traj_p, (int64_t*)io.traj_s, io.traj_prmsd, io.traj_ppl, st);
+  if (rc) return rc;
+  const bool keep = (flags & ABOPT_KEEP_TRAJECTORY) != 0;
+  const bool prm = m->cfg.has_prmsd != 0 && traj_prmsd && traj_ppl;
+  auto copy_slots = [&](int first, int count) -> int {
+    CUDA_TRY(cudaMemcpyAsync(traj_v + (size_t)first * M * 3, io.traj_v + (size_t)first * M * 3, (size_t)count * M * 12, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(traj_p + (size_t)first * M * 3, io.traj_p + (size_t)first * M * 3, (size_t)count * M * 12, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(traj_s + (size_t)first * M, io.traj_s + (size_t)first * M, (size_t)count * M * 8, cudaMemcpyDeviceToHost, st));
+    if (prm) {
+      CUDA_TRY(cudaMemcpyAsync(traj_prmsd + (size_t)first * N, io.traj_prmsd + (size_t)first * N, (size_t)count * N * 4, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(traj_ppl + (size_t)first * N, io.traj_ppl + (size_t)first * N, (size_t)count * N * 4, cudaMemcpyDeviceToHost, st));
+    }
+    return ABOPT_OK;
+  };
+  if (keep) { rc = copy_slots(0, T0 + 1); if (rc) return rc; }
+  else { rc = copy_slots(0, 1); if (rc) return rc; rc = copy_slots(T0, 1); if (rc) return rc; }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return ABOPT_OK;
+}

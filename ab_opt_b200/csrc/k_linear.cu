@@ -1,0 +1,421 @@
+// Node-feature linear layers of the hot path (v1: FP32 FFMA on CUDA cores, cp.async pipelined).
+//   mixer_kernel  : EpsilonNet input mixer + R = exp(v_t)           dpm_full.py:86-89
+//   proj_kernel   : the six GABlock input projections + local->global points   ga.py:82-83,96-105,122,129-132
+//   tail_kernel   : out_transform -> mask -> LN -> MLP -> LN        ga.py:173-178
+//   heads_kernel  : eps_crd / eps_rot / eps_seq / pRMSD heads + SO(3) update    dpm_full.py:92-110
+#include "rowtile.cuh"
+#include "params.cuh"
+#include "kernels.h"
+
+namespace abopt {
+
+// ------------------------------------------------------------------------------------------ mixer
+__global__ void __launch_bounds__(RT_THREADS, 2)
+mixer_kernel(int M, const float* __restrict__ res_feat, const long long* __restrict__ s_t,
+             const float* __restrict__ v_t, EpsW w, float* __restrict__ x_out, float* __restrict__ Rbuf,
+             const float* __restrict__ p_ang, float* __restrict__ p_norm, float mean0, float mean1, float mean2, float scale) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RowTileSmem& s = *reinterpret_cast<RowTileSmem*>(smem_raw);
+  float* act = reinterpret_cast<float*>(smem_raw + sizeof(RowTileSmem));      // [64][RT_ACT_LD]
+  __shared__ int aa[RT_ROWS];
+  const int row0 = blockIdx.x * RT_ROWS;
+  if (threadIdx.x < RT_ROWS) {
+    const int r = row0 + threadIdx.x;
+    long long a = (r < M) ? s_t[r] : 0;
+    aa[threadIdx.x] = (int)(a < 0 ? 0 : (a > 24 ? 24 : a));
+    if (r < M && p_ang != nullptr) {     // FullDPM._normalize_position (dpm_full.py:148-150)
+      p_norm[(size_t)r * 3 + 0] = __fdiv_rn(__fadd_rn(p_ang[(size_t)r * 3 + 0], -mean0), scale);
+      p_norm[(size_t)r * 3 + 1] = __fdiv_rn(__fadd_rn(p_ang[(size_t)r * 3 + 1], -mean1), scale);
+      p_norm[(size_t)r * 3 + 2] = __fdiv_rn(__fadd_rn(p_ang[(size_t)r * 3 + 2], -mean2), scale);
+    }
+    if (r < M && Rbuf != nullptr) {
+      const Mat3 R = so3_exp(v_t[r * 3 + 0], v_t[r * 3 + 1], v_t[r * 3 + 2]);
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Rbuf[(size_t)r * 9 + i] = R.m[i];
+    }
+  }
+  __syncthreads();
+  float acc[8][4];
+  rt_zero(acc);
+  // layer 0: [res_feat | embedding(s_t)] (K = 256) -> 128, ReLU
+  rt_gemm_globalA(acc, s, [&](int r, int k) -> const float* {
+    if (row0 + r >= M) return nullptr;
+    return (k < F) ? res_feat + (size_t)(row0 + r) * F + k : w.emb + (size_t)aa[r] * F + (k - F);
+  }, w.Wm0_t, 2 * F);
+  rt_add_bias(acc, w.bm0);
+  rt_relu(acc);
+  rt_store_act(acc, act, RT_ACT_LD);
+  __syncthreads();
+  rt_zero(acc);
+  rt_gemm_smemA(acc, s, act, RT_ACT_LD, w.Wm2_t, F);
+  rt_add_bias(acc, w.bm2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int row = row0 + warp * 8 + r;
+    if (row < M) *reinterpret_cast<float4*>(x_out + (size_t)row * F + lane * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ projections
+// proj[M][2016] = x[M][128] * Wcat^T, point columns mapped to the global frame (R p + t).
+// CTA tile 128 rows x 96 columns (96 | 1152 and 96 | 864, so a tile never straddles the q/k/v | points
+// boundary and every thread's 6 consecutive columns are two whole xyz points).
+constexpr int PJ_BM = 128, PJ_BN = 96, PJ_BK = 16, PJ_THREADS = 256;
+
+__global__ void __launch_bounds__(PJ_THREADS, 2)
+proj_kernel(int M, const float* __restrict__ x, const float* __restrict__ Wcat, const float* __restrict__ R,
+            const float* __restrict__ t, float* __restrict__ proj) {
+  __shared__ __align__(16) float As[2][PJ_BK][PJ_BM + 4];
+  __shared__ __align__(16) float Bs[2][PJ_BK][PJ_BN + 2];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int row0 = blockIdx.y * PJ_BM, col0 = blockIdx.x * PJ_BN;
+
+  float4 ra[2], rb[2];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {                       // A: 128 x 16 = 512 float4
+      const int f4 = tid + i * PJ_THREADS, r = f4 >> 2, kq = f4 & 3;
+      ra[i] = (row0 + r < M) ? *reinterpret_cast<const float4*>(x + (size_t)(row0 + r) * F + k0 + kq * 4)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {                       // B: 96 x 16 = 384 float4
+      const int f4 = tid + i * PJ_THREADS;
+      if (f4 < PJ_BN * 4) {
+        const int n = f4 >> 2, kq = f4 & 3;
+        rb[i] = *reinterpret_cast<const float4*>(Wcat + (size_t)(col0 + n) * F + k0 + kq * 4);
+      }
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int f4 = tid + i * PJ_THREADS, r = f4 >> 2, kq = f4 & 3;
+      As[buf][kq * 4 + 0][r] = ra[i].x; As[buf][kq * 4 + 1][r] = ra[i].y;
+      As[buf][kq * 4 + 2][r] = ra[i].z; As[buf][kq * 4 + 3][r] = ra[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int f4 = tid + i * PJ_THREADS;
+      if (f4 < PJ_BN * 4) {
+        const int n = f4 >> 2, kq = f4 & 3;
+        Bs[buf][kq * 4 + 0][n] = rb[i].x; Bs[buf][kq * 4 + 1][n] = rb[i].y;
+        Bs[buf][kq * 4 + 2][n] = rb[i].z; Bs[buf][kq * 4 + 3][n] = rb[i].w;
+      }
+    }
+  };
+
+  float acc[8][6];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc[r][c] = 0.f;
+
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  constexpr int NK = F / PJ_BK;
+  for (int kb = 0; kb < NK; ++kb) {
+    const int buf = kb & 1;
+    if (kb + 1 < NK) gload((kb + 1) * PJ_BK);
+#pragma unroll
+    for (int k = 0; k < PJ_BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+      const float2 b0 = *reinterpret_cast<const float2*>(&Bs[buf][k][tx * 6]);
+      const float2 b1 = *reinterpret_cast<const float2*>(&Bs[buf][k][tx * 6 + 2]);
+      const float2 b2 = *reinterpret_cast<const float2*>(&Bs[buf][k][tx * 6 + 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[6] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y};
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
+    }
+    if (kb + 1 < NK) sstore(buf ^ 1);
+    __syncthreads();
+  }
+
+  const int col = col0 + tx * 6;
+  const bool is_point = col0 >= OFF_QP;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int row = row0 + ty * 8 + r;
+    if (row >= M) continue;
+    float o[6];
+    if (is_point) {                                       // q = R p + t   (geometry.py:72-91)
+      float Rm[9], tv[3];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Rm[i] = __ldg(R + (size_t)row * 9 + i);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) tv[i] = __ldg(t + (size_t)row * 3 + i);
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          o[q * 3 + i] = Rm[i * 3 + 0] * acc[r][q * 3 + 0] + Rm[i * 3 + 1] * acc[r][q * 3 + 1] + Rm[i * 3 + 2] * acc[r][q * 3 + 2] + tv[i];
+    } else {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) o[c] = acc[r][c];
+    }
+    float2* dst = reinterpret_cast<float2*>(proj + (size_t)row * NPROJ + col);
+    dst[0] = make_float2(o[0], o[1]); dst[1] = make_float2(o[2], o[3]); dst[2] = make_float2(o[4], o[5]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ block tail
+__global__ void __launch_bounds__(RT_THREADS, 2)
+tail_kernel(int M, const float* __restrict__ feat, const float* __restrict__ x, const uint8_t* __restrict__ mask,
+            BlockW w, float* __restrict__ x_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RowTileSmem& s = *reinterpret_cast<RowTileSmem*>(smem_raw);
+  float* act = reinterpret_cast<float*>(smem_raw + sizeof(RowTileSmem));      // [64][RT_ACT_LD]
+  const int row0 = blockIdx.x * RT_ROWS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  float acc[8][4], h[8][4];
+  rt_zero(acc);
+  rt_gemm_globalA(acc, s, [&](int r, int k) -> const float* {
+    return (row0 + r < M) ? feat + (size_t)(row0 + r) * NFEAT + k : nullptr;
+  }, w.Wout_t, NFEAT);
+  rt_add_bias(acc, w.bout);
+  // mask_zero (layers.py:6-7) then residual + LayerNorm 1
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int row = row0 + warp * 8 + r;
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool mk = false;
+    if (row < M) { xv = *reinterpret_cast<const float4*>(x + (size_t)row * F + lane * 4); mk = mask[row] != 0; }
+    h[r][0] = xv.x + (mk ? acc[r][0] : 0.f); h[r][1] = xv.y + (mk ? acc[r][1] : 0.f);
+    h[r][2] = xv.z + (mk ? acc[r][2] : 0.f); h[r][3] = xv.w + (mk ? acc[r][3] : 0.f);
+  }
+  rt_layernorm(h, w.ln1_g, w.ln1_b, 1e-10f);
+  // 3-layer transition MLP
+  rt_store_act(h, act, RT_ACT_LD);
+  __syncthreads();
+  rt_zero(acc);
+  rt_gemm_smemA(acc, s, act, RT_ACT_LD, w.W1_t, F);
+  rt_add_bias(acc, w.b1); rt_relu(acc);
+  rt_store_act(acc, act, RT_ACT_LD);
+  __syncthreads();
+  rt_zero(acc);
+  rt_gemm_smemA(acc, s, act, RT_ACT_LD, w.W2_t, F);
+  rt_add_bias(acc, w.b2); rt_relu(acc);
+  rt_store_act(acc, act, RT_ACT_LD);
+  __syncthreads();
+  rt_zero(acc);
+  rt_gemm_smemA(acc, s, act, RT_ACT_LD, w.W3_t, F);
+  rt_add_bias(acc, w.b3);
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) h[r][c] += acc[r][c];
+  rt_layernorm(h, w.ln2_g, w.ln2_b, 1e-10f);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int row = row0 + warp * 8 + r;
+    if (row < M) *reinterpret_cast<float4*>(x_out + (size_t)row * F + lane * 4) = make_float4(h[r][0], h[r][1], h[r][2], h[r][3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ heads
+constexpr int HD_OUT_LD = 68;      // staged head outputs per row: crd 0-2 | rot 3-5 | seq 6-25 | prmsd 26-65
+
+// One 3-layer head over the 64-row tile.  `in_act` holds the 128 node features; the 3 time-embedding
+// inputs enter as a per-row rank-3 correction `ext[r][q]` (q = 0..2) times W0_ext.
+__device__ __forceinline__ void run_head(float (&acc)[8][4], RowTileSmem& s, const float* in_act, float* hid,
+                                         const HeadW& hw, const float (&ext)[8][3]) {
+  const int lane = threadIdx.x & 31;
+  rt_zero(acc);
+  rt_gemm_smemA(acc, s, in_act, RT_ACT_LD, hw.W0_t, F);
+  rt_add_bias(acc, hw.b0);
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const float4 we = *reinterpret_cast<const float4*>(hw.W0_ext + q * F + lane * 4);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      acc[r][0] = fmaf(ext[r][q], we.x, acc[r][0]); acc[r][1] = fmaf(ext[r][q], we.y, acc[r][1]);
+      acc[r][2] = fmaf(ext[r][q], we.z, acc[r][2]); acc[r][3] = fmaf(ext[r][q], we.w, acc[r][3]);
+    }
+  }
+  rt_relu(acc);
+  __syncthreads();                       // everyone is done reading `hid` from a previous head
+  rt_store_act(acc, hid, RT_ACT_LD);
+  __syncthreads();
+  rt_zero(acc);
+  rt_gemm_smemA(acc, s, hid, RT_ACT_LD, hw.W2_t, F);
+  rt_add_bias(acc, hw.b2);
+  rt_relu(acc);
+  __syncthreads();
+  rt_store_act(acc, hid, RT_ACT_LD);
+  __syncthreads();
+  rt_zero(acc);
+  rt_gemm_smemA(acc, s, hid, RT_ACT_LD, hw.W4_t, F);
+  rt_add_bias(acc, hw.b4);
+}
+
+// copy output columns [0, n) of the tile into the staging buffer at column offset `off`
+__device__ __forceinline__ void stage_out(const float (&acc)[8][4], float* outs, int off, int n) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int col = lane * 4 + c;
+    if (col < n)
+#pragma unroll
+      for (int r = 0; r < 8; ++r) outs[(warp * 8 + r) * HD_OUT_LD + off + col] = acc[r][c];
+  }
+}
+
+__global__ void __launch_bounds__(RT_THREADS, 1)
+heads_kernel(int M, int L, const float* __restrict__ x, const float* __restrict__ beta, int beta_stride,
+             const float* __restrict__ Rbuf, const float* __restrict__ v_t, const uint8_t* __restrict__ mask_gen,
+             EpsW w, float* __restrict__ v_next, float* __restrict__ R_next, float* __restrict__ eps_pos,
+             float* __restrict__ c_den, float* __restrict__ prmsd_rows) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RowTileSmem& s = *reinterpret_cast<RowTileSmem*>(smem_raw);
+  float* xin = reinterpret_cast<float*>(smem_raw + sizeof(RowTileSmem));      // [64][RT_ACT_LD]
+  float* hid = xin + RT_ROWS * RT_ACT_LD;                                     // [64][RT_ACT_LD]
+  float* outs = hid + RT_ROWS * RT_ACT_LD;                                    // [64][HD_OUT_LD]
+  const int row0 = blockIdx.x * RT_ROWS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // resident input tile + per-row time embedding (dpm_full.py:92-93)
+  float ext[8][3];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int row = row0 + warp * 8 + r;
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+    float b = 0.f;
+    if (row < M) { xv = *reinterpret_cast<const float4*>(x + (size_t)row * F + lane * 4); b = beta[(size_t)(row / L) * beta_stride]; }
+    *reinterpret_cast<float4*>(xin + (warp * 8 + r) * RT_ACT_LD + lane * 4) = xv;
+    ext[r][0] = b; ext[r][1] = sinf(b); ext[r][2] = cosf(b);
+  }
+  __syncthreads();
+
+  float acc[8][4];
+  run_head(acc, s, xin, hid, w.crd, ext);  stage_out(acc, outs, 0, 3);
+  run_head(acc, s, xin, hid, w.rot, ext);  stage_out(acc, outs, 3, 3);
+  run_head(acc, s, xin, hid, w.seq, ext);  stage_out(acc, outs, 6, NAA);
+
+  if (w.has_prmsd) {
+    // PerResiduePredictor (common/nn.py:164-188): LayerNorm over the 131 inputs, then 3 linears.
+    float g[8][4], gext[8][3];
+    const float4 lg = *reinterpret_cast<const float4*>(w.prm_ln_g + lane * 4);
+    const float4 lb = *reinterpret_cast<const float4*>(w.prm_ln_b + lane * 4);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float4 xv = *reinterpret_cast<const float4*>(xin + (warp * 8 + r) * RT_ACT_LD + lane * 4);
+      const float sum = warp_sum(xv.x + xv.y + xv.z + xv.w) + (ext[r][0] + ext[r][1] + ext[r][2]);
+      const float mean = sum * (1.f / 131.f);
+      const float d0 = xv.x - mean, d1 = xv.y - mean, d2 = xv.z - mean, d3 = xv.w - mean;
+      const float e0 = ext[r][0] - mean, e1 = ext[r][1] - mean, e2 = ext[r][2] - mean;
+      const float var = (warp_sum(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3) + (e0 * e0 + e1 * e1 + e2 * e2)) * (1.f / 131.f);
+      const float sd = sqrtf(var + 1e-10f);
+      g[r][0] = d0 / sd * lg.x + lb.x; g[r][1] = d1 / sd * lg.y + lb.y;
+      g[r][2] = d2 / sd * lg.z + lb.z; g[r][3] = d3 / sd * lg.w + lb.w;
+      gext[r][0] = e0 / sd * w.prm_ln_g[128] + w.prm_ln_b[128];
+      gext[r][1] = e1 / sd * w.prm_ln_g[129] + w.prm_ln_b[129];
+      gext[r][2] = e2 / sd * w.prm_ln_g[130] + w.prm_ln_b[130];
+    }
+    __syncthreads();                                   // all heads finished reading xin
+    rt_store_act(g, xin, RT_ACT_LD);
+    __syncthreads();
+    run_head(acc, s, xin, hid, w.prm, gext);
+    stage_out(acc, outs, 26, w.prmsd_bins);
+  }
+  __syncthreads();
+
+  // per-residue epilogue: rotate eps_crd, compose the rotation update, softmax the aa logits
+  if (threadIdx.x < RT_ROWS) {
+    const int row = row0 + threadIdx.x;
+    if (row < M) {
+      const float* o = outs + threadIdx.x * HD_OUT_LD;
+      const bool gen = mask_gen[row] != 0;
+      Mat3 R;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) R.m[i] = Rbuf[(size_t)row * 9 + i];
+      // eps_pos = R eps_crd, zero outside the generated region (dpm_full.py:96-98)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float e = R.m[i * 3 + 0] * o[0] + R.m[i * 3 + 1] * o[1] + R.m[i * 3 + 2] * o[2] + 0.f;
+        eps_pos[(size_t)row * 3 + i] = gen ? e : 0.f;
+      }
+      // R_next = R U(eps_rot), v_next = log(R_next) on generated residues (dpm_full.py:101-105)
+      const Mat3 U = quat1ijk_to_rot(o[3], o[4], o[5]);
+      const Mat3 Rn = matmul3(R, U);
+      if (R_next != nullptr)
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R_next[(size_t)row * 9 + i] = Rn.m[i];
+      float vx, vy, vz;
+      so3_log(Rn, vx, vy, vz);
+      v_next[(size_t)row * 3 + 0] = gen ? vx : v_t[(size_t)row * 3 + 0];
+      v_next[(size_t)row * 3 + 1] = gen ? vy : v_t[(size_t)row * 3 + 1];
+      v_next[(size_t)row * 3 + 2] = gen ? vz : v_t[(size_t)row * 3 + 2];
+      // softmax over 20 classes (dpm_full.py:61,108)
+      float mx = o[6];
+#pragma unroll
+      for (int k = 1; k < NAA; ++k) mx = fmaxf(mx, o[6 + k]);
+      float e[NAA], sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < NAA; ++k) { e[k] = expf(o[6 + k] - mx); sum += e[k]; }
+#pragma unroll
+      for (int k = 0; k < NAA; ++k) c_den[(size_t)row * NAA + k] = e[k] / sum;
+      if (w.has_prmsd)
+        for (int k = 0; k < w.prmsd_bins; ++k) prmsd_rows[(size_t)row * w.prmsd_bins + k] = o[26 + k];
+    }
+  }
+}
+
+// prmsd_logits[n][k] = mean over ALL L rows, padding included (dpm_full.py:110).  One CTA per complex,
+// fixed summation order (deterministic).
+__global__ void prmsd_mean_kernel(int L, int bins, const float* __restrict__ prmsd_rows, float* __restrict__ out) {
+  const int n = blockIdx.x, k = threadIdx.x;
+  if (k >= bins) return;
+  float sum = 0.f;
+  for (int l = 0; l < L; ++l) sum += prmsd_rows[((size_t)n * L + l) * bins + k];
+  out[(size_t)n * bins + k] = sum / (float)L;
+}
+
+// ------------------------------------------------------------------------------------------ launchers
+size_t mixer_smem() { return sizeof(RowTileSmem) + RT_ROWS * RT_ACT_LD * sizeof(float); }
+size_t tail_smem() { return sizeof(RowTileSmem) + RT_ROWS * RT_ACT_LD * sizeof(float); }
+size_t heads_smem() { return sizeof(RowTileSmem) + (2 * RT_ROWS * RT_ACT_LD + RT_ROWS * HD_OUT_LD) * sizeof(float); }
+
+cudaError_t linear_kernels_init() {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(mixer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mixer_smem())) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem())) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_smem())) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
+void launch_mixer(int M, const float* res_feat, const long long* s_t, const float* v_t, const EpsW& w,
+                  float* x_out, float* Rbuf, const float* p_ang, float* p_norm, const float* mean, float scale,
+                  cudaStream_t st) {
+  mixer_kernel<<<(M + RT_ROWS - 1) / RT_ROWS, RT_THREADS, mixer_smem(), st>>>(M, res_feat, s_t, v_t, w, x_out, Rbuf, p_ang, p_norm,
+                                                                           mean[0], mean[1], mean[2], scale);
+  count_launch();
+}
+void launch_proj(int M, const float* x, const float* Wcat, const float* R, const float* t, float* proj, cudaStream_t st) {
+  dim3 grid(NPROJ / PJ_BN, (M + PJ_BM - 1) / PJ_BM);
+  proj_kernel<<<grid, PJ_THREADS, 0, st>>>(M, x, Wcat, R, t, proj);
+  count_launch();
+}
+void launch_tail(int M, const float* feat, const float* x, const uint8_t* mask, const BlockW& w, float* x_out, cudaStream_t st) {
+  tail_kernel<<<(M + RT_ROWS - 1) / RT_ROWS, RT_THREADS, tail_smem(), st>>>(M, feat, x, mask, w, x_out);
+  count_launch();
+}
+void launch_heads(int M, int L, const float* x, const float* beta, int beta_stride, const float* Rbuf, const float* v_t,
+                  const uint8_t* mask_gen, const EpsW& w, float* v_next, float* R_next, float* eps_pos, float* c_den,
+                  float* prmsd_rows, float* prmsd_logits, cudaStream_t st) {
+  heads_kernel<<<(M + RT_ROWS - 1) / RT_ROWS, RT_THREADS, heads_smem(), st>>>(M, L, x, beta, beta_stride, Rbuf, v_t, mask_gen, w,
+                                                                           v_next, R_next, eps_pos, c_den, prmsd_rows);
+  count_launch();
+  if (w.has_prmsd && prmsd_logits != nullptr) {
+    prmsd_mean_kernel<<<M / L, 64, 0, st>>>(L, w.prmsd_bins, prmsd_rows, prmsd_logits);
+    count_launch();
+  }
+}
+
+}  // namespace abopt

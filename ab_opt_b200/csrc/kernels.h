@@ -1,0 +1,67 @@
+// Host-side launcher declarations shared by api.cu and the kernel translation units.
+#pragma once
+#include "common.cuh"
+#include "params.cuh"
+
+namespace abopt {
+
+struct NoisePtrs {
+  const float* u; const float* unif_ang; const float* gauss_ang; const float* z_pos; const float* expo_seq;
+  const int* bin_idx;
+};
+struct StepArgs {
+  int M, L, t;
+  int sample_structure, sample_sequence, pred_x0, masked_ppl;
+  const float* v_t; const float* p_t_ang; const long long* s_t;
+  const float* v_net; const float* p_pred; const float* c_den;
+  const uint8_t* mask_gen;
+  float* v_out; float* p_out_ang; long long* s_out;
+  float* maxprob_rows;
+  NoisePtrs nz;
+  uint64_t seed;
+};
+struct InitArgs {
+  int M, L, T0;
+  int sample_structure, sample_sequence, optimize, has_prmsd;
+  const float* v; const float* p_ang; const long long* s; const uint8_t* mask_gen;
+  const float* g4; const float* gp; const long long* s_rand;
+  NoisePtrs add;
+  float* v_out; float* p_out_ang; long long* s_out;
+  float* prmsd_out; float* ppl_out;
+  uint64_t seed;
+};
+
+cudaError_t linear_kernels_init();
+cudaError_t attn_kernels_init();
+
+void launch_mixer(int M, const float* res_feat, const long long* s_t, const float* v_t, const EpsW& w,
+                  float* x_out, float* Rbuf, const float* p_ang, float* p_norm, const float* mean, float scale,
+                  cudaStream_t st);
+void launch_proj(int M, const float* x, const float* Wcat, const float* R, const float* t, float* proj, cudaStream_t st);
+void launch_tail(int M, const float* feat, const float* x, const uint8_t* mask, const BlockW& w, float* x_out, cudaStream_t st);
+void launch_heads(int M, int L, const float* x, const float* beta, int beta_stride, const float* Rbuf, const float* v_t,
+                  const uint8_t* mask_gen, const EpsW& w, float* v_next, float* R_next, float* eps_pos, float* c_den,
+                  float* prmsd_rows, float* prmsd_logits, cudaStream_t st);
+
+void launch_logits(int nb, int L, int Lp, const float* proj_chunk, const float* coef, float* S, cudaStream_t st);
+void launch_pair(int nb, int b0, int L, int Lp, const float* z, const uint8_t* mask, const float* S,
+                 const PairBiasParams& pb, float* alpha, float* feat, cudaStream_t st);
+void launch_aggr(int nb, int b0, int L, int Lp, const float* alpha, const float* proj, const float* R, const float* t,
+                 float* feat, cudaStream_t st);
+void launch_alpha_tap(int nb, int b0, int L, int Lp, const float* alpha, float* out, cudaStream_t st);
+size_t pair_smem_bytes(int L);
+
+void launch_angle_argmax(int M, int L, const long long* tvec, int t_uniform, const float* Y, const float* expo,
+                         const uint8_t* mask_gen, int* bin_idx, cudaStream_t st);
+void launch_step(const StepArgs& a, const DiffW& dw, cudaStream_t st);
+void launch_complex_reduce(int N, int L, int bins, float dmin, float dmax, int masked_ppl, const float* prmsd_logits,
+                           const float* maxprob_rows, const uint8_t* mask_gen, float* prmsd_out, float* ppl_out, cudaStream_t st);
+void launch_init(const InitArgs& a, const DiffW& dw, cudaStream_t st);
+void launch_rot_denoise(int M, int L, const float* v_t, const float* v_net, const uint8_t* mask_gen, const long long* tvec,
+                        const NoisePtrs& nz, const DiffW& dw, float* v_out, cudaStream_t st);
+void launch_pos(int M, int L, int mode, const float* p_t, const float* other, const uint8_t* mask_gen, const long long* tvec,
+                const float* z_pos, const DiffW& dw, float* out, cudaStream_t st);
+void launch_seq_denoise(int M, int L, const long long* s_t, const float* c0, const uint8_t* mask_gen, const long long* tvec,
+                        const float* expo_seq, const DiffW& dw, float* post, long long* s_out, cudaStream_t st);
+
+}  // namespace abopt

@@ -1,0 +1,214 @@
+/*
+ * abopt_b200.h -- C ABI of libabopt_b200.so: the B200 (sm_100a) implementation of ab_opt's
+ * reverse-diffusion sampling hot path.
+ *
+ * The reference (pengzhangzhi/ab_opt) has no FFI of its own: its seam is Python class
+ * substitution behind the model registry.  Each entry point below
+ * therefore replaces one reference *method*; the citation gives the method it stands in for
+ * (paths relative to the reference root, AbDock flavour; the AbDesign mirror is noted where it
+ * differs).  INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; tensors are raw pointers + sizes, row-major contiguous, with the
+ *     reference's shapes: N complexes, L residues, F=128 node channels, C=64 pair channels.
+ *   - fp32 for every floating tensor, int64 for amino-acid indices and step indices, one byte
+ *     per element (0/1) for masks -- exactly torch.float32 / torch.int64 / torch.bool storage.
+ *   - "dev" pointers are device memory on the model's device; "host" pointers are host memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device entry
+ *     points only enqueue work; they never synchronise.  Host entry points return after the
+ *     outputs are complete in host memory.
+ *   - every function returns ABOPT_OK (0) or a negative error code; abopt_last_error() gives a
+ *     thread-local message.  Nothing falls back to the CPU: if no CUDA device of compute
+ *     capability 10.x is usable the calls fail.
+ */
+#ifndef ABOPT_B200_H_
+#define ABOPT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABOPT_OK              0
+#define ABOPT_ERR_ARG        -1   /* bad argument / unsupported shape                       */
+#define ABOPT_ERR_CUDA       -2   /* CUDA runtime error (message has the cudaError string)   */
+#define ABOPT_ERR_STATE      -3   /* model not finalised, tensor missing, ...               */
+#define ABOPT_ERR_KEY        -4   /* unknown state-dict key or wrong element count          */
+
+#define ABOPT_NODE_DIM      128   /* res_feat_dim  (configs/train/dock_single.yml:3)        */
+#define ABOPT_PAIR_DIM       64   /* pair_feat_dim (configs/train/dock_single.yml:4)        */
+#define ABOPT_NUM_HEADS      12   /* modules/encoders/ga.py:43                              */
+#define ABOPT_NUM_AA         20   /* modules/diffusion/transition.py:165                    */
+#define ABOPT_ANGLE_BINS   8192   /* modules/common/so3.py:73                               */
+#define ABOPT_MAX_L         704   /* longest complex the single-pass pair kernel can hold   */
+
+typedef struct abopt_model abopt_model;
+
+/* Hyper-parameters of FullDPM.__init__ (modules/diffusion/dpm_full.py:117-146). */
+typedef struct abopt_config {
+  int32_t num_layers;        /* eps_net_opt.num_layers (6)                                   */
+  int32_t num_steps;         /* num_steps (100)                                              */
+  int32_t has_prmsd;         /* 1 = AbDock flavour (pRMSD head, 5 trajectory fields)         */
+  int32_t prmsd_bins;        /* num_bins (40); ignored when has_prmsd == 0                   */
+  float   prmsd_min;         /* dist_min (0.5)                                               */
+  float   prmsd_max;         /* dist_max (19.5)                                              */
+  int32_t obj_pred_x0;       /* 1 = obj 'pred_x0', 0 = 'pred_noise' (dpm_full.py:143)        */
+  int32_t scope;             /* ABOPT_SCOPE_*: which module this handle backs                */
+} abopt_config;
+
+/* A handle can back a whole FullDPM, or a stand-alone GAEncoder / EpsilonNet module: the scope
+ * decides which state-dict keys are expected (always spelled as inside FullDPM, i.e. with the
+ * "eps_net.encoder.blocks.N." / "eps_net." prefixes) and which entry points are usable. */
+#define ABOPT_SCOPE_FULL     0   /* FullDPM: every entry point                                */
+#define ABOPT_SCOPE_ENCODER  1   /* GAEncoder: abopt_ga_* only                                */
+#define ABOPT_SCOPE_EPSNET   2   /* EpsilonNet: abopt_ga_* and abopt_eps_net_forward          */
+
+/* Flags of abopt_sample_*. */
+#define ABOPT_SAMPLE_STRUCTURE   1u   /* sample_structure=True                               */
+#define ABOPT_SAMPLE_SEQUENCE    2u   /* sample_sequence=True                                */
+#define ABOPT_KEEP_TRAJECTORY    4u   /* fill every trajectory slot (else only slot 0 and T0) */
+
+/* Per-step noise for replayed ("parity") runs; every pointer is a DEVICE pointer holding the
+ * draw the reference makes at that point (RNG draw order):
+ *   u         (N,L,3)      randn            modules/common/so3.py:143
+ *   expo_ang  (N*L,8191)   exponential_(1)  inside multinomial, so3.py:123
+ *   unif_ang  (N*L)        rand             so3.py:126
+ *   gauss_ang (N*L)        randn            so3.py:131
+ *   z_pos     (N,L,3)      randn            modules/diffusion/transition.py:95
+ *   expo_seq  (N*L,20)     exponential_(1)  inside multinomial, transition.py:179          */
+typedef struct abopt_step_noise {
+  const float* u;
+  const float* expo_ang;
+  const float* unif_ang;
+  const float* gauss_ang;
+  const float* z_pos;
+  const float* expo_seq;
+} abopt_step_noise;
+
+/* ------------------------------------------------------------------ library / model life cycle */
+int         abopt_version(void);
+const char* abopt_last_error(void);
+/* Number of kernels this library has launched in the calling process (all models). */
+uint64_t    abopt_kernel_launch_count(void);
+
+/* FullDPM.__init__ : allocate an empty model on CUDA device `device`. */
+int  abopt_model_create(const abopt_config* cfg, int device, abopt_model** out);
+void abopt_model_destroy(abopt_model* m);
+
+/* nn.Module.load_state_dict (tools/runner/design_for_pdb.py:94): copy one tensor of the FullDPM
+ * state-dict, addressed by its reference key (e.g. "eps_net.encoder.blocks.0.proj_query.weight",
+ * "trans_rot.angular_distrib_inv.Y", "position_scale").  `numel` must match the reference shape.
+ * `dtype`: 0 = float32, 1 = uint8/bool, 2 = int64.  `on_device` != 0 if `data` is device memory. */
+int abopt_model_set_tensor(abopt_model* m, const char* key, const void* data, size_t numel,
+                           int dtype, int on_device);
+/* Verify that every tensor is present and build the packed device layout. */
+int abopt_model_finalize(abopt_model* m);
+
+/* ------------------------------------------------------------------ encoder (device pointers) */
+/* GABlock.forward, modules/encoders/ga.py:149-178.
+ *   R (N,L,3,3)  t (N,L,3)  x (N,L,128)  z (N,L,L,64)  mask (N,L) u8  ->  x_out (N,L,128)   */
+int abopt_ga_block_forward(abopt_model* m, int layer, int N, int L, const float* R, const float* t,
+                           const float* x, const float* z, const uint8_t* mask, float* x_out,
+                           void* stream);
+/* GAEncoder.forward, modules/encoders/ga.py:190-193 (all layers). */
+int abopt_ga_encoder_forward(abopt_model* m, int N, int L, const float* R, const float* t,
+                             const float* x, const float* z, const uint8_t* mask, float* x_out,
+                             void* stream);
+/* Debug/parity taps of one block: attention weights alpha (N,L,L,12) in the reference layout and
+ * the concatenated aggregate (N,L,1824) that feeds out_transform (ga.py:166-174).  Either output
+ * may be NULL. */
+int abopt_ga_block_taps(abopt_model* m, int layer, int N, int L, const float* R, const float* t,
+                        const float* x, const float* z, const uint8_t* mask, float* alpha,
+                        float* feat, void* stream);
+
+/* ------------------------------------------------------------------ denoiser network */
+/* EpsilonNet.forward, modules/diffusion/dpm_full.py:70-112 (AbDesign: :62-102).
+ *   v_t,p_t (N,L,3)  s_t (N,L) i64  res_feat (N,L,128)  pair_feat (N,L,L,64)  beta (N,)
+ *   -> v_next (N,L,3)  R_next (N,L,3,3)  eps_pos (N,L,3)  c_denoised (N,L,20)
+ *      prmsd_logits (N,prmsd_bins) (has_prmsd models; may be NULL otherwise)                  */
+int abopt_eps_net_forward(abopt_model* m, int N, int L, const float* v_t, const float* p_t,
+                          const int64_t* s_t, const float* res_feat, const float* pair_feat,
+                          const float* beta, const uint8_t* mask_generate, const uint8_t* mask_res,
+                          float* v_next, float* R_next, float* eps_pos, float* c_denoised,
+                          float* prmsd_logits, void* stream);
+
+/* ------------------------------------------------------------------ transitions (device pointers)
+ * `t` is the (N,) int64 step tensor the reference passes.  Noise pointers follow abopt_step_noise. */
+/* RotationTransition.denoise, modules/diffusion/transition.py:146-160 (+ so3.py:111-146). */
+int abopt_rot_denoise(abopt_model* m, int N, int L, const float* v_t, const float* v_net,
+                      const uint8_t* mask_generate, const int64_t* t, const float* u,
+                      const float* expo_ang, const float* unif_ang, const float* gauss_ang,
+                      float* v_out, void* stream);
+/* PositionTransition.pred_noise_from_start, transition.py:42-50. */
+int abopt_pos_pred_noise_from_start(abopt_model* m, int N, int L, const float* p_t, const float* p_0,
+                                    const uint8_t* mask_generate, const int64_t* t, float* eps_out,
+                                    void* stream);
+/* PositionTransition.denoise, transition.py:80-101. */
+int abopt_pos_denoise(abopt_model* m, int N, int L, const float* p_t, const float* eps_p,
+                      const uint8_t* mask_generate, const int64_t* t, const float* z_pos,
+                      float* p_out, void* stream);
+/* AminoacidCategoricalTransition.denoise, transition.py:229-245: post (N,L,20), s_out (N,L) i64. */
+int abopt_seq_denoise(abopt_model* m, int N, int L, const int64_t* s_t, const float* c0_pred,
+                      const uint8_t* mask_generate, const int64_t* t, const float* expo_seq,
+                      float* post, int64_t* s_out, void* stream);
+
+/* ------------------------------------------------------------------ sampling loop
+ * FullDPM.sample (dpm_full.py:236-302) when opt_step == 0, FullDPM.optimize (:304-367) when
+ * opt_step > 0.  Trajectory outputs are indexed by step: slot k holds traj[k] of the reference,
+ * k = 0..T0 with T0 = num_steps (sample) or opt_step (optimize):
+ *   traj_v (T0+1,N,L,3)  traj_p (T0+1,N,L,3) in Angstrom  traj_s (T0+1,N,L) i64
+ *   traj_prmsd, traj_ppl (T0+1,N)  (has_prmsd models; may be NULL otherwise)
+ * Without ABOPT_KEEP_TRAJECTORY only slots 0 and T0 are guaranteed to be filled.
+ * Randomness: `noise` == NULL -> counter-based Philox4x32-10 keyed by `seed` inside the kernels
+ * ("fast" mode, distributionally identical to the reference).  Otherwise `noise` points to T0
+ * per-step records, noise[T0 - t] for step t, plus `init_noise` = the initialisation draws
+ * (sample: g4 (N,L,4), gp (N,L,3) floats and s_rand (N,L) i64; optimize: one abopt_step_noise)
+ * ("parity" mode: bit-identical consumption of the reference's draws).                        */
+typedef struct abopt_init_noise {
+  const float*   g4;      /* sample(): randn (N,L,4), so3.py:67                                */
+  const float*   gp;      /* sample(): randn_like(p), dpm_full.py:257                          */
+  const int64_t* s_rand;  /* sample(): randint_like(s, 0, 19), dpm_full.py:264                 */
+  const abopt_step_noise* add;   /* optimize(): draws of the three add_noise calls             */
+} abopt_init_noise;
+
+/* The two halves of the loop, for callers that drive it step by step (the parity mode of the
+ * Python FullDPM draws each step's noise with the reference's own ATen calls and hands it in):
+ *   abopt_sample_init  = dpm_full.py:254-269 (sample) / :321-339 (optimize): inputs -> traj[T0]
+ *   abopt_reverse_step = one iteration of dpm_full.py:274-300: traj[t] -> traj[t-1]
+ * p / p_t / p_out are in Angstrom, as stored in the reference's trajectory.  `noise` / `init_noise`
+ * may be NULL (Philox). prmsd_out / ppl_out (N,) may be NULL. */
+int abopt_sample_init(abopt_model* m, int N, int L, const float* v, const float* p, const int64_t* s,
+                      const uint8_t* mask_generate, uint32_t flags, int opt_step, uint64_t seed,
+                      const abopt_init_noise* init_noise, float* v_out, float* p_out, int64_t* s_out,
+                      void* stream);
+int abopt_reverse_step(abopt_model* m, int N, int L, int t, int optimize, const float* v_t,
+                       const float* p_t, const int64_t* s_t, const float* res_feat,
+                       const float* pair_feat, const uint8_t* mask_generate, const uint8_t* mask_res,
+                       uint32_t flags, uint64_t seed, const abopt_step_noise* noise, float* v_out,
+                       float* p_out, int64_t* s_out, float* prmsd_out, float* ppl_out, void* stream);
+
+int abopt_sample_device(abopt_model* m, int N, int L, const float* v, const float* p, const int64_t* s,
+                        const float* res_feat, const float* pair_feat, const uint8_t* mask_generate,
+                        const uint8_t* mask_res, uint32_t flags, int opt_step, uint64_t seed,
+                        const abopt_init_noise* init_noise, const abopt_step_noise* noise,
+                        float* traj_v, float* traj_p, int64_t* traj_s, float* traj_prmsd,
+                        float* traj_ppl, void* stream);
+
+/* Same, HOST buffers in and out: copies inputs to the device, runs the loop, copies the requested
+ * trajectory slots back, synchronises.  This is the call design_pdb.py / dock_pdb.py would make
+ * per batch; bench.py times it as the end-to-end number. */
+int abopt_sample_host(abopt_model* m, int N, int L, const float* v, const float* p, const int64_t* s,
+                      const float* res_feat, const float* pair_feat, const uint8_t* mask_generate,
+                      const uint8_t* mask_res, uint32_t flags, int opt_step, uint64_t seed,
+                      float* traj_v, float* traj_p, int64_t* traj_s, float* traj_prmsd,
+                      float* traj_ppl);
+
+/* Size in bytes of the device scratch the model holds for (N, L); 0 if none allocated yet. */
+size_t abopt_workspace_bytes(const abopt_model* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABOPT_B200_H_ */

@@ -1,0 +1,335 @@
+"""GPU parity tests: the sm_100a path (called through the C ABI via ab_opt_b200) against the CPU
+oracle and the committed reference fixtures.  Run on the B200 box:  pytest tests -m gpu
+
+Tolerances.  north_star asks for 1e-4 relative on coordinates and bit-exact sampled amino-acid
+indices.  fp32 evaluation order differs between implementations, and SURVEY.md section 8c shows
+the reference's own fp32 error against an fp64 run is a few 1e-4 on some outputs, so wherever it
+matters the arbiter is the oracle evaluated in fp64:
+    err(cuda, fp64) <= 2 * err(oracle_fp32, fp64) + floor
+Rotations are compared as matrices (the log map is ill-conditioned near pi by construction).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ab_opt_b200
+from oracle import weights, ipa, epsnet, sampler, transitions as T, geometry as G
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def load(golden_dir, name):
+    d = np.load(os.path.join(golden_dir, name))
+    return {k: torch.from_numpy(d[k]) if d[k].ndim else d[k].item() for k in d.files}
+
+
+def cu(d):
+    return {k: v.to(DEV) for k, v in d.items()}
+
+
+def to64(d):
+    return {k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in d.items()}
+
+
+def build_model(W, num_layers, flavour='abdock', obj='pred_x0', rng=None):
+    if flavour == 'abdock':
+        m = ab_opt_b200.FullDPM(128, 64, 100, eps_net_opt=dict(num_layers=num_layers), obj=obj, num_bins=40, rng=rng)
+    else:
+        m = ab_opt_b200.FullDPMAbDesign(128, 64, 100, eps_net_opt=dict(num_layers=num_layers), rng=rng)
+    m.load_state_dict(W, strict=True)
+    return m.to(DEV).eval()
+
+
+def assert_vs_fp64(name, got, ref32, ref64, floor, factor=2.0):
+    e_got = (got.double().cpu() - ref64).abs().max().item()
+    e_ref = (ref32.double() - ref64).abs().max().item()
+    assert e_got <= factor * e_ref + floor, f'{name}: cuda err {e_got:.3e} vs oracle-fp32 err {e_ref:.3e} (floor {floor:.1e})'
+
+
+@pytest.fixture(scope='module')
+def small():
+    W = weights.make_state_dict(seed=11, num_layers=2, flavour='abdock')
+    inp = weights.synthetic_inputs(21, 2, 24, gen_slices=((8, 14),), ragged=True)
+    return W, inp, build_model(W, 2)
+
+
+# ------------------------------------------------------------------------------------------ fixtures
+def test_block_against_reference_fixture(golden_dir, small):
+    """CUDA GABlock / GAEncoder vs outputs of the unmodified reference (tests/golden/ga_block.npz)."""
+    g = load(golden_dir, 'ga_block.npz')
+    W, inp, model = small
+    ci = cu(inp)
+    R = G.so3_exp(inp['v']).to(DEV)
+    t = ci['p'] / 10.0
+    enc = model.eps_net.encoder
+    alpha, feat = enc.block_taps(0, R, t, ci['res_feat'], ci['pair_feat'], ci['mask_res'])
+    torch.testing.assert_close(alpha.cpu(), g['alpha'], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(feat.cpu(), g['feat'], rtol=1e-4, atol=2e-5)
+    out = enc.blocks[0](R, t, ci['res_feat'], ci['pair_feat'], ci['mask_res'])
+    torch.testing.assert_close(out.cpu(), g['x_out'], rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(enc(R, t, ci['res_feat'], ci['pair_feat'], ci['mask_res']).cpu(), g['enc_out'],
+                               rtol=1e-4, atol=3e-5)
+
+
+def test_eps_net_against_reference_fixture(golden_dir, small):
+    g = load(golden_dir, 'eps_net_abdock.npz')
+    W, inp, model = small
+    ci = cu(inp)
+    beta = W['trans_pos.var_sched.betas'][g['t']].expand(g['N']).contiguous().to(DEV)
+    v_next, R_next, eps_pos, c_den, prm = model.eps_net(ci['v'], ci['p'] / 10.0, ci['s'], ci['res_feat'], ci['pair_feat'],
+                                                        beta, ci['mask_generate'], ci['mask_res'])
+    torch.testing.assert_close(R_next.cpu(), g['R_next'], rtol=0, atol=5e-6)
+    torch.testing.assert_close(eps_pos.cpu(), g['eps_pos'], rtol=1e-4, atol=2e-6)
+    torch.testing.assert_close(c_den.cpu(), g['c_denoised'], rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(prm.cpu(), g['prmsd_logits'], rtol=1e-4, atol=2e-6)
+    torch.testing.assert_close(G.so3_exp(v_next.cpu()), G.so3_exp(g['v_next']), rtol=0, atol=1e-5)
+    keep = ~inp['mask_generate']
+    assert torch.equal(v_next.cpu()[keep], inp['v'][keep])
+
+
+@pytest.mark.parametrize('tstep', [57, 3, 1])
+def test_transitions_against_reference_fixture(golden_dir, tstep):
+    """Replayed noise: positions to 1e-6, rotations as matrices, amino-acid indices BIT-EXACT."""
+    g = load(golden_dir, f'transitions_t{tstep}.npz')
+    W = weights.make_state_dict(seed=0, num_layers=1)
+    model = build_model(W, 1)
+    sm = weights.synthetic_inputs(g['seed_in'], g['N'], g['L'], gen_slices=((3, 9),))
+    N, L = g['N'], g['L']
+    mg = sm['mask_generate'].to(DEV)
+    tt = torch.full((N,), tstep, dtype=torch.long, device=DEV)
+    v_t, p_t, s_t = sm['v'].to(DEV), (sm['p'] / 10.0).to(DEV), sm['s'].to(DEV)
+    nz = {k[6:]: v.to(DEV) for k, v in g.items() if k.startswith('noise_')}
+    lib, C = ab_opt_b200._capi.lib(), ab_opt_b200._capi
+    nm = model.native()
+    st = C.stream_ptr(torch.device(DEV))
+    eps = torch.empty_like(p_t)
+    C.check(lib.abopt_pos_pred_noise_from_start(nm.handle, N, L, C.ptr(p_t), C.ptr(g['p_pred'].to(DEV)), C.ptr(mg), C.ptr(tt), C.ptr(eps), st))
+    torch.testing.assert_close(eps.cpu(), g['eps_p'], rtol=1e-6, atol=1e-6)
+    v_out = torch.empty_like(v_t)
+    C.check(lib.abopt_rot_denoise(nm.handle, N, L, C.ptr(v_t), C.ptr(g['v_net'].to(DEV)), C.ptr(mg), C.ptr(tt), C.ptr(nz['u']),
+                                  C.ptr(nz['expo_ang']), C.ptr(nz['unif_ang']), C.ptr(nz['gauss_ang']), C.ptr(v_out), st))
+    torch.testing.assert_close(G.so3_exp(v_out.cpu()), G.so3_exp(g['v_next']), rtol=0, atol=1e-5)
+    assert torch.equal(v_out.cpu()[~sm['mask_generate']], sm['v'][~sm['mask_generate']])
+    p_out = torch.empty_like(p_t)
+    C.check(lib.abopt_pos_denoise(nm.handle, N, L, C.ptr(p_t), C.ptr(g['eps_p'].to(DEV)), C.ptr(mg), C.ptr(tt), C.ptr(nz['z_pos']),
+                                  C.ptr(p_out), st))
+    torch.testing.assert_close(p_out.cpu(), g['p_next'], rtol=1e-6, atol=1e-6)
+    post = torch.empty(N, L, 20, device=DEV)
+    s_out = torch.empty_like(s_t)
+    C.check(lib.abopt_seq_denoise(nm.handle, N, L, C.ptr(s_t), C.ptr(g['c0'].to(DEV)), C.ptr(mg), C.ptr(tt), C.ptr(nz['expo_seq']),
+                                  C.ptr(post), C.ptr(s_out), st))
+    torch.testing.assert_close(post.cpu(), g['post'], rtol=1e-6, atol=1e-8)
+    assert torch.equal(s_out.cpu(), g['s_next'])
+
+
+# ------------------------------------------------------------------------------------------ oracle, more shapes
+@pytest.mark.parametrize('N,L,ragged', [(2, 24, True), (3, 100, True), (1, 300, False), (2, 64, False)])
+def test_block_vs_oracle_shapes(N, L, ragged):
+    """Tile-edge cases: L not a multiple of 64 / 4-row tiles, L > 256 (two keys per thread), ragged masks."""
+    W = weights.make_state_dict(seed=5, num_layers=1, flavour='abdesign')
+    model = build_model(W, 1, flavour='abdesign')
+    inp = weights.synthetic_inputs(100 + L, N, L, gen_slices=((2, 6),), ragged=ragged)
+    R, t = G.so3_exp(inp['v']), inp['p'] / 10.0
+    pre = 'eps_net.encoder.blocks.0.'
+    o32, parts = ipa.ga_block(W, pre, R, t, inp['res_feat'], inp['pair_feat'], inp['mask_res'], materialize=False, return_parts=True)
+    W64, i64 = weights.cast(W, torch.double), to64(inp)
+    o64, parts64 = ipa.ga_block(W64, pre, G.so3_exp(i64['v']), i64['p'] / 10.0, i64['res_feat'], i64['pair_feat'], i64['mask_res'],
+                                materialize=False, return_parts=True)
+    ci = cu(inp)
+    enc = model.eps_net.encoder
+    alpha, feat = enc.block_taps(0, R.to(DEV), t.to(DEV), ci['res_feat'], ci['pair_feat'], ci['mask_res'])
+    out = enc.blocks[0](R.to(DEV), t.to(DEV), ci['res_feat'], ci['pair_feat'], ci['mask_res'])
+    assert_vs_fp64('alpha', alpha, parts['alpha'], parts64['alpha'], 1e-6)
+    # masked query rows: the aggregate is ignored downstream (mask_zero) -> compare valid rows only
+    mr = inp['mask_res']
+    assert_vs_fp64('feat', feat.cpu()[mr], parts['feat'][mr], parts64['feat'][mr], 2e-5)
+    assert_vs_fp64('x_out', out, o32, o64, 2e-5)
+    torch.testing.assert_close(out.cpu(), o32, rtol=1e-4, atol=3e-5)
+    # attention rows of valid residues sum to one; masked rows / columns are exactly zero
+    a = alpha.cpu()
+    torch.testing.assert_close(a[mr].sum(1), torch.ones_like(a[mr].sum(1)), rtol=0, atol=1e-5)
+    if (~mr).any():
+        assert a[~mr].abs().max() == 0 and a.transpose(1, 2)[~mr].abs().max() == 0
+
+
+@pytest.mark.parametrize('flavour', ['abdock', 'abdesign'])
+def test_eps_net_vs_oracle(flavour):
+    W = weights.make_state_dict(seed=7, num_layers=3, flavour=flavour)
+    model = build_model(W, 3, flavour=flavour)
+    inp = weights.synthetic_inputs(31, 2, 72, gen_slices=((10, 20), (40, 44)), ragged=True)
+    beta = torch.tensor([W['trans_pos.var_sched.betas'][80], W['trans_pos.var_sched.betas'][3]])    # per-complex beta
+    o32 = epsnet.eps_net(W, inp['v'], inp['p'] / 10, inp['s'], inp['res_feat'], inp['pair_feat'], beta, inp['mask_generate'],
+                         inp['mask_res'], materialize=False)
+    i64 = to64(inp)
+    o64 = epsnet.eps_net(weights.cast(W, torch.double), i64['v'], i64['p'] / 10, i64['s'], i64['res_feat'], i64['pair_feat'],
+                         beta.double(), i64['mask_generate'], i64['mask_res'], materialize=False)
+    ci = cu(inp)
+    got = model.eps_net(ci['v'], ci['p'] / 10, ci['s'], ci['res_feat'], ci['pair_feat'], beta.to(DEV), ci['mask_generate'],
+                        ci['mask_res'])
+    assert len(got) == (5 if flavour == 'abdock' else 4)
+    for i, (nm_, floor) in enumerate((('v_next', None), ('R_next', 2e-6), ('eps_pos', 2e-6), ('c_denoised', 2e-7), ('prmsd', 2e-6))):
+        if i >= len(got) or floor is None:
+            continue
+        assert_vs_fp64(nm_, got[i], o32[i], o64[i], floor)
+    torch.testing.assert_close(G.so3_exp(got[0].cpu()), G.so3_exp(o32[0]), rtol=0, atol=2e-5)
+
+
+def test_reverse_step_teacher_forced(small):
+    """One full loop iteration per t with replayed noise, fed the ORACLE's state (teacher forcing):
+    positions 1e-4 relative, rotations as matrices, sequence indices bit-exact."""
+    W, inp, model = small
+    N, L = inp['mask_res'].shape
+    ci = cu(inp)
+    gen = torch.Generator().manual_seed(77)
+    v_t = G.uniform_so3_from_gauss4(torch.randn(N, L, 4, generator=gen))
+    v_t = torch.where(inp['mask_generate'][..., None], v_t, inp['v'])
+    p_t = torch.where(inp['mask_generate'][..., None], torch.randn(N, L, 3, generator=gen) * 10, inp['p'])
+    s_t = inp['s']
+    flips = 0
+    for t in (100, 64, 20, 2, 1):
+        nz = T.draw_step_noise(N, L, gen)
+        ref = sampler.reverse_step(W, t, v_t, (p_t - 0.0) / 10.0, s_t, inp['res_feat'], inp['pair_feat'], inp['mask_generate'],
+                                   inp['mask_res'], nz, obj='pred_x0', materialize=False)
+        got = model.reverse_step(t, v_t.to(DEV), p_t.to(DEV), s_t.to(DEV), ci['res_feat'], ci['pair_feat'], ci['mask_generate'],
+                                 ci['mask_res'], noise={k: v.to(DEV) for k, v in nz.items()})
+        v_o, p_o, s_o, prm, ppl = [x.cpu() for x in got]
+        torch.testing.assert_close(p_o, ref['p_next'] * 10.0, rtol=1e-4, atol=1e-4)           # Angstrom
+        torch.testing.assert_close(G.so3_exp(v_o), G.so3_exp(ref['v_next']), rtol=0, atol=2e-5)
+        flips += (s_o != ref['s_next']).sum().item()
+        torch.testing.assert_close(prm, ref['prmsd'], rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(ppl, epsnet.perplexity(ref['post'], inp['mask_generate']), rtol=1e-5, atol=1e-6)
+        keep = ~inp['mask_generate']
+        assert torch.equal(v_o[keep], v_t[keep]) and torch.equal(s_o[keep & inp['mask_res']], s_t[keep & inp['mask_res']])
+        v_t, p_t, s_t = ref['v_next'], ref['p_next'] * 10.0, ref['s_next']
+    assert flips == 0
+
+
+# ------------------------------------------------------------------------------------------ sampling loop
+def test_sample_parity_mode_matches_oracle_start(small):
+    """rng='torch': the Python mirror draws with the reference's ATen calls on the GPU; replaying the
+    same draws through the oracle must reproduce the trajectory start (then chaos, SURVEY finding 4)
+    and the full amino-acid trajectory of this seed."""
+    W, inp, model = small
+    N, L = inp['mask_res'].shape
+    ci = cu(inp)
+    torch.manual_seed(123)
+    traj = model.sample(ci['v'], ci['p'], ci['s'], ci['res_feat'], ci['pair_feat'], ci['mask_generate'], ci['mask_res'], rng='torch')
+    # regenerate the very same CUDA draws and replay them through the CPU oracle
+    torch.manual_seed(123)
+    tape = {'init': {'g4': torch.randn(N, L, 4, device=DEV).cpu(), 'gp': torch.randn(N, L, 3, device=DEV).cpu(),
+                     's_rand': torch.randint_like(ci['s'], low=0, high=19).cpu()}}
+    M = N * L
+    for t in range(100, 0, -1):
+        tape[t] = {'u': torch.randn(N, L, 3, device=DEV).cpu(), 'expo_ang': torch.empty(M, 8191, device=DEV).exponential_(1).cpu(),
+                   'unif_ang': torch.rand(M, device=DEV).cpu(), 'gauss_ang': torch.randn(M, device=DEV).cpu(),
+                   'z_pos': torch.randn(N, L, 3, device=DEV).cpu(), 'expo_seq': torch.empty(M, 20, device=DEV).exponential_(1).cpu()}
+    ref = sampler.sample(W, inp['v'], inp['p'], inp['s'], inp['res_feat'], inp['pair_feat'], inp['mask_generate'], inp['mask_res'],
+                         obj='pred_x0', tape=tape, materialize=False, stop_at=97)
+    assert sorted(traj.keys()) == list(range(101))
+    assert traj[0][0].is_cuda and not traj[5][0].is_cuda and isinstance(traj[5], list) and len(traj[5]) == 5
+    assert traj[100][3].shape == (N, L) and traj[100][3].dtype == torch.int64 and traj[100][4].min() == 1
+    for t in (100, 99, 98):
+        assert torch.equal(traj[t][2], ref[t][2])
+        torch.testing.assert_close(traj[t][1], ref[t][1], rtol=1e-4, atol=2e-3)
+    torch.testing.assert_close(G.so3_exp(traj[99][0]), G.so3_exp(ref[99][0]), rtol=0, atol=1e-4)
+    torch.testing.assert_close(traj[99][3], ref[99][3], rtol=1e-4, atol=1e-4)
+    keep = (~inp['mask_generate']) & inp['mask_res']
+    assert torch.equal(traj[0][2].cpu()[keep], inp['s'][keep])
+    torch.testing.assert_close(traj[0][1].cpu()[keep], inp['p'][keep], rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize('flavour', ['abdock', 'abdesign'])
+def test_sample_philox_mode_properties(flavour):
+    """Fast mode: deterministic for a seed, context untouched, outputs finite and in range; host-buffer
+    entry point (abopt_sample_host) agrees with the device one for the same seed."""
+    W = weights.make_state_dict(seed=2, num_layers=2, flavour=flavour)
+    model = build_model(W, 2, flavour=flavour, obj='pred_noise')
+    inp = weights.synthetic_inputs(9, 3, 40, gen_slices=((12, 22),), ragged=True)
+    ci = cu(inp)
+    args = (ci['v'], ci['p'], ci['s'], ci['res_feat'], ci['pair_feat'], ci['mask_generate'], ci['mask_res'])
+    torch.manual_seed(5); a = model.sample(*args)
+    torch.manual_seed(5); b = model.sample(*args)
+    torch.manual_seed(6); c = model.sample(*args)
+    n = 5 if flavour == 'abdock' else 3
+    assert all(len(a[t]) == n for t in a)
+    for k in range(3):
+        assert torch.equal(a[0][k], b[0][k]) and torch.equal(a[37][k], b[37][k])
+    assert not torch.equal(a[0][1], c[0][1])
+    gen, keep = inp['mask_generate'], (~inp['mask_generate']) & inp['mask_res']
+    v0, p0, s0 = [x.cpu() for x in a[0][:3]]
+    assert torch.isfinite(v0).all() and torch.isfinite(p0).all()
+    assert torch.equal(v0[~gen], inp['v'][~gen]) and torch.equal(s0[keep], inp['s'][keep])
+    torch.testing.assert_close(p0[~gen], inp['p'][~gen], rtol=1e-5, atol=1e-4)
+    assert (s0[gen] >= 0).all() and (s0[gen] < 20).all()
+    assert (a[100][2][gen] < 19).all()                                   # randint_like(s, 0, 19) never draws 19
+    assert (v0[gen] != inp['v'][gen]).any() and (p0[gen] != inp['p'][gen]).any()
+    if flavour == 'abdock':
+        assert torch.isfinite(a[0][3]).all() and ((a[0][4] > 0) & (a[0][4] <= 1)).all()
+    # structure-only and sequence-only runs leave the other modality alone
+    torch.manual_seed(5); d = model.sample(*args, sample_sequence=False)
+    assert torch.equal(d[0][2].cpu(), inp['s'])
+    torch.manual_seed(5); e = model.sample(*args, sample_structure=False)
+    assert torch.equal(e[0][0].cpu(), inp['v'])
+    # optimize(): starts from the noised input, 8 steps
+    torch.manual_seed(5); o = model.optimize(ci['v'], ci['p'], ci['s'], 8, *args[3:])
+    assert sorted(o.keys()) == list(range(9)) and isinstance(o[3], tuple)
+    assert torch.equal(o[0][0].cpu()[~gen], inp['v'][~gen])
+
+
+def test_sample_host_entry_point():
+    import ctypes
+    C = ab_opt_b200._capi
+    W = weights.make_state_dict(seed=2, num_layers=2, flavour='abdock')
+    model = build_model(W, 2, obj='pred_x0')
+    inp = weights.synthetic_inputs(9, 2, 40, gen_slices=((12, 22),), ragged=True)
+    ci = cu(inp)
+    N, L, T0 = 2, 40, 100
+    nm = model.native()
+    flags = C.SAMPLE_STRUCTURE | C.SAMPLE_SEQUENCE | C.KEEP_TRAJECTORY
+    tv, tp, ts = torch.empty(T0 + 1, N, L, 3), torch.empty(T0 + 1, N, L, 3), torch.empty(T0 + 1, N, L, dtype=torch.int64)
+    pr, pl = torch.empty(T0 + 1, N), torch.empty(T0 + 1, N)
+    host = {k: v.contiguous() for k, v in inp.items()}
+    C.check(C.lib().abopt_sample_host(nm.handle, N, L, C.ptr(host['v']), C.ptr(host['p']), C.ptr(host['s']), C.ptr(host['res_feat']),
+                                      C.ptr(host['pair_feat']), C.ptr(host['mask_generate']), C.ptr(host['mask_res']), flags, 0, 99,
+                                      C.ptr(tv), C.ptr(tp), C.ptr(ts), C.ptr(pr), C.ptr(pl)))
+    dv, dp, ds = torch.empty(T0 + 1, N, L, 3, device=DEV), torch.empty(T0 + 1, N, L, 3, device=DEV), torch.empty(T0 + 1, N, L, dtype=torch.int64, device=DEV)
+    dpr, dpl = torch.empty(T0 + 1, N, device=DEV), torch.empty(T0 + 1, N, device=DEV)
+    C.check(C.lib().abopt_sample_device(nm.handle, N, L, C.ptr(ci['v']), C.ptr(ci['p']), C.ptr(ci['s']), C.ptr(ci['res_feat']),
+                                        C.ptr(ci['pair_feat']), C.ptr(ci['mask_generate']), C.ptr(ci['mask_res']), flags, 0, 99, None, None,
+                                        C.ptr(dv), C.ptr(dp), C.ptr(ds), C.ptr(dpr), C.ptr(dpl), C.stream_ptr(torch.device(DEV))))
+    torch.cuda.synchronize()
+    assert torch.equal(tv, dv.cpu()) and torch.equal(tp, dp.cpu()) and torch.equal(ts, ds.cpu())
+    assert torch.equal(pr[:T0], dpr.cpu()[:T0]) and torch.equal(pl, dpl.cpu())
+    assert ab_opt_b200.launch_count() > 0
+
+
+def test_philox_angle_distribution_matches_histogram():
+    """Fast-mode inverse-CDF sampling draws from the same 8192-bin histogram the reference's multinomial uses:
+    compare the empirical rotation-angle distribution of one noising step with the table (chi-square-ish bound)."""
+    W = weights.make_state_dict(seed=0, num_layers=1)
+    model = build_model(W, 1, obj='pred_noise')
+    N, L, t = 8, 512, 60
+    inp = weights.synthetic_inputs(1, N, L, gen_slices=((0, L),))
+    ci = cu(inp)
+    zero_v = torch.zeros(N, L, 3, device=DEV)
+    # optimize()-style init with v = 0: the noised orientation is exp(e) itself, |log| = sampled angle
+    C = ab_opt_b200._capi
+    nm = model.native()
+    vo, po, so = torch.empty(N, L, 3, device=DEV), torch.empty(N, L, 3, device=DEV), torch.empty(N, L, dtype=torch.int64, device=DEV)
+    C.check(C.lib().abopt_sample_init(nm.handle, N, L, C.ptr(zero_v), C.ptr(ci['p']), C.ptr(ci['s']), C.ptr(ci['mask_generate']),
+                                      C.SAMPLE_STRUCTURE | C.SAMPLE_SEQUENCE, t, 1234, None, C.ptr(vo), C.ptr(po), C.ptr(so),
+                                      C.stream_ptr(torch.device(DEV))))
+    ang = vo.norm(dim=-1).flatten().cpu().double()
+    Y = W['trans_rot.angular_distrib_fwd.Y'][t, :-1].double()
+    X = W['trans_rot.angular_distrib_fwd.X'][t].double()
+    assert not W['trans_rot.angular_distrib_fwd.approx_flag'][t]
+    cdf = torch.cumsum(Y, 0) / Y.sum()
+    # empirical CDF at 64 probe angles vs table CDF: Kolmogorov-Smirnov distance small for 4096 samples
+    probes = torch.linspace(0.05, 3.1, 64, dtype=torch.double)
+    emp = (ang[None, :] <= probes[:, None]).double().mean(1)
+    idx = torch.searchsorted(X[1:].contiguous(), probes).clamp(max=len(cdf) - 1)
+    ks = (emp - cdf[idx]).abs().max().item()
+    assert ks < 0.04, ks
