@@ -21,7 +21,7 @@ EXPORTS = (
     'abopt_model_destroy', 'abopt_model_set_tensor', 'abopt_model_finalize', 'abopt_ga_block_forward',
     'abopt_ga_encoder_forward', 'abopt_ga_block_taps', 'abopt_eps_net_forward', 'abopt_rot_denoise',
     'abopt_pos_pred_noise_from_start', 'abopt_pos_denoise', 'abopt_seq_denoise', 'abopt_sample_device',
-    'abopt_sample_host', 'abopt_workspace_bytes', 'abopt_sample_init', 'abopt_reverse_step',
+    'abopt_sample_host', 'abopt_workspace_bytes', 'abopt_sample_init', 'abopt_reverse_step', 'abopt_profile_enable', 'abopt_profile_collect', 'abopt_debug_gemm3x',
 )
 
 
@@ -76,6 +76,7 @@ def lib():
                                                                    C.POINTER(InitNoise), C.POINTER(StepNoise)] + [vp] * 6
         L.abopt_sample_init.argtypes = [vp, ci, ci] + [vp] * 4 + [C.c_uint32, ci, C.c_uint64, C.POINTER(InitNoise)] + [vp] * 4
         L.abopt_reverse_step.argtypes = [vp, ci, ci, ci, ci] + [vp] * 7 + [C.c_uint32, C.c_uint64, C.POINTER(StepNoise)] + [vp] * 6
+        L.abopt_debug_gemm3x.argtypes = [ci, ci, ci, ci] + [vp] * 5
         L.abopt_sample_host.argtypes = [vp, ci, ci] + [vp] * 7 + [C.c_uint32, ci, C.c_uint64] + [vp] * 5
         _lib = L
     return _lib
@@ -84,6 +85,22 @@ def lib():
 def check(rc):
     if rc != OK:
         raise AboptError(f'libabopt_b200 error {rc}: {lib().abopt_last_error().decode()}')
+
+
+KERNEL_KINDS = ('mixer', 'proj', 'logits', 'pair', 'aggr', 'tail', 'heads', 'step', 'other')
+
+
+def profile_enable(on):
+    check(lib().abopt_profile_enable(int(bool(on))))
+
+
+def profile_collect():
+    """-> {kind: (total_ms, launches)} since profile_enable(True)."""
+    n = len(KERNEL_KINDS)
+    ms = (C.c_double * n)()
+    cnt = (C.c_uint64 * n)()
+    check(lib().abopt_profile_collect(ms, cnt, n))
+    return {k: (ms[i], int(cnt[i])) for i, k in enumerate(KERNEL_KINDS)}
 
 
 def launch_count():

@@ -13,6 +13,24 @@
 
 namespace abopt {
 unsigned long long g_launches = 0;
+// ---- optional profiler: one cudaEvent pair per launch, summed per kernel kind on collection
+static bool g_prof_on = false;
+struct ProfRec { int kind; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof;
+static cudaEvent_t g_prof_open = nullptr;
+void prof_begin(int kind, cudaStream_t st) {
+  if (!g_prof_on) return;
+  cudaEventCreate(&g_prof_open);
+  cudaEventRecord(g_prof_open, st);
+}
+void prof_end(int kind, cudaStream_t st) {
+  if (!g_prof_on || !g_prof_open) return;
+  cudaEvent_t b;
+  cudaEventCreate(&b);
+  cudaEventRecord(b, st);
+  g_prof.push_back({kind, g_prof_open, b});
+  g_prof_open = nullptr;
+}
 }
 using namespace abopt;
 
@@ -131,6 +149,44 @@ static void build_spec(abopt_model* m) {
 }
 
 extern "C" int abopt_version(void) { return 100; }
+// Test hook for the tcgen05 3xTF32 GEMM: D[M][N] = A[M][K] * B[N][K]^T (+ bias), all device pointers.
+extern "C" int abopt_debug_gemm3x(int device, int M, int N, int K, const float* A, const float* B, const float* bias, float* D, void* stream) {
+  if (M < 1 || N < 4 || N % 4 || K < 32 || K % 32) return fail(ABOPT_ERR_ARG, "need N % 4 == 0 and K % 32 == 0");
+  DeviceGuard g(device);
+  CUDA_TRY(tc_init());
+  cudaStream_t st = (cudaStream_t)stream;
+  float *Ah, *Al, *Bh, *Bl;
+  CUDA_TRY(cudaMalloc(&Ah, (size_t)M * K * 4)); CUDA_TRY(cudaMalloc(&Al, (size_t)M * K * 4));
+  CUDA_TRY(cudaMalloc(&Bh, (size_t)N * K * 4)); CUDA_TRY(cudaMalloc(&Bl, (size_t)N * K * 4));
+  launch_split(A, Ah, Al, (size_t)M * K, st);
+  launch_split(B, Bh, Bl, (size_t)N * K, st);
+  const bool ok = launch_gemm3x_plain(M, N, K, Ah, Al, K, Bh, Bl, K, D, N, bias, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(Ah); cudaFree(Al); cudaFree(Bh); cudaFree(Bl);
+  if (!ok) return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  if (e != cudaSuccess) return fail(ABOPT_ERR_CUDA, std::string("gemm3x: ") + cudaGetErrorString(e));
+  CHECK_LAUNCH();
+  return ABOPT_OK;
+}
+extern "C" int abopt_profile_enable(int on) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_prof_on = on != 0;
+  return ABOPT_OK;
+}
+extern "C" int abopt_profile_collect(double* ms_per_kind, uint64_t* launches_per_kind, int n_kinds) {
+  if (!ms_per_kind || !launches_per_kind || n_kinds < KK_COUNT) return fail(ABOPT_ERR_ARG, "need room for all kernel kinds");
+  for (int k = 0; k < n_kinds; ++k) { ms_per_kind[k] = 0.0; launches_per_kind[k] = 0; }
+  for (auto& r : g_prof) {
+    CUDA_TRY(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_per_kind[r.kind] += ms; launches_per_kind[r.kind] += 1;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  return ABOPT_OK;
+}
 extern "C" const char* abopt_last_error(void) { return g_err.c_str(); }
 extern "C" uint64_t abopt_kernel_launch_count(void) { return (uint64_t)g_launches; }
 
@@ -149,6 +205,7 @@ extern "C" int abopt_model_create(const abopt_config* cfg, int device, abopt_mod
   DeviceGuard g(device);
   CUDA_TRY(linear_kernels_init());
   CUDA_TRY(attn_kernels_init());
+  CUDA_TRY(tc_init());
   abopt_model* m = new abopt_model();
   m->cfg = *cfg;
   m->device = device;
@@ -341,11 +398,14 @@ extern "C" int abopt_model_finalize(abopt_model* m) {
 static int chunk_size(int N, int L, int Lp) {
   const char* env = getenv("ABOPT_CHUNK");
   if (env && atoi(env) > 0) return atoi(env) < N ? atoi(env) : N;
-  // logits + attention weights of a chunk should stay L2 resident (126 MB on B200): budget 48 MB
+  // logits + attention weights of a chunk should stay L2 resident (126 MB on B200): budget 56 MB,
+  // then balance the chunks (e.g. N=64, L=256: 8 chunks of 8 rather than 9 x 7 + 1)
   const double per = 2.0 * H * (double)L * Lp * 4.0;
-  int nb = (int)(48.0 * 1024 * 1024 / per);
+  int nb = (int)(56.0 * 1024 * 1024 / per);
   if (nb < 1) nb = 1;
-  return nb < N ? nb : N;
+  if (nb >= N) return N;
+  const int nch = (N + nb - 1) / nb;
+  return (N + nch - 1) / nch;
 }
 
 static int ensure_workspace(abopt_model* m, int N, int L) {

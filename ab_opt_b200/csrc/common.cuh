@@ -26,8 +26,16 @@ constexpr int FEAT_DIR = FEAT_DIST + H * P;        // 1536
 constexpr int NAA = 20;
 constexpr int NBINS = 8192;
 
-// launch bookkeeping (abopt_kernel_launch_count)
+// launch bookkeeping (abopt_kernel_launch_count) and the optional per-kernel event profiler
 extern unsigned long long g_launches;
+enum KernelKind { KK_MIXER = 0, KK_PROJ, KK_LOGITS, KK_PAIR, KK_AGGR, KK_TAIL, KK_HEADS, KK_STEP, KK_OTHER, KK_COUNT };
+void prof_begin(int kind, cudaStream_t st);     // no-ops unless abopt_profile_enable(1)
+void prof_end(int kind, cudaStream_t st);
+struct ProfScope {
+  int kind; cudaStream_t st;
+  ProfScope(int k, cudaStream_t s) : kind(k), st(s) { prof_begin(k, s); }
+  ~ProfScope() { prof_end(kind, st); g_launches += 1ull; }
+};
 inline void count_launch(int n = 1) { g_launches += (unsigned long long)n; }
 
 __device__ __forceinline__ float warp_sum(float v) {

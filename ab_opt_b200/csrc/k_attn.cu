@@ -29,10 +29,11 @@ logits_kernel(int L, int Lp, const float* __restrict__ proj, const float* __rest
   for (int f = tid; f < LG_T * (LG_K / 4); f += 256) {
     const int r = f / (LG_K / 4), q4 = f % (LG_K / 4);
     const int d = q4 * 4;
-    const int coff = (d < D) ? (h * D + d) : (OFF_QP - OFF_Q + h * P * 3 + (d - D));   // relative to OFF_Q / OFF_K
+    const int qoff = (d < D) ? (OFF_Q + h * D + d) : (OFF_QP + h * P * 3 + (d - D));
+    const int koff = (d < D) ? (OFF_K + h * D + d) : (OFF_KP + h * P * 3 + (d - D));
     float4 qv = make_float4(0.f, 0.f, 0.f, 0.f), kv = qv;
-    if (i0 + r < L) qv = *reinterpret_cast<const float4*>(proj + (size_t)(b * L + i0 + r) * NPROJ + OFF_Q + coff);
-    if (j0 + r < L) kv = *reinterpret_cast<const float4*>(proj + (size_t)(b * L + j0 + r) * NPROJ + OFF_K + coff);
+    if (i0 + r < L) qv = *reinterpret_cast<const float4*>(proj + (size_t)(b * L + i0 + r) * NPROJ + qoff);
+    if (j0 + r < L) kv = *reinterpret_cast<const float4*>(proj + (size_t)(b * L + j0 + r) * NPROJ + koff);
     Qs[d + 0][r] = qv.x; Qs[d + 1][r] = qv.y; Qs[d + 2][r] = qv.z; Qs[d + 3][r] = qv.w;
     Ks[d + 0][r] = kv.x; Ks[d + 1][r] = kv.y; Ks[d + 2][r] = kv.z; Ks[d + 3][r] = kv.w;
   }
@@ -372,37 +373,37 @@ cudaError_t attn_kernels_init() {
   const int mx = 200 * 1024;
   if ((e = cudaFuncSetAttribute(pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
 void launch_logits(int nb, int L, int Lp, const float* proj_chunk, const float* coef, float* S, cudaStream_t st) {
+  ProfScope prof__(KK_LOGITS, st);
   dim3 grid((L + LG_T - 1) / LG_T, (L + LG_T - 1) / LG_T, nb * H);
   logits_kernel<<<grid, 256, 0, st>>>(L, Lp, proj_chunk, coef, S);
-  count_launch();
 }
 
 void launch_pair(int nb, int b0, int L, int Lp, const float* z, const uint8_t* mask, const float* S,
                  const PairBiasParams& pb, float* alpha, float* feat, cudaStream_t st) {
+  ProfScope prof__(KK_PAIR, st);
   const size_t smem = pair_smem_bytes(L);
   const int grid = nb * L;
   if (L <= 256) pair_kernel<1><<<grid, PK_THREADS, smem, st>>>(L, Lp, b0, z, mask, S, pb, alpha, feat);
   else if (L <= 512) pair_kernel<2><<<grid, PK_THREADS, smem, st>>>(L, Lp, b0, z, mask, S, pb, alpha, feat);
   else pair_kernel<3><<<grid, PK_THREADS, smem, st>>>(L, Lp, b0, z, mask, S, pb, alpha, feat);
-  count_launch();
 }
 
 void launch_aggr(int nb, int b0, int L, int Lp, const float* alpha, const float* proj, const float* R, const float* t,
                  float* feat, cudaStream_t st) {
+  ProfScope prof__(KK_AGGR, st);
   dim3 grid((L + AG_TI - 1) / AG_TI, nb * H);
   aggr_kernel<<<grid, 256, 0, st>>>(L, Lp, b0, alpha, proj, R, t, feat);
-  count_launch();
 }
 
 void launch_alpha_tap(int nb, int b0, int L, int Lp, const float* alpha, float* out, cudaStream_t st) {
+  ProfScope prof__(KK_OTHER, st);
   dim3 grid(64, nb);
   alpha_to_reference_layout<<<grid, 256, 0, st>>>(L, Lp, b0, alpha, out);
-  count_launch();
 }
 
 }  // namespace abopt

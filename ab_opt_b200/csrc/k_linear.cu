@@ -393,25 +393,25 @@ cudaError_t linear_kernels_init() {
 void launch_mixer(int M, const float* res_feat, const long long* s_t, const float* v_t, const EpsW& w,
                   float* x_out, float* Rbuf, const float* p_ang, float* p_norm, const float* mean, float scale,
                   cudaStream_t st) {
+  ProfScope prof__(KK_MIXER, st);
   mixer_kernel<<<(M + RT_ROWS - 1) / RT_ROWS, RT_THREADS, mixer_smem(), st>>>(M, res_feat, s_t, v_t, w, x_out, Rbuf, p_ang, p_norm,
                                                                            mean[0], mean[1], mean[2], scale);
-  count_launch();
 }
 void launch_proj(int M, const float* x, const float* Wcat, const float* R, const float* t, float* proj, cudaStream_t st) {
+  ProfScope prof__(KK_PROJ, st);
   dim3 grid(NPROJ / PJ_BN, (M + PJ_BM - 1) / PJ_BM);
   proj_kernel<<<grid, PJ_THREADS, 0, st>>>(M, x, Wcat, R, t, proj);
-  count_launch();
 }
 void launch_tail(int M, const float* feat, const float* x, const uint8_t* mask, const BlockW& w, float* x_out, cudaStream_t st) {
+  ProfScope prof__(KK_TAIL, st);
   tail_kernel<<<(M + RT_ROWS - 1) / RT_ROWS, RT_THREADS, tail_smem(), st>>>(M, feat, x, mask, w, x_out);
-  count_launch();
 }
 void launch_heads(int M, int L, const float* x, const float* beta, int beta_stride, const float* Rbuf, const float* v_t,
                   const uint8_t* mask_gen, const EpsW& w, float* v_next, float* R_next, float* eps_pos, float* c_den,
                   float* prmsd_rows, float* prmsd_logits, cudaStream_t st) {
+  ProfScope prof__(KK_HEADS, st);
   heads_kernel<<<(M + RT_ROWS - 1) / RT_ROWS, RT_THREADS, heads_smem(), st>>>(M, L, x, beta, beta_stride, Rbuf, v_t, mask_gen, w,
                                                                            v_next, R_next, eps_pos, c_den, prmsd_rows);
-  count_launch();
   if (w.has_prmsd && prmsd_logits != nullptr) {
     prmsd_mean_kernel<<<M / L, 64, 0, st>>>(L, w.prmsd_bins, prmsd_rows, prmsd_logits);
     count_launch();

@@ -393,36 +393,36 @@ __global__ void seq_denoise_kernel(int M, int L, const long long* s_t, const flo
 // ---------------------------------------------------------------- launchers
 void launch_angle_argmax(int M, int L, const long long* tvec, int t_uniform, const float* Y, const float* expo,
                          const uint8_t* mask_gen, int* bin_idx, cudaStream_t st) {
+  ProfScope prof__(KK_OTHER, st);
   angle_argmax_kernel<<<M, 256, 0, st>>>(M, L, tvec, t_uniform, Y, expo, mask_gen, bin_idx);
-  count_launch();
 }
 void launch_step(const StepArgs& a, const DiffW& dw, cudaStream_t st) {
+  ProfScope prof__(KK_STEP, st);
   step_kernel<<<(a.M + 127) / 128, 128, 0, st>>>(a, dw);
-  count_launch();
 }
 void launch_complex_reduce(int N, int L, int bins, float dmin, float dmax, int masked_ppl, const float* prmsd_logits,
                            const float* maxprob_rows, const uint8_t* mask_gen, float* prmsd_out, float* ppl_out, cudaStream_t st) {
+  ProfScope prof__(KK_STEP, st);
   complex_reduce_kernel<<<N, 32, 0, st>>>(N, L, bins, dmin, dmax, masked_ppl, prmsd_logits, maxprob_rows, mask_gen, prmsd_out, ppl_out);
-  count_launch();
 }
 void launch_init(const InitArgs& a, const DiffW& dw, cudaStream_t st) {
+  ProfScope prof__(KK_OTHER, st);
   init_kernel<<<(a.M + 127) / 128, 128, 0, st>>>(a, dw);
-  count_launch();
 }
 void launch_rot_denoise(int M, int L, const float* v_t, const float* v_net, const uint8_t* mask_gen, const long long* tvec,
                         const NoisePtrs& nz, const DiffW& dw, float* v_out, cudaStream_t st) {
+  ProfScope prof__(KK_OTHER, st);
   rot_denoise_kernel<<<(M + 127) / 128, 128, 0, st>>>(M, L, v_t, v_net, mask_gen, tvec, nz, dw, v_out);
-  count_launch();
 }
 void launch_pos(int M, int L, int mode, const float* p_t, const float* other, const uint8_t* mask_gen, const long long* tvec,
                 const float* z_pos, const DiffW& dw, float* out, cudaStream_t st) {
+  ProfScope prof__(KK_OTHER, st);
   pos_kernel<<<(M + 127) / 128, 128, 0, st>>>(M, L, mode, p_t, other, mask_gen, tvec, z_pos, dw, out);
-  count_launch();
 }
 void launch_seq_denoise(int M, int L, const long long* s_t, const float* c0, const uint8_t* mask_gen, const long long* tvec,
                         const float* expo_seq, const DiffW& dw, float* post, long long* s_out, cudaStream_t st) {
+  ProfScope prof__(KK_OTHER, st);
   seq_denoise_kernel<<<(M + 127) / 128, 128, 0, st>>>(M, L, s_t, c0, mask_gen, tvec, expo_seq, dw, post, s_out);
-  count_launch();
 }
 
 }  // namespace abopt

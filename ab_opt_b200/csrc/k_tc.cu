@@ -1,0 +1,261 @@
+// tcgen05 "3xTF32" GEMM:  D[M][N] = A[M][K] * B[N][K]^T  with fp32-grade accuracy on the 5th-gen tensor cores.
+//
+// Both operands arrive pre-split into tf32-exact parts, x = hi + lo (tc::split_tf32), and every 128x BN x 32 k-block
+// issues the three products  A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  into one TMEM accumulator (the dropped lo*lo term is
+// ~2^-22 relative).  The reference runs these linears in true fp32 (allow_tf32 is off in its inference runners), and
+// plain TF32 (10-bit mantissa) would break the 1e-4 parity bar, hence the split.
+//
+// Structure (one CTA per 128 x BN output tile, 192 threads):
+//   warp 0      : TMA producer  -- cp.async.bulk.tensor, 128B-swizzled [rows][32 tf32] boxes, mbarrier expect_tx
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma.kind::tf32, commits to mbarriers)
+//   warps 2..5  : epilogue      -- tcgen05.ld (thread = output row), fused epilogue functor, global stores
+#include "tc.cuh"
+#include "params.cuh"
+#include "kernels.h"
+
+namespace abopt {
+
+using namespace tc;
+
+constexpr int G_BM = 128, G_BK = 32, G_THREADS = 192;
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = G_BM * G_BK * 4;       // 16 KB
+  static constexpr int B_BYTES = BN * G_BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;    // barriers (<= 11 x 8 B + slot) + slack for 1024 B alignment
+  static_assert(BN % 32 == 0, "epilogue reads TMEM in 32-column chunks");    // barriers + slack for 1024 B alignment
+};
+
+// ---- epilogues: called once per output row with the BN accumulators of that row in registers
+struct EpiPlain {            // D = acc (+ bias)
+  float* D; int ldd; const float* bias;
+  template <int BN>
+  __device__ __forceinline__ void operator()(int row, int n0, int N, float (&v)[BN]) const {
+    float* dst = D + (size_t)row * ldd + n0;
+#pragma unroll
+    for (int c = 0; c < BN; c += 4) {
+      if (n0 + c < N) {
+        float4 o = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        if (bias) { o.x += bias[n0 + c]; o.y += bias[n0 + c + 1]; o.z += bias[n0 + c + 2]; o.w += bias[n0 + c + 3]; }
+        *reinterpret_cast<float4*>(dst + c) = o;
+      }
+    }
+  }
+};
+
+// GABlock projections: q | k | v stored as is, point columns mapped local -> global (R p + t)   ga.py:96-105,129-132
+struct EpiProj {
+  float* proj; const float* R; const float* t;
+  template <int BN>
+  __device__ __forceinline__ void operator()(int row, int n0, int N, float (&v)[BN]) const {
+    static_assert(BN % 3 == 0, "point triples must not straddle tiles");
+    float* dst = proj + (size_t)row * NPROJ + n0;
+    if (n0 >= OFF_QP) {
+      float Rm[9], tv[3];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Rm[i] = __ldg(R + (size_t)row * 9 + i);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) tv[i] = __ldg(t + (size_t)row * 3 + i);
+#pragma unroll
+      for (int p = 0; p < BN; p += 3) {
+        const float x = v[p], y = v[p + 1], z = v[p + 2];
+        v[p + 0] = Rm[0] * x + Rm[1] * y + Rm[2] * z + tv[0];
+        v[p + 1] = Rm[3] * x + Rm[4] * y + Rm[5] * z + tv[1];
+        v[p + 2] = Rm[6] * x + Rm[7] * y + Rm[8] * z + tv[2];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < BN; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+  }
+};
+
+// Accuracy note (measured on B200, scripts/debug_gemm.py): the tensor core TRUNCATES the fp32 accumulator on every
+// tcgen05.mma, a systematic -2^-24 relative bias per accumulation that grows linearly with K (4e-5 at K = 1824).
+// Two counter-measures keep the result fp32-grade:
+//   (1) the large product A_hi*B_hi and the small corrections A_hi*B_lo + A_lo*B_hi go to SEPARATE TMEM accumulators
+//       (the corrections are 2^-11 smaller, so their truncation is irrelevant), summed in fp32 registers at the end;
+//   (2) "promotion": every KCH k-blocks the accumulators are drained into fp32 registers (round-to-nearest adds on the
+//       CUDA cores) while the MMAs continue into the other half of a double-buffered TMEM allocation.
+template <int BN, int STAGES, int KCH, class Epi>
+__global__ void __launch_bounds__(G_THREADS, 1)
+gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+              const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, int M, int N, int K, Epi epi) {
+  using S = GemmSmem<BN, STAGES>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;        // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * G_BM;
+  const int nkb = K / G_BK;
+  const int nchunk = (nkb + KCH - 1) / KCH;
+  constexpr uint32_t ACC_COLS = 2 * BN;                                  // main | small
+  constexpr uint32_t TMEM_COLS = (2 * ACC_COLS <= 256) ? 256 : 512;      // double buffered
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);                                  // slot free (first round passes immediately)
+        unsigned char* st = smem + s * S::STAGE_BYTES;
+        mbar_expect_tx(&full[s], S::STAGE_BYTES);
+        tma_load_2d(st, &tmAh, kb * G_BK, m0, &full[s]);
+        tma_load_2d(st + S::A_BYTES, &tmAl, kb * G_BK, m0, &full[s]);
+        tma_load_2d(st + 2 * S::A_BYTES, &tmBh, kb * G_BK, n0, &full[s]);
+        tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &tmBl, kb * G_BK, n0, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = idesc_tf32(G_BM, BN);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      const int c = kb / KCH, buf = c & 1;
+      const bool first = (kb % KCH) == 0, last = (kb % KCH) == KCH - 1 || kb == nkb - 1;
+      if (first && c >= 2) { mbar_wait(&tmem_empty[buf], ((c >> 1) - 1) & 1); }     // epilogue drained this buffer
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES), a_lo = a_hi + S::A_BYTES;
+        const uint32_t b_hi = a_hi + 2 * S::A_BYTES, b_lo = b_hi + S::B_BYTES;
+        const uint32_t d_main = tmem_base + buf * ACC_COLS, d_small = d_main + BN;
+#pragma unroll
+        for (int k = 0; k < G_BK / 8; ++k) {                           // UMMA_K = 8 tf32 = 32 B inside the 128 B swizzle row
+          const uint64_t dah = smem_desc_sw128(a_hi + k * 32), dal = smem_desc_sw128(a_lo + k * 32);
+          const uint64_t dbh = smem_desc_sw128(b_hi + k * 32), dbl = smem_desc_sw128(b_lo + k * 32);
+          const uint32_t acc = (first && k == 0) ? 0u : 1u;
+          mma_tf32(d_main, dah, dbh, idesc, acc);
+          mma_tf32(d_small, dah, dbl, idesc, acc);
+          mma_tf32(d_small, dal, dbh, idesc, 1u);
+        }
+        mma_commit(&empty[s]);                                         // smem slot reusable once these MMAs retire
+        if (last) mma_commit(&tmem_full[buf]);                         // this chunk's accumulators are complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                                            // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    float v[BN];
+#pragma unroll
+    for (int i = 0; i < BN; ++i) v[i] = 0.f;
+    for (int c = 0; c < nchunk; ++c) {
+      const int buf = c & 1;
+      mbar_wait(&tmem_full[buf], (c >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS;
+#pragma unroll
+      for (int cc = 0; cc < BN; cc += 32) {
+        float tm[32], ts[32];
+        tmem_ld_32x32(tbase + cc, tm);
+        tmem_ld_32x32(tbase + BN + cc, ts);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[cc + i] += tm[i] + ts[i];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+    if (row < M) epi.template operator()<BN>(row, n0, N, v);
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+cudaError_t tc_init() {
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess) return e;
+    if (qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+    g_encode = (PFN_encodeTiled)fn;
+  }
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(gemm3x_kernel<128, 3, 8, EpiPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<128, 3>::TOTAL)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(gemm3x_kernel<96, 3, 8, EpiProj>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<96, 3>::TOTAL)) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
+// 2-D fp32 row-major [rows][cols] with row pitch ld (floats); box = [box_rows][32 floats], 128 B swizzle
+bool make_tmap(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {G_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+__global__ void split_kernel(const float* __restrict__ in, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float h, l;
+    split_tf32(in[i], h, l);
+    hi[i] = h; lo[i] = l;
+  }
+}
+void launch_split(const float* in, float* hi, float* lo, size_t n, cudaStream_t st) {
+  ProfScope prof__(KK_OTHER, st);
+  int grid = (int)((n + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  split_kernel<<<grid, 256, 0, st>>>(in, hi, lo, n);
+}
+
+// D[M][N] = A * B^T (+bias), operands given as hi / lo planes.  K % 32 == 0, N % 4 == 0.
+bool launch_gemm3x_plain(int M, int N, int K, const float* Ah, const float* Al, int lda, const float* Bh, const float* Bl, int ldb,
+                         float* D, int ldd, const float* bias, cudaStream_t st) {
+  CUtensorMap a_h, a_l, b_h, b_l;
+  if (!make_tmap(&a_h, Ah, M, K, lda, G_BM) || !make_tmap(&a_l, Al, M, K, lda, G_BM) || !make_tmap(&b_h, Bh, N, K, ldb, 128) ||
+      !make_tmap(&b_l, Bl, N, K, ldb, 128))
+    return false;
+  ProfScope prof__(KK_TAIL, st);
+  dim3 grid((N + 127) / 128, (M + G_BM - 1) / G_BM);
+  gemm3x_kernel<128, 3, 8, EpiPlain><<<grid, G_THREADS, GemmSmem<128, 3>::TOTAL, st>>>(a_h, a_l, b_h, b_l, M, N, K, EpiPlain{D, ldd, bias});
+  return true;
+}
+
+// the six GABlock projections + local->global points: proj[M][2016] = x * Wcat^T
+bool launch_proj_tc(int M, const float* xh, const float* xl, const float* Wh, const float* Wl, const float* R, const float* t,
+                    float* proj, cudaStream_t st) {
+  CUtensorMap a_h, a_l, b_h, b_l;
+  if (!make_tmap(&a_h, xh, M, F, F, G_BM) || !make_tmap(&a_l, xl, M, F, F, G_BM) || !make_tmap(&b_h, Wh, NPROJ, F, F, 96) ||
+      !make_tmap(&b_l, Wl, NPROJ, F, F, 96))
+    return false;
+  ProfScope prof__(KK_PROJ, st);
+  dim3 grid(NPROJ / 96, (M + G_BM - 1) / G_BM);
+  gemm3x_kernel<96, 3, 8, EpiProj><<<grid, G_THREADS, GemmSmem<96, 3>::TOTAL, st>>>(a_h, a_l, b_h, b_l, M, NPROJ, F, EpiProj{proj, R, t});
+  return true;
+}
+
+}  // namespace abopt

@@ -33,6 +33,12 @@ struct InitArgs {
 
 cudaError_t linear_kernels_init();
 cudaError_t attn_kernels_init();
+cudaError_t tc_init();
+void launch_split(const float* in, float* hi, float* lo, size_t n, cudaStream_t st);
+bool launch_gemm3x_plain(int M, int N, int K, const float* Ah, const float* Al, int lda, const float* Bh, const float* Bl, int ldb,
+                         float* D, int ldd, const float* bias, cudaStream_t st);
+bool launch_proj_tc(int M, const float* xh, const float* xl, const float* Wh, const float* Wl, const float* R, const float* t,
+                    float* proj, cudaStream_t st);
 
 void launch_mixer(int M, const float* res_feat, const long long* s_t, const float* v_t, const EpsW& w,
                   float* x_out, float* Rbuf, const float* p_ang, float* p_norm, const float* mean, float scale,

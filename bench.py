@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the reverse-diffusion sampling hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c4]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one complete FullDPM.sample() (T=100 reverse steps) over one synthetic batch per GPU.
+Metric: sampled CDR residues / s = (#GPUs x B x n_gen x K) / time, whole job.
+  ours      : ab_opt_b200.FullDPM.sample -> libabopt_b200 (sm_100a kernels), inputs resident in HBM (`value`);
+              `e2e` = the C-ABI host entry point abopt_sample_host with pinned HOST buffers, H2D + D2H inside
+              the timed region.
+  reference : the reference's CPU path (oracle port, evaluation order of the reference: broadcast-multiply-sum
+              with full temporaries) on the host cores, on a bounded sample of the same workload.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # SURVEY.md section 8d.  c2 is the configuration BASELINE.json's metric is quoted on.
+    'c2': dict(name='C2 AbDesign CDR-H3 co-design', B=64, L=256, gen=((120, 136),), flavour='abdesign',
+               sample_structure=True, sample_sequence=True, obj='pred_noise'),
+    'c3': dict(name='C3 AbDock pose diffusion', B=64, L=256, gen=((120, 136),), flavour='abdock',
+               sample_structure=True, sample_sequence=False, obj='pred_x0'),
+    'c4': dict(name='C4 AbDesign all-6-CDR co-design (per-GPU shard of B=256)', B=32, L=320,
+               gen=((20, 30), (50, 60), (95, 105), (160, 170), (190, 200), (230, 240)), flavour='abdesign',
+               sample_structure=True, sample_sequence=True, obj='pred_noise'),
+}
+NUM_LAYERS, T_STEPS = 6, 100
+
+
+def algorithmic_bytes_per_complex_layer(L):
+    """stream z once per layer + node state (x in/out, R, t, mask)."""
+    return L * L * 64 * 4 + L * (2 * 128 * 4 + 36 + 12 + 1)
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        return float(json.load(open(path))['hbm_gbs']), 'MEASURED_PEAKS.json'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def synthetic_batch(cfg, seed, device, B=None):
+    """Seeded synthetic inputs of SURVEY.md 8d on `device`."""
+    B = B or cfg['B']
+    L = cfg['L']
+    g = torch.Generator(device=device).manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=g, device=device)
+    q = torch.nn.functional.normalize(rn(B, L, 4), dim=-1)            # uniform rotations -> so(3) vectors
+    ang = 2 * torch.acos(q[..., :1].clamp(-1, 1))
+    ang = torch.where(ang > torch.pi, ang - 2 * torch.pi, ang)
+    v = torch.nn.functional.normalize(q[..., 1:], dim=-1) * ang
+    mask_generate = torch.zeros(B, L, dtype=torch.bool, device=device)
+    for a, b in cfg['gen']:
+        mask_generate[:, a:b] = True
+    return dict(v=v.contiguous(), p=rn(B, L, 3) * 10.0, s=torch.randint(0, 20, (B, L), generator=g, device=device),
+                res_feat=rn(B, L, 128), pair_feat=rn(B, L, L, 64), mask_generate=mask_generate,
+                mask_res=torch.ones(B, L, dtype=torch.bool, device=device))
+
+
+def build_model(cfg, device):
+    import ab_opt_b200
+    torch.manual_seed(1234)
+    if cfg['flavour'] == 'abdock':
+        m = ab_opt_b200.FullDPM(128, 64, T_STEPS, eps_net_opt=dict(num_layers=NUM_LAYERS), obj=cfg['obj'], num_bins=40)
+        for lin in (m.eps_net.prmsd_predictor.linear_1, m.eps_net.prmsd_predictor.linear_2, m.eps_net.prmsd_predictor.linear_3):
+            torch.nn.init.normal_(lin.weight, std=0.05)
+    else:
+        m = ab_opt_b200.FullDPMAbDesign(128, 64, T_STEPS, eps_net_opt=dict(num_layers=NUM_LAYERS))
+    return m.to(device).eval()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200',
+                                          '-i', str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 6 or not f[0].isdigit():
+                continue
+            sm.append(int(f[0])); mx.append(int(f[1]))
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[2:6]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        busy = [x for x in sm if x > 0.5 * max(sm)] if sm else []
+        return {'sm_mhz': statistics.median(busy) if busy else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm (CPU)
+def cpu_reference_run(cfg, steps, warmup, n_reverse_steps=2, B_cpu=1):
+    """Times the oracle port of the reference's CPU path: `n_reverse_steps` reverse steps of a B_cpu-complex batch at
+    the config's L / n_gen per bench step, extrapolated linearly in B and T (BASELINE.md section 2 shows linearity)."""
+    from oracle import weights as ow, sampler as osamp, transitions as OT
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    W = ow.make_state_dict(seed=1234, num_layers=NUM_LAYERS, flavour=cfg['flavour'])
+    inp = synthetic_batch(cfg, 1234, 'cpu', B=B_cpu)
+    n_gen = int(inp['mask_generate'][0].sum())
+    gen = torch.Generator().manual_seed(0)
+    L = cfg['L']
+
+    def one():
+        v, p, s = inp['v'], inp['p'] / 10.0, inp['s']
+        for k in range(n_reverse_steps):
+            nz = OT.draw_step_noise(B_cpu, L, gen)
+            st = osamp.reverse_step(W, T_STEPS - k, v, p, s, inp['res_feat'], inp['pair_feat'], inp['mask_generate'],
+                                    inp['mask_res'], nz, obj=cfg['obj'], materialize=True)
+            v, p, s = st['v_next'], st['p_next'], st['s_next']
+    with torch.no_grad():
+        for _ in range(warmup):
+            one()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one()
+        dt = (time.perf_counter() - t0) / steps
+    sec_per_reverse_step_per_complex = dt / (n_reverse_steps * B_cpu)
+    value = n_gen / (sec_per_reverse_step_per_complex * T_STEPS)          # residues/s for a full T=100 sample
+    sample = (f'{n_reverse_steps} reverse steps x B={B_cpu} complexes at L={L}, n_gen={n_gen}, {NUM_LAYERS} IPA layers, fp32, '
+              f'{cores} threads; {dt:.2f} s per sample; scaled linearly to T={T_STEPS}')
+    return value, dt, cores, sample, n_gen
+
+
+def run_reference(args, cfg, rank):
+    if rank != 0:
+        return
+    value, dt, cores, sample, n_gen = cpu_reference_run(cfg, args.steps, args.warmup)
+    line = {
+        'impl': 'reference', 'metric': 'sampled CDR residues/sec', 'value': value, 'unit': 'residues/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(cfg), 'B': cfg['B'], 'L': cfg['L'], 'n_gen': n_gen, 'T': T_STEPS, 'layers': NUM_LAYERS},
+        'cpu_baseline': {'value': value, 'unit': 'residues/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'residues/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(cfg):
+    return (f"{cfg['name']}: FullDPM.sample, B={cfg['B']} complexes/GPU, L={cfg['L']}, n_gen={sum(b - a for a, b in cfg['gen'])}, "
+            f"{NUM_LAYERS} IPA layers, T={T_STEPS}")
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args, cfg, rank, world, local_rank):
+    import torch.distributed as dist
+    import ab_opt_b200
+    from ab_opt_b200 import _capi
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    model = build_model(cfg, dev)
+    inp = synthetic_batch(cfg, 1000 + rank, dev)          # each rank owns its own complexes (weak scaling, no exchange)
+    B, L = cfg['B'], cfg['L']
+    n_gen = int(inp['mask_generate'][0].sum())
+    a = (inp['v'], inp['p'], inp['s'], inp['res_feat'], inp['pair_feat'], inp['mask_generate'], inp['mask_res'])
+    kw = dict(sample_structure=cfg['sample_structure'], sample_sequence=cfg['sample_sequence'])
+    gathered = None
+
+    def step():
+        nonlocal gathered
+        traj = model.sample(*a, **kw)
+        if world > 1:     # the one collective of the path: gather the finished structures
+            fin = torch.cat([traj[0][0], traj[0][1], traj[0][2].float()[..., None]], -1).contiguous()
+            gathered = torch.empty(world * B, L, 7, device=dev)
+            dist.all_gather_into_tensor(gathered, fin)
+        return traj
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    torch.manual_seed(rank)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    l0 = ab_opt_b200.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        traj = step()
+    e1.record()
+    barrier()
+    launches = ab_opt_b200.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if clocks else None
+    if world > 1:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    ms_per_step = ms / args.steps
+    value = world * B * n_gen / (ms_per_step / 1e3)
+    assert torch.isfinite(traj[0][1]).all()
+
+    # ---- end to end through the C ABI with HOST buffers (pinned), H2D + D2H inside the timed region
+    nm = model.native()
+    host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in inp.items()}
+    T0 = T_STEPS
+    abdock = cfg['flavour'] == 'abdock'
+    otv = torch.empty(T0 + 1, B, L, 3, pin_memory=True); otp = torch.empty(T0 + 1, B, L, 3, pin_memory=True)
+    ots = torch.empty(T0 + 1, B, L, dtype=torch.int64, pin_memory=True)
+    opr = torch.empty(T0 + 1, B, pin_memory=True) if abdock else None
+    opl = torch.empty(T0 + 1, B, pin_memory=True) if abdock else None
+    flags = (_capi.SAMPLE_STRUCTURE if cfg['sample_structure'] else 0) | (_capi.SAMPLE_SEQUENCE if cfg['sample_sequence'] else 0)
+
+    def e2e_step(seed):
+        _capi.check(_capi.lib().abopt_sample_host(nm.handle, B, L, _capi.ptr(host['v']), _capi.ptr(host['p']), _capi.ptr(host['s']),
+                                                  _capi.ptr(host['res_feat']), _capi.ptr(host['pair_feat']), _capi.ptr(host['mask_generate']),
+                                                  _capi.ptr(host['mask_res']), flags, 0, seed, _capi.ptr(otv), _capi.ptr(otp), _capi.ptr(ots),
+                                                  _capi.ptr(opr), _capi.ptr(opl)))
+    e2e_step(1)
+    barrier()
+    n_e2e = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for i in range(n_e2e):
+        e2e_step(2 + i)
+    dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * n_gen / float(dt.item())
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = 2 * (B * L * 3 * 4 * 2 + B * L * 8) + (4 * B * 4 if abdock else 0)       # slots 0 and T0 of v, p, s (+ prmsd, ppl)
+
+    # ---- per-kernel timing pass (CUDA events around every launch, outside the timed region) -> roofline
+    roof, breakdown = None, None
+    if rank == 0:
+        _capi.profile_enable(True)
+        torch.manual_seed(0)
+        model.sample(*a, **kw)
+        torch.cuda.synchronize()
+        prof = _capi.profile_collect()
+        _capi.profile_enable(False)
+        pair_ms, pair_n = prof['pair']
+        total_ms = sum(v[0] for v in prof.values())
+        peak, peak_src = measured_peak_gbs()
+        per_launch_complexes = B * NUM_LAYERS * T_STEPS / max(pair_n, 1)
+        alg_bytes = per_launch_complexes * algorithmic_bytes_per_complex_layer(L)
+        achieved = alg_bytes / (pair_ms / pair_n * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'pair_kernel_traffic.json')
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get('L') == L:
+                traffic = tj['dram_bytes_per_complex'] * per_launch_complexes
+        roof = {'bound': 'hbm', 'kernel': 'pair_kernel (streams pair_feat once per layer)', 'achieved': achieved, 'peak': peak,
+                'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': alg_bytes, 'avg_launch_ms': pair_ms / pair_n, 'launches_per_sample': pair_n,
+                'share_of_gpu_time': pair_ms / total_ms,
+                'whole_step_achieved': B * NUM_LAYERS * T_STEPS * algorithmic_bytes_per_complex_layer(L) / (ms_per_step * 1e-3) / 1e9,
+                'whole_step_frac': B * NUM_LAYERS * T_STEPS * algorithmic_bytes_per_complex_layer(L) / (ms_per_step * 1e-3) / 1e9 / peak}
+        breakdown = {k: {'ms': round(v[0], 3), 'launches': v[1]} for k, v in prof.items() if v[1]}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cv, cdt, cores, sample, _ = cpu_reference_run(cfg, steps=2, warmup=1)
+            cpu = {'value': cv, 'unit': 'residues/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+        line = {
+            'metric': 'sampled CDR residues/sec', 'value': value, 'unit': 'residues/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload_name(cfg), 'B_per_gpu': B, 'L': L, 'n_gen': n_gen, 'T': T_STEPS, 'layers': NUM_LAYERS,
+                       'flavour': cfg['flavour'], 'rng': 'philox (in-kernel)', 'weights': 'seeded random init',
+                       'l2': 'inputs larger than L2 (pair_feat %.2f GB per GPU)' % (B * L * L * 64 * 4 / 1e9),
+                       'value_includes': 'init noise, 100 reverse steps, trajectory D2H, final gather (N>1)',
+                       'e2e_result': 'traj[0] and traj[T] (v, p, s) read back; full trajectory not copied'},
+            'clocks': clk,
+            'e2e': {'value': e2e_value, 'unit': 'residues/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': float(dt.item()) * 1e3},
+            'gpu_launches': int(launches),
+            'roofline': roof, 'cpu_baseline': cpu, 'kernel_breakdown_ms_per_sample': breakdown,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, cfg, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl ours needs a CUDA device (there is no CPU fallback)')
+    if world != args.gpus:
+        raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}')
+    run_ours(args, cfg, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

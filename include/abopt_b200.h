@@ -93,6 +93,20 @@ const char* abopt_last_error(void);
 /* Number of kernels this library has launched in the calling process (all models). */
 uint64_t    abopt_kernel_launch_count(void);
 
+/* Optional per-kernel timing (bench.py's roofline line): while enabled, every kernel launch of this
+ * library is bracketed by a CUDA event pair on its stream.  abopt_profile_collect() synchronises,
+ * sums milliseconds and launch counts per kernel kind and clears the records.  Kinds, in order:
+ * 0 mixer, 1 projections, 2 logits, 3 pair stream, 4 aggregation, 5 block tail, 6 heads,
+ * 7 transition step, 8 other.  Not for use inside timed regions (events perturb the pipeline). */
+#define ABOPT_KERNEL_KINDS 9
+int abopt_profile_enable(int on);
+int abopt_profile_collect(double* ms_per_kind, uint64_t* launches_per_kind, int n_kinds);
+
+/* Test hook for the tcgen05 "3xTF32" GEMM building block used by the linear layers:
+ * D[M][N] = A[M][K] * B[N][K]^T (+ bias[N]); device pointers; N % 4 == 0, K % 32 == 0.  Synchronises. */
+int abopt_debug_gemm3x(int device, int M, int N, int K, const float* A, const float* B, const float* bias,
+                       float* D, void* stream);
+
 /* FullDPM.__init__ : allocate an empty model on CUDA device `device`. */
 int  abopt_model_create(const abopt_config* cfg, int device, abopt_model** out);
 void abopt_model_destroy(abopt_model* m);

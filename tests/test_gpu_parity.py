@@ -49,6 +49,20 @@ def assert_vs_fp64(name, got, ref32, ref64, floor, factor=2.0):
     assert e_got <= factor * e_ref + floor, f'{name}: cuda err {e_got:.3e} vs oracle-fp32 err {e_ref:.3e} (floor {floor:.1e})'
 
 
+def assert_rot_close(name, v_got, v_ref, base=2e-5, c=3e-6, skip=0.05):
+    """Compare so(3) vectors as rotation matrices with the conditioning of the reference's log map taken into
+    account (so3.py:10-22: sin = sqrt(1 - cos^2), coef = theta / 2 sin -> error ~ eps / (pi - theta)^2, SURVEY
+    finding 4 / section 8c-iii): tolerance base + c / (pi - theta)^2, residues within `skip` rad of pi excluded."""
+    v_got, v_ref = v_got.detach().cpu().double(), v_ref.detach().cpu().double()
+    gap = (np.pi - v_ref.norm(dim=-1)).clamp_min(1e-9)
+    ok = gap > skip
+    err = (G.so3_exp(v_got) - G.so3_exp(v_ref)).abs().amax(dim=(-1, -2))
+    tol = base + c / gap ** 2
+    bad = ok & (err > tol)
+    assert not bad.any(), f'{name}: {int(bad.sum())} residues off, worst err {err[bad].max().item():.3e} at gap {gap[bad][err[bad].argmax()].item():.3f}'
+    assert ok.float().mean() > 0.5
+
+
 @pytest.fixture(scope='module')
 def small():
     W = weights.make_state_dict(seed=11, num_layers=2, flavour='abdock')
@@ -85,7 +99,7 @@ def test_eps_net_against_reference_fixture(golden_dir, small):
     torch.testing.assert_close(eps_pos.cpu(), g['eps_pos'], rtol=1e-4, atol=2e-6)
     torch.testing.assert_close(c_den.cpu(), g['c_denoised'], rtol=1e-4, atol=1e-7)
     torch.testing.assert_close(prm.cpu(), g['prmsd_logits'], rtol=1e-4, atol=2e-6)
-    torch.testing.assert_close(G.so3_exp(v_next.cpu()), G.so3_exp(g['v_next']), rtol=0, atol=1e-5)
+    assert_rot_close('v_next', v_next, g['v_next'])
     keep = ~inp['mask_generate']
     assert torch.equal(v_next.cpu()[keep], inp['v'][keep])
 
@@ -111,7 +125,7 @@ def test_transitions_against_reference_fixture(golden_dir, tstep):
     v_out = torch.empty_like(v_t)
     C.check(lib.abopt_rot_denoise(nm.handle, N, L, C.ptr(v_t), C.ptr(g['v_net'].to(DEV)), C.ptr(mg), C.ptr(tt), C.ptr(nz['u']),
                                   C.ptr(nz['expo_ang']), C.ptr(nz['unif_ang']), C.ptr(nz['gauss_ang']), C.ptr(v_out), st))
-    torch.testing.assert_close(G.so3_exp(v_out.cpu()), G.so3_exp(g['v_next']), rtol=0, atol=1e-5)
+    assert_rot_close('v_out', v_out, g['v_next'])
     assert torch.equal(v_out.cpu()[~sm['mask_generate']], sm['v'][~sm['mask_generate']])
     p_out = torch.empty_like(p_t)
     C.check(lib.abopt_pos_denoise(nm.handle, N, L, C.ptr(p_t), C.ptr(g['eps_p'].to(DEV)), C.ptr(mg), C.ptr(tt), C.ptr(nz['z_pos']),
@@ -174,7 +188,7 @@ def test_eps_net_vs_oracle(flavour):
         if i >= len(got) or floor is None:
             continue
         assert_vs_fp64(nm_, got[i], o32[i], o64[i], floor)
-    torch.testing.assert_close(G.so3_exp(got[0].cpu()), G.so3_exp(o32[0]), rtol=0, atol=2e-5)
+    assert_rot_close('v_next', got[0], o64[0])
 
 
 def test_reverse_step_teacher_forced(small):
@@ -197,7 +211,7 @@ def test_reverse_step_teacher_forced(small):
                                  ci['mask_res'], noise={k: v.to(DEV) for k, v in nz.items()})
         v_o, p_o, s_o, prm, ppl = [x.cpu() for x in got]
         torch.testing.assert_close(p_o, ref['p_next'] * 10.0, rtol=1e-4, atol=1e-4)           # Angstrom
-        torch.testing.assert_close(G.so3_exp(v_o), G.so3_exp(ref['v_next']), rtol=0, atol=2e-5)
+        assert_rot_close(f'v_next t={t}', v_o, ref['v_next'])
         flips += (s_o != ref['s_next']).sum().item()
         torch.testing.assert_close(prm, ref['prmsd'], rtol=1e-4, atol=1e-4)
         torch.testing.assert_close(ppl, epsnet.perplexity(ref['post'], inp['mask_generate']), rtol=1e-5, atol=1e-6)
@@ -234,7 +248,7 @@ def test_sample_parity_mode_matches_oracle_start(small):
     for t in (100, 99, 98):
         assert torch.equal(traj[t][2], ref[t][2])
         torch.testing.assert_close(traj[t][1], ref[t][1], rtol=1e-4, atol=2e-3)
-    torch.testing.assert_close(G.so3_exp(traj[99][0]), G.so3_exp(ref[99][0]), rtol=0, atol=1e-4)
+    assert_rot_close('v_99', traj[99][0], ref[99][0], base=1e-4)
     torch.testing.assert_close(traj[99][3], ref[99][3], rtol=1e-4, atol=1e-4)
     keep = (~inp['mask_generate']) & inp['mask_res']
     assert torch.equal(traj[0][2].cpu()[keep], inp['s'][keep])
