@@ -84,6 +84,12 @@ struct abopt_model {
   void* wbase = nullptr; size_t wbytes = 0;
   std::vector<BlockW> blocks;
   std::vector<PairBiasParams> pb;
+  std::vector<PairBiasPacked> pbp;
+  // TMA descriptor of the pair tensor, cached per (pointer, shape): pair_feat is constant over a sampling run
+  CUtensorMap zmap; const float* zmap_ptr = nullptr; int zmap_N = 0, zmap_L = 0, zmap_box_rows = 0;
+  // pair bias z . W_b of every layer, [slot][N][H][L][Lp].  Inside abopt_sample_* it is computed once per run for all
+  // layers (z and the weights are loop invariants of the T reverse steps); elsewhere slot 0 is recomputed per block call.
+  float* bias_buf = nullptr; size_t bias_slots = 0, bias_slot_floats = 0; bool bias_hoisted = false;
   EpsW eps;
   DiffW diff;
   Workspace ws;
@@ -206,6 +212,7 @@ extern "C" int abopt_model_create(const abopt_config* cfg, int device, abopt_mod
   CUDA_TRY(linear_kernels_init());
   CUDA_TRY(attn_kernels_init());
   CUDA_TRY(tc_init());
+  CUDA_TRY(pair_stream_init());
   abopt_model* m = new abopt_model();
   m->cfg = *cfg;
   m->device = device;
@@ -221,6 +228,7 @@ extern "C" void abopt_model_destroy(abopt_model* m) {
   if (m->wbase) cudaFree(m->wbase);
   if (m->ws.base) cudaFree(m->ws.base);
   if (m->io.base) cudaFree(m->io.base);
+  if (m->bias_buf) cudaFree(m->bias_buf);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   delete m;
 }
@@ -276,6 +284,7 @@ extern "C" int abopt_model_finalize(abopt_model* m) {
   const int NL = m->cfg.num_layers;
   m->blocks.assign(NL, BlockW{});
   m->pb.assign(NL, PairBiasParams{});
+  m->pbp.assign(NL, PairBiasPacked{});
   for (int l = 0; l < NL; ++l) {
     const std::string p = "eps_net.encoder.blocks." + std::to_string(l) + ".";
     BlockW& b = m->blocks[l];
@@ -290,6 +299,8 @@ extern "C" int abopt_model_finalize(abopt_model* m) {
     std::vector<float> wbt = transpose(wb, H, C);                    // [64][12]
     reg(&b.Wb, pk.put(wbt));
     memcpy(m->pb[l].Wb, wbt.data(), sizeof(float) * C * H);
+    for (int c = 0; c < C; ++c)
+      for (int hp = 0; hp < H / 2; ++hp) m->pbp[l].w[hp / 3][c][hp % 3] = make_float2(wb[(2 * hp) * C + c], wb[(2 * hp + 1) * C + c]);
     std::vector<float> coef(H);
     const float* sc = F32(m, p + "spatial_coef");
     for (int h = 0; h < H; ++h) {                                    // ga.py:109-111
@@ -451,17 +462,37 @@ static int check_ready(abopt_model* m, int N, int L, int need_scope = ABOPT_SCOP
 }
 
 // ------------------------------------------------------------------------------------------ encoder
+// TMA descriptor of pair_feat + room for `slots` layers of pair bias
+static int ensure_pair_inputs(abopt_model* m, int N, int L, const float* z, size_t slots) {
+  if (m->zmap_ptr != z || m->zmap_N != N || m->zmap_L != L) {
+    if (!make_pair_tmap(&m->zmap, z, (size_t)N * L * L, &m->zmap_box_rows)) return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed for pair_feat");
+    m->zmap_ptr = z; m->zmap_N = N; m->zmap_L = L;
+  }
+  const size_t slot_floats = (size_t)N * H * L * ((L + 3) & ~3);
+  if (!m->bias_buf || m->bias_slot_floats != slot_floats || m->bias_slots < slots) {
+    if (m->bias_buf) { CUDA_TRY(cudaFree(m->bias_buf)); m->bias_buf = nullptr; }
+    CUDA_TRY(cudaMalloc(&m->bias_buf, slots * slot_floats * sizeof(float)));
+    m->bias_slots = slots; m->bias_slot_floats = slot_floats;
+  }
+  return ABOPT_OK;
+}
+
 // one GABlock: x_in -> x_out (may not alias); feat/alpha taps optional
 static int run_block(abopt_model* m, int layer, int N, int L, const float* R, const float* t, const float* x,
                      const float* z, const uint8_t* mask, float* x_out, float* alpha_tap, cudaStream_t st) {
   Workspace& w = m->ws;
   const int M = N * L;
   const BlockW& bw = m->blocks[layer];
+  int rc = ensure_pair_inputs(m, N, L, z, m->bias_hoisted ? (size_t)m->cfg.num_layers : 1); if (rc) return rc;
+  const float* bias = m->bias_buf + (m->bias_hoisted ? (size_t)layer * m->bias_slot_floats : 0);
+  if (!m->bias_hoisted && !launch_pair_bias(N, 0, L, w.Lp, m->zmap, m->zmap_box_rows, m->pbp[layer], m->bias_buf, st))
+    return fail(ABOPT_ERR_ARG, "pair_bias_kernel: L too large for shared memory");
   launch_proj(M, x, bw.Wcat, R, t, w.proj, st);
   for (int b0 = 0; b0 < N; b0 += w.NB) {
     const int nb = (N - b0 < w.NB) ? (N - b0) : w.NB;
-    launch_logits(nb, L, w.Lp, w.proj + (size_t)b0 * L * NPROJ, bw.coef, w.S, st);
-    launch_pair(nb, b0, L, w.Lp, z, mask, w.S, m->pb[layer], w.alpha, w.feat, st);
+    launch_logits(nb, L, w.Lp, w.proj + (size_t)b0 * L * NPROJ, bw.coef, bias + (size_t)b0 * H * L * w.Lp, mask + (size_t)b0 * L, w.S, st);
+    if (!launch_pair_stream(nb, b0, L, w.Lp, m->zmap, m->zmap_box_rows, mask, w.S, w.alpha, w.feat, st))
+      return fail(ABOPT_ERR_ARG, "pair_stream_kernel: L too large for shared memory");
     launch_aggr(nb, b0, L, w.Lp, w.alpha, w.proj, R, t, w.feat, st);
     if (alpha_tap) launch_alpha_tap(nb, b0, L, w.Lp, w.alpha, alpha_tap, st);
   }
@@ -729,12 +760,17 @@ extern "C" int abopt_sample_device(abopt_model* m, int N, int L, const float* v,
   rc = run_init(m, N, L, v, p, (const long long*)s, mask_generate, flags, opt_step, seed, init_noise, V(T0), Pp(T0), S(T0),
                 PR(T0), PL(T0), st);
   if (rc) return rc;
-  for (int t = T0; t >= 1; --t) {
+  // loop-invariant hoist: the pair bias z . W_b of all layers, once per run instead of once per step
+  rc = ensure_pair_inputs(m, N, L, pair_feat, (size_t)m->cfg.num_layers); if (rc) return rc;
+  for (int l = 0; l < m->cfg.num_layers; ++l)
+    if (!launch_pair_bias(N, 0, L, m->ws.Lp, m->zmap, m->zmap_box_rows, m->pbp[l], m->bias_buf + (size_t)l * m->bias_slot_floats, st))
+      return fail(ABOPT_ERR_ARG, "pair_bias_kernel: L too large for shared memory");
+  m->bias_hoisted = true;
+  for (int t = T0; t >= 1 && rc == ABOPT_OK; --t)
     rc = run_step(m, N, L, t, optimize, flags, seed, V(t), Pp(t), S(t), res_feat, pair_feat, mask_generate, mask_res,
                   noise ? &noise[T0 - t] : nullptr, V(t - 1), Pp(t - 1), S(t - 1), PR(t - 1), PL(t - 1), st);
-    if (rc) return rc;
-  }
-  return ABOPT_OK;
+  m->bias_hoisted = false;
+  return rc;
 }
 
 static int ensure_hostio(abopt_model* m, int N, int L, int T0) {

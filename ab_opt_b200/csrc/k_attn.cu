@@ -1,10 +1,10 @@
 // Pairwise part of one GABlock, decoupled into three kernels that exchange the (heads x L x L)
 // logits / attention weights through L2 (the batch is processed in chunks small enough to stay
 // L2-resident, see api.cu):
-//   logits_kernel : node + spatial logits, a register-tiled batched "Q K^T"         ga.py:81-86,92-112
-//   pair_kernel   : streams z ONCE per layer: pair bias, masked softmax over j,
-//                   pair aggregation                                               ga.py:88-90,11-26,114-118
-//   aggr_kernel   : node + point aggregation ("P V") and the local-frame features   ga.py:120-147
+//   logits_kernel      : node + spatial logits, a register-tiled batched "Q K^T", + pair bias, scale,
+//                        key mask -> final logits                                 ga.py:81-86,92-112,166,23
+//   pair_stream_kernel : (k_pair.cu) streams z ONCE per layer: softmax over j, pair aggregation
+//   aggr_kernel        : node + point aggregation ("P V") and the local-frame features   ga.py:120-147
 // Layouts: S / alpha are [chunk complex][head][i][Lp] (j contiguous, Lp = L rounded up to 4).
 #include "common.cuh"
 #include "params.cuh"
@@ -18,7 +18,8 @@ constexpr int LG_K = D + P * 3;   // 56 = 32 qk channels + 24 point coordinates
 constexpr int LG_LD = LG_T + 4;
 
 __global__ void __launch_bounds__(256, 2)
-logits_kernel(int L, int Lp, const float* __restrict__ proj, const float* __restrict__ coef, float* __restrict__ S) {
+logits_kernel(int L, int Lp, const float* __restrict__ proj, const float* __restrict__ coef, const float* __restrict__ bias,
+              const uint8_t* __restrict__ mask, float* __restrict__ S) {
   __shared__ __align__(16) float Qs[LG_K][LG_LD];
   __shared__ __align__(16) float Ks[LG_K][LG_LD];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -66,193 +67,24 @@ logits_kernel(int L, int Lp, const float* __restrict__ proj, const float* __rest
   }
   const float cf = coef[h];
   const float inv_sqrt_d = 0.17677669529663687f;      // 1/sqrt(32)
+  const float scale = 0.57735026918962576f;           // sqrt(1/3), ga.py:166
+  // + pair bias (pair_bias_kernel), * sqrt(1/3), key mask as a finite -1e5 (ga.py:23,166): the final logits
+  const int jq = j0 + tx * 4;
+  float pen[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) pen[c] = (jq + c < L && mask[(size_t)b * L + jq + c] != 0) ? 0.f : 1e5f;
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
-    const int i = i0 + ty * 4 + a, j = j0 + tx * 4;
-    if (i < L && j < L) {
-      float4 o = make_float4(nd[a][0] * inv_sqrt_d + sp[a][0] * cf, nd[a][1] * inv_sqrt_d + sp[a][1] * cf,
-                             nd[a][2] * inv_sqrt_d + sp[a][2] * cf, nd[a][3] * inv_sqrt_d + sp[a][3] * cf);
-      *reinterpret_cast<float4*>(S + ((size_t)bh * L + i) * Lp + j) = o;      // columns >= L are padding
+    const int i = i0 + ty * 4 + a;
+    if (i < L && jq < L) {
+      const size_t off = ((size_t)bh * L + i) * Lp + jq;
+      const float4 pbv = __ldg(reinterpret_cast<const float4*>(bias + off));
+      const float pbs[4] = {pbv.x, pbv.y, pbv.z, pbv.w};
+      float o[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[c] = ((nd[a][c] * inv_sqrt_d + pbs[c]) + sp[a][c] * cf) * scale - pen[c];
+      *reinterpret_cast<float4*>(S + off) = make_float4(o[0], o[1], o[2], o[3]);      // columns >= L are padding
     }
-  }
-}
-
-// ------------------------------------------------------------------------------------------ pair stream
-// One CTA per query residue (b, i).  The residue's z row-block (L x 64 floats) is staged in shared
-// memory once, XOR-swizzled at 16-byte granularity so that both access patterns are conflict free:
-//   (a) thread = key residue j reads its own 256 B row          (pair bias, z . Wb)
-//   (b) 16 lanes = the 16 float4 column groups of one row j      (pair aggregation, alpha . z)
-constexpr int PK_THREADS = 256;
-constexpr int PK_SLICES = PK_THREADS / 16;       // 16 j-slices in the aggregation phase
-
-template <int JPT>   // key residues per thread: L <= 256 * JPT
-__global__ void __launch_bounds__(PK_THREADS, 2)
-pair_kernel(int L, int Lp, int b0, const float* __restrict__ z, const uint8_t* __restrict__ mask,
-            const float* __restrict__ S, const __grid_constant__ PairBiasParams pb,
-            float* __restrict__ alpha, float* __restrict__ feat) {
-  extern __shared__ __align__(16) float smem[];
-  const int zs_floats = max(L * C, PK_SLICES * H * C);
-  float* zs = smem;                       // [L][64] swizzled; later the cross-slice reduction buffer
-  float* al = smem + zs_floats;           // [L][12]
-  __shared__ float red[PK_THREADS / 32][H];
-  __shared__ float fin[H];
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int bl = blockIdx.x / L, i = blockIdx.x % L;       // complex within the chunk, query residue
-  const int b = b0 + bl;
-  const bool row_ok = mask[(size_t)b * L + i] != 0;
-  float* feat_row = feat + ((size_t)b * L + i) * NFEAT;
-
-  if (!row_ok) {
-    // masked query: alpha row = 0 (ga.py:25) -> zero pair aggregate
-    for (int o = tid; o < H * C; o += PK_THREADS) feat_row[o] = 0.f;
-    for (int o = tid; o < H * Lp; o += PK_THREADS) {
-      const int h = o / Lp, j = o % Lp;
-      alpha[((size_t)(bl * H + h) * L + i) * Lp + j] = 0.f;
-    }
-    return;
-  }
-
-  // ---- stage z[b, i, :, :] (coalesced 16 B cp.async, swizzled destination)
-  const float* zrow = z + ((size_t)b * L + i) * (size_t)L * C;
-  for (int ch = tid; ch < L * 16; ch += PK_THREADS) {
-    const int j = ch >> 4, q = ch & 15;
-    cp_async16(zs + j * C + ((q ^ (j & 15)) << 2), zrow + (size_t)ch * 4);
-  }
-  cp_async_commit();
-
-  // ---- logits of this thread's key residues: S (node + spatial, from L2) while z is in flight
-  float lg[JPT][H];
-  bool jok[JPT];
-#pragma unroll
-  for (int u = 0; u < JPT; ++u) {
-    const int j = tid + u * PK_THREADS;
-    jok[u] = (j < L);
-#pragma unroll
-    for (int h = 0; h < H; ++h)
-      lg[u][h] = jok[u] ? __ldg(S + ((size_t)(bl * H + h) * L + i) * Lp + j) : 0.f;
-  }
-  cp_async_wait<0>();
-  __syncthreads();
-
-  const float scale = 0.57735026918962576f;      // sqrt(1/3), ga.py:166
-#pragma unroll
-  for (int u = 0; u < JPT; ++u) {
-    const int j = tid + u * PK_THREADS;
-    if (jok[u]) {
-      float bias[H];
-#pragma unroll
-      for (int h = 0; h < H; ++h) bias[h] = 0.f;
-      const float* zr = zs + j * C;
-      const int sw = j & 15;
-#pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const float4 v = *reinterpret_cast<const float4*>(zr + ((q ^ sw) << 2));
-#pragma unroll
-        for (int h = 0; h < H; ++h) {
-          bias[h] = fmaf(v.x, pb.Wb[q * 4 + 0][h], bias[h]);
-          bias[h] = fmaf(v.y, pb.Wb[q * 4 + 1][h], bias[h]);
-          bias[h] = fmaf(v.z, pb.Wb[q * 4 + 2][h], bias[h]);
-          bias[h] = fmaf(v.w, pb.Wb[q * 4 + 3][h], bias[h]);
-        }
-      }
-      const bool mj = mask[(size_t)b * L + j] != 0;
-#pragma unroll
-      for (int h = 0; h < H; ++h) {
-        const float v = (lg[u][h] + bias[h]) * scale;
-        lg[u][h] = mj ? v : v - 1e5f;                 // ga.py:23 (finite "-inf")
-      }
-    } else {
-#pragma unroll
-      for (int h = 0; h < H; ++h) lg[u][h] = -INFINITY;
-    }
-  }
-
-  // ---- softmax over j (ga.py:24), block-wide per head
-  float mx[H];
-#pragma unroll
-  for (int h = 0; h < H; ++h) {
-    float m = lg[0][h];
-#pragma unroll
-    for (int u = 1; u < JPT; ++u) m = fmaxf(m, lg[u][h]);
-    mx[h] = warp_max(m);
-  }
-  if (lane == 0)
-#pragma unroll
-    for (int h = 0; h < H; ++h) red[warp][h] = mx[h];
-  __syncthreads();
-  if (tid < H) {
-    float m = red[0][tid];
-    for (int w = 1; w < PK_THREADS / 32; ++w) m = fmaxf(m, red[w][tid]);
-    fin[tid] = m;
-  }
-  __syncthreads();
-  float sm[H];
-#pragma unroll
-  for (int h = 0; h < H; ++h) {
-    const float m = fin[h];
-    float s = 0.f;
-#pragma unroll
-    for (int u = 0; u < JPT; ++u) { lg[u][h] = expf(lg[u][h] - m); s += lg[u][h]; }   // exp(-inf) = 0 for j >= L
-    sm[h] = warp_sum(s);
-  }
-  __syncthreads();                                      // everyone has read fin[] (max)
-  if (lane == 0)
-#pragma unroll
-    for (int h = 0; h < H; ++h) red[warp][h] = sm[h];
-  __syncthreads();
-  if (tid < H) {
-    float s = 0.f;
-    for (int w = 0; w < PK_THREADS / 32; ++w) s += red[w][tid];
-    fin[tid] = s;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int u = 0; u < JPT; ++u) {
-    const int j = tid + u * PK_THREADS;
-    if (j < Lp) {
-#pragma unroll
-      for (int h = 0; h < H; ++h) {
-        const float a = (j < L) ? lg[u][h] / fin[h] : 0.f;
-        lg[u][h] = a;
-        alpha[((size_t)(bl * H + h) * L + i) * Lp + j] = a;
-      }
-      if (j < L) {
-        float4* dst = reinterpret_cast<float4*>(al + j * H);
-        dst[0] = make_float4(lg[u][0], lg[u][1], lg[u][2], lg[u][3]);
-        dst[1] = make_float4(lg[u][4], lg[u][5], lg[u][6], lg[u][7]);
-        dst[2] = make_float4(lg[u][8], lg[u][9], lg[u][10], lg[u][11]);
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- pair aggregation out[h][c] = sum_j alpha[j][h] z[j][c]   (ga.py:114-118)
-  const int c4 = tid & 15, js = tid >> 4;
-  float acc[H][4];
-#pragma unroll
-  for (int h = 0; h < H; ++h) { acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f; }
-  for (int j = js; j < L; j += PK_SLICES) {
-    const float4 zv = *reinterpret_cast<const float4*>(zs + j * C + ((c4 ^ (j & 15)) << 2));
-    const float4* ap = reinterpret_cast<const float4*>(al + j * H);
-    const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2];
-    const float a[H] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
-#pragma unroll
-    for (int h = 0; h < H; ++h) {
-      acc[h][0] = fmaf(a[h], zv.x, acc[h][0]); acc[h][1] = fmaf(a[h], zv.y, acc[h][1]);
-      acc[h][2] = fmaf(a[h], zv.z, acc[h][2]); acc[h][3] = fmaf(a[h], zv.w, acc[h][3]);
-    }
-  }
-  __syncthreads();                                      // all reads of zs done -> reuse as reduction buffer
-#pragma unroll
-  for (int h = 0; h < H; ++h)
-    *reinterpret_cast<float4*>(zs + js * (H * C) + h * C + c4 * 4) = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
-  __syncthreads();
-  for (int o = tid; o < H * C; o += PK_THREADS) {
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < PK_SLICES; ++k) s += zs[k * (H * C) + o];
-    feat_row[o] = s;
   }
 }
 
@@ -363,34 +195,13 @@ __global__ void alpha_to_reference_layout(int L, int Lp, int b0, const float* __
 }
 
 // ------------------------------------------------------------------------------------------ launchers
-size_t pair_smem_bytes(int L) {
-  const size_t zs = (size_t)((L * C > PK_SLICES * H * C) ? L * C : PK_SLICES * H * C);
-  return (zs + (size_t)L * H) * sizeof(float);
-}
+cudaError_t attn_kernels_init() { return cudaSuccess; }
 
-cudaError_t attn_kernels_init() {
-  cudaError_t e;
-  const int mx = 200 * 1024;
-  if ((e = cudaFuncSetAttribute(pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)) != cudaSuccess) return e;
-  return cudaSuccess;
-}
-
-void launch_logits(int nb, int L, int Lp, const float* proj_chunk, const float* coef, float* S, cudaStream_t st) {
+void launch_logits(int nb, int L, int Lp, const float* proj_chunk, const float* coef, const float* bias_chunk,
+                   const uint8_t* mask_chunk, float* S, cudaStream_t st) {
   ProfScope prof__(KK_LOGITS, st);
   dim3 grid((L + LG_T - 1) / LG_T, (L + LG_T - 1) / LG_T, nb * H);
-  logits_kernel<<<grid, 256, 0, st>>>(L, Lp, proj_chunk, coef, S);
-}
-
-void launch_pair(int nb, int b0, int L, int Lp, const float* z, const uint8_t* mask, const float* S,
-                 const PairBiasParams& pb, float* alpha, float* feat, cudaStream_t st) {
-  ProfScope prof__(KK_PAIR, st);
-  const size_t smem = pair_smem_bytes(L);
-  const int grid = nb * L;
-  if (L <= 256) pair_kernel<1><<<grid, PK_THREADS, smem, st>>>(L, Lp, b0, z, mask, S, pb, alpha, feat);
-  else if (L <= 512) pair_kernel<2><<<grid, PK_THREADS, smem, st>>>(L, Lp, b0, z, mask, S, pb, alpha, feat);
-  else pair_kernel<3><<<grid, PK_THREADS, smem, st>>>(L, Lp, b0, z, mask, S, pb, alpha, feat);
+  logits_kernel<<<grid, 256, 0, st>>>(L, Lp, proj_chunk, coef, bias_chunk, mask_chunk, S);
 }
 
 void launch_aggr(int nb, int b0, int L, int Lp, const float* alpha, const float* proj, const float* R, const float* t,

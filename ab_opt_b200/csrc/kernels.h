@@ -1,5 +1,6 @@
 // Host-side launcher declarations shared by api.cu and the kernel translation units.
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
 #include "params.cuh"
 
@@ -49,13 +50,19 @@ void launch_heads(int M, int L, const float* x, const float* beta, int beta_stri
                   const uint8_t* mask_gen, const EpsW& w, float* v_next, float* R_next, float* eps_pos, float* c_den,
                   float* prmsd_rows, float* prmsd_logits, cudaStream_t st);
 
-void launch_logits(int nb, int L, int Lp, const float* proj_chunk, const float* coef, float* S, cudaStream_t st);
-void launch_pair(int nb, int b0, int L, int Lp, const float* z, const uint8_t* mask, const float* S,
-                 const PairBiasParams& pb, float* alpha, float* feat, cudaStream_t st);
+void launch_logits(int nb, int L, int Lp, const float* proj_chunk, const float* coef, const float* bias_chunk,
+                   const uint8_t* mask_chunk, float* S, cudaStream_t st);
 void launch_aggr(int nb, int b0, int L, int Lp, const float* alpha, const float* proj, const float* R, const float* t,
                  float* feat, cudaStream_t st);
 void launch_alpha_tap(int nb, int b0, int L, int Lp, const float* alpha, float* out, cudaStream_t st);
-size_t pair_smem_bytes(int L);
+// pair_stream_kernel (k_pair.cu): TMA-fed persistent replacement of pair_kernel
+cudaError_t pair_stream_init();
+bool make_tmap_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
+bool make_pair_tmap(CUtensorMap* m, const float* z, size_t total_rows, int* box_rows_out);
+bool launch_pair_bias(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, int box_rows, const PairBiasPacked& pb, float* bias,
+                      cudaStream_t st);
+bool launch_pair_stream(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, int box_rows, const uint8_t* mask, const float* logits,
+                        float* alpha, float* feat, cudaStream_t st);
 
 void launch_angle_argmax(int M, int L, const long long* tvec, int t_uniform, const float* Y, const float* expo,
                          const uint8_t* mask_gen, int* bin_idx, cudaStream_t st);

@@ -25,6 +25,13 @@ struct PairBiasParams {
   float coef[H];
 };
 
+// The same pair-bias weight packed as head PAIRS for the FFMA2 (fma.rn.f32x2) inner loop of pair_stream_kernel:
+// w[half][c][k] = (W_b[6 half + 2k][c], W_b[6 half + 2k + 1][c]); by-value kernel parameter -> constant bank ->
+// uniform registers (the head half is warp-uniform in the kernel).
+struct PairBiasPacked {
+  float2 w[2][C][3];       // 3072 B
+};
+
 // One 3-layer head (eps_crd_net / eps_rot_net / eps_seq_net, dpm_full.py:45-62).
 struct HeadW {
   const float* W0_t;       // [128][128]   first 128 input columns of layer 0, transposed

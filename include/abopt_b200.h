@@ -42,7 +42,7 @@ extern "C" {
 #define ABOPT_NUM_HEADS      12   /* modules/encoders/ga.py:43                              */
 #define ABOPT_NUM_AA         20   /* modules/diffusion/transition.py:165                    */
 #define ABOPT_ANGLE_BINS   8192   /* modules/common/so3.py:73                               */
-#define ABOPT_MAX_L         704   /* longest complex the single-pass pair kernel can hold   */
+#define ABOPT_MAX_L         640   /* longest complex whose z row-block fits one smem stage   */
 
 typedef struct abopt_model abopt_model;
 
