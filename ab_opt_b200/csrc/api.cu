@@ -61,7 +61,7 @@ struct Workspace {
   int N = 0, L = 0, Lp = 0, NB = 0;
   size_t bytes = 0;
   void* base = nullptr;
-  float *Rbuf, *pnorm, *xa, *xb, *proj, *feat, *S, *alpha, *prmsd_rows, *prmsd_logits, *maxprob;
+  float *Rbuf, *pnorm, *xa, *xb, *xa_lo, *xb_lo, *xin_lo, *proj, *feat, *feat_lo, *outD, *S, *alpha, *prmsd_rows, *prmsd_logits, *maxprob;
   float *v_net, *eps_pos, *c_den, *R_next;
   int* bin_idx;
   long long* tvec_scratch;
@@ -161,14 +161,14 @@ extern "C" int abopt_debug_gemm3x(int device, int M, int N, int K, const float* 
   DeviceGuard g(device);
   CUDA_TRY(tc_init());
   cudaStream_t st = (cudaStream_t)stream;
-  float *Ah, *Al, *Bh, *Bl;
-  CUDA_TRY(cudaMalloc(&Ah, (size_t)M * K * 4)); CUDA_TRY(cudaMalloc(&Al, (size_t)M * K * 4));
-  CUDA_TRY(cudaMalloc(&Bh, (size_t)N * K * 4)); CUDA_TRY(cudaMalloc(&Bl, (size_t)N * K * 4));
-  launch_split(A, Ah, Al, (size_t)M * K, st);
-  launch_split(B, Bh, Bl, (size_t)N * K, st);
-  const bool ok = launch_gemm3x_plain(M, N, K, Ah, Al, K, Bh, Bl, K, D, N, bias, st);
+  // exactly as the model uses it: the raw fp32 operands serve as the "hi" planes (the tensor core truncates to tf32)
+  float *Al, *Bl;
+  CUDA_TRY(cudaMalloc(&Al, (size_t)M * K * 4)); CUDA_TRY(cudaMalloc(&Bl, (size_t)N * K * 4));
+  launch_lo(A, Al, (size_t)M * K, st);
+  launch_lo(B, Bl, (size_t)N * K, st);
+  const bool ok = launch_gemm3x_plain(M, N, K, A, Al, K, B, Bl, K, D, N, bias, st);
   cudaError_t e = cudaStreamSynchronize(st);
-  cudaFree(Ah); cudaFree(Al); cudaFree(Bh); cudaFree(Bl);
+  cudaFree(Al); cudaFree(Bl);
   if (!ok) return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   if (e != cudaSuccess) return fail(ABOPT_ERR_CUDA, std::string("gemm3x: ") + cudaGetErrorString(e));
   CHECK_LAUNCH();
@@ -272,6 +272,16 @@ static std::vector<float> transpose(const float* w, int rows, int cols, int pad_
   return o;
 }
 
+static std::vector<float> lo_plane(const float* w, size_t n) {      // x - trunc_tf32(x), see k_tc.cu
+  std::vector<float> o(n);
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t u; memcpy(&u, &w[i], 4); u &= 0xFFFFE000u;
+    float h; memcpy(&h, &u, 4);
+    o[i] = w[i] - h;
+  }
+  return o;
+}
+
 extern "C" int abopt_model_finalize(abopt_model* m) {
   if (!m) return fail(ABOPT_ERR_ARG, "null model");
   for (auto& kv : m->spec)
@@ -295,6 +305,12 @@ extern "C" int abopt_model_finalize(abopt_model* m) {
       memcpy(wcat.data() + o, t.bytes.data(), t.numel * 4); o += t.numel;
     }
     reg(&b.Wcat, pk.put(wcat));
+    reg(&b.Wcat_lo, pk.put(lo_plane(wcat.data(), wcat.size())));
+    {
+      const HostTensor& wo = m->sd[p + "out_transform.weight"];                 // [128][1824]
+      reg(&b.Wout, pk.put(wo.bytes.data(), wo.numel * 4));
+      reg(&b.Wout_lo, pk.put(lo_plane(reinterpret_cast<const float*>(wo.bytes.data()), wo.numel)));
+    }
     const float* wb = F32(m, p + "proj_pair_bias.weight");         // [12][64]
     std::vector<float> wbt = transpose(wb, H, C);                    // [64][12]
     reg(&b.Wb, pk.put(wbt));
@@ -433,7 +449,8 @@ static int ensure_workspace(abopt_model* m, int N, int L) {
                oProj = take(M * NPROJ * 4), oFeat = take(M * NFEAT * 4), oS = take((size_t)NB * H * L * Lp * 4),
                oAl = take((size_t)NB * H * L * Lp * 4), oPr = take(M * bins * 4), oPl = take((size_t)N * bins * 4),
                oMp = take(M * 4), oVn = take(M * 3 * 4), oEp = take(M * 3 * 4), oCd = take(M * NAA * 4), oRn = take(M * 9 * 4),
-               oBi = take(M * 4), oTv = take((size_t)N * 8);
+               oBi = take(M * 4), oTv = take((size_t)N * 8), oXal = take(M * F * 4), oXbl = take(M * F * 4), oXil = take(M * F * 4),
+               oFl = take(M * NFEAT * 4), oOd = take(M * F * 4);
   CUDA_TRY(cudaMalloc(&w.base, off));
   unsigned char* b = static_cast<unsigned char*>(w.base);
   w.Rbuf = (float*)(b + oR); w.pnorm = (float*)(b + oP); w.xa = (float*)(b + oXa); w.xb = (float*)(b + oXb);
@@ -441,6 +458,8 @@ static int ensure_workspace(abopt_model* m, int N, int L) {
   w.prmsd_rows = (float*)(b + oPr); w.prmsd_logits = (float*)(b + oPl); w.maxprob = (float*)(b + oMp);
   w.v_net = (float*)(b + oVn); w.eps_pos = (float*)(b + oEp); w.c_den = (float*)(b + oCd); w.R_next = (float*)(b + oRn);
   w.bin_idx = (int*)(b + oBi); w.tvec_scratch = (long long*)(b + oTv);
+  w.xa_lo = (float*)(b + oXal); w.xb_lo = (float*)(b + oXbl); w.xin_lo = (float*)(b + oXil); w.feat_lo = (float*)(b + oFl);
+  w.outD = (float*)(b + oOd);
   w.N = N; w.L = L; w.Lp = Lp; w.NB = NB; w.bytes = off;
   return ABOPT_OK;
 }
@@ -477,9 +496,10 @@ static int ensure_pair_inputs(abopt_model* m, int N, int L, const float* z, size
   return ABOPT_OK;
 }
 
-// one GABlock: x_in -> x_out (may not alias); feat/alpha taps optional
-static int run_block(abopt_model* m, int layer, int N, int L, const float* R, const float* t, const float* x,
-                     const float* z, const uint8_t* mask, float* x_out, float* alpha_tap, cudaStream_t st) {
+// one GABlock: x_in -> x_out (may not alias); feat/alpha taps optional.
+// x_lo = tf32 "lo" plane of x (nullptr: computed here); x_lo_out = where to put the lo plane of x_out (may be nullptr)
+static int run_block(abopt_model* m, int layer, int N, int L, const float* R, const float* t, const float* x, const float* x_lo,
+                     const float* z, const uint8_t* mask, float* x_out, float* x_lo_out, float* alpha_tap, cudaStream_t st) {
   Workspace& w = m->ws;
   const int M = N * L;
   const BlockW& bw = m->blocks[layer];
@@ -487,16 +507,23 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
   const float* bias = m->bias_buf + (m->bias_hoisted ? (size_t)layer * m->bias_slot_floats : 0);
   if (!m->bias_hoisted && !launch_pair_bias(N, 0, L, w.Lp, m->zmap, m->zmap_box_rows, m->pbp[layer], m->bias_buf, st))
     return fail(ABOPT_ERR_ARG, "pair_bias_kernel: L too large for shared memory");
-  launch_proj(M, x, bw.Wcat, R, t, w.proj, st);
+  // the six input projections: tcgen05 3xTF32 GEMM (x raw = "hi" plane, x_lo = "lo" plane)
+  if (x_lo == nullptr) { launch_lo(x, w.xin_lo, (size_t)M * F, st); x_lo = w.xin_lo; }
+  if (!launch_proj_tc(M, x, x_lo, bw.Wcat, bw.Wcat_lo, R, t, w.proj, st)) return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (proj)");
   for (int b0 = 0; b0 < N; b0 += w.NB) {
     const int nb = (N - b0 < w.NB) ? (N - b0) : w.NB;
     launch_logits(nb, L, w.Lp, w.proj + (size_t)b0 * L * NPROJ, bw.coef, bias + (size_t)b0 * H * L * w.Lp, mask + (size_t)b0 * L, w.S, st);
-    if (!launch_pair_stream(nb, b0, L, w.Lp, m->zmap, m->zmap_box_rows, mask, w.S, w.alpha, w.feat, st))
+    if (!launch_pair_stream(nb, b0, L, w.Lp, m->zmap, m->zmap_box_rows, mask, w.S, w.alpha, w.feat, w.feat_lo, st))
       return fail(ABOPT_ERR_ARG, "pair_stream_kernel: L too large for shared memory");
-    launch_aggr(nb, b0, L, w.Lp, w.alpha, w.proj, R, t, w.feat, st);
+    launch_aggr(nb, b0, L, w.Lp, w.alpha, w.proj, R, t, w.feat, w.feat_lo, st);
     if (alpha_tap) launch_alpha_tap(nb, b0, L, w.Lp, w.alpha, alpha_tap, st);
   }
-  if (x_out) launch_tail(M, w.feat, x, mask, bw, x_out, st);
+  if (x_out) {
+    // out_transform (K = 1824) on the tensor cores, then mask / residual / LN / MLP / LN
+    if (!launch_gemm3x_plain(M, F, NFEAT, w.feat, w.feat_lo, NFEAT, bw.Wout, bw.Wout_lo, NFEAT, w.outD, F, bw.bout, st))
+      return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (out_transform)");
+    launch_tail(M, w.feat, w.outD, x, mask, bw, x_out, x_lo_out, st);
+  }
   CHECK_LAUNCH();
   return ABOPT_OK;
 }
@@ -510,7 +537,7 @@ extern "C" int abopt_ga_block_forward(abopt_model* m, int layer, int N, int L, c
   rc = ensure_workspace(m, N, L); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   float* dst = (x_out == x) ? m->ws.xa : x_out;
-  rc = run_block(m, layer, N, L, R, t, x, z, mask, dst, nullptr, st); if (rc) return rc;
+  rc = run_block(m, layer, N, L, R, t, x, nullptr, z, mask, dst, nullptr, nullptr, st); if (rc) return rc;
   if (dst != x_out) CUDA_TRY(cudaMemcpyAsync(x_out, dst, (size_t)N * L * F * 4, cudaMemcpyDeviceToDevice, st));
   return ABOPT_OK;
 }
@@ -523,21 +550,23 @@ extern "C" int abopt_ga_block_taps(abopt_model* m, int layer, int N, int L, cons
   DeviceGuard g(m->device);
   rc = ensure_workspace(m, N, L); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  rc = run_block(m, layer, N, L, R, t, x, z, mask, nullptr, alpha, st); if (rc) return rc;
+  rc = run_block(m, layer, N, L, R, t, x, nullptr, z, mask, nullptr, nullptr, alpha, st); if (rc) return rc;
   if (feat) CUDA_TRY(cudaMemcpyAsync(feat, m->ws.feat, (size_t)N * L * NFEAT * 4, cudaMemcpyDeviceToDevice, st));
   return ABOPT_OK;
 }
 
 // all layers; result lands in *result (one of the two workspace ping-pong buffers)
-static int run_encoder(abopt_model* m, int N, int L, const float* R, const float* t, const float* x, const float* z,
-                       const uint8_t* mask, float** result, cudaStream_t st) {
+static int run_encoder(abopt_model* m, int N, int L, const float* R, const float* t, const float* x, const float* x_lo,
+                       const float* z, const uint8_t* mask, float** result, cudaStream_t st) {
   Workspace& w = m->ws;
   const float* cur = x;
+  const float* cur_lo = x_lo;
   float* bufs[2] = {w.xa, w.xb};
+  float* bufs_lo[2] = {w.xa_lo, w.xb_lo};
   int which = (x == w.xa) ? 1 : 0;
   for (int l = 0; l < m->cfg.num_layers; ++l) {
-    int rc = run_block(m, l, N, L, R, t, cur, z, mask, bufs[which], nullptr, st); if (rc) return rc;
-    cur = bufs[which]; which ^= 1;
+    int rc = run_block(m, l, N, L, R, t, cur, cur_lo, z, mask, bufs[which], bufs_lo[which], nullptr, st); if (rc) return rc;
+    cur = bufs[which]; cur_lo = bufs_lo[which]; which ^= 1;
   }
   *result = const_cast<float*>(cur);
   return ABOPT_OK;
@@ -551,7 +580,7 @@ extern "C" int abopt_ga_encoder_forward(abopt_model* m, int N, int L, const floa
   rc = ensure_workspace(m, N, L); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   float* res = nullptr;
-  rc = run_encoder(m, N, L, R, t, x, z, mask, &res, st); if (rc) return rc;
+  rc = run_encoder(m, N, L, R, t, x, nullptr, z, mask, &res, st); if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(x_out, res, (size_t)N * L * F * 4, cudaMemcpyDeviceToDevice, st));
   return ABOPT_OK;
 }
@@ -564,10 +593,10 @@ static int run_eps_net(abopt_model* m, int N, int L, const float* v_t, const flo
                        float* c_den, float* prmsd_logits, cudaStream_t st) {
   Workspace& w = m->ws;
   const int M = N * L;
-  launch_mixer(M, res_feat, s_t, v_t, m->eps, w.xa, w.Rbuf, p_ang, w.pnorm, m->diff.pos_mean, m->diff.pos_scale, st);
+  launch_mixer(M, res_feat, s_t, v_t, m->eps, w.xa, w.Rbuf, p_ang, w.pnorm, m->diff.pos_mean, m->diff.pos_scale, w.xa_lo, st);
   const float* tpos = p_ang ? w.pnorm : p_t;
   float* enc = nullptr;
-  int rc = run_encoder(m, N, L, w.Rbuf, tpos, w.xa, pair_feat, mask_res, &enc, st); if (rc) return rc;
+  int rc = run_encoder(m, N, L, w.Rbuf, tpos, w.xa, w.xa_lo, pair_feat, mask_res, &enc, st); if (rc) return rc;
   launch_heads(M, L, enc, beta, beta_stride, w.Rbuf, v_t, mask_gen, m->eps, v_next, R_next, eps_pos, c_den, w.prmsd_rows,
                m->cfg.has_prmsd ? (prmsd_logits ? prmsd_logits : w.prmsd_logits) : nullptr, st);
   CHECK_LAUNCH();

@@ -57,6 +57,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// x - trunc_tf32(x): the "lo" plane of the 3xTF32 operand split (the tensor core reads trunc_tf32(x) from the raw value)
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
 // ---------------------------------------------------------------- 3x3 helpers (row-major R[9])
 struct Mat3 { float m[9]; };
 

@@ -94,7 +94,7 @@ constexpr int AG_ALD = AG_TI + 4, AG_VLD = AG_N, AG_OLD = AG_N + 1;
 
 __global__ void __launch_bounds__(256, 2)
 aggr_kernel(int L, int Lp, int b0, const float* __restrict__ alpha, const float* __restrict__ proj,
-            const float* __restrict__ R, const float* __restrict__ t, float* __restrict__ feat) {
+            const float* __restrict__ R, const float* __restrict__ t, float* __restrict__ feat, float* __restrict__ feat_lo) {
   __shared__ __align__(16) float As[AG_TJ][AG_ALD];      // alpha tile, transposed [j][i]
   __shared__ __align__(16) float Vs[AG_TJ][AG_VLD];      // [j][n]  n < 32: value channels, n >= 32: global value points
   __shared__ float Os[AG_TI][AG_OLD];
@@ -152,7 +152,10 @@ aggr_kernel(int L, int Lp, int b0, const float* __restrict__ alpha, const float*
   // node aggregate -> feat[:, 768 + h*32 + d]   (ga.py:120-125)
   for (int o = tid; o < AG_TI * D; o += 256) {
     const int r = o >> 5, d = o & 31;
-    if (i0 + r < L) feat[((size_t)b * L + i0 + r) * NFEAT + FEAT_NODE + h * D + d] = Os[r][d];
+    if (i0 + r < L) {
+      const size_t o2 = ((size_t)b * L + i0 + r) * NFEAT + FEAT_NODE + h * D + d;
+      feat[o2] = Os[r][d]; feat_lo[o2] = tf32_lo(Os[r][d]);
+    }
   }
   // point aggregate -> local frame, norm, direction   (ga.py:137-146)
   for (int o = tid; o < AG_TI * P; o += 256) {
@@ -173,10 +176,15 @@ aggr_kernel(int L, int Lp, int b0, const float* __restrict__ alpha, const float*
     const float nrm = sqrtf(lx * lx + ly * ly + lz * lz);
     const float den = nrm + 1e-4f;                        // normalize_vector(eps=1e-4), ga.py:139
     float* fr = feat + row * NFEAT;
+    float* fl = feat_lo + row * NFEAT;
     const int hp = h * P + p;
+    const float dx = lx / den, dy = ly / den, dz = lz / den;
     fr[FEAT_PTS + hp * 3 + 0] = lx; fr[FEAT_PTS + hp * 3 + 1] = ly; fr[FEAT_PTS + hp * 3 + 2] = lz;
     fr[FEAT_DIST + hp] = nrm;
-    fr[FEAT_DIR + hp * 3 + 0] = lx / den; fr[FEAT_DIR + hp * 3 + 1] = ly / den; fr[FEAT_DIR + hp * 3 + 2] = lz / den;
+    fr[FEAT_DIR + hp * 3 + 0] = dx; fr[FEAT_DIR + hp * 3 + 1] = dy; fr[FEAT_DIR + hp * 3 + 2] = dz;
+    fl[FEAT_PTS + hp * 3 + 0] = tf32_lo(lx); fl[FEAT_PTS + hp * 3 + 1] = tf32_lo(ly); fl[FEAT_PTS + hp * 3 + 2] = tf32_lo(lz);
+    fl[FEAT_DIST + hp] = tf32_lo(nrm);
+    fl[FEAT_DIR + hp * 3 + 0] = tf32_lo(dx); fl[FEAT_DIR + hp * 3 + 1] = tf32_lo(dy); fl[FEAT_DIR + hp * 3 + 2] = tf32_lo(dz);
   }
 }
 
@@ -205,10 +213,10 @@ void launch_logits(int nb, int L, int Lp, const float* proj_chunk, const float* 
 }
 
 void launch_aggr(int nb, int b0, int L, int Lp, const float* alpha, const float* proj, const float* R, const float* t,
-                 float* feat, cudaStream_t st) {
+                 float* feat, float* feat_lo, cudaStream_t st) {
   ProfScope prof__(KK_AGGR, st);
   dim3 grid((L + AG_TI - 1) / AG_TI, nb * H);
-  aggr_kernel<<<grid, 256, 0, st>>>(L, Lp, b0, alpha, proj, R, t, feat);
+  aggr_kernel<<<grid, 256, 0, st>>>(L, Lp, b0, alpha, proj, R, t, feat, feat_lo);
 }
 
 void launch_alpha_tap(int nb, int b0, int L, int Lp, const float* alpha, float* out, cudaStream_t st) {

@@ -13,7 +13,8 @@ namespace abopt {
 __global__ void __launch_bounds__(RT_THREADS, 2)
 mixer_kernel(int M, const float* __restrict__ res_feat, const long long* __restrict__ s_t,
              const float* __restrict__ v_t, EpsW w, float* __restrict__ x_out, float* __restrict__ Rbuf,
-             const float* __restrict__ p_ang, float* __restrict__ p_norm, float mean0, float mean1, float mean2, float scale) {
+             const float* __restrict__ p_ang, float* __restrict__ p_norm, float mean0, float mean1, float mean2, float scale,
+             float* __restrict__ x_lo_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RowTileSmem& s = *reinterpret_cast<RowTileSmem*>(smem_raw);
   float* act = reinterpret_cast<float*>(smem_raw + sizeof(RowTileSmem));      // [64][RT_ACT_LD]
@@ -53,7 +54,11 @@ mixer_kernel(int M, const float* __restrict__ res_feat, const long long* __restr
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const int row = row0 + warp * 8 + r;
-    if (row < M) *reinterpret_cast<float4*>(x_out + (size_t)row * F + lane * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    if (row < M) {
+      *reinterpret_cast<float4*>(x_out + (size_t)row * F + lane * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      if (x_lo_out != nullptr)
+        *reinterpret_cast<float4*>(x_lo_out + (size_t)row * F + lane * 4) = make_float4(tf32_lo(acc[r][0]), tf32_lo(acc[r][1]), tf32_lo(acc[r][2]), tf32_lo(acc[r][3]));
+    }
   }
 }
 
@@ -166,8 +171,8 @@ proj_kernel(int M, const float* __restrict__ x, const float* __restrict__ Wcat, 
 
 // ------------------------------------------------------------------------------------------ block tail
 __global__ void __launch_bounds__(RT_THREADS, 2)
-tail_kernel(int M, const float* __restrict__ feat, const float* __restrict__ x, const uint8_t* __restrict__ mask,
-            BlockW w, float* __restrict__ x_out) {
+tail_kernel(int M, const float* __restrict__ feat, const float* __restrict__ pre, const float* __restrict__ x,
+            const uint8_t* __restrict__ mask, BlockW w, float* __restrict__ x_out, float* __restrict__ x_lo_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RowTileSmem& s = *reinterpret_cast<RowTileSmem*>(smem_raw);
   float* act = reinterpret_cast<float*>(smem_raw + sizeof(RowTileSmem));      // [64][RT_ACT_LD]
@@ -176,10 +181,21 @@ tail_kernel(int M, const float* __restrict__ feat, const float* __restrict__ x, 
 
   float acc[8][4], h[8][4];
   rt_zero(acc);
-  rt_gemm_globalA(acc, s, [&](int r, int k) -> const float* {
-    return (row0 + r < M) ? feat + (size_t)(row0 + r) * NFEAT + k : nullptr;
-  }, w.Wout_t, NFEAT);
-  rt_add_bias(acc, w.bout);
+  if (pre != nullptr) {          // out_transform (+ bias) already done by the tcgen05 GEMM
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int row = row0 + warp * 8 + r;
+      if (row < M) {
+        const float4 v = *reinterpret_cast<const float4*>(pre + (size_t)row * F + lane * 4);
+        acc[r][0] = v.x; acc[r][1] = v.y; acc[r][2] = v.z; acc[r][3] = v.w;
+      }
+    }
+  } else {
+    rt_gemm_globalA(acc, s, [&](int r, int k) -> const float* {
+      return (row0 + r < M) ? feat + (size_t)(row0 + r) * NFEAT + k : nullptr;
+    }, w.Wout_t, NFEAT);
+    rt_add_bias(acc, w.bout);
+  }
   // mask_zero (layers.py:6-7) then residual + LayerNorm 1
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
@@ -215,7 +231,11 @@ tail_kernel(int M, const float* __restrict__ feat, const float* __restrict__ x, 
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const int row = row0 + warp * 8 + r;
-    if (row < M) *reinterpret_cast<float4*>(x_out + (size_t)row * F + lane * 4) = make_float4(h[r][0], h[r][1], h[r][2], h[r][3]);
+    if (row < M) {
+      *reinterpret_cast<float4*>(x_out + (size_t)row * F + lane * 4) = make_float4(h[r][0], h[r][1], h[r][2], h[r][3]);
+      if (x_lo_out != nullptr)
+        *reinterpret_cast<float4*>(x_lo_out + (size_t)row * F + lane * 4) = make_float4(tf32_lo(h[r][0]), tf32_lo(h[r][1]), tf32_lo(h[r][2]), tf32_lo(h[r][3]));
+    }
   }
 }
 
@@ -392,19 +412,20 @@ cudaError_t linear_kernels_init() {
 
 void launch_mixer(int M, const float* res_feat, const long long* s_t, const float* v_t, const EpsW& w,
                   float* x_out, float* Rbuf, const float* p_ang, float* p_norm, const float* mean, float scale,
-                  cudaStream_t st) {
+                  float* x_lo_out, cudaStream_t st) {
   ProfScope prof__(KK_MIXER, st);
   mixer_kernel<<<(M + RT_ROWS - 1) / RT_ROWS, RT_THREADS, mixer_smem(), st>>>(M, res_feat, s_t, v_t, w, x_out, Rbuf, p_ang, p_norm,
-                                                                           mean[0], mean[1], mean[2], scale);
+                                                                           mean[0], mean[1], mean[2], scale, x_lo_out);
 }
 void launch_proj(int M, const float* x, const float* Wcat, const float* R, const float* t, float* proj, cudaStream_t st) {
   ProfScope prof__(KK_PROJ, st);
   dim3 grid(NPROJ / PJ_BN, (M + PJ_BM - 1) / PJ_BM);
   proj_kernel<<<grid, PJ_THREADS, 0, st>>>(M, x, Wcat, R, t, proj);
 }
-void launch_tail(int M, const float* feat, const float* x, const uint8_t* mask, const BlockW& w, float* x_out, cudaStream_t st) {
+void launch_tail(int M, const float* feat, const float* pre, const float* x, const uint8_t* mask, const BlockW& w, float* x_out,
+                 float* x_lo_out, cudaStream_t st) {
   ProfScope prof__(KK_TAIL, st);
-  tail_kernel<<<(M + RT_ROWS - 1) / RT_ROWS, RT_THREADS, tail_smem(), st>>>(M, feat, x, mask, w, x_out);
+  tail_kernel<<<(M + RT_ROWS - 1) / RT_ROWS, RT_THREADS, tail_smem(), st>>>(M, feat, pre, x, mask, w, x_out, x_lo_out);
 }
 void launch_heads(int M, int L, const float* x, const float* beta, int beta_stride, const float* Rbuf, const float* v_t,
                   const uint8_t* mask_gen, const EpsW& w, float* v_next, float* R_next, float* eps_pos, float* c_den,

@@ -72,6 +72,7 @@ struct PairStreamArgs {
   const float* logits;            // [chunk complex][h][i][Lp]  final (scaled, masked) logits from logits_kernel
   float* alpha;                   // [chunk complex][h][i][Lp]
   float* feat;
+  float* feat_lo;                 // tf32 "lo" plane of feat for the out_transform tensor-core GEMM
   float* bias;                    // pair_bias_kernel output [complex][h][i][Lp]
 };
 
@@ -206,10 +207,11 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap zmap, const PairStreamArg
   for (int row = blockIdx.x; row < a.nrows; row += gridDim.x) {
     const int bl = row / L, i = row - bl * L, b = a.b0 + bl;
     float* feat_row = a.feat + ((size_t)b * L + i) * NFEAT;
+    float* feat_lo_row = a.feat_lo + ((size_t)b * L + i) * NFEAT;
     if (row != live) {
       // masked query: alpha row = 0 (ga.py:25) -> zero pair aggregate
       float* alpha_row0 = a.alpha + ((size_t)(bl * H) * L + i) * Lp;
-      for (int o = tid; o < H * C; o += PS_THREADS) feat_row[o] = 0.f;
+      for (int o = tid; o < H * C; o += PS_THREADS) { feat_row[o] = 0.f; feat_lo_row[o] = 0.f; }
       for (int o = tid; o < H * Lp; o += PS_THREADS) {
         const int h = o / Lp, j = o - h * Lp;
         alpha_row0[(size_t)h * L * Lp + j] = 0.f;
@@ -319,6 +321,7 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap zmap, const PairStreamArg
         sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
       }
       *reinterpret_cast<float4*>(feat_row + tid * 4) = sum;
+      *reinterpret_cast<float4*>(feat_lo_row + tid * 4) = make_float4(tf32_lo(sum.x), tf32_lo(sum.y), tf32_lo(sum.z), tf32_lo(sum.w));
     }
     // generic-proxy accesses to this stage must be ordered before the next TMA (async proxy) write into it
     fence_async_smem();
@@ -380,14 +383,14 @@ bool launch_pair_bias(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, in
 }
 
 bool launch_pair_stream(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, int box_rows, const uint8_t* mask, const float* logits,
-                        float* alpha, float* feat, cudaStream_t st) {
+                        float* alpha, float* feat, float* feat_lo, cudaStream_t st) {
   ProfScope prof__(KK_PAIR, st);
   if (L > 32 * 4 * PS_MAXF) return false;
   PairStreamArgs a{};
   size_t smem = 0;
   const int Lq = (L + 3) & ~3;
   if (!fill_args(a, nb, b0, L, Lp, box_rows, (size_t)H * Lq * 4 + 8 * 8 + 1024, &smem)) return false;
-  a.mask = mask; a.logits = logits; a.alpha = alpha; a.feat = feat;
+  a.mask = mask; a.logits = logits; a.alpha = alpha; a.feat = feat; a.feat_lo = feat_lo;
   int grid = g_sm_count > 0 ? g_sm_count : 148;
   if (grid > a.nrows) grid = a.nrows;
   pair_stream_kernel<<<grid, PS_THREADS, smem, st>>>(zmap, a);

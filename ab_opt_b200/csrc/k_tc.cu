@@ -9,6 +9,9 @@
 //   warp 0      : TMA producer  -- cp.async.bulk.tensor, 128B-swizzled [rows][32 tf32] boxes, mbarrier expect_tx
 //   warp 1      : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma.kind::tf32, commits to mbarriers)
 //   warps 2..5  : epilogue      -- tcgen05.ld (thread = output row), fused epilogue functor, global stores
+#include <map>
+#include <mutex>
+#include <tuple>
 #include "tc.cuh"
 #include "params.cuh"
 #include "kernels.h"
@@ -206,16 +209,26 @@ cudaError_t tc_init() {
   return cudaSuccess;
 }
 
-// 2-D fp32 row-major [rows][cols] with row pitch ld (floats); box = [box_rows][32 floats], 128 B swizzle
+// 2-D fp32 row-major [rows][cols] with row pitch ld (floats); box = [box_rows][32 floats], 128 B swizzle.
+// Descriptors are cached per (address, shape): the workspace buffers and weights they describe are long-lived, and
+// encoding costs a few microseconds of host time per call.
+struct TmapKey {
+  const void* base; uint64_t rows, cols, ld; uint32_t box_rows;
+  bool operator<(const TmapKey& o) const {
+    return std::tie(base, rows, cols, ld, box_rows) < std::tie(o.base, o.rows, o.cols, o.ld, o.box_rows);
+  }
+};
+static std::map<TmapKey, CUtensorMap> g_tmaps;
+static std::mutex g_tmaps_mu;
 bool make_tmap(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * sizeof(float)};
-  cuuint32_t box[2] = {G_BK, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
+  std::lock_guard<std::mutex> lk(g_tmaps_mu);
+  const TmapKey key{base, rows, cols, ld, box_rows};
+  auto it = g_tmaps.find(key);
+  if (it != g_tmaps.end()) { *m = it->second; return true; }
+  if (!make_tmap_2d(m, base, rows, cols, ld, box_rows, G_BK)) return false;
+  if (g_tmaps.size() > 4096) g_tmaps.clear();
+  g_tmaps[key] = *m;
+  return true;
 }
 
 bool make_tmap_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
@@ -236,6 +249,24 @@ __global__ void split_kernel(const float* __restrict__ in, float* __restrict__ h
     split_tf32(in[i], h, l);
     hi[i] = h; lo[i] = l;
   }
+}
+// lo = x - trunc_tf32(x): the second operand plane of the 3xTF32 scheme.  The FIRST plane is the raw fp32 tensor itself:
+// tcgen05.mma.kind::tf32 ignores the low 13 mantissa bits of its 32-bit inputs, i.e. it sees trunc_tf32(x).
+__global__ void lo_kernel(const float4* __restrict__ in, float4* __restrict__ lo, size_t n4) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = in[i];
+    float h, l0, l1, l2, l3;
+    split_tf32(v.x, h, l0); split_tf32(v.y, h, l1); split_tf32(v.z, h, l2); split_tf32(v.w, h, l3);
+    lo[i] = make_float4(l0, l1, l2, l3);
+  }
+}
+void launch_lo(const float* in, float* lo, size_t n, cudaStream_t st) {      // n % 4 == 0
+  ProfScope prof__(KK_OTHER, st);
+  const size_t n4 = n / 4;
+  int grid = (int)((n4 + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (grid < 1) grid = 1;
+  lo_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(lo), n4);
 }
 void launch_split(const float* in, float* hi, float* lo, size_t n, cudaStream_t st) {
   ProfScope prof__(KK_OTHER, st);

@@ -36,6 +36,7 @@ cudaError_t linear_kernels_init();
 cudaError_t attn_kernels_init();
 cudaError_t tc_init();
 void launch_split(const float* in, float* hi, float* lo, size_t n, cudaStream_t st);
+void launch_lo(const float* in, float* lo, size_t n, cudaStream_t st);
 bool launch_gemm3x_plain(int M, int N, int K, const float* Ah, const float* Al, int lda, const float* Bh, const float* Bl, int ldb,
                          float* D, int ldd, const float* bias, cudaStream_t st);
 bool launch_proj_tc(int M, const float* xh, const float* xl, const float* Wh, const float* Wl, const float* R, const float* t,
@@ -43,9 +44,10 @@ bool launch_proj_tc(int M, const float* xh, const float* xl, const float* Wh, co
 
 void launch_mixer(int M, const float* res_feat, const long long* s_t, const float* v_t, const EpsW& w,
                   float* x_out, float* Rbuf, const float* p_ang, float* p_norm, const float* mean, float scale,
-                  cudaStream_t st);
+                  float* x_lo_out, cudaStream_t st);
 void launch_proj(int M, const float* x, const float* Wcat, const float* R, const float* t, float* proj, cudaStream_t st);
-void launch_tail(int M, const float* feat, const float* x, const uint8_t* mask, const BlockW& w, float* x_out, cudaStream_t st);
+void launch_tail(int M, const float* feat, const float* pre, const float* x, const uint8_t* mask, const BlockW& w, float* x_out,
+                 float* x_lo_out, cudaStream_t st);
 void launch_heads(int M, int L, const float* x, const float* beta, int beta_stride, const float* Rbuf, const float* v_t,
                   const uint8_t* mask_gen, const EpsW& w, float* v_next, float* R_next, float* eps_pos, float* c_den,
                   float* prmsd_rows, float* prmsd_logits, cudaStream_t st);
@@ -53,7 +55,7 @@ void launch_heads(int M, int L, const float* x, const float* beta, int beta_stri
 void launch_logits(int nb, int L, int Lp, const float* proj_chunk, const float* coef, const float* bias_chunk,
                    const uint8_t* mask_chunk, float* S, cudaStream_t st);
 void launch_aggr(int nb, int b0, int L, int Lp, const float* alpha, const float* proj, const float* R, const float* t,
-                 float* feat, cudaStream_t st);
+                 float* feat, float* feat_lo, cudaStream_t st);
 void launch_alpha_tap(int nb, int b0, int L, int Lp, const float* alpha, float* out, cudaStream_t st);
 // pair_stream_kernel (k_pair.cu): TMA-fed persistent replacement of pair_kernel
 cudaError_t pair_stream_init();
@@ -62,7 +64,7 @@ bool make_pair_tmap(CUtensorMap* m, const float* z, size_t total_rows, int* box_
 bool launch_pair_bias(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, int box_rows, const PairBiasPacked& pb, float* bias,
                       cudaStream_t st);
 bool launch_pair_stream(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, int box_rows, const uint8_t* mask, const float* logits,
-                        float* alpha, float* feat, cudaStream_t st);
+                        float* alpha, float* feat, float* feat_lo, cudaStream_t st);
 
 void launch_angle_argmax(int M, int L, const long long* tvec, int t_uniform, const float* Y, const float* expo,
                          const uint8_t* mask_gen, int* bin_idx, cudaStream_t st);

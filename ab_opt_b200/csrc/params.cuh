@@ -7,6 +7,9 @@ namespace abopt {
 // One GABlock (modules/encoders/ga.py:41-79).  "t" suffix = stored K-major (transposed nn.Linear weight).
 struct BlockW {
   const float* Wcat;       // [2016][128]  rows: proj_query | proj_key | proj_value | proj_query_point | proj_key_point | proj_value_point
+  const float* Wcat_lo;    // [2016][128]  tf32 "lo" plane of Wcat (3xTF32 tensor-core GEMM)
+  const float* Wout;       // [128][1824]  out_transform.weight as stored by nn.Linear (K-major B operand)
+  const float* Wout_lo;    // [128][1824]
   const float* Wb;         // [64][12]     proj_pair_bias.weight transposed (c-major)
   const float* coef;       // [12]         -softplus(spatial_coef) * sqrt(2/(9*8)) / 2
   const float* Wout_t;     // [1824][128]  out_transform.weight^T
