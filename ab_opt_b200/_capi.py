@@ -21,7 +21,7 @@ EXPORTS = (
     'abopt_model_destroy', 'abopt_model_set_tensor', 'abopt_model_finalize', 'abopt_ga_block_forward',
     'abopt_ga_encoder_forward', 'abopt_ga_block_taps', 'abopt_eps_net_forward', 'abopt_rot_denoise',
     'abopt_pos_pred_noise_from_start', 'abopt_pos_denoise', 'abopt_seq_denoise', 'abopt_sample_device',
-    'abopt_sample_host', 'abopt_workspace_bytes', 'abopt_sample_init', 'abopt_reverse_step', 'abopt_profile_enable', 'abopt_profile_collect', 'abopt_debug_gemm3x',
+    'abopt_sample_host', 'abopt_workspace_bytes', 'abopt_sample_init', 'abopt_reverse_step', 'abopt_profile_enable', 'abopt_profile_collect', 'abopt_debug_gemm3x', 'abopt_debug_clocks',
 )
 
 

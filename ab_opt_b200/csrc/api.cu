@@ -61,6 +61,7 @@ struct Workspace {
   int N = 0, L = 0, Lp = 0, NB = 0;
   size_t bytes = 0;
   void* base = nullptr;
+  AttnOperands op;
   float *Rbuf, *pnorm, *xa, *xb, *xa_lo, *xb_lo, *xin_lo, *proj, *feat, *feat_lo, *outD, *S, *alpha, *prmsd_rows, *prmsd_logits, *maxprob;
   float *v_net, *eps_pos, *c_den, *R_next;
   int* bin_idx;
@@ -174,6 +175,13 @@ extern "C" int abopt_debug_gemm3x(int device, int M, int N, int K, const float* 
   CHECK_LAUNCH();
   return ABOPT_OK;
 }
+// Debug: SM-clock timestamps of the phases of CTA (0,0,0) of the last attn_logits_tc_kernel launch (synchronises).
+extern "C" int abopt_debug_clocks(long long* out16) {
+  if (!out16) return fail(ABOPT_ERR_ARG, "null argument");
+  CUDA_TRY(cudaDeviceSynchronize());
+  attn_debug_clocks(out16);
+  return ABOPT_OK;
+}
 extern "C" int abopt_profile_enable(int on) {
   for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   g_prof.clear();
@@ -213,6 +221,7 @@ extern "C" int abopt_model_create(const abopt_config* cfg, int device, abopt_mod
   CUDA_TRY(attn_kernels_init());
   CUDA_TRY(tc_init());
   CUDA_TRY(pair_stream_init());
+  CUDA_TRY(attn_tc_init());
   abopt_model* m = new abopt_model();
   m->cfg = *cfg;
   m->device = device;
@@ -439,7 +448,7 @@ static int ensure_workspace(abopt_model* m, int N, int L) {
   Workspace& w = m->ws;
   if (w.base && w.N >= N && w.L == L) return ABOPT_OK;
   if (w.base) { CUDA_TRY(cudaFree(w.base)); w.base = nullptr; }
-  const int Lp = (L + 3) & ~3;
+  const int Lp = (L + 7) & ~7;      // row pitch of the attention tensors: 32-byte aligned rows (256-bit stores)
   const int NB = chunk_size(N, L, Lp);
   const size_t M = (size_t)N * L;
   const int bins = m->cfg.has_prmsd ? m->cfg.prmsd_bins : 1;
@@ -450,7 +459,8 @@ static int ensure_workspace(abopt_model* m, int N, int L) {
                oAl = take((size_t)NB * H * L * Lp * 4), oPr = take(M * bins * 4), oPl = take((size_t)N * bins * 4),
                oMp = take(M * 4), oVn = take(M * 3 * 4), oEp = take(M * 3 * 4), oCd = take(M * NAA * 4), oRn = take(M * 9 * 4),
                oBi = take(M * 4), oTv = take((size_t)N * 8), oXal = take(M * F * 4), oXbl = take(M * F * 4), oXil = take(M * F * 4),
-               oFl = take(M * NFEAT * 4), oOd = take(M * F * 4);
+               oFl = take(M * NFEAT * 4), oOd = take(M * F * 4), oQa = take(M * H * 64 * 4), oQl = take(M * H * 64 * 4),
+               oKb = take(M * H * 64 * 4), oKl = take(M * H * 64 * 4), oRq = take(M * H * 4), oRk = take(M * H * 4);
   CUDA_TRY(cudaMalloc(&w.base, off));
   unsigned char* b = static_cast<unsigned char*>(w.base);
   w.Rbuf = (float*)(b + oR); w.pnorm = (float*)(b + oP); w.xa = (float*)(b + oXa); w.xb = (float*)(b + oXb);
@@ -460,6 +470,7 @@ static int ensure_workspace(abopt_model* m, int N, int L) {
   w.bin_idx = (int*)(b + oBi); w.tvec_scratch = (long long*)(b + oTv);
   w.xa_lo = (float*)(b + oXal); w.xb_lo = (float*)(b + oXbl); w.xin_lo = (float*)(b + oXil); w.feat_lo = (float*)(b + oFl);
   w.outD = (float*)(b + oOd);
+  w.op = AttnOperands{(float*)(b + oQa), (float*)(b + oQl), (float*)(b + oKb), (float*)(b + oKl), (float*)(b + oRq), (float*)(b + oRk)};
   w.N = N; w.L = L; w.Lp = Lp; w.NB = NB; w.bytes = off;
   return ABOPT_OK;
 }
@@ -487,7 +498,7 @@ static int ensure_pair_inputs(abopt_model* m, int N, int L, const float* z, size
     if (!make_pair_tmap(&m->zmap, z, (size_t)N * L * L, &m->zmap_box_rows)) return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed for pair_feat");
     m->zmap_ptr = z; m->zmap_N = N; m->zmap_L = L;
   }
-  const size_t slot_floats = (size_t)N * H * L * ((L + 3) & ~3);
+  const size_t slot_floats = (size_t)N * H * L * ((L + 7) & ~7);
   if (!m->bias_buf || m->bias_slot_floats != slot_floats || m->bias_slots < slots) {
     if (m->bias_buf) { CUDA_TRY(cudaFree(m->bias_buf)); m->bias_buf = nullptr; }
     CUDA_TRY(cudaMalloc(&m->bias_buf, slots * slot_floats * sizeof(float)));
@@ -509,11 +520,19 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
     return fail(ABOPT_ERR_ARG, "pair_bias_kernel: L too large for shared memory");
   // the six input projections: tcgen05 3xTF32 GEMM (x raw = "hi" plane, x_lo = "lo" plane)
   if (x_lo == nullptr) { launch_lo(x, w.xin_lo, (size_t)M * F, st); x_lo = w.xin_lo; }
-  if (!launch_proj_tc(M, x, x_lo, bw.Wcat, bw.Wcat_lo, R, t, w.proj, st)) return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (proj)");
   for (int b0 = 0; b0 < N; b0 += w.NB) {
     const int nb = (N - b0 < w.NB) ? (N - b0) : w.NB;
-    launch_logits(nb, L, w.Lp, w.proj + (size_t)b0 * L * NPROJ, bw.coef, bias + (size_t)b0 * H * L * w.Lp, mask + (size_t)b0 * L, w.S, st);
-    if (!launch_pair_stream(nb, b0, L, w.Lp, m->zmap, m->zmap_box_rows, mask, w.S, w.alpha, w.feat, w.feat_lo, st))
+    // everything a chunk of complexes produces and consumes below stays L2 resident: its projections (packed attention
+    // operands), its attention weights, its aggregates; only z and the pair bias stream from HBM
+    {
+      const size_t r0 = (size_t)b0 * L, o64 = (size_t)b0 * H * L * 64, o1 = (size_t)b0 * H * L;
+      const AttnOperands opc{w.op.QA + o64, w.op.QA_lo + o64, w.op.KB + o64, w.op.KB_lo + o64, w.op.rq + o1, w.op.rk + o1};
+      if (!launch_proj_pack(nb * L, L, x + r0 * F, x_lo + r0 * F, bw.Wcat, bw.Wcat_lo, R + r0 * 9, t + r0 * 3, bw.coef, w.proj + r0 * NPROJ, opc, st))
+        return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (proj)");
+    }
+    // logits (node + spatial + pair bias, scaled, masked) and softmax on the tensor cores -> alpha (L2 resident chunk)
+    if (!launch_attn_logits_tc(nb, b0, N, L, w.Lp, w.op, bias, mask, w.alpha, st)) return fail(ABOPT_ERR_CUDA, "attn_logits_tc launch failed");
+    if (!launch_pair_stream(nb, b0, L, w.Lp, m->zmap, m->zmap_box_rows, mask, w.alpha, w.feat, w.feat_lo, st))
       return fail(ABOPT_ERR_ARG, "pair_stream_kernel: L too large for shared memory");
     launch_aggr(nb, b0, L, w.Lp, w.alpha, w.proj, R, t, w.feat, w.feat_lo, st);
     if (alpha_tap) launch_alpha_tap(nb, b0, L, w.Lp, w.alpha, alpha_tap, st);

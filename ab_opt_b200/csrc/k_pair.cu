@@ -69,11 +69,11 @@ struct PairStreamArgs {
   int L, Lp, b0, nrows;           // nrows = complexes covered by this launch * L; b0 = first complex
   int nstage, stage_bytes, tile_tx_bytes, nbox_rows;   // nbox_rows = 64-row boxes per row-block
   const uint8_t* mask;
-  const float* logits;            // [chunk complex][h][i][Lp]  final (scaled, masked) logits from logits_kernel
-  float* alpha;                   // [chunk complex][h][i][Lp]
+  float* alpha;                   // [chunk complex][h][i][Lp]  attention weights from attn_logits_tc_kernel (rows of masked
+                                  // queries are zeroed here, ga.py:25)
   float* feat;
   float* feat_lo;                 // tf32 "lo" plane of feat for the out_transform tensor-core GEMM
-  float* bias;                    // pair_bias_kernel output [complex][h][i][Lp]
+  float* bias;                    // pair_bias_kernel output, transposed: [complex][h][j][Lp] (query index i contiguous)
 };
 
 // ---- TMA producer shared by both kernels: thread 0 walks the CTA's rows (blockIdx.x, + gridDim.x, ...) and loads
@@ -102,7 +102,7 @@ struct TileProducer {
 };
 
 // ------------------------------------------------------------------------------------------ pair bias
-// bias[b][h][i][j] = z[b,i,j,:] . W_b[h,:]   (ga.py:88-90).  z and W_b do not change over the T reverse steps, so
+// bias(b, h, i, j) = z[b,i,j,:] . W_b[h,:]   (ga.py:88-90).  z and W_b do not change over the T reverse steps, so
 // FullDPM.sample runs this ONCE per layer per sampling run (api.cu) instead of once per layer per step.
 // thread = (key residue j, 6 of the 12 heads); the head half is warp-uniform so the weight pairs are uniform-register
 // operands of FFMA2 (fma.rn.f32x2: scalar z  x  (W[c][h], W[c][h+1])).
@@ -150,7 +150,10 @@ pair_bias_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant
           }
         };
         if (ch == 0) body(std::integral_constant<int, 0>{}); else body(std::integral_constant<int, 1>{});
-        float* dst = a.bias + ((size_t)(b * H + ch * (H / 2)) * L + i) * Lp + j;
+        // stored TRANSPOSED, bias[b][h][j][i] (query index contiguous): attn_logits_tc_kernel's epilogue threads are
+        // query rows, so a warp reads 32 consecutive i of one key j in one coalesced request.  The scattered 4-byte
+        // stores here happen once per sampling run and merge in L2 (neighbouring i are written by neighbouring CTAs).
+        float* dst = a.bias + ((size_t)(b * H + ch * (H / 2)) * L + j) * Lp + i;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           dst[(size_t)(2 * k) * L * Lp] = acc[0][k].x + acc[1][k].x;
@@ -165,7 +168,7 @@ pair_bias_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------ softmax + pair aggregation
-constexpr int PS_MAXF = 5;        // float4 groups of a logits row per lane: L <= 32 * 4 * 5 = 640
+constexpr int PS_MAXF = 4;        // float4 groups of an alpha row per lane: L <= 32 * 4 * 4 = 512
 
 __global__ void __launch_bounds__(PS_THREADS, 1)
 pair_stream_kernel(const __grid_constant__ CUtensorMap zmap, const PairStreamArgs a) {
@@ -190,14 +193,14 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap zmap, const PairStreamArg
 
   auto masked = [&](int row) { const int bl = row / L; return a.mask[(size_t)(a.b0 + bl) * L + (row - bl * L)] == 0; };
   auto next_live = [&](int row) { while (row < a.nrows && masked(row)) row += gridDim.x; return row; };
-  // logits of one query row, one warp per head, lane-strided float4 groups (prefetched one row ahead)
+  // alpha of one query row, one warp per head, lane-strided float4 groups (prefetched one row ahead)
   float4 lg[PS_MAXF];
   auto load_logits = [&](int row) {
     if (warp < H && row < a.nrows) {
       const int bl = row / L, i = row - bl * L;
-      const float4* src = reinterpret_cast<const float4*>(a.logits + ((size_t)(bl * H + warp) * L + i) * Lp);
+      const float4* src = reinterpret_cast<const float4*>(a.alpha + ((size_t)(bl * H + warp) * L + i) * Lp);
 #pragma unroll
-      for (int m = 0; m < PS_MAXF; ++m) { const int f = lane + 32 * m; if (f < nf) lg[m] = __ldg(src + f); }
+      for (int m = 0; m < PS_MAXF; ++m) { const int f = lane + 32 * m; if (f < nf) lg[m] = src[f]; }
     }
   };
   int live = next_live(blockIdx.x);
@@ -223,46 +226,13 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap zmap, const PairStreamArg
     ++n;
     const unsigned char* zs = stages + (size_t)s * a.stage_bytes;
 
-    // ---- softmax over j (ga.py:24), one warp per head; alpha -> L2 (for aggr_kernel) and -> shared [h][j]
+    // ---- alpha[h][:] of this query row (prefetched registers) -> shared, regrouped as [4 residues][head][4]
     if (warp < H) {
-      float m = -INFINITY;
+      float4* dsts = reinterpret_cast<float4*>(als) + warp;
 #pragma unroll
       for (int k = 0; k < PS_MAXF; ++k) {
         const int f = lane + 32 * k;
-        if (f < nf) {
-          const int j = 4 * f;                             // entries j >= L of the last group are padding
-          if (j + 1 >= L) lg[k].y = -INFINITY;
-          if (j + 2 >= L) lg[k].z = -INFINITY;
-          if (j + 3 >= L) lg[k].w = -INFINITY;
-          m = fmaxf(fmaxf(m, fmaxf(lg[k].x, lg[k].y)), fmaxf(lg[k].z, lg[k].w));
-        }
-      }
-      m = warp_max(m);
-      // exp(x - m) = 2^(x log2e - m log2e): one FFMA + MUFU.EX2 per element (<= 2 ulp of the exact value near the
-      // row maximum, where the attention mass is)
-      const float l2e = 1.4426950408889634f, ml2e = m * l2e;
-      float sum = 0.f;
-#pragma unroll
-      for (int k = 0; k < PS_MAXF; ++k) {
-        const int f = lane + 32 * k;
-        if (f < nf) {
-          lg[k].x = exp2f(fmaf(lg[k].x, l2e, -ml2e)); lg[k].y = exp2f(fmaf(lg[k].y, l2e, -ml2e));
-          lg[k].z = exp2f(fmaf(lg[k].z, l2e, -ml2e)); lg[k].w = exp2f(fmaf(lg[k].w, l2e, -ml2e));
-          sum += (lg[k].x + lg[k].y) + (lg[k].z + lg[k].w);
-        }
-      }
-      sum = warp_sum(sum);
-      const float inv = 1.0f / sum;
-      float4* dstg = reinterpret_cast<float4*>(a.alpha + ((size_t)(bl * H + warp) * L + i) * Lp);
-      float4* dsts = reinterpret_cast<float4*>(als) + warp;            // [group of 4 residues][head][4]
-#pragma unroll
-      for (int k = 0; k < PS_MAXF; ++k) {
-        const int f = lane + 32 * k;
-        if (f < nf) {
-          const float4 o = make_float4(lg[k].x * inv, lg[k].y * inv, lg[k].z * inv, lg[k].w * inv);
-          dstg[f] = o;
-          dsts[f * H] = o;
-        }
+        if (f < nf) dsts[f * H] = lg[k];
       }
     }
     live = next_live(row + gridDim.x);
@@ -382,7 +352,7 @@ bool launch_pair_bias(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, in
   return true;
 }
 
-bool launch_pair_stream(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, int box_rows, const uint8_t* mask, const float* logits,
+bool launch_pair_stream(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, int box_rows, const uint8_t* mask,
                         float* alpha, float* feat, float* feat_lo, cudaStream_t st) {
   ProfScope prof__(KK_PAIR, st);
   if (L > 32 * 4 * PS_MAXF) return false;
@@ -390,7 +360,7 @@ bool launch_pair_stream(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, 
   size_t smem = 0;
   const int Lq = (L + 3) & ~3;
   if (!fill_args(a, nb, b0, L, Lp, box_rows, (size_t)H * Lq * 4 + 8 * 8 + 1024, &smem)) return false;
-  a.mask = mask; a.logits = logits; a.alpha = alpha; a.feat = feat; a.feat_lo = feat_lo;
+  a.mask = mask; a.alpha = alpha; a.feat = feat; a.feat_lo = feat_lo;
   int grid = g_sm_count > 0 ? g_sm_count : 148;
   if (grid > a.nrows) grid = a.nrows;
   pair_stream_kernel<<<grid, PS_THREADS, smem, st>>>(zmap, a);

@@ -75,6 +75,84 @@ struct EpiProj {
   }
 };
 
+// GABlock projections, packed for the tensor-core attention kernels (k_attn_tc.cu).  Per (complex b, head h, residue r):
+//   QA[b][h][r][64] = [ q / sqrt(32) (32) | global query points (24) | 0 (8) ]                    ga.py:82-85,96-99
+//   KB[b][h][r][64] = [ k (32)            | -2 c_h * global key points (24) | 0 (8) ]             ga.py:83,102-105
+//   rq[b][h][r] = c_h |query points|^2,  rk[b][h][r] = c_h |key points|^2,   c_h = -softplus(coef_h) sqrt(2/(9*8)) / 2
+// so that  QA . KB + rq + rk = node logits + spatial logits  (|q - k|^2 expanded; ga.py:108-111).  Every tensor also gets
+// its tf32 "lo" plane.  Value channels and value points keep the plain proj layout (aggr_kernel reads them).
+struct EpiProjPack {
+  float* proj; const float* R; const float* t; const float* coef;
+  float* QA; float* QA_lo; float* KB; float* KB_lo; float* rq; float* rk;
+  int L;
+  template <int BN>
+  __device__ __forceinline__ void operator()(int row, int n0, int N, float (&v)[BN]) const {
+    static_assert(BN == 96, "tile = 3 heads of 32 channels or 4 heads of 8 points");
+    const int b = row / L, r = row - b * L;
+    if (n0 < OFF_V) {                                   // q or k channels: heads n0 / 32 ...
+      const bool is_q = n0 < OFF_K;
+      const int h0 = (is_q ? n0 : n0 - OFF_K) / D;
+      const float sc = is_q ? 0.17677669529663687f : 1.f;               // 1 / sqrt(32) folded into q
+      float* dst = is_q ? QA : KB;
+      float* dlo = is_q ? QA_lo : KB_lo;
+#pragma unroll
+      for (int hh = 0; hh < 3; ++hh) {
+        const size_t o = ((size_t)(b * H + h0 + hh) * L + r) * 64;
+#pragma unroll
+        for (int c = 0; c < D; c += 4) {
+          const float4 w = make_float4(v[hh * D + c] * sc, v[hh * D + c + 1] * sc, v[hh * D + c + 2] * sc, v[hh * D + c + 3] * sc);
+          *reinterpret_cast<float4*>(dst + o + c) = w;
+          *reinterpret_cast<float4*>(dlo + o + c) = make_float4(tf32_lo(w.x), tf32_lo(w.y), tf32_lo(w.z), tf32_lo(w.w));
+        }
+      }
+      return;
+    }
+    if (n0 >= OFF_QP) {                                 // points: local -> global, q = R p + t (geometry.py:72-91)
+      float Rm[9], tv[3];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Rm[i] = __ldg(R + (size_t)row * 9 + i);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) tv[i] = __ldg(t + (size_t)row * 3 + i);
+#pragma unroll
+      for (int p = 0; p < BN; p += 3) {
+        const float x = v[p], y = v[p + 1], z = v[p + 2];
+        v[p + 0] = Rm[0] * x + Rm[1] * y + Rm[2] * z + tv[0];
+        v[p + 1] = Rm[3] * x + Rm[4] * y + Rm[5] * z + tv[1];
+        v[p + 2] = Rm[6] * x + Rm[7] * y + Rm[8] * z + tv[2];
+      }
+      if (n0 < OFF_VP) {                                // query / key points -> QA / KB columns 32..63 + norm terms
+        const bool is_q = n0 < OFF_KP;
+        const int h0 = (is_q ? n0 - OFF_QP : n0 - OFF_KP) / (P * 3);
+        float* dst = is_q ? QA : KB;
+        float* dlo = is_q ? QA_lo : KB_lo;
+        float* rn = is_q ? rq : rk;
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) {
+          const float ch = __ldg(coef + h0 + hh);
+          const float sc = is_q ? 1.f : -2.f * ch;
+          float n2 = 0.f;
+#pragma unroll
+          for (int c = 0; c < P * 3; ++c) n2 = fmaf(v[hh * P * 3 + c], v[hh * P * 3 + c], n2);
+          rn[(size_t)(b * H + h0 + hh) * L + r] = ch * n2;
+          const size_t o = ((size_t)(b * H + h0 + hh) * L + r) * 64 + D;
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            float w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[e] = (c + e < P * 3) ? v[hh * P * 3 + c + e] * sc : 0.f;
+            *reinterpret_cast<float4*>(dst + o + c) = make_float4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<float4*>(dlo + o + c) = make_float4(tf32_lo(w[0]), tf32_lo(w[1]), tf32_lo(w[2]), tf32_lo(w[3]));
+          }
+        }
+        return;
+      }
+    }
+    float* dst = proj + (size_t)row * NPROJ + n0;        // value channels / global value points: plain layout
+#pragma unroll
+    for (int c = 0; c < BN; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+  }
+};
+
 // Accuracy note (measured on B200, scripts/debug_gemm.py): the tensor core TRUNCATES the fp32 accumulator on every
 // tcgen05.mma, a systematic -2^-24 relative bias per accumulation that grows linearly with K (4e-5 at K = 1824).
 // Two counter-measures keep the result fp32-grade:
@@ -206,6 +284,7 @@ cudaError_t tc_init() {
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(gemm3x_kernel<128, 3, 8, EpiPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<128, 3>::TOTAL)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(gemm3x_kernel<96, 3, 8, EpiProj>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<96, 3>::TOTAL)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(gemm3x_kernel<96, 3, 8, EpiProjPack>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<96, 3>::TOTAL)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -239,6 +318,19 @@ bool make_tmap_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t col
   if (!g_encode) return false;
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// plain (unswizzled) 2-D fp32 tensor map, used for L2 prefetches only
+bool make_tmap_plain(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  if (!g_encode) return false;
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -298,6 +390,20 @@ bool launch_proj_tc(int M, const float* xh, const float* xl, const float* Wh, co
   ProfScope prof__(KK_PROJ, st);
   dim3 grid(NPROJ / 96, (M + G_BM - 1) / G_BM);
   gemm3x_kernel<96, 3, 8, EpiProj><<<grid, G_THREADS, GemmSmem<96, 3>::TOTAL, st>>>(a_h, a_l, b_h, b_l, M, NPROJ, F, EpiProj{proj, R, t});
+  return true;
+}
+
+// same GEMM, outputs packed for the tensor-core attention kernels (see EpiProjPack)
+bool launch_proj_pack(int M, int L, const float* xh, const float* xl, const float* Wh, const float* Wl, const float* R, const float* t,
+                      const float* coef, float* proj, const AttnOperands& op, cudaStream_t st) {
+  CUtensorMap a_h, a_l, b_h, b_l;
+  if (!make_tmap(&a_h, xh, M, F, F, G_BM) || !make_tmap(&a_l, xl, M, F, F, G_BM) || !make_tmap(&b_h, Wh, NPROJ, F, F, 96) ||
+      !make_tmap(&b_l, Wl, NPROJ, F, F, 96))
+    return false;
+  ProfScope prof__(KK_PROJ, st);
+  dim3 grid(NPROJ / 96, (M + G_BM - 1) / G_BM);
+  gemm3x_kernel<96, 3, 8, EpiProjPack><<<grid, G_THREADS, GemmSmem<96, 3>::TOTAL, st>>>(
+      a_h, a_l, b_h, b_l, M, NPROJ, F, EpiProjPack{proj, R, t, coef, op.QA, op.QA_lo, op.KB, op.KB_lo, op.rq, op.rk, L});
   return true;
 }
 

@@ -42,6 +42,22 @@ bool launch_gemm3x_plain(int M, int N, int K, const float* Ah, const float* Al, 
 bool launch_proj_tc(int M, const float* xh, const float* xl, const float* Wh, const float* Wl, const float* R, const float* t,
                     float* proj, cudaStream_t st);
 
+// operands of the tensor-core attention kernels, produced by the projection GEMM epilogue (k_tc.cu: EpiProjPack)
+struct AttnOperands {
+  float* QA; float* QA_lo;      // [N][H][L][64]
+  float* KB; float* KB_lo;      // [N][H][L][64]
+  float* rq; float* rk;         // [N][H][L]
+};
+bool launch_proj_pack(int M, int L, const float* xh, const float* xl, const float* Wh, const float* Wl, const float* R, const float* t,
+                      const float* coef, float* proj, const AttnOperands& op, cudaStream_t st);
+bool make_tmap(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+bool make_tmap_plain(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
+cudaError_t attn_tc_init();
+void attn_debug_clocks(long long* out16);
+// final logits + softmax on the tensor cores: alpha[chunk][h][i][Lp] for complexes [b0, b0 + nb)
+bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOperands& op, const float* bias_layer, const uint8_t* mask,
+                           float* alpha, cudaStream_t st);
+
 void launch_mixer(int M, const float* res_feat, const long long* s_t, const float* v_t, const EpsW& w,
                   float* x_out, float* Rbuf, const float* p_ang, float* p_norm, const float* mean, float scale,
                   float* x_lo_out, cudaStream_t st);
@@ -63,7 +79,7 @@ bool make_tmap_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t col
 bool make_pair_tmap(CUtensorMap* m, const float* z, size_t total_rows, int* box_rows_out);
 bool launch_pair_bias(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, int box_rows, const PairBiasPacked& pb, float* bias,
                       cudaStream_t st);
-bool launch_pair_stream(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, int box_rows, const uint8_t* mask, const float* logits,
+bool launch_pair_stream(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, int box_rows, const uint8_t* mask,
                         float* alpha, float* feat, float* feat_lo, cudaStream_t st);
 
 void launch_angle_argmax(int M, int L, const long long* tvec, int t_uniform, const float* Y, const float* expo,

@@ -42,7 +42,7 @@ extern "C" {
 #define ABOPT_NUM_HEADS      12   /* modules/encoders/ga.py:43                              */
 #define ABOPT_NUM_AA         20   /* modules/diffusion/transition.py:165                    */
 #define ABOPT_ANGLE_BINS   8192   /* modules/common/so3.py:73                               */
-#define ABOPT_MAX_L         640   /* longest complex whose z row-block fits one smem stage   */
+#define ABOPT_MAX_L         512   /* longest complex: one attention row = 512 TMEM columns    */
 
 typedef struct abopt_model abopt_model;
 
@@ -106,6 +106,9 @@ int abopt_profile_collect(double* ms_per_kind, uint64_t* launches_per_kind, int 
  * D[M][N] = A[M][K] * B[N][K]^T (+ bias[N]); device pointers; N % 4 == 0, K % 32 == 0.  Synchronises. */
 int abopt_debug_gemm3x(int device, int M, int N, int K, const float* A, const float* B, const float* bias,
                        float* D, void* stream);
+
+/* Debug hook: SM-clock timestamps of the phases of one CTA of the last attention-logits kernel (16 slots). */
+int abopt_debug_clocks(long long* out16);
 
 /* FullDPM.__init__ : allocate an empty model on CUDA device `device`. */
 int  abopt_model_create(const abopt_config* cfg, int device, abopt_model** out);

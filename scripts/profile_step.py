@@ -33,6 +33,13 @@ def main():
         v, p, s = out[0], out[1], out[2]
     torch.cuda.synchronize()
     print('ok', float(p.abs().mean()))
+    import ctypes
+    from ab_opt_b200 import _capi
+    clk = (ctypes.c_longlong * 16)()
+    _capi.check(_capi.lib().abopt_debug_clocks(clk))
+    t0 = clk[0]
+    names = ['start', 'a_full', 'b_full0', 'b_full1', 'tables', 'tmem_full', 'pass1', 'pass2', 'pass3', 'end']
+    print('attn_logits CTA(0,0,0) timeline [cycles]:', {n: int(clk[k] - t0) for k, n in enumerate(names)})
 
 
 if __name__ == '__main__':

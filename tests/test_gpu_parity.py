@@ -156,7 +156,8 @@ def test_block_vs_oracle_shapes(N, L, ragged):
     enc = model.eps_net.encoder
     alpha, feat = enc.block_taps(0, R.to(DEV), t.to(DEV), ci['res_feat'], ci['pair_feat'], ci['mask_res'])
     out = enc.blocks[0](R.to(DEV), t.to(DEV), ci['res_feat'], ci['pair_feat'], ci['mask_res'])
-    assert_vs_fp64('alpha', alpha, parts['alpha'], parts64['alpha'], 1e-6)
+    # floor: logits come from a 3xTF32 tensor-core GEMM with |q - k|^2 expanded (|q|^2 + |k|^2 - 2 q.k) -> a few 1e-6
+    assert_vs_fp64('alpha', alpha, parts['alpha'], parts64['alpha'], 5e-6)
     # masked query rows: the aggregate is ignored downstream (mask_zero) -> compare valid rows only
     mr = inp['mask_res']
     assert_vs_fp64('feat', feat.cpu()[mr], parts['feat'][mr], parts64['feat'][mr], 2e-5)
