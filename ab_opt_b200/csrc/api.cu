@@ -62,7 +62,7 @@ struct Workspace {
   size_t bytes = 0;
   void* base = nullptr;
   AttnOperands op;
-  float *Rbuf, *pnorm, *xa, *xb, *xa_lo, *xb_lo, *xin_lo, *proj, *feat, *feat_lo, *outD, *S, *alpha, *prmsd_rows, *prmsd_logits, *maxprob;
+  float *Rbuf, *pnorm, *xa, *xb, *xa_lo, *xb_lo, *xin_lo, *feat, *feat_lo, *outD, *alpha, *prmsd_rows, *prmsd_logits, *maxprob;
   float *v_net, *eps_pos, *c_den, *R_next;
   int* bin_idx;
   long long* tvec_scratch;
@@ -222,6 +222,7 @@ extern "C" int abopt_model_create(const abopt_config* cfg, int device, abopt_mod
   CUDA_TRY(tc_init());
   CUDA_TRY(pair_stream_init());
   CUDA_TRY(attn_tc_init());
+  CUDA_TRY(aggr_tc_init());
   abopt_model* m = new abopt_model();
   m->cfg = *cfg;
   m->device = device;
@@ -434,10 +435,11 @@ extern "C" int abopt_model_finalize(abopt_model* m) {
 static int chunk_size(int N, int L, int Lp) {
   const char* env = getenv("ABOPT_CHUNK");
   if (env && atoi(env) > 0) return atoi(env) < N ? atoi(env) : N;
-  // logits + attention weights of a chunk should stay L2 resident (126 MB on B200): budget 56 MB,
-  // then balance the chunks (e.g. N=64, L=256: 8 chunks of 8 rather than 9 x 7 + 1)
-  const double per = 2.0 * H * (double)L * Lp * 4.0;
-  int nb = (int)(56.0 * 1024 * 1024 / per);
+  // Complexes per pass of the attention kernels.  Measured on B200 (profiles/): one pass over the whole batch beats
+  // L2-sized chunks -- the per-launch ramp-up / tail of the persistent kernels costs more than the L2 misses on alpha.
+  // The only cap is memory: the attention weights of a chunk (H * L * Lp floats per complex) stay below 2 GiB.
+  const double per = (double)H * L * Lp * 4.0;
+  int nb = (int)(2.0 * 1024 * 1024 * 1024 / per);
   if (nb < 1) nb = 1;
   if (nb >= N) return N;
   const int nch = (N + nb - 1) / nb;
@@ -455,22 +457,25 @@ static int ensure_workspace(abopt_model* m, int N, int L) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
   const size_t oR = take(M * 9 * 4), oP = take(M * 3 * 4), oXa = take(M * F * 4), oXb = take(M * F * 4),
-               oProj = take(M * NPROJ * 4), oFeat = take(M * NFEAT * 4), oS = take((size_t)NB * H * L * Lp * 4),
+               oFeat = take(M * NFEAT * 4),
                oAl = take((size_t)NB * H * L * Lp * 4), oPr = take(M * bins * 4), oPl = take((size_t)N * bins * 4),
                oMp = take(M * 4), oVn = take(M * 3 * 4), oEp = take(M * 3 * 4), oCd = take(M * NAA * 4), oRn = take(M * 9 * 4),
                oBi = take(M * 4), oTv = take((size_t)N * 8), oXal = take(M * F * 4), oXbl = take(M * F * 4), oXil = take(M * F * 4),
                oFl = take(M * NFEAT * 4), oOd = take(M * F * 4), oQa = take(M * H * 64 * 4), oQl = take(M * H * 64 * 4),
-               oKb = take(M * H * 64 * 4), oKl = take(M * H * 64 * 4), oRq = take(M * H * 4), oRk = take(M * H * 4);
+               oKb = take(M * H * 64 * 4), oKl = take(M * H * 64 * 4), oRq = take(M * H * 4), oRk = take(M * H * 4),
+               oVt = take((size_t)N * H * 64 * Lp * 4), oVl = take((size_t)N * H * 64 * Lp * 4);
   CUDA_TRY(cudaMalloc(&w.base, off));
+  CUDA_TRY(cudaMemset(w.base, 0, off));        // the padding rows / columns of the packed attention operands must stay zero
   unsigned char* b = static_cast<unsigned char*>(w.base);
   w.Rbuf = (float*)(b + oR); w.pnorm = (float*)(b + oP); w.xa = (float*)(b + oXa); w.xb = (float*)(b + oXb);
-  w.proj = (float*)(b + oProj); w.feat = (float*)(b + oFeat); w.S = (float*)(b + oS); w.alpha = (float*)(b + oAl);
+  w.feat = (float*)(b + oFeat); w.alpha = (float*)(b + oAl);
   w.prmsd_rows = (float*)(b + oPr); w.prmsd_logits = (float*)(b + oPl); w.maxprob = (float*)(b + oMp);
   w.v_net = (float*)(b + oVn); w.eps_pos = (float*)(b + oEp); w.c_den = (float*)(b + oCd); w.R_next = (float*)(b + oRn);
   w.bin_idx = (int*)(b + oBi); w.tvec_scratch = (long long*)(b + oTv);
   w.xa_lo = (float*)(b + oXal); w.xb_lo = (float*)(b + oXbl); w.xin_lo = (float*)(b + oXil); w.feat_lo = (float*)(b + oFl);
   w.outD = (float*)(b + oOd);
-  w.op = AttnOperands{(float*)(b + oQa), (float*)(b + oQl), (float*)(b + oKb), (float*)(b + oKl), (float*)(b + oRq), (float*)(b + oRk)};
+  w.op = AttnOperands{(float*)(b + oQa), (float*)(b + oQl), (float*)(b + oKb), (float*)(b + oKl), (float*)(b + oRq), (float*)(b + oRk),
+                      (float*)(b + oVt), (float*)(b + oVl)};
   w.N = N; w.L = L; w.Lp = Lp; w.NB = NB; w.bytes = off;
   return ABOPT_OK;
 }
@@ -525,16 +530,18 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
     // everything a chunk of complexes produces and consumes below stays L2 resident: its projections (packed attention
     // operands), its attention weights, its aggregates; only z and the pair bias stream from HBM
     {
-      const size_t r0 = (size_t)b0 * L, o64 = (size_t)b0 * H * L * 64, o1 = (size_t)b0 * H * L;
-      const AttnOperands opc{w.op.QA + o64, w.op.QA_lo + o64, w.op.KB + o64, w.op.KB_lo + o64, w.op.rq + o1, w.op.rk + o1};
-      if (!launch_proj_pack(nb * L, L, x + r0 * F, x_lo + r0 * F, bw.Wcat, bw.Wcat_lo, R + r0 * 9, t + r0 * 3, bw.coef, w.proj + r0 * NPROJ, opc, st))
+      const size_t r0 = (size_t)b0 * L, o64 = (size_t)b0 * H * L * 64, o1 = (size_t)b0 * H * L, ov = (size_t)b0 * H * 64 * w.Lp;
+      const AttnOperands opc{w.op.QA + o64, w.op.QA_lo + o64, w.op.KB + o64, w.op.KB_lo + o64, w.op.rq + o1, w.op.rk + o1,
+                             w.op.VT + ov, w.op.VT_lo + ov};
+      if (!launch_proj_pack(nb * L, L, w.Lp, x + r0 * F, x_lo + r0 * F, bw.Wcat, bw.Wcat_lo, R + r0 * 9, t + r0 * 3, bw.coef, opc, st))
         return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (proj)");
     }
     // logits (node + spatial + pair bias, scaled, masked) and softmax on the tensor cores -> alpha (L2 resident chunk)
     if (!launch_attn_logits_tc(nb, b0, N, L, w.Lp, w.op, bias, mask, w.alpha, st)) return fail(ABOPT_ERR_CUDA, "attn_logits_tc launch failed");
     if (!launch_pair_stream(nb, b0, L, w.Lp, m->zmap, m->zmap_box_rows, mask, w.alpha, w.feat, w.feat_lo, st))
       return fail(ABOPT_ERR_ARG, "pair_stream_kernel: L too large for shared memory");
-    launch_aggr(nb, b0, L, w.Lp, w.alpha, w.proj, R, t, w.feat, w.feat_lo, st);
+    if (!launch_aggr_tc(nb, b0, N, L, w.Lp, w.alpha, w.op.VT, w.op.VT_lo, R, t, w.feat, w.feat_lo, st))
+      return fail(ABOPT_ERR_CUDA, "aggr_tc launch failed");
     if (alpha_tap) launch_alpha_tap(nb, b0, L, w.Lp, w.alpha, alpha_tap, st);
   }
   if (x_out) {

@@ -80,11 +80,12 @@ struct EpiProj {
 //   KB[b][h][r][64] = [ k (32)            | -2 c_h * global key points (24) | 0 (8) ]             ga.py:83,102-105
 //   rq[b][h][r] = c_h |query points|^2,  rk[b][h][r] = c_h |key points|^2,   c_h = -softplus(coef_h) sqrt(2/(9*8)) / 2
 // so that  QA . KB + rq + rk = node logits + spatial logits  (|q - k|^2 expanded; ga.py:108-111).  Every tensor also gets
-// its tf32 "lo" plane.  Value channels and value points keep the plain proj layout (aggr_kernel reads them).
+// its tf32 "lo" plane.  Values go out TRANSPOSED (key index contiguous), the K-major B operand of aggr_tc_kernel:
+//   VT[b][h][n][r] = value channel n (n < 32) | global value point coordinate n - 32 (32 <= n < 56); rows 56..63 stay 0.
 struct EpiProjPack {
-  float* proj; const float* R; const float* t; const float* coef;
-  float* QA; float* QA_lo; float* KB; float* KB_lo; float* rq; float* rk;
-  int L;
+  const float* R; const float* t; const float* coef;
+  float* QA; float* QA_lo; float* KB; float* KB_lo; float* rq; float* rk; float* VT; float* VT_lo;
+  int L, Lp;
   template <int BN>
   __device__ __forceinline__ void operator()(int row, int n0, int N, float (&v)[BN]) const {
     static_assert(BN == 96, "tile = 3 heads of 32 channels or 4 heads of 8 points");
@@ -147,9 +148,33 @@ struct EpiProjPack {
         return;
       }
     }
-    float* dst = proj + (size_t)row * NPROJ + n0;        // value channels / global value points: plain layout
+    // value channels (3 heads x 32) or global value points (4 heads x 24): one coalesced 4-byte store per column --
+    // the 32 lanes of the warp are 32 consecutive residues r of the same complex (or straddle two: still contiguous runs)
+    if (n0 >= OFF_VP) {
+      const int h0 = (n0 - OFF_VP) / (P * 3);
 #pragma unroll
-    for (int c = 0; c < BN; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+      for (int hh = 0; hh < 4; ++hh) {
+        const size_t o = ((size_t)(b * H + h0 + hh) * 64 + D) * Lp + r;
+#pragma unroll
+        for (int c = 0; c < P * 3; ++c) {
+          const float w = v[hh * P * 3 + c];
+          VT[o + (size_t)c * Lp] = w;
+          VT_lo[o + (size_t)c * Lp] = tf32_lo(w);
+        }
+      }
+    } else {
+      const int h0 = (n0 - OFF_V) / D;
+#pragma unroll
+      for (int hh = 0; hh < 3; ++hh) {
+        const size_t o = ((size_t)(b * H + h0 + hh) * 64) * Lp + r;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          const float w = v[hh * D + c];
+          VT[o + (size_t)c * Lp] = w;
+          VT_lo[o + (size_t)c * Lp] = tf32_lo(w);
+        }
+      }
+    }
   }
 };
 
@@ -322,6 +347,26 @@ bool make_tmap_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t col
   return r == CUDA_SUCCESS;
 }
 
+// 3-D fp32 tensor [d2][d1][d0] (d0 contiguous, dense), box [1][box1][box0], 128 B swizzle (box0 * 4 <= 128); cached
+bool make_tmap_3d(CUtensorMap* m, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1) {
+  std::lock_guard<std::mutex> lk(g_tmaps_mu);
+  const TmapKey key{base, d1 * 4096 + d2, d0, ((uint64_t)box0 << 32) | 0x3D, box1};
+  auto it = g_tmaps.find(key);
+  if (it != g_tmaps.end()) { *m = it->second; return true; }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0 * sizeof(float), d0 * d1 * sizeof(float)};
+  cuuint32_t box[3] = {box0, d1 < box1 ? (cuuint32_t)d1 : box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if (!g_encode) return false;
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  if (g_tmaps.size() > 4096) g_tmaps.clear();
+  g_tmaps[key] = *m;
+  return true;
+}
+
 // plain (unswizzled) 2-D fp32 tensor map, used for L2 prefetches only
 bool make_tmap_plain(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
   cuuint64_t dims[2] = {cols, rows};
@@ -394,8 +439,8 @@ bool launch_proj_tc(int M, const float* xh, const float* xl, const float* Wh, co
 }
 
 // same GEMM, outputs packed for the tensor-core attention kernels (see EpiProjPack)
-bool launch_proj_pack(int M, int L, const float* xh, const float* xl, const float* Wh, const float* Wl, const float* R, const float* t,
-                      const float* coef, float* proj, const AttnOperands& op, cudaStream_t st) {
+bool launch_proj_pack(int M, int L, int Lp, const float* xh, const float* xl, const float* Wh, const float* Wl, const float* R, const float* t,
+                      const float* coef, const AttnOperands& op, cudaStream_t st) {
   CUtensorMap a_h, a_l, b_h, b_l;
   if (!make_tmap(&a_h, xh, M, F, F, G_BM) || !make_tmap(&a_l, xl, M, F, F, G_BM) || !make_tmap(&b_h, Wh, NPROJ, F, F, 96) ||
       !make_tmap(&b_l, Wl, NPROJ, F, F, 96))
@@ -403,7 +448,7 @@ bool launch_proj_pack(int M, int L, const float* xh, const float* xl, const floa
   ProfScope prof__(KK_PROJ, st);
   dim3 grid(NPROJ / 96, (M + G_BM - 1) / G_BM);
   gemm3x_kernel<96, 3, 8, EpiProjPack><<<grid, G_THREADS, GemmSmem<96, 3>::TOTAL, st>>>(
-      a_h, a_l, b_h, b_l, M, NPROJ, F, EpiProjPack{proj, R, t, coef, op.QA, op.QA_lo, op.KB, op.KB_lo, op.rq, op.rk, L});
+      a_h, a_l, b_h, b_l, M, NPROJ, F, EpiProjPack{R, t, coef, op.QA, op.QA_lo, op.KB, op.KB_lo, op.rq, op.rk, op.VT, op.VT_lo, L, Lp});
   return true;
 }
 

@@ -47,9 +47,13 @@ struct AttnOperands {
   float* QA; float* QA_lo;      // [N][H][L][64]
   float* KB; float* KB_lo;      // [N][H][L][64]
   float* rq; float* rk;         // [N][H][L]
+  float* VT; float* VT_lo;      // [N][H][64][Lp]  values, key index contiguous (rows 56..63 and columns >= L stay zero)
 };
-bool launch_proj_pack(int M, int L, const float* xh, const float* xl, const float* Wh, const float* Wl, const float* R, const float* t,
-                      const float* coef, float* proj, const AttnOperands& op, cudaStream_t st);
+bool launch_proj_pack(int M, int L, int Lp, const float* xh, const float* xl, const float* Wh, const float* Wl, const float* R, const float* t,
+                      const float* coef, const AttnOperands& op, cudaStream_t st);
+cudaError_t aggr_tc_init();
+bool launch_aggr_tc(int nb, int b0, int N, int L, int Lp, const float* alpha, const float* VT, const float* VT_lo,
+                    const float* R, const float* t, float* feat, float* feat_lo, cudaStream_t st);
 bool make_tmap(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 bool make_tmap_plain(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
 cudaError_t attn_tc_init();
@@ -57,6 +61,7 @@ void attn_debug_clocks(long long* out16);
 // final logits + softmax on the tensor cores: alpha[chunk][h][i][Lp] for complexes [b0, b0 + nb)
 bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOperands& op, const float* bias_layer, const uint8_t* mask,
                            float* alpha, cudaStream_t st);
+bool make_tmap_3d(CUtensorMap* m, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1);
 
 void launch_mixer(int M, const float* res_feat, const long long* s_t, const float* v_t, const EpsW& w,
                   float* x_out, float* Rbuf, const float* p_ang, float* p_norm, const float* mean, float scale,

@@ -5,7 +5,7 @@ from oracle import weights, ipa, geometry as G
 DEV='cuda:0'
 W = weights.make_state_dict(seed=5, num_layers=1, flavour='abdesign')
 m = ab_opt_b200.FullDPMAbDesign(128, 64, 100, eps_net_opt=dict(num_layers=1)); m.load_state_dict(W); m = m.to(DEV)
-for (N, L, rag) in [(2, 24, False), (2, 64, False), (3, 100, True)]:
+for (N, L, rag) in [(2, 24, True), (2, 64, False), (3, 100, True)]:
     inp = weights.synthetic_inputs(100 + L, N, L, gen_slices=((2, 6),), ragged=rag)
     R, t = G.so3_exp(inp['v']), inp['p'] / 10.0
     o32, parts = ipa.ga_block(W, 'eps_net.encoder.blocks.0.', R, t, inp['res_feat'], inp['pair_feat'], inp['mask_res'], materialize=False, return_parts=True)
