@@ -253,8 +253,8 @@ attn_logits_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
             if (k * 32 < ncols / 2 && c0 < Lp) tma_store_3d(&tmAl, stg + (hf * 4 + k) * AL_BOX_BYTES, c0, i0, bl * H + h);
           }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-      }
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // smem must outlive the reads; the writes complete
+      }                                                                     // by the end of the grid
     } else {
       float bv[32], bn[32];
       load_bias(cbeg, bv);
