@@ -280,7 +280,8 @@ def run_ours(args, cfg, rank, world, local_rank):
             tj = json.load(open(tpath))
             if tj.get('L') == L:
                 traffic = tj['dram_bytes_per_complex'] * per_launch_complexes
-        roof = {'bound': 'hbm', 'kernel': 'pair_kernel (streams pair_feat once per layer)', 'achieved': achieved, 'peak': peak,
+        roof = {'bound': 'hbm', 'kernel': 'pair_stream_kernel (streams pair_feat once per IPA layer: softmax-weighted pair aggregation)',
+                'achieved': achieved, 'peak': peak,
                 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': alg_bytes, 'avg_launch_ms': pair_ms / pair_n, 'launches_per_sample': pair_n,
                 'share_of_gpu_time': pair_ms / total_ms,
@@ -291,7 +292,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cv, cdt, cores, sample, _ = cpu_reference_run(cfg, steps=2, warmup=1)
+            cv, cdt, cores, sample, _ = cpu_reference_run(cfg, steps=2, warmup=1, n_reverse_steps=4, B_cpu=4)
             cpu = {'value': cv, 'unit': 'residues/s', 'cores': cores, 'kind': 'port', 'sample': sample}
         line = {
             'metric': 'sampled CDR residues/sec', 'value': value, 'unit': 'residues/s', 'n_gpus': world, 'steps': args.steps,
