@@ -348,14 +348,15 @@ bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOpera
 // aggr_tc_kernel: node and point aggregation  O[i][n] = sum_j alpha[i][j] V[j][n]  (ga.py:120-136) on the tensor cores,
 // followed by the local-frame features (ga.py:137-146).  V^T[b][h][n][j] = [ value channels (32) | global value points (24)
 // | 0 (8) ] comes K-major (key index contiguous) from the projection epilogue, alpha from attn_logits_tc_kernel.
-//   warp 0     TMA producer: key blocks of 32 through a 4-stage ring (alpha 128 x 32 raw fp32; V^T 64 x 32 hi and lo planes)
+//   warp 0     TMA producer: key blocks of 32 through a 2-stage ring (alpha 128 x 32 raw fp32; V^T 64 x 32 hi and lo planes);
+//              two CTAs are resident per SM (2 x 97 KB smem, 2 x 256 TMEM columns) and hide each other's latencies
 //   warps 2-5  (a) during the main loop: "splitters" -- build the tf32 lo plane of each landed alpha box in shared memory
 //              (lo = x - trunc_tf32(x), same swizzled offsets), so alpha_lo never exists in global memory;
 //              (b) then the epilogue: thread = query row: 64 sums -> node aggregate, R_i^T (o - t_i), norms, directions,
 //              transposed through shared memory so that every global store instruction writes one contiguous row segment
-//   warp 1     MMA issuer: per key block 4 k-steps; hi*hi -> one of four 64-column TMEM accumulators (one per quarter of the
-//              keys), hi*lo + lo*hi -> a fifth (short accumulation chains: see the truncation note in k_tc.cu)
-constexpr int AG2_THREADS = 192, AG2_STAGES = 4;
+//   warp 1     MMA issuer: per key block 4 k-steps; hi*hi -> one of three 64-column TMEM accumulators (one per third of the
+//              keys), hi*lo + lo*hi -> a fourth (short accumulation chains: see the truncation note in k_tc.cu)
+constexpr int AG2_THREADS = 192, AG2_STAGES = 2;      // 2 stages x 48 KB: two CTAs per SM overlap each other's phases
 constexpr int AG2_A_BYTES = 128 * 32 * 4, AG2_B_BYTES = 64 * 32 * 4;
 constexpr int AG2_STAGE_BYTES = 2 * AG2_A_BYTES + 2 * AG2_B_BYTES;      // 48 KB: alpha raw | alpha lo | V^T hi | V^T lo
 constexpr int AG2_TX_BYTES = AG2_A_BYTES + 2 * AG2_B_BYTES;             // what TMA delivers per stage
@@ -368,7 +369,7 @@ struct AggrArgs {
   float* feat; float* feat_lo;           // [N][L][1824]
 };
 
-__global__ void __launch_bounds__(AG2_THREADS, 1)
+__global__ void __launch_bounds__(AG2_THREADS, 2)
 aggr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmVh,
                const __grid_constant__ CUtensorMap tmVl, const AggrArgs a) {
   extern __shared__ unsigned char smem_raw[];
@@ -389,11 +390,11 @@ aggr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_fence_init();
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmVh); tma_prefetch_desc(&tmVl);
   }
-  // TMEM: four "main" accumulators of 64 columns, one per quarter of the key axis, + one correction accumulator.
-  // The tensor core truncates the fp32 accumulator on every accumulation (k_tc.cu), so the long K = L chain is cut into
-  // four short ones that are added in fp32 registers (round to nearest) by the epilogue.
-  const int gsz = (nkb + 3) / 4;                         // key blocks per main accumulator
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  // TMEM: three "main" accumulators of 64 columns, one per third of the key axis, + one correction accumulator
+  // (256 columns, so two CTAs fit the SM's 512).  The tensor core truncates the fp32 accumulator on every accumulation
+  // (k_tc.cu), so the long K = L chain is cut into short ones that are added in fp32 registers by the epilogue.
+  const int gsz = (nkb + 2) / 3;                         // key blocks per main accumulator
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -426,8 +427,8 @@ aggr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t dah = smem_desc_sw128(a_hi + k * 32), dal = smem_desc_sw128(a_lo + k * 32);
           const uint64_t dbh = smem_desc_sw128(b_hi + k * 32), dbl = smem_desc_sw128(b_lo + k * 32);
           mma_tf32(tmem_base + (kb / gsz) * 64, dah, dbh, idesc, (kb % gsz == 0 && k == 0) ? 0u : 1u);
-          mma_tf32(tmem_base + 256, dah, dbl, idesc, (kb == 0 && k == 0) ? 0u : 1u);
-          mma_tf32(tmem_base + 256, dal, dbh, idesc, 1u);
+          mma_tf32(tmem_base + 192, dah, dbl, idesc, (kb == 0 && k == 0) ? 0u : 1u);
+          mma_tf32(tmem_base + 192, dal, dbh, idesc, 1u);
         }
         mma_commit(&empty[s]);
         if (kb == nkb - 1) mma_commit(tmem_full);
@@ -462,7 +463,7 @@ aggr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
     for (int c = 0; c < 64; c += 32) {
       float v[32], w[32];
-      tmem_ld_32x32(trow + 256 + c, w);                   // corrections
+      tmem_ld_32x32(trow + 192 + c, w);                   // corrections
       tmem_ld_32x32(trow + c, v);
 #pragma unroll
       for (int e = 0; e < 32; ++e) o[c + e] = v[e];
@@ -524,7 +525,7 @@ aggr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
 }
 
 cudaError_t aggr_tc_init() {
