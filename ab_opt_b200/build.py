@@ -11,31 +11,55 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, '_lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libabopt_b200.so')
 SOURCES = ['api.cu', 'k_linear.cu', 'k_attn.cu', 'k_attn_tc.cu', 'k_pair.cu', 'k_step.cu', 'k_tc.cu']
-NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '--std=c++17',
-              '-Xcompiler', '-fPIC', '-shared', '-Xptxas', '-v']
+ARCH_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a']
+COMPILE_FLAGS = ARCH_FLAGS + ['-lineinfo', '-O3', '--std=c++17', '-Xcompiler', '-fPIC', '-Xptxas', '-v']
+LINK_FLAGS = ARCH_FLAGS + ['-shared', '-Xcompiler', '-fPIC']
 
 
-def _newest_source_mtime():
-    paths = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+OBJ_DIR = os.path.join(LIB_DIR, 'obj')
+HEADERS_GLOB = ('.cuh', '.h')
+
+
+def _header_mtime():
+    paths = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(HEADERS_GLOB)]
     paths.append(os.path.join(os.path.dirname(HERE), 'include', 'abopt_b200.h'))
     return max(os.path.getmtime(p) for p in paths)
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source into ab_opt_b200/_lib/libabopt_b200.so; returns the path."""
-    os.makedirs(LIB_DIR, exist_ok=True)
-    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _newest_source_mtime():
-        return LIB_PATH
+    """Compile every CUDA source into ab_opt_b200/_lib/libabopt_b200.so; returns the path.
+    One nvcc process per translation unit, run concurrently; objects are reused when neither the
+    source nor any header is newer."""
+    os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = os.environ.get('NVCC', 'nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ['-o', LIB_PATH]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    log = proc.stdout + proc.stderr
-    with open(os.path.join(LIB_DIR, 'build.log'), 'w') as f:
-        f.write(' '.join(cmd) + '\n' + log)
-    if proc.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + log[-4000:])
+    hdr = _header_mtime()
+    jobs, objs, logs = [], [], []
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(OBJ_DIR, s[:-3] + '.o')
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), hdr):
+            continue
+        cmd = [nvcc] + COMPILE_FLAGS + ['-c', src, '-o', obj]
+        jobs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = None
+    for cmd, proc in jobs:
+        out, _ = proc.communicate()
+        logs.append(' '.join(cmd) + '\n' + out)
+        if proc.returncode != 0 and failed is None:
+            failed = out
+    if jobs:
+        with open(os.path.join(LIB_DIR, 'build.log'), 'a' if not force else 'w') as f:
+            f.write('\n'.join(logs))
+    if failed is not None:
+        raise RuntimeError('nvcc failed:\n' + failed[-4000:])
+    if jobs or not os.path.exists(LIB_PATH):
+        cmd = [nvcc] + LINK_FLAGS + objs + ['-o', LIB_PATH]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError('link failed:\n' + (proc.stdout + proc.stderr)[-4000:])
     if verbose:
-        print(log)
+        print('\n'.join(logs))
     return LIB_PATH
 
 

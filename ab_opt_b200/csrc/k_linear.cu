@@ -1,7 +1,6 @@
-// Node-feature linear layers of the hot path (v1: FP32 FFMA on CUDA cores, cp.async pipelined).
+// Small node-feature layers of the hot path on CUDA cores (FP32 FFMA, cp.async pipelined); the big GEMMs are in k_tc.cu.
 //   mixer_kernel  : EpsilonNet input mixer + R = exp(v_t)           dpm_full.py:86-89
-//   proj_kernel   : the six GABlock input projections + local->global points   ga.py:82-83,96-105,122,129-132
-//   tail_kernel   : out_transform -> mask -> LN -> MLP -> LN        ga.py:173-178
+//   tail_kernel   : (out_transform on tensor cores, k_tc.cu) -> mask -> LN -> MLP -> LN        ga.py:173-178
 //   heads_kernel  : eps_crd / eps_rot / eps_seq / pRMSD heads + SO(3) update    dpm_full.py:92-110
 #include "rowtile.cuh"
 #include "params.cuh"
@@ -59,113 +58,6 @@ mixer_kernel(int M, const float* __restrict__ res_feat, const long long* __restr
       if (x_lo_out != nullptr)
         *reinterpret_cast<float4*>(x_lo_out + (size_t)row * F + lane * 4) = make_float4(tf32_lo(acc[r][0]), tf32_lo(acc[r][1]), tf32_lo(acc[r][2]), tf32_lo(acc[r][3]));
     }
-  }
-}
-
-// ------------------------------------------------------------------------------------------ projections
-// proj[M][2016] = x[M][128] * Wcat^T, point columns mapped to the global frame (R p + t).
-// CTA tile 128 rows x 96 columns (96 | 1152 and 96 | 864, so a tile never straddles the q/k/v | points
-// boundary and every thread's 6 consecutive columns are two whole xyz points).
-constexpr int PJ_BM = 128, PJ_BN = 96, PJ_BK = 16, PJ_THREADS = 256;
-
-__global__ void __launch_bounds__(PJ_THREADS, 2)
-proj_kernel(int M, const float* __restrict__ x, const float* __restrict__ Wcat, const float* __restrict__ R,
-            const float* __restrict__ t, float* __restrict__ proj) {
-  __shared__ __align__(16) float As[2][PJ_BK][PJ_BM + 4];
-  __shared__ __align__(16) float Bs[2][PJ_BK][PJ_BN + 2];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int row0 = blockIdx.y * PJ_BM, col0 = blockIdx.x * PJ_BN;
-
-  float4 ra[2], rb[2];
-  auto gload = [&](int k0) {
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {                       // A: 128 x 16 = 512 float4
-      const int f4 = tid + i * PJ_THREADS, r = f4 >> 2, kq = f4 & 3;
-      ra[i] = (row0 + r < M) ? *reinterpret_cast<const float4*>(x + (size_t)(row0 + r) * F + k0 + kq * 4)
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {                       // B: 96 x 16 = 384 float4
-      const int f4 = tid + i * PJ_THREADS;
-      if (f4 < PJ_BN * 4) {
-        const int n = f4 >> 2, kq = f4 & 3;
-        rb[i] = *reinterpret_cast<const float4*>(Wcat + (size_t)(col0 + n) * F + k0 + kq * 4);
-      }
-    }
-  };
-  auto sstore = [&](int buf) {
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int f4 = tid + i * PJ_THREADS, r = f4 >> 2, kq = f4 & 3;
-      As[buf][kq * 4 + 0][r] = ra[i].x; As[buf][kq * 4 + 1][r] = ra[i].y;
-      As[buf][kq * 4 + 2][r] = ra[i].z; As[buf][kq * 4 + 3][r] = ra[i].w;
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int f4 = tid + i * PJ_THREADS;
-      if (f4 < PJ_BN * 4) {
-        const int n = f4 >> 2, kq = f4 & 3;
-        Bs[buf][kq * 4 + 0][n] = rb[i].x; Bs[buf][kq * 4 + 1][n] = rb[i].y;
-        Bs[buf][kq * 4 + 2][n] = rb[i].z; Bs[buf][kq * 4 + 3][n] = rb[i].w;
-      }
-    }
-  };
-
-  float acc[8][6];
-#pragma unroll
-  for (int r = 0; r < 8; ++r)
-#pragma unroll
-    for (int c = 0; c < 6; ++c) acc[r][c] = 0.f;
-
-  gload(0);
-  sstore(0);
-  __syncthreads();
-  constexpr int NK = F / PJ_BK;
-  for (int kb = 0; kb < NK; ++kb) {
-    const int buf = kb & 1;
-    if (kb + 1 < NK) gload((kb + 1) * PJ_BK);
-#pragma unroll
-    for (int k = 0; k < PJ_BK; ++k) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
-      const float2 b0 = *reinterpret_cast<const float2*>(&Bs[buf][k][tx * 6]);
-      const float2 b1 = *reinterpret_cast<const float2*>(&Bs[buf][k][tx * 6 + 2]);
-      const float2 b2 = *reinterpret_cast<const float2*>(&Bs[buf][k][tx * 6 + 4]);
-      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float b[6] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y};
-#pragma unroll
-      for (int r = 0; r < 8; ++r)
-#pragma unroll
-        for (int c = 0; c < 6; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
-    }
-    if (kb + 1 < NK) sstore(buf ^ 1);
-    __syncthreads();
-  }
-
-  const int col = col0 + tx * 6;
-  const bool is_point = col0 >= OFF_QP;
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int row = row0 + ty * 8 + r;
-    if (row >= M) continue;
-    float o[6];
-    if (is_point) {                                       // q = R p + t   (geometry.py:72-91)
-      float Rm[9], tv[3];
-#pragma unroll
-      for (int i = 0; i < 9; ++i) Rm[i] = __ldg(R + (size_t)row * 9 + i);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) tv[i] = __ldg(t + (size_t)row * 3 + i);
-#pragma unroll
-      for (int q = 0; q < 2; ++q)
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-          o[q * 3 + i] = Rm[i * 3 + 0] * acc[r][q * 3 + 0] + Rm[i * 3 + 1] * acc[r][q * 3 + 1] + Rm[i * 3 + 2] * acc[r][q * 3 + 2] + tv[i];
-    } else {
-#pragma unroll
-      for (int c = 0; c < 6; ++c) o[c] = acc[r][c];
-    }
-    float2* dst = reinterpret_cast<float2*>(proj + (size_t)row * NPROJ + col);
-    dst[0] = make_float2(o[0], o[1]); dst[1] = make_float2(o[2], o[3]); dst[2] = make_float2(o[4], o[5]);
   }
 }
 
@@ -416,11 +308,6 @@ void launch_mixer(int M, const float* res_feat, const long long* s_t, const floa
   ProfScope prof__(KK_MIXER, st);
   mixer_kernel<<<(M + RT_ROWS - 1) / RT_ROWS, RT_THREADS, mixer_smem(), st>>>(M, res_feat, s_t, v_t, w, x_out, Rbuf, p_ang, p_norm,
                                                                            mean[0], mean[1], mean[2], scale, x_lo_out);
-}
-void launch_proj(int M, const float* x, const float* Wcat, const float* R, const float* t, float* proj, cudaStream_t st) {
-  ProfScope prof__(KK_PROJ, st);
-  dim3 grid(NPROJ / PJ_BN, (M + PJ_BM - 1) / PJ_BM);
-  proj_kernel<<<grid, PJ_THREADS, 0, st>>>(M, x, Wcat, R, t, proj);
 }
 void launch_tail(int M, const float* feat, const float* pre, const float* x, const uint8_t* mask, const BlockW& w, float* x_out,
                  float* x_lo_out, cudaStream_t st) {

@@ -1,25 +1,14 @@
-// pair_stream_kernel: the kernel that streams the pair tensor z (N, L, L, 64) ONCE per GABlock.
-// For every query residue (b, i) it consumes the row-block z[b, i, :, :] (L x 64 fp32) and produces
-//   pair bias        z_ij . W_b                                   ga.py:88-90
-//   attention        softmax_j((node + spatial + pair) * sqrt(1/3)), masked          ga.py:11-26,166
-//   pair aggregate   sum_j alpha_ijh z_ijc                          ga.py:114-118
-// The node + spatial logits S arrive from logits_kernel through L2; alpha leaves through L2 for aggr_kernel.
-//
-// Structure: persistent CTAs (one per SM), 16 warps.
-//   producer : thread 0 walks the CTA's rows and issues TMA tensor loads (cp.async.bulk.tensor.2d, 128-byte
-//              swizzle, L2 evict-first) of whole row-blocks into a ring of shared-memory stages, completion on
-//              mbarriers (expect_tx).  A stage is refilled right after the first block barrier of the NEXT row,
-//              i.e. as soon as every warp is known to have left it -- no "empty" barriers, no extra warp.
-//   consumers: phase A  thread = (key residue j, 6 of the 12 heads): 64 channels x 3 head pairs from the swizzled
-//                       256 B row, issued as packed FFMA2 (fma.rn.f32x2: scalar z  x  (W[c][h], W[c][h+1]) pairs
-//                       that live in the constant bank -> uniform registers), then scale / mask;
-//              phase B  block softmax over j through a [12][L] shared tile (one warp per head);
-//              phase C  lane = channel pair, warp = 1 of 16 j-slices: 12 x 2 accumulators of alpha x z, FFMA2
-//                       again (scalar alpha x channel pair), cross-slice reduction through the drained stage.
-// Why CUDA cores and not tcgen05 here: the two contractions are skinny (N = 12 heads) and need fp32-grade
-// accuracy, i.e. a 3xTF32 split of z; splitting z in shared memory plus the operand reads of the three MMAs
-// cost ~7 passes over the 64 KB tile (~3600 clk/row of shared-memory bandwidth) against 3072 clk/row of
-// FFMA2 issue -- no gain, so the tensor cores are kept for the node-feature linears.
+// The two kernels that touch the pair tensor z (N, L, L, 64):
+//   pair_bias_kernel    z_ij . W_b for every pair and head (ga.py:88-90) -- run ONCE per layer per sampling run: z and the
+//                       weights do not change over the T reverse steps (the hoist is in api.cu)
+//   pair_stream_kernel  the kernel that streams z once per GABlock: sum_j alpha_ijh z_ijc (ga.py:114-118); alpha comes from
+//                       attn_logits_tc_kernel (k_attn_tc.cu)
+// Both are persistent, TMA-fed (cp.async.bulk.tensor.2d, 128-byte swizzle, L2 evict-first, mbarrier expect_tx) and do
+// their arithmetic as packed FFMA2 (fma.rn.f32x2) on the CUDA cores.
+// Why CUDA cores and not tcgen05 here: the contractions are skinny (N = 12 heads) and need fp32-grade accuracy, i.e. a
+// 3xTF32 split of z; splitting the 64 KB row block in shared memory plus the operand reads of three MMAs cost ~7 passes
+// over the tile (~3600 clk/row of shared-memory bandwidth) against 1536 clk/row of FFMA issue per contraction -- no gain,
+// so the tensor cores are kept for the dense GEMMs.
 #include <type_traits>
 #include "tc.cuh"
 #include "params.cuh"
@@ -32,10 +21,8 @@ using namespace tc;
 constexpr int PS_CONSUMERS = 512;                     // 16 warps (4 per scheduler); thread 0 doubles as the TMA producer
 constexpr int PS_THREADS = PS_CONSUMERS;
 constexpr int PS_ROWS = PS_CONSUMERS / 2;             // key residues covered per pass of phase A (2 threads per residue)
-constexpr int PS_SLICES = PS_CONSUMERS / 32;          // j-slices in phase C (one per warp)
 constexpr int PS_BOX_ROWS = 64;                       // key residues per TMA box
 constexpr int PS_HALF_BYTES = PS_BOX_ROWS * 128;      // one TMA box: 64 rows x 32 floats
-constexpr int PS_RED_BYTES = PS_SLICES * H * C * 4;   // cross-slice reduction scratch (lives in the drained stage)
 
 __device__ __forceinline__ float2 ffma2(float a, float2 b, float2 c) {
   unsigned long long ra, rb, rc, rd;
@@ -167,17 +154,29 @@ pair_bias_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant
   }
 }
 
-// ------------------------------------------------------------------------------------------ softmax + pair aggregation
-constexpr int PS_MAXF = 4;        // float4 groups of an alpha row per lane: L <= 32 * 4 * 4 = 512
+// ------------------------------------------------------------------------------------------ pair aggregation
+// pair_stream_kernel: out[b,i,h,c] = sum_j alpha[b,i,j,h] z[b,i,j,c]  (ga.py:114-118), alpha from attn_logits_tc_kernel.
+// Persistent CTAs of 8 warps, TWO resident per SM: each owns one shared-memory stage that holds a whole row block
+// z[b,i,:,:] (TMA, 128-byte swizzle, L2 evict-first).  While one CTA waits for its next row block the other computes,
+// so the SM alternates between them and neither the HBM latency nor the two block barriers per row are exposed.
+//   per row: alpha[h][:] (registers, prefetched one row ahead) -> shared [4 residues][head][4]; barrier;
+//            lane = 4 channels, half-warp = one 4-residue group, FFMA2 = scalar alpha x channel pair; partial sums ->
+//            dedicated scratch; barrier; the stage is refilled at once (thread 0) while 192 threads reduce the 8 slices
+//            and store the row of feat (+ its tf32 lo plane).
+constexpr int PA_THREADS = 256;
+constexpr int PA_SLICES = PA_THREADS / 32;            // 8
+constexpr int PA_MAXQ = 6;                            // float4 of alpha per thread per row: 12 heads * L / 4 / 256 <= 6 for L <= 512
+constexpr int PA_RED_BYTES = PA_SLICES * H * C * 4;   // 24 KB
 
-__global__ void __launch_bounds__(PS_THREADS, 1)
+__global__ void __launch_bounds__(PA_THREADS, 2)
 pair_stream_kernel(const __grid_constant__ CUtensorMap zmap, const PairStreamArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* stages = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);    // keeps the shared address space
   const int L = a.L, Lp = a.Lp;
-  const int Lq = (L + 3) & ~3;                       // pitch of the attention tile (floats), == Lp
-  const int nf = Lq / 4;
-  float* als = reinterpret_cast<float*>(stages + (size_t)a.nstage * a.stage_bytes);    // [Lq / 4][12][4] alpha of the current row
+  const int Lq = (L + 3) & ~3;
+  const int nf = Lq / 4;                              // 4-residue groups per row
+  float* red = reinterpret_cast<float*>(stages + (size_t)a.nstage * a.stage_bytes);     // [8 slices][12][64] partial sums
+  float* als = red + PA_SLICES * H * C;                                                  // [nf][12][4] alpha of the current row
   uint64_t* full = reinterpret_cast<uint64_t*>(als + H * Lq);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -193,18 +192,22 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap zmap, const PairStreamArg
 
   auto masked = [&](int row) { const int bl = row / L; return a.mask[(size_t)(a.b0 + bl) * L + (row - bl * L)] == 0; };
   auto next_live = [&](int row) { while (row < a.nrows && masked(row)) row += gridDim.x; return row; };
-  // alpha of one query row, one warp per head, lane-strided float4 groups (prefetched one row ahead)
-  float4 lg[PS_MAXF];
-  auto load_logits = [&](int row) {
-    if (warp < H && row < a.nrows) {
+  // alpha of one query row: 12 * nf float4, thread-strided, prefetched one row ahead into registers
+  const int nq = H * nf;
+  float4 lg[PA_MAXQ];
+  auto load_alpha = [&](int row) {
+    if (row < a.nrows) {
       const int bl = row / L, i = row - bl * L;
-      const float4* src = reinterpret_cast<const float4*>(a.alpha + ((size_t)(bl * H + warp) * L + i) * Lp);
+      const float* base = a.alpha + ((size_t)(bl * H) * L + i) * Lp;
 #pragma unroll
-      for (int m = 0; m < PS_MAXF; ++m) { const int f = lane + 32 * m; if (f < nf) lg[m] = src[f]; }
+      for (int m = 0; m < PA_MAXQ; ++m) {
+        const int idx = tid + PA_THREADS * m;
+        if (idx < nq) { const int h = idx / nf, f = idx - h * nf; lg[m] = *reinterpret_cast<const float4*>(base + (size_t)h * L * Lp + 4 * f); }
+      }
     }
   };
   int live = next_live(blockIdx.x);
-  load_logits(live);
+  load_alpha(live);
 
   int n = 0;
   for (int row = blockIdx.x; row < a.nrows; row += gridDim.x) {
@@ -214,8 +217,8 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap zmap, const PairStreamArg
     if (row != live) {
       // masked query: alpha row = 0 (ga.py:25) -> zero pair aggregate
       float* alpha_row0 = a.alpha + ((size_t)(bl * H) * L + i) * Lp;
-      for (int o = tid; o < H * C; o += PS_THREADS) { feat_row[o] = 0.f; feat_lo_row[o] = 0.f; }
-      for (int o = tid; o < H * Lp; o += PS_THREADS) {
+      for (int o = tid; o < H * C; o += PA_THREADS) { feat_row[o] = 0.f; feat_lo_row[o] = 0.f; }
+      for (int o = tid; o < H * Lp; o += PA_THREADS) {
         const int h = o / Lp, j = o - h * Lp;
         alpha_row0[(size_t)h * L * Lp + j] = 0.f;
       }
@@ -226,76 +229,72 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap zmap, const PairStreamArg
     ++n;
     const unsigned char* zs = stages + (size_t)s * a.stage_bytes;
 
-    // ---- alpha[h][:] of this query row (prefetched registers) -> shared, regrouped as [4 residues][head][4]
-    if (warp < H) {
-      float4* dsts = reinterpret_cast<float4*>(als) + warp;
+    // ---- alpha -> shared, regrouped as [4 residues][head][4]
 #pragma unroll
-      for (int k = 0; k < PS_MAXF; ++k) {
-        const int f = lane + 32 * k;
-        if (f < nf) dsts[f * H] = lg[k];
-      }
+    for (int m = 0; m < PA_MAXQ; ++m) {
+      const int idx = tid + PA_THREADS * m;
+      if (idx < nq) { const int h = idx / nf, f = idx - h * nf; reinterpret_cast<float4*>(als)[f * H + h] = lg[m]; }
     }
     live = next_live(row + gridDim.x);
-    load_logits(live);                                   // next row's logits travel while this row aggregates
+    load_alpha(live);                                    // next row's alpha travels while this row aggregates
     __syncthreads();
-    // every thread has left the previous row: its stage is drained -> thread 0 refills it (the generic-proxy accesses
-    // to that stage were ordered before this async-proxy write by the fence each thread issued at the end of the row)
-    if (tid == 0 && a.nstage > 1 && n > 1) prod.issue(&zmap, a, stages, full, gridDim.x, true);
     mbar_wait(&full[s], ph);
 
-    // ---- pair aggregation out[h][c] = sum_j alpha[j][h] z[j][c]   (ga.py:114-118)
-    //      lane = channel pair (a warp reads whole 256 B rows), warp = slice of 4-residue groups; alpha[h][j..j+3]
-    //      is one broadcast LDS.128; FFMA2 = scalar alpha x channel pair
-    float2 acc[H];
+    // ---- aggregation.  lane = (4 channels = one 16-byte group, half-warp); the two half-warps of a warp take different
+    //      4-residue groups, so one iteration issues 4 LDS.128 of z + 12 LDS.128 of alpha (2 addresses each) for 96 FFMA2
+    //      (scalar alpha x channel pair) -- the shared-memory instruction rate, not its bandwidth, is what limits this loop
+    float2 acc[H][2];
 #pragma unroll
-    for (int h = 0; h < H; ++h) acc[h] = make_float2(0.f, 0.f);
+    for (int h = 0; h < H; ++h) { acc[h][0] = make_float2(0.f, 0.f); acc[h][1] = make_float2(0.f, 0.f); }
     {
-      // lane -> 8 bytes of the 256 B row: box half (lane >> 4), 16-byte group q = (lane >> 1) & 7, low / high 8 bytes.
-      // Row j0 + k (j0 % 4 == 0) stores group q at ((q ^ k) ^ (j0 & 4)) * 16 -- see zoff().
-      const int q = (lane >> 1) & 7;
-      const uint32_t lane_off = (uint32_t)((lane >> 4) * PS_HALF_BYTES + (lane & 1) * 8);
+      // Row j0 + k (j0 % 4 == 0) stores the 16-byte group q at ((q ^ k) ^ (j0 & 4)) * 16 inside its box half -- see zoff().
+      const int c4 = lane & 15, q = c4 & 7;
+      const uint32_t lane_off = (uint32_t)((c4 >> 3) * PS_HALF_BYTES);
       uint32_t xk[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) xk[k] = lane_off + k * 128 + ((q ^ k) << 4);
-      for (int g = warp; g < nf; g += PS_SLICES) {
+      for (int g = warp * 2 + (lane >> 4); g < nf; g += 2 * PA_SLICES) {
         const int j0 = 4 * g;
         const unsigned char* zr = zs + (j0 / PS_BOX_ROWS) * (2 * PS_HALF_BYTES) + (j0 & (PS_BOX_ROWS - 1)) * 128;
         const uint32_t flip = (uint32_t)(j0 & 4) << 4;
-        float2 zv[4];
+        float4 zv[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) zv[k] = *reinterpret_cast<const float2*>(zr + (xk[k] ^ flip));
+        for (int k = 0; k < 4; ++k) zv[k] = *reinterpret_cast<const float4*>(zr + (xk[k] ^ flip));
         const float4* ap = reinterpret_cast<const float4*>(als) + g * H;
-        float4 av[H];
 #pragma unroll
-        for (int h = 0; h < H; ++h) av[h] = ap[h];
-#pragma unroll
-        for (int h = 0; h < H; ++h) acc[h] = ffma2(av[h].x, zv[0], acc[h]);
-#pragma unroll
-        for (int h = 0; h < H; ++h) acc[h] = ffma2(av[h].y, zv[1], acc[h]);
-#pragma unroll
-        for (int h = 0; h < H; ++h) acc[h] = ffma2(av[h].z, zv[2], acc[h]);
-#pragma unroll
-        for (int h = 0; h < H; ++h) acc[h] = ffma2(av[h].w, zv[3], acc[h]);
+        for (int h = 0; h < H; ++h) {
+          const float4 av = ap[h];
+          acc[h][0] = ffma2(av.x, make_float2(zv[0].x, zv[0].y), acc[h][0]); acc[h][1] = ffma2(av.x, make_float2(zv[0].z, zv[0].w), acc[h][1]);
+          acc[h][0] = ffma2(av.y, make_float2(zv[1].x, zv[1].y), acc[h][0]); acc[h][1] = ffma2(av.y, make_float2(zv[1].z, zv[1].w), acc[h][1]);
+          acc[h][0] = ffma2(av.z, make_float2(zv[2].x, zv[2].y), acc[h][0]); acc[h][1] = ffma2(av.z, make_float2(zv[2].z, zv[2].w), acc[h][1]);
+          acc[h][0] = ffma2(av.w, make_float2(zv[3].x, zv[3].y), acc[h][0]); acc[h][1] = ffma2(av.w, make_float2(zv[3].z, zv[3].w), acc[h][1]);
+        }
       }
-    }
-    __syncthreads();                                     // every read of the stage is done -> reuse it as scratch
-    float* red = reinterpret_cast<float*>(const_cast<unsigned char*>(zs));
+      // the two half-warps hold partial sums of the same channels: combine, lanes 0..15 write the warp's slice
 #pragma unroll
-    for (int h = 0; h < H; ++h) *reinterpret_cast<float2*>(red + warp * (H * C) + h * C + lane * 2) = acc[h];
-    __syncthreads();
+      for (int h = 0; h < H; ++h) {
+        acc[h][0].x += __shfl_xor_sync(0xffffffffu, acc[h][0].x, 16); acc[h][0].y += __shfl_xor_sync(0xffffffffu, acc[h][0].y, 16);
+        acc[h][1].x += __shfl_xor_sync(0xffffffffu, acc[h][1].x, 16); acc[h][1].y += __shfl_xor_sync(0xffffffffu, acc[h][1].y, 16);
+      }
+      if (lane < 16)
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+          *reinterpret_cast<float4*>(red + warp * (H * C) + h * C + c4 * 4) = make_float4(acc[h][0].x, acc[h][0].y, acc[h][1].x, acc[h][1].y);
+    }
+    fence_async_smem();                                  // generic reads of the stage ordered before the async-proxy refill
+    __syncthreads();                                     // every read of the stage is done, every partial sum is visible
+    if (tid == 0) prod.issue(&zmap, a, stages, full, gridDim.x, true);       // refill at once: the load overlaps the rest
     if (tid < H * C / 4) {
       float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < PS_SLICES; ++k) {
+      for (int k = 0; k < PA_SLICES; ++k) {
         const float4 v = *reinterpret_cast<const float4*>(red + k * (H * C) + tid * 4);
         sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
       }
       *reinterpret_cast<float4*>(feat_row + tid * 4) = sum;
       *reinterpret_cast<float4*>(feat_lo_row + tid * 4) = make_float4(tf32_lo(sum.x), tf32_lo(sum.y), tf32_lo(sum.z), tf32_lo(sum.w));
     }
-    // generic-proxy accesses to this stage must be ordered before the next TMA (async proxy) write into it
-    fence_async_smem();
-    if (a.nstage == 1) { __syncthreads(); if (tid == 0) prod.issue(&zmap, a, stages, full, gridDim.x, true); }
+    // the next row's first barrier (alpha staged) also separates this reduction from the next partial-sum writes
   }
 }
 
@@ -325,8 +324,7 @@ bool make_pair_tmap(CUtensorMap* m, const float* z, size_t total_rows, int* box_
 static bool fill_args(PairStreamArgs& a, int nb, int b0, int L, int Lp, int box_rows, size_t fixed, size_t* smem) {
   a.L = L; a.Lp = Lp; a.b0 = b0; a.nrows = nb * L;
   a.nbox_rows = (L + PS_BOX_ROWS - 1) / PS_BOX_ROWS;
-  const int tile_bytes = a.nbox_rows * 2 * PS_HALF_BYTES;
-  a.stage_bytes = tile_bytes > PS_RED_BYTES ? tile_bytes : PS_RED_BYTES;
+  a.stage_bytes = a.nbox_rows * 2 * PS_HALF_BYTES;
   a.tile_tx_bytes = a.nbox_rows * 2 * box_rows * 128;
   int nstage = (int)((227 * 1024 - fixed) / a.stage_bytes);
   if (nstage < 1) return false;
@@ -355,15 +353,27 @@ bool launch_pair_bias(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, in
 bool launch_pair_stream(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, int box_rows, const uint8_t* mask,
                         float* alpha, float* feat, float* feat_lo, cudaStream_t st) {
   ProfScope prof__(KK_PAIR, st);
-  if (L > 32 * 4 * PS_MAXF) return false;
+  if (H * ((L + 3) / 4) > PA_THREADS * PA_MAXQ) return false;
   PairStreamArgs a{};
-  size_t smem = 0;
   const int Lq = (L + 3) & ~3;
-  if (!fill_args(a, nb, b0, L, Lp, box_rows, (size_t)H * Lq * 4 + 8 * 8 + 1024, &smem)) return false;
+  a.L = L; a.Lp = Lp; a.b0 = b0; a.nrows = nb * L;
+  a.nbox_rows = (L + PS_BOX_ROWS - 1) / PS_BOX_ROWS;
+  a.stage_bytes = a.nbox_rows * 2 * PS_HALF_BYTES;
+  a.tile_tx_bytes = a.nbox_rows * 2 * box_rows * 128;
+  const size_t fixed = (size_t)PA_RED_BYTES + (size_t)H * Lq * 4 + 8 * 8 + 1024;
+  // two CTAs per SM when a stage + the fixed part fit half of the shared memory, else one CTA with what fits
+  const size_t half = (227 * 1024) / 2 - 1024;
+  int nstage, per_sm;
+  if (a.stage_bytes + fixed <= half) { per_sm = 2; nstage = (int)((half - fixed) / a.stage_bytes); }
+  else { per_sm = 1; nstage = (int)((227 * 1024 - fixed) / a.stage_bytes); }
+  if (nstage < 1) return false;
+  if (nstage > 4) nstage = 4;
+  a.nstage = nstage;
   a.mask = mask; a.alpha = alpha; a.feat = feat; a.feat_lo = feat_lo;
-  int grid = g_sm_count > 0 ? g_sm_count : 148;
+  const size_t smem = (size_t)nstage * a.stage_bytes + fixed;
+  int grid = (g_sm_count > 0 ? g_sm_count : 148) * per_sm;
   if (grid > a.nrows) grid = a.nrows;
-  pair_stream_kernel<<<grid, PS_THREADS, smem, st>>>(zmap, a);
+  pair_stream_kernel<<<grid, PA_THREADS, smem, st>>>(zmap, a);
   return true;
 }
 

@@ -49,32 +49,6 @@ struct EpiPlain {            // D = acc (+ bias)
   }
 };
 
-// GABlock projections: q | k | v stored as is, point columns mapped local -> global (R p + t)   ga.py:96-105,129-132
-struct EpiProj {
-  float* proj; const float* R; const float* t;
-  template <int BN>
-  __device__ __forceinline__ void operator()(int row, int n0, int N, float (&v)[BN]) const {
-    static_assert(BN % 3 == 0, "point triples must not straddle tiles");
-    float* dst = proj + (size_t)row * NPROJ + n0;
-    if (n0 >= OFF_QP) {
-      float Rm[9], tv[3];
-#pragma unroll
-      for (int i = 0; i < 9; ++i) Rm[i] = __ldg(R + (size_t)row * 9 + i);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) tv[i] = __ldg(t + (size_t)row * 3 + i);
-#pragma unroll
-      for (int p = 0; p < BN; p += 3) {
-        const float x = v[p], y = v[p + 1], z = v[p + 2];
-        v[p + 0] = Rm[0] * x + Rm[1] * y + Rm[2] * z + tv[0];
-        v[p + 1] = Rm[3] * x + Rm[4] * y + Rm[5] * z + tv[1];
-        v[p + 2] = Rm[6] * x + Rm[7] * y + Rm[8] * z + tv[2];
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < BN; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-  }
-};
-
 // GABlock projections, packed for the tensor-core attention kernels (k_attn_tc.cu).  Per (complex b, head h, residue r):
 //   QA[b][h][r][64] = [ q / sqrt(32) (32) | global query points (24) | 0 (8) ]                    ga.py:82-85,96-99
 //   KB[b][h][r][64] = [ k (32)            | -2 c_h * global key points (24) | 0 (8) ]             ga.py:83,102-105
@@ -308,7 +282,6 @@ cudaError_t tc_init() {
   }
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(gemm3x_kernel<128, 3, 8, EpiPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<128, 3>::TOTAL)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(gemm3x_kernel<96, 3, 8, EpiProj>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<96, 3>::TOTAL)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(gemm3x_kernel<96, 3, 8, EpiProjPack>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<96, 3>::TOTAL)) != cudaSuccess) return e;
   return cudaSuccess;
 }
@@ -425,20 +398,7 @@ bool launch_gemm3x_plain(int M, int N, int K, const float* Ah, const float* Al, 
   return true;
 }
 
-// the six GABlock projections + local->global points: proj[M][2016] = x * Wcat^T
-bool launch_proj_tc(int M, const float* xh, const float* xl, const float* Wh, const float* Wl, const float* R, const float* t,
-                    float* proj, cudaStream_t st) {
-  CUtensorMap a_h, a_l, b_h, b_l;
-  if (!make_tmap(&a_h, xh, M, F, F, G_BM) || !make_tmap(&a_l, xl, M, F, F, G_BM) || !make_tmap(&b_h, Wh, NPROJ, F, F, 96) ||
-      !make_tmap(&b_l, Wl, NPROJ, F, F, 96))
-    return false;
-  ProfScope prof__(KK_PROJ, st);
-  dim3 grid(NPROJ / 96, (M + G_BM - 1) / G_BM);
-  gemm3x_kernel<96, 3, 8, EpiProj><<<grid, G_THREADS, GemmSmem<96, 3>::TOTAL, st>>>(a_h, a_l, b_h, b_l, M, NPROJ, F, EpiProj{proj, R, t});
-  return true;
-}
-
-// same GEMM, outputs packed for the tensor-core attention kernels (see EpiProjPack)
+// the six GABlock projections as one GEMM, outputs packed for the tensor-core attention kernels (see EpiProjPack)
 bool launch_proj_pack(int M, int L, int Lp, const float* xh, const float* xl, const float* Wh, const float* Wl, const float* R, const float* t,
                       const float* coef, const AttnOperands& op, cudaStream_t st) {
   CUtensorMap a_h, a_l, b_h, b_l;

@@ -39,8 +39,6 @@ void launch_split(const float* in, float* hi, float* lo, size_t n, cudaStream_t 
 void launch_lo(const float* in, float* lo, size_t n, cudaStream_t st);
 bool launch_gemm3x_plain(int M, int N, int K, const float* Ah, const float* Al, int lda, const float* Bh, const float* Bl, int ldb,
                          float* D, int ldd, const float* bias, cudaStream_t st);
-bool launch_proj_tc(int M, const float* xh, const float* xl, const float* Wh, const float* Wl, const float* R, const float* t,
-                    float* proj, cudaStream_t st);
 
 // operands of the tensor-core attention kernels, produced by the projection GEMM epilogue (k_tc.cu: EpiProjPack)
 struct AttnOperands {
@@ -66,17 +64,12 @@ bool make_tmap_3d(CUtensorMap* m, const float* base, uint64_t d0, uint64_t d1, u
 void launch_mixer(int M, const float* res_feat, const long long* s_t, const float* v_t, const EpsW& w,
                   float* x_out, float* Rbuf, const float* p_ang, float* p_norm, const float* mean, float scale,
                   float* x_lo_out, cudaStream_t st);
-void launch_proj(int M, const float* x, const float* Wcat, const float* R, const float* t, float* proj, cudaStream_t st);
 void launch_tail(int M, const float* feat, const float* pre, const float* x, const uint8_t* mask, const BlockW& w, float* x_out,
                  float* x_lo_out, cudaStream_t st);
 void launch_heads(int M, int L, const float* x, const float* beta, int beta_stride, const float* Rbuf, const float* v_t,
                   const uint8_t* mask_gen, const EpsW& w, float* v_next, float* R_next, float* eps_pos, float* c_den,
                   float* prmsd_rows, float* prmsd_logits, cudaStream_t st);
 
-void launch_logits(int nb, int L, int Lp, const float* proj_chunk, const float* coef, const float* bias_chunk,
-                   const uint8_t* mask_chunk, float* S, cudaStream_t st);
-void launch_aggr(int nb, int b0, int L, int Lp, const float* alpha, const float* proj, const float* R, const float* t,
-                 float* feat, float* feat_lo, cudaStream_t st);
 void launch_alpha_tap(int nb, int b0, int L, int Lp, const float* alpha, float* out, cudaStream_t st);
 // pair_stream_kernel (k_pair.cu): TMA-fed persistent replacement of pair_kernel
 cudaError_t pair_stream_init();
