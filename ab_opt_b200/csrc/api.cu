@@ -538,7 +538,7 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
     }
     // logits (node + spatial + pair bias, scaled, masked) and softmax on the tensor cores -> alpha (L2 resident chunk)
     if (!launch_attn_logits_tc(nb, b0, N, L, w.Lp, w.op, bias, mask, w.alpha, st)) return fail(ABOPT_ERR_CUDA, "attn_logits_tc launch failed");
-    if (!launch_pair_stream(nb, b0, L, w.Lp, m->zmap, m->zmap_box_rows, mask, w.alpha, w.feat, w.feat_lo, st))
+    if (!launch_pair_stream(nb, b0, L, w.Lp, z, mask, w.alpha, w.feat, w.feat_lo, st))
       return fail(ABOPT_ERR_ARG, "pair_stream_kernel: L too large for shared memory");
     if (!launch_aggr_tc(nb, b0, N, L, w.Lp, w.alpha, w.op.VT, w.op.VT_lo, R, t, w.feat, w.feat_lo, st))
       return fail(ABOPT_ERR_CUDA, "aggr_tc launch failed");

@@ -156,145 +156,164 @@ pair_bias_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant
 
 // ------------------------------------------------------------------------------------------ pair aggregation
 // pair_stream_kernel: out[b,i,h,c] = sum_j alpha[b,i,j,h] z[b,i,j,c]  (ga.py:114-118), alpha from attn_logits_tc_kernel.
-// Persistent CTAs of 8 warps, TWO resident per SM: each owns one shared-memory stage that holds a whole row block
-// z[b,i,:,:] (TMA, 128-byte swizzle, L2 evict-first).  While one CTA waits for its next row block the other computes,
-// so the SM alternates between them and neither the HBM latency nor the two block barriers per row are exposed.
-//   per row: alpha[h][:] (registers, prefetched one row ahead) -> shared [4 residues][head][4]; barrier;
-//            lane = 4 channels, half-warp = one 4-residue group, FFMA2 = scalar alpha x channel pair; partial sums ->
-//            dedicated scratch; barrier; the stage is refilled at once (thread 0) while 192 threads reduce the 8 slices
-//            and store the row of feat (+ its tf32 lo plane).
-constexpr int PA_THREADS = 256;
-constexpr int PA_SLICES = PA_THREADS / 32;            // 8
-constexpr int PA_MAXQ = 6;                            // float4 of alpha per thread per row: 12 heads * L / 4 / 256 <= 6 for L <= 512
-constexpr int PA_RED_BYTES = PA_SLICES * H * C * 4;   // 24 KB
+// One persistent CTA per SM, 12 fully independent warps -- no block barrier anywhere.  Each WARP owns whole query rows
+// (b, i) and streams its row block z[b,i,:,:] through a private 3-stage shared-memory ring in chunks of 16 key residues:
+//   lane 0     producer: per chunk one 1-D bulk copy of z (4 KB contiguous, L2 evict-first) + one 3-D tensor-map box of
+//              alpha [12 heads][1 query][16 keys] (768 B; out-of-range keys arrive as zeros), mbarrier expect_tx
+//   all lanes  quarter-warp q = 4 keys of the chunk, lane l of the quarter = channels 4l..4l+3 and 32+4l..32+4l+3
+//              (conflict-free LDS.128: a quarter reads one whole 128-byte line, the four quarters four rows);
+//              per chunk 8 LDS.128 of z + 12 LDS.128 of alpha (4 distinct addresses) feed 192 FFMA2
+//              (scalar alpha x channel pair, 96 accumulators per lane)
+//   per row    the four quarters are combined with a 2-step shuffle reduce-scatter (each lane ends up with 3 heads x 8
+//              channels) and stored with their tf32 lo plane.
+constexpr int PW_WARPS = 12, PW_THREADS = PW_WARPS * 32, PW_STAGES = 3;
+constexpr int PW_CJ = 16;                               // key residues per chunk
+constexpr int PW_Z_BYTES = PW_CJ * C * 4;               // 4096
+constexpr int PW_A_BYTES = H * PW_CJ * 4;               // 768
+constexpr int PW_STAGE_BYTES = PW_Z_BYTES + PW_A_BYTES; // 4864 (a multiple of 128)
+constexpr int PW_WARP_BYTES = PW_STAGES * PW_STAGE_BYTES;
+constexpr int PW_SMEM = PW_WARPS * PW_WARP_BYTES + PW_WARPS * PW_STAGES * 8 + 1024;
 
-__global__ void __launch_bounds__(PA_THREADS, 2)
-pair_stream_kernel(const __grid_constant__ CUtensorMap zmap, const PairStreamArgs a) {
+struct PairRowsArgs {
+  int L, Lp, b0, nrows, nchunk;   // nrows = complexes covered by this launch * L; b0 = first complex; nchunk = ceil(L / 16)
+  const float* z;                 // (N, L, L, 64)
+  const uint8_t* mask;
+  float* alpha;                   // [chunk complex][h][i][Lp]; rows of masked queries are zeroed here (ga.py:25)
+  float* feat; float* feat_lo;
+};
+
+__device__ __forceinline__ void bulk_load_1d_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(smem_u32(dst)), "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(PW_THREADS, 1)
+pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs a) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* stages = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);    // keeps the shared address space
+  unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = a.L, Lp = a.Lp;
-  const int Lq = (L + 3) & ~3;
-  const int nf = Lq / 4;                              // 4-residue groups per row
-  float* red = reinterpret_cast<float*>(stages + (size_t)a.nstage * a.stage_bytes);     // [8 slices][12][64] partial sums
-  float* als = red + PA_SLICES * H * C;                                                  // [nf][12][4] alpha of the current row
-  uint64_t* full = reinterpret_cast<uint64_t*>(als + H * Lq);
+  unsigned char* wst = base + warp * PW_WARP_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + PW_WARPS * PW_WARP_BYTES) + warp * PW_STAGES;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  TileProducer prod{(int)blockIdx.x, 0, 0};
-  if (tid == 0) {
-    for (int s = 0; s < a.nstage; ++s) mbar_init(&full[s], 1);
+  // a short last chunk leaves the rest of its stage untouched: start from zeros so that stale data is always finite
+  // (it is multiplied by alpha = 0)
+  for (int o = lane; o < PW_WARP_BYTES / 16; o += 32) reinterpret_cast<float4*>(wst)[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane == 0) {
+    for (int s = 0; s < PW_STAGES; ++s) mbar_init(&full[s], 1);
     mbar_fence_init();
-    tma_prefetch_desc(&zmap);
-    prod.pol = policy_evict_first();
-    for (int s = 0; s < a.nstage; ++s) prod.issue(&zmap, a, stages, full, gridDim.x, true);
+    tma_prefetch_desc(&amap);
   }
-  __syncthreads();
+  fence_async_smem();                                   // the generic-proxy zeroes are ordered before the first TMA writes
+  __syncwarp();
 
+  const int stride = gridDim.x * PW_WARPS;
+  const int first = warp * gridDim.x + blockIdx.x;      // consecutive rows go to different SMs
   auto masked = [&](int row) { const int bl = row / L; return a.mask[(size_t)(a.b0 + bl) * L + (row - bl * L)] == 0; };
-  auto next_live = [&](int row) { while (row < a.nrows && masked(row)) row += gridDim.x; return row; };
-  // alpha of one query row: 12 * nf float4, thread-strided, prefetched one row ahead into registers
-  const int nq = H * nf;
-  float4 lg[PA_MAXQ];
-  auto load_alpha = [&](int row) {
-    if (row < a.nrows) {
-      const int bl = row / L, i = row - bl * L;
-      const float* base = a.alpha + ((size_t)(bl * H) * L + i) * Lp;
-#pragma unroll
-      for (int m = 0; m < PA_MAXQ; ++m) {
-        const int idx = tid + PA_THREADS * m;
-        if (idx < nq) { const int h = idx / nf, f = idx - h * nf; lg[m] = *reinterpret_cast<const float4*>(base + (size_t)h * L * Lp + 4 * f); }
-      }
-    }
-  };
-  int live = next_live(blockIdx.x);
-  load_alpha(live);
 
-  int n = 0;
-  for (int row = blockIdx.x; row < a.nrows; row += gridDim.x) {
+  // ---- producer cursor (lane 0): the warp's live rows, chunk by chunk, up to PW_STAGES chunks ahead of the consumer
+  int prow = first, pjc = 0, ps = 0;
+  const uint64_t pol = policy_evict_first();
+  auto issue = [&]() {
+    while (prow < a.nrows && pjc == 0 && masked(prow)) prow += stride;
+    if (prow >= a.nrows) return;
+    const int bl = prow / L, i = prow - bl * L, b = a.b0 + bl;
+    const int j0 = pjc * PW_CJ;
+    const int nj = (L - j0 < PW_CJ) ? (L - j0) : PW_CJ;
+    unsigned char* st = wst + ps * PW_STAGE_BYTES;
+    mbar_expect_tx(&full[ps], (uint32_t)(nj * C * 4 + PW_A_BYTES));
+    bulk_load_1d_hint(st, a.z + (((size_t)b * L + i) * L + j0) * C, (uint32_t)(nj * C * 4), &full[ps], pol);
+    tma_load_3d(st + PW_Z_BYTES, &amap, j0, i, bl * H, &full[ps]);
+    if (++ps == PW_STAGES) ps = 0;
+    if (++pjc == a.nchunk) { pjc = 0; prow += stride; }
+  };
+  if (lane == 0)
+    for (int s = 0; s < PW_STAGES; ++s) issue();
+
+  const int q = lane >> 3, l = lane & 7;
+  const uint32_t zoff0 = (uint32_t)(q * 4 * (C * 4) + l * 16);          // row 4q of the chunk, 16-byte group l
+  const uint32_t aoff0 = (uint32_t)(PW_Z_BYTES + q * 16);               // alpha[h][4q..4q+3] at + h * 64
+  int cs = 0;
+  uint32_t cph = 0;
+  for (int row = first; row < a.nrows; row += stride) {
     const int bl = row / L, i = row - bl * L, b = a.b0 + bl;
     float* feat_row = a.feat + ((size_t)b * L + i) * NFEAT;
     float* feat_lo_row = a.feat_lo + ((size_t)b * L + i) * NFEAT;
-    if (row != live) {
+    if (masked(row)) {
       // masked query: alpha row = 0 (ga.py:25) -> zero pair aggregate
       float* alpha_row0 = a.alpha + ((size_t)(bl * H) * L + i) * Lp;
-      for (int o = tid; o < H * C; o += PA_THREADS) { feat_row[o] = 0.f; feat_lo_row[o] = 0.f; }
-      for (int o = tid; o < H * Lp; o += PA_THREADS) {
+      for (int o = lane; o < H * C; o += 32) { feat_row[o] = 0.f; feat_lo_row[o] = 0.f; }
+      for (int o = lane; o < H * Lp; o += 32) {
         const int h = o / Lp, j = o - h * Lp;
         alpha_row0[(size_t)h * L * Lp + j] = 0.f;
       }
       continue;
     }
-    const int s = n % a.nstage;
-    const uint32_t ph = (n / a.nstage) & 1;
-    ++n;
-    const unsigned char* zs = stages + (size_t)s * a.stage_bytes;
+    float2 acc[H][4];
+#pragma unroll
+    for (int h = 0; h < H; ++h)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) acc[h][p] = make_float2(0.f, 0.f);
 
-    // ---- alpha -> shared, regrouped as [4 residues][head][4]
+    for (int jc = 0; jc < a.nchunk; ++jc) {
+      mbar_wait(&full[cs], cph);
+      const unsigned char* st = wst + cs * PW_STAGE_BYTES;
+      float4 z0[4], z1[4];
 #pragma unroll
-    for (int m = 0; m < PA_MAXQ; ++m) {
-      const int idx = tid + PA_THREADS * m;
-      if (idx < nq) { const int h = idx / nf, f = idx - h * nf; reinterpret_cast<float4*>(als)[f * H + h] = lg[m]; }
-    }
-    live = next_live(row + gridDim.x);
-    load_alpha(live);                                    // next row's alpha travels while this row aggregates
-    __syncthreads();
-    mbar_wait(&full[s], ph);
-
-    // ---- aggregation.  lane = (4 channels = one 16-byte group, half-warp); the two half-warps of a warp take different
-    //      4-residue groups, so one iteration issues 4 LDS.128 of z + 12 LDS.128 of alpha (2 addresses each) for 96 FFMA2
-    //      (scalar alpha x channel pair) -- the shared-memory instruction rate, not its bandwidth, is what limits this loop
-    float2 acc[H][2];
-#pragma unroll
-    for (int h = 0; h < H; ++h) { acc[h][0] = make_float2(0.f, 0.f); acc[h][1] = make_float2(0.f, 0.f); }
-    {
-      // Row j0 + k (j0 % 4 == 0) stores the 16-byte group q at ((q ^ k) ^ (j0 & 4)) * 16 inside its box half -- see zoff().
-      const int c4 = lane & 15, q = c4 & 7;
-      const uint32_t lane_off = (uint32_t)((c4 >> 3) * PS_HALF_BYTES);
-      uint32_t xk[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) xk[k] = lane_off + k * 128 + ((q ^ k) << 4);
-      for (int g = warp * 2 + (lane >> 4); g < nf; g += 2 * PA_SLICES) {
-        const int j0 = 4 * g;
-        const unsigned char* zr = zs + (j0 / PS_BOX_ROWS) * (2 * PS_HALF_BYTES) + (j0 & (PS_BOX_ROWS - 1)) * 128;
-        const uint32_t flip = (uint32_t)(j0 & 4) << 4;
-        float4 zv[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) zv[k] = *reinterpret_cast<const float4*>(zr + (xk[k] ^ flip));
-        const float4* ap = reinterpret_cast<const float4*>(als) + g * H;
-#pragma unroll
-        for (int h = 0; h < H; ++h) {
-          const float4 av = ap[h];
-          acc[h][0] = ffma2(av.x, make_float2(zv[0].x, zv[0].y), acc[h][0]); acc[h][1] = ffma2(av.x, make_float2(zv[0].z, zv[0].w), acc[h][1]);
-          acc[h][0] = ffma2(av.y, make_float2(zv[1].x, zv[1].y), acc[h][0]); acc[h][1] = ffma2(av.y, make_float2(zv[1].z, zv[1].w), acc[h][1]);
-          acc[h][0] = ffma2(av.z, make_float2(zv[2].x, zv[2].y), acc[h][0]); acc[h][1] = ffma2(av.z, make_float2(zv[2].z, zv[2].w), acc[h][1]);
-          acc[h][0] = ffma2(av.w, make_float2(zv[3].x, zv[3].y), acc[h][0]); acc[h][1] = ffma2(av.w, make_float2(zv[3].z, zv[3].w), acc[h][1]);
-        }
+      for (int k = 0; k < 4; ++k) {
+        z0[k] = *reinterpret_cast<const float4*>(st + zoff0 + k * (C * 4));
+        z1[k] = *reinterpret_cast<const float4*>(st + zoff0 + k * (C * 4) + 128);
       }
-      // the two half-warps hold partial sums of the same channels: combine, lanes 0..15 write the warp's slice
 #pragma unroll
       for (int h = 0; h < H; ++h) {
-        acc[h][0].x += __shfl_xor_sync(0xffffffffu, acc[h][0].x, 16); acc[h][0].y += __shfl_xor_sync(0xffffffffu, acc[h][0].y, 16);
-        acc[h][1].x += __shfl_xor_sync(0xffffffffu, acc[h][1].x, 16); acc[h][1].y += __shfl_xor_sync(0xffffffffu, acc[h][1].y, 16);
-      }
-      if (lane < 16)
+        const float4 av = *reinterpret_cast<const float4*>(st + aoff0 + h * (PW_CJ * 4));
+        const float aj[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
-        for (int h = 0; h < H; ++h)
-          *reinterpret_cast<float4*>(red + warp * (H * C) + h * C + c4 * 4) = make_float4(acc[h][0].x, acc[h][0].y, acc[h][1].x, acc[h][1].y);
-    }
-    fence_async_smem();                                  // generic reads of the stage ordered before the async-proxy refill
-    __syncthreads();                                     // every read of the stage is done, every partial sum is visible
-    if (tid == 0) prod.issue(&zmap, a, stages, full, gridDim.x, true);       // refill at once: the load overlaps the rest
-    if (tid < H * C / 4) {
-      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int k = 0; k < PA_SLICES; ++k) {
-        const float4 v = *reinterpret_cast<const float4*>(red + k * (H * C) + tid * 4);
-        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        for (int k = 0; k < 4; ++k) {
+          acc[h][0] = ffma2(aj[k], make_float2(z0[k].x, z0[k].y), acc[h][0]);
+          acc[h][1] = ffma2(aj[k], make_float2(z0[k].z, z0[k].w), acc[h][1]);
+          acc[h][2] = ffma2(aj[k], make_float2(z1[k].x, z1[k].y), acc[h][2]);
+          acc[h][3] = ffma2(aj[k], make_float2(z1[k].z, z1[k].w), acc[h][3]);
+        }
       }
-      *reinterpret_cast<float4*>(feat_row + tid * 4) = sum;
-      *reinterpret_cast<float4*>(feat_lo_row + tid * 4) = make_float4(tf32_lo(sum.x), tf32_lo(sum.y), tf32_lo(sum.z), tf32_lo(sum.w));
+      __syncwarp();                                      // every lane's reads of the stage have completed -> refill it
+      if (lane == 0) issue();
+      if (++cs == PW_STAGES) { cs = 0; cph ^= 1u; }
     }
-    // the next row's first barrier (alpha staged) also separates this reduction from the next partial-sum writes
+
+    // ---- combine the four quarters: reduce-scatter over lane bits 4 and 3, so lane (q, l) ends with heads 3q'..3q'+2
+    const bool up = (lane & 16) != 0, odd = (lane & 8) != 0;
+    float2 r[6][4];
+#pragma unroll
+    for (int hh = 0; hh < 6; ++hh)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float2 keep = up ? acc[hh + 6][p] : acc[hh][p];
+        const float2 send = up ? acc[hh][p] : acc[hh + 6][p];
+        r[hh][p].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, 16);
+        r[hh][p].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, 16);
+      }
+    const int h0 = (up ? 6 : 0) + (odd ? 3 : 0);
+#pragma unroll
+    for (int hh = 0; hh < 3; ++hh) {
+      float2 o[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float2 keep = odd ? r[hh + 3][p] : r[hh][p];
+        const float2 send = odd ? r[hh][p] : r[hh + 3][p];
+        o[p].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, 8);
+        o[p].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, 8);
+      }
+      const int off = (h0 + hh) * C + 4 * l;
+      *reinterpret_cast<float4*>(feat_row + off) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+      *reinterpret_cast<float4*>(feat_row + off + 32) = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
+      *reinterpret_cast<float4*>(feat_lo_row + off) = make_float4(tf32_lo(o[0].x), tf32_lo(o[0].y), tf32_lo(o[1].x), tf32_lo(o[1].y));
+      *reinterpret_cast<float4*>(feat_lo_row + off + 32) = make_float4(tf32_lo(o[2].x), tf32_lo(o[2].y), tf32_lo(o[3].x), tf32_lo(o[3].y));
+    }
   }
 }
 
@@ -307,7 +326,7 @@ cudaError_t pair_stream_init() {
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
   const int mx = 227 * 1024;
-  if ((e = cudaFuncSetAttribute(pair_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(pair_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(pair_bias_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(pair_bias_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(pair_bias_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
@@ -350,30 +369,19 @@ bool launch_pair_bias(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, in
   return true;
 }
 
-bool launch_pair_stream(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, int box_rows, const uint8_t* mask,
+bool launch_pair_stream(int nb, int b0, int L, int Lp, const float* z, const uint8_t* mask,
                         float* alpha, float* feat, float* feat_lo, cudaStream_t st) {
+  CUtensorMap amap;
+  // alpha as a plain 3-D tensor [nb * H][L queries][Lp keys]; box = [12 heads][1 query][16 keys]
+  if (!make_tmap_3d_plain(&amap, alpha, (uint64_t)Lp, (uint64_t)L, (uint64_t)nb * H, PW_CJ, 1, H)) return false;
   ProfScope prof__(KK_PAIR, st);
-  if (H * ((L + 3) / 4) > PA_THREADS * PA_MAXQ) return false;
-  PairStreamArgs a{};
-  const int Lq = (L + 3) & ~3;
-  a.L = L; a.Lp = Lp; a.b0 = b0; a.nrows = nb * L;
-  a.nbox_rows = (L + PS_BOX_ROWS - 1) / PS_BOX_ROWS;
-  a.stage_bytes = a.nbox_rows * 2 * PS_HALF_BYTES;
-  a.tile_tx_bytes = a.nbox_rows * 2 * box_rows * 128;
-  const size_t fixed = (size_t)PA_RED_BYTES + (size_t)H * Lq * 4 + 8 * 8 + 1024;
-  // two CTAs per SM when a stage + the fixed part fit half of the shared memory, else one CTA with what fits
-  const size_t half = (227 * 1024) / 2 - 1024;
-  int nstage, per_sm;
-  if (a.stage_bytes + fixed <= half) { per_sm = 2; nstage = (int)((half - fixed) / a.stage_bytes); }
-  else { per_sm = 1; nstage = (int)((227 * 1024 - fixed) / a.stage_bytes); }
-  if (nstage < 1) return false;
-  if (nstage > 4) nstage = 4;
-  a.nstage = nstage;
-  a.mask = mask; a.alpha = alpha; a.feat = feat; a.feat_lo = feat_lo;
-  const size_t smem = (size_t)nstage * a.stage_bytes + fixed;
-  int grid = (g_sm_count > 0 ? g_sm_count : 148) * per_sm;
-  if (grid > a.nrows) grid = a.nrows;
-  pair_stream_kernel<<<grid, PA_THREADS, smem, st>>>(zmap, a);
+  PairRowsArgs a{};
+  a.L = L; a.Lp = Lp; a.b0 = b0; a.nrows = nb * L; a.nchunk = (L + PW_CJ - 1) / PW_CJ;
+  a.z = z; a.mask = mask; a.alpha = alpha; a.feat = feat; a.feat_lo = feat_lo;
+  int grid = g_sm_count > 0 ? g_sm_count : 148;
+  const int need = (a.nrows + PW_WARPS - 1) / PW_WARPS;
+  if (grid > need) grid = need;
+  pair_stream_kernel<<<grid, PW_THREADS, PW_SMEM, st>>>(amap, a);
   return true;
 }
 

@@ -77,8 +77,9 @@ bool make_tmap_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t col
 bool make_pair_tmap(CUtensorMap* m, const float* z, size_t total_rows, int* box_rows_out);
 bool launch_pair_bias(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, int box_rows, const PairBiasPacked& pb, float* bias,
                       cudaStream_t st);
-bool launch_pair_stream(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, int box_rows, const uint8_t* mask,
+bool launch_pair_stream(int nb, int b0, int L, int Lp, const float* z, const uint8_t* mask,
                         float* alpha, float* feat, float* feat_lo, cudaStream_t st);
+bool make_tmap_3d_plain(CUtensorMap* m, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1, uint32_t box2);
 
 void launch_angle_argmax(int M, int L, const long long* tvec, int t_uniform, const float* Y, const float* expo,
                          const uint8_t* mask_gen, int* bin_idx, cudaStream_t st);
