@@ -15,6 +15,7 @@
 //              row in TMEM, 32 columns at a time: (1) logits -> running max, written back with tcgen05.st,
 //              (2) exp -> running sum, written back, (3) normalise and store alpha.  The only cross-thread traffic is
 //              the exchange of the two half-row maxima / sums through shared memory.
+#include <cstdlib>
 #include "tc.cuh"
 #include "params.cuh"
 #include "kernels.h"
@@ -316,8 +317,272 @@ attn_logits_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
+// ------------------------------------------------------------------------------------------ persistent variant (keys <= 256)
+// attn_logits_persist_kernel: same arithmetic as attn_logits_tc_kernel<true>, restructured so that the phases of consecutive
+// tiles overlap and no thread ever waits on a global load.  One CTA per SM walks the (complex, head, 128-query tile) list;
+// 18 warps:
+//   warp 0      TMA producer, one thread running a small event loop over two independent streams:
+//                 operands -- the query operand (single buffer, released by the MMA warp) and key groups of 64 residues
+//                             through a 3-stage ring;
+//                 bias     -- the tile's pair bias in chunks of [32 keys][128 queries] (16 KB) through a 3-stage ring,
+//                             running ahead of the epilogue (the bias is the HBM stream of this kernel)
+//   warp 1      MMA issuer -- accumulates tile n into TMEM buffer n & 1 (2 x 256 columns) while the epilogue warps are still
+//               busy with tile n - 1; per key group 16 correction products first, then the 8 hi*hi ones (truncation note above)
+//   warps 2-17  epilogue   -- 4 threads per query row; thread (row, kq) owns keys 32 m + 8 kq + (0..7) of every chunk m:
+//               TMEM -> registers (buffer released at once), per chunk bias from shared memory (conflict-free: lanes are
+//               consecutive queries) -> logits; max / exp / sum exchanged through shared memory; alpha stored with 256-bit
+//               global stores (one full 32-byte sector each)
+constexpr int AP_THREADS = 576, AP_EPI = 512;
+constexpr int AP_BST = 3, AP_BGRP_BYTES = 4 * 64 * 32 * 4;            // key-group stage: 64 keys x (hi k0 | hi k1 | lo k0 | lo k1) = 32 KB
+constexpr int AP_KBOX = 64 * 32 * 4;                                  // one key box: 64 rows x 32 floats
+constexpr int AP_NBIAS = 3, AP_BIAS_BYTES = 32 * 128 * 4;             // bias chunk: 32 keys x 128 queries
+constexpr int AP_B_OFF = 2 * AL_OPER_BYTES;
+constexpr int AP_BIAS_OFF = AP_B_OFF + AP_BST * AP_BGRP_BYTES;
+constexpr int AP_TAB_OFF = AP_BIAS_OFF + AP_NBIAS * AP_BIAS_BYTES;    // ck[256] | pen[256] | xmax[4][128] | xsum[4][128]
+constexpr int AP_BAR_OFF = AP_TAB_OFF + 2 * 256 * 4 + 8 * 128 * 4;
+constexpr int AP_SMEM = AP_BAR_OFF + 256 + 1024;
+
+// 2^x, x <= 0 (MUFU.EX2, 2 ulp; results below the normal range flush to zero -- attention weights < 1e-38)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void epi_sync512() { asm volatile("bar.sync 1, %0;" ::"n"(AP_EPI) : "memory"); }
+// 32 lanes x 8 consecutive fp32 columns, no wait (the caller issues one tcgen05.wait::ld for a batch)
+__device__ __forceinline__ void tmem_ld_32x8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+}
+
+struct AttnPersistArgs {
+  int nb_complex;                 // complexes covered by this launch
+  int bias_pitch;                 // floats between consecutive keys of a bias chunk in shared memory (= box width)
+  int bias_tx;                    // bytes one bias box delivers
+};
+
+template <int NCH>                                      // 32-key chunks per row: 4 (keys <= 128) or 8 (keys <= 256)
+__global__ void __launch_bounds__(AP_THREADS, 1)
+attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
+                           const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
+                           const __grid_constant__ CUtensorMap tmBias, const AttnLogitsArgs a, const AttnPersistArgs pa) {
+  constexpr int NGRP = NCH / 2;                         // 64-key MMA groups
+  constexpr int NLG = NCH * 8;                          // logits per epilogue thread
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* ck = reinterpret_cast<float*>(smem + AP_TAB_OFF);
+  float* pen = ck + 256;
+  float* xmax = pen + 256;                // [4][128]
+  float* xsum = xmax + 4 * 128;           // [4][128]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + AP_BAR_OFF);
+  uint64_t* a_empty = a_full + 1;
+  uint64_t* b_full = a_empty + 1;         // [AP_BST]
+  uint64_t* b_empty = b_full + AP_BST;    // [AP_BST]
+  uint64_t* bias_full = b_empty + AP_BST;       // [AP_NBIAS]
+  uint64_t* bias_empty = bias_full + AP_NBIAS;  // [AP_NBIAS]
+  uint64_t* tmem_full = bias_empty + AP_NBIAS;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = a.L, Lp = a.Lp;
+  const int nit = (L + AL_BM - 1) / AL_BM;              // query tiles per (complex, head)
+  const int ntiles = pa.nb_complex * H * nit;
+
+  if (threadIdx.x == 0) {
+    mbar_init(a_full, 1); mbar_init(a_empty, 1);
+    for (int s = 0; s < AP_BST; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < AP_NBIAS; ++s) { mbar_init(&bias_full[s], 1); mbar_init(&bias_empty[s], AP_EPI / 32); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], AP_EPI / 32); }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmQh); tma_prefetch_desc(&tmQl); tma_prefetch_desc(&tmKh); tma_prefetch_desc(&tmKl); tma_prefetch_desc(&tmBias);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: event loop over the operand stream and the bias stream =====================
+    if (elect_one()) {
+      int otile = blockIdx.x, on = 0, og = 0, ostep = 0;        // operand stream: tile, tile count, key-group count, step in tile
+      int btile = blockIdx.x, bc = 0, bm = 0;                   // bias stream: tile, chunk count, chunk in tile
+      while (otile < ntiles || btile < ntiles) {
+        if (otile < ntiles) {
+          const int it = otile % nit, bh = otile / nit, h = bh % H, bl = bh / H;
+          const int row_base = ((a.b0 + bl) * H + h) * L;
+          if (ostep == 0) {
+            if (mbar_try_wait(a_empty, (on & 1) ^ 1)) {
+              unsigned char* A = smem + AL_A_OFF;
+              const int r0 = row_base + it * AL_BM;
+              mbar_expect_tx(a_full, 2 * AL_OPER_BYTES);
+              tma_load_2d(A, &tmQh, 0, r0, a_full);
+              tma_load_2d(A + AL_BOX_BYTES, &tmQh, 32, r0, a_full);
+              tma_load_2d(A + AL_OPER_BYTES, &tmQl, 0, r0, a_full);
+              tma_load_2d(A + AL_OPER_BYTES + AL_BOX_BYTES, &tmQl, 32, r0, a_full);
+              ostep = 1;
+            }
+          } else {
+            const int s = og % AP_BST;
+            if (mbar_try_wait(&b_empty[s], ((og / AP_BST) & 1) ^ 1)) {
+              unsigned char* B = smem + AP_B_OFF + s * AP_BGRP_BYTES;
+              const int r0 = row_base + (ostep - 1) * 64;
+              mbar_expect_tx(&b_full[s], AP_BGRP_BYTES);
+              tma_load_2d(B, &tmKh, 0, r0, &b_full[s]);
+              tma_load_2d(B + AP_KBOX, &tmKh, 32, r0, &b_full[s]);
+              tma_load_2d(B + 2 * AP_KBOX, &tmKl, 0, r0, &b_full[s]);
+              tma_load_2d(B + 3 * AP_KBOX, &tmKl, 32, r0, &b_full[s]);
+              ++og;
+              if (++ostep > NGRP) { ostep = 0; ++on; otile += gridDim.x; }
+            }
+          }
+        }
+        if (btile < ntiles) {
+          const int s = bc % AP_NBIAS;
+          if (mbar_try_wait(&bias_empty[s], ((bc / AP_NBIAS) & 1) ^ 1)) {
+            const int it = btile % nit, bh = btile / nit, h = bh % H, bl = bh / H;
+            const int row_base = ((a.b0 + bl) * H + h) * L;
+            mbar_expect_tx(&bias_full[s], (uint32_t)pa.bias_tx);
+            tma_load_2d(smem + AP_BIAS_OFF + s * AP_BIAS_BYTES, &tmBias, it * AL_BM, row_base + bm * 32, &bias_full[s]);
+            ++bc;
+            if (++bm == NCH) { bm = 0; btile += gridDim.x; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = idesc_tf32(AL_BM, 64);
+    int n = 0, g = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+      const int buf = n & 1;
+      mbar_wait(&tmem_empty[buf], ((n >> 1) & 1) ^ 1);    // the epilogue has read this TMEM buffer (tile n - 2)
+      mbar_wait(a_full, n & 1);
+      for (int gi = 0; gi < NGRP; ++gi, ++g) {
+        const int s = g % AP_BST;
+        mbar_wait(&b_full[s], (g / AP_BST) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_hi = smem_u32(smem + AL_A_OFF), a_lo = a_hi + AL_OPER_BYTES;
+          const uint32_t b_hi = smem_u32(smem + AP_B_OFF + s * AP_BGRP_BYTES), b_lo = b_hi + 2 * AP_KBOX;
+          const uint32_t d = tmem_base + buf * 256 + gi * 64;
+#pragma unroll
+          for (int kk = 0; kk < AL_K / 8; ++kk) {
+            const uint32_t ka = (kk >> 2) * AL_BOX_BYTES + (kk & 3) * 32, kb = (kk >> 2) * AP_KBOX + (kk & 3) * 32;
+            mma_tf32(d, smem_desc_sw128(a_hi + ka), smem_desc_sw128(b_lo + kb), idesc, kk == 0 ? 0u : 1u);
+            mma_tf32(d, smem_desc_sw128(a_lo + ka), smem_desc_sw128(b_hi + kb), idesc, 1u);
+          }
+#pragma unroll
+          for (int kk = 0; kk < AL_K / 8; ++kk) {
+            const uint32_t ka = (kk >> 2) * AL_BOX_BYTES + (kk & 3) * 32, kb = (kk >> 2) * AP_KBOX + (kk & 3) * 32;
+            mma_tf32(d, smem_desc_sw128(a_hi + ka), smem_desc_sw128(b_hi + kb), idesc, 1u);
+          }
+          mma_commit(&b_empty[s]);
+          if (gi == NGRP - 1) { mma_commit(a_empty); mma_commit(&tmem_full[buf]); }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..17) =====================
+    const int q = warp & 3;                               // TMEM lane quarter this warp may access
+    const int kq = (warp - 2) >> 2;                       // which 8 keys of every 32-key chunk this thread handles
+    const int te = q * 32 + lane;                         // 0..127: query row in the tile
+    const int et = (warp - 2) * 32 + lane;                // 0..511
+    const float scale = 0.57735026918962576f;             // sqrt(1/3), ga.py:166
+    const float l2e = 1.4426950408889634f;
+    const int bpitch = pa.bias_pitch;
+    int n = 0, bc = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+      const int it = tile % nit, bh = tile / nit, h = bh % H, bl = bh / H, b = a.b0 + bl;
+      const int row_base = (b * H + h) * L, i0 = it * AL_BM;
+      const int buf = n & 1;
+      const int i = i0 + te;
+      const bool valid = i < L;
+      // per-key tables: rk[j] and the mask penalty (1e5 for masked keys, +inf beyond the end -> alpha = 0)
+      if (et < NCH * 32) {
+        ck[et] = (et < L) ? __ldg(a.rk + (size_t)row_base + et) : 0.f;
+        pen[et] = (et < L) ? (a.mask[(size_t)b * L + et] != 0 ? 0.f : 1e5f) : INFINITY;
+      }
+      const float rqi = valid ? __ldg(a.rq + (size_t)row_base + i) : 0.f;
+      float* alpha_row = a.alpha + ((size_t)(bl * H + h) * L + (valid ? i : 0)) * Lp;
+      epi_sync512();                                      // tables visible; also: every warp is done with the previous tile
+      mbar_wait(&tmem_full[buf], (n >> 1) & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + kq * 8;
+      float lg[NLG];
+      {
+        uint32_t raw[NCH][8];
+#pragma unroll
+        for (int m = 0; m < NCH; ++m) tmem_ld_32x8_nowait(trow + m * 32, raw[m]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int m = 0; m < NCH; ++m)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) lg[m * 8 + e] = __uint_as_float(raw[m][e]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);       // the accumulator is in registers: the MMA warp may reuse the buffer
+      float mx = -INFINITY;
+#pragma unroll
+      for (int m = 0; m < NCH; ++m, ++bc) {
+        const int s = bc % AP_NBIAS;
+        mbar_wait(&bias_full[s], (bc / AP_NBIAS) & 1);
+        const float* bs = reinterpret_cast<const float*>(smem + AP_BIAS_OFF + s * AP_BIAS_BYTES) + (kq * 8) * bpitch + te;
+        float bv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bv[e] = bs[e * bpitch];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bias_empty[s]);       // values are in registers: the producer may refill the slot
+        const int j0 = m * 32 + kq * 8;
+        const float4 c0 = *reinterpret_cast<const float4*>(ck + j0), c1 = *reinterpret_cast<const float4*>(ck + j0 + 4);
+        const float4 p0 = *reinterpret_cast<const float4*>(pen + j0), p1 = *reinterpret_cast<const float4*>(pen + j0 + 4);
+        const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        const float pp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float lgt = ((lg[m * 8 + e] + bv[e]) + (rqi + cc[e])) * scale - pp[e];
+          mx = fmaxf(mx, lgt);
+          lg[m * 8 + e] = lgt;
+        }
+      }
+      xmax[kq * 128 + te] = mx;
+      epi_sync512();
+      mx = fmaxf(fmaxf(xmax[te], xmax[128 + te]), fmaxf(xmax[256 + te], xmax[384 + te]));
+      // exp(l - m) = 2^((l - m) log2e): subtract FIRST (exact near the maximum, where the attention mass is)
+      float sum = 0.f;
+#pragma unroll
+      for (int e = 0; e < NLG; ++e) { lg[e] = ex2_approx((lg[e] - mx) * l2e); sum += lg[e]; }
+      xsum[kq * 128 + te] = sum;
+      epi_sync512();
+      const float inv = 1.0f / ((xsum[te] + xsum[128 + te]) + (xsum[256 + te] + xsum[384 + te]));
+      if (valid) {
+#pragma unroll
+        for (int m = 0; m < NCH; ++m) {
+          const int j0 = m * 32 + kq * 8;
+          if (j0 < Lp)
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(alpha_row + j0), "f"(lg[m * 8] * inv),
+                         "f"(lg[m * 8 + 1] * inv), "f"(lg[m * 8 + 2] * inv), "f"(lg[m * 8 + 3] * inv), "f"(lg[m * 8 + 4] * inv),
+                         "f"(lg[m * 8 + 5] * inv), "f"(lg[m * 8 + 6] * inv), "f"(lg[m * 8 + 7] * inv) : "memory");
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+static bool g_attn_legacy = false;      // ABOPT_ATTN_LEGACY=1: one-tile-per-CTA kernel (A/B comparisons)
 cudaError_t attn_tc_init() {
+  { const char* ev = getenv("ABOPT_ATTN_LEGACY"); g_attn_legacy = ev && ev[0] == '1'; }
   cudaError_t e = cudaFuncSetAttribute(attn_logits_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AL_SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(attn_logits_persist_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(attn_logits_persist_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(attn_logits_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AL_SMEM);
 }
@@ -339,7 +604,20 @@ bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOpera
   AttnLogitsArgs a{L, Lp, b0, op.rq, op.rk, bias_layer, mask, alpha};
   dim3 grid((L + AL_BM - 1) / AL_BM, H, nb);
   const int ncols = ((L + AL_BN - 1) / AL_BN) * AL_BN;
-  if (ncols <= 256) attn_logits_tc_kernel<true><<<grid, AL_THREADS, AL_SMEM, st>>>(qh, ql, kh, kl, bm, al, a);
+  if (ncols <= 256 && !g_attn_legacy) {
+    // key operands in groups of 64 residues; the pair bias as [32 keys][<= 128 queries] boxes
+    CUtensorMap kh64, kl64, bm32;
+    const uint32_t brows = rows < 32 ? (uint32_t)rows : 32u, bcols = Lp < 128 ? (uint32_t)Lp : 128u;
+    if (!make_tmap(&kh64, op.KB, rows, 64, 64, 64) || !make_tmap(&kl64, op.KB_lo, rows, 64, 64, 64) ||
+        !make_tmap_plain(&bm32, bias_layer, rows, (uint64_t)Lp, (uint64_t)Lp, brows, bcols))
+      return false;
+    const int ntiles = nb * H * ((L + AL_BM - 1) / AL_BM);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const AttnPersistArgs pa{nb, (int)bcols, (int)(brows * bcols * 4)};
+    if (ncols <= 128) attn_logits_persist_kernel<4><<<ntiles < sms ? ntiles : sms, AP_THREADS, AP_SMEM, st>>>(qh, ql, kh64, kl64, bm32, a, pa);
+    else attn_logits_persist_kernel<8><<<ntiles < sms ? ntiles : sms, AP_THREADS, AP_SMEM, st>>>(qh, ql, kh64, kl64, bm32, a, pa);
+  } else if (ncols <= 256) attn_logits_tc_kernel<true><<<grid, AL_THREADS, AL_SMEM, st>>>(qh, ql, kh, kl, bm, al, a);
   else attn_logits_tc_kernel<false><<<grid, AL_THREADS, AL_SMEM, st>>>(qh, ql, kh, kl, bm, al, a);
   return true;
 }
