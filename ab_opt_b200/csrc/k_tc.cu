@@ -9,6 +9,7 @@
 //   warp 0      : TMA producer  -- cp.async.bulk.tensor, 128B-swizzled [rows][32 tf32] boxes, mbarrier expect_tx
 //   warp 1      : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma.kind::tf32, commits to mbarriers)
 //   warps 2..5  : epilogue      -- tcgen05.ld (thread = output row), fused epilogue functor, global stores
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -265,12 +266,258 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
+// ---------------------------------------------------------------- persistent projection GEMM
+// proj_persist_kernel: the six GABlock projections, (B*L, 128) x (128, 2016), with the EpiProjPack packing, restructured
+// around what bounds it -- the 235 MB of packed operands it writes per layer:
+//   * one CTA per 128-row tile keeps x (hi + lo, 128 KB) RESIDENT in shared memory and walks the 21 column tiles of 96,
+//     streaming only the weights (24 KB per k-block, L2 resident) through a 3-stage ring;
+//   * two 192-column TMEM accumulator sets: while the tensor core fills one, the other is being packed;
+//   * two epilogue warp groups (4 warps each) take alternate column tiles, so two tiles are packed concurrently;
+//   * the packed rows leave as 256-bit stores (one full 32-byte sector per lane) instead of 128-bit ones.
+// warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 / 6-9 = epilogue groups 0 / 1.
+constexpr int PP_THREADS = 320, PP_BN = 96, PP_NT = NPROJ / PP_BN, PP_KB = F / G_BK, PP_ST = 3;
+constexpr int PP_A_BYTES = G_BM * G_BK * 4;                 // 16 KB: 128 rows x 32 tf32
+constexpr int PP_B_BYTES = PP_BN * G_BK * 4;                // 12 KB
+constexpr int PP_A_TOTAL = PP_KB * 2 * PP_A_BYTES;          // 128 KB: [k-block][hi | lo]
+constexpr int PP_STAGE = 2 * PP_B_BYTES;                    // 24 KB: weights hi | lo of one k-block
+constexpr int PP_BAR_OFF = PP_A_TOTAL + PP_ST * PP_STAGE;
+constexpr int PP_SMEM = PP_BAR_OFF + 256 + 1024;
+static_assert(PP_NT * PP_BN == NPROJ && PP_KB * G_BK == F, "projection tiling");
+
+__device__ __forceinline__ void tmem_ld_32x8_nw(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// W columns (a multiple of 8) of the main and the correction accumulator, summed
+template <int W>
+__device__ __forceinline__ void tmem_ld_sum(uint32_t t_main, uint32_t t_small, float (&v)[W]) {
+  float m[W], c[W];
+#pragma unroll
+  for (int i = 0; i < W; i += 8) { tmem_ld_32x8_nw(t_main + i, m + i); tmem_ld_32x8_nw(t_small + i, c + i); }
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < W; ++i) v[i] = m[i] + c[i];
+}
+__device__ __forceinline__ void st_v8(float* p, const float (&w)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(w[0]), "f"(w[1]), "f"(w[2]), "f"(w[3]),
+               "f"(w[4]), "f"(w[5]), "f"(w[6]), "f"(w[7]) : "memory");
+}
+__device__ __forceinline__ void st_v8_hi_lo(float* hi, float* lo, const float (&w)[8]) {
+  st_v8(hi, w);
+  float l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) l[i] = tf32_lo(w[i]);
+  st_v8(lo, l);
+}
+
+__global__ void __launch_bounds__(PP_THREADS, 1)
+proj_persist_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, int M, EpiProjPack ep) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + PP_BAR_OFF);
+  uint64_t* a_empty = a_full + 1;
+  uint64_t* b_full = a_empty + 1;            // [PP_ST]
+  uint64_t* b_empty = b_full + PP_ST;        // [PP_ST]
+  uint64_t* tmem_full = b_empty + PP_ST;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nmt = (M + G_BM - 1) / G_BM;
+  constexpr uint32_t ACC_COLS = 2 * PP_BN;                  // main | corrections
+
+  if (threadIdx.x == 0) {
+    mbar_init(a_full, 1); mbar_init(a_empty, 1);
+    for (int s = 0; s < PP_ST; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int na = 0, g = 0;
+      for (int mt = blockIdx.x; mt < nmt; mt += gridDim.x, ++na) {
+        mbar_wait(a_empty, (na & 1) ^ 1);
+        mbar_expect_tx(a_full, PP_A_TOTAL);
+        for (int kb = 0; kb < PP_KB; ++kb) {
+          tma_load_2d(smem + kb * 2 * PP_A_BYTES, &tmAh, kb * G_BK, mt * G_BM, a_full);
+          tma_load_2d(smem + kb * 2 * PP_A_BYTES + PP_A_BYTES, &tmAl, kb * G_BK, mt * G_BM, a_full);
+        }
+        for (int nt = 0; nt < PP_NT; ++nt)
+          for (int kb = 0; kb < PP_KB; ++kb, ++g) {
+            const int s = g % PP_ST;
+            mbar_wait(&b_empty[s], ((g / PP_ST) & 1) ^ 1);
+            unsigned char* st = smem + PP_A_TOTAL + s * PP_STAGE;
+            mbar_expect_tx(&b_full[s], PP_STAGE);
+            tma_load_2d(st, &tmBh, kb * G_BK, nt * PP_BN, &b_full[s]);
+            tma_load_2d(st + PP_B_BYTES, &tmBl, kb * G_BK, nt * PP_BN, &b_full[s]);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = idesc_tf32(G_BM, PP_BN);
+    int na = 0, g = 0, n = 0;
+    for (int mt = blockIdx.x; mt < nmt; mt += gridDim.x, ++na) {
+      mbar_wait(a_full, na & 1);
+      for (int nt = 0; nt < PP_NT; ++nt, ++n) {
+        const int buf = n & 1;
+        mbar_wait(&tmem_empty[buf], ((n >> 1) & 1) ^ 1);              // epilogue group `buf` drained tile n - 2
+        for (int kb = 0; kb < PP_KB; ++kb, ++g) {
+          const int s = g % PP_ST;
+          mbar_wait(&b_full[s], (g / PP_ST) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_hi = smem_u32(smem + kb * 2 * PP_A_BYTES), a_lo = a_hi + PP_A_BYTES;
+            const uint32_t b_hi = smem_u32(smem + PP_A_TOTAL + s * PP_STAGE), b_lo = b_hi + PP_B_BYTES;
+            const uint32_t d_main = tmem_base + buf * ACC_COLS, d_small = d_main + PP_BN;
+#pragma unroll
+            for (int k = 0; k < G_BK / 8; ++k) {
+              const uint64_t dah = smem_desc_sw128(a_hi + k * 32), dal = smem_desc_sw128(a_lo + k * 32);
+              const uint64_t dbh = smem_desc_sw128(b_hi + k * 32), dbl = smem_desc_sw128(b_lo + k * 32);
+              const uint32_t acc = (kb == 0 && k == 0) ? 0u : 1u;
+              mma_tf32(d_main, dah, dbh, idesc, acc);
+              mma_tf32(d_small, dah, dbl, idesc, acc);
+              mma_tf32(d_small, dal, dbh, idesc, 1u);
+            }
+            mma_commit(&b_empty[s]);
+            if (kb == PP_KB - 1) {
+              mma_commit(&tmem_full[buf]);
+              if (nt == PP_NT - 1) mma_commit(a_empty);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue groups =====================
+    const int q = warp & 3;                                            // TMEM lane quarter this warp may access
+    const int gp = (warp - 2) >> 2;                                    // group: takes the tiles with n % 2 == gp
+    const int L = ep.L, Lp = ep.Lp;
+    int n = 0;
+    for (int mt = blockIdx.x; mt < nmt; mt += gridDim.x) {
+      const int row = mt * G_BM + q * 32 + lane;
+      const bool valid = row < M;
+      const int rr = valid ? row : 0;
+      const int b = rr / L, r = rr - b * L;
+      float Rm[9], tv[3];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Rm[i] = __ldg(ep.R + (size_t)rr * 9 + i);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) tv[i] = __ldg(ep.t + (size_t)rr * 3 + i);
+      for (int nt = 0; nt < PP_NT; ++nt, ++n) {
+        if ((n & 1) != gp) continue;
+        mbar_wait(&tmem_full[gp], (n >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + gp * ACC_COLS, ts = tm + PP_BN;
+        const int n0 = nt * PP_BN;
+        if (n0 < OFF_V) {
+          // ---- q or k channels: 3 heads x 32                                      ga.py:82-85
+          const bool is_q = n0 < OFF_K;
+          const int h0 = (is_q ? n0 : n0 - OFF_K) / D;
+          const float sc = is_q ? 0.17677669529663687f : 1.f;          // 1 / sqrt(32) folded into q
+          float* dst = is_q ? ep.QA : ep.KB;
+          float* dlo = is_q ? ep.QA_lo : ep.KB_lo;
+#pragma unroll 1
+          for (int hh = 0; hh < 3; ++hh) {
+            float v[32];
+            tmem_ld_sum<32>(tm + hh * D, ts + hh * D, v);
+            if (valid) {
+              const size_t o = ((size_t)(b * H + h0 + hh) * L + r) * 64;
+#pragma unroll
+              for (int c = 0; c < D; c += 8) {
+                float w[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) w[e] = v[c + e] * sc;
+                st_v8_hi_lo(dst + o + c, dlo + o + c, w);
+              }
+            }
+          }
+        } else if (n0 < OFF_QP) {
+          // ---- value channels: 3 heads x 32, stored transposed (key index contiguous)  ga.py:122
+          const int h0 = (n0 - OFF_V) / D;
+#pragma unroll 1
+          for (int hh = 0; hh < 3; ++hh) {
+            float v[32];
+            tmem_ld_sum<32>(tm + hh * D, ts + hh * D, v);
+            if (valid) {
+              const size_t o = ((size_t)(b * H + h0 + hh) * 64) * Lp + r;
+#pragma unroll
+              for (int c = 0; c < D; ++c) { ep.VT[o + (size_t)c * Lp] = v[c]; ep.VT_lo[o + (size_t)c * Lp] = tf32_lo(v[c]); }
+            }
+          }
+        } else {
+          // ---- points: 4 heads x 8 points x 3, local -> global q = R p + t      geometry.py:72-91
+          const int kind = n0 < OFF_KP ? 0 : (n0 < OFF_VP ? 1 : 2);      // query / key / value points
+          const int h0 = (n0 - (kind == 0 ? OFF_QP : (kind == 1 ? OFF_KP : OFF_VP))) / (P * 3);
+#pragma unroll 1
+          for (int hh = 0; hh < 4; ++hh) {
+            float v[24];
+            tmem_ld_sum<24>(tm + hh * P * 3, ts + hh * P * 3, v);
+            if (valid) {
+#pragma unroll
+              for (int p = 0; p < P * 3; p += 3) {
+                const float x = v[p], y = v[p + 1], z = v[p + 2];
+                v[p + 0] = Rm[0] * x + Rm[1] * y + Rm[2] * z + tv[0];
+                v[p + 1] = Rm[3] * x + Rm[4] * y + Rm[5] * z + tv[1];
+                v[p + 2] = Rm[6] * x + Rm[7] * y + Rm[8] * z + tv[2];
+              }
+              const int h = h0 + hh;
+              if (kind < 2) {
+                // query / key points -> QA / KB columns 32..63 + norm terms           ga.py:96-111
+                float* dst = kind == 0 ? ep.QA : ep.KB;
+                float* dlo = kind == 0 ? ep.QA_lo : ep.KB_lo;
+                float* rn = kind == 0 ? ep.rq : ep.rk;
+                const float ch = __ldg(ep.coef + h);
+                const float sc = kind == 0 ? 1.f : -2.f * ch;
+                float n2 = 0.f;
+#pragma unroll
+                for (int c = 0; c < P * 3; ++c) n2 = fmaf(v[c], v[c], n2);
+                rn[(size_t)(b * H + h) * L + r] = ch * n2;
+                const size_t o = ((size_t)(b * H + h) * L + r) * 64 + D;
+#pragma unroll
+                for (int c = 0; c < 32; c += 8) {
+                  float w[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) w[e] = (c + e < P * 3) ? v[c + e] * sc : 0.f;
+                  st_v8_hi_lo(dst + o + c, dlo + o + c, w);
+                }
+              } else {
+                const size_t o = ((size_t)(b * H + h) * 64 + D) * Lp + r;
+#pragma unroll
+                for (int c = 0; c < P * 3; ++c) { ep.VT[o + (size_t)c * Lp] = v[c]; ep.VT_lo[o + (size_t)c * Lp] = tf32_lo(v[c]); }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[gp]);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_encodeTiled g_encode = nullptr;
 
+static bool g_proj_legacy = false;       // ABOPT_PROJ_LEGACY=1: one-tile-per-CTA projection GEMM (A/B comparisons)
 cudaError_t tc_init() {
   if (!g_encode) {
     void* fn = nullptr;
@@ -283,6 +530,8 @@ cudaError_t tc_init() {
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(gemm3x_kernel<128, 3, 8, EpiPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<128, 3>::TOTAL)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(gemm3x_kernel<96, 3, 8, EpiProjPack>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<96, 3>::TOTAL)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(proj_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM)) != cudaSuccess) return e;
+  { const char* ev = getenv("ABOPT_PROJ_LEGACY"); g_proj_legacy = ev && ev[0] == '1'; }
   return cudaSuccess;
 }
 
@@ -426,6 +675,14 @@ bool launch_proj_pack(int M, int L, int Lp, const float* xh, const float* xl, co
       !make_tmap(&b_l, Wl, NPROJ, F, F, 96))
     return false;
   ProfScope prof__(KK_PROJ, st);
+  const EpiProjPack ep{R, t, coef, op.QA, op.QA_lo, op.KB, op.KB_lo, op.rq, op.rk, op.VT, op.VT_lo, L, Lp};
+  if (!g_proj_legacy) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int nmt = (M + G_BM - 1) / G_BM;
+    proj_persist_kernel<<<nmt < sms ? nmt : sms, PP_THREADS, PP_SMEM, st>>>(a_h, a_l, b_h, b_l, M, ep);
+    return true;
+  }
   dim3 grid(NPROJ / 96, (M + G_BM - 1) / G_BM);
   gemm3x_kernel<96, 3, 8, EpiProjPack><<<grid, G_THREADS, GemmSmem<96, 3>::TOTAL, st>>>(
       a_h, a_l, b_h, b_l, M, NPROJ, F, EpiProjPack{R, t, coef, op.QA, op.QA_lo, op.KB, op.KB_lo, op.rq, op.rk, op.VT, op.VT_lo, L, Lp});
