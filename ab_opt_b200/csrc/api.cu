@@ -96,6 +96,7 @@ struct abopt_model {
   Workspace ws;
   HostIO io;
   cudaStream_t own_stream = nullptr;
+  void* train_buf = nullptr; size_t train_bytes = 0;      // scratch of abopt_loss_forward
 };
 
 static void add_key(abopt_model* m, const std::string& k, size_t numel, int dtype = 0, bool required = true) {
@@ -826,6 +827,65 @@ extern "C" int abopt_sample_device(abopt_model* m, int N, int L, const float* v,
                   noise ? &noise[T0 - t] : nullptr, V(t - 1), Pp(t - 1), S(t - 1), PR(t - 1), PL(t - 1), st);
   m->bias_hoisted = false;
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------ training forward
+// FullDPM.forward without autograd: the three add_noise calls at per-complex steps t, one EpsilonNet evaluation, the loss
+// dict (dpm_full.py:156-234; AbDesign :138-190).  losses_out (device, 5 floats) = rot, pos, seq, prmsd, dist.
+extern "C" int abopt_loss_forward(abopt_model* m, int N, int L, const float* v_0, const float* p_0, const int64_t* s_0,
+                                  const float* res_feat, const float* pair_feat, const uint8_t* mask_generate,
+                                  const uint8_t* mask_res, uint32_t flags, const int64_t* t, uint64_t seed,
+                                  const abopt_step_noise* noise, float* losses_out, void* stream) {
+  int rc = check_ready(m, N, L, ABOPT_SCOPE_FULL); if (rc) return rc;
+  if (!v_0 || !p_0 || !s_0 || !res_feat || !pair_feat || !mask_generate || !mask_res || !t || !losses_out)
+    return fail(ABOPT_ERR_ARG, "null tensor");
+  if (noise && (!noise->u || !noise->expo_ang || !noise->unif_ang || !noise->gauss_ang || !noise->z_pos || !noise->expo_seq))
+    return fail(ABOPT_ERR_ARG, "incomplete abopt_step_noise record");
+  DeviceGuard g(m->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = ensure_workspace(m, N, L); if (rc) return rc;
+  Workspace& w = m->ws;
+  const size_t M = (size_t)N * L;
+  const size_t need = M * (3 + 3 + 3 + 6) * sizeof(float) + M * sizeof(long long) + (size_t)N * sizeof(float) + 256;
+  if (m->train_bytes < need) {
+    if (m->train_buf) { CUDA_TRY(cudaFree(m->train_buf)); m->train_buf = nullptr; m->train_bytes = 0; }
+    CUDA_TRY(cudaMalloc(&m->train_buf, need));
+    m->train_bytes = need;
+  }
+  long long* s_noisy = reinterpret_cast<long long*>(m->train_buf);
+  float* v_noisy = reinterpret_cast<float*>(s_noisy + M);
+  float* p_noisy = v_noisy + M * 3;            // Angstrom, like every position that crosses a kernel boundary
+  float* zbuf = p_noisy + M * 3;
+  float* rows = zbuf + M * 3;
+  float* beta = rows + M * 6;
+  const bool ds = (flags & ABOPT_SAMPLE_STRUCTURE) != 0, dq = (flags & ABOPT_SAMPLE_SEQUENCE) != 0;
+
+  InitArgs ia{};
+  ia.M = (int)M; ia.L = L; ia.T0 = 0;
+  ia.sample_structure = ds ? 1 : 0; ia.sample_sequence = dq ? 1 : 0; ia.optimize = 1; ia.has_prmsd = 0;
+  ia.v = v_0; ia.p_ang = p_0; ia.s = (const long long*)s_0; ia.mask_gen = mask_generate;
+  ia.v_out = v_noisy; ia.p_out_ang = p_noisy; ia.s_out = s_noisy;
+  ia.seed = seed; ia.tvec = (const long long*)t; ia.seq_all_rows = 1; ia.z_out = ds ? zbuf : nullptr;
+  if (noise) {
+    if (ds) launch_angle_argmax((int)M, L, (const long long*)t, 0, m->diff.ang_Y[0], noise->expo_ang, mask_generate, w.bin_idx, st);
+    ia.add = NoisePtrs{noise->u, noise->unif_ang, noise->gauss_ang, noise->z_pos, noise->expo_seq, w.bin_idx};
+  }
+  launch_init(ia, m->diff, st);
+  launch_gather_beta(N, (const long long*)t, m->diff.betas, beta, st);
+  rc = run_eps_net(m, N, L, v_noisy, nullptr, p_noisy, s_noisy, res_feat, pair_feat, beta, 1, mask_generate, mask_res,
+                   w.v_net, w.R_next, w.eps_pos, w.c_den, nullptr, st);
+  if (rc) return rc;
+  LossArgs la{};
+  la.N = N; la.L = L; la.abdock = m->cfg.has_prmsd ? 1 : 0; la.pred_x0 = m->cfg.obj_pred_x0 ? 1 : 0;
+  la.has_prmsd = m->cfg.has_prmsd; la.bins = m->cfg.prmsd_bins; la.dmin = m->cfg.prmsd_min; la.dmax = m->cfg.prmsd_max;
+  la.v_0 = v_0; la.p_0_ang = p_0; la.s_0 = (const long long*)s_0;
+  la.p_noisy_ang = p_noisy; la.s_noisy = s_noisy; la.z = ds ? zbuf : nullptr;
+  la.R_pred = w.R_next; la.p_pred = w.eps_pos; la.c_den = w.c_den; la.prmsd_logits = w.prmsd_logits;
+  la.mask_gen = mask_generate; la.mask_res = mask_res; la.tvec = (const long long*)t;
+  la.rows = rows; la.out = losses_out;
+  launch_loss(la, m->diff, st);
+  CHECK_LAUNCH();
+  return ABOPT_OK;
 }
 
 static int ensure_hostio(abopt_model* m, int N, int L, int T0) {

@@ -213,37 +213,58 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs 
 
   const int stride = gridDim.x * PW_WARPS;
   const int first = warp * gridDim.x + blockIdx.x;      // consecutive rows go to different SMs
-  auto masked = [&](int row) { const int bl = row / L; return a.mask[(size_t)(a.b0 + bl) * L + (row - bl * L)] == 0; };
+  // (complex, residue) of a row advance incrementally: no integer division in the loops
+  const int dbl = stride / L, di = stride - dbl * L;
+  auto advance = [&](int& bl, int& i) { bl += dbl; i += di; if (i >= L) { i -= L; ++bl; } };
+  // query mask of the warp's next 32 rows as one ballot word (lane k <-> the k-th row from `row`), so that neither the
+  // producer nor the consumer ever waits on a global load per row
+  auto live_word = [&](int row) {
+    const long long r = (long long)row + (long long)lane * stride;
+    bool live = false;
+    if (r < a.nrows) { const int bl = (int)(r / L); live = a.mask[(size_t)(a.b0 + bl) * L + (int)(r - (long long)bl * L)] != 0; }
+    return __ballot_sync(0xffffffffu, live);
+  };
 
-  // ---- producer cursor (lane 0): the warp's live rows, chunk by chunk, up to PW_STAGES chunks ahead of the consumer
-  int prow = first, pjc = 0, ps = 0;
+  // ---- producer cursor (lane 0 issues): the warp's live rows, chunk by chunk, up to PW_STAGES chunks ahead of the consumer
+  int prow = first, pbl = first / L, pi = first - pbl * L, pjc = 0, ps = 0, pk = 0;
+  unsigned pword = live_word(first);
   const uint64_t pol = policy_evict_first();
-  auto issue = [&]() {
-    while (prow < a.nrows && pjc == 0 && masked(prow)) prow += stride;
+  auto issue = [&]() {                                  // executed by the whole warp (uniform control flow)
+    while (prow < a.nrows && !((pword >> pk) & 1u)) {    // skip masked query rows
+      prow += stride; advance(pbl, pi);
+      if (++pk == 32) { pk = 0; pword = live_word(prow); }
+    }
     if (prow >= a.nrows) return;
-    const int bl = prow / L, i = prow - bl * L, b = a.b0 + bl;
     const int j0 = pjc * PW_CJ;
     const int nj = (L - j0 < PW_CJ) ? (L - j0) : PW_CJ;
-    unsigned char* st = wst + ps * PW_STAGE_BYTES;
-    mbar_expect_tx(&full[ps], (uint32_t)(nj * C * 4 + PW_A_BYTES));
-    bulk_load_1d_hint(st, a.z + (((size_t)b * L + i) * L + j0) * C, (uint32_t)(nj * C * 4), &full[ps], pol);
-    tma_load_3d(st + PW_Z_BYTES, &amap, j0, i, bl * H, &full[ps]);
+    if (lane == 0) {
+      unsigned char* st = wst + ps * PW_STAGE_BYTES;
+      mbar_expect_tx(&full[ps], (uint32_t)(nj * C * 4 + PW_A_BYTES));
+      bulk_load_1d_hint(st, a.z + (((size_t)(a.b0 + pbl) * L + pi) * L + j0) * C, (uint32_t)(nj * C * 4), &full[ps], pol);
+      tma_load_3d(st + PW_Z_BYTES, &amap, j0, pi, pbl * H, &full[ps]);
+    }
     if (++ps == PW_STAGES) ps = 0;
-    if (++pjc == a.nchunk) { pjc = 0; prow += stride; }
+    if (++pjc == a.nchunk) {
+      pjc = 0; prow += stride; advance(pbl, pi);
+      if (++pk == 32) { pk = 0; pword = live_word(prow); }
+    }
   };
-  if (lane == 0)
-    for (int s = 0; s < PW_STAGES; ++s) issue();
+  for (int s = 0; s < PW_STAGES; ++s) issue();
 
   const int q = lane >> 3, l = lane & 7;
   const uint32_t zoff0 = (uint32_t)(q * 4 * (C * 4) + l * 16);          // row 4q of the chunk, 16-byte group l
   const uint32_t aoff0 = (uint32_t)(PW_Z_BYTES + q * 16);               // alpha[h][4q..4q+3] at + h * 64
-  int cs = 0;
+  int cs = 0, ck = 0;
   uint32_t cph = 0;
-  for (int row = first; row < a.nrows; row += stride) {
-    const int bl = row / L, i = row - bl * L, b = a.b0 + bl;
+  unsigned cword = live_word(first);
+  int bl = first / L, i = first - bl * L;
+  for (int row = first; row < a.nrows; row += stride, advance(bl, i)) {
+    const int b = a.b0 + bl;
     float* feat_row = a.feat + ((size_t)b * L + i) * NFEAT;
     float* feat_lo_row = a.feat_lo + ((size_t)b * L + i) * NFEAT;
-    if (masked(row)) {
+    const bool live = (cword >> ck) & 1u;
+    if (++ck == 32) { ck = 0; cword = live_word(row + stride); }
+    if (!live) {
       // masked query: alpha row = 0 (ga.py:25) -> zero pair aggregate
       float* alpha_row0 = a.alpha + ((size_t)(bl * H) * L + i) * Lp;
       for (int o = lane; o < H * C; o += 32) { feat_row[o] = 0.f; feat_lo_row[o] = 0.f; }
@@ -281,7 +302,7 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs 
         }
       }
       __syncwarp();                                      // every lane's reads of the stage have completed -> refill it
-      if (lane == 0) issue();
+      issue();
       if (++cs == PW_STAGES) { cs = 0; cph ^= 1u; }
     }
 

@@ -286,7 +286,7 @@ init_kernel(InitArgs a, DiffW dw) {
       else { const uint4 x = ph(r, tt, RS_INIT_S, 0); s = (long long)(x.x % 19u); }   // randint_like(s, 0, 19): class 19 never drawn
     }
   } else {                                           // FullDPM.optimize, dpm_full.py:321-337
-    const int t = a.T0;
+    const int t = a.tvec ? (int)a.tvec[r / a.L] : a.T0;
     const bool parity = a.add.u != nullptr;
     if (gen && a.sample_structure) {
       float u[3], unif, gauss, ucdf = 0.f, z[3];
@@ -309,15 +309,21 @@ init_kernel(InitArgs a, DiffW dw) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) p[i] = add_(mul_(c0, p[i]), mul_(c1, z[i]));     // transition.py:62-78
     }
+    if (a.z_out && a.sample_structure) {               // e_rand is returned for every row (transition.py:74-78)
+      float z[3];
+      if (parity) { z[0] = a.add.z_pos[(size_t)r * 3]; z[1] = a.add.z_pos[(size_t)r * 3 + 1]; z[2] = a.add.z_pos[(size_t)r * 3 + 2]; }
+      else { const uint4 w = ph(r, tt, RS_ZPOS, 0); float g3; box_muller(w.x, w.y, z[0], z[1]); box_muller(w.z, w.w, z[2], g3); }
+      a.z_out[(size_t)r * 3] = z[0]; a.z_out[(size_t)r * 3 + 1] = z[1]; a.z_out[(size_t)r * 3 + 2] = z[2];
+    }
     if (a.sample_sequence) {                          // transition.py:183-200 on every row; kept only where generated
       float q[NAA];
       if (parity) {
 #pragma unroll
         for (int k = 0; k < NAA; ++k) q[k] = a.add.expo_seq[(size_t)r * NAA + k];
       } else philox_exp20(ph, r, tt, q);
-      if (gen) {
-        const float ab = dw.alpha_bars_seq[t];
-        const float base = div_(add_(1.f, -ab), (float)NAA);
+      if (gen || a.seq_all_rows) {
+        const float ab = gen ? dw.alpha_bars_seq[t] : 1.f;          // not generated: c_t = c_0 (transition.py:198)
+        const float base = gen ? div_(add_(1.f, -ab), (float)NAA) : 0.f;
         const bool s_ok = (s >= 0 && s < NAA);
         float best = -INFINITY; int bi = 0;
 #pragma unroll
@@ -337,6 +343,157 @@ init_kernel(InitArgs a, DiffW dw) {
     a.p_out_ang[(size_t)r * 3 + i] = add_(mul_(p[i], dw.pos_scale), dw.pos_mean[i]);
   }
   a.s_out[r] = s;
+}
+
+// ---------------------------------------------------------------- training losses (FullDPM.forward)
+__global__ void gather_beta_kernel(int N, const long long* tvec, const float* betas, float* out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < N) out[n] = betas[tvec[n]];
+}
+
+// one thread per residue: the per-residue terms of the rot / pos / seq losses, the squared deviation behind the pRMSD
+// target and one row of the distance loss.  dpm_full.py:186-232, :15-32, :369-378; transition.py:202-227
+__global__ void __launch_bounds__(128)
+loss_rows_kernel(LossArgs a, DiffW dw) {
+  const int M = a.N * a.L;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= M) return;
+  const int n = r / a.L;
+  const int t = (int)a.tvec[n];
+  const bool gen = a.mask_gen[r] != 0;
+  float rot = 0.f, pos = 0.f, seq = 0.f, sq = 0.f, dsum = 0.f, dcnt = 0.f;
+  float p0[3], pn[3], pp[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    p0[i] = div_(add_(a.p_0_ang[(size_t)r * 3 + i], -dw.pos_mean[i]), dw.pos_scale);
+    pn[i] = div_(add_(a.p_noisy_ang[(size_t)r * 3 + i], -dw.pos_mean[i]), dw.pos_scale);
+    pp[i] = a.p_pred[(size_t)r * 3 + i];
+  }
+  if (gen) {
+    // ---- rotation: sum over columns of 1 - cos(col_pred, col_true)   (cosine_embedding_loss, EPSILON = 1e-12)
+    const Mat3 R0 = so3_exp(a.v_0[(size_t)r * 3], a.v_0[(size_t)r * 3 + 1], a.v_0[(size_t)r * 3 + 2]);
+    const float* Rp = a.R_pred + (size_t)r * 9;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float x0 = Rp[c], x1 = Rp[3 + c], x2 = Rp[6 + c];
+      const float y0 = R0.m[c], y1 = R0.m[3 + c], y2 = R0.m[6 + c];
+      const float dot = x0 * y0 + x1 * y1 + x2 * y2;
+      const float m1 = x0 * x0 + x1 * x1 + x2 * x2 + 1e-12f, m2 = y0 * y0 + y1 * y1 + y2 * y2 + 1e-12f;
+      rot += 1.f - dot / sqrtf(m1 * m2);
+    }
+    // ---- position: AbDesign compares the predicted noise with e_rand; AbDock p_pred with p_0 (pred_x0) or p_noisy (sic)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float tgt = a.abdock ? (a.pred_x0 ? p0[i] : pn[i]) : (a.z ? a.z[(size_t)r * 3 + i] : 0.f);
+      const float d = pp[i] - tgt;
+      pos += d * d;
+    }
+    // ---- sequence: KL( posterior(s_noisy, s_0) || posterior(s_noisy, c_denoised) )
+    const float ab = dw.alpha_bars_seq[t];
+    const float base = (1.f - ab) / (float)NAA;
+    const long long st = a.s_noisy[r], s0 = a.s_0[r];
+    float tt_[NAA], tp_[NAA], st_sum = 0.f, sp_sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < NAA; ++k) {
+      const float ct = (st == k) ? 1.f : 0.f, c0 = (s0 == k) ? 1.f : 0.f;
+      const float lhs = ab * ct + base;
+      tt_[k] = lhs * (ab * c0 + base);
+      tp_[k] = lhs * (ab * a.c_den[(size_t)r * NAA + k] + base);
+      st_sum += tt_[k]; sp_sum += tp_[k];
+    }
+#pragma unroll
+    for (int k = 0; k < NAA; ++k) {
+      const float tg = tt_[k] / (st_sum + 1e-8f);
+      const float lp = logf(tp_[k] / (sp_sum + 1e-8f) + 1e-8f);
+      if (tg > 0.f) seq += tg * (logf(tg) - lp);
+    }
+    // ---- pRMSD target: |pred_p0 - p_0|^2 in Angstrom over generated residues   (common/prmsd.py:86-111)
+    if (a.abdock) {
+      const float c0 = dw.sqrt_recip_ab[t], c1 = dw.sqrt_recipm1_ab[t];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float pred0 = a.pred_x0 ? pp[i] : (c0 * p0[i] - c1 * pp[i]);      // pred_start_from_noise(p_0, p_pred, ...)
+        const float d = (pred0 * dw.pos_scale + dw.pos_mean[i]) - (p0[i] * dw.pos_scale + dw.pos_mean[i]);
+        sq += d * d;
+      }
+    }
+    // ---- distance loss row: SmoothL1(|p_pred_i - p_pred_j| - |p_0i - p_0j|) over valid residues j
+    if (a.abdock && a.pred_x0 && a.mask_res[r]) {
+      const int base_r = n * a.L;
+      for (int j = 0; j < a.L; ++j) {
+        if (!a.mask_res[base_r + j]) continue;
+        float dp = 0.f, dt = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float qp = a.p_pred[(size_t)(base_r + j) * 3 + i];
+          const float q0 = div_(add_(a.p_0_ang[(size_t)(base_r + j) * 3 + i], -dw.pos_mean[i]), dw.pos_scale);
+          dp += (pp[i] - qp) * (pp[i] - qp);
+          dt += (p0[i] - q0) * (p0[i] - q0);
+        }
+        const float x = fabsf(sqrtf(dp) - sqrtf(dt));
+        dsum += x < 1.f ? 0.5f * x * x : x - 0.5f;
+        dcnt += 1.f;
+      }
+    }
+  }
+  a.rows[r] = rot; a.rows[(size_t)M + r] = pos; a.rows[(size_t)2 * M + r] = seq; a.rows[(size_t)3 * M + r] = sq;
+  a.rows[(size_t)4 * M + r] = dsum; a.rows[(size_t)5 * M + r] = dcnt;
+}
+
+__device__ double block_sum_double(double v, double* sh) {
+  const int tid = threadIdx.x;
+  __syncthreads();
+  sh[tid] = v;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) { if (tid < s) sh[tid] += sh[tid + s]; __syncthreads(); }
+  return sh[0];
+}
+
+// one block: masked means in a fixed order (deterministic), pRMSD cross entropy per complex
+__global__ void __launch_bounds__(1024)
+loss_reduce_kernel(LossArgs a) {
+  __shared__ double sh[1024];
+  const int M = a.N * a.L, tid = threadIdx.x;
+  double acc[6] = {0, 0, 0, 0, 0, 0}, ngen = 0;
+  for (int r = tid; r < M; r += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) if (k != 3) acc[k] += (double)a.rows[(size_t)k * M + r];
+    ngen += a.mask_gen[r] ? 1.0 : 0.0;
+  }
+  const double n_gen = block_sum_double(ngen, sh);
+  const double rot = block_sum_double(acc[0], sh), pos = block_sum_double(acc[1], sh), seq = block_sum_double(acc[2], sh);
+  const double dsum = block_sum_double(acc[4], sh), dcnt = block_sum_double(acc[5], sh);
+  // pRMSD: rmsd per complex -> nearest bin of linspace(dmin, dmax, bins) -> cross entropy; averaged with mask_generate[:, 0]
+  double ce_sum = 0, m_sum = 0;
+  if (a.abdock && a.has_prmsd) {
+    for (int n = tid; n < a.N; n += blockDim.x) {
+      float s2 = 0.f, cnt = 0.f;
+      for (int l = 0; l < a.L; ++l) { s2 += a.rows[(size_t)3 * M + (size_t)n * a.L + l]; cnt += a.mask_gen[(size_t)n * a.L + l] ? 1.f : 0.f; }
+      const float rmsd = sqrtf(s2 / cnt);
+      const float step = (a.dmax - a.dmin) / (float)(a.bins - 1);
+      int best = 0; float bd = INFINITY;
+      for (int k = 0; k < a.bins; ++k) {
+        const float off = (k < a.bins / 2) ? a.dmin + step * (float)k : a.dmax - step * (float)(a.bins - 1 - k);     // torch.linspace
+        const float d = fabsf(rmsd - off);
+        if (d < bd) { bd = d; best = k; }
+      }
+      const float* lg = a.prmsd_logits + (size_t)n * a.bins;
+      float mx = -INFINITY;
+      for (int k = 0; k < a.bins; ++k) mx = fmaxf(mx, lg[k]);
+      float se = 0.f;
+      for (int k = 0; k < a.bins; ++k) se += expf(lg[k] - mx);
+      const float ce = (mx + logf(se)) - lg[best];
+      const float mk = a.mask_gen[(size_t)n * a.L] ? 1.f : 0.f;
+      ce_sum += (double)(ce * mk); m_sum += (double)mk;
+    }
+  }
+  const double ce = block_sum_double(ce_sum, sh), ms = block_sum_double(m_sum, sh);
+  if (tid == 0) {
+    const double den = n_gen + 1e-8;
+    a.out[0] = (float)(rot / den); a.out[1] = (float)(pos / den); a.out[2] = (float)(seq / den);
+    a.out[3] = (a.abdock && a.has_prmsd) ? (float)(ce / (ms + 1e-10)) : 0.f;
+    a.out[4] = (a.abdock && a.pred_x0) ? (float)(dsum / dcnt) : 0.f;
+  }
 }
 
 // ---------------------------------------------------------------- stand-alone transition entry points
@@ -408,6 +565,16 @@ void launch_complex_reduce(int N, int L, int bins, float dmin, float dmax, int m
 void launch_init(const InitArgs& a, const DiffW& dw, cudaStream_t st) {
   ProfScope prof__(KK_OTHER, st);
   init_kernel<<<(a.M + 127) / 128, 128, 0, st>>>(a, dw);
+}
+void launch_loss(const LossArgs& a, const DiffW& dw, cudaStream_t st) {
+  ProfScope prof__(KK_OTHER, st);
+  const int M = a.N * a.L;
+  loss_rows_kernel<<<(M + 127) / 128, 128, 0, st>>>(a, dw);
+  loss_reduce_kernel<<<1, 1024, 0, st>>>(a);
+}
+void launch_gather_beta(int N, const long long* tvec, const float* betas, float* out, cudaStream_t st) {
+  ProfScope prof__(KK_OTHER, st);
+  gather_beta_kernel<<<(N + 127) / 128, 128, 0, st>>>(N, tvec, betas, out);
 }
 void launch_rot_denoise(int M, int L, const float* v_t, const float* v_net, const uint8_t* mask_gen, const long long* tvec,
                         const NoisePtrs& nz, const DiffW& dw, float* v_out, cudaStream_t st) {

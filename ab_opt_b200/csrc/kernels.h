@@ -30,7 +30,24 @@ struct InitArgs {
   float* v_out; float* p_out_ang; long long* s_out;
   float* prmsd_out; float* ppl_out;
   uint64_t seed;
+  // FullDPM.forward (training): per-complex steps, the sequence draw on every row, the position noise kept
+  const long long* tvec;        // (N,) steps; nullptr -> T0 for every complex
+  int seq_all_rows;             // 1: _sample(c_t) also where nothing is generated (transition.py:198-199)
+  float* z_out;                 // (M,3) the position noise e_rand (transition.py:74), may be nullptr
 };
+// FullDPM.forward losses (dpm_full.py:156-234; AbDesign :138-190)
+struct LossArgs {
+  int N, L, abdock, pred_x0, has_prmsd, bins;
+  float dmin, dmax;
+  const float* v_0; const float* p_0_ang; const long long* s_0;
+  const float* p_noisy_ang; const long long* s_noisy; const float* z;      // z may be nullptr (denoise_structure = False)
+  const float* R_pred; const float* p_pred; const float* c_den; const float* prmsd_logits;
+  const uint8_t* mask_gen; const uint8_t* mask_res; const long long* tvec;
+  float* rows;                  // scratch [6][M]: rot | pos | seq | squared deviation (A^2) | dist sum | dist count
+  float* out;                   // [5]: rot, pos, seq, prmsd, dist
+};
+void launch_loss(const LossArgs& a, const DiffW& dw, cudaStream_t st);
+void launch_gather_beta(int N, const long long* tvec, const float* betas, float* out, cudaStream_t st);
 
 cudaError_t linear_kernels_init();
 cudaError_t attn_kernels_init();

@@ -156,9 +156,54 @@ class FullDPM(nn.Module, _native.NativeOwner):
     def _unnormalize_position(self, p_norm):
         return p_norm * self.position_scale + self.position_mean
 
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError('FullDPM.forward (training losses + autograd, dpm_full.py:156-234) is not part of this '
-                                  'round: the sm_100a path covers sample() / optimize() and their building blocks')
+    @torch.no_grad()
+    def forward(self, v_0, p_0, s_0, res_feat, pair_feat, mask_generate, mask_res, denoise_structure, denoise_sequence,
+                t=None, noise=None, rng=None):
+        """dpm_full.py:156-234 (AbDesign :138-190): the loss dict of one training step, FORWARD ONLY -- the values are
+        computed by the sm_100a kernels (abopt_loss_forward) and carry no autograd graph; the backward pass is not part
+        of the native path yet.  `noise` (dict of the six draws of one step) replays given draws; otherwise rng='torch'
+        makes the reference's ATen draws in the reference's order, rng='philox' draws inside the kernels."""
+        nm = self.native()
+        N, L = res_feat.shape[:2]
+        dev = self._dummy.device
+        if t is None:
+            t = torch.randint(0, self.num_steps, (N,), dtype=torch.long, device=dev)
+        t = _capi.cuda_i64(t, 't')
+        v_0, p_0, s_0 = _capi.cuda_f32(v_0, 'v_0'), _capi.cuda_f32(p_0, 'p_0'), _capi.cuda_i64(s_0, 's_0')
+        res_feat, pair_feat = _capi.cuda_f32(res_feat, 'res_feat'), _capi.cuda_f32(pair_feat, 'pair_feat')
+        mg, mr = _capi.cuda_mask(mask_generate, 'mask_generate'), _capi.cuda_mask(mask_res, 'mask_res')
+        if res_feat.shape != (N, L, 128) or pair_feat.shape != (N, L, L, 64) or t.shape != (N,):
+            raise ValueError('bad input shapes')
+        flags = (_capi.SAMPLE_STRUCTURE if denoise_structure else 0) | (_capi.SAMPLE_SEQUENCE if denoise_sequence else 0)
+        rng = rng or self.rng
+        M = N * L
+        keep, nz, seed = None, None, 0
+        if noise is None and rng == 'torch':      # transition.py:133 (so3.py:143,123,126,131), :74, :199
+            noise = {}
+            if denoise_structure:
+                noise.update(u=torch.randn(N, L, 3, device=dev), expo_ang=torch.empty(M, 8191, device=dev).exponential_(1),
+                             unif_ang=torch.rand(M, device=dev), gauss_ang=torch.randn(M, device=dev), z_pos=torch.randn(N, L, 3, device=dev))
+            else:
+                noise.update(u=torch.zeros(N, L, 3, device=dev), expo_ang=torch.ones(M, 8191, device=dev),
+                             unif_ang=torch.zeros(M, device=dev), gauss_ang=torch.zeros(M, device=dev), z_pos=torch.zeros(N, L, 3, device=dev))
+            noise['expo_seq'] = torch.empty(M, 20, device=dev).exponential_(1) if denoise_sequence else torch.ones(M, 20, device=dev)
+        if noise is not None:
+            keep = {k: _capi.cuda_f32(noise[k], k) for k in ('u', 'expo_ang', 'unif_ang', 'gauss_ang', 'z_pos', 'expo_seq')}
+            nz = ctypes.byref(_capi.StepNoise(*[keep[k].data_ptr() for k in ('u', 'expo_ang', 'unif_ang', 'gauss_ang', 'z_pos', 'expo_seq')]))
+        else:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        out = torch.zeros(5, device=dev)
+        _capi.check(_capi.lib().abopt_loss_forward(
+            nm.handle, N, L, _capi.ptr(v_0), _capi.ptr(p_0), _capi.ptr(s_0), _capi.ptr(res_feat), _capi.ptr(pair_feat),
+            _capi.ptr(mg), _capi.ptr(mr), flags, _capi.ptr(t), seed, nz, _capi.ptr(out), _capi.stream_ptr(dev)))
+        del keep
+        loss = {}
+        if self.flavour == 'abdock':
+            loss['prmsd'] = out[3]
+            if self.obj == 'pred_x0':
+                loss['dist'] = out[4]
+        loss['rot'], loss['pos'], loss['seq'] = out[0], out[1], out[2]
+        return loss
 
     # ---------------------------------------------------------------- sampling
     @torch.no_grad()

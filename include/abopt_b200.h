@@ -222,6 +222,19 @@ int abopt_sample_host(abopt_model* m, int N, int L, const float* v, const float*
                       float* traj_v, float* traj_p, int64_t* traj_s, float* traj_prmsd,
                       float* traj_ppl);
 
+/* ------------------------------------------------------------------ training forward
+ * FullDPM.forward without autograd (dpm_full.py:156-234; AbDesign flavour :138-190): noise v_0 / p_0 / s_0 to the
+ * per-complex steps t (N,) i64 with the three add_noise calls (transition.py:62-78,120-144,183-200), evaluate
+ * EpsilonNet once and reduce the loss dict on the device.  flags: ABOPT_SAMPLE_STRUCTURE = denoise_structure,
+ * ABOPT_SAMPLE_SEQUENCE = denoise_sequence.  p_0 in Angstrom.  `noise` == NULL -> Philox draws keyed by `seed`, else one
+ * abopt_step_noise record = the reference's draws in its own order.  losses_out: DEVICE pointer to 5 floats
+ *   [0] rot  [1] pos  [2] seq  [3] prmsd (has_prmsd models, else 0)  [4] dist (has_prmsd + obj pred_x0, else 0).
+ * The backward pass (autograd through EpsilonNet) is not part of this library yet. */
+int abopt_loss_forward(abopt_model* m, int N, int L, const float* v_0, const float* p_0, const int64_t* s_0,
+                       const float* res_feat, const float* pair_feat, const uint8_t* mask_generate,
+                       const uint8_t* mask_res, uint32_t flags, const int64_t* t, uint64_t seed,
+                       const abopt_step_noise* noise, float* losses_out, void* stream);
+
 /* Size in bytes of the device scratch the model holds for (N, L); 0 if none allocated yet. */
 size_t abopt_workspace_bytes(const abopt_model* m);
 

@@ -35,6 +35,28 @@ def npz(name, **arrays):
 
 
 @torch.no_grad()
+def make_train_forward():
+    """FullDPM.forward (training losses, dpm_full.py:156-234) of the unmodified reference, both objectives, at per-complex
+    steps t; N=2, L=12 keeps the (N*L, 8191) exponential draw small enough to store."""
+    torch.set_num_threads(1)
+    seed_w, nl, seed_n = 13, 2, 77
+    W = weights.make_state_dict(seed=seed_w, num_layers=nl, flavour='abdock')
+    inp = weights.synthetic_inputs(23, 2, 12, gen_slices=((0, 5), (8, 10)), ragged=True)
+    t = torch.tensor([57, 3])
+    noise = T.draw_step_noise(2, 12, torch.Generator().manual_seed(seed_n))
+    keep = {}
+    for obj in ('pred_x0', 'pred_noise'):
+        model, _ = build_reference_fulldpm(W, num_layers=nl, obj=obj)
+        torch.manual_seed(seed_n)      # the reference draws from the global generator
+        loss = model(inp['v'], inp['p'], inp['s'], inp['res_feat'], inp['pair_feat'], inp['mask_generate'], inp['mask_res'],
+                     denoise_structure=True, denoise_sequence=True, t=t)
+        for k, v in loss.items():
+            keep[f'{obj}_{k}'] = v
+    npz('train_forward.npz', seed_w=seed_w, num_layers=nl, seed_in=23, N=2, L=12, t=t, **keep,
+        **{'noise_' + k: v for k, v in noise.items()})
+
+
+@torch.no_grad()
 def main():
     torch.set_num_threads(1)          # single-thread reference: reproducible reduction order
     # ---------------------------------------------------------------- GABlock / GAEncoder
@@ -112,4 +134,8 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'train_forward':      # only the training fixture (the others are unchanged)
+        make_train_forward()
+    else:
+        main()
+        make_train_forward()

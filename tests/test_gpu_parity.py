@@ -352,3 +352,56 @@ def test_philox_angle_distribution_matches_histogram():
     idx = torch.searchsorted(X[1:].contiguous(), probes).clamp(max=len(cdf) - 1)
     ks = (emp - cdf[idx]).abs().max().item()
     assert ks < 0.04, ks
+
+
+# ------------------------------------------------------------------------------------------ training forward (a23)
+@pytest.mark.parametrize('obj', ['pred_x0', 'pred_noise'])
+def test_training_forward_against_reference_fixture(golden_dir, obj):
+    """FullDPM.forward on the sm_100a path (abopt_loss_forward) vs the loss dict of the unmodified reference on the same
+    replayed draws (tests/golden/train_forward.npz; dpm_full.py:156-234)."""
+    g = load(golden_dir, 'train_forward.npz')
+    W = weights.make_state_dict(seed=g['seed_w'], num_layers=g['num_layers'], flavour='abdock')
+    inp = weights.synthetic_inputs(g['seed_in'], g['N'], g['L'], gen_slices=((0, 5), (8, 10)), ragged=True)
+    model = build_model(W, g['num_layers'], obj=obj)
+    ci = cu(inp)
+    noise = {k[len('noise_'):]: v.to(DEV) for k, v in g.items() if k.startswith('noise_')}
+    got = model(ci['v'], ci['p'], ci['s'], ci['res_feat'], ci['pair_feat'], ci['mask_generate'], ci['mask_res'], True, True,
+                t=g['t'].to(DEV), noise=noise)
+    want = {k[len(obj) + 1:]: v for k, v in g.items() if k.startswith(obj + '_')}
+    assert sorted(got) == sorted(want)
+    for k in want:
+        torch.testing.assert_close(got[k].cpu(), torch.as_tensor(want[k]), rtol=1e-4, atol=1e-5, msg=lambda m, k=k: f'{k}: {m}')
+
+
+@pytest.mark.parametrize('flavour,ds,dq', [('abdesign', True, True), ('abdock', True, False), ('abdesign', False, True)])
+def test_training_forward_vs_oracle(flavour, ds, dq):
+    """Larger ragged batch, both flavours and the denoise_structure / denoise_sequence switches, against the oracle
+    (fp32 and fp64) on replayed draws."""
+    from oracle import training
+    N, L = 3, 72
+    W = weights.make_state_dict(seed=17, num_layers=2, flavour=flavour)
+    inp = weights.synthetic_inputs(31, N, L, gen_slices=((10, 22), (40, 44)), ragged=True)
+    t = torch.tensor([88, 12, 40])
+    noise = T.draw_step_noise(N, L, torch.Generator().manual_seed(5))
+    obj = 'pred_x0' if flavour == 'abdock' else 'pred_noise'
+    args = (inp['v'], inp['p'], inp['s'], inp['res_feat'], inp['pair_feat'], inp['mask_generate'], inp['mask_res'], ds, dq, t)
+    ref32 = training.loss_forward(W, *args, noise, flavour=flavour, obj=obj)
+    W64 = {k: (v.double() if v.is_floating_point() else v) for k, v in W.items()}
+    a64 = [x.double() if torch.is_tensor(x) and x.is_floating_point() else x for x in args]
+    ref64 = training.loss_forward(W64, *a64, to64(noise), flavour=flavour, obj=obj)
+    model = build_model(W, 2, flavour=flavour, obj=obj)
+    ci = cu(inp)
+    got = model(ci['v'], ci['p'], ci['s'], ci['res_feat'], ci['pair_feat'], ci['mask_generate'], ci['mask_res'], ds, dq,
+                t=t.to(DEV), noise=cu(noise))
+    assert sorted(got) == sorted(ref32)
+    for k in ref32:
+        e_got = abs(got[k].double().item() - ref64[k].item())
+        e_ref = abs(ref32[k].double().item() - ref64[k].item())
+        assert e_got <= 2 * e_ref + 1e-5 * max(1.0, abs(ref64[k].item())), f'{k}: cuda {got[k].item()} oracle64 {ref64[k].item()}'
+    # Philox mode: finite, deterministic under torch.manual_seed
+    torch.manual_seed(3)
+    a = model(ci['v'], ci['p'], ci['s'], ci['res_feat'], ci['pair_feat'], ci['mask_generate'], ci['mask_res'], ds, dq, t=t.to(DEV))
+    torch.manual_seed(3)
+    b = model(ci['v'], ci['p'], ci['s'], ci['res_feat'], ci['pair_feat'], ci['mask_generate'], ci['mask_res'], ds, dq, t=t.to(DEV))
+    for k in a:
+        assert torch.isfinite(a[k]).all() and torch.equal(a[k], b[k])

@@ -142,3 +142,19 @@ def test_schedule_properties():
     assert s['betas'][0] == 0 and (s['betas'][1:] > 0).all() and s['betas'].max() <= 0.999
     assert (s['alpha_bars'][1:] < s['alpha_bars'][:-1]).all()
     assert math.isclose(s['alpha_bars'][0].item(), 1.0)
+
+
+@pytest.mark.parametrize('obj', ['pred_x0', 'pred_noise'])
+def test_training_forward_matches_reference(golden_dir, obj):
+    """oracle.training.loss_forward vs FullDPM.forward of the unmodified reference (tests/golden/train_forward.npz)."""
+    from oracle import training
+    g = load(golden_dir, 'train_forward.npz')
+    W = weights.make_state_dict(seed=g['seed_w'], num_layers=g['num_layers'], flavour='abdock')
+    inp = weights.synthetic_inputs(g['seed_in'], g['N'], g['L'], gen_slices=((0, 5), (8, 10)), ragged=True)
+    noise = {k[len('noise_'):]: v for k, v in g.items() if k.startswith('noise_')}
+    got = training.loss_forward(W, inp['v'], inp['p'], inp['s'], inp['res_feat'], inp['pair_feat'], inp['mask_generate'],
+                                inp['mask_res'], True, True, g['t'], noise, flavour='abdock', obj=obj)
+    want = {k[len(obj) + 1:]: v for k, v in g.items() if k.startswith(obj + '_')}
+    assert sorted(got) == sorted(want)
+    for k in want:
+        torch.testing.assert_close(got[k], torch.as_tensor(want[k]), rtol=2e-5, atol=2e-6, msg=lambda m, k=k: f"{k}: {m}")

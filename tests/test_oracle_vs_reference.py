@@ -109,3 +109,24 @@ def test_abdesign_flavour_eps_net():
     torch.testing.assert_close(out[1], ref[1], rtol=0, atol=5e-6)
     torch.testing.assert_close(out[2], ref[2], rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(out[3], ref[3], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize('obj', ['pred_x0', 'pred_noise'])
+def test_training_forward_losses(obj):
+    """FullDPM.forward (dpm_full.py:156-234) vs oracle.training.loss_forward on replayed draws: the reference draws from
+    the default generator inside its three add_noise calls, the oracle receives the same stream as a noise record."""
+    from oracle import training, transitions as T
+    W = weights.make_state_dict(seed=5, num_layers=2, flavour='abdock')
+    model, _ = build_reference_fulldpm(W, num_layers=2, obj=obj)
+    inp = weights.synthetic_inputs(8, 3, 24, gen_slices=((0, 6), (14, 18)), ragged=True)
+    t = torch.tensor([57, 3, 99])
+    torch.manual_seed(11)
+    with torch.no_grad():
+        ref = model(inp['v'], inp['p'], inp['s'], inp['res_feat'], inp['pair_feat'], inp['mask_generate'], inp['mask_res'],
+                    denoise_structure=True, denoise_sequence=True, t=t)
+    noise = T.draw_step_noise(3, 24, torch.Generator().manual_seed(11))
+    got = training.loss_forward(W, inp['v'], inp['p'], inp['s'], inp['res_feat'], inp['pair_feat'], inp['mask_generate'],
+                                inp['mask_res'], True, True, t, noise, flavour='abdock', obj=obj)
+    assert sorted(got) == sorted(ref)
+    for k in ref:
+        torch.testing.assert_close(got[k], ref[k], rtol=2e-5, atol=2e-6, msg=lambda m, k=k: f'{k}: {m}')
