@@ -526,6 +526,9 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
     return fail(ABOPT_ERR_ARG, "pair_bias_kernel: L too large for shared memory");
   // the six input projections: tcgen05 3xTF32 GEMM (x raw = "hi" plane, x_lo = "lo" plane)
   if (x_lo == nullptr) { launch_lo(x, w.xin_lo, (size_t)M * F, st); x_lo = w.xin_lo; }
+  // ABOPT_OUTT_LEGACY=1: materialise feat_lo and use the plain 3xTF32 GEMM for out_transform (A/B comparisons)
+  static const bool outt_legacy = [] { const char* ev = getenv("ABOPT_OUTT_LEGACY"); return ev && ev[0] == '1'; }();
+  float* flo = outt_legacy ? w.feat_lo : nullptr;
   for (int b0 = 0; b0 < N; b0 += w.NB) {
     const int nb = (N - b0 < w.NB) ? (N - b0) : w.NB;
     // everything a chunk of complexes produces and consumes below stays L2 resident: its projections (packed attention
@@ -539,16 +542,17 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
     }
     // logits (node + spatial + pair bias, scaled, masked) and softmax on the tensor cores -> alpha (L2 resident chunk)
     if (!launch_attn_logits_tc(nb, b0, N, L, w.Lp, w.op, bias, mask, w.alpha, st)) return fail(ABOPT_ERR_CUDA, "attn_logits_tc launch failed");
-    if (!launch_pair_stream(nb, b0, L, w.Lp, z, mask, w.alpha, w.feat, w.feat_lo, st))
+    if (!launch_pair_stream(nb, b0, L, w.Lp, z, mask, w.alpha, w.feat, flo, st))
       return fail(ABOPT_ERR_ARG, "pair_stream_kernel: L too large for shared memory");
-    if (!launch_aggr_tc(nb, b0, N, L, w.Lp, w.alpha, w.op.VT, w.op.VT_lo, R, t, w.feat, w.feat_lo, st))
+    if (!launch_aggr_tc(nb, b0, N, L, w.Lp, w.alpha, w.op.VT, w.op.VT_lo, R, t, w.feat, flo, st))
       return fail(ABOPT_ERR_CUDA, "aggr_tc launch failed");
     if (alpha_tap) launch_alpha_tap(nb, b0, L, w.Lp, w.alpha, alpha_tap, st);
   }
   if (x_out) {
     // out_transform (K = 1824) on the tensor cores, then mask / residual / LN / MLP / LN
-    if (!launch_gemm3x_plain(M, F, NFEAT, w.feat, w.feat_lo, NFEAT, bw.Wout, bw.Wout_lo, NFEAT, w.outD, F, bw.bout, st))
-      return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (out_transform)");
+    const bool ok = flo ? launch_gemm3x_plain(M, F, NFEAT, w.feat, flo, NFEAT, bw.Wout, bw.Wout_lo, NFEAT, w.outD, F, bw.bout, st)
+                        : launch_gemm3x_splitA(M, F, NFEAT, w.feat, NFEAT, bw.Wout, bw.Wout_lo, NFEAT, w.outD, F, bw.bout, st);
+    if (!ok) return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (out_transform)");
     launch_tail(M, w.feat, w.outD, x, mask, bw, x_out, x_lo_out, st);
   }
   CHECK_LAUNCH();

@@ -328,11 +328,13 @@ attn_logits_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
 //                             running ahead of the epilogue (the bias is the HBM stream of this kernel)
 //   warp 1      MMA issuer -- accumulates tile n into TMEM buffer n & 1 (2 x 256 columns) while the epilogue warps are still
 //               busy with tile n - 1; per key group 16 correction products first, then the 8 hi*hi ones (truncation note above)
+//   warps 18-19 splitters  -- build the tf32 "lo" plane (x - trunc_tf32(x)) of every landed operand box in shared memory,
+//               so QA_lo / KB_lo never exist in global memory (saves their write in the projection kernel and their read here)
 //   warps 2-17  epilogue   -- 4 threads per query row; thread (row, kq) owns keys 32 m + 8 kq + (0..7) of every chunk m:
 //               TMEM -> registers (buffer released at once), per chunk bias from shared memory (conflict-free: lanes are
 //               consecutive queries) -> logits; max / exp / sum exchanged through shared memory; alpha stored with 256-bit
 //               global stores (one full 32-byte sector each)
-constexpr int AP_THREADS = 576, AP_EPI = 512;
+constexpr int AP_THREADS = 640, AP_EPI = 512, AP_SPLIT = 64;      // (18 warps are allocated registers as 20 anyway)
 constexpr int AP_BST = 3, AP_BGRP_BYTES = 4 * 64 * 32 * 4;            // key-group stage: 64 keys x (hi k0 | hi k1 | lo k0 | lo k1) = 32 KB
 constexpr int AP_KBOX = 64 * 32 * 4;                                  // one key box: 64 rows x 32 floats
 constexpr int AP_NBIAS = 3, AP_BIAS_BYTES = 32 * 128 * 4;             // bias chunk: 32 keys x 128 queries
@@ -382,7 +384,9 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
   uint64_t* bias_empty = bias_full + AP_NBIAS;  // [AP_NBIAS]
   uint64_t* tmem_full = bias_empty + AP_NBIAS;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* a_split = tmem_empty + 2;
+  uint64_t* b_split = a_split + 1;        // [AP_BST]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_split + AP_BST);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = a.L, Lp = a.Lp;
@@ -391,7 +395,8 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
 
   if (threadIdx.x == 0) {
     mbar_init(a_full, 1); mbar_init(a_empty, 1);
-    for (int s = 0; s < AP_BST; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    mbar_init(a_split, AP_SPLIT);
+    for (int s = 0; s < AP_BST; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); mbar_init(&b_split[s], AP_SPLIT); }
     for (int s = 0; s < AP_NBIAS; ++s) { mbar_init(&bias_full[s], 1); mbar_init(&bias_empty[s], AP_EPI / 32); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], AP_EPI / 32); }
     mbar_fence_init();
@@ -416,11 +421,9 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
             if (mbar_try_wait(a_empty, (on & 1) ^ 1)) {
               unsigned char* A = smem + AL_A_OFF;
               const int r0 = row_base + it * AL_BM;
-              mbar_expect_tx(a_full, 2 * AL_OPER_BYTES);
+              mbar_expect_tx(a_full, AL_OPER_BYTES);          // raw fp32 = the "hi" plane; the splitters add the lo plane
               tma_load_2d(A, &tmQh, 0, r0, a_full);
               tma_load_2d(A + AL_BOX_BYTES, &tmQh, 32, r0, a_full);
-              tma_load_2d(A + AL_OPER_BYTES, &tmQl, 0, r0, a_full);
-              tma_load_2d(A + AL_OPER_BYTES + AL_BOX_BYTES, &tmQl, 32, r0, a_full);
               ostep = 1;
             }
           } else {
@@ -428,11 +431,9 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
             if (mbar_try_wait(&b_empty[s], ((og / AP_BST) & 1) ^ 1)) {
               unsigned char* B = smem + AP_B_OFF + s * AP_BGRP_BYTES;
               const int r0 = row_base + (ostep - 1) * 64;
-              mbar_expect_tx(&b_full[s], AP_BGRP_BYTES);
+              mbar_expect_tx(&b_full[s], 2 * AP_KBOX);
               tma_load_2d(B, &tmKh, 0, r0, &b_full[s]);
               tma_load_2d(B + AP_KBOX, &tmKh, 32, r0, &b_full[s]);
-              tma_load_2d(B + 2 * AP_KBOX, &tmKl, 0, r0, &b_full[s]);
-              tma_load_2d(B + 3 * AP_KBOX, &tmKl, 32, r0, &b_full[s]);
               ++og;
               if (++ostep > NGRP) { ostep = 0; ++on; otile += gridDim.x; }
             }
@@ -458,10 +459,10 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
       const int buf = n & 1;
       mbar_wait(&tmem_empty[buf], ((n >> 1) & 1) ^ 1);    // the epilogue has read this TMEM buffer (tile n - 2)
-      mbar_wait(a_full, n & 1);
+      mbar_wait(a_split, n & 1);                          // query operand landed AND its lo plane is built
       for (int gi = 0; gi < NGRP; ++gi, ++g) {
         const int s = g % AP_BST;
-        mbar_wait(&b_full[s], (g / AP_BST) & 1);
+        mbar_wait(&b_split[s], (g / AP_BST) & 1);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_hi = smem_u32(smem + AL_A_OFF), a_lo = a_hi + AL_OPER_BYTES;
@@ -482,6 +483,32 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
           if (gi == NGRP - 1) { mma_commit(a_empty); mma_commit(&tmem_full[buf]); }
         }
         __syncwarp();
+      }
+    }
+  } else if (warp >= 18) {
+    // ===================== splitters: lo = x - trunc_tf32(x), same swizzled offsets as the hi plane =====================
+    const int st = threadIdx.x - 18 * 32;                 // 0..63
+    auto split = [&](const unsigned char* hi, unsigned char* lo, int n16) {
+      const float4* src = reinterpret_cast<const float4*>(hi);
+      float4* dst = reinterpret_cast<float4*>(lo);
+#pragma unroll 4
+      for (int k = st; k < n16; k += AP_SPLIT) {
+        const float4 v = src[k];
+        dst[k] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+      }
+      fence_async_smem();                                 // generic-proxy writes -> visible to the tensor core (async proxy)
+    };
+    int n = 0, g = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+      mbar_wait(a_full, n & 1);
+      split(smem + AL_A_OFF, smem + AL_A_OFF + AL_OPER_BYTES, AL_OPER_BYTES / 16);
+      mbar_arrive(a_split);
+      for (int gi = 0; gi < NGRP; ++gi, ++g) {
+        const int s = g % AP_BST;
+        mbar_wait(&b_full[s], (g / AP_BST) & 1);
+        unsigned char* B = smem + AP_B_OFF + s * AP_BGRP_BYTES;
+        split(B, B + 2 * AP_KBOX, 2 * AP_KBOX / 16);
+        mbar_arrive(&b_split[s]);
       }
     }
   } else {
@@ -576,6 +603,7 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
 }
 
 static bool g_attn_legacy = false;      // ABOPT_ATTN_LEGACY=1: one-tile-per-CTA kernel (A/B comparisons)
+bool attn_needs_qk_lo(int L) { return g_attn_legacy || ((L + AL_BN - 1) / AL_BN) * AL_BN > 256; }
 cudaError_t attn_tc_init() {
   { const char* ev = getenv("ABOPT_ATTN_LEGACY"); g_attn_legacy = ev && ev[0] == '1'; }
   cudaError_t e = cudaFuncSetAttribute(attn_logits_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AL_SMEM);
@@ -796,7 +824,7 @@ aggr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (c < AG2_NOUT) {
           const float v = stage[rr * AG2_PITCH + c];
           a.feat[base + col[k]] = v;
-          a.feat_lo[base + col[k]] = tf32_lo(v);
+          if (a.feat_lo) a.feat_lo[base + col[k]] = tf32_lo(v);
         }
       }
     }

@@ -267,7 +267,7 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs 
     if (!live) {
       // masked query: alpha row = 0 (ga.py:25) -> zero pair aggregate
       float* alpha_row0 = a.alpha + ((size_t)(bl * H) * L + i) * Lp;
-      for (int o = lane; o < H * C; o += 32) { feat_row[o] = 0.f; feat_lo_row[o] = 0.f; }
+      for (int o = lane; o < H * C; o += 32) { feat_row[o] = 0.f; if (a.feat_lo) feat_lo_row[o] = 0.f; }
       for (int o = lane; o < H * Lp; o += 32) {
         const int h = o / Lp, j = o - h * Lp;
         alpha_row0[(size_t)h * L * Lp + j] = 0.f;
@@ -332,8 +332,10 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs 
       const int off = (h0 + hh) * C + 4 * l;
       *reinterpret_cast<float4*>(feat_row + off) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
       *reinterpret_cast<float4*>(feat_row + off + 32) = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
-      *reinterpret_cast<float4*>(feat_lo_row + off) = make_float4(tf32_lo(o[0].x), tf32_lo(o[0].y), tf32_lo(o[1].x), tf32_lo(o[1].y));
-      *reinterpret_cast<float4*>(feat_lo_row + off + 32) = make_float4(tf32_lo(o[2].x), tf32_lo(o[2].y), tf32_lo(o[3].x), tf32_lo(o[3].y));
+      if (a.feat_lo) {                                   // only the non-splitting out_transform GEMM reads a lo plane
+        *reinterpret_cast<float4*>(feat_lo_row + off) = make_float4(tf32_lo(o[0].x), tf32_lo(o[0].y), tf32_lo(o[1].x), tf32_lo(o[1].y));
+        *reinterpret_cast<float4*>(feat_lo_row + off + 32) = make_float4(tf32_lo(o[2].x), tf32_lo(o[2].y), tf32_lo(o[3].x), tf32_lo(o[3].y));
+      }
     }
   }
 }

@@ -57,6 +57,9 @@ void launch_lo(const float* in, float* lo, size_t n, cudaStream_t st);
 bool launch_gemm3x_plain(int M, int N, int K, const float* Ah, const float* Al, int lda, const float* Bh, const float* Bl, int ldb,
                          float* D, int ldd, const float* bias, cudaStream_t st);
 
+bool launch_gemm3x_splitA(int M, int N, int K, const float* A, int lda, const float* Bh, const float* Bl, int ldb,
+                          float* D, int ldd, const float* bias, cudaStream_t st);
+
 // operands of the tensor-core attention kernels, produced by the projection GEMM epilogue (k_tc.cu: EpiProjPack)
 struct AttnOperands {
   float* QA; float* QA_lo;      // [N][H][L][64]
@@ -72,6 +75,7 @@ bool launch_aggr_tc(int nb, int b0, int N, int L, int Lp, const float* alpha, co
 bool make_tmap(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 bool make_tmap_plain(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
 cudaError_t attn_tc_init();
+bool attn_needs_qk_lo(int L);      // true when the logits kernel for this length reads QA_lo / KB_lo from global memory
 void attn_debug_clocks(long long* out16);
 // final logits + softmax on the tensor cores: alpha[chunk][h][i][Lp] for complexes [b0, b0 + nb)
 bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOperands& op, const float* bias_layer, const uint8_t* mask,
