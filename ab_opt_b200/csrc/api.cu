@@ -224,6 +224,7 @@ extern "C" int abopt_model_create(const abopt_config* cfg, int device, abopt_mod
   CUDA_TRY(pair_stream_init());
   CUDA_TRY(attn_tc_init());
   CUDA_TRY(aggr_tc_init());
+  CUDA_TRY(tail_tc_init());
   abopt_model* m = new abopt_model();
   m->cfg = *cfg;
   m->device = device;
@@ -343,6 +344,14 @@ extern "C" int abopt_model_finalize(abopt_model* m) {
     reg(&b.W1_t, pk.put(transpose(F32(m, p + "mlp_transition.0.weight"), F, F))); reg(&b.b1, pk.put(F32(m, p + "mlp_transition.0.bias"), F * 4));
     reg(&b.W2_t, pk.put(transpose(F32(m, p + "mlp_transition.2.weight"), F, F))); reg(&b.b2, pk.put(F32(m, p + "mlp_transition.2.bias"), F * 4));
     reg(&b.W3_t, pk.put(transpose(F32(m, p + "mlp_transition.4.weight"), F, F))); reg(&b.b3, pk.put(F32(m, p + "mlp_transition.4.bias"), F * 4));
+    {
+      std::vector<float> wm((size_t)3 * F * F);
+      int li = 0;
+      for (const char* nm : {"mlp_transition.0.weight", "mlp_transition.2.weight", "mlp_transition.4.weight"})
+        memcpy(wm.data() + (size_t)(li++) * F * F, F32(m, p + nm), sizeof(float) * F * F);
+      reg(&b.Wmlp, pk.put(wm));
+      reg(&b.Wmlp_lo, pk.put(lo_plane(wm.data(), wm.size())));
+    }
   }
   EpsW& e = m->eps;
   e = EpsW{};
@@ -550,10 +559,16 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
   }
   if (x_out) {
     // out_transform (K = 1824) on the tensor cores, then mask / residual / LN / MLP / LN
-    const bool ok = flo ? launch_gemm3x_plain(M, F, NFEAT, w.feat, flo, NFEAT, bw.Wout, bw.Wout_lo, NFEAT, w.outD, F, bw.bout, st)
-                        : launch_gemm3x_splitA(M, F, NFEAT, w.feat, NFEAT, bw.Wout, bw.Wout_lo, NFEAT, w.outD, F, bw.bout, st);
-    if (!ok) return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (out_transform)");
-    launch_tail(M, w.feat, w.outD, x, mask, bw, x_out, x_lo_out, st);
+    // ABOPT_TAIL_LEGACY=1: out_transform GEMM + CUDA-core tail_kernel instead of the fused tensor-core tail (A/B comparisons)
+    static const bool tail_legacy = [] { const char* ev = getenv("ABOPT_TAIL_LEGACY"); return ev && ev[0] == '1'; }();
+    if (!flo && !tail_legacy) {
+      if (!launch_outT_tail(M, w.feat, x, mask, bw, x_out, x_lo_out, st)) return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (tail)");
+    } else {
+      const bool ok = flo ? launch_gemm3x_plain(M, F, NFEAT, w.feat, flo, NFEAT, bw.Wout, bw.Wout_lo, NFEAT, w.outD, F, bw.bout, st)
+                          : launch_gemm3x_splitA(M, F, NFEAT, w.feat, NFEAT, bw.Wout, bw.Wout_lo, NFEAT, w.outD, F, bw.bout, st);
+      if (!ok) return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (out_transform)");
+      launch_tail(M, w.feat, w.outD, x, mask, bw, x_out, x_lo_out, st);
+    }
   }
   CHECK_LAUNCH();
   return ABOPT_OK;

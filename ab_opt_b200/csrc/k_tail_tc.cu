@@ -1,0 +1,323 @@
+// outT_tail_kernel: the whole tail of a GABlock in ONE kernel on the 5th-gen tensor cores (ga.py:173-178):
+//   out_transform (1824 -> 128, bias) -> mask_zero -> LayerNorm(x + .) -> 3-layer ReLU MLP -> LayerNorm(res + .)
+// Phase 1 is gemm3x_splitA_kernel (k_tc.cu): D[128 rows][128] = feat[128][1824] * W_out^T as 3xTF32, raw feat streamed
+// from HBM through a 3-stage TMA ring, its tf32 lo plane built on chip, accumulators promoted every 8 k-blocks.
+// Phase 2 keeps the row tile on chip: the epilogue threads (thread = row x half of the 128 columns) apply bias / mask /
+// residual / LayerNorm 1 in registers, write the activations as a K-major 128-byte-swizzled A operand (hi and lo plane)
+// into the drained pipeline memory, and the three 128 x 128 MLP layers run as tcgen05 GEMMs whose weights (L2 resident)
+// arrive through a 2-stage TMA ring; bias + ReLU happen between layers in registers, the residual and LayerNorm 2 at the
+// end.  Replaces gemm3x + the FFMA tail_kernel (which spent 58 us per layer on CUDA-core MLPs) and the outD round trip.
+#include "tc.cuh"
+#include "params.cuh"
+#include "kernels.h"
+
+namespace abopt {
+
+using namespace tc;
+
+constexpr int OT_THREADS = 320, OT_ST = 3, OT_KCH = 8, OT_BK = 32;
+constexpr int OT_A = 128 * OT_BK * 4;                     // 16 KB: 128 rows x 32 tf32
+constexpr int OT_STAGE = 4 * OT_A;                        // 64 KB: A raw | A lo | B hi | B lo
+constexpr int OT_ACT_KB = 2 * OT_A;                       // phase 2: one activation k-block, hi | lo
+constexpr int OT_W_OFF = 4 * OT_ACT_KB;                   // phase 2: weight stages start behind the 4 activation k-blocks
+constexpr int OT_BAR_OFF = OT_ST * OT_STAGE;              // 192 KB
+constexpr int OT_EXCH_OFF = OT_BAR_OFF + 256;             // LayerNorm partial sums: [2 kinds][2 halves][128 rows]
+constexpr int OT_SMEM = OT_EXCH_OFF + 4 * 128 * 4 + 1024;
+
+struct TailArgs {
+  const float* x; const uint8_t* mask;
+  const float* bout; const float* ln1_g; const float* ln1_b;
+  const float* b1; const float* b2; const float* b3;
+  const float* ln2_g; const float* ln2_b;
+  float* x_out; float* x_lo_out;
+};
+
+__device__ __forceinline__ void epi_sync256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(OT_THREADS, 1)
+outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                 const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmWh,
+                 const __grid_constant__ CUtensorMap tmWl, int M, int K, const TailArgs ta) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + OT_BAR_OFF);
+  uint64_t* empty = full + OT_ST;
+  uint64_t* split = empty + OT_ST;
+  uint64_t* tmem_full = split + OT_ST;         // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint64_t* w_full = tmem_empty + 2;           // [2]
+  uint64_t* w_empty = w_full + 2;              // [2]
+  uint64_t* act_ready = w_empty + 2;
+  uint64_t* acc_full = act_ready + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  float* exch_sum = reinterpret_cast<float*>(smem + OT_EXCH_OFF);      // [2][128]
+  float* exch_sq = exch_sum + 256;                                     // [2][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128;
+  const int nkb = K / OT_BK;
+  const int nchunk = (nkb + OT_KCH - 1) / OT_KCH;
+  constexpr uint32_t ACC_COLS = 256;                                   // main 128 | corrections 128
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < OT_ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&split[s], 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); mbar_init(&w_full[b], 1); mbar_init(&w_empty[b], 1); }
+    mbar_init(act_ready, 8); mbar_init(acc_full, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl); tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWl);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int last_c = nchunk - 1;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % OT_ST;
+        mbar_wait(&empty[s], ((kb / OT_ST) & 1) ^ 1);
+        unsigned char* st = smem + s * OT_STAGE;
+        mbar_expect_tx(&full[s], 3 * OT_A);
+        tma_load_2d(st, &tmA, kb * OT_BK, m0, &full[s]);
+        tma_load_2d(st + 2 * OT_A, &tmBh, kb * OT_BK, 0, &full[s]);
+        tma_load_2d(st + 3 * OT_A, &tmBl, kb * OT_BK, 0, &full[s]);
+      }
+      // phase 2: the pipeline memory is free once every out_transform MMA has retired
+      mbar_wait(&tmem_full[last_c & 1], (last_c >> 1) & 1);
+      for (int g = 0; g < 12; ++g) {
+        const int l = g >> 2, kb = g & 3, s = g & 1;
+        mbar_wait(&w_empty[s], ((g >> 1) & 1) ^ 1);
+        unsigned char* st = smem + OT_W_OFF + s * OT_ACT_KB;
+        mbar_expect_tx(&w_full[s], 2 * OT_A);
+        tma_load_2d(st, &tmWh, kb * OT_BK, l * 128, &w_full[s]);
+        tma_load_2d(st + OT_A, &tmWl, kb * OT_BK, l * 128, &w_full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = idesc_tf32(128, 128);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % OT_ST;
+      const int c = kb / OT_KCH, buf = c & 1;
+      const bool first = (kb % OT_KCH) == 0, last = (kb % OT_KCH) == OT_KCH - 1 || kb == nkb - 1;
+      if (first && c >= 2) mbar_wait(&tmem_empty[buf], ((c >> 1) - 1) & 1);
+      mbar_wait(&split[s], (kb / OT_ST) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_hi = smem_u32(smem + s * OT_STAGE), a_lo = a_hi + OT_A, b_hi = a_hi + 2 * OT_A, b_lo = a_hi + 3 * OT_A;
+        const uint32_t d_main = tmem_base + buf * ACC_COLS, d_small = d_main + 128;
+#pragma unroll
+        for (int k = 0; k < OT_BK / 8; ++k) {
+          const uint64_t dah = smem_desc_sw128(a_hi + k * 32), dal = smem_desc_sw128(a_lo + k * 32);
+          const uint64_t dbh = smem_desc_sw128(b_hi + k * 32), dbl = smem_desc_sw128(b_lo + k * 32);
+          const uint32_t acc = (first && k == 0) ? 0u : 1u;
+          mma_tf32(d_main, dah, dbh, idesc, acc);
+          mma_tf32(d_small, dah, dbl, idesc, acc);
+          mma_tf32(d_small, dal, dbh, idesc, 1u);
+        }
+        mma_commit(&empty[s]);
+        if (last) mma_commit(&tmem_full[buf]);
+      }
+      __syncwarp();
+    }
+    // phase 2: three 128 x 128 x 128 layers, A = activations written by the epilogue warps, accumulators in TMEM buffer 0
+    for (int l = 0; l < 3; ++l) {
+      mbar_wait(act_ready, l & 1);
+      tc_fence_after();
+      for (int kb = 0; kb < 4; ++kb) {
+        const int g = l * 4 + kb, s = g & 1;
+        mbar_wait(&w_full[s], (g >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_hi = smem_u32(smem + kb * OT_ACT_KB), a_lo = a_hi + OT_A;
+          const uint32_t b_hi = smem_u32(smem + OT_W_OFF + s * OT_ACT_KB), b_lo = b_hi + OT_A;
+          const uint32_t d_main = tmem_base, d_small = tmem_base + 128;
+#pragma unroll
+          for (int k = 0; k < OT_BK / 8; ++k) {
+            const uint64_t dah = smem_desc_sw128(a_hi + k * 32), dal = smem_desc_sw128(a_lo + k * 32);
+            const uint64_t dbh = smem_desc_sw128(b_hi + k * 32), dbl = smem_desc_sw128(b_lo + k * 32);
+            const uint32_t acc = (kb == 0 && k == 0) ? 0u : 1u;
+            mma_tf32(d_main, dah, dbh, idesc, acc);
+            mma_tf32(d_small, dah, dbl, idesc, acc);
+            mma_tf32(d_small, dal, dbh, idesc, 1u);
+          }
+          mma_commit(&w_empty[s]);
+          if (kb == 3) mma_commit(acc_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== splitters + epilogue (warps 2..9) =====================
+    const int q = warp & 3;                                            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;                                  // which 64 of the 128 columns
+    const int et = (warp - 2) * 32 + lane;                             // 0..255
+    const int te = q * 32 + lane;                                      // row in the tile
+    const int row = m0 + te;
+    const int c0 = half * 64;
+    float v[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = 0.f;
+    auto promote = [&](int c) {
+      const int buf = c & 1;
+      mbar_wait(&tmem_full[buf], (c >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + c0;
+#pragma unroll
+      for (int cc = 0; cc < 64; cc += 32) {
+        float tm[32], ts[32];
+        tmem_ld_32x32(tbase + cc, tm);
+        tmem_ld_32x32(tbase + 128 + cc, ts);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[cc + i] += tm[i] + ts[i];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    };
+    int promoted = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % OT_ST;
+      mbar_wait(&full[s], (kb / OT_ST) & 1);
+      const float4* src = reinterpret_cast<const float4*>(smem + s * OT_STAGE);
+      float4* dst = reinterpret_cast<float4*>(smem + s * OT_STAGE + OT_A);
+#pragma unroll
+      for (int m = 0; m < OT_A / 16 / 256; ++m) {
+        const float4 x = src[et + 256 * m];
+        dst[et + 256 * m] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&split[s]);
+      if (kb % OT_KCH == 2 && kb / OT_KCH - 1 == promoted && kb >= OT_KCH) { promote(promoted); ++promoted; }
+    }
+    while (promoted < nchunk) { promote(promoted); ++promoted; }
+
+    // ---------------- phase 2 ----------------
+    const bool valid = row < M;
+    const size_t grow = (size_t)(valid ? row : 0) * F + c0;
+    // LayerNorm over the 128 columns of a row held by two threads (common/layers.py:146-155: biased variance, eps inside
+    // the sqrt): partial sums exchanged through shared memory
+    auto layer_norm = [&](float (&h)[64], const float* gamma, const float* beta) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) s += h[i];
+      exch_sum[half * 128 + te] = s;
+      epi_sync256();
+      const float mean = (exch_sum[te] + exch_sum[128 + te]) * (1.f / 128.f);
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) { h[i] -= mean; sq += h[i] * h[i]; }
+      exch_sq[half * 128 + te] = sq;
+      epi_sync256();
+      const float sd = sqrtf((exch_sq[te] + exch_sq[128 + te]) * (1.f / 128.f) + 1e-10f);
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c0 + i)), b = __ldg(reinterpret_cast<const float4*>(beta + c0 + i));
+        h[i] = h[i] / sd * g.x + b.x; h[i + 1] = h[i + 1] / sd * g.y + b.y;
+        h[i + 2] = h[i + 2] / sd * g.z + b.z; h[i + 3] = h[i + 3] / sd * g.w + b.w;
+      }
+    };
+    // this thread's 64 activations -> A operand of the next layer: k-blocks 2 half, 2 half + 1; row te of a k-block is 128
+    // bytes, its 16-byte chunk c sits at (c ^ (te & 7)) (128-byte swizzle, what the UMMA descriptor expects)
+    auto store_act = [&](const float (&h)[64]) {
+#pragma unroll
+      for (int kbl = 0; kbl < 2; ++kbl) {
+        unsigned char* base = smem + (2 * half + kbl) * OT_ACT_KB + te * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int i = kbl * 32 + c * 4;
+          const uint32_t off = (uint32_t)((c ^ (te & 7)) << 4);
+          *reinterpret_cast<float4*>(base + off) = make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]);
+          *reinterpret_cast<float4*>(base + OT_A + off) = make_float4(tf32_lo(h[i]), tf32_lo(h[i + 1]), tf32_lo(h[i + 2]), tf32_lo(h[i + 3]));
+        }
+      }
+      fence_async_smem();                                              // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(act_ready);
+    };
+    // out_transform bias, mask_zero (layers.py:6-7), residual, LayerNorm 1
+    {
+      const bool mk = valid && ta.mask[row] != 0;
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) {
+        const float4 bo = __ldg(reinterpret_cast<const float4*>(ta.bout + c0 + i));
+        const float4 xv = valid ? *reinterpret_cast<const float4*>(ta.x + grow + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i] = xv.x + (mk ? v[i] + bo.x : 0.f); v[i + 1] = xv.y + (mk ? v[i + 1] + bo.y : 0.f);
+        v[i + 2] = xv.z + (mk ? v[i + 2] + bo.z : 0.f); v[i + 3] = xv.w + (mk ? v[i + 3] + bo.w : 0.f);
+      }
+    }
+    layer_norm(v, ta.ln1_g, ta.ln1_b);
+    if (valid) {                                                       // parked in x_out (L2) until the residual at the end
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) *reinterpret_cast<float4*>(ta.x_out + grow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+    store_act(v);
+    const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + c0;
+    for (int l = 0; l < 3; ++l) {
+      mbar_wait(acc_full, l & 1);
+      tc_fence_after();
+      const float* bias = l == 0 ? ta.b1 : (l == 1 ? ta.b2 : ta.b3);
+#pragma unroll
+      for (int cc = 0; cc < 64; cc += 32) {
+        float tm[32], ts[32];
+        tmem_ld_32x32(tbase + cc, tm);
+        tmem_ld_32x32(tbase + 128 + cc, ts);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + cc + i));
+          v[cc + i] = (tm[i] + ts[i]) + b.x; v[cc + i + 1] = (tm[i + 1] + ts[i + 1]) + b.y;
+          v[cc + i + 2] = (tm[i + 2] + ts[i + 2]) + b.z; v[cc + i + 3] = (tm[i + 3] + ts[i + 3]) + b.w;
+        }
+      }
+      tc_fence_before();
+      if (l < 2) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
+        store_act(v);
+      }
+    }
+    // residual (LayerNorm 1 output, read back from x_out) + LayerNorm 2
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) {
+        const float4 y = *reinterpret_cast<const float4*>(ta.x_out + grow + i);
+        v[i] += y.x; v[i + 1] += y.y; v[i + 2] += y.z; v[i + 3] += y.w;
+      }
+    }
+    layer_norm(v, ta.ln2_g, ta.ln2_b);
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) {
+        *reinterpret_cast<float4*>(ta.x_out + grow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        if (ta.x_lo_out)
+          *reinterpret_cast<float4*>(ta.x_lo_out + grow + i) = make_float4(tf32_lo(v[i]), tf32_lo(v[i + 1]), tf32_lo(v[i + 2]), tf32_lo(v[i + 3]));
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+cudaError_t tail_tc_init() {
+  return cudaFuncSetAttribute(outT_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OT_SMEM);
+}
+
+// x_out = GABlock tail(feat, x); feat (M, 1824) raw fp32, weights as hi / lo planes (Wmlp = [W1; W2; W3], each [128][128])
+bool launch_outT_tail(int M, const float* feat, const float* x, const uint8_t* mask, const BlockW& w, float* x_out,
+                      float* x_lo_out, cudaStream_t st) {
+  CUtensorMap a, bh, bl, wh, wl;
+  if (!make_tmap(&a, feat, M, NFEAT, NFEAT, 128) || !make_tmap(&bh, w.Wout, F, NFEAT, NFEAT, 128) ||
+      !make_tmap(&bl, w.Wout_lo, F, NFEAT, NFEAT, 128) || !make_tmap(&wh, w.Wmlp, 3 * F, F, F, 128) ||
+      !make_tmap(&wl, w.Wmlp_lo, 3 * F, F, F, 128))
+    return false;
+  ProfScope prof__(KK_TAIL, st);
+  const TailArgs ta{x, mask, w.bout, w.ln1_g, w.ln1_b, w.b1, w.b2, w.b3, w.ln2_g, w.ln2_b, x_out, x_lo_out};
+  outT_tail_kernel<<<(M + 127) / 128, OT_THREADS, OT_SMEM, st>>>(a, bh, bl, wh, wl, M, NFEAT, ta);
+  return true;
+}
+
+}  // namespace abopt

@@ -60,6 +60,10 @@ bool launch_gemm3x_plain(int M, int N, int K, const float* Ah, const float* Al, 
 bool launch_gemm3x_splitA(int M, int N, int K, const float* A, int lda, const float* Bh, const float* Bl, int ldb,
                           float* D, int ldd, const float* bias, cudaStream_t st);
 
+cudaError_t tail_tc_init();
+bool launch_outT_tail(int M, const float* feat, const float* x, const uint8_t* mask, const BlockW& w, float* x_out,
+                      float* x_lo_out, cudaStream_t st);
+
 // operands of the tensor-core attention kernels, produced by the projection GEMM epilogue (k_tc.cu: EpiProjPack)
 struct AttnOperands {
   float* QA; float* QA_lo;      // [N][H][L][64]

@@ -18,6 +18,8 @@ struct BlockW {
   const float* W1_t; const float* b1;      // mlp_transition.0  [128][128]^T
   const float* W2_t; const float* b2;      // mlp_transition.2
   const float* W3_t; const float* b3;      // mlp_transition.4
+  const float* Wmlp;       // [3 * 128][128]  mlp_transition.{0,2,4}.weight stacked as stored by nn.Linear (K-major B operands)
+  const float* Wmlp_lo;    // [3 * 128][128]  tf32 lo plane
   const float* ln2_g; const float* ln2_b;
 };
 
