@@ -180,7 +180,8 @@ extern "C" int abopt_debug_gemm3x(int device, int M, int N, int K, const float* 
 extern "C" int abopt_debug_clocks(long long* out16) {
   if (!out16) return fail(ABOPT_ERR_ARG, "null argument");
   CUDA_TRY(cudaDeviceSynchronize());
-  attn_debug_clocks(out16);
+  attn_debug_clocks(out16);                 // slots 0..9 (legacy one-tile-per-CTA logits kernel only)
+  tail_debug_clocks(out16 + 10);            // slots 10..14: outT_tail_kernel CTA 0: start, phase 1 done, LN1 done, MLP done, end
   return ABOPT_OK;
 }
 extern "C" int abopt_profile_enable(int on) {

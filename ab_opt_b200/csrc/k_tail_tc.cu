@@ -32,12 +32,18 @@ struct TailArgs {
   float* x_out; float* x_lo_out;
 };
 
+// phase timestamps of CTA 0 (SM clock), read back by abopt_debug_clocks() slots 10..15
+__device__ long long g_tail_clk[6];
+__device__ __forceinline__ void tstamp(int slot) { if (blockIdx.x == 0) g_tail_clk[slot] = clock64(); }
+void tail_debug_clocks(long long* out6) { cudaMemcpyFromSymbol(out6, g_tail_clk, sizeof(long long) * 6); }
+
 __device__ __forceinline__ void epi_sync256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __global__ void __launch_bounds__(OT_THREADS, 1)
 outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                  const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmWh,
-                 const __grid_constant__ CUtensorMap tmWl, int M, int K, const TailArgs ta) {
+                 const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmX,
+                 const __grid_constant__ CUtensorMap tmXo, const __grid_constant__ CUtensorMap tmXl, int M, int K, const TailArgs ta) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + OT_BAR_OFF);
@@ -49,7 +55,8 @@ outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* w_empty = w_full + 2;              // [2]
   uint64_t* act_ready = w_empty + 2;
   uint64_t* acc_full = act_ready + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* x_full = acc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 1);
   float* exch_sum = reinterpret_cast<float*>(smem + OT_EXCH_OFF);      // [2][128]
   float* exch_sq = exch_sum + 256;                                     // [2][128]
 
@@ -62,9 +69,10 @@ outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < OT_ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&split[s], 8); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); mbar_init(&w_full[b], 1); mbar_init(&w_empty[b], 1); }
-    mbar_init(act_ready, 8); mbar_init(acc_full, 1);
+    mbar_init(act_ready, 8); mbar_init(acc_full, 1); mbar_init(x_full, 1);
     mbar_fence_init();
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl); tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWl);
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmXo); tma_prefetch_desc(&tmXl);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -72,12 +80,17 @@ outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int last_c = nchunk - 1;
+  if (threadIdx.x == 64) tstamp(0);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % OT_ST;
+        // x tile of phase 2: pull it into L2 while the main loop runs
+        if (kb == nkb / 2)
+          for (int k2 = 0; k2 < 4; ++k2)
+            asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(&tmX), "r"(k2 * OT_BK), "r"(m0) : "memory");
         mbar_wait(&empty[s], ((kb / OT_ST) & 1) ^ 1);
         unsigned char* st = smem + s * OT_STAGE;
         mbar_expect_tx(&full[s], 3 * OT_A);
@@ -87,6 +100,10 @@ outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       // phase 2: the pipeline memory is free once every out_transform MMA has retired
       mbar_wait(&tmem_full[last_c & 1], (last_c >> 1) & 1);
+      // the block input x (residual) of this row tile lands in the hi slots of the four activation k-blocks, in the
+      // swizzled layout the epilogue threads use anyway: no uncoalesced global loads
+      mbar_expect_tx(x_full, 4 * OT_A);
+      for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem + kb * OT_ACT_KB, &tmX, kb * OT_BK, m0, x_full);
       for (int g = 0; g < 12; ++g) {
         const int l = g >> 2, kb = g & 3, s = g & 1;
         mbar_wait(&w_empty[s], ((g >> 1) & 1) ^ 1);
@@ -195,10 +212,9 @@ outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (kb % OT_KCH == 2 && kb / OT_KCH - 1 == promoted && kb >= OT_KCH) { promote(promoted); ++promoted; }
     }
     while (promoted < nchunk) { promote(promoted); ++promoted; }
+    if (et == 0) tstamp(1);
 
     // ---------------- phase 2 ----------------
-    const bool valid = row < M;
-    const size_t grow = (size_t)(valid ? row : 0) * F + c0;
     // LayerNorm over the 128 columns of a row held by two threads (common/layers.py:146-155: biased variance, eps inside
     // the sqrt): partial sums exchanged through shared memory
     auto layer_norm = [&](float (&h)[64], const float* gamma, const float* beta) {
@@ -213,17 +229,17 @@ outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int i = 0; i < 64; ++i) { h[i] -= mean; sq += h[i] * h[i]; }
       exch_sq[half * 128 + te] = sq;
       epi_sync256();
-      const float sd = sqrtf((exch_sq[te] + exch_sq[128 + te]) * (1.f / 128.f) + 1e-10f);
+      const float inv = 1.f / sqrtf((exch_sq[te] + exch_sq[128 + te]) * (1.f / 128.f) + 1e-10f);
 #pragma unroll
       for (int i = 0; i < 64; i += 4) {
         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c0 + i)), b = __ldg(reinterpret_cast<const float4*>(beta + c0 + i));
-        h[i] = h[i] / sd * g.x + b.x; h[i + 1] = h[i + 1] / sd * g.y + b.y;
-        h[i + 2] = h[i + 2] / sd * g.z + b.z; h[i + 3] = h[i + 3] / sd * g.w + b.w;
+        h[i] = h[i] * inv * g.x + b.x; h[i + 1] = h[i + 1] * inv * g.y + b.y;
+        h[i + 2] = h[i + 2] * inv * g.z + b.z; h[i + 3] = h[i + 3] * inv * g.w + b.w;
       }
     };
-    // this thread's 64 activations -> A operand of the next layer: k-blocks 2 half, 2 half + 1; row te of a k-block is 128
-    // bytes, its 16-byte chunk c sits at (c ^ (te & 7)) (128-byte swizzle, what the UMMA descriptor expects)
-    auto store_act = [&](const float (&h)[64]) {
+    // this thread's 64 values <-> rows te of the k-blocks 2 half, 2 half + 1: a row of a k-block is 128 bytes, its 16-byte
+    // chunk c sits at (c ^ (te & 7)) (128-byte swizzle: what TMA writes / reads and what the UMMA descriptor expects)
+    auto store_planes = [&](const float (&h)[64]) {
 #pragma unroll
       for (int kbl = 0; kbl < 2; ++kbl) {
         unsigned char* base = smem + (2 * half + kbl) * OT_ACT_KB + te * 128;
@@ -235,28 +251,38 @@ outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           *reinterpret_cast<float4*>(base + OT_A + off) = make_float4(tf32_lo(h[i]), tf32_lo(h[i + 1]), tf32_lo(h[i + 2]), tf32_lo(h[i + 3]));
         }
       }
-      fence_async_smem();                                              // generic-proxy writes -> visible to the tensor core
+      fence_async_smem();                                              // generic-proxy writes -> visible to the async proxy
+    };
+    auto store_act = [&](const float (&h)[64]) {
+      store_planes(h);
       __syncwarp();
       if (lane == 0) mbar_arrive(act_ready);
     };
-    // out_transform bias, mask_zero (layers.py:6-7), residual, LayerNorm 1
+    const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + c0;
+    // out_transform bias, mask_zero (layers.py:6-7), residual (x from the TMA-loaded tile), LayerNorm 1
     {
-      const bool mk = valid && ta.mask[row] != 0;
+      const bool mk = row < M && ta.mask[row] != 0;
+      mbar_wait(x_full, 0);
 #pragma unroll
-      for (int i = 0; i < 64; i += 4) {
-        const float4 bo = __ldg(reinterpret_cast<const float4*>(ta.bout + c0 + i));
-        const float4 xv = valid ? *reinterpret_cast<const float4*>(ta.x + grow + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        v[i] = xv.x + (mk ? v[i] + bo.x : 0.f); v[i + 1] = xv.y + (mk ? v[i + 1] + bo.y : 0.f);
-        v[i + 2] = xv.z + (mk ? v[i + 2] + bo.z : 0.f); v[i + 3] = xv.w + (mk ? v[i + 3] + bo.w : 0.f);
+      for (int kbl = 0; kbl < 2; ++kbl) {
+        const unsigned char* base = smem + (2 * half + kbl) * OT_ACT_KB + te * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int i = kbl * 32 + c * 4;
+          const float4 xv = *reinterpret_cast<const float4*>(base + ((c ^ (te & 7)) << 4));
+          const float4 bo = __ldg(reinterpret_cast<const float4*>(ta.bout + c0 + i));
+          v[i] = xv.x + (mk ? v[i] + bo.x : 0.f); v[i + 1] = xv.y + (mk ? v[i + 1] + bo.y : 0.f);
+          v[i + 2] = xv.z + (mk ? v[i + 2] + bo.z : 0.f); v[i + 3] = xv.w + (mk ? v[i + 3] + bo.w : 0.f);
+        }
       }
     }
     layer_norm(v, ta.ln1_g, ta.ln1_b);
-    if (valid) {                                                       // parked in x_out (L2) until the residual at the end
-#pragma unroll
-      for (int i = 0; i < 64; i += 4) *reinterpret_cast<float4*>(ta.x_out + grow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-    }
+    // the LayerNorm 1 output is needed again for the residual at the end: park it in the idle TMEM buffer 1
+    tmem_st_32x32(tbase + ACC_COLS, *reinterpret_cast<const float(*)[32]>(&v[0]));
+    tmem_st_32x32(tbase + ACC_COLS + 32, *reinterpret_cast<const float(*)[32]>(&v[32]));
+    tc_fence_before();
     store_act(v);
-    const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + c0;
+    if (et == 0) tstamp(2);
     for (int l = 0; l < 3; ++l) {
       mbar_wait(acc_full, l & 1);
       tc_fence_after();
@@ -280,25 +306,35 @@ outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         store_act(v);
       }
     }
-    // residual (LayerNorm 1 output, read back from x_out) + LayerNorm 2
-    if (valid) {
+    if (et == 0) tstamp(3);
+    // residual (LayerNorm 1 output from TMEM) + LayerNorm 2
 #pragma unroll
-      for (int i = 0; i < 64; i += 4) {
-        const float4 y = *reinterpret_cast<const float4*>(ta.x_out + grow + i);
-        v[i] += y.x; v[i + 1] += y.y; v[i + 2] += y.z; v[i + 3] += y.w;
-      }
+    for (int cc = 0; cc < 64; cc += 32) {
+      float y[32];
+      tmem_ld_32x32(tbase + ACC_COLS + cc, y);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[cc + i] += y[i];
     }
+    tc_fence_before();
     layer_norm(v, ta.ln2_g, ta.ln2_b);
-    if (valid) {
-#pragma unroll
-      for (int i = 0; i < 64; i += 4) {
-        *reinterpret_cast<float4*>(ta.x_out + grow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    // x_out and its tf32 lo plane leave through the (drained) activation slots and TMA tensor stores: whole 128-byte
+    // lines, rows >= M clipped by the hardware
+    store_planes(v);
+    epi_sync256();
+    if (et == 0) {
+      for (int kb = 0; kb < 4; ++kb) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                     ::"l"(&tmXo), "r"(smem_u32(smem + kb * OT_ACT_KB)), "r"(kb * OT_BK), "r"(m0) : "memory");
         if (ta.x_lo_out)
-          *reinterpret_cast<float4*>(ta.x_lo_out + grow + i) = make_float4(tf32_lo(v[i]), tf32_lo(v[i + 1]), tf32_lo(v[i + 2]), tf32_lo(v[i + 3]));
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(&tmXl), "r"(smem_u32(smem + kb * OT_ACT_KB + OT_A)), "r"(kb * OT_BK), "r"(m0) : "memory");
       }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // smem must outlive the reads
     }
   }
   __syncthreads();
+  if (threadIdx.x == 64) tstamp(4);
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
@@ -309,14 +345,16 @@ cudaError_t tail_tc_init() {
 // x_out = GABlock tail(feat, x); feat (M, 1824) raw fp32, weights as hi / lo planes (Wmlp = [W1; W2; W3], each [128][128])
 bool launch_outT_tail(int M, const float* feat, const float* x, const uint8_t* mask, const BlockW& w, float* x_out,
                       float* x_lo_out, cudaStream_t st) {
-  CUtensorMap a, bh, bl, wh, wl;
-  if (!make_tmap(&a, feat, M, NFEAT, NFEAT, 128) || !make_tmap(&bh, w.Wout, F, NFEAT, NFEAT, 128) ||
+  CUtensorMap a, bh, bl, wh, wl, tx, txo, txl;
+  if (!make_tmap(&tx, x, M, F, F, 128) || !make_tmap(&txo, x_out, M, F, F, 128) ||
+      !make_tmap(&txl, x_lo_out ? x_lo_out : x_out, M, F, F, 128) ||
+      !make_tmap(&a, feat, M, NFEAT, NFEAT, 128) || !make_tmap(&bh, w.Wout, F, NFEAT, NFEAT, 128) ||
       !make_tmap(&bl, w.Wout_lo, F, NFEAT, NFEAT, 128) || !make_tmap(&wh, w.Wmlp, 3 * F, F, F, 128) ||
       !make_tmap(&wl, w.Wmlp_lo, 3 * F, F, F, 128))
     return false;
   ProfScope prof__(KK_TAIL, st);
   const TailArgs ta{x, mask, w.bout, w.ln1_g, w.ln1_b, w.b1, w.b2, w.b3, w.ln2_g, w.ln2_b, x_out, x_lo_out};
-  outT_tail_kernel<<<(M + 127) / 128, OT_THREADS, OT_SMEM, st>>>(a, bh, bl, wh, wl, M, NFEAT, ta);
+  outT_tail_kernel<<<(M + 127) / 128, OT_THREADS, OT_SMEM, st>>>(a, bh, bl, wh, wl, tx, txo, txl, M, NFEAT, ta);
   return true;
 }
 

@@ -61,6 +61,7 @@ bool launch_gemm3x_splitA(int M, int N, int K, const float* A, int lda, const fl
                           float* D, int ldd, const float* bias, cudaStream_t st);
 
 cudaError_t tail_tc_init();
+void tail_debug_clocks(long long* out6);
 bool launch_outT_tail(int M, const float* feat, const float* x, const uint8_t* mask, const BlockW& w, float* x_out,
                       float* x_lo_out, cudaStream_t st);
 

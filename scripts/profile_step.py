@@ -40,6 +40,8 @@ def main():
     t0 = clk[0]
     names = ['start', 'a_full', 'b_full0', 'b_full1', 'tables', 'tmem_full', 'pass1', 'pass2', 'pass3', 'end']
     print('attn_logits CTA(0,0,0) timeline [cycles]:', {n: int(clk[k] - t0) for k, n in enumerate(names)})
+    tn = ['start', 'out_transform done', 'LN1 + act stored', 'MLP done', 'end']
+    print('outT_tail CTA 0 timeline [cycles]:', {n: int(clk[10 + k] - clk[10]) for k, n in enumerate(tn)})
 
 
 if __name__ == '__main__':
