@@ -367,7 +367,8 @@ template <int NCH>                                      // 32-key chunks per row
 __global__ void __launch_bounds__(AP_THREADS, 1)
 attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
                            const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
-                           const __grid_constant__ CUtensorMap tmBias, const AttnLogitsArgs a, const AttnPersistArgs pa) {
+                           const __grid_constant__ CUtensorMap tmBias, const __grid_constant__ CUtensorMap tmBiasPf,
+                           const AttnLogitsArgs a, const AttnPersistArgs pa) {
   constexpr int NGRP = NCH / 2;                         // 64-key MMA groups
   constexpr int NLG = NCH * 8;                          // logits per epilogue thread
   extern __shared__ unsigned char smem_raw[];
@@ -401,6 +402,7 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], AP_EPI / 32); }
     mbar_fence_init();
     tma_prefetch_desc(&tmQh); tma_prefetch_desc(&tmQl); tma_prefetch_desc(&tmKh); tma_prefetch_desc(&tmKl); tma_prefetch_desc(&tmBias);
+    tma_prefetch_desc(&tmBiasPf);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -444,6 +446,14 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
           if (mbar_try_wait(&bias_empty[s], ((bc / AP_NBIAS) & 1) ^ 1)) {
             const int it = btile % nit, bh = btile / nit, h = bh % H, bl = bh / H;
             const int row_base = ((a.b0 + bl) * H + h) * L;
+            // the 3-slot ring (48 KB in flight) cannot cover the HBM latency of the bias stream by itself: when a tile's
+            // stream starts, pull the NEXT tile's bias into L2 (boxes of [<= 256 keys][128 queries])
+            if (bm == 0 && btile + (int)gridDim.x < ntiles) {
+              const int nt = btile + gridDim.x, nit2 = nt % nit, nbh = nt / nit;
+              const int nrow = ((a.b0 + nbh / H) * H + nbh % H) * L;
+              for (int j0 = 0; j0 < L; j0 += 256)
+                asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(&tmBiasPf), "r"(nit2 * AL_BM), "r"(nrow + j0) : "memory");
+            }
             mbar_expect_tx(&bias_full[s], (uint32_t)pa.bias_tx);
             tma_load_2d(smem + AP_BIAS_OFF + s * AP_BIAS_BYTES, &tmBias, it * AL_BM, row_base + bm * 32, &bias_full[s]);
             ++bc;
@@ -643,8 +653,8 @@ bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOpera
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     const AttnPersistArgs pa{nb, (int)bcols, (int)(brows * bcols * 4)};
-    if (ncols <= 128) attn_logits_persist_kernel<4><<<ntiles < sms ? ntiles : sms, AP_THREADS, AP_SMEM, st>>>(qh, ql, kh64, kl64, bm32, a, pa);
-    else attn_logits_persist_kernel<8><<<ntiles < sms ? ntiles : sms, AP_THREADS, AP_SMEM, st>>>(qh, ql, kh64, kl64, bm32, a, pa);
+    if (ncols <= 128) attn_logits_persist_kernel<4><<<ntiles < sms ? ntiles : sms, AP_THREADS, AP_SMEM, st>>>(qh, ql, kh64, kl64, bm32, bm, a, pa);
+    else attn_logits_persist_kernel<8><<<ntiles < sms ? ntiles : sms, AP_THREADS, AP_SMEM, st>>>(qh, ql, kh64, kl64, bm32, bm, a, pa);
   } else if (ncols <= 256) attn_logits_tc_kernel<true><<<grid, AL_THREADS, AL_SMEM, st>>>(qh, ql, kh, kl, bm, al, a);
   else attn_logits_tc_kernel<false><<<grid, AL_THREADS, AL_SMEM, st>>>(qh, ql, kh, kl, bm, al, a);
   return true;
@@ -834,7 +844,192 @@ aggr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
 }
 
+// ------------------------------------------------------------------------------------------ persistent aggregation GEMM
+// aggr_persist_kernel: same arithmetic as aggr_tc_kernel, restructured like attn_logits_persist_kernel.  One CTA per SM walks
+// the (complex, head, 128-query tile) list; the k-block ring runs across tile boundaries and the epilogue of tile n overlaps
+// the main loop of tile n + 1 (two 256-column TMEM accumulator sets):
+//   warp 0      TMA producer: key blocks of 32 through a 4-stage ring (alpha 128 x 32 raw fp32; V^T 64 x 32 hi and lo planes)
+//   warp 1      MMA issuer (waits for "split")
+//   warps 2-5   splitters: tf32 lo plane of every landed alpha box, in shared memory
+//   warps 6-9   epilogue: thread = query row: 64 sums -> node aggregate, R_i^T (o - t_i), norms, directions; every feature
+//               group of a row is a 32-byte-aligned run, stored with 256-bit stores (full sectors, no staging buffer)
+constexpr int AGP_THREADS = 320, AGP_ST = 4;
+constexpr int AGP_SMEM = AGP_ST * AG2_STAGE_BYTES + 256 + 1024;
+
+__device__ __forceinline__ void st_v8f(float* p, float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a0), "f"(a1), "f"(a2), "f"(a3), "f"(a4),
+               "f"(a5), "f"(a6), "f"(a7) : "memory");
+}
+
+__global__ void __launch_bounds__(AGP_THREADS, 1)
+aggr_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmVh,
+                    const __grid_constant__ CUtensorMap tmVl, const AggrArgs a, const int nb_complex) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + AGP_ST * AG2_STAGE_BYTES);
+  uint64_t* split = full + AGP_ST;
+  uint64_t* empty = split + AGP_ST;
+  uint64_t* tmem_full = empty + AGP_ST;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = a.L;
+  const int nkb = (L + 31) / 32;
+  const int gsz = (nkb + 2) / 3;                        // key blocks per main accumulator (three short accumulation chains)
+  const int nit = (L + 127) / 128;
+  const int ntiles = nb_complex * H * nit;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < AGP_ST; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 4); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmVh); tma_prefetch_desc(&tmVl);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int g = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int it = tile % nit, bh = tile / nit, h = bh % H, bl = bh / H;
+        const int arow = (bl * H + h) * L + it * 128, vrow = ((a.b0 + bl) * H + h) * 64;
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const int s = g % AGP_ST;
+          mbar_wait(&empty[s], ((g / AGP_ST) & 1) ^ 1);
+          unsigned char* st = smem + s * AG2_STAGE_BYTES;
+          mbar_expect_tx(&full[s], AG2_TX_BYTES);
+          tma_load_2d(st, &tmA, kb * 32, arow, &full[s]);
+          tma_load_2d(st + 2 * AG2_A_BYTES, &tmVh, kb * 32, vrow, &full[s]);
+          tma_load_2d(st + 2 * AG2_A_BYTES + AG2_B_BYTES, &tmVl, kb * 32, vrow, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = idesc_tf32(128, 64);
+    int g = 0, n = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+      const int buf = n & 1;
+      mbar_wait(&tmem_empty[buf], ((n >> 1) & 1) ^ 1);
+      const uint32_t tb = tmem_base + buf * 256;
+      for (int kb = 0; kb < nkb; ++kb, ++g) {
+        const int s = g % AGP_ST;
+        mbar_wait(&split[s], (g / AGP_ST) & 1);             // TMA data landed AND the lo plane is built
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_hi = smem_u32(smem + s * AG2_STAGE_BYTES), a_lo = a_hi + AG2_A_BYTES;
+          const uint32_t b_hi = a_hi + 2 * AG2_A_BYTES, b_lo = b_hi + AG2_B_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t dah = smem_desc_sw128(a_hi + k * 32), dal = smem_desc_sw128(a_lo + k * 32);
+            const uint64_t dbh = smem_desc_sw128(b_hi + k * 32), dbl = smem_desc_sw128(b_lo + k * 32);
+            mma_tf32(tb + (kb / gsz) * 64, dah, dbh, idesc, (kb % gsz == 0 && k == 0) ? 0u : 1u);
+            mma_tf32(tb + 192, dah, dbl, idesc, (kb == 0 && k == 0) ? 0u : 1u);
+            mma_tf32(tb + 192, dal, dbh, idesc, 1u);
+          }
+          mma_commit(&empty[s]);
+          if (kb == nkb - 1) mma_commit(&tmem_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 6) {
+    // ---- splitters: lo plane of every landed alpha box
+    const int te = (warp - 2) * 32 + lane;
+    int g = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+      for (int kb = 0; kb < nkb; ++kb, ++g) {
+        const int s = g % AGP_ST;
+        mbar_wait(&full[s], (g / AGP_ST) & 1);
+        const float4* src = reinterpret_cast<const float4*>(smem + s * AG2_STAGE_BYTES);
+        float4* dst = reinterpret_cast<float4*>(smem + s * AG2_STAGE_BYTES + AG2_A_BYTES);
+#pragma unroll
+        for (int m = 0; m < AG2_A_BYTES / 16 / 128; ++m) {
+          const float4 v = src[te + 128 * m];
+          dst[te + 128 * m] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split[s]);
+      }
+  } else {
+    // ---- epilogue
+    const int q = warp & 3;
+    const int ngrp = (nkb + gsz - 1) / gsz;
+    int n = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+      const int it = tile % nit, bh = tile / nit, h = bh % H, bl = bh / H, b = a.b0 + bl;
+      const int buf = n & 1;
+      const int i = it * 128 + q * 32 + lane;
+      mbar_wait(&tmem_full[buf], (n >> 1) & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
+      float o[64];
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        float v[32], w[32];
+        tmem_ld_32x32(trow + 192 + c, w);                   // corrections
+        tmem_ld_32x32(trow + c, v);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[c + e] = v[e];
+        for (int gq = 1; gq < ngrp; ++gq) {
+          tmem_ld_32x32(trow + gq * 64 + c, v);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o[c + e] += v[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[c + e] += w[e];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);        // sums are in registers: the MMA warp may reuse the buffer
+      if (i < L) {
+        const size_t row = (size_t)b * L + i;
+        float* fr = a.feat + row * NFEAT;
+        // node aggregate (ga.py:120-125)
+#pragma unroll
+        for (int d = 0; d < D; d += 8) st_v8f(fr + FEAT_NODE + h * D + d, o[d], o[d + 1], o[d + 2], o[d + 3], o[d + 4], o[d + 5], o[d + 6], o[d + 7]);
+        // point aggregate -> local frame p = R^T (q - t) (geometry.py:94-113), norm, direction (eps 1e-4, ga.py:139)
+        float Rm[9], tv[3];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Rm[k] = __ldg(a.R + row * 9 + k);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tv[k] = __ldg(a.t + row * 3 + k);
+        float pts[24], nrm[8], dir[24];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          const float gx = o[D + p * 3 + 0] - tv[0], gy = o[D + p * 3 + 1] - tv[1], gz = o[D + p * 3 + 2] - tv[2];
+          const float lx = Rm[0] * gx + Rm[3] * gy + Rm[6] * gz;
+          const float ly = Rm[1] * gx + Rm[4] * gy + Rm[7] * gz;
+          const float lz = Rm[2] * gx + Rm[5] * gy + Rm[8] * gz;
+          const float nn = sqrtf(lx * lx + ly * ly + lz * lz);
+          const float den = nn + 1e-4f;
+          pts[p * 3] = lx; pts[p * 3 + 1] = ly; pts[p * 3 + 2] = lz;
+          nrm[p] = nn;
+          dir[p * 3] = lx / den; dir[p * 3 + 1] = ly / den; dir[p * 3 + 2] = lz / den;
+        }
+#pragma unroll
+        for (int d = 0; d < 24; d += 8) {
+          st_v8f(fr + FEAT_PTS + h * P * 3 + d, pts[d], pts[d + 1], pts[d + 2], pts[d + 3], pts[d + 4], pts[d + 5], pts[d + 6], pts[d + 7]);
+          st_v8f(fr + FEAT_DIR + h * P * 3 + d, dir[d], dir[d + 1], dir[d + 2], dir[d + 3], dir[d + 4], dir[d + 5], dir[d + 6], dir[d + 7]);
+        }
+        st_v8f(fr + FEAT_DIST + h * P, nrm[0], nrm[1], nrm[2], nrm[3], nrm[4], nrm[5], nrm[6], nrm[7]);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+static bool g_aggr_legacy = false;      // ABOPT_AGGR_LEGACY=1: one-tile-per-CTA kernel (A/B comparisons)
 cudaError_t aggr_tc_init() {
+  { const char* ev = getenv("ABOPT_AGGR_LEGACY"); g_aggr_legacy = ev && ev[0] == '1'; }
+  cudaError_t e = cudaFuncSetAttribute(aggr_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AGP_SMEM);
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(aggr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AG2_SMEM);
 }
 
@@ -847,6 +1042,13 @@ bool launch_aggr_tc(int nb, int b0, int N, int L, int Lp, const float* alpha, co
     return false;
   ProfScope prof__(KK_AGGR, st);
   AggrArgs a{L, Lp, b0, R, t, feat, feat_lo};
+  if (!g_aggr_legacy && feat_lo == nullptr) {
+    const int ntiles = nb * H * ((L + 127) / 128);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    aggr_persist_kernel<<<ntiles < sms ? ntiles : sms, AGP_THREADS, AGP_SMEM, st>>>(ah, vh, vl, a, nb);
+    return true;
+  }
   dim3 grid((L + 127) / 128, H, nb);
   aggr_tc_kernel<<<grid, AG2_THREADS, AG2_SMEM, st>>>(ah, vh, vl, a);
   return true;
