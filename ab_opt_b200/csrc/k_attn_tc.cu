@@ -335,12 +335,14 @@ attn_logits_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
 //               consecutive queries) -> logits; max / exp / sum exchanged through shared memory; alpha stored with 256-bit
 //               global stores (one full 32-byte sector each)
 constexpr int AP_THREADS = 640, AP_EPI = 512, AP_SPLIT = 64;      // (18 warps are allocated registers as 20 anyway)
-constexpr int AP_BST = 3, AP_BGRP_BYTES = 4 * 64 * 32 * 4;            // key-group stage: 64 keys x (hi k0 | hi k1 | lo k0 | lo k1) = 32 KB
+constexpr int AP_BST = 2, AP_BGRP_BYTES = 4 * 64 * 32 * 4;            // key-group stage: 64 keys x (hi k0 | hi k1 | lo k0 | lo k1) = 32 KB
 constexpr int AP_KBOX = 64 * 32 * 4;                                  // one key box: 64 rows x 32 floats
 constexpr int AP_NBIAS = 3, AP_BIAS_BYTES = 32 * 128 * 4;             // bias chunk: 32 keys x 128 queries
 constexpr int AP_B_OFF = 2 * AL_OPER_BYTES;
 constexpr int AP_BIAS_OFF = AP_B_OFF + AP_BST * AP_BGRP_BYTES;
-constexpr int AP_TAB_OFF = AP_BIAS_OFF + AP_NBIAS * AP_BIAS_BYTES;    // ck[256] | pen[256] | xmax[4][128] | xsum[4][128]
+constexpr int AP_STG_OFF = AP_BIAS_OFF + AP_NBIAS * AP_BIAS_BYTES;    // alpha staging: 2 boxes of [128 queries][32 keys], 128-byte swizzle
+constexpr int AP_STG_BYTES = 128 * 32 * 4;
+constexpr int AP_TAB_OFF = AP_STG_OFF + 2 * AP_STG_BYTES;             // ck[256] | pen[256] | xmax[4][128] | xsum[4][128]
 constexpr int AP_BAR_OFF = AP_TAB_OFF + 2 * 256 * 4 + 8 * 128 * 4;
 constexpr int AP_SMEM = AP_BAR_OFF + 256 + 1024;
 
@@ -367,7 +369,7 @@ template <int NCH>                                      // 32-key chunks per row
 __global__ void __launch_bounds__(AP_THREADS, 1)
 attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
                            const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
-                           const __grid_constant__ CUtensorMap tmBias, const __grid_constant__ CUtensorMap tmBiasPf,
+                           const __grid_constant__ CUtensorMap tmBias, const __grid_constant__ CUtensorMap tmAl,
                            const AttnLogitsArgs a, const AttnPersistArgs pa) {
   constexpr int NGRP = NCH / 2;                         // 64-key MMA groups
   constexpr int NLG = NCH * 8;                          // logits per epilogue thread
@@ -402,7 +404,7 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], AP_EPI / 32); }
     mbar_fence_init();
     tma_prefetch_desc(&tmQh); tma_prefetch_desc(&tmQl); tma_prefetch_desc(&tmKh); tma_prefetch_desc(&tmKl); tma_prefetch_desc(&tmBias);
-    tma_prefetch_desc(&tmBiasPf);
+    tma_prefetch_desc(&tmAl);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -446,14 +448,6 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
           if (mbar_try_wait(&bias_empty[s], ((bc / AP_NBIAS) & 1) ^ 1)) {
             const int it = btile % nit, bh = btile / nit, h = bh % H, bl = bh / H;
             const int row_base = ((a.b0 + bl) * H + h) * L;
-            // the 3-slot ring (48 KB in flight) cannot cover the HBM latency of the bias stream by itself: when a tile's
-            // stream starts, pull the NEXT tile's bias into L2 (boxes of [<= 256 keys][128 queries])
-            if (bm == 0 && btile + (int)gridDim.x < ntiles) {
-              const int nt = btile + gridDim.x, nit2 = nt % nit, nbh = nt / nit;
-              const int nrow = ((a.b0 + nbh / H) * H + nbh % H) * L;
-              for (int j0 = 0; j0 < L; j0 += 256)
-                asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(&tmBiasPf), "r"(nit2 * AL_BM), "r"(nrow + j0) : "memory");
-            }
             mbar_expect_tx(&bias_full[s], (uint32_t)pa.bias_tx);
             tma_load_2d(smem + AP_BIAS_OFF + s * AP_BIAS_BYTES, &tmBias, it * AL_BM, row_base + bm * 32, &bias_full[s]);
             ++bc;
@@ -595,17 +589,28 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
       xsum[kq * 128 + te] = sum;
       epi_sync512();
       const float inv = 1.0f / ((xsum[te] + xsum[128 + te]) + (xsum[256 + te] + xsum[384 + te]));
-      if (valid) {
+      // alpha leaves chunk by chunk through two staging boxes ([128 queries][32 keys], 128-byte swizzle) and TMA tensor
+      // stores: whole lines, rows >= L and keys >= Lp clipped by the hardware.  (Per-lane 256-bit global stores of a
+      // row-per-lane layout cost 32 sector requests per instruction and kept the LSU the bottleneck of this kernel.)
 #pragma unroll
-        for (int m = 0; m < NCH; ++m) {
-          const int j0 = m * 32 + kq * 8;
-          if (j0 < Lp)
-            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(alpha_row + j0), "f"(lg[m * 8] * inv),
-                         "f"(lg[m * 8 + 1] * inv), "f"(lg[m * 8 + 2] * inv), "f"(lg[m * 8 + 3] * inv), "f"(lg[m * 8 + 4] * inv),
-                         "f"(lg[m * 8 + 5] * inv), "f"(lg[m * 8 + 6] * inv), "f"(lg[m * 8 + 7] * inv) : "memory");
+      for (int m = 0; m < NCH; ++m) {
+        unsigned char* stg = smem + AP_STG_OFF + (m & 1) * AP_STG_BYTES;
+        // the store that last read this box (chunk m - 2) was waited for by thread 0 BEFORE the previous barrier
+        unsigned char* rowp = stg + te * 128;
+        *reinterpret_cast<float4*>(rowp + (((2 * kq) ^ (te & 7)) << 4)) =
+            make_float4(lg[m * 8] * inv, lg[m * 8 + 1] * inv, lg[m * 8 + 2] * inv, lg[m * 8 + 3] * inv);
+        *reinterpret_cast<float4*>(rowp + (((2 * kq + 1) ^ (te & 7)) << 4)) =
+            make_float4(lg[m * 8 + 4] * inv, lg[m * 8 + 5] * inv, lg[m * 8 + 6] * inv, lg[m * 8 + 7] * inv);
+        fence_async_smem();
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // store of chunk m - 1 has read its box
+        epi_sync512();
+        if (et == 0 && m * 32 < Lp) {
+          tma_store_3d(&tmAl, stg, m * 32, i0, bl * H + h);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
     }
+    if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");          // smem must outlive the reads
     tc_fence_before();
   }
   __syncthreads();
@@ -653,8 +658,8 @@ bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOpera
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     const AttnPersistArgs pa{nb, (int)bcols, (int)(brows * bcols * 4)};
-    if (ncols <= 128) attn_logits_persist_kernel<4><<<ntiles < sms ? ntiles : sms, AP_THREADS, AP_SMEM, st>>>(qh, ql, kh64, kl64, bm32, bm, a, pa);
-    else attn_logits_persist_kernel<8><<<ntiles < sms ? ntiles : sms, AP_THREADS, AP_SMEM, st>>>(qh, ql, kh64, kl64, bm32, bm, a, pa);
+    if (ncols <= 128) attn_logits_persist_kernel<4><<<ntiles < sms ? ntiles : sms, AP_THREADS, AP_SMEM, st>>>(qh, ql, kh64, kl64, bm32, al, a, pa);
+    else attn_logits_persist_kernel<8><<<ntiles < sms ? ntiles : sms, AP_THREADS, AP_SMEM, st>>>(qh, ql, kh64, kl64, bm32, al, a, pa);
   } else if (ncols <= 256) attn_logits_tc_kernel<true><<<grid, AL_THREADS, AL_SMEM, st>>>(qh, ql, kh, kl, bm, al, a);
   else attn_logits_tc_kernel<false><<<grid, AL_THREADS, AL_SMEM, st>>>(qh, ql, kh, kl, bm, al, a);
   return true;
