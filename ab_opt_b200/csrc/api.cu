@@ -66,6 +66,7 @@ struct Workspace {
   float *v_net, *eps_pos, *c_den, *R_next;
   int* bin_idx;
   long long* tvec_scratch;
+  Focus focus;
 };
 
 struct HostIO {       // device staging for abopt_sample_host
@@ -91,6 +92,7 @@ struct abopt_model {
   // pair bias z . W_b of every layer, [slot][N][H][L][Lp].  Inside abopt_sample_* it is computed once per run for all
   // layers (z and the weights are loop invariants of the T reverse steps); elsewhere slot 0 is recomputed per block call.
   float* bias_buf = nullptr; size_t bias_slots = 0, bias_slot_floats = 0; bool bias_hoisted = false;
+  bool focus_built = false;     // inside abopt_sample_*: the focus lists of mask_generate were built once for the whole run
   EpsW eps;
   DiffW diff;
   Workspace ws;
@@ -474,7 +476,9 @@ static int ensure_workspace(abopt_model* m, int N, int L) {
                oBi = take(M * 4), oTv = take((size_t)N * 8), oXal = take(M * F * 4), oXbl = take(M * F * 4), oXil = take(M * F * 4),
                oFl = take(M * NFEAT * 4), oOd = take(M * F * 4), oQa = take(M * H * 64 * 4), oQl = take(M * H * 64 * 4),
                oKb = take(M * H * 64 * 4), oKl = take(M * H * 64 * 4), oRq = take(M * H * 4), oRk = take(M * H * 4),
-               oVt = take((size_t)N * H * 64 * Lp * 4), oVl = take((size_t)N * H * 64 * Lp * 4);
+               oVt = take((size_t)N * H * 64 * Lp * 4), oVl = take((size_t)N * H * 64 * Lp * 4),
+               oFc = take(M * 4), oFr = take(M * 4), oFw = take((size_t)N * (L / 64 + 2) * 8), oFn = take(64), oFs = take((size_t)N * 8),
+               oFx = take(M * F * 4), oFm = take(M);
   CUDA_TRY(cudaMalloc(&w.base, off));
   CUDA_TRY(cudaMemset(w.base, 0, off));        // the padding rows / columns of the packed attention operands must stay zero
   unsigned char* b = static_cast<unsigned char*>(w.base);
@@ -487,6 +491,7 @@ static int ensure_workspace(abopt_model* m, int N, int L) {
   w.outD = (float*)(b + oOd);
   w.op = AttnOperands{(float*)(b + oQa), (float*)(b + oQl), (float*)(b + oKb), (float*)(b + oKl), (float*)(b + oRq), (float*)(b + oRk),
                       (float*)(b + oVt), (float*)(b + oVl)};
+  w.focus = Focus{(int*)(b + oFc), (int*)(b + oFr), (int2*)(b + oFw), (int*)(b + oFn), (int*)(b + oFs), (float*)(b + oFx), (uint8_t*)(b + oFm)};
   w.N = N; w.L = L; w.Lp = Lp; w.NB = NB; w.bytes = off;
   return ABOPT_OK;
 }
@@ -525,8 +530,10 @@ static int ensure_pair_inputs(abopt_model* m, int N, int L, const float* z, size
 
 // one GABlock: x_in -> x_out (may not alias); feat/alpha taps optional.
 // x_lo = tf32 "lo" plane of x (nullptr: computed here); x_lo_out = where to put the lo plane of x_out (may be nullptr)
+// fc != nullptr ("focus", last block inside the sampling loop): only the rows listed in fc are produced, x_out is COMPACT
 static int run_block(abopt_model* m, int layer, int N, int L, const float* R, const float* t, const float* x, const float* x_lo,
-                     const float* z, const uint8_t* mask, float* x_out, float* x_lo_out, float* alpha_tap, cudaStream_t st) {
+                     const float* z, const uint8_t* mask, float* x_out, float* x_lo_out, float* alpha_tap, cudaStream_t st,
+                     const Focus* fc = nullptr) {
   Workspace& w = m->ws;
   const int M = N * L;
   const BlockW& bw = m->blocks[layer];
@@ -551,10 +558,12 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
         return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (proj)");
     }
     // logits (node + spatial + pair bias, scaled, masked) and softmax on the tensor cores -> alpha (L2 resident chunk)
-    if (!launch_attn_logits_tc(nb, b0, N, L, w.Lp, w.op, bias, mask, w.alpha, st)) return fail(ABOPT_ERR_CUDA, "attn_logits_tc launch failed");
-    if (!launch_pair_stream(nb, b0, L, w.Lp, z, mask, w.alpha, w.feat, flo, st))
+    if (!launch_attn_logits_tc(nb, b0, N, L, w.Lp, w.op, bias, mask, w.alpha, st, fc ? fc->windows : nullptr, fc ? fc->count : nullptr))
+      return fail(ABOPT_ERR_CUDA, "attn_logits_tc launch failed");
+    if (!launch_pair_stream(nb, b0, L, w.Lp, z, mask, w.alpha, w.feat, flo, st, fc ? fc->cidx : nullptr))
       return fail(ABOPT_ERR_ARG, "pair_stream_kernel: L too large for shared memory");
-    if (!launch_aggr_tc(nb, b0, N, L, w.Lp, w.alpha, w.op.VT, w.op.VT_lo, R, t, w.feat, flo, st))
+    if (!launch_aggr_tc(nb, b0, N, L, w.Lp, w.alpha, w.op.VT, w.op.VT_lo, R, t, w.feat, flo, st, fc ? fc->windows : nullptr,
+                        fc ? fc->count : nullptr, fc ? fc->cidx : nullptr))
       return fail(ABOPT_ERR_CUDA, "aggr_tc launch failed");
     if (alpha_tap) launch_alpha_tap(nb, b0, L, w.Lp, w.alpha, alpha_tap, st);
   }
@@ -562,7 +571,11 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
     // out_transform (K = 1824) on the tensor cores, then mask / residual / LN / MLP / LN
     // ABOPT_TAIL_LEGACY=1: out_transform GEMM + CUDA-core tail_kernel instead of the fused tensor-core tail (A/B comparisons)
     static const bool tail_legacy = [] { const char* ev = getenv("ABOPT_TAIL_LEGACY"); return ev && ev[0] == '1'; }();
-    if (!flo && !tail_legacy) {
+    if (fc) {
+      launch_focus_gather(fc->rows, fc->count, x, mask, fc->x_c, fc->mask_c, st);
+      if (!launch_outT_tail(M, w.feat, fc->x_c, fc->mask_c, bw, x_out, nullptr, st, fc->count))
+        return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (tail)");
+    } else if (!flo && !tail_legacy) {
       if (!launch_outT_tail(M, w.feat, x, mask, bw, x_out, x_lo_out, st)) return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (tail)");
     } else {
       const bool ok = flo ? launch_gemm3x_plain(M, F, NFEAT, w.feat, flo, NFEAT, bw.Wout, bw.Wout_lo, NFEAT, w.outD, F, bw.bout, st)
@@ -604,7 +617,7 @@ extern "C" int abopt_ga_block_taps(abopt_model* m, int layer, int N, int L, cons
 
 // all layers; result lands in *result (one of the two workspace ping-pong buffers)
 static int run_encoder(abopt_model* m, int N, int L, const float* R, const float* t, const float* x, const float* x_lo,
-                       const float* z, const uint8_t* mask, float** result, cudaStream_t st) {
+                       const float* z, const uint8_t* mask, float** result, cudaStream_t st, const Focus* fc = nullptr) {
   Workspace& w = m->ws;
   const float* cur = x;
   const float* cur_lo = x_lo;
@@ -612,7 +625,8 @@ static int run_encoder(abopt_model* m, int N, int L, const float* R, const float
   float* bufs_lo[2] = {w.xa_lo, w.xb_lo};
   int which = (x == w.xa) ? 1 : 0;
   for (int l = 0; l < m->cfg.num_layers; ++l) {
-    int rc = run_block(m, l, N, L, R, t, cur, cur_lo, z, mask, bufs[which], bufs_lo[which], nullptr, st); if (rc) return rc;
+    const bool last = l == m->cfg.num_layers - 1;
+    int rc = run_block(m, l, N, L, R, t, cur, cur_lo, z, mask, bufs[which], bufs_lo[which], nullptr, st, last ? fc : nullptr); if (rc) return rc;
     cur = bufs[which]; cur_lo = bufs_lo[which]; which ^= 1;
   }
   *result = const_cast<float*>(cur);
@@ -637,15 +651,32 @@ extern "C" int abopt_ga_encoder_forward(abopt_model* m, int N, int L, const floa
 static int run_eps_net(abopt_model* m, int N, int L, const float* v_t, const float* p_t, const float* p_ang,
                        const long long* s_t, const float* res_feat, const float* pair_feat, const float* beta, int beta_stride,
                        const uint8_t* mask_gen, const uint8_t* mask_res, float* v_next, float* R_next, float* eps_pos,
-                       float* c_den, float* prmsd_logits, cudaStream_t st) {
+                       float* c_den, float* prmsd_logits, cudaStream_t st, bool focus = false) {
   Workspace& w = m->ws;
   const int M = N * L;
+  // "focus": the caller consumes the outputs on generated residues only (sampling loop, no pRMSD head), so the last
+  // GABlock and the heads run on those rows alone.  Results on the consumed rows are unchanged.
+  static const bool focus_off = [] {
+    for (const char* k : {"ABOPT_NO_FOCUS", "ABOPT_ATTN_LEGACY", "ABOPT_AGGR_LEGACY", "ABOPT_TAIL_LEGACY", "ABOPT_OUTT_LEGACY"}) {
+      const char* ev = getenv(k);
+      if (ev && ev[0] == '1') return true;
+    }
+    return false;
+  }();
+  const Focus* fc = nullptr;
+  if (focus && !focus_off && !m->cfg.has_prmsd && L <= 256 && w.NB >= N && m->cfg.num_layers >= 1) {
+    if (!m->focus_built)
+      launch_focus_build(N, L, mask_gen, w.focus.cidx, w.focus.rows, w.focus.windows, w.focus.count, w.focus.scratch, st);
+    if (m->bias_hoisted) m->focus_built = true;           // the sampling loop: mask_generate is a loop invariant
+    fc = &w.focus;
+  }
   launch_mixer(M, res_feat, s_t, v_t, m->eps, w.xa, w.Rbuf, p_ang, w.pnorm, m->diff.pos_mean, m->diff.pos_scale, w.xa_lo, st);
   const float* tpos = p_ang ? w.pnorm : p_t;
   float* enc = nullptr;
-  int rc = run_encoder(m, N, L, w.Rbuf, tpos, w.xa, w.xa_lo, pair_feat, mask_res, &enc, st); if (rc) return rc;
+  int rc = run_encoder(m, N, L, w.Rbuf, tpos, w.xa, w.xa_lo, pair_feat, mask_res, &enc, st, fc); if (rc) return rc;
   launch_heads(M, L, enc, beta, beta_stride, w.Rbuf, v_t, mask_gen, m->eps, v_next, R_next, eps_pos, c_den, w.prmsd_rows,
-               m->cfg.has_prmsd ? (prmsd_logits ? prmsd_logits : w.prmsd_logits) : nullptr, st);
+               m->cfg.has_prmsd ? (prmsd_logits ? prmsd_logits : w.prmsd_logits) : nullptr, st, fc ? fc->rows : nullptr,
+               fc ? fc->count : nullptr);
   CHECK_LAUNCH();
   return ABOPT_OK;
 }
@@ -752,7 +783,7 @@ static int run_step(abopt_model* m, int N, int L, int t, bool optimize, uint32_t
   const int M = N * L;
   const bool prm = m->cfg.has_prmsd != 0 && prmsd_out && ppl_out;
   int rc = run_eps_net(m, N, L, v_t, nullptr, p_t_ang, s_t, res_feat, pair_feat, m->diff.betas + t, 0, mask_generate, mask_res,
-                       w.v_net, w.R_next, w.eps_pos, w.c_den, nullptr, st);
+                       w.v_net, w.R_next, w.eps_pos, w.c_den, nullptr, st, /*focus=*/true);
   if (rc) return rc;
   StepArgs sa{};
   sa.M = M; sa.L = L; sa.t = t;
@@ -842,10 +873,12 @@ extern "C" int abopt_sample_device(abopt_model* m, int N, int L, const float* v,
     if (!launch_pair_bias(N, 0, L, m->ws.Lp, m->zmap, m->zmap_box_rows, m->pbp[l], m->bias_buf + (size_t)l * m->bias_slot_floats, st))
       return fail(ABOPT_ERR_ARG, "pair_bias_kernel: L too large for shared memory");
   m->bias_hoisted = true;
+  m->focus_built = false;
   for (int t = T0; t >= 1 && rc == ABOPT_OK; --t)
     rc = run_step(m, N, L, t, optimize, flags, seed, V(t), Pp(t), S(t), res_feat, pair_feat, mask_generate, mask_res,
                   noise ? &noise[T0 - t] : nullptr, V(t - 1), Pp(t - 1), S(t - 1), PR(t - 1), PL(t - 1), st);
   m->bias_hoisted = false;
+  m->focus_built = false;
   return rc;
 }
 

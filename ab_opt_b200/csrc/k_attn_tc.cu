@@ -360,10 +360,21 @@ __device__ __forceinline__ void tmem_ld_32x8_nowait(uint32_t taddr, uint32_t (&r
 }
 
 struct AttnPersistArgs {
+  const int2* windows;            // optional (focus mode): query windows (complex, first query row), 128 rows each; else the regular grid
+  const int* wcount;              // device: wcount[1] = number of windows
   int nb_complex;                 // complexes covered by this launch
   int bias_pitch;                 // floats between consecutive keys of a bias chunk in shared memory (= box width)
   int bias_tx;                    // bytes one bias box delivers
 };
+
+// tile index -> (complex in the launch, head, first query row): regular 128-row grid, or the focus windows (heads fastest)
+struct TileRef { int bl, h, i0; };
+__device__ __forceinline__ TileRef tile_ref(int tile, int nit, const int2* windows) {
+  TileRef t;
+  if (windows) { const int2 w = windows[tile / H]; t.bl = w.x; t.i0 = w.y; t.h = tile % H; }
+  else { const int bh = tile / nit; t.i0 = (tile % nit) * 128; t.h = bh % H; t.bl = bh / H; }
+  return t;
+}
 
 template <int NCH>                                      // 32-key chunks per row: 4 (keys <= 128) or 8 (keys <= 256)
 __global__ void __launch_bounds__(AP_THREADS, 1)
@@ -394,7 +405,7 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = a.L, Lp = a.Lp;
   const int nit = (L + AL_BM - 1) / AL_BM;              // query tiles per (complex, head)
-  const int ntiles = pa.nb_complex * H * nit;
+  const int ntiles = pa.windows ? pa.wcount[1] * H : pa.nb_complex * H * nit;
 
   if (threadIdx.x == 0) {
     mbar_init(a_full, 1); mbar_init(a_empty, 1);
@@ -419,12 +430,12 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
       int btile = blockIdx.x, bc = 0, bm = 0;                   // bias stream: tile, chunk count, chunk in tile
       while (otile < ntiles || btile < ntiles) {
         if (otile < ntiles) {
-          const int it = otile % nit, bh = otile / nit, h = bh % H, bl = bh / H;
-          const int row_base = ((a.b0 + bl) * H + h) * L;
+          const TileRef tr = tile_ref(otile, nit, pa.windows);
+          const int row_base = ((a.b0 + tr.bl) * H + tr.h) * L;
           if (ostep == 0) {
             if (mbar_try_wait(a_empty, (on & 1) ^ 1)) {
               unsigned char* A = smem + AL_A_OFF;
-              const int r0 = row_base + it * AL_BM;
+              const int r0 = row_base + tr.i0;
               mbar_expect_tx(a_full, AL_OPER_BYTES);          // raw fp32 = the "hi" plane; the splitters add the lo plane
               tma_load_2d(A, &tmQh, 0, r0, a_full);
               tma_load_2d(A + AL_BOX_BYTES, &tmQh, 32, r0, a_full);
@@ -446,10 +457,10 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
         if (btile < ntiles) {
           const int s = bc % AP_NBIAS;
           if (mbar_try_wait(&bias_empty[s], ((bc / AP_NBIAS) & 1) ^ 1)) {
-            const int it = btile % nit, bh = btile / nit, h = bh % H, bl = bh / H;
-            const int row_base = ((a.b0 + bl) * H + h) * L;
+            const TileRef tr = tile_ref(btile, nit, pa.windows);
+            const int row_base = ((a.b0 + tr.bl) * H + tr.h) * L;
             mbar_expect_tx(&bias_full[s], (uint32_t)pa.bias_tx);
-            tma_load_2d(smem + AP_BIAS_OFF + s * AP_BIAS_BYTES, &tmBias, it * AL_BM, row_base + bm * 32, &bias_full[s]);
+            tma_load_2d(smem + AP_BIAS_OFF + s * AP_BIAS_BYTES, &tmBias, tr.i0, row_base + bm * 32, &bias_full[s]);
             ++bc;
             if (++bm == NCH) { bm = 0; btile += gridDim.x; }
           }
@@ -526,8 +537,9 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
     const int bpitch = pa.bias_pitch;
     int n = 0, bc = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
-      const int it = tile % nit, bh = tile / nit, h = bh % H, bl = bh / H, b = a.b0 + bl;
-      const int row_base = (b * H + h) * L, i0 = it * AL_BM;
+      const TileRef tr = tile_ref(tile, nit, pa.windows);
+      const int h = tr.h, bl = tr.bl, b = a.b0 + bl, i0 = tr.i0;
+      const int row_base = (b * H + h) * L;
       const int buf = n & 1;
       const int i = i0 + te;
       const bool valid = i < L;
@@ -631,7 +643,7 @@ cudaError_t attn_tc_init() {
 }
 
 bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOperands& op, const float* bias_layer, const uint8_t* mask,
-                           float* alpha, cudaStream_t st) {
+                           float* alpha, cudaStream_t st, const int2* windows, const int* wcount) {
   if (L > AL_MAXCOLS) return false;
   CUtensorMap qh, ql, kh, kl, bm, al;
   const uint64_t rows = (uint64_t)N * H * L;
@@ -657,7 +669,7 @@ bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOpera
     const int ntiles = nb * H * ((L + AL_BM - 1) / AL_BM);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    const AttnPersistArgs pa{nb, (int)bcols, (int)(brows * bcols * 4)};
+    const AttnPersistArgs pa{windows, wcount, nb, (int)bcols, (int)(brows * bcols * 4)};
     if (ncols <= 128) attn_logits_persist_kernel<4><<<ntiles < sms ? ntiles : sms, AP_THREADS, AP_SMEM, st>>>(qh, ql, kh64, kl64, bm32, al, a, pa);
     else attn_logits_persist_kernel<8><<<ntiles < sms ? ntiles : sms, AP_THREADS, AP_SMEM, st>>>(qh, ql, kh64, kl64, bm32, al, a, pa);
   } else if (ncols <= 256) attn_logits_tc_kernel<true><<<grid, AL_THREADS, AL_SMEM, st>>>(qh, ql, kh, kl, bm, al, a);
@@ -868,7 +880,8 @@ __device__ __forceinline__ void st_v8f(float* p, float a0, float a1, float a2, f
 
 __global__ void __launch_bounds__(AGP_THREADS, 1)
 aggr_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmVh,
-                    const __grid_constant__ CUtensorMap tmVl, const AggrArgs a, const int nb_complex) {
+                    const __grid_constant__ CUtensorMap tmVl, const AggrArgs a, const int nb_complex,
+                    const int2* windows, const int* wcount, const int* cidx) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + AGP_ST * AG2_STAGE_BYTES);
@@ -882,7 +895,7 @@ aggr_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int nkb = (L + 31) / 32;
   const int gsz = (nkb + 2) / 3;                        // key blocks per main accumulator (three short accumulation chains)
   const int nit = (L + 127) / 128;
-  const int ntiles = nb_complex * H * nit;
+  const int ntiles = windows ? wcount[1] * H : nb_complex * H * nit;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < AGP_ST; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 4); mbar_init(&empty[s], 1); }
@@ -900,8 +913,8 @@ aggr_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (elect_one()) {
       int g = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int it = tile % nit, bh = tile / nit, h = bh % H, bl = bh / H;
-        const int arow = (bl * H + h) * L + it * 128, vrow = ((a.b0 + bl) * H + h) * 64;
+        const TileRef tr = tile_ref(tile, nit, windows);
+        const int arow = (tr.bl * H + tr.h) * L + tr.i0, vrow = ((a.b0 + tr.bl) * H + tr.h) * 64;
         for (int kb = 0; kb < nkb; ++kb, ++g) {
           const int s = g % AGP_ST;
           mbar_wait(&empty[s], ((g / AGP_ST) & 1) ^ 1);
@@ -966,9 +979,10 @@ aggr_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int ngrp = (nkb + gsz - 1) / gsz;
     int n = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
-      const int it = tile % nit, bh = tile / nit, h = bh % H, bl = bh / H, b = a.b0 + bl;
+      const TileRef tr = tile_ref(tile, nit, windows);
+      const int h = tr.h, b = a.b0 + tr.bl;
       const int buf = n & 1;
-      const int i = it * 128 + q * 32 + lane;
+      const int i = tr.i0 + q * 32 + lane;
       mbar_wait(&tmem_full[buf], (n >> 1) & 1);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
@@ -991,9 +1005,10 @@ aggr_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);        // sums are in registers: the MMA warp may reuse the buffer
-      if (i < L) {
+      const int crow = (i < L) ? (cidx ? cidx[(size_t)b * L + i] : b * L + i) : -1;      // focus mode: compact output row, -1 = not needed
+      if (crow >= 0) {
         const size_t row = (size_t)b * L + i;
-        float* fr = a.feat + row * NFEAT;
+        float* fr = a.feat + (size_t)crow * NFEAT;
         // node aggregate (ga.py:120-125)
 #pragma unroll
         for (int d = 0; d < D; d += 8) st_v8f(fr + FEAT_NODE + h * D + d, o[d], o[d + 1], o[d + 2], o[d + 3], o[d + 4], o[d + 5], o[d + 6], o[d + 7]);
@@ -1040,7 +1055,8 @@ cudaError_t aggr_tc_init() {
 
 // alpha: [chunk][H][L][Lp]; VT / VT_lo: [N][H][64][Lp]
 bool launch_aggr_tc(int nb, int b0, int N, int L, int Lp, const float* alpha, const float* VT, const float* VT_lo,
-                    const float* R, const float* t, float* feat, float* feat_lo, cudaStream_t st) {
+                    const float* R, const float* t, float* feat, float* feat_lo, cudaStream_t st, const int2* windows, const int* wcount,
+                    const int* cidx) {
   CUtensorMap ah, vh, vl;
   const uint64_t arows = (uint64_t)nb * H * L, vrows = (uint64_t)N * H * 64;
   if (!make_tmap(&ah, alpha, arows, Lp, Lp, 128) || !make_tmap(&vh, VT, vrows, Lp, Lp, 64) || !make_tmap(&vl, VT_lo, vrows, Lp, Lp, 64))
@@ -1051,7 +1067,7 @@ bool launch_aggr_tc(int nb, int b0, int N, int L, int Lp, const float* alpha, co
     const int ntiles = nb * H * ((L + 127) / 128);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    aggr_persist_kernel<<<ntiles < sms ? ntiles : sms, AGP_THREADS, AGP_SMEM, st>>>(ah, vh, vl, a, nb);
+    aggr_persist_kernel<<<ntiles < sms ? ntiles : sms, AGP_THREADS, AGP_SMEM, st>>>(ah, vh, vl, a, nb, windows, wcount, cidx);
     return true;
   }
   dim3 grid((L + 127) / 128, H, nb);

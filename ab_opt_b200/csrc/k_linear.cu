@@ -183,8 +183,12 @@ __global__ void __launch_bounds__(RT_THREADS, 1)
 heads_kernel(int M, int L, const float* __restrict__ x, const float* __restrict__ beta, int beta_stride,
              const float* __restrict__ Rbuf, const float* __restrict__ v_t, const uint8_t* __restrict__ mask_gen,
              EpsW w, float* __restrict__ v_next, float* __restrict__ R_next, float* __restrict__ eps_pos,
-             float* __restrict__ c_den, float* __restrict__ prmsd_rows) {
+             float* __restrict__ c_den, float* __restrict__ prmsd_rows, const int* __restrict__ rows, const int* __restrict__ count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // focus mode: x holds only the `count[0]` needed rows (compact); rows[k] is the residue row of compact row k.  Every
+  // other tensor is indexed by the residue row.
+  if (count) { const int g = count[0]; M = g < M ? g : M; }
+  if ((int)blockIdx.x * RT_ROWS >= M) return;
   RowTileSmem& s = *reinterpret_cast<RowTileSmem*>(smem_raw);
   float* xin = reinterpret_cast<float*>(smem_raw + sizeof(RowTileSmem));      // [64][RT_ACT_LD]
   float* hid = xin + RT_ROWS * RT_ACT_LD;                                     // [64][RT_ACT_LD]
@@ -199,7 +203,10 @@ heads_kernel(int M, int L, const float* __restrict__ x, const float* __restrict_
     const int row = row0 + warp * 8 + r;
     float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
     float b = 0.f;
-    if (row < M) { xv = *reinterpret_cast<const float4*>(x + (size_t)row * F + lane * 4); b = beta[(size_t)(row / L) * beta_stride]; }
+    if (row < M) {
+      xv = *reinterpret_cast<const float4*>(x + (size_t)row * F + lane * 4);
+      b = beta[(size_t)((rows ? rows[row] : row) / L) * beta_stride];
+    }
     *reinterpret_cast<float4*>(xin + (warp * 8 + r) * RT_ACT_LD + lane * 4) = xv;
     ext[r][0] = b; ext[r][1] = sinf(b); ext[r][2] = cosf(b);
   }
@@ -240,8 +247,9 @@ heads_kernel(int M, int L, const float* __restrict__ x, const float* __restrict_
 
   // per-residue epilogue: rotate eps_crd, compose the rotation update, softmax the aa logits
   if (threadIdx.x < RT_ROWS) {
-    const int row = row0 + threadIdx.x;
-    if (row < M) {
+    const int krow = row0 + threadIdx.x;
+    if (krow < M) {
+      const int row = rows ? rows[krow] : krow;
       const float* o = outs + threadIdx.x * HD_OUT_LD;
       const bool gen = mask_gen[row] != 0;
       Mat3 R;
@@ -289,6 +297,65 @@ __global__ void prmsd_mean_kernel(int L, int bins, const float* __restrict__ prm
   out[(size_t)n * bins + k] = sum / (float)L;
 }
 
+// ------------------------------------------------------------------------------------------ focus (last-layer row restriction)
+// Inside the sampling loop of a model WITHOUT the pRMSD head, the output of the last GABlock is consumed only by the three
+// heads, and their outputs only on generated residues (dpm_full.py:98,105; transition.py:99,158,176).  So the last block
+// needs its query side (logits rows, pair / node / point aggregation, tail) only for the generated rows.  focus_build_kernel
+// turns mask_generate into: the compact row list, its inverse, and per complex the 128-row query windows that cover them.
+__global__ void __launch_bounds__(256)
+focus_build_kernel(int N, int L, const uint8_t* __restrict__ mask_gen, int* __restrict__ cidx, int* __restrict__ rows,
+                   int2* __restrict__ windows, int* __restrict__ count, int* __restrict__ scratch) {
+  int* nrow = scratch;            // [N] generated rows per complex -> exclusive prefix
+  int* nwin = scratch + N;        // [N] windows per complex -> exclusive prefix
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    int g = 0, wct = 0, cover = -1;
+    for (int i = 0; i < L; ++i)
+      if (mask_gen[(size_t)n * L + i]) {
+        ++g;
+        if (i >= cover) { ++wct; cover = (i & ~7) + 128; }
+      }
+    nrow[n] = g; nwin[n] = wct;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int a = 0, b = 0;
+    for (int n = 0; n < N; ++n) { const int g = nrow[n], wv = nwin[n]; nrow[n] = a; nwin[n] = b; a += g; b += wv; }
+    count[0] = a; count[1] = b;
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    int k = nrow[n], wk = nwin[n], cover = -1;
+    for (int i = 0; i < L; ++i) {
+      const size_t r = (size_t)n * L + i;
+      if (mask_gen[r]) {
+        cidx[r] = k; rows[k] = (int)r; ++k;
+        if (i >= cover) { windows[wk++] = make_int2(n, i & ~7); cover = (i & ~7) + 128; }
+      } else cidx[r] = -1;
+    }
+  }
+}
+// x_c[k] = x[rows[k]], mask_c[k] = mask[rows[k]]: the residual input and the residue mask of the compact tail
+__global__ void focus_gather_kernel(const int* __restrict__ rows, const int* __restrict__ count, const float* __restrict__ x,
+                                    const uint8_t* __restrict__ mask, float* __restrict__ x_c, uint8_t* __restrict__ mask_c) {
+  const int g = count[0];
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nwarp = (gridDim.x * blockDim.x) >> 5;
+  for (int k = warp; k < g; k += nwarp) {
+    const int r = rows[k];
+    reinterpret_cast<float4*>(x_c + (size_t)k * F)[lane] = reinterpret_cast<const float4*>(x + (size_t)r * F)[lane];
+    if (lane == 0) mask_c[k] = mask[r];
+  }
+}
+void launch_focus_build(int N, int L, const uint8_t* mask_gen, int* cidx, int* rows, int2* windows, int* count, int* scratch,
+                        cudaStream_t st) {
+  ProfScope prof__(KK_OTHER, st);
+  focus_build_kernel<<<1, 256, 0, st>>>(N, L, mask_gen, cidx, rows, windows, count, scratch);
+}
+void launch_focus_gather(const int* rows, const int* count, const float* x, const uint8_t* mask, float* x_c, uint8_t* mask_c,
+                         cudaStream_t st) {
+  ProfScope prof__(KK_OTHER, st);
+  focus_gather_kernel<<<64, 256, 0, st>>>(rows, count, x, mask, x_c, mask_c);
+}
+
 // ------------------------------------------------------------------------------------------ launchers
 size_t mixer_smem() { return sizeof(RowTileSmem) + RT_ROWS * RT_ACT_LD * sizeof(float); }
 size_t tail_smem() { return sizeof(RowTileSmem) + RT_ROWS * RT_ACT_LD * sizeof(float); }
@@ -316,10 +383,10 @@ void launch_tail(int M, const float* feat, const float* pre, const float* x, con
 }
 void launch_heads(int M, int L, const float* x, const float* beta, int beta_stride, const float* Rbuf, const float* v_t,
                   const uint8_t* mask_gen, const EpsW& w, float* v_next, float* R_next, float* eps_pos, float* c_den,
-                  float* prmsd_rows, float* prmsd_logits, cudaStream_t st) {
+                  float* prmsd_rows, float* prmsd_logits, cudaStream_t st, const int* rows, const int* count) {
   ProfScope prof__(KK_HEADS, st);
   heads_kernel<<<(M + RT_ROWS - 1) / RT_ROWS, RT_THREADS, heads_smem(), st>>>(M, L, x, beta, beta_stride, Rbuf, v_t, mask_gen, w,
-                                                                           v_next, R_next, eps_pos, c_den, prmsd_rows);
+                                                                           v_next, R_next, eps_pos, c_den, prmsd_rows, rows, count);
   if (w.has_prmsd && prmsd_logits != nullptr) {
     prmsd_mean_kernel<<<M / L, 64, 0, st>>>(L, w.prmsd_bins, prmsd_rows, prmsd_logits);
     count_launch();

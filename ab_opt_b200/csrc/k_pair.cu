@@ -180,6 +180,7 @@ struct PairRowsArgs {
   const uint8_t* mask;
   float* alpha;                   // [chunk complex][h][i][Lp]; rows of masked queries are zeroed here (ga.py:25)
   float* feat; float* feat_lo;
+  const int* cidx;                // optional (focus mode): compact output row of query row r, -1 = row not needed at all
 };
 
 __device__ __forceinline__ void bulk_load_1d_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
@@ -218,21 +219,29 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs 
   auto advance = [&](int& bl, int& i) { bl += dbl; i += di; if (i >= L) { i -= L; ++bl; } };
   // query mask of the warp's next 32 rows as one ballot word (lane k <-> the k-th row from `row`), so that neither the
   // producer nor the consumer ever waits on a global load per row
-  auto live_word = [&](int row) {
+  // need_word: rows this launch has to produce at all (focus mode skips the others without touching anything)
+  auto live_word = [&](int row, unsigned& need_word) {
     const long long r = (long long)row + (long long)lane * stride;
-    bool live = false;
-    if (r < a.nrows) { const int bl = (int)(r / L); live = a.mask[(size_t)(a.b0 + bl) * L + (int)(r - (long long)bl * L)] != 0; }
+    bool live = false, need = false;
+    if (r < a.nrows) {
+      const int bl = (int)(r / L);
+      const size_t gr = (size_t)(a.b0 + bl) * L + (int)(r - (long long)bl * L);
+      need = a.cidx ? a.cidx[gr] >= 0 : true;
+      live = need && a.mask[gr] != 0;
+    }
+    need_word = __ballot_sync(0xffffffffu, need);
     return __ballot_sync(0xffffffffu, live);
   };
 
   // ---- producer cursor (lane 0 issues): the warp's live rows, chunk by chunk, up to PW_STAGES chunks ahead of the consumer
   int prow = first, pbl = first / L, pi = first - pbl * L, pjc = 0, ps = 0, pk = 0;
-  unsigned pword = live_word(first);
+  unsigned pneed_unused;
+  unsigned pword = live_word(first, pneed_unused);
   const uint64_t pol = policy_evict_first();
   auto issue = [&]() {                                  // executed by the whole warp (uniform control flow)
     while (prow < a.nrows && !((pword >> pk) & 1u)) {    // skip masked query rows
       prow += stride; advance(pbl, pi);
-      if (++pk == 32) { pk = 0; pword = live_word(prow); }
+      if (++pk == 32) { pk = 0; pword = live_word(prow, pneed_unused); }
     }
     if (prow >= a.nrows) return;
     const int j0 = pjc * PW_CJ;
@@ -246,7 +255,7 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs 
     if (++ps == PW_STAGES) ps = 0;
     if (++pjc == a.nchunk) {
       pjc = 0; prow += stride; advance(pbl, pi);
-      if (++pk == 32) { pk = 0; pword = live_word(prow); }
+      if (++pk == 32) { pk = 0; pword = live_word(prow, pneed_unused); }
     }
   };
   for (int s = 0; s < PW_STAGES; ++s) issue();
@@ -256,14 +265,17 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs 
   const uint32_t aoff0 = (uint32_t)(PW_Z_BYTES + q * 16);               // alpha[h][4q..4q+3] at + h * 64
   int cs = 0, ck = 0;
   uint32_t cph = 0;
-  unsigned cword = live_word(first);
+  unsigned cneed;
+  unsigned cword = live_word(first, cneed);
   int bl = first / L, i = first - bl * L;
   for (int row = first; row < a.nrows; row += stride, advance(bl, i)) {
     const int b = a.b0 + bl;
-    float* feat_row = a.feat + ((size_t)b * L + i) * NFEAT;
-    float* feat_lo_row = a.feat_lo + ((size_t)b * L + i) * NFEAT;
-    const bool live = (cword >> ck) & 1u;
-    if (++ck == 32) { ck = 0; cword = live_word(row + stride); }
+    const bool live = (cword >> ck) & 1u, need = (cneed >> ck) & 1u;
+    if (++ck == 32) { ck = 0; cword = live_word(row + stride, cneed); }
+    if (!need) continue;
+    const size_t orow = a.cidx ? (size_t)a.cidx[(size_t)b * L + i] : (size_t)b * L + i;
+    float* feat_row = a.feat + orow * NFEAT;
+    float* feat_lo_row = a.feat_lo + orow * NFEAT;
     if (!live) {
       // masked query: alpha row = 0 (ga.py:25) -> zero pair aggregate
       float* alpha_row0 = a.alpha + ((size_t)(bl * H) * L + i) * Lp;
@@ -393,14 +405,14 @@ bool launch_pair_bias(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, in
 }
 
 bool launch_pair_stream(int nb, int b0, int L, int Lp, const float* z, const uint8_t* mask,
-                        float* alpha, float* feat, float* feat_lo, cudaStream_t st) {
+                        float* alpha, float* feat, float* feat_lo, cudaStream_t st, const int* cidx) {
   CUtensorMap amap;
   // alpha as a plain 3-D tensor [nb * H][L queries][Lp keys]; box = [12 heads][1 query][16 keys]
   if (!make_tmap_3d_plain(&amap, alpha, (uint64_t)Lp, (uint64_t)L, (uint64_t)nb * H, PW_CJ, 1, H)) return false;
   ProfScope prof__(KK_PAIR, st);
   PairRowsArgs a{};
   a.L = L; a.Lp = Lp; a.b0 = b0; a.nrows = nb * L; a.nchunk = (L + PW_CJ - 1) / PW_CJ;
-  a.z = z; a.mask = mask; a.alpha = alpha; a.feat = feat; a.feat_lo = feat_lo;
+  a.z = z; a.mask = mask; a.alpha = alpha; a.feat = feat; a.feat_lo = feat_lo; a.cidx = cidx;
   int grid = g_sm_count > 0 ? g_sm_count : 148;
   const int need = (a.nrows + PW_WARPS - 1) / PW_WARPS;
   if (grid > need) grid = need;

@@ -30,6 +30,7 @@ struct TailArgs {
   const float* b1; const float* b2; const float* b3;
   const float* ln2_g; const float* ln2_b;
   float* x_out; float* x_lo_out;
+  const int* count;               // optional (focus mode): count[0] = number of valid rows, on the device (<= M)
 };
 
 // phase timestamps of CTA 0 (SM clock), read back by abopt_debug_clocks() slots 10..15
@@ -45,6 +46,11 @@ outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmWl, const __grid_constant__ CUtensorMap tmX,
                  const __grid_constant__ CUtensorMap tmXo, const __grid_constant__ CUtensorMap tmXl, int M, int K, const TailArgs ta) {
   extern __shared__ unsigned char smem_raw[];
+  if (ta.count) {                              // focus mode: the row count lives on the device; surplus CTAs leave at once
+    const int rows = ta.count[0];
+    if ((int)blockIdx.x * 128 >= rows) return;
+    M = rows < M ? rows : M;
+  }
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + OT_BAR_OFF);
   uint64_t* empty = full + OT_ST;
@@ -344,7 +350,7 @@ cudaError_t tail_tc_init() {
 
 // x_out = GABlock tail(feat, x); feat (M, 1824) raw fp32, weights as hi / lo planes (Wmlp = [W1; W2; W3], each [128][128])
 bool launch_outT_tail(int M, const float* feat, const float* x, const uint8_t* mask, const BlockW& w, float* x_out,
-                      float* x_lo_out, cudaStream_t st) {
+                      float* x_lo_out, cudaStream_t st, const int* count) {
   CUtensorMap a, bh, bl, wh, wl, tx, txo, txl;
   if (!make_tmap(&tx, x, M, F, F, 128) || !make_tmap(&txo, x_out, M, F, F, 128) ||
       !make_tmap(&txl, x_lo_out ? x_lo_out : x_out, M, F, F, 128) ||
@@ -353,7 +359,7 @@ bool launch_outT_tail(int M, const float* feat, const float* x, const uint8_t* m
       !make_tmap(&wl, w.Wmlp_lo, 3 * F, F, F, 128))
     return false;
   ProfScope prof__(KK_TAIL, st);
-  const TailArgs ta{x, mask, w.bout, w.ln1_g, w.ln1_b, w.b1, w.b2, w.b3, w.ln2_g, w.ln2_b, x_out, x_lo_out};
+  const TailArgs ta{x, mask, w.bout, w.ln1_g, w.ln1_b, w.b1, w.b2, w.b3, w.ln2_g, w.ln2_b, x_out, x_lo_out, count};
   outT_tail_kernel<<<(M + 127) / 128, OT_THREADS, OT_SMEM, st>>>(a, bh, bl, wh, wl, tx, txo, txl, M, NFEAT, ta);
   return true;
 }

@@ -63,7 +63,7 @@ bool launch_gemm3x_splitA(int M, int N, int K, const float* A, int lda, const fl
 cudaError_t tail_tc_init();
 void tail_debug_clocks(long long* out6);
 bool launch_outT_tail(int M, const float* feat, const float* x, const uint8_t* mask, const BlockW& w, float* x_out,
-                      float* x_lo_out, cudaStream_t st);
+                      float* x_lo_out, cudaStream_t st, const int* count = nullptr);
 
 // operands of the tensor-core attention kernels, produced by the projection GEMM epilogue (k_tc.cu: EpiProjPack)
 struct AttnOperands {
@@ -76,7 +76,8 @@ bool launch_proj_pack(int M, int L, int Lp, const float* xh, const float* xl, co
                       const float* coef, const AttnOperands& op, cudaStream_t st);
 cudaError_t aggr_tc_init();
 bool launch_aggr_tc(int nb, int b0, int N, int L, int Lp, const float* alpha, const float* VT, const float* VT_lo,
-                    const float* R, const float* t, float* feat, float* feat_lo, cudaStream_t st);
+                    const float* R, const float* t, float* feat, float* feat_lo, cudaStream_t st, const int2* windows = nullptr,
+                    const int* wcount = nullptr, const int* cidx = nullptr);
 bool make_tmap(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 bool make_tmap_plain(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
 cudaError_t attn_tc_init();
@@ -84,7 +85,7 @@ bool attn_needs_qk_lo(int L);      // true when the logits kernel for this lengt
 void attn_debug_clocks(long long* out16);
 // final logits + softmax on the tensor cores: alpha[chunk][h][i][Lp] for complexes [b0, b0 + nb)
 bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOperands& op, const float* bias_layer, const uint8_t* mask,
-                           float* alpha, cudaStream_t st);
+                           float* alpha, cudaStream_t st, const int2* windows = nullptr, const int* wcount = nullptr);
 bool make_tmap_3d(CUtensorMap* m, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1);
 
 void launch_mixer(int M, const float* res_feat, const long long* s_t, const float* v_t, const EpsW& w,
@@ -94,7 +95,21 @@ void launch_tail(int M, const float* feat, const float* pre, const float* x, con
                  float* x_lo_out, cudaStream_t st);
 void launch_heads(int M, int L, const float* x, const float* beta, int beta_stride, const float* Rbuf, const float* v_t,
                   const uint8_t* mask_gen, const EpsW& w, float* v_next, float* R_next, float* eps_pos, float* c_den,
-                  float* prmsd_rows, float* prmsd_logits, cudaStream_t st);
+                  float* prmsd_rows, float* prmsd_logits, cudaStream_t st, const int* rows = nullptr, const int* count = nullptr);
+// focus mode (k_linear.cu): restriction of the last GABlock to the generated rows inside the sampling loop
+struct Focus {
+  int* cidx;          // [M]  compact row of residue row r, -1 = not needed
+  int* rows;          // [M]  residue row of compact row k
+  int2* windows;      // [N * ceil(L / 128) + N]  (complex, first query row) of the 128-row query windows
+  int* count;         // [2]  count[0] = needed rows, count[1] = windows (device)
+  int* scratch;       // [2 N]
+  float* x_c;         // [M][128] gathered block input of the compact rows
+  uint8_t* mask_c;    // [M]
+};
+void launch_focus_build(int N, int L, const uint8_t* mask_gen, int* cidx, int* rows, int2* windows, int* count, int* scratch,
+                        cudaStream_t st);
+void launch_focus_gather(const int* rows, const int* count, const float* x, const uint8_t* mask, float* x_c, uint8_t* mask_c,
+                         cudaStream_t st);
 
 void launch_alpha_tap(int nb, int b0, int L, int Lp, const float* alpha, float* out, cudaStream_t st);
 // pair_stream_kernel (k_pair.cu): TMA-fed persistent replacement of pair_kernel
@@ -104,7 +119,7 @@ bool make_pair_tmap(CUtensorMap* m, const float* z, size_t total_rows, int* box_
 bool launch_pair_bias(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, int box_rows, const PairBiasPacked& pb, float* bias,
                       cudaStream_t st);
 bool launch_pair_stream(int nb, int b0, int L, int Lp, const float* z, const uint8_t* mask,
-                        float* alpha, float* feat, float* feat_lo, cudaStream_t st);
+                        float* alpha, float* feat, float* feat_lo, cudaStream_t st, const int* cidx = nullptr);
 bool make_tmap_3d_plain(CUtensorMap* m, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1, uint32_t box2);
 
 void launch_angle_argmax(int M, int L, const long long* tvec, int t_uniform, const float* Y, const float* expo,
