@@ -439,8 +439,9 @@ def test_reverse_step_abdesign_focus(N, L, segs, ragged):
         e_cuda = (G.so3_exp(v_o.double()) - R64).abs().amax(dim=(-1, -2))
         e_o32 = (G.so3_exp(ref['v_next'].double()) - R64).abs().amax(dim=(-1, -2))
         gap = (np.pi - ref64['v_next'].norm(dim=-1)).clamp_min(1e-9)
-        ok = gap > 0.05
+        ok = (gap > 0.05) & (e_o32 < 1e-3)       # where even fp32-vs-fp64 of the oracle differs by > 1e-3 nothing can be concluded
         bad = ok & (e_cuda > 4 * e_o32 + 2e-5 + 3e-6 / gap ** 2)
+        assert ok[inp['mask_generate']].float().mean() > 0.8
         assert not bad.any(), f'v_next t={t}: {int(bad.sum())} residues off: cuda {e_cuda[bad].max().item():.3e} oracle32 {e_o32[bad].max().item():.3e}'
         flips += (s_o != ref['s_next']).sum().item()
         keep = ~inp['mask_generate']
