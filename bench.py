@@ -272,18 +272,26 @@ def run_ours(args, cfg, rank, world, local_rank):
         total_ms = sum(v[0] for v in prof.values())
         peak, peak_src = measured_peak_gbs()
         per_launch_complexes = B * NUM_LAYERS * T_STEPS / max(pair_n, 1)
-        alg_bytes = per_launch_complexes * algorithmic_bytes_per_complex_layer(L)
+        # Focus mode: for models without the pRMSD head the LAST block streams z only for the generated
+        # query rows, so that launch has fewer algorithmic bytes.  The kernel-level roofline is bytes-weighted over all
+        # pair_stream_kernel launches of a sample; whole_step_* keep SURVEY 8d's fixed denominator (z once per layer).
+        focus = cfg['flavour'] == 'abdesign' and L <= 256 and os.environ.get('ABOPT_NO_FOCUS', '0') != '1'
+        alg_full = per_launch_complexes * algorithmic_bytes_per_complex_layer(L)
+        alg_focus = per_launch_complexes * (n_gen * L * 64 * 4 + L * (2 * 128 * 4 + 36 + 12 + 1))
+        alg_bytes = ((NUM_LAYERS - 1) * alg_full + (alg_focus if focus else alg_full)) / NUM_LAYERS      # mean per launch
         achieved = alg_bytes / (pair_ms / pair_n * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, 'profiles', 'pair_kernel_traffic.json')
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             if tj.get('L') == L:
-                traffic = tj['dram_bytes_per_complex'] * per_launch_complexes
+                traffic = tj['dram_bytes_per_complex'] * per_launch_complexes * alg_bytes / alg_full
         roof = {'bound': 'hbm', 'kernel': 'pair_stream_kernel (streams pair_feat once per IPA layer: softmax-weighted pair aggregation)',
                 'achieved': achieved, 'peak': peak,
                 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': alg_bytes, 'avg_launch_ms': pair_ms / pair_n, 'launches_per_sample': pair_n,
+                'focus': ('last of %d layers streams only the %d generated query rows per complex; achieved / traffic / '
+                          'algorithmic bytes are means over all launches of a sample' % (NUM_LAYERS, n_gen)) if focus else None,
                 'share_of_gpu_time': pair_ms / total_ms,
                 'whole_step_achieved': B * NUM_LAYERS * T_STEPS * algorithmic_bytes_per_complex_layer(L) / (ms_per_step * 1e-3) / 1e9,
                 'whole_step_frac': B * NUM_LAYERS * T_STEPS * algorithmic_bytes_per_complex_layer(L) / (ms_per_step * 1e-3) / 1e9 / peak}

@@ -8,7 +8,7 @@ top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 hdr = rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
 stall_cols = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
-data = [r for r in rows[2:] if len(r) == len(hdr)]
+data = [r for r in rows[2:] if len(r) == len(hdr) and r[idx['# Samples']].strip().isdigit()]      # several launches: header rows repeat
 tot = {c: sum(int(r[idx[c]] or 0) for r in data) for c in stall_cols}
 all_s = sum(int(r[idx['# Samples']] or 0) for r in data)
 print('total samples', all_s)
