@@ -212,12 +212,15 @@ heads_kernel(int M, int L, const float* __restrict__ x, const float* __restrict_
   }
   __syncthreads();
 
+  // blockIdx.y selects the head (0 eps_crd, 1 eps_rot, 2 eps_seq, 3 pRMSD): the four heads are independent down to their
+  // per-residue epilogues, so they run as separate CTAs (4x the parallelism of one CTA walking all heads; in focus mode
+  // only a few row tiles exist)
+  const int head = blockIdx.y;
   float acc[8][4];
-  run_head(acc, s, xin, hid, w.crd, ext);  stage_out(acc, outs, 0, 3);
-  run_head(acc, s, xin, hid, w.rot, ext);  stage_out(acc, outs, 3, 3);
-  run_head(acc, s, xin, hid, w.seq, ext);  stage_out(acc, outs, 6, NAA);
-
-  if (w.has_prmsd) {
+  if (head == 0) { run_head(acc, s, xin, hid, w.crd, ext); stage_out(acc, outs, 0, 3); }
+  else if (head == 1) { run_head(acc, s, xin, hid, w.rot, ext); stage_out(acc, outs, 3, 3); }
+  else if (head == 2) { run_head(acc, s, xin, hid, w.seq, ext); stage_out(acc, outs, 6, NAA); }
+  else {
     // PerResiduePredictor (common/nn.py:164-188): LayerNorm over the 131 inputs, then 3 linears.
     float g[8][4], gext[8][3];
     const float4 lg = *reinterpret_cast<const float4*>(w.prm_ln_g + lane * 4);
@@ -237,7 +240,7 @@ heads_kernel(int M, int L, const float* __restrict__ x, const float* __restrict_
       gext[r][1] = e1 / sd * w.prm_ln_g[129] + w.prm_ln_b[129];
       gext[r][2] = e2 / sd * w.prm_ln_g[130] + w.prm_ln_b[130];
     }
-    __syncthreads();                                   // all heads finished reading xin
+    __syncthreads();                                   // every warp has read xin
     rt_store_act(g, xin, RT_ACT_LD);
     __syncthreads();
     run_head(acc, s, xin, hid, w.prm, gext);
@@ -245,44 +248,51 @@ heads_kernel(int M, int L, const float* __restrict__ x, const float* __restrict_
   }
   __syncthreads();
 
-  // per-residue epilogue: rotate eps_crd, compose the rotation update, softmax the aa logits
+  // per-residue epilogue of this head
   if (threadIdx.x < RT_ROWS) {
     const int krow = row0 + threadIdx.x;
     if (krow < M) {
       const int row = rows ? rows[krow] : krow;
       const float* o = outs + threadIdx.x * HD_OUT_LD;
       const bool gen = mask_gen[row] != 0;
-      Mat3 R;
+      if (head == 0) {
+        // eps_pos = R eps_crd, zero outside the generated region (dpm_full.py:96-98)
+        Mat3 R;
 #pragma unroll
-      for (int i = 0; i < 9; ++i) R.m[i] = Rbuf[(size_t)row * 9 + i];
-      // eps_pos = R eps_crd, zero outside the generated region (dpm_full.py:96-98)
+        for (int i = 0; i < 9; ++i) R.m[i] = Rbuf[(size_t)row * 9 + i];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const float e = R.m[i * 3 + 0] * o[0] + R.m[i * 3 + 1] * o[1] + R.m[i * 3 + 2] * o[2] + 0.f;
-        eps_pos[(size_t)row * 3 + i] = gen ? e : 0.f;
-      }
-      // R_next = R U(eps_rot), v_next = log(R_next) on generated residues (dpm_full.py:101-105)
-      const Mat3 U = quat1ijk_to_rot(o[3], o[4], o[5]);
-      const Mat3 Rn = matmul3(R, U);
-      if (R_next != nullptr)
+        for (int i = 0; i < 3; ++i) {
+          const float e = R.m[i * 3 + 0] * o[0] + R.m[i * 3 + 1] * o[1] + R.m[i * 3 + 2] * o[2] + 0.f;
+          eps_pos[(size_t)row * 3 + i] = gen ? e : 0.f;
+        }
+      } else if (head == 1) {
+        // R_next = R U(eps_rot), v_next = log(R_next) on generated residues (dpm_full.py:101-105)
+        Mat3 R;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) R_next[(size_t)row * 9 + i] = Rn.m[i];
-      float vx, vy, vz;
-      so3_log(Rn, vx, vy, vz);
-      v_next[(size_t)row * 3 + 0] = gen ? vx : v_t[(size_t)row * 3 + 0];
-      v_next[(size_t)row * 3 + 1] = gen ? vy : v_t[(size_t)row * 3 + 1];
-      v_next[(size_t)row * 3 + 2] = gen ? vz : v_t[(size_t)row * 3 + 2];
-      // softmax over 20 classes (dpm_full.py:61,108)
-      float mx = o[6];
+        for (int i = 0; i < 9; ++i) R.m[i] = Rbuf[(size_t)row * 9 + i];
+        const Mat3 U = quat1ijk_to_rot(o[3], o[4], o[5]);
+        const Mat3 Rn = matmul3(R, U);
+        if (R_next != nullptr)
 #pragma unroll
-      for (int k = 1; k < NAA; ++k) mx = fmaxf(mx, o[6 + k]);
-      float e[NAA], sum = 0.f;
+          for (int i = 0; i < 9; ++i) R_next[(size_t)row * 9 + i] = Rn.m[i];
+        float vx, vy, vz;
+        so3_log(Rn, vx, vy, vz);
+        v_next[(size_t)row * 3 + 0] = gen ? vx : v_t[(size_t)row * 3 + 0];
+        v_next[(size_t)row * 3 + 1] = gen ? vy : v_t[(size_t)row * 3 + 1];
+        v_next[(size_t)row * 3 + 2] = gen ? vz : v_t[(size_t)row * 3 + 2];
+      } else if (head == 2) {
+        // softmax over 20 classes (dpm_full.py:61,108)
+        float mx = o[6];
 #pragma unroll
-      for (int k = 0; k < NAA; ++k) { e[k] = expf(o[6 + k] - mx); sum += e[k]; }
+        for (int k = 1; k < NAA; ++k) mx = fmaxf(mx, o[6 + k]);
+        float e[NAA], sum = 0.f;
 #pragma unroll
-      for (int k = 0; k < NAA; ++k) c_den[(size_t)row * NAA + k] = e[k] / sum;
-      if (w.has_prmsd)
+        for (int k = 0; k < NAA; ++k) { e[k] = expf(o[6 + k] - mx); sum += e[k]; }
+#pragma unroll
+        for (int k = 0; k < NAA; ++k) c_den[(size_t)row * NAA + k] = e[k] / sum;
+      } else {
         for (int k = 0; k < w.prmsd_bins; ++k) prmsd_rows[(size_t)row * w.prmsd_bins + k] = o[26 + k];
+      }
     }
   }
 }
@@ -385,7 +395,7 @@ void launch_heads(int M, int L, const float* x, const float* beta, int beta_stri
                   const uint8_t* mask_gen, const EpsW& w, float* v_next, float* R_next, float* eps_pos, float* c_den,
                   float* prmsd_rows, float* prmsd_logits, cudaStream_t st, const int* rows, const int* count) {
   ProfScope prof__(KK_HEADS, st);
-  heads_kernel<<<(M + RT_ROWS - 1) / RT_ROWS, RT_THREADS, heads_smem(), st>>>(M, L, x, beta, beta_stride, Rbuf, v_t, mask_gen, w,
+  heads_kernel<<<dim3((M + RT_ROWS - 1) / RT_ROWS, w.has_prmsd ? 4 : 3), RT_THREADS, heads_smem(), st>>>(M, L, x, beta, beta_stride, Rbuf, v_t, mask_gen, w,
                                                                            v_next, R_next, eps_pos, c_den, prmsd_rows, rows, count);
   if (w.has_prmsd && prmsd_logits != nullptr) {
     prmsd_mean_kernel<<<M / L, 64, 0, st>>>(L, w.prmsd_bins, prmsd_rows, prmsd_logits);
