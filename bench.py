@@ -208,6 +208,10 @@ def run_ours(args, cfg, rank, world, local_rank):
         torch.cuda.synchronize()
 
     torch.manual_seed(rank)
+    # initialisation, not warm-up: the first two calls pay one-off costs (3 GB workspace cudaMalloc + memset, TMA descriptor
+    # encodes, first-touch page faults of the host-side trajectory buffers) that measured 150-190 ms each on B200
+    for _ in range(2):
+        step()
     for _ in range(args.warmup):
         step()
     barrier()
@@ -310,6 +314,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                        'flavour': cfg['flavour'], 'rng': 'philox (in-kernel)', 'weights': 'seeded random init',
                        'l2': 'inputs larger than L2 (pair_feat %.2f GB per GPU)' % (B * L * L * 64 * 4 / 1e9),
                        'value_includes': 'init noise, 100 reverse steps, trajectory D2H, final gather (N>1)',
+                       'init_calls_before_warmup': 2,
                        'e2e_result': 'traj[0] and traj[T] (v, p, s) read back; full trajectory not copied'},
             'clocks': clk,
             'e2e': {'value': e2e_value, 'unit': 'residues/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
