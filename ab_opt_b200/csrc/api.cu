@@ -548,8 +548,8 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
   float* flo = outt_legacy ? w.feat_lo : nullptr;
   for (int b0 = 0; b0 < N; b0 += w.NB) {
     const int nb = (N - b0 < w.NB) ? (N - b0) : w.NB;
-    // everything a chunk of complexes produces and consumes below stays L2 resident: its projections (packed attention
-    // operands), its attention weights, its aggregates; only z and the pair bias stream from HBM
+    // one pass = as many complexes as the alpha buffer holds (normally the whole batch, see chunk_size): projections ->
+    // packed attention operands -> alpha -> aggregates; every tensor between two kernels travels through HBM / L2 once
     {
       const size_t r0 = (size_t)b0 * L, o64 = (size_t)b0 * H * L * 64, o1 = (size_t)b0 * H * L, ov = (size_t)b0 * H * 64 * w.Lp;
       const AttnOperands opc{w.op.QA + o64, w.op.QA_lo + o64, w.op.KB + o64, w.op.KB_lo + o64, w.op.rq + o1, w.op.rk + o1,
@@ -557,7 +557,7 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
       if (!launch_proj_pack(nb * L, L, w.Lp, x + r0 * F, x_lo + r0 * F, bw.Wcat, bw.Wcat_lo, R + r0 * 9, t + r0 * 3, bw.coef, opc, st))
         return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (proj)");
     }
-    // logits (node + spatial + pair bias, scaled, masked) and softmax on the tensor cores -> alpha (L2 resident chunk)
+    // logits (node + spatial + pair bias, scaled, masked) and softmax on the tensor cores -> alpha
     if (!launch_attn_logits_tc(nb, b0, N, L, w.Lp, w.op, bias, mask, w.alpha, st, fc ? fc->windows : nullptr, fc ? fc->count : nullptr))
       return fail(ABOPT_ERR_CUDA, "attn_logits_tc launch failed");
     if (!launch_pair_stream(nb, b0, L, w.Lp, z, mask, w.alpha, w.feat, flo, st, fc ? fc->cidx : nullptr))

@@ -112,7 +112,7 @@ void launch_focus_gather(const int* rows, const int* count, const float* x, cons
                          cudaStream_t st);
 
 void launch_alpha_tap(int nb, int b0, int L, int Lp, const float* alpha, float* out, cudaStream_t st);
-// pair_stream_kernel (k_pair.cu): TMA-fed persistent replacement of pair_kernel
+// k_pair.cu: pair_bias_kernel (hoisted z . W_b) and pair_stream_kernel (streams z once per GABlock)
 cudaError_t pair_stream_init();
 bool make_tmap_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
 bool make_pair_tmap(CUtensorMap* m, const float* z, size_t total_rows, int* box_rows_out);
