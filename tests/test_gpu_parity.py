@@ -449,3 +449,42 @@ def test_reverse_step_abdesign_focus(N, L, segs, ragged):
         assert torch.equal(s_o[keep & inp['mask_res']], s_t[keep & inp['mask_res']])
         v_t, p_t, s_t = ref['v_next'], ref['p_next'] * 10.0, ref['s_next']
     assert flips == 0
+
+
+def test_focus_edge_cases():
+    """Focus mode with an odd length (L = 33, row pitch 40), one complex without any generated residue, one whose
+    generated residues sit at both ends of the chain, and one generated residue that is masked out (mask_res False):
+    the next state must match the oracle everywhere (positions, rotations where well conditioned, sequence exactly)."""
+    N, L = 4, 33
+    W = weights.make_state_dict(seed=23, num_layers=2, flavour='abdesign')
+    inp = weights.synthetic_inputs(51, N, L, gen_slices=((0, 3), (29, 33)), ragged=False)
+    inp['mask_generate'][1] = False                       # nothing to generate in complex 1
+    inp['mask_generate'][2, 10:14] = True                 # a third segment in complex 2
+    inp['mask_res'][3, 30:] = False                       # complex 3: part of the generated tail is padding
+    inp['s'][3, 30:] = 21
+    model = build_model(W, 2, flavour='abdesign')
+    W64 = {k: (v.double() if v.is_floating_point() else v) for k, v in W.items()}
+    ci = cu(inp)
+    gen = torch.Generator().manual_seed(9)
+    v_t, p_t, s_t = inp['v'], inp['p'], inp['s']
+    for t in (50, 1):
+        nz = T.draw_step_noise(N, L, gen)
+        ref = sampler.reverse_step(W, t, v_t, p_t / 10.0, s_t, inp['res_feat'], inp['pair_feat'], inp['mask_generate'],
+                                   inp['mask_res'], nz, obj='pred_noise', materialize=False)
+        ref64 = sampler.reverse_step(W64, t, v_t.double(), p_t.double() / 10.0, s_t, inp['res_feat'].double(), inp['pair_feat'].double(),
+                                     inp['mask_generate'], inp['mask_res'], to64(nz), obj='pred_noise', materialize=False)
+        got = model.reverse_step(t, v_t.to(DEV), p_t.to(DEV), s_t.to(DEV), ci['res_feat'], ci['pair_feat'], ci['mask_generate'],
+                                 ci['mask_res'], noise={k: v.to(DEV) for k, v in nz.items()})
+        v_o, p_o, s_o = [x.cpu() for x in got]
+        live = inp['mask_res']                                # padded residues carry no defined features in either implementation
+        torch.testing.assert_close(p_o[live], (ref['p_next'] * 10.0)[live], rtol=1e-4, atol=1e-4)
+        R64 = G.so3_exp(ref64['v_next'])
+        e_cuda = (G.so3_exp(v_o.double()) - R64).abs().amax(dim=(-1, -2))
+        e_o32 = (G.so3_exp(ref['v_next'].double()) - R64).abs().amax(dim=(-1, -2))
+        gap = (np.pi - ref64['v_next'].norm(dim=-1)).clamp_min(1e-9)
+        ok = live & (gap > 0.05) & (e_o32 < 1e-3)
+        assert not (ok & (e_cuda > 4 * e_o32 + 2e-5 + 3e-6 / gap ** 2)).any()
+        assert torch.equal(s_o[live], ref['s_next'][live])
+        keep = ~inp['mask_generate']
+        assert torch.equal(v_o[keep], v_t[keep]) and torch.equal(p_o[keep], p_t[keep])
+        v_t, p_t, s_t = ref['v_next'], ref['p_next'] * 10.0, ref['s_next']
