@@ -663,20 +663,22 @@ static int run_eps_net(abopt_model* m, int N, int L, const float* v_t, const flo
     }
     return false;
   }();
-  const Focus* fc = nullptr;
-  if (focus && !focus_off && !m->cfg.has_prmsd && L <= 256 && w.NB >= N && m->cfg.num_layers >= 1) {
+  const Focus* fc = nullptr;      // last block + heads on the generated rows (models without the pRMSD head)
+  const Focus* hf = nullptr;      // crd / rot / seq heads on the generated rows (every model); the pRMSD head needs all rows
+  if (focus && !focus_off && m->cfg.num_layers >= 1) {
     if (!m->focus_built)
       launch_focus_build(N, L, mask_gen, w.focus.cidx, w.focus.rows, w.focus.windows, w.focus.count, w.focus.scratch, st);
     if (m->bias_hoisted) m->focus_built = true;           // the sampling loop: mask_generate is a loop invariant
-    fc = &w.focus;
+    hf = &w.focus;
+    if (!m->cfg.has_prmsd && L <= 256 && w.NB >= N) fc = &w.focus;
   }
   launch_mixer(M, res_feat, s_t, v_t, m->eps, w.xa, w.Rbuf, p_ang, w.pnorm, m->diff.pos_mean, m->diff.pos_scale, w.xa_lo, st);
   const float* tpos = p_ang ? w.pnorm : p_t;
   float* enc = nullptr;
   int rc = run_encoder(m, N, L, w.Rbuf, tpos, w.xa, w.xa_lo, pair_feat, mask_res, &enc, st, fc); if (rc) return rc;
   launch_heads(M, L, enc, beta, beta_stride, w.Rbuf, v_t, mask_gen, m->eps, v_next, R_next, eps_pos, c_den, w.prmsd_rows,
-               m->cfg.has_prmsd ? (prmsd_logits ? prmsd_logits : w.prmsd_logits) : nullptr, st, fc ? fc->rows : nullptr,
-               fc ? fc->count : nullptr);
+               m->cfg.has_prmsd ? (prmsd_logits ? prmsd_logits : w.prmsd_logits) : nullptr, st, hf ? hf->rows : nullptr,
+               hf ? hf->count : nullptr, /*x_compact=*/fc != nullptr);
   CHECK_LAUNCH();
   return ABOPT_OK;
 }

@@ -183,10 +183,11 @@ __global__ void __launch_bounds__(RT_THREADS, 1)
 heads_kernel(int M, int L, const float* __restrict__ x, const float* __restrict__ beta, int beta_stride,
              const float* __restrict__ Rbuf, const float* __restrict__ v_t, const uint8_t* __restrict__ mask_gen,
              EpsW w, float* __restrict__ v_next, float* __restrict__ R_next, float* __restrict__ eps_pos,
-             float* __restrict__ c_den, float* __restrict__ prmsd_rows, const int* __restrict__ rows, const int* __restrict__ count) {
+             float* __restrict__ c_den, float* __restrict__ prmsd_rows, const int* __restrict__ rows, const int* __restrict__ count,
+             int head_lo, int x_compact) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // focus mode: x holds only the `count[0]` needed rows (compact); rows[k] is the residue row of compact row k.  Every
-  // other tensor is indexed by the residue row.
+  // focus mode: only the `count[0]` rows listed in rows[] are evaluated.  x is either compact (x_compact: row k of x is
+  // residue rows[k], the output of a focused last block) or the full tensor; every other tensor is indexed by residue row.
   if (count) { const int g = count[0]; M = g < M ? g : M; }
   if ((int)blockIdx.x * RT_ROWS >= M) return;
   RowTileSmem& s = *reinterpret_cast<RowTileSmem*>(smem_raw);
@@ -204,8 +205,9 @@ heads_kernel(int M, int L, const float* __restrict__ x, const float* __restrict_
     float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
     float b = 0.f;
     if (row < M) {
-      xv = *reinterpret_cast<const float4*>(x + (size_t)row * F + lane * 4);
-      b = beta[(size_t)((rows ? rows[row] : row) / L) * beta_stride];
+      const int rr = rows ? rows[row] : row;
+      xv = *reinterpret_cast<const float4*>(x + (size_t)(x_compact ? row : rr) * F + lane * 4);
+      b = beta[(size_t)(rr / L) * beta_stride];
     }
     *reinterpret_cast<float4*>(xin + (warp * 8 + r) * RT_ACT_LD + lane * 4) = xv;
     ext[r][0] = b; ext[r][1] = sinf(b); ext[r][2] = cosf(b);
@@ -215,7 +217,7 @@ heads_kernel(int M, int L, const float* __restrict__ x, const float* __restrict_
   // blockIdx.y selects the head (0 eps_crd, 1 eps_rot, 2 eps_seq, 3 pRMSD): the four heads are independent down to their
   // per-residue epilogues, so they run as separate CTAs (4x the parallelism of one CTA walking all heads; in focus mode
   // only a few row tiles exist)
-  const int head = blockIdx.y;
+  const int head = head_lo + blockIdx.y;
   float acc[8][4];
   if (head == 0) { run_head(acc, s, xin, hid, w.crd, ext); stage_out(acc, outs, 0, 3); }
   else if (head == 1) { run_head(acc, s, xin, hid, w.rot, ext); stage_out(acc, outs, 3, 3); }
@@ -393,10 +395,22 @@ void launch_tail(int M, const float* feat, const float* pre, const float* x, con
 }
 void launch_heads(int M, int L, const float* x, const float* beta, int beta_stride, const float* Rbuf, const float* v_t,
                   const uint8_t* mask_gen, const EpsW& w, float* v_next, float* R_next, float* eps_pos, float* c_den,
-                  float* prmsd_rows, float* prmsd_logits, cudaStream_t st, const int* rows, const int* count) {
+                  float* prmsd_rows, float* prmsd_logits, cudaStream_t st, const int* rows, const int* count, bool x_compact) {
   ProfScope prof__(KK_HEADS, st);
-  heads_kernel<<<dim3((M + RT_ROWS - 1) / RT_ROWS, w.has_prmsd ? 4 : 3), RT_THREADS, heads_smem(), st>>>(M, L, x, beta, beta_stride, Rbuf, v_t, mask_gen, w,
-                                                                           v_next, R_next, eps_pos, c_den, prmsd_rows, rows, count);
+  const dim3 tiles((M + RT_ROWS - 1) / RT_ROWS);
+  if (rows && w.has_prmsd) {
+    // the crd / rot / seq heads on the listed (generated) rows only, the pRMSD head on every row (its logits are averaged
+    // over all L rows, dpm_full.py:110)
+    heads_kernel<<<dim3(tiles.x, 3), RT_THREADS, heads_smem(), st>>>(M, L, x, beta, beta_stride, Rbuf, v_t, mask_gen, w, v_next, R_next,
+                                                                    eps_pos, c_den, prmsd_rows, rows, count, 0, x_compact ? 1 : 0);
+    count_launch();
+    heads_kernel<<<dim3(tiles.x, 1), RT_THREADS, heads_smem(), st>>>(M, L, x, beta, beta_stride, Rbuf, v_t, mask_gen, w, v_next, R_next,
+                                                                    eps_pos, c_den, prmsd_rows, nullptr, nullptr, 3, 0);
+  } else {
+    heads_kernel<<<dim3(tiles.x, w.has_prmsd ? 4 : 3), RT_THREADS, heads_smem(), st>>>(M, L, x, beta, beta_stride, Rbuf, v_t, mask_gen, w, v_next,
+                                                                                    R_next, eps_pos, c_den, prmsd_rows, rows, count, 0,
+                                                                                    x_compact ? 1 : 0);
+  }
   if (w.has_prmsd && prmsd_logits != nullptr) {
     prmsd_mean_kernel<<<M / L, 64, 0, st>>>(L, w.prmsd_bins, prmsd_rows, prmsd_logits);
     count_launch();

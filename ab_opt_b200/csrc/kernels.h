@@ -95,7 +95,8 @@ void launch_tail(int M, const float* feat, const float* pre, const float* x, con
                  float* x_lo_out, cudaStream_t st);
 void launch_heads(int M, int L, const float* x, const float* beta, int beta_stride, const float* Rbuf, const float* v_t,
                   const uint8_t* mask_gen, const EpsW& w, float* v_next, float* R_next, float* eps_pos, float* c_den,
-                  float* prmsd_rows, float* prmsd_logits, cudaStream_t st, const int* rows = nullptr, const int* count = nullptr);
+                  float* prmsd_rows, float* prmsd_logits, cudaStream_t st, const int* rows = nullptr, const int* count = nullptr,
+                  bool x_compact = false);
 // focus mode (k_linear.cu): restriction of the last GABlock to the generated rows inside the sampling loop
 struct Focus {
   int* cidx;          // [M]  compact row of residue row r, -1 = not needed
