@@ -409,10 +409,10 @@ def test_training_forward_vs_oracle(flavour, ds, dq):
 
 # ------------------------------------------------------------------------------------------ focus mode (last block on generated rows)
 @pytest.mark.parametrize('N,L,segs,ragged', [(3, 72, ((10, 22), (40, 44)), True), (2, 250, ((3, 9), (120, 136), (236, 250)), True),
-                                              (2, 256, ((120, 136),), False)])
+                                              (2, 256, ((120, 136),), False), (1, 300, ((5, 12), (280, 300)), False)])
 def test_reverse_step_abdesign_focus(N, L, segs, ragged):
     """AbDesign flavour (no pRMSD head): inside the sampling loop the last GABlock and the heads run on the generated
-    rows only (query windows + compact rows).  One teacher-forced reverse step must match the oracle on the full state:
+    rows only (query windows + compact rows; for L > 256 only the heads are restricted).  One teacher-forced reverse step must match the oracle on the full state:
     positions 1e-4 relative, rotations as matrices, sequence indices bit-exact, context untouched."""
     W = weights.make_state_dict(seed=19, num_layers=2, flavour='abdesign')
     inp = weights.synthetic_inputs(41, N, L, gen_slices=segs, ragged=ragged)
