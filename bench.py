@@ -38,6 +38,9 @@ CONFIGS = {
                gen=((20, 30), (50, 60), (95, 105), (160, 170), (190, 200), (230, 240)), flavour='abdesign',
                sample_structure=True, sample_sequence=True, obj='pred_noise'),
 }
+# c5: SURVEY.md 8d config 5, FORWARD ONLY (FullDPM.forward losses on the CUDA path; the backward pass is not implemented)
+TRAIN_CFG = dict(name='C5 AbDesign train.py FullDPM.forward (losses only, no backward)', B=128, L=256, gen=((120, 136),),
+                 flavour='abdesign', obj='pred_noise')
 NUM_LAYERS, T_STEPS = 6, 100
 
 
@@ -327,15 +330,54 @@ def run_ours(args, cfg, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_train_forward(args):
+    """--config c5: ms per FullDPM.forward call (add_noise, one EpsilonNet evaluation, loss reductions; no autograd) and
+    residues/s = B * L / time, as SURVEY.md 8d defines config 5.  One GPU, not a bench line of the headline metric."""
+    cfg = TRAIN_CFG
+    dev = torch.device('cuda', 0)
+    model = build_model(cfg, dev)
+    inp = synthetic_batch(cfg, 1000, dev)
+    B, L = cfg['B'], cfg['L']
+    t = torch.randint(1, T_STEPS, (B,), device=dev)
+    a = (inp['v'], inp['p'], inp['s'], inp['res_feat'], inp['pair_feat'], inp['mask_generate'], inp['mask_res'], True, True)
+    for _ in range(2 + args.warmup):
+        loss = model(*a, t=t)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(max(args.steps, 10)):
+        loss = model(*a, t=t)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / max(args.steps, 10)
+    assert all(torch.isfinite(v) for v in loss.values())
+    peak, peak_src = measured_peak_gbs()
+    alg = B * NUM_LAYERS * algorithmic_bytes_per_complex_layer(L)
+    print(json.dumps({'metric': 'training forward residues/sec (FullDPM.forward, losses only)', 'value': B * L / (ms / 1e3),
+                      'unit': 'residues/s', 'n_gpus': 1, 'steps': max(args.steps, 10), 'warmup': args.warmup, 'ms_per_step': ms,
+                      'higher_is_better': True, 'dtype': 'f32', 'data': 'synthetic',
+                      'config': {'workload': f"{cfg['name']}: B={B}, L={L}, n_gen=16, {NUM_LAYERS} IPA layers", 'backward': 'not implemented'},
+                      'losses': {k: float(v) for k, v in loss.items()}, 'clocks': clocks.stop(),
+                      'roofline': {'bound': 'hbm', 'achieved': alg / (ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                                   'frac': alg / (ms * 1e-3) / 1e9 / peak, 'peak_source': peak_src,
+                                   'note': 'whole forward against SURVEY 8d algorithmic bytes (z once per layer + node state)'}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
+    ap.add_argument('--config', default='c2', choices=sorted(CONFIGS) + ['c5'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
+    if args.config == 'c5':
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py --config c5 needs a CUDA device (there is no CPU fallback)')
+        run_train_forward(args)
+        return
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
