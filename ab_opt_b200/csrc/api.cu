@@ -89,7 +89,7 @@ struct abopt_model {
   std::vector<PairBiasPacked> pbp;
   // TMA descriptor of the pair tensor, cached per (pointer, shape): pair_feat is constant over a sampling run
   CUtensorMap zmap; const float* zmap_ptr = nullptr; int zmap_N = 0, zmap_L = 0, zmap_box_rows = 0;
-  // pair bias z . W_b of every layer, [slot][N][H][L][Lp].  Inside abopt_sample_* it is computed once per run for all
+  // pair bias z . W_b of every layer, [slot][N][H][L queries][Lp keys].  Inside abopt_sample_* it is computed once per run for all
   // layers (z and the weights are loop invariants of the T reverse steps); elsewhere slot 0 is recomputed per block call.
   float* bias_buf = nullptr; size_t bias_slots = 0, bias_slot_floats = 0; bool bias_hoisted = false;
   bool focus_built = false;     // inside abopt_sample_*: the focus lists of mask_generate were built once for the whole run
@@ -539,7 +539,7 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
   const BlockW& bw = m->blocks[layer];
   int rc = ensure_pair_inputs(m, N, L, z, m->bias_hoisted ? (size_t)m->cfg.num_layers : 1); if (rc) return rc;
   const float* bias = m->bias_buf + (m->bias_hoisted ? (size_t)layer * m->bias_slot_floats : 0);
-  if (!m->bias_hoisted && !launch_pair_bias(N, 0, L, w.Lp, m->zmap, m->zmap_box_rows, m->pbp[layer], m->bias_buf, st))
+  if (!m->bias_hoisted && !launch_pair_bias(N, 0, N, L, w.Lp, z, m->pbp[layer], m->bias_buf, st))
     return fail(ABOPT_ERR_ARG, "pair_bias_kernel: L too large for shared memory");
   // the six input projections: tcgen05 3xTF32 GEMM (x raw = "hi" plane, x_lo = "lo" plane)
   if (x_lo == nullptr) { launch_lo(x, w.xin_lo, (size_t)M * F, st); x_lo = w.xin_lo; }
@@ -872,7 +872,7 @@ extern "C" int abopt_sample_device(abopt_model* m, int N, int L, const float* v,
   // loop-invariant hoist: the pair bias z . W_b of all layers, once per run instead of once per step
   rc = ensure_pair_inputs(m, N, L, pair_feat, (size_t)m->cfg.num_layers); if (rc) return rc;
   for (int l = 0; l < m->cfg.num_layers; ++l)
-    if (!launch_pair_bias(N, 0, L, m->ws.Lp, m->zmap, m->zmap_box_rows, m->pbp[l], m->bias_buf + (size_t)l * m->bias_slot_floats, st))
+    if (!launch_pair_bias(N, 0, N, L, m->ws.Lp, pair_feat, m->pbp[l], m->bias_buf + (size_t)l * m->bias_slot_floats, st))
       return fail(ABOPT_ERR_ARG, "pair_bias_kernel: L too large for shared memory");
   m->bias_hoisted = true;
   m->focus_built = false;

@@ -39,7 +39,7 @@ constexpr int AL_SMEM = AL_BAR_OFF + 128 + 1024;
 struct AttnLogitsArgs {
   int L, Lp, b0;
   const float* rq; const float* rk;      // [N][H][L]
-  const float* bias;                     // [N][H][L keys][Lp] (query index contiguous)
+  const float* bias;                     // [N][H][L queries][Lp] (key index contiguous, like alpha)
   const uint8_t* mask;                   // [N][L]
   float* alpha;                          // [chunk][H][L][Lp]
 };
@@ -124,7 +124,7 @@ attn_logits_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
           // once the first operand loads are queued: pull this tile of the (HBM-resident) pair bias into L2 while the
           // MMAs run -- boxes of [<= 256 keys][128 queries] of the [N*H*L keys][Lp queries] view
           for (int j0 = 0; j0 < L; j0 += 256)
-            asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(&tmBias), "r"(i0), "r"(row_base + j0) : "memory");
+            asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(&tmBias), "r"(j0), "r"(row_base + i0) : "memory");
         }
       }
     }
@@ -175,12 +175,12 @@ attn_logits_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
       pen[j] = (j < L) ? (a.mask[(size_t)b * L + j] != 0 ? 0.f : 1e5f) : INFINITY;
     }
     const float rqi = valid ? __ldg(a.rq + (size_t)row_base + i) : 0.f;
-    const float* bias_col = a.bias + (size_t)row_base * Lp + (valid ? i : 0);     // + j * Lp: bias is stored [j][i]
+    const float* bias_col = a.bias + ((size_t)row_base + (valid ? i : 0)) * Lp;      // + j: bias is stored [i][j]
     float* alpha_row = a.alpha + ((size_t)(bl * H + h) * L + (valid ? i : 0)) * Lp;
     (void)alpha_row; (void)cend;
     auto load_bias = [&](int c0, float (&dst)[32]) {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) dst[e] = (c0 + e < L) ? __ldg(bias_col + (size_t)(c0 + e) * Lp) : 0.f;
+      for (int e = 0; e < 32; ++e) dst[e] = (c0 + e < L) ? __ldg(bias_col + (c0 + e)) : 0.f;
     };
     epi_sync();                                           // tables visible to all epilogue warps
     if (te == 0 && half == 0) stamp(4);
@@ -204,7 +204,7 @@ attn_logits_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
           for (int e0 = 0; e0 < 32; e0 += 8) {
             float bv[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) bv[e] = (c0 + e0 + e < L) ? __ldg(bias_col + (size_t)(c0 + e0 + e) * Lp) : 0.f;
+            for (int e = 0; e < 8; ++e) bv[e] = (c0 + e0 + e < L) ? __ldg(bias_col + (c0 + e0 + e)) : 0.f;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const int j = c0 + e0 + e;
@@ -324,20 +324,20 @@ attn_logits_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
 //   warp 0      TMA producer, one thread running a small event loop over two independent streams:
 //                 operands -- the query operand (single buffer, released by the MMA warp) and key groups of 64 residues
 //                             through a 3-stage ring;
-//                 bias     -- the tile's pair bias in chunks of [32 keys][128 queries] (16 KB) through a 3-stage ring,
+//                 bias     -- the tile's pair bias in chunks of [128 queries][32 keys] (16 KB, swizzled) through a 3-stage ring,
 //                             running ahead of the epilogue (the bias is the HBM stream of this kernel)
 //   warp 1      MMA issuer -- accumulates tile n into TMEM buffer n & 1 (2 x 256 columns) while the epilogue warps are still
 //               busy with tile n - 1; per key group 16 correction products first, then the 8 hi*hi ones (truncation note above)
 //   warps 18-19 splitters  -- build the tf32 "lo" plane (x - trunc_tf32(x)) of every landed operand box in shared memory,
 //               so QA_lo / KB_lo never exist in global memory (saves their write in the projection kernel and their read here)
 //   warps 2-17  epilogue   -- 4 threads per query row; thread (row, kq) owns keys 32 m + 8 kq + (0..7) of every chunk m:
-//               TMEM -> registers (buffer released at once), per chunk bias from shared memory (conflict-free: lanes are
-//               consecutive queries) -> logits; max / exp / sum exchanged through shared memory; alpha stored with 256-bit
+//               TMEM -> registers (buffer released at once), per chunk bias from shared memory (two conflict-free LDS.128 of
+//               the swizzled box) -> logits; max / exp / sum exchanged through shared memory; alpha stored with 256-bit
 //               global stores (one full 32-byte sector each)
 constexpr int AP_THREADS = 640, AP_EPI = 512, AP_SPLIT = 64;      // (18 warps are allocated registers as 20 anyway)
 constexpr int AP_BST = 2, AP_BGRP_BYTES = 4 * 64 * 32 * 4;            // key-group stage: 64 keys x (hi k0 | hi k1 | lo k0 | lo k1) = 32 KB
 constexpr int AP_KBOX = 64 * 32 * 4;                                  // one key box: 64 rows x 32 floats
-constexpr int AP_NBIAS = 3, AP_BIAS_BYTES = 32 * 128 * 4;             // bias chunk: 32 keys x 128 queries
+constexpr int AP_NBIAS = 3, AP_BIAS_BYTES = 128 * 32 * 4;             // bias chunk: 128 queries x 32 keys
 constexpr int AP_B_OFF = 2 * AL_OPER_BYTES;
 constexpr int AP_BIAS_OFF = AP_B_OFF + AP_BST * AP_BGRP_BYTES;
 constexpr int AP_STG_OFF = AP_BIAS_OFF + AP_NBIAS * AP_BIAS_BYTES;    // alpha staging: 2 boxes of [128 queries][32 keys], 128-byte swizzle
@@ -363,8 +363,6 @@ struct AttnPersistArgs {
   const int2* windows;            // optional (focus mode): query windows (complex, first query row), 128 rows each; else the regular grid
   const int* wcount;              // device: wcount[1] = number of windows
   int nb_complex;                 // complexes covered by this launch
-  int bias_pitch;                 // floats between consecutive keys of a bias chunk in shared memory (= box width)
-  int bias_tx;                    // bytes one bias box delivers
 };
 
 // tile index -> (complex in the launch, head, first query row): regular 128-row grid, or the focus windows (heads fastest)
@@ -459,8 +457,8 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
           if (mbar_try_wait(&bias_empty[s], ((bc / AP_NBIAS) & 1) ^ 1)) {
             const TileRef tr = tile_ref(btile, nit, pa.windows);
             const int row_base = ((a.b0 + tr.bl) * H + tr.h) * L;
-            mbar_expect_tx(&bias_full[s], (uint32_t)pa.bias_tx);
-            tma_load_2d(smem + AP_BIAS_OFF + s * AP_BIAS_BYTES, &tmBias, tr.i0, row_base + bm * 32, &bias_full[s]);
+            mbar_expect_tx(&bias_full[s], AP_BIAS_BYTES);
+            tma_load_2d(smem + AP_BIAS_OFF + s * AP_BIAS_BYTES, &tmBias, bm * 32, row_base + tr.i0, &bias_full[s]);
             ++bc;
             if (++bm == NCH) { bm = 0; btile += gridDim.x; }
           }
@@ -534,7 +532,6 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
     const int et = (warp - 2) * 32 + lane;                // 0..511
     const float scale = 0.57735026918962576f;             // sqrt(1/3), ga.py:166
     const float l2e = 1.4426950408889634f;
-    const int bpitch = pa.bias_pitch;
     int n = 0, bc = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
       const TileRef tr = tile_ref(tile, nit, pa.windows);
@@ -573,10 +570,11 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
       for (int m = 0; m < NCH; ++m, ++bc) {
         const int s = bc % AP_NBIAS;
         mbar_wait(&bias_full[s], (bc / AP_NBIAS) & 1);
-        const float* bs = reinterpret_cast<const float*>(smem + AP_BIAS_OFF + s * AP_BIAS_BYTES) + (kq * 8) * bpitch + te;
-        float bv[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) bv[e] = bs[e * bpitch];
+        // chunk = box of [128 queries][32 keys], 128-byte swizzle: row te, 16-byte chunks 2 kq and 2 kq + 1
+        const unsigned char* bs = smem + AP_BIAS_OFF + s * AP_BIAS_BYTES + te * 128;
+        const float4 b0v = *reinterpret_cast<const float4*>(bs + (((2 * kq) ^ (te & 7)) << 4));
+        const float4 b1v = *reinterpret_cast<const float4*>(bs + (((2 * kq + 1) ^ (te & 7)) << 4));
+        const float bv[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
         __syncwarp();
         if (lane == 0) mbar_arrive(&bias_empty[s]);       // values are in registers: the producer may refill the slot
         const int j0 = m * 32 + kq * 8;
@@ -650,8 +648,8 @@ bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOpera
   if (!make_tmap(&qh, op.QA, rows, 64, 64, 128) || !make_tmap(&ql, op.QA_lo, rows, 64, 64, 128) ||
       !make_tmap(&kh, op.KB, rows, 64, 64, 128) || !make_tmap(&kl, op.KB_lo, rows, 64, 64, 128))
     return false;
-  // pair bias as a plain (unswizzled) 2-D tensor for L2 prefetches: [N*H*L keys][Lp queries], box [<=256][<=128]
-  if (!make_tmap_plain(&bm, bias_layer, rows, (uint64_t)Lp, (uint64_t)Lp, rows < 256 ? (uint32_t)rows : 256u, Lp < 128 ? (uint32_t)Lp : 128u))
+  // pair bias as a plain (unswizzled) 2-D tensor for L2 prefetches: [N*H*L queries][Lp keys], box [<=128][<=256]
+  if (!make_tmap_plain(&bm, bias_layer, rows, (uint64_t)Lp, (uint64_t)Lp, rows < 128 ? (uint32_t)rows : 128u, Lp < 256 ? (uint32_t)Lp : 256u))
     return false;
   // alpha / alpha_lo as 3-D tensors [chunk * H][L queries][Lp keys] for the TMA stores (rows >= L are clipped)
   if (!make_tmap_3d(&al, alpha, Lp, L, (uint64_t)nb * H, 32, 128)) return false;
@@ -660,16 +658,15 @@ bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOpera
   dim3 grid((L + AL_BM - 1) / AL_BM, H, nb);
   const int ncols = ((L + AL_BN - 1) / AL_BN) * AL_BN;
   if (ncols <= 256 && !g_attn_legacy) {
-    // key operands in groups of 64 residues; the pair bias as [32 keys][<= 128 queries] boxes
+    // key operands in groups of 64 residues; the pair bias [(b,h,i) rows][Lp keys] as swizzled [128 queries][32 keys] boxes
     CUtensorMap kh64, kl64, bm32;
-    const uint32_t brows = rows < 32 ? (uint32_t)rows : 32u, bcols = Lp < 128 ? (uint32_t)Lp : 128u;
     if (!make_tmap(&kh64, op.KB, rows, 64, 64, 64) || !make_tmap(&kl64, op.KB_lo, rows, 64, 64, 64) ||
-        !make_tmap_plain(&bm32, bias_layer, rows, (uint64_t)Lp, (uint64_t)Lp, brows, bcols))
+        !make_tmap(&bm32, bias_layer, rows, (uint64_t)Lp, (uint64_t)Lp, 128))
       return false;
     const int ntiles = nb * H * ((L + AL_BM - 1) / AL_BM);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    const AttnPersistArgs pa{windows, wcount, nb, (int)bcols, (int)(brows * bcols * 4)};
+    const AttnPersistArgs pa{windows, wcount, nb};
     if (ncols <= 128) attn_logits_persist_kernel<4><<<ntiles < sms ? ntiles : sms, AP_THREADS, AP_SMEM, st>>>(qh, ql, kh64, kl64, bm32, al, a, pa);
     else attn_logits_persist_kernel<8><<<ntiles < sms ? ntiles : sms, AP_THREADS, AP_SMEM, st>>>(qh, ql, kh64, kl64, bm32, al, a, pa);
   } else if (ncols <= 256) attn_logits_tc_kernel<true><<<grid, AL_THREADS, AL_SMEM, st>>>(qh, ql, kh, kl, bm, al, a);

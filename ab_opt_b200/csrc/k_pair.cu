@@ -63,94 +63,102 @@ struct PairStreamArgs {
   float* bias;                    // pair_bias_kernel output, transposed: [complex][h][j][Lp] (query index i contiguous)
 };
 
-// ---- TMA producer shared by both kernels: thread 0 walks the CTA's rows (blockIdx.x, + gridDim.x, ...) and loads
-//      whole row-blocks z[b, i, :, :] into the ring; `skip_masked` drops rows whose query residue is masked.
-struct TileProducer {
-  int row, n;
-  uint64_t pol;
-  __device__ __forceinline__ void issue(const CUtensorMap* zmap, const PairStreamArgs& a, unsigned char* stages, uint64_t* full,
-                                        int stride, bool skip_masked) {
-    while (row < a.nrows) {
-      const int bl = row / a.L, i = row - bl * a.L, b = a.b0 + bl;
-      row += stride;
-      if (skip_masked && a.mask[(size_t)b * a.L + i] == 0) continue;
-      const int s = n % a.nstage;
-      ++n;
-      unsigned char* st = stages + (size_t)s * a.stage_bytes;
-      mbar_expect_tx(&full[s], a.tile_tx_bytes);
-      const int grow = (b * a.L + i) * a.L;              // first row of z[b, i] in the (N*L*L, 64) view
-      for (int r = 0; r < a.nbox_rows; ++r) {
-        tma_load_2d_hint(st + (r * 2 + 0) * PS_HALF_BYTES, zmap, 0, grow + r * PS_BOX_ROWS, &full[s], pol);
-        tma_load_2d_hint(st + (r * 2 + 1) * PS_HALF_BYTES, zmap, 32, grow + r * PS_BOX_ROWS, &full[s], pol);
-      }
-      return;
-    }
-  }
+// ------------------------------------------------------------------------------------------ pair bias
+// pair_bias_kernel: bias[b,h,i,j] = z[b,i,j,:] . W_b[h,:]   (ga.py:88-90), stored like alpha: [b][h][i][Lp], key index
+// contiguous.  z and W_b do not change over the T reverse steps, so FullDPM.sample runs this ONCE per layer per sampling run
+// (api.cu); a training step runs it once per layer.
+// Same barrier-free structure as pair_stream_kernel: 12 independent warps per SM, each owns whole query rows (b, i) and
+// streams the row block z[b,i,:,:] through a private 2-stage ring of 32-key chunks (two TMA boxes of [32 keys][32 channels],
+// 128-byte swizzle, L2 evict-first).  lane = key residue: 16 conflict-free LDS.128 of its z row feed 384 FFMA2
+// (scalar z  x  (W[c][h], W[c][h+1]) head pairs that live in the constant bank -> uniform registers); the 12 results per lane
+// leave as 12 coalesced 128-byte stores.  Columns L <= j < Lp are written as zeros (the logits kernel reads whole chunks).
+constexpr int PB_WARPS = 12, PB_THREADS = PB_WARPS * 32, PB_STAGES = 2, PB_CJ = 32;
+constexpr int PB_BOX_BYTES = PB_CJ * 128;               // one TMA box: 32 keys x 32 channels
+constexpr int PB_STAGE_BYTES = 2 * PB_BOX_BYTES;        // 8 KB: channels 0..31 | 32..63
+constexpr int PB_WARP_BYTES = PB_STAGES * PB_STAGE_BYTES;
+constexpr int PB_SMEM = PB_WARPS * PB_WARP_BYTES + PB_WARPS * PB_STAGES * 8 + 1024;
+
+struct PairBiasArgs {
+  int L, Lp, b0, nrows, nchunk;   // nrows = complexes covered by this launch * L; nchunk = ceil(Lp / 32)
+  float* bias;                    // [complex][h][i][Lp]
 };
 
-// ------------------------------------------------------------------------------------------ pair bias
-// bias(b, h, i, j) = z[b,i,j,:] . W_b[h,:]   (ga.py:88-90).  z and W_b do not change over the T reverse steps, so
-// FullDPM.sample runs this ONCE per layer per sampling run (api.cu) instead of once per layer per step.
-// thread = (key residue j, 6 of the 12 heads); the head half is warp-uniform so the weight pairs are uniform-register
-// operands of FFMA2 (fma.rn.f32x2: scalar z  x  (W[c][h], W[c][h+1])).
-template <int JPT>
-__global__ void __launch_bounds__(PS_THREADS, 1)
-pair_bias_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant__ PairBiasPacked pb, const PairStreamArgs a) {
+__global__ void __launch_bounds__(PB_THREADS, 1)
+pair_bias_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant__ PairBiasPacked pb, const PairBiasArgs a) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* stages = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);    // keeps the shared address space
-  uint64_t* full = reinterpret_cast<uint64_t*>(stages + (size_t)a.nstage * a.stage_bytes);
+  unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = a.L, Lp = a.Lp;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  TileProducer prod{(int)blockIdx.x, 0, 0};
-  if (tid == 0) {
-    for (int s = 0; s < a.nstage; ++s) mbar_init(&full[s], 1);
+  unsigned char* wst = base + warp * PB_WARP_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + PB_WARPS * PB_WARP_BYTES) + warp * PB_STAGES;
+  if (lane == 0) {
+    for (int s = 0; s < PB_STAGES; ++s) mbar_init(&full[s], 1);
     mbar_fence_init();
     tma_prefetch_desc(&zmap);
-    prod.pol = policy_evict_first();
-    for (int s = 0; s < a.nstage; ++s) prod.issue(&zmap, a, stages, full, gridDim.x, false);
   }
-  __syncthreads();
-  const int ja = (warp >> 1) * 32 + lane, ch = warp & 1;
-  int n = 0;
-  for (int row = blockIdx.x; row < a.nrows; row += gridDim.x, ++n) {
-    const int bl = row / L, i = row - bl * L, b = a.b0 + bl;
-    const int s = n % a.nstage;
-    const unsigned char* zs = stages + (size_t)s * a.stage_bytes;
-    mbar_wait(&full[s], (n / a.nstage) & 1);
+  __syncwarp();
+  const int stride = gridDim.x * PB_WARPS;
+  const int first = warp * gridDim.x + blockIdx.x;
+  const int dbl = stride / L, di = stride - dbl * L;
+  auto advance = [&](int& bl, int& i) { bl += dbl; i += di; if (i >= L) { i -= L; ++bl; } };
+
+  // producer cursor (lane 0 issues): chunk by chunk, PB_STAGES chunks ahead of the consumer
+  int prow = first, pbl = first / L, pi = first - pbl * L, pjc = 0, ps = 0;
+  const uint64_t pol = policy_evict_first();
+  auto issue = [&]() {
+    if (prow >= a.nrows) return;
+    if (lane == 0) {
+      unsigned char* st = wst + ps * PB_STAGE_BYTES;
+      const int grow = ((a.b0 + pbl) * L + pi) * L + pjc * PB_CJ;      // first row of the chunk in the (N*L*L, 64) view
+      mbar_expect_tx(&full[ps], PB_STAGE_BYTES);                        // rows past the end of the tensor arrive as zeros
+      tma_load_2d_hint(st, &zmap, 0, grow, &full[ps], pol);
+      tma_load_2d_hint(st + PB_BOX_BYTES, &zmap, 32, grow, &full[ps], pol);
+    }
+    if (++ps == PB_STAGES) ps = 0;
+    if (++pjc == a.nchunk) { pjc = 0; prow += stride; advance(pbl, pi); }
+  };
+  for (int s = 0; s < PB_STAGES; ++s) issue();
+
+  int cs = 0;
+  uint32_t cph = 0;
+  int bl = first / L, i = first - bl * L;
+  for (int row = first; row < a.nrows; row += stride, advance(bl, i)) {
+    const int b = a.b0 + bl;
+    float* out = a.bias + ((size_t)(b * H) * L + i) * Lp;               // + h * L * Lp + j
+    for (int jc = 0; jc < a.nchunk; ++jc) {
+      mbar_wait(&full[cs], cph);
+      const unsigned char* zr = wst + cs * PB_STAGE_BYTES + lane * 128;  // this lane's key row; 16-byte chunk q sits at q ^ (lane & 7)
+      float2 acc[2][3];
 #pragma unroll
-    for (int u = 0; u < JPT; ++u) {
-      const int j = ja + u * PS_ROWS;
-      if (j < L) {
-        float2 acc[2][3];
+      for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { acc[0][k] = make_float2(0.f, 0.f); acc[1][k] = make_float2(0.f, 0.f); }
-        auto body = [&](auto chc) {
-          constexpr int CH = decltype(chc)::value;
+        for (int k = 0; k < 3; ++k) acc[hf][k] = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const float4 v = *reinterpret_cast<const float4*>(zs + zoff(j, q));
-            const float zz[4] = {v.x, v.y, v.z, v.w};
+      for (int q = 0; q < 16; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(zr + (q >> 3) * PB_BOX_BYTES + (((q & 7) ^ (lane & 7)) << 4));
+        const float zz[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
+        for (int e = 0; e < 4; ++e)
 #pragma unroll
-              for (int k = 0; k < 3; ++k) acc[e & 1][k] = ffma2(zz[e], pb.w[CH][q * 4 + e][k], acc[e & 1][k]);
+          for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) acc[hf][k] = ffma2(zz[e], pb.w[hf][q * 4 + e][k], acc[hf][k]);
+      }
+      __syncwarp();                                      // every lane's reads of the stage have completed -> refill it
+      issue();
+      if (++cs == PB_STAGES) { cs = 0; cph ^= 1u; }
+      const int j = jc * PB_CJ + lane;
+      if (j < Lp) {
+        const bool in = j < L;                           // padding columns hold zeros
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            out[(size_t)(hf * 6 + 2 * k) * L * Lp + j] = in ? acc[hf][k].x : 0.f;
+            out[(size_t)(hf * 6 + 2 * k + 1) * L * Lp + j] = in ? acc[hf][k].y : 0.f;
           }
-        };
-        if (ch == 0) body(std::integral_constant<int, 0>{}); else body(std::integral_constant<int, 1>{});
-        // stored TRANSPOSED, bias[b][h][j][i] (query index contiguous): attn_logits_tc_kernel's epilogue threads are
-        // query rows, so a warp reads 32 consecutive i of one key j in one coalesced request.  The scattered 4-byte
-        // stores here happen once per sampling run and merge in L2 (neighbouring i are written by neighbouring CTAs).
-        float* dst = a.bias + ((size_t)(b * H + ch * (H / 2)) * L + j) * Lp + i;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          dst[(size_t)(2 * k) * L * Lp] = acc[0][k].x + acc[1][k].x;
-          dst[(size_t)(2 * k + 1) * L * Lp] = acc[0][k].y + acc[1][k].y;
-        }
       }
     }
-    fence_async_smem();                                  // order the generic reads before the async-proxy refill
-    __syncthreads();
-    if (tid == 0) prod.issue(&zmap, a, stages, full, gridDim.x, false);
   }
 }
 
@@ -362,9 +370,7 @@ cudaError_t pair_stream_init() {
   if ((e = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
   const int mx = 227 * 1024;
   if ((e = cudaFuncSetAttribute(pair_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(pair_bias_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(pair_bias_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(pair_bias_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(pair_bias_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PB_SMEM)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -375,32 +381,18 @@ bool make_pair_tmap(CUtensorMap* m, const float* z, size_t total_rows, int* box_
   return make_tmap_2d(m, z, total_rows, C, C, box_rows, 32);
 }
 
-static bool fill_args(PairStreamArgs& a, int nb, int b0, int L, int Lp, int box_rows, size_t fixed, size_t* smem) {
-  a.L = L; a.Lp = Lp; a.b0 = b0; a.nrows = nb * L;
-  a.nbox_rows = (L + PS_BOX_ROWS - 1) / PS_BOX_ROWS;
-  a.stage_bytes = a.nbox_rows * 2 * PS_HALF_BYTES;
-  a.tile_tx_bytes = a.nbox_rows * 2 * box_rows * 128;
-  int nstage = (int)((227 * 1024 - fixed) / a.stage_bytes);
-  if (nstage < 1) return false;
-  if (nstage > 4) nstage = 4;
-  a.nstage = nstage;
-  *smem = (size_t)nstage * a.stage_bytes + fixed;
-  return true;
-}
-
-// bias[b][h][i][Lp] for complexes [b0, b0 + nb)
-bool launch_pair_bias(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, int box_rows, const PairBiasPacked& pb, float* bias,
-                      cudaStream_t st) {
+// bias[b][h][i][Lp] for complexes [b0, b0 + nb); z viewed as a 2-D fp32 matrix [(N*L*L) rows][64]
+bool launch_pair_bias(int nb, int b0, int N, int L, int Lp, const float* z, const PairBiasPacked& pb, float* bias, cudaStream_t st) {
+  CUtensorMap zmap;
+  const uint64_t rows = (uint64_t)N * L * L;
+  if (!make_tmap(&zmap, z, rows, C, C, rows < (uint64_t)PB_CJ ? (uint32_t)rows : (uint32_t)PB_CJ)) return false;
   ProfScope prof__(KK_OTHER, st);
-  PairStreamArgs a{};
-  size_t smem = 0;
-  if (!fill_args(a, nb, b0, L, Lp, box_rows, 8 * 8 + 1024, &smem)) return false;
-  a.bias = bias;
+  PairBiasArgs a{};
+  a.L = L; a.Lp = Lp; a.b0 = b0; a.nrows = nb * L; a.nchunk = (Lp + PB_CJ - 1) / PB_CJ; a.bias = bias;
   int grid = g_sm_count > 0 ? g_sm_count : 148;
-  if (grid > a.nrows) grid = a.nrows;
-  if (L <= PS_ROWS) pair_bias_kernel<1><<<grid, PS_THREADS, smem, st>>>(zmap, pb, a);
-  else if (L <= 2 * PS_ROWS) pair_bias_kernel<2><<<grid, PS_THREADS, smem, st>>>(zmap, pb, a);
-  else pair_bias_kernel<3><<<grid, PS_THREADS, smem, st>>>(zmap, pb, a);
+  const int need = (a.nrows + PB_WARPS - 1) / PB_WARPS;
+  if (grid > need) grid = need;
+  pair_bias_kernel<<<grid, PB_THREADS, PB_SMEM, st>>>(zmap, pb, a);
   return true;
 }
 

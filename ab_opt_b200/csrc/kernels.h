@@ -117,8 +117,7 @@ void launch_alpha_tap(int nb, int b0, int L, int Lp, const float* alpha, float* 
 cudaError_t pair_stream_init();
 bool make_tmap_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
 bool make_pair_tmap(CUtensorMap* m, const float* z, size_t total_rows, int* box_rows_out);
-bool launch_pair_bias(int nb, int b0, int L, int Lp, const CUtensorMap& zmap, int box_rows, const PairBiasPacked& pb, float* bias,
-                      cudaStream_t st);
+bool launch_pair_bias(int nb, int b0, int N, int L, int Lp, const float* z, const PairBiasPacked& pb, float* bias, cudaStream_t st);
 bool launch_pair_stream(int nb, int b0, int L, int Lp, const float* z, const uint8_t* mask,
                         float* alpha, float* feat, float* feat_lo, cudaStream_t st, const int* cidx = nullptr);
 bool make_tmap_3d_plain(CUtensorMap* m, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1, uint32_t box2);
