@@ -87,8 +87,6 @@ struct abopt_model {
   std::vector<BlockW> blocks;
   std::vector<PairBiasParams> pb;
   std::vector<PairBiasPacked> pbp;
-  // TMA descriptor of the pair tensor, cached per (pointer, shape): pair_feat is constant over a sampling run
-  CUtensorMap zmap; const float* zmap_ptr = nullptr; int zmap_N = 0, zmap_L = 0, zmap_box_rows = 0;
   // pair bias z . W_b of every layer, [slot][N][H][L queries][Lp keys].  Inside abopt_sample_* it is computed once per run for all
   // layers (z and the weights are loop invariants of the T reverse steps); elsewhere slot 0 is recomputed per block call.
   float* bias_buf = nullptr; size_t bias_slots = 0, bias_slot_floats = 0; bool bias_hoisted = false;
@@ -513,12 +511,9 @@ static int check_ready(abopt_model* m, int N, int L, int need_scope = ABOPT_SCOP
 }
 
 // ------------------------------------------------------------------------------------------ encoder
-// TMA descriptor of pair_feat + room for `slots` layers of pair bias
+// room for `slots` layers of pair bias
 static int ensure_pair_inputs(abopt_model* m, int N, int L, const float* z, size_t slots) {
-  if (m->zmap_ptr != z || m->zmap_N != N || m->zmap_L != L) {
-    if (!make_pair_tmap(&m->zmap, z, (size_t)N * L * L, &m->zmap_box_rows)) return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed for pair_feat");
-    m->zmap_ptr = z; m->zmap_N = N; m->zmap_L = L;
-  }
+  (void)z;
   const size_t slot_floats = (size_t)N * H * L * ((L + 7) & ~7);
   if (!m->bias_buf || m->bias_slot_floats != slot_floats || m->bias_slots < slots) {
     if (m->bias_buf) { CUDA_TRY(cudaFree(m->bias_buf)); m->bias_buf = nullptr; }

@@ -2,9 +2,9 @@
 //   pair_bias_kernel    z_ij . W_b for every pair and head (ga.py:88-90) -- run ONCE per layer per sampling run: z and the
 //                       weights do not change over the T reverse steps (the hoist is in api.cu)
 //   pair_stream_kernel  the kernel that streams z once per GABlock: sum_j alpha_ijh z_ijc (ga.py:114-118); alpha comes from
-//                       attn_logits_tc_kernel (k_attn_tc.cu)
-// Both are persistent, TMA-fed (cp.async.bulk.tensor.2d, 128-byte swizzle, L2 evict-first, mbarrier expect_tx) and do
-// their arithmetic as packed FFMA2 (fma.rn.f32x2) on the CUDA cores.
+//                       attn_logits_persist_kernel (k_attn_tc.cu)
+// Both are persistent and barrier-free: every warp owns whole query rows and streams its row block through a private TMA
+// ring (mbarrier expect_tx, L2 evict-first); the arithmetic is packed FFMA2 (fma.rn.f32x2) on the CUDA cores.
 // Why CUDA cores and not tcgen05 here: the contractions are skinny (N = 12 heads) and need fp32-grade accuracy, i.e. a
 // 3xTF32 split of z; splitting the 64 KB row block in shared memory plus the operand reads of three MMAs cost ~7 passes
 // over the tile (~3600 clk/row of shared-memory bandwidth) against 1536 clk/row of FFMA issue per contraction -- no gain,
@@ -18,12 +18,6 @@ namespace abopt {
 
 using namespace tc;
 
-constexpr int PS_CONSUMERS = 512;                     // 16 warps (4 per scheduler); thread 0 doubles as the TMA producer
-constexpr int PS_THREADS = PS_CONSUMERS;
-constexpr int PS_ROWS = PS_CONSUMERS / 2;             // key residues covered per pass of phase A (2 threads per residue)
-constexpr int PS_BOX_ROWS = 64;                       // key residues per TMA box
-constexpr int PS_HALF_BYTES = PS_BOX_ROWS * 128;      // one TMA box: 64 rows x 32 floats
-
 __device__ __forceinline__ float2 ffma2(float a, float2 b, float2 c) {
   unsigned long long ra, rb, rc, rd;
   float2 aa = make_float2(a, a);
@@ -33,7 +27,6 @@ __device__ __forceinline__ float2 ffma2(float a, float2 b, float2 c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
   return *reinterpret_cast<float2*>(&rd);
 }
-__device__ __forceinline__ void consumer_sync() { __syncthreads(); }
 
 __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
@@ -44,24 +37,6 @@ __device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* m
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
                ::"r"(smem_u32(dst)), "l"(m), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
-
-// byte offset of the 16-byte group q (0..15) of key row j inside a stage (TMA SWIZZLE_128B layout):
-// box (j / 64, q / 8) of 64 rows x 128 B; inside a box the group index is XORed with (row & 7)
-__device__ __forceinline__ uint32_t zoff(int j, int q) {
-  const int jr = j & (PS_BOX_ROWS - 1);
-  return (uint32_t)((((j / PS_BOX_ROWS) * 2 + (q >> 3)) * PS_HALF_BYTES) + jr * 128 + (((q & 7) ^ (jr & 7)) << 4));
-}
-
-struct PairStreamArgs {
-  int L, Lp, b0, nrows;           // nrows = complexes covered by this launch * L; b0 = first complex
-  int nstage, stage_bytes, tile_tx_bytes, nbox_rows;   // nbox_rows = 64-row boxes per row-block
-  const uint8_t* mask;
-  float* alpha;                   // [chunk complex][h][i][Lp]  attention weights from attn_logits_tc_kernel (rows of masked
-                                  // queries are zeroed here, ga.py:25)
-  float* feat;
-  float* feat_lo;                 // tf32 "lo" plane of feat for the out_transform tensor-core GEMM
-  float* bias;                    // pair_bias_kernel output, transposed: [complex][h][j][Lp] (query index i contiguous)
-};
 
 // ------------------------------------------------------------------------------------------ pair bias
 // pair_bias_kernel: bias[b,h,i,j] = z[b,i,j,:] . W_b[h,:]   (ga.py:88-90), stored like alpha: [b][h][i][Lp], key index
@@ -368,17 +343,9 @@ cudaError_t pair_stream_init() {
   int dev = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-  const int mx = 227 * 1024;
   if ((e = cudaFuncSetAttribute(pair_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(pair_bias_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PB_SMEM)) != cudaSuccess) return e;
   return cudaSuccess;
-}
-
-// z viewed as a 2-D fp32 matrix [(N*L*L) rows][64]; boxes of [<=64 rows][32 floats], 128-byte swizzle
-bool make_pair_tmap(CUtensorMap* m, const float* z, size_t total_rows, int* box_rows_out) {
-  const uint32_t box_rows = total_rows < (size_t)PS_BOX_ROWS ? (uint32_t)total_rows : (uint32_t)PS_BOX_ROWS;
-  *box_rows_out = (int)box_rows;
-  return make_tmap_2d(m, z, total_rows, C, C, box_rows, 32);
 }
 
 // bias[b][h][i][Lp] for complexes [b0, b0 + nb); z viewed as a 2-D fp32 matrix [(N*L*L) rows][64]

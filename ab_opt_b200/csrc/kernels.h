@@ -116,7 +116,6 @@ void launch_alpha_tap(int nb, int b0, int L, int Lp, const float* alpha, float* 
 // k_pair.cu: pair_bias_kernel (hoisted z . W_b) and pair_stream_kernel (streams z once per GABlock)
 cudaError_t pair_stream_init();
 bool make_tmap_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
-bool make_pair_tmap(CUtensorMap* m, const float* z, size_t total_rows, int* box_rows_out);
 bool launch_pair_bias(int nb, int b0, int N, int L, int Lp, const float* z, const PairBiasPacked& pb, float* bias, cudaStream_t st);
 bool launch_pair_stream(int nb, int b0, int L, int Lp, const float* z, const uint8_t* mask,
                         float* alpha, float* feat, float* feat_lo, cudaStream_t st, const int* cidx = nullptr);
