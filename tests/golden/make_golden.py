@@ -57,6 +57,28 @@ def make_train_forward():
 
 
 @torch.no_grad()
+def make_pair_embed():
+    """PairEmbedding.forward (encoders/pair.py:37-101) of the unmodified reference: full-atom (A=15) and backbone+CB (A=5)
+    tables, with and without the structure / sequence masks; N=2, L=20, ragged, three chains."""
+    torch.set_num_threads(1)
+    if os.path.join(os.environ.get('ABOPT_REFERENCE', '/root/reference'), 'AbDock') not in sys.path:
+        sys.path.insert(0, os.path.join(os.environ.get('ABOPT_REFERENCE', '/root/reference'), 'AbDock'))
+    from src.modules.encoders.pair import PairEmbedding
+    from oracle import pair_embed as PE
+    seed_w, seed_in, N, L = 3, 5, 2, 20
+    inp = PE.synthetic_complex(seed_in, N, L)
+    keep = {}
+    for A in (15, 5):
+        ref = PairEmbedding(64, A)
+        ref.load_state_dict(PE.make_state_dict(seed_w, A), strict=True)
+        ref.eval()
+        args = (inp['aa'], inp['res_nb'], inp['chain_nb'], inp['pos_atoms'], inp['mask_atoms'])
+        keep[f'z_a{A}_plain'] = ref(*args)
+        keep[f'z_a{A}_masked'] = ref(*args, structure_mask=inp['context_mask'], sequence_mask=inp['context_mask'])
+    npz('pair_embed.npz', seed_w=seed_w, seed_in=seed_in, N=N, L=L, **inp, **keep)
+
+
+@torch.no_grad()
 def main():
     torch.set_num_threads(1)          # single-thread reference: reproducible reduction order
     # ---------------------------------------------------------------- GABlock / GAEncoder
@@ -136,6 +158,9 @@ def main():
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'train_forward':      # only the training fixture (the others are unchanged)
         make_train_forward()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'pair_embed':       # only the pair-featurisation fixture
+        make_pair_embed()
     else:
         main()
         make_train_forward()
+        make_pair_embed()

@@ -158,3 +158,25 @@ def test_training_forward_matches_reference(golden_dir, obj):
     assert sorted(got) == sorted(want)
     for k in want:
         torch.testing.assert_close(got[k], torch.as_tensor(want[k]), rtol=2e-5, atol=2e-6, msg=lambda m, k=k: f"{k}: {m}")
+
+
+# ------------------------------------------------------------------------------------------ pair featurisation
+@pytest.mark.parametrize('A', [15, 5])
+@pytest.mark.parametrize('masked', [False, True])
+def test_pair_embedding_matches_reference(golden_dir, A, masked):
+    """oracle.pair_embed.pair_embedding vs PairEmbedding.forward of the unmodified reference (tests/golden/pair_embed.npz)."""
+    from oracle import pair_embed as PE
+    g = load(golden_dir, 'pair_embed.npz')
+    W = PE.make_state_dict(g['seed_w'], A)
+    inp = PE.synthetic_complex(g['seed_in'], g['N'], g['L'])
+    for k in ('aa', 'res_nb', 'chain_nb', 'pos_atoms', 'mask_atoms', 'context_mask'):       # the generator is part of the pin
+        assert torch.equal(inp[k], g[k]), k
+    m = inp['context_mask'] if masked else None
+    z = PE.pair_embedding(W, inp['aa'], inp['res_nb'], inp['chain_nb'], inp['pos_atoms'], inp['mask_atoms'], m, m)
+    ref = g[f'z_a{A}_' + ('masked' if masked else 'plain')]
+    off = ~torch.eye(g['L'], dtype=torch.bool)[None, :, :, None]
+    torch.testing.assert_close(z * off, ref * off, rtol=1e-5, atol=2e-6)
+    # i == j: the sign of the inter-residue dihedral is the sign of a triple product that is zero in exact arithmetic
+    # (geometry.py:268 with p0 == p3), i.e. rounding noise in the reference itself; +-0.0014 rad moves z by < 1e-3
+    torch.testing.assert_close(z, ref, rtol=0, atol=2e-3)
+    assert (z[~inp['mask_atoms'][:, :, 1]] == 0).all()

@@ -130,3 +130,33 @@ def test_training_forward_losses(obj):
     assert sorted(got) == sorted(ref)
     for k in ref:
         torch.testing.assert_close(got[k], ref[k], rtol=2e-5, atol=2e-6, msg=lambda m, k=k: f'{k}: {m}')
+
+
+@torch.no_grad()
+@pytest.mark.parametrize('ckpt,A', [('dock_single_cdr/250000.pt', 15), ('seq_design/300000.pt', 5)])
+def test_pair_embedding_trained_weights(ckpt, A):
+    """oracle.pair_embed vs the reference PairEmbedding (encoders/pair.py:37-101) with the shipped `pair_embed.*` weights."""
+    path = os.path.join(REF_ROOT, 'AbDock/reproduction', ckpt)
+    if not os.path.exists(path):
+        pytest.skip('checkpoint missing')
+    if os.path.join(REF_ROOT, 'AbDock') not in sys.path:
+        sys.path.insert(0, os.path.join(REF_ROOT, 'AbDock'))
+    from src.modules.encoders.pair import PairEmbedding
+    from oracle import pair_embed as PE
+    _load_ckpt_state(path)                      # installs the unpickling stubs
+    ck = torch.load(path, map_location='cpu', weights_only=False)
+    W = {k[len('pair_embed.'):]: v for k, v in ck['model'].items() if k.startswith('pair_embed.')}
+    assert W['aapair_to_distcoef.weight'].shape[1] == A * A
+    assert set(W) == set(PE.make_state_dict(0, A)) and all(W[k].shape == v.shape for k, v in PE.make_state_dict(0, A).items())
+    ref = PairEmbedding(64, A)
+    ref.load_state_dict(W, strict=True)
+    ref.eval()
+    inp = PE.synthetic_complex(9, 2, 32)
+    m = inp['context_mask']
+    args = (inp['aa'], inp['res_nb'], inp['chain_nb'], inp['pos_atoms'], inp['mask_atoms'])
+    for sm, qm in ((None, None), (m, m)):
+        want = ref(*args, structure_mask=sm, sequence_mask=qm)
+        got = PE.pair_embedding(W, *args, sm, qm)
+        off = ~torch.eye(32, dtype=torch.bool)[None, :, :, None]
+        torch.testing.assert_close(got * off, want * off, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(got, want, rtol=0, atol=5e-3)
