@@ -7,11 +7,12 @@ reference's module interface.  There is no CPU fallback.
 from . import _capi
 from ._capi import AboptError, launch_count
 from .modules.encoders.ga import GABlock, GAEncoder
+from .modules.encoders.pair import PairEmbedding
 from .modules.diffusion.dpm_full import EpsilonNet, FullDPM, FullDPMAbDesign
 from .modules.diffusion.transition import (VarianceSchedule, PositionTransition, RotationTransition,
                                            AminoacidCategoricalTransition)
 
-__all__ = ['GABlock', 'GAEncoder', 'EpsilonNet', 'FullDPM', 'FullDPMAbDesign', 'VarianceSchedule',
+__all__ = ['GABlock', 'GAEncoder', 'PairEmbedding', 'EpsilonNet', 'FullDPM', 'FullDPMAbDesign', 'VarianceSchedule',
            'PositionTransition', 'RotationTransition', 'AminoacidCategoricalTransition', 'AboptError',
            'launch_count', 'install_into_reference']
 
@@ -30,4 +31,5 @@ def install_into_reference(package='src'):
     dpm.EpsilonNet = EpsilonNet
     ga.GAEncoder = GAEncoder
     ga.GABlock = GABlock
+    importlib.import_module(f'{package}.modules.encoders.pair').PairEmbedding = PairEmbedding      # models/diffab.py:28
     return dpm, ga

@@ -22,7 +22,8 @@ EXPORTS = (
     'abopt_ga_encoder_forward', 'abopt_ga_block_taps', 'abopt_eps_net_forward', 'abopt_rot_denoise',
     'abopt_pos_pred_noise_from_start', 'abopt_pos_denoise', 'abopt_seq_denoise', 'abopt_sample_device',
     'abopt_sample_host', 'abopt_workspace_bytes', 'abopt_sample_init', 'abopt_reverse_step', 'abopt_profile_enable', 'abopt_profile_collect', 'abopt_debug_gemm3x', 'abopt_debug_clocks',
-    'abopt_loss_forward',
+    'abopt_loss_forward', 'abopt_pair_embed_create', 'abopt_pair_embed_destroy', 'abopt_pair_embed_set_tensor',
+    'abopt_pair_embed_finalize', 'abopt_pair_embed_forward',
 )
 
 
@@ -80,6 +81,12 @@ def lib():
         L.abopt_debug_gemm3x.argtypes = [ci, ci, ci, ci] + [vp] * 5
         L.abopt_loss_forward.argtypes = [vp, ci, ci] + [vp] * 7 + [C.c_uint32, vp, C.c_uint64, C.POINTER(StepNoise), vp, vp]
         L.abopt_sample_host.argtypes = [vp, ci, ci] + [vp] * 7 + [C.c_uint32, ci, C.c_uint64] + [vp] * 5
+        L.abopt_pair_embed_create.argtypes = [ci, ci, C.POINTER(C.c_void_p)]
+        L.abopt_pair_embed_destroy.argtypes = [vp]
+        L.abopt_pair_embed_destroy.restype = None
+        L.abopt_pair_embed_set_tensor.argtypes = [vp, C.c_char_p, vp, C.c_size_t, ci]
+        L.abopt_pair_embed_finalize.argtypes = [vp]
+        L.abopt_pair_embed_forward.argtypes = [vp, ci, ci, ci] + [vp] * 9
         _lib = L
     return _lib
 

@@ -37,6 +37,7 @@ using namespace abopt;
 // ------------------------------------------------------------------------------------------ errors
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+namespace abopt { int api_fail(int code, const std::string& msg) { return fail(code, msg); } }      // for the other translation units
 #define CUDA_TRY(expr)                                                                          \
   do {                                                                                          \
     cudaError_t e__ = (expr);                                                                   \

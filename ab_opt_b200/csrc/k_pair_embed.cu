@@ -1,0 +1,476 @@
+// Pair featurisation (the step before the sampling loop): PairEmbedding.forward,
+// /root/reference/AbDock/src/modules/encoders/pair.py:37-101 (AbDesign: diffab/modules/encoders/pair.py, same lines), with
+// pairwise_dihedrals (modules/common/geometry.py:351-376), dihedral_from_four_points (:254-271) and AngularEncoding
+// (modules/common/layers.py:85-106), as ONE persistent kernel that writes pair_feat (N,L,L,64) once and never materialises the
+// (N,L,L,A*A) distance tensor (3.8 GB at N=64, L=256, A=15), the (N,L,L,218) concatenation or any MLP intermediate.
+//
+// Work unit = one query residue (n, i): its atoms, its 22 rows of the softplus'd distance-coefficient table and its scalars are
+// staged once, then the L keys are walked in tiles of 64 pairs.  Per tile, all in shared memory / registers:
+//   g[ab][pair] = mask_a mask_b exp(-softplus(coef[aa_i aa_j][ab]) (|x_ia - x_jb| / 10)^2)          pair.py:77-84
+//   h1 = relu(Wd1 g + b), h2 = relu(Wd2 h1 + b) * structure_pair                                      pair.py:84-87
+//   phi/psi -> [x, sin(x f), cos(x f)] * structure_pair                                               pair.py:90-94
+//   o1 = relu(T_aa[aa_i aa_j] + same_chain T_rel[clamp(res_i - res_j)] + W1[:,128:192] h2 + W1[:,192:218] ang + b1)
+//        (the aa-pair and relative-position embeddings go through the first out_mlp layer as pre-multiplied tables)  pair.py:65-74,97-98
+//   o2 = relu(W2 o1 + b2), z = (W3 o2 + b3) * has_CA_i has_CA_j                                        pair.py:98-99
+// The five dense layers are 64-pair x 64-channel register-tiled FP32 FFMA GEMMs (4 x 4 per thread, weights resident in shared
+// memory as [k][out]); fp32 end to end because the parity target is the reference's fp32 output.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/abopt_b200.h"
+#include "kernels.h"
+
+namespace abopt {
+int api_fail(int code, const std::string& msg);      // api.cu: sets abopt_last_error()
+
+namespace {
+constexpr int PE_THREADS = 256;
+constexpr int PE_TILE = 64;          // pairs per tile
+constexpr int PE_KC = 75;            // distance entries per chunk of the first layer's K loop
+constexpr int PE_MAXA = 15;          // max_num_heavyatoms (utils/protein/constants.py:143)
+constexpr int PE_AA = 22;            // max_aa_types (pair.py:12)
+constexpr int PE_RELPOS = 32;        // max_relpos (pair.py:12)
+constexpr int PE_UNK = 20;           // AA.UNK (constants.py:108)
+constexpr int PE_ANG = 26;           // AngularEncoding.get_out_dim(2) (layers.py:94-95)
+
+struct PairEmbedW {                  // device pointers into one packed allocation
+  int A, A2;
+  const float* coef;                 // [484][A2]   softplus(aapair_to_distcoef)
+  const float* Taa;                  // [484][64]   aa_pair_embed . W1[:, 0:64]^T
+  const float* Trel;                 // [65][64]    relpos_embed  . W1[:, 64:128]^T
+  const float* Wd1;                  // [A2][64]    distance_embed.0.weight^T
+  const float* W64;                  // [4][64][64] distance_embed.2, out_mlp.0[:,128:192], out_mlp.2, out_mlp.4 (all [k][out])
+  const float* W1h;                  // [26][64]    out_mlp.0[:,192:218]^T
+  const float* bias;                 // [5][64]     bd1, bd2, b1, b2, b3
+  float freq[6];                     // dihedral_embed.freq_bands
+};
+
+struct PairEmbedArgs {
+  int N, L, A_in;
+  const long long* aa; const long long* res_nb; const long long* chain_nb;
+  const float* pos; const uint8_t* mask_atoms; const uint8_t* structure_mask; const uint8_t* sequence_mask;
+  float* out;
+};
+
+// smem carve-up (floats); the host computes the same total
+__host__ __device__ inline int pe_smem_floats(int A2) {
+  return A2 * 64 + 4 * 4096 + PE_ANG * 64 + 5 * 64      // weights
+         + PE_KC * 64 + 4096 + PE_ANG * 64               // g chunk (aliased by hA), hB, angle features
+         + ((PE_AA * A2 + 3) & ~3)                        // coefficient rows of aa_i
+         + PE_TILE * PE_MAXA * 3 + 48                     // key atoms, query atoms
+         + 6 * PE_TILE;                                   // per-pair ints
+}
+
+// acc[r][c] += sum_k act[k][pg*4 + r] * W[k][og*4 + c]
+template <int UNROLL>
+__device__ __forceinline__ void tile_gemm(float (&acc)[4][4], const float* __restrict__ act, const float* __restrict__ W, int K, int pg, int og) {
+  const float4* a4 = reinterpret_cast<const float4*>(act) + pg;
+  const float4* w4 = reinterpret_cast<const float4*>(W) + og;
+#pragma unroll UNROLL
+  for (int k = 0; k < K; ++k) {
+    const float4 a = a4[k * 16];
+    const float4 w = w4[k * 16];
+    const float av[4] = {a.x, a.y, a.z, a.w};
+    const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], wv[c], acc[r][c]);
+  }
+}
+
+__device__ __forceinline__ void zero_acc(float (&acc)[4][4]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+}
+
+// relu(acc + bias) [* scale[pair]] -> dst[o][pair]
+__device__ __forceinline__ void store_act(const float (&acc)[4][4], const float* __restrict__ b, float* dst, int pg, int og, const int* keep) {
+  float s[4] = {1.f, 1.f, 1.f, 1.f};
+  if (keep) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) s[r] = keep[pg * 4 + r] ? 1.f : 0.f;
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float bb = b[og * 4 + c];
+    float4 v;
+    v.x = fmaxf(acc[0][c] + bb, 0.f) * s[0];
+    v.y = fmaxf(acc[1][c] + bb, 0.f) * s[1];
+    v.z = fmaxf(acc[2][c] + bb, 0.f) * s[2];
+    v.w = fmaxf(acc[3][c] + bb, 0.f) * s[3];
+    *reinterpret_cast<float4*>(dst + (og * 4 + c) * 64 + pg * 4) = v;
+  }
+}
+
+// dihedral_from_four_points, geometry.py:254-271, operation by operation (no FMA contraction: the sign of the result is the sign
+// of a triple product, so the rounding of the products matters when it is close to zero).
+__device__ __forceinline__ void cross_rn(const float* a, const float* b, float* o) {
+  o[0] = __fsub_rn(__fmul_rn(a[1], b[2]), __fmul_rn(a[2], b[1]));
+  o[1] = __fsub_rn(__fmul_rn(a[2], b[0]), __fmul_rn(a[0], b[2]));
+  o[2] = __fsub_rn(__fmul_rn(a[0], b[1]), __fmul_rn(a[1], b[0]));
+}
+__device__ __forceinline__ float dot_rn(const float* a, const float* b) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(a[0], b[0]), __fmul_rn(a[1], b[1])), __fmul_rn(a[2], b[2]));
+}
+__device__ __forceinline__ float dihedral(const float* p0, const float* p1, const float* p2, const float* p3) {
+  float v0[3], v1[3], v2[3], u1[3], u2[3], w[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { v0[c] = p2[c] - p1[c]; v1[c] = p0[c] - p1[c]; v2[c] = p3[c] - p2[c]; }
+  cross_rn(v0, v1, u1);
+  cross_rn(v0, v2, u2);
+  const float l1 = sqrtf(dot_rn(u1, u1)), l2 = sqrtf(dot_rn(u2, u2));
+  float n1[3], n2[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { n1[c] = u1[c] / l1; n2[c] = u2[c] / l2; }      // 0 / 0 -> NaN, as in the reference
+  cross_rn(v1, v2, w);
+  const float tp = dot_rn(w, v0);
+  const float sgn = tp > 0.f ? 1.f : (tp < 0.f ? -1.f : 0.f);
+  float cs = dot_rn(n1, n2);
+  if (isnan(cs) || isnan(tp)) return 0.f;                                       // nan_to_num, geometry.py:270
+  cs = fminf(fmaxf(cs, -0.999999f), 0.999999f);
+  return sgn * acosf(cs);
+}
+
+__global__ void __launch_bounds__(PE_THREADS, 1) pair_embed_kernel(PairEmbedW w, PairEmbedArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int A = w.A, A2 = w.A2;
+  float* sWd1 = smem;                              // [A2][64]
+  float* sW64 = sWd1 + A2 * 64;                    // [4][64][64]
+  float* sW1h = sW64 + 4 * 4096;                   // [26][64]
+  float* sBias = sW1h + PE_ANG * 64;               // [5][64]
+  float* sG = sBias + 5 * 64;                      // [75][64] distance chunk; later hA [64][64]
+  float* sHB = sG + PE_KC * 64;                    // [64][64]
+  float* sAng = sHB + 4096;                        // [26][64]
+  float* sCoef = sAng + PE_ANG * 64;               // [22][A2]
+  float* sPosJ = sCoef + ((PE_AA * A2 + 3) & ~3);  // [64][A*3]
+  float* sPosI = sPosJ + PE_TILE * PE_MAXA * 3;    // [A*3] (48 slots)
+  int* sAaJ = reinterpret_cast<int*>(sPosI + 48);  // [64] amino-acid slot of the key
+  int* sRel = sAaJ + PE_TILE;                      // [64] row of T_rel, -1 = other chain
+  int* sKeep = sRel + PE_TILE;                     // [64] structure_mask_i & structure_mask_j
+  int* sOk = sKeep + PE_TILE;                      // [64] has_CA_i & has_CA_j (& j < L)
+  int* sBitsJ = sOk + PE_TILE;                     // [64] atom mask of the key, one bit per atom
+  int* sMisc = sBitsJ + PE_TILE;                   // [64] scalars of the query residue
+
+  const int tid = threadIdx.x;
+  const int pg = tid & 15, og = tid >> 4;          // GEMM phases: 4 pairs x 4 channels per thread
+  const int L = a.L, A_in = a.A_in;
+
+  // ---- weights: once per CTA
+  for (int i = tid; i < A2 * 64; i += PE_THREADS) sWd1[i] = w.Wd1[i];
+  for (int i = tid; i < 4 * 4096; i += PE_THREADS) sW64[i] = w.W64[i];
+  for (int i = tid; i < PE_ANG * 64; i += PE_THREADS) sW1h[i] = w.W1h[i];
+  for (int i = tid; i < 5 * 64; i += PE_THREADS) sBias[i] = w.bias[i];
+
+  const int n_tiles = (L + PE_TILE - 1) / PE_TILE;
+  const long long rows = (long long)a.N * L;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = (int)(row / L), i = (int)(row % L);
+    __syncthreads();                               // previous row fully consumed (also orders the weight fill)
+    // ---- query residue
+    if (tid < A * 3) sPosI[tid] = a.pos[((size_t)row * A_in) * 3 + tid];
+    if (tid == 32) {
+      long long aa = a.aa[row];
+      if (a.sequence_mask && !a.sequence_mask[row]) aa = PE_UNK;                     // pair.py:62-64
+      aa = aa < 0 ? 0 : (aa >= PE_AA ? PE_AA - 1 : aa);
+      int bits = 0;
+      for (int k = 0; k < A; ++k) bits |= (a.mask_atoms[(size_t)row * A_in + k] ? 1 : 0) << k;
+      sMisc[0] = (int)aa;
+      sMisc[1] = bits;
+      sMisc[2] = a.structure_mask ? (a.structure_mask[row] ? 1 : 0) : 1;
+    }
+    __syncthreads();
+    const int aa_i = sMisc[0], bits_i = sMisc[1], keep_i = sMisc[2];
+    const int ok_i = (bits_i >> 1) & 1;                                              // BBHeavyAtom.CA = 1, pair.py:57
+    {
+      const float* src = w.coef + (size_t)aa_i * PE_AA * A2;
+      for (int k = tid; k < PE_AA * A2; k += PE_THREADS) sCoef[k] = src[k];
+    }
+    const long long res_i = a.res_nb[row], chain_i = a.chain_nb[row];
+
+    for (int jt = 0; jt < n_tiles; ++jt) {
+      const int j0 = jt * PE_TILE;
+      __syncthreads();                             // previous tile's readers done (sCoef fill ordered too)
+      // ---- stage the 64 keys
+      for (int k = tid; k < PE_TILE * A * 3; k += PE_THREADS) {
+        const int p = k / (A * 3), c = k - p * (A * 3);
+        const int j = j0 + p;
+        sPosJ[p * (A * 3) + c] = j < L ? a.pos[(((size_t)n * L + j) * A_in) * 3 + c] : 0.f;
+      }
+      if (tid < PE_TILE) {
+        const int j = j0 + tid;
+        int aaj = 0, rel = -1, keep = 0, ok = 0, bits = 0;
+        if (j < L) {
+          const size_t rj = (size_t)n * L + j;
+          long long aa = a.aa[rj];
+          if (a.sequence_mask && !a.sequence_mask[rj]) aa = PE_UNK;
+          aaj = (int)(aa < 0 ? 0 : (aa >= PE_AA ? PE_AA - 1 : aa));
+          for (int k = 0; k < A; ++k) bits |= (a.mask_atoms[rj * A_in + k] ? 1 : 0) << k;
+          long long d = res_i - a.res_nb[rj];                                        // pair.py:70-73
+          d = d < -PE_RELPOS ? -PE_RELPOS : (d > PE_RELPOS ? PE_RELPOS : d);
+          rel = (a.chain_nb[rj] == chain_i) ? (int)d + PE_RELPOS : -1;
+          keep = keep_i && (a.structure_mask ? (a.structure_mask[rj] != 0) : 1);
+          ok = ok_i && ((bits >> 1) & 1);
+        }
+        sAaJ[tid] = aaj; sRel[tid] = rel; sKeep[tid] = keep; sOk[tid] = ok; sBitsJ[tid] = bits;
+      }
+      __syncthreads();
+
+      // ---- inter-residue dihedrals + angular encoding (threads 0..127: one angle of one pair each)
+      if (tid < 2 * PE_TILE) {
+        const int p = tid & 63, which = tid >> 6;
+        const float* Ni = sPosI; const float* CAi = sPosI + 3; const float* Ci = sPosI + 6;
+        const float* Nj = sPosJ + p * (A * 3); const float* CAj = Nj + 3; const float* Cj = Nj + 6;
+        float x = which == 0 ? dihedral(Ci, Nj, CAj, Cj) : dihedral(Ni, CAi, Ci, Nj);   // geometry.py:362-373
+        const float s = sKeep[p] ? 1.f : 0.f;                                           // pair.py:92-94
+        float* dst = sAng + which * 13 * 64 + p;
+        dst[0] = x * s;
+#pragma unroll
+        for (int f = 0; f < 6; ++f) {
+          const float xf = x * w.freq[f];
+          dst[(1 + f) * 64] = sinf(xf) * s;
+          dst[(7 + f) * 64] = cosf(xf) * s;
+        }
+      }
+
+      // ---- distance Gaussians -> first distance layer, K walked in chunks of 75
+      float acc[4][4];
+      zero_acc(acc);
+      for (int e0 = 0; e0 < A2; e0 += PE_KC) {
+        const int ne = min(PE_KC, A2 - e0);
+        for (int k = tid; k < ne * PE_TILE; k += PE_THREADS) {
+          const int p = k & 63, e = e0 + (k >> 6);
+          const int ia = e / A, ib = e - ia * A;
+          const float* xi = sPosI + ia * 3;
+          const float* xj = sPosJ + p * (A * 3) + ib * 3;
+          const float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
+          const float d = sqrtf(dx * dx + dy * dy + dz * dz) / 10.f;                    // angstrom_to_nm, pair.py:77
+          const float cf = sCoef[sAaJ[p] * A2 + e];
+          const bool on = ((bits_i >> ia) & 1) && ((sBitsJ[p] >> ib) & 1);
+          sG[(k >> 6) * 64 + p] = on ? expf(-cf * (d * d)) : 0.f;                       // pair.py:82-84
+        }
+        __syncthreads();
+        tile_gemm<5>(acc, sG, sWd1 + e0 * 64, ne, pg, og);
+        __syncthreads();
+      }
+      store_act(acc, sBias, sHB, pg, og, nullptr);                                      // h1
+      __syncthreads();
+      zero_acc(acc);
+      tile_gemm<8>(acc, sHB, sW64, 64, pg, og);
+      store_act(acc, sBias + 64, sG, pg, og, sKeep);                                    // h2 * structure pair mask (pair.py:85-87)
+      // table part of the first out_mlp layer: issued here so the gathers overlap the GEMM below
+      float tab[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int p = pg * 4 + r;
+        const float4 ta = *reinterpret_cast<const float4*>(w.Taa + ((size_t)(aa_i * PE_AA + sAaJ[p])) * 64 + og * 4);
+        const int rel = sRel[p];
+        float4 tr = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rel >= 0) tr = *reinterpret_cast<const float4*>(w.Trel + (size_t)rel * 64 + og * 4);
+        tab[r][0] = ta.x + tr.x; tab[r][1] = ta.y + tr.y; tab[r][2] = ta.z + tr.z; tab[r][3] = ta.w + tr.w;
+      }
+      __syncthreads();
+      zero_acc(acc);
+      tile_gemm<8>(acc, sG, sW64 + 4096, 64, pg, og);
+      tile_gemm<2>(acc, sAng, sW1h, PE_ANG, pg, og);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] += tab[r][c];
+      store_act(acc, sBias + 128, sHB, pg, og, nullptr);                                // o1 (sHB's readers passed the barrier above)
+      __syncthreads();
+      zero_acc(acc);
+      tile_gemm<8>(acc, sHB, sW64 + 2 * 4096, 64, pg, og);
+      store_act(acc, sBias + 192, sG, pg, og, nullptr);                                 // o2
+      __syncthreads();
+      // ---- last layer with the roles of the lanes swapped: 16 lanes cover the 64 channels of one pair -> 256-byte rows
+      {
+        const int og2 = tid & 15, pg2 = tid >> 4;
+        zero_acc(acc);
+        tile_gemm<8>(acc, sG, sW64 + 3 * 4096, 64, pg2, og2);
+        const float4 b3 = *reinterpret_cast<const float4*>(sBias + 256 + og2 * 4);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int p = pg2 * 4 + r, j = j0 + p;
+          if (j < L) {
+            const float s = sOk[p] ? 1.f : 0.f;                                        // pair.py:99
+            float4 v = make_float4((acc[r][0] + b3.x) * s, (acc[r][1] + b3.y) * s, (acc[r][2] + b3.z) * s, (acc[r][3] + b3.w) * s);
+            __stcs(reinterpret_cast<float4*>(a.out + ((size_t)row * L + j) * 64 + og2 * 4), v);
+          }
+        }
+      }
+    }
+  }
+}
+}  // namespace
+}  // namespace abopt
+
+using namespace abopt;
+
+// ------------------------------------------------------------------------------------------ C ABI
+struct abopt_pair_embed {
+  int device = 0, A = 0;
+  bool finalized = false;
+  std::map<std::string, size_t> spec;
+  std::map<std::string, std::vector<float>> sd;
+  void* wbase = nullptr;
+  PairEmbedW w;
+  int sm_count = 148;
+  size_t smem_bytes = 0;
+};
+
+#define PE_CUDA_TRY(expr)                                                                       \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) return api_fail(ABOPT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+extern "C" int abopt_pair_embed_create(int max_num_atoms, int device, abopt_pair_embed** out) {
+  if (!out) return api_fail(ABOPT_ERR_ARG, "null argument");
+  if (max_num_atoms < 3 || max_num_atoms > PE_MAXA) return api_fail(ABOPT_ERR_ARG, "max_num_atoms must be in [3, 15] (N, CA, C are needed)");
+  int ndev = 0;
+  PE_CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return api_fail(ABOPT_ERR_ARG, "no such CUDA device");
+  cudaDeviceProp prop;
+  PE_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return api_fail(ABOPT_ERR_CUDA, std::string("libabopt_b200 needs a B200-class GPU (sm_100); found ") + prop.name);
+  abopt_pair_embed* pe = new abopt_pair_embed();
+  pe->device = device; pe->A = max_num_atoms; pe->sm_count = prop.multiProcessorCount;
+  const size_t A2 = (size_t)max_num_atoms * max_num_atoms;
+  pe->spec = {{"aa_pair_embed.weight", (size_t)PE_AA * PE_AA * 64}, {"relpos_embed.weight", (size_t)(2 * PE_RELPOS + 1) * 64},
+              {"aapair_to_distcoef.weight", (size_t)PE_AA * PE_AA * A2}, {"dihedral_embed.freq_bands", 6},
+              {"distance_embed.0.weight", 64 * A2}, {"distance_embed.0.bias", 64},
+              {"distance_embed.2.weight", 64 * 64}, {"distance_embed.2.bias", 64},
+              {"out_mlp.0.weight", (size_t)64 * (192 + PE_ANG)}, {"out_mlp.0.bias", 64},
+              {"out_mlp.2.weight", 64 * 64}, {"out_mlp.2.bias", 64}, {"out_mlp.4.weight", 64 * 64}, {"out_mlp.4.bias", 64}};
+  pe->smem_bytes = (size_t)pe_smem_floats((int)A2) * sizeof(float);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  cudaSetDevice(device);
+  // the attribute is per function, not per handle: always opt in for the full-atom size (206 KB)
+  cudaError_t e = cudaFuncSetAttribute(pair_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(pe_smem_floats(PE_MAXA * PE_MAXA) * sizeof(float)));
+  cudaSetDevice(cur);
+  if (e != cudaSuccess) { delete pe; return api_fail(ABOPT_ERR_CUDA, std::string("pair_embed_kernel shared memory: ") + cudaGetErrorString(e)); }
+  *out = pe;
+  return ABOPT_OK;
+}
+
+extern "C" void abopt_pair_embed_destroy(abopt_pair_embed* pe) {
+  if (!pe) return;
+  if (pe->wbase) {
+    int cur = 0;
+    cudaGetDevice(&cur); cudaSetDevice(pe->device);
+    cudaFree(pe->wbase);
+    cudaSetDevice(cur);
+  }
+  delete pe;
+}
+
+extern "C" int abopt_pair_embed_set_tensor(abopt_pair_embed* pe, const char* key, const float* data, size_t numel, int on_device) {
+  if (!pe || !key) return api_fail(ABOPT_ERR_ARG, "null argument");
+  auto it = pe->spec.find(key);
+  if (it == pe->spec.end()) return api_fail(ABOPT_ERR_KEY, std::string("unexpected state-dict key: ") + key);
+  if (it->second != numel) return api_fail(ABOPT_ERR_KEY, std::string("size mismatch for ") + key + ": expected " + std::to_string(it->second) +
+                                                              " elements, got " + std::to_string(numel));
+  if (!data) return api_fail(ABOPT_ERR_ARG, "null data");
+  std::vector<float>& t = pe->sd[key];
+  t.resize(numel);
+  if (on_device) {
+    int cur = 0;
+    cudaGetDevice(&cur); cudaSetDevice(pe->device);
+    cudaError_t e = cudaMemcpy(t.data(), data, numel * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaSetDevice(cur);
+    if (e != cudaSuccess) return api_fail(ABOPT_ERR_CUDA, std::string("cudaMemcpy: ") + cudaGetErrorString(e));
+  } else {
+    memcpy(t.data(), data, numel * sizeof(float));
+  }
+  pe->finalized = false;
+  return ABOPT_OK;
+}
+
+extern "C" int abopt_pair_embed_finalize(abopt_pair_embed* pe) {
+  if (!pe) return api_fail(ABOPT_ERR_ARG, "null argument");
+  for (auto& kv : pe->spec)
+    if (!pe->sd.count(kv.first)) return api_fail(ABOPT_ERR_STATE, "missing state-dict key: " + kv.first);
+  const int A2 = pe->A * pe->A, NP = PE_AA * PE_AA, NR = 2 * PE_RELPOS + 1, K1 = 192 + PE_ANG;
+  const std::vector<float>& W1 = pe->sd["out_mlp.0.weight"];
+  std::vector<float> img;
+  auto reserve = [&](size_t n) { size_t off = (img.size() + 63) & ~size_t(63); img.resize(off + n, 0.f); return off; };
+  const size_t o_coef = reserve((size_t)NP * A2), o_taa = reserve((size_t)NP * 64), o_trel = reserve((size_t)NR * 64),
+               o_wd1 = reserve((size_t)A2 * 64), o_w64 = reserve(4 * 4096), o_w1h = reserve(PE_ANG * 64), o_bias = reserve(5 * 64);
+  {  // F.softplus (beta 1, threshold 20), pair.py:81
+    const std::vector<float>& c = pe->sd["aapair_to_distcoef.weight"];
+    for (size_t k = 0; k < c.size(); ++k) img[o_coef + k] = c[k] > 20.f ? c[k] : log1pf(expf(c[k]));
+  }
+  auto premul = [&](const std::vector<float>& E, int rows, int col0, size_t off) {      // T[r][o] = sum_c E[r][c] W1[o][col0 + c]
+    for (int r = 0; r < rows; ++r)
+      for (int o = 0; o < 64; ++o) {
+        double s = 0.0;
+        for (int c = 0; c < 64; ++c) s += (double)E[(size_t)r * 64 + c] * (double)W1[(size_t)o * K1 + col0 + c];
+        img[off + (size_t)r * 64 + o] = (float)s;
+      }
+  };
+  premul(pe->sd["aa_pair_embed.weight"], NP, 0, o_taa);
+  premul(pe->sd["relpos_embed.weight"], NR, 64, o_trel);
+  auto transpose = [&](const float* Wsrc, int ld, int col0, int K, size_t off) {        // dst[k][o] = W[o][col0 + k]
+    for (int k = 0; k < K; ++k)
+      for (int o = 0; o < 64; ++o) img[off + (size_t)k * 64 + o] = Wsrc[(size_t)o * ld + col0 + k];
+  };
+  transpose(pe->sd["distance_embed.0.weight"].data(), A2, 0, A2, o_wd1);
+  transpose(pe->sd["distance_embed.2.weight"].data(), 64, 0, 64, o_w64);
+  transpose(W1.data(), K1, 128, 64, o_w64 + 4096);
+  transpose(pe->sd["out_mlp.2.weight"].data(), 64, 0, 64, o_w64 + 2 * 4096);
+  transpose(pe->sd["out_mlp.4.weight"].data(), 64, 0, 64, o_w64 + 3 * 4096);
+  transpose(W1.data(), K1, 192, PE_ANG, o_w1h);
+  const char* bkeys[5] = {"distance_embed.0.bias", "distance_embed.2.bias", "out_mlp.0.bias", "out_mlp.2.bias", "out_mlp.4.bias"};
+  for (int b = 0; b < 5; ++b) memcpy(&img[o_bias + b * 64], pe->sd[bkeys[b]].data(), 64 * sizeof(float));
+
+  int cur = 0;
+  cudaGetDevice(&cur); cudaSetDevice(pe->device);
+  if (pe->wbase) { cudaFree(pe->wbase); pe->wbase = nullptr; }
+  cudaError_t e = cudaMalloc(&pe->wbase, img.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(pe->wbase, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice);
+  cudaSetDevice(cur);
+  if (e != cudaSuccess) return api_fail(ABOPT_ERR_CUDA, std::string("pair-embed weights: ") + cudaGetErrorString(e));
+  const float* base = static_cast<const float*>(pe->wbase);
+  pe->w.A = pe->A; pe->w.A2 = A2;
+  pe->w.coef = base + o_coef; pe->w.Taa = base + o_taa; pe->w.Trel = base + o_trel; pe->w.Wd1 = base + o_wd1;
+  pe->w.W64 = base + o_w64; pe->w.W1h = base + o_w1h; pe->w.bias = base + o_bias;
+  memcpy(pe->w.freq, pe->sd["dihedral_embed.freq_bands"].data(), 6 * sizeof(float));
+  pe->finalized = true;
+  return ABOPT_OK;
+}
+
+extern "C" int abopt_pair_embed_forward(abopt_pair_embed* pe, int N, int L, int num_atoms_in, const int64_t* aa, const int64_t* res_nb,
+                                        const int64_t* chain_nb, const float* pos_atoms, const uint8_t* mask_atoms,
+                                        const uint8_t* structure_mask, const uint8_t* sequence_mask, float* pair_feat, void* stream) {
+  if (!pe) return api_fail(ABOPT_ERR_ARG, "null handle");
+  if (!pe->finalized) return api_fail(ABOPT_ERR_STATE, "pair embedding not finalised");
+  if (N < 0 || L < 0) return api_fail(ABOPT_ERR_ARG, "negative size");
+  if (num_atoms_in < pe->A) return api_fail(ABOPT_ERR_ARG, "pos_atoms / mask_atoms have fewer atoms per residue than max_num_atoms");
+  if (N == 0 || L == 0) return ABOPT_OK;
+  if (!aa || !res_nb || !chain_nb || !pos_atoms || !mask_atoms || !pair_feat) return api_fail(ABOPT_ERR_ARG, "null tensor");
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cur != pe->device) cudaSetDevice(pe->device);
+  PairEmbedArgs a{N, L, num_atoms_in, (const long long*)aa, (const long long*)res_nb, (const long long*)chain_nb, pos_atoms, mask_atoms,
+                  structure_mask, sequence_mask, pair_feat};
+  const long long rows = (long long)N * L;
+  const int grid = (int)std::min<long long>(rows, pe->sm_count);
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    ProfScope ps(KK_OTHER, st);
+    pair_embed_kernel<<<grid, PE_THREADS, pe->smem_bytes, st>>>(pe->w, a);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (cur != pe->device) cudaSetDevice(cur);
+  if (e != cudaSuccess) return api_fail(ABOPT_ERR_CUDA, std::string("pair_embed_kernel: ") + cudaGetErrorString(e));
+  return ABOPT_OK;
+}

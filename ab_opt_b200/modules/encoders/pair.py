@@ -1,0 +1,103 @@
+"""PairEmbedding with the reference's constructor signature, state-dict keys and call signature
+(/root/reference/AbDock/src/modules/encoders/pair.py:10-101; AbDesign: diffab/modules/encoders/pair.py), executing as ONE
+sm_100a kernel of libabopt_b200 (csrc/k_pair_embed.cu) through the C ABI.  No PyTorch arithmetic happens here."""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from ... import _capi
+
+
+class AngularEncoding(nn.Module):
+    """Holds the `freq_bands` buffer of the reference (common/layers.py:85-95); the encoding runs inside the kernel."""
+
+    def __init__(self, num_funcs=3):
+        super().__init__()
+        if num_funcs != 3:
+            raise ValueError('the CUDA kernel implements the reference default num_funcs=3 only')
+        self.num_funcs = num_funcs
+        self.register_buffer('freq_bands', torch.FloatTensor([i + 1 for i in range(num_funcs)]
+                                                             + [1. / (i + 1) for i in range(num_funcs)]))
+
+    def get_out_dim(self, in_dim):
+        return in_dim * (1 + 2 * 2 * self.num_funcs)
+
+
+class _NativePairEmbed:
+    def __init__(self, max_num_atoms, device, tensors):
+        L = _capi.lib()
+        dev = torch.device(device)
+        if dev.type != 'cuda':
+            raise _capi.AboptError('ab_opt_b200 runs on CUDA devices only (no CPU fallback); got device ' + str(dev))
+        self.index = dev.index if dev.index is not None else torch.cuda.current_device()
+        h = C.c_void_p()
+        _capi.check(L.abopt_pair_embed_create(max_num_atoms, self.index, C.byref(h)))
+        self.handle = h
+        try:
+            for key, t in tensors.items():
+                t = t.detach().float().contiguous()
+                _capi.check(L.abopt_pair_embed_set_tensor(h, key.encode(), _capi.ptr(t), t.numel(), 1 if t.is_cuda else 0))
+            _capi.check(L.abopt_pair_embed_finalize(h))
+        except Exception:
+            L.abopt_pair_embed_destroy(h)
+            self.handle = None
+            raise
+
+    def __del__(self):
+        if getattr(self, 'handle', None) is not None and _capi._lib is not None:
+            _capi._lib.abopt_pair_embed_destroy(self.handle)
+            self.handle = None
+
+
+class PairEmbedding(nn.Module):
+
+    def __init__(self, feat_dim, max_num_atoms, max_aa_types=22, max_relpos=32):
+        super().__init__()
+        if (feat_dim, max_aa_types, max_relpos) != (64, 22, 32) or not 3 <= max_num_atoms <= 15:
+            raise ValueError('the sm_100a kernel is specialised for the reference configuration: feat_dim 64, 22 amino-acid '
+                             'types, max_relpos 32, 3..15 atoms per residue')
+        self.max_num_atoms, self.max_aa_types, self.max_relpos = max_num_atoms, max_aa_types, max_relpos
+        self.aa_pair_embed = nn.Embedding(max_aa_types * max_aa_types, feat_dim)
+        self.relpos_embed = nn.Embedding(2 * max_relpos + 1, feat_dim)
+        self.aapair_to_distcoef = nn.Embedding(max_aa_types * max_aa_types, max_num_atoms * max_num_atoms)
+        nn.init.zeros_(self.aapair_to_distcoef.weight)
+        self.distance_embed = nn.Sequential(nn.Linear(max_num_atoms * max_num_atoms, feat_dim), nn.ReLU(),
+                                            nn.Linear(feat_dim, feat_dim), nn.ReLU())
+        self.dihedral_embed = AngularEncoding()
+        infeat_dim = 3 * feat_dim + self.dihedral_embed.get_out_dim(2)
+        self.out_mlp = nn.Sequential(nn.Linear(infeat_dim, feat_dim), nn.ReLU(), nn.Linear(feat_dim, feat_dim), nn.ReLU(),
+                                     nn.Linear(feat_dim, feat_dim))
+
+    def native(self):
+        state = self.state_dict(keep_vars=True)
+        fp = tuple((k, t.data_ptr(), t._version, str(t.device)) for k, t in state.items())
+        cached = self.__dict__.get('_native_cache')
+        if cached is not None and cached[0] == fp:
+            return cached[1]
+        devs = {t.device for t in state.values()}
+        if len(devs) != 1:
+            raise _capi.AboptError(f'parameters live on several devices: {devs}')
+        nm = _NativePairEmbed(self.max_num_atoms, devs.pop(), state)
+        self.__dict__['_native_cache'] = (fp, nm)
+        return nm
+
+    @torch.no_grad()
+    def forward(self, aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask=None, sequence_mask=None):
+        """aa, res_nb, chain_nb (N,L); pos_atoms (N,L,A,3); mask_atoms (N,L,A); structure_mask, sequence_mask (N,L) or None
+        -> (N,L,L,feat_dim).  pair.py:37-101."""
+        nm = self.native()
+        aa = _capi.cuda_i64(aa, 'aa'); res_nb = _capi.cuda_i64(res_nb, 'res_nb'); chain_nb = _capi.cuda_i64(chain_nb, 'chain_nb')
+        pos = _capi.cuda_f32(pos_atoms, 'pos_atoms'); mask = _capi.cuda_mask(mask_atoms, 'mask_atoms')
+        sm = _capi.cuda_mask(structure_mask, 'structure_mask') if structure_mask is not None else None
+        qm = _capi.cuda_mask(sequence_mask, 'sequence_mask') if sequence_mask is not None else None
+        N, L = aa.shape
+        A = pos.shape[2] if pos.dim() == 4 else -1
+        if pos.shape != (N, L, A, 3) or mask.shape != (N, L, A) or res_nb.shape != (N, L) or chain_nb.shape != (N, L) \
+                or any(m is not None and m.shape != (N, L) for m in (sm, qm)):
+            raise ValueError(f'bad shapes: aa {tuple(aa.shape)} pos_atoms {tuple(pos.shape)} mask_atoms {tuple(mask.shape)}')
+        out = torch.empty(N, L, L, 64, device=aa.device, dtype=torch.float32)
+        _capi.check(_capi.lib().abopt_pair_embed_forward(nm.handle, N, L, A, _capi.ptr(aa), _capi.ptr(res_nb), _capi.ptr(chain_nb),
+                                                         _capi.ptr(pos), _capi.ptr(mask), _capi.ptr(sm), _capi.ptr(qm), _capi.ptr(out),
+                                                         _capi.stream_ptr(aa.device)))
+        return out

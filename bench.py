@@ -364,19 +364,87 @@ def run_train_forward(args):
                                    'note': 'whole forward against SURVEY 8d algorithmic bytes (z once per layer + node state)'}}), flush=True)
 
 
+def run_pair_embed(args):
+    """--config f1: PairEmbedding.forward (the O(L^2) featurisation that produces pair_feat before the
+    loop) at the C2 shapes: B=64, L=256, 15 atoms per residue.  pairs/s = B * L^2 / time.  One GPU; not the headline metric."""
+    import ab_opt_b200
+    from oracle import pair_embed as PE
+    B, L, A = 64, 256, 15
+    dev = torch.device('cuda', 0)
+    W = PE.make_state_dict(3, A)
+    mod = ab_opt_b200.PairEmbedding(64, A)
+    mod.load_state_dict(W, strict=True)
+    mod = mod.to(dev).eval()
+    host = PE.synthetic_complex(77, B, L)
+    inp = {k: v.to(dev) for k, v in host.items()}
+    a = (inp['aa'], inp['res_nb'], inp['chain_nb'], inp['pos_atoms'], inp['mask_atoms'], inp['context_mask'], inp['context_mask'])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(max(args.warmup, 3)):
+        z = mod(*a)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(0)
+    steps = max(args.steps, 5)
+    tot = 0.0
+    for _ in range(steps):
+        flush.zero_()                                      # L2 flush between timed iterations (256 MiB > 126 MB L2)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        z = mod(*a)
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    ms = tot / steps
+    ck = clocks.stop()
+    assert torch.isfinite(z).all()
+    # CPU: the oracle (= the reference's evaluation order, bit-equal to it) on one complex, all host threads
+    cpu = None
+    if not args.no_cpu_baseline:
+        Wc = W
+        one = {k: v[:1] for k, v in host.items()}
+        ac = (one['aa'], one['res_nb'], one['chain_nb'], one['pos_atoms'], one['mask_atoms'], one['context_mask'], one['context_mask'])
+        PE.pair_embedding(Wc, *ac)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            PE.pair_embedding(Wc, *ac)
+        dt = (time.perf_counter() - t0) / reps
+        cpu = {'value': L * L / dt, 'unit': 'pairs/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+               'sample': f'one complex (L={L}, A={A}) x {reps} calls, {dt:.2f} s per call'}
+    peak, peak_src = measured_peak_gbs()
+    pairs = B * L * L
+    alg = pairs * 64 * 4 + B * L * (A * 13 + 3 * 8 + 2)                         # pair_feat written once + the per-residue inputs
+    flops = pairs * 2 * 64 * (A * A + 64 + 64 + 26 + 64 + 64)                  # the five dense layers as executed (tables pre-multiplied)
+    print(json.dumps({'metric': 'pair featurisation pairs/sec (PairEmbedding.forward)', 'value': pairs / (ms / 1e3), 'unit': 'pairs/s',
+                      'n_gpus': 1, 'steps': steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True,
+                      'dtype': 'f32', 'data': 'synthetic',
+                      'config': {'workload': f'F1 PairEmbedding.forward: B={B}, L={L}, {A} atoms per residue, structure + sequence masks',
+                                 'l2': 'flushed between timed iterations (256 MiB memset)'},
+                      'clocks': ck, 'gpu_launches': steps,
+                      'roofline': {'bound': 'hbm', 'achieved': alg / (ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                                   'frac': alg / (ms * 1e-3) / 1e9 / peak, 'peak_source': peak_src, 'traffic': None,
+                                   'note': 'FP32 CUDA-core bound, not HBM bound: the MLP is 65 kflop per pair',
+                                   'fp32_tflops': flops / (ms * 1e-3) / 1e12},
+                      'cpu_baseline': cpu}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--config', default='c2', choices=sorted(CONFIGS) + ['c5'])
+    ap.add_argument('--config', default='c2', choices=sorted(CONFIGS) + ['c5', 'f1'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.config == 'c5':
         if not torch.cuda.is_available():
             raise SystemExit('bench.py --config c5 needs a CUDA device (there is no CPU fallback)')
         run_train_forward(args)
+        return
+    if args.config == 'f1':
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py --config f1 needs a CUDA device (there is no CPU fallback)')
+        run_pair_embed(args)
         return
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get('RANK', 0))

@@ -235,6 +235,30 @@ int abopt_loss_forward(abopt_model* m, int N, int L, const float* v_0, const flo
                        const uint8_t* mask_res, uint32_t flags, const int64_t* t, uint64_t seed,
                        const abopt_step_noise* noise, float* losses_out, void* stream);
 
+/* ------------------------------------------------------------------ pair featurisation (the step before the loop)
+ * PairEmbedding, modules/encoders/pair.py:10-101 (AbDesign: diffab/modules/encoders/pair.py, same lines), including
+ * pairwise_dihedrals (modules/common/geometry.py:351-376) and AngularEncoding (modules/common/layers.py:85-106): builds
+ * pair_feat (N,L,L,64), the loop-invariant `z` every GABlock streams.  Its own handle because it is a separate module of
+ * DiffusionAntibodyDesign (models/diffab.py:28, state-dict prefix "pair_embed.").
+ *   create      PairEmbedding.__init__(feat_dim=64, max_num_atoms) with max_aa_types=22, max_relpos=32 (pair.py:12);
+ *               max_num_atoms = 15 ('full'), 5 ('backbone+CB') or 4 ('backbone') (models/diffab.py:13-17)
+ *   set_tensor  one float32 tensor of PairEmbedding.state_dict(), by key: aa_pair_embed.weight (484,64), relpos_embed.weight
+ *               (65,64), aapair_to_distcoef.weight (484,A*A), distance_embed.{0,2}.{weight,bias}, dihedral_embed.freq_bands (6),
+ *               out_mlp.{0,2,4}.{weight,bias}; out_mlp.0.weight is (64, 218)
+ *   forward     PairEmbedding.forward (pair.py:37-101).  DEVICE pointers: aa, res_nb, chain_nb (N,L) i64; pos_atoms
+ *               (N,L,num_atoms_in,3) f32 in Angstrom and mask_atoms (N,L,num_atoms_in) u8 with num_atoms_in >= max_num_atoms
+ *               (the first max_num_atoms atoms are used, pair.py:54-55); structure_mask / sequence_mask (N,L) u8 or NULL;
+ *               pair_feat (N,L,L,64) f32 out.  Enqueues one kernel on `stream`, never synchronises.  Amino-acid indices
+ *               outside [0, 22) are clamped (the reference's embedding lookup would raise). */
+typedef struct abopt_pair_embed abopt_pair_embed;
+int  abopt_pair_embed_create(int max_num_atoms, int device, abopt_pair_embed** out);
+void abopt_pair_embed_destroy(abopt_pair_embed* pe);
+int  abopt_pair_embed_set_tensor(abopt_pair_embed* pe, const char* key, const float* data, size_t numel, int on_device);
+int  abopt_pair_embed_finalize(abopt_pair_embed* pe);
+int  abopt_pair_embed_forward(abopt_pair_embed* pe, int N, int L, int num_atoms_in, const int64_t* aa, const int64_t* res_nb,
+                              const int64_t* chain_nb, const float* pos_atoms, const uint8_t* mask_atoms,
+                              const uint8_t* structure_mask, const uint8_t* sequence_mask, float* pair_feat, void* stream);
+
 /* Size in bytes of the device scratch the model holds for (N, L); 0 if none allocated yet. */
 size_t abopt_workspace_bytes(const abopt_model* m);
 

@@ -54,7 +54,7 @@ def synthetic_complex(seed, N, L, num_atoms_in=15, ragged=True, dtype=torch.floa
     chain_nb = torch.zeros(N, L, dtype=torch.long)
     res_nb = torch.zeros(N, L, dtype=torch.long)
     for n in range(N):
-        cuts = sorted(torch.randint(1, L, (2,), generator=g).tolist())
+        cuts = sorted(torch.randint(1, max(L, 2), (2,), generator=g).tolist())
         chain_nb[n, cuts[0]:] += 1
         chain_nb[n, cuts[1]:] += 1
         start = 0
