@@ -7,12 +7,12 @@ reference's module interface.  There is no CPU fallback.
 from . import _capi
 from ._capi import AboptError, launch_count
 from .modules.encoders.ga import GABlock, GAEncoder
-from .modules.encoders.pair import PairEmbedding
+from .modules.encoders.pair import PairEmbedding, ResidueEmbedding
 from .modules.diffusion.dpm_full import EpsilonNet, FullDPM, FullDPMAbDesign
 from .modules.diffusion.transition import (VarianceSchedule, PositionTransition, RotationTransition,
                                            AminoacidCategoricalTransition)
 
-__all__ = ['GABlock', 'GAEncoder', 'PairEmbedding', 'EpsilonNet', 'FullDPM', 'FullDPMAbDesign', 'VarianceSchedule',
+__all__ = ['GABlock', 'GAEncoder', 'PairEmbedding', 'ResidueEmbedding', 'EpsilonNet', 'FullDPM', 'FullDPMAbDesign', 'VarianceSchedule',
            'PositionTransition', 'RotationTransition', 'AminoacidCategoricalTransition', 'AboptError',
            'launch_count', 'install_into_reference']
 
@@ -32,4 +32,5 @@ def install_into_reference(package='src'):
     ga.GAEncoder = GAEncoder
     ga.GABlock = GABlock
     importlib.import_module(f'{package}.modules.encoders.pair').PairEmbedding = PairEmbedding      # models/diffab.py:28
+    importlib.import_module(f'{package}.modules.encoders.residue').ResidueEmbedding = ResidueEmbedding  # models/diffab.py:27
     return dpm, ga

@@ -23,7 +23,8 @@ EXPORTS = (
     'abopt_pos_pred_noise_from_start', 'abopt_pos_denoise', 'abopt_seq_denoise', 'abopt_sample_device',
     'abopt_sample_host', 'abopt_workspace_bytes', 'abopt_sample_init', 'abopt_reverse_step', 'abopt_profile_enable', 'abopt_profile_collect', 'abopt_debug_gemm3x', 'abopt_debug_clocks',
     'abopt_loss_forward', 'abopt_pair_embed_create', 'abopt_pair_embed_destroy', 'abopt_pair_embed_set_tensor',
-    'abopt_pair_embed_finalize', 'abopt_pair_embed_forward',
+    'abopt_pair_embed_finalize', 'abopt_pair_embed_forward', 'abopt_res_embed_create', 'abopt_res_embed_destroy',
+    'abopt_res_embed_set_tensor', 'abopt_res_embed_finalize', 'abopt_res_embed_forward',
 )
 
 
@@ -87,6 +88,12 @@ def lib():
         L.abopt_pair_embed_set_tensor.argtypes = [vp, C.c_char_p, vp, C.c_size_t, ci]
         L.abopt_pair_embed_finalize.argtypes = [vp]
         L.abopt_pair_embed_forward.argtypes = [vp, ci, ci, ci] + [vp] * 9
+        L.abopt_res_embed_create.argtypes = [ci, ci, C.POINTER(C.c_void_p)]
+        L.abopt_res_embed_destroy.argtypes = [vp]
+        L.abopt_res_embed_destroy.restype = None
+        L.abopt_res_embed_set_tensor.argtypes = [vp, C.c_char_p, vp, C.c_size_t, ci]
+        L.abopt_res_embed_finalize.argtypes = [vp]
+        L.abopt_res_embed_forward.argtypes = [vp, ci, ci, ci] + [vp] * 10
         _lib = L
     return _lib
 

@@ -62,7 +62,7 @@ __host__ __device__ inline int pe_smem_floats(int A2) {
          + PE_KC * 64 + 4096 + PE_ANG * 64               // g chunk (aliased by hA), hB, angle features
          + ((PE_AA * A2 + 3) & ~3)                        // coefficient rows of aa_i
          + PE_TILE * PE_MAXA * 3 + 48                     // key atoms, query atoms
-         + 6 * PE_TILE;                                   // per-pair ints
+         + 6 * PE_TILE + ((A2 + 3) & ~3);                 // per-pair ints, entry -> atom table
 }
 
 // acc[r][c] += sum_k act[k][pg*4 + r] * W[k][og*4 + c]
@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(PE_THREADS, 1) pair_embed_kernel(PairEmbedW w,
   int* sOk = sKeep + PE_TILE;                      // [64] has_CA_i & has_CA_j (& j < L)
   int* sBitsJ = sOk + PE_TILE;                     // [64] atom mask of the key, one bit per atom
   int* sMisc = sBitsJ + PE_TILE;                   // [64] scalars of the query residue
+  int* sAB = sMisc + PE_TILE;                      // [A2] atom indices of distance entry e = ia * A + ib (see the distance phase)
 
   const int tid = threadIdx.x;
   const int pg = tid & 15, og = tid >> 4;          // GEMM phases: 4 pairs x 4 channels per thread
@@ -167,6 +168,10 @@ __global__ void __launch_bounds__(PE_THREADS, 1) pair_embed_kernel(PairEmbedW w,
   for (int i = tid; i < 4 * 4096; i += PE_THREADS) sW64[i] = w.W64[i];
   for (int i = tid; i < PE_ANG * 64; i += PE_THREADS) sW1h[i] = w.W1h[i];
   for (int i = tid; i < 5 * 64; i += PE_THREADS) sBias[i] = w.bias[i];
+  for (int e = tid; e < A2; e += PE_THREADS) {
+    const int ia = e / A, ib = e - ia * A;
+    sAB[e] = (ia * 3) | ((ib * 3) << 8) | (ia << 16) | (ib << 24);
+  }
 
   const int n_tiles = (L + PE_TILE - 1) / PE_TILE;
   const long long rows = (long long)a.N * L;
@@ -222,20 +227,23 @@ __global__ void __launch_bounds__(PE_THREADS, 1) pair_embed_kernel(PairEmbedW w,
       }
       __syncthreads();
 
-      // ---- inter-residue dihedrals + angular encoding (threads 0..127: one angle of one pair each)
-      if (tid < 2 * PE_TILE) {
-        const int p = tid & 63, which = tid >> 6;
+      // ---- inter-residue dihedrals + angular encoding: every thread evaluates the angle of (pair, phi|psi); the two halves
+      //      of the CTA split the six frequencies between them
+      {
+        const int p = tid & 63, which = (tid >> 6) & 1, half = tid >> 7;
         const float* Ni = sPosI; const float* CAi = sPosI + 3; const float* Ci = sPosI + 6;
         const float* Nj = sPosJ + p * (A * 3); const float* CAj = Nj + 3; const float* Cj = Nj + 6;
-        float x = which == 0 ? dihedral(Ci, Nj, CAj, Cj) : dihedral(Ni, CAi, Ci, Nj);   // geometry.py:362-373
-        const float s = sKeep[p] ? 1.f : 0.f;                                           // pair.py:92-94
+        const float x = which == 0 ? dihedral(Ci, Nj, CAj, Cj) : dihedral(Ni, CAi, Ci, Nj);   // geometry.py:362-373
+        const float s = sKeep[p] ? 1.f : 0.f;                                                 // pair.py:92-94
         float* dst = sAng + which * 13 * 64 + p;
-        dst[0] = x * s;
+        if (half == 0) dst[0] = x * s;
 #pragma unroll
-        for (int f = 0; f < 6; ++f) {
-          const float xf = x * w.freq[f];
-          dst[(1 + f) * 64] = sinf(xf) * s;
-          dst[(7 + f) * 64] = cosf(xf) * s;
+        for (int f = 0; f < 3; ++f) {
+          const int ff = half * 3 + f;
+          float sn, cs;
+          sincosf(x * w.freq[ff], &sn, &cs);
+          dst[(1 + ff) * 64] = sn * s;
+          dst[(7 + ff) * 64] = cs * s;
         }
       }
 
@@ -244,16 +252,22 @@ __global__ void __launch_bounds__(PE_THREADS, 1) pair_embed_kernel(PairEmbedW w,
       zero_acc(acc);
       for (int e0 = 0; e0 < A2; e0 += PE_KC) {
         const int ne = min(PE_KC, A2 - e0);
-        for (int k = tid; k < ne * PE_TILE; k += PE_THREADS) {
-          const int p = k & 63, e = e0 + (k >> 6);
-          const int ia = e / A, ib = e - ia * A;
-          const float* xi = sPosI + ia * 3;
-          const float* xj = sPosJ + p * (A * 3) + ib * 3;
-          const float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
-          const float d = sqrtf(dx * dx + dy * dy + dz * dz) / 10.f;                    // angstrom_to_nm, pair.py:77
-          const float cf = sCoef[sAaJ[p] * A2 + e];
-          const bool on = ((bits_i >> ia) & 1) && ((sBitsJ[p] >> ib) & 1);
-          sG[(k >> 6) * 64 + p] = on ? expf(-cf * (d * d)) : 0.f;                       // pair.py:82-84
+        {  // thread = (pair p, entry slot tid >> 6); entries e0 + slot, + 4, + 8, ...: independent chains, no integer division
+          const int p = tid & 63;
+          const float* xjb = sPosJ + p * (A * 3);
+          const float* cfp = sCoef + sAaJ[p] * A2 + e0;
+          const int bits_j = sBitsJ[p];
+#pragma unroll 4
+          for (int el = tid >> 6; el < ne; el += 4) {
+            const int ab = sAB[e0 + el];                                                  // ia * 3 | ib * 3 << 8 | ia << 16 | ib << 24
+            const float* xi = sPosI + (ab & 255);
+            const float* xj = xjb + ((ab >> 8) & 255);
+            const float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
+            // (|x_ia - x_jb| / 10)^2 (angstrom_to_nm, then squared; pair.py:77-82)
+            const float d2 = (dx * dx + dy * dy + dz * dz) * 0.01f;
+            const bool on = ((bits_i >> ((ab >> 16) & 255)) & 1) && ((bits_j >> (ab >> 24)) & 1);
+            sG[el * 64 + p] = on ? expf(-cfp[el] * d2) : 0.f;                             // pair.py:82-84
+          }
         }
         __syncthreads();
         tile_gemm<5>(acc, sG, sWd1 + e0 * 64, ne, pg, og);

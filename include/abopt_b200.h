@@ -259,6 +259,24 @@ int  abopt_pair_embed_forward(abopt_pair_embed* pe, int N, int L, int num_atoms_
                               const int64_t* chain_nb, const float* pos_atoms, const uint8_t* mask_atoms,
                               const uint8_t* structure_mask, const uint8_t* sequence_mask, float* pair_feat, void* stream);
 
+/* ResidueEmbedding, modules/encoders/residue.py:9-94 (state-dict prefix "residue_embed.", models/diffab.py:27): builds res_feat
+ * (N,L,128) from the amino-acid type, the atom coordinates in the residue's own backbone frame (construct_3d_basis /
+ * global_to_local, modules/common/geometry.py:47-69,94-113), the backbone dihedrals (geometry.py:307-348, topology.py:5-24)
+ * and the fragment type.  Same life cycle as abopt_pair_embed_*.
+ *   set_tensor  keys of ResidueEmbedding.state_dict(): aatype_embed.weight (22,128), type_embed.weight (10,128),
+ *               dihed_embed.freq_bands (6), mlp.0.weight (256, 128 + 22*A*3 + 39 + 128), mlp.{2,4,6}.weight, mlp.{0,2,4,6}.bias
+ *   forward     ResidueEmbedding.forward (residue.py:27-94); arguments as abopt_pair_embed_forward plus fragment_type (N,L) i64
+ *               (clamped to [0, 10)); res_feat (N,L,128) f32 out. */
+typedef struct abopt_res_embed abopt_res_embed;
+int  abopt_res_embed_create(int max_num_atoms, int device, abopt_res_embed** out);
+void abopt_res_embed_destroy(abopt_res_embed* re);
+int  abopt_res_embed_set_tensor(abopt_res_embed* re, const char* key, const float* data, size_t numel, int on_device);
+int  abopt_res_embed_finalize(abopt_res_embed* re);
+int  abopt_res_embed_forward(abopt_res_embed* re, int N, int L, int num_atoms_in, const int64_t* aa, const int64_t* res_nb,
+                             const int64_t* chain_nb, const float* pos_atoms, const uint8_t* mask_atoms,
+                             const int64_t* fragment_type, const uint8_t* structure_mask, const uint8_t* sequence_mask,
+                             float* res_feat, void* stream);
+
 /* Size in bytes of the device scratch the model holds for (N, L); 0 if none allocated yet. */
 size_t abopt_workspace_bytes(const abopt_model* m);
 

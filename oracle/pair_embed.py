@@ -142,3 +142,74 @@ def pair_embedding(W, aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mas
     h = torch.relu(lin('out_mlp.2', h))
     h = lin('out_mlp.4', h)
     return h * pair_ok[..., None]                                                                  # pair.py:99
+
+
+# ------------------------------------------------------------------------------------------ per-residue features
+def make_residue_state_dict(seed=0, num_atoms=15, feat_dim=128):
+    """Seeded synthetic ResidueEmbedding.state_dict() (encoders/residue.py:11-25): keys and shapes of the reference."""
+    rs = np.random.RandomState(seed)
+    f32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))
+    W = {'aatype_embed.weight': f32(rs.standard_normal((MAX_AA, feat_dim))),
+         'dihed_embed.freq_bands': f32([1, 2, 3, 1.0, 1.0 / 2, 1.0 / 3]),
+         'type_embed.weight': f32(rs.standard_normal((10, feat_dim)))}
+    W['type_embed.weight'][0] = 0                                       # padding_idx=0 (residue.py:17)
+    dims = [feat_dim + MAX_AA * num_atoms * 3 + 39 + feat_dim, 2 * feat_dim, feat_dim, feat_dim, feat_dim]
+    for i in range(4):
+        b = 1.0 / math.sqrt(dims[i])
+        W[f'mlp.{2 * i}.weight'] = f32(rs.uniform(-b, b, (dims[i + 1], dims[i])))
+        W[f'mlp.{2 * i}.bias'] = f32(rs.uniform(-b, b, (dims[i + 1],)))
+    return W
+
+
+def backbone_frames(ca, c, n):
+    """construct_3d_basis, geometry.py:47-69: Gram-Schmidt on (C - CA, N - CA), columns e1 e2 e3; normalisation with +1e-6."""
+    e1 = c - ca
+    e1 = e1 / (torch.linalg.norm(e1, dim=-1, keepdim=True) + 1e-6)
+    v2 = n - ca
+    u2 = v2 - (e1 * v2).sum(-1, keepdim=True) * e1
+    e2 = u2 / (torch.linalg.norm(u2, dim=-1, keepdim=True) + 1e-6)
+    return torch.stack([e1, e2, torch.linalg.cross(e1, e2, dim=-1)], dim=-1)
+
+
+def backbone_dihedrals(pos_atoms, chain_nb, res_nb, mask):
+    """get_backbone_dihedral_angles, geometry.py:307-348 with topology.py:5-24: omega / phi need a bonded predecessor,
+    psi a bonded successor; bonded(i, i+1) = |res_nb step| == 1, same chain, mask[i]."""
+    n, ca, c = pos_atoms[:, :, ATOM_N], pos_atoms[:, :, ATOM_CA], pos_atoms[:, :, ATOM_C]
+    bonded = ((res_nb[:, 1:] - res_nb[:, :-1]).abs() == 1) & (chain_nb[:, 1:] == chain_nb[:, :-1]) & mask[:, :-1]
+    pad = torch.zeros_like(mask[:, :1])
+    has_prev, has_next = torch.cat([pad, bonded], 1), torch.cat([bonded, pad], 1)
+    zero = torch.zeros_like(ca[:, :1, 0])
+    omega = torch.cat([zero, _dihedral(ca[:, :-1], c[:, :-1], n[:, 1:], ca[:, 1:])], 1)
+    phi = torch.cat([zero, _dihedral(c[:, :-1], n[:, 1:], ca[:, 1:], c[:, 1:])], 1)
+    psi = torch.cat([_dihedral(n[:, :-1], ca[:, :-1], c[:, :-1], n[:, 1:]), zero], 1)
+    valid = torch.stack([has_prev, has_prev, has_next], -1)
+    return torch.stack([omega, phi, psi], -1) * valid, valid
+
+
+def residue_embedding(W, aa, res_nb, chain_nb, pos_atoms, mask_atoms, fragment_type, structure_mask=None, sequence_mask=None):
+    """ResidueEmbedding.forward, encoders/residue.py:27-94 -> (N, L, 128)."""
+    lin = lambda name, x: torch.nn.functional.linear(x, W[name + '.weight'], W[name + '.bias'])
+    A = (W['mlp.0.weight'].shape[1] - 2 * W['aatype_embed.weight'].shape[1] - 39) // (3 * MAX_AA)
+    N, L = aa.shape
+    has_ca = mask_atoms[:, :, ATOM_CA]
+    pos_atoms, mask_atoms = pos_atoms[:, :, :A], mask_atoms[:, :, :A]                              # residue.py:43-44
+    if sequence_mask is not None:                                                                  # residue.py:47-49
+        aa = torch.where(sequence_mask, aa, torch.full_like(aa, UNK))
+    f_aa = W['aatype_embed.weight'][aa]
+    ca = pos_atoms[:, :, ATOM_CA]
+    R = backbone_frames(ca, pos_atoms[:, :, ATOM_C], pos_atoms[:, :, ATOM_N])                       # residue.py:53-58
+    local = torch.einsum('nlkc,nlak->nlac', R, pos_atoms - ca[:, :, None, :])                       # R^T (x - t), geometry.py:94-113
+    local = local * mask_atoms[..., None]                                                           # residue.py:60-61
+    slot = torch.nn.functional.one_hot(aa, MAX_AA).to(local.dtype)                                  # residue.py:63-68
+    f_crd = (slot[:, :, :, None, None] * local[:, :, None, :, :]).reshape(N, L, MAX_AA * A * 3)
+    if structure_mask is not None:
+        f_crd = f_crd * structure_mask[:, :, None]                                                  # residue.py:69-71
+    ang, valid = backbone_dihedrals(pos_atoms, chain_nb, res_nb, has_ca)                            # residue.py:74
+    f_ang = (angular_encoding(ang[..., None], W['dihed_embed.freq_bands']).reshape(N, L, 3, 13) * valid[..., None]).reshape(N, L, 39)
+    if structure_mask is not None:                                                                  # residue.py:77-86
+        near = structure_mask & torch.roll(structure_mask, 1, 1) & torch.roll(structure_mask, -1, 1)
+        f_ang = f_ang * near[:, :, None]
+    h = torch.cat([f_aa, f_crd, f_ang, W['type_embed.weight'][fragment_type]], dim=-1)              # residue.py:89-92
+    for i in range(3):
+        h = torch.relu(lin(f'mlp.{2 * i}', h))
+    return lin('mlp.6', h) * has_ca[:, :, None]                                                     # residue.py:93

@@ -75,7 +75,17 @@ def make_pair_embed():
         args = (inp['aa'], inp['res_nb'], inp['chain_nb'], inp['pos_atoms'], inp['mask_atoms'])
         keep[f'z_a{A}_plain'] = ref(*args)
         keep[f'z_a{A}_masked'] = ref(*args, structure_mask=inp['context_mask'], sequence_mask=inp['context_mask'])
-    npz('pair_embed.npz', seed_w=seed_w, seed_in=seed_in, N=N, L=L, **inp, **keep)
+    # ResidueEmbedding.forward (encoders/residue.py:27-94) on the same complexes
+    from src.modules.encoders.residue import ResidueEmbedding
+    ft = torch.randint(0, 4, (N, L), generator=torch.Generator().manual_seed(seed_in))
+    for A in (15, 5):
+        ref = ResidueEmbedding(128, A)
+        ref.load_state_dict(PE.make_residue_state_dict(seed_w + 1, A), strict=True)
+        ref.eval()
+        args = (inp['aa'], inp['res_nb'], inp['chain_nb'], inp['pos_atoms'], inp['mask_atoms'], ft)
+        keep[f'x_a{A}_plain'] = ref(*args)
+        keep[f'x_a{A}_masked'] = ref(*args, structure_mask=inp['context_mask'], sequence_mask=inp['context_mask'])
+    npz('pair_embed.npz', seed_w=seed_w, seed_in=seed_in, N=N, L=L, fragment_type=ft, **inp, **keep)
 
 
 @torch.no_grad()

@@ -105,3 +105,55 @@ def test_full_size_properties():
     has_ca = inp['mask_atoms'][:, :, 1].to(DEV)
     assert (z[~has_ca] == 0).all()
     assert torch.isfinite(z).all()
+
+
+# ------------------------------------------------------------------------------------------ ResidueEmbedding
+def build_res(W, A):
+    m = ab_opt_b200.ResidueEmbedding(128, A)
+    m.load_state_dict(W, strict=True)
+    return m.to(DEV).eval()
+
+
+def run_res(mod, inp, ft, sm=None, qm=None):
+    c = {k: v.to(DEV) for k, v in inp.items()}
+    return mod(c['aa'], c['res_nb'], c['chain_nb'], c['pos_atoms'], c['mask_atoms'], ft.to(DEV),
+               None if sm is None else sm.to(DEV), None if qm is None else qm.to(DEV))
+
+
+def check_res(got, W, inp, ft, sm, qm):
+    def orc(dtype):
+        Wd = {k: v.to(dtype) for k, v in W.items()}
+        return PE.residue_embedding(Wd, inp['aa'], inp['res_nb'], inp['chain_nb'], inp['pos_atoms'].to(dtype), inp['mask_atoms'], ft, sm, qm)
+    x32, x64 = orc(torch.float32), orc(torch.float64)
+    e_got = (got.cpu().double() - x64).abs().max().item()
+    e_ref = (x32.double() - x64).abs().max().item()
+    assert e_got <= 2 * e_ref + 2e-6, f'cuda err {e_got:.3e}, oracle fp32 err {e_ref:.3e}'
+    assert (got.cpu()[~inp['mask_atoms'][:, :, 1]] == 0).all()                                   # residue.py:93
+
+
+@pytest.mark.parametrize('A', [15, 5])
+@pytest.mark.parametrize('masked', [False, True])
+def test_residue_against_reference_fixture(golden_dir, A, masked):
+    d = np.load(os.path.join(golden_dir, 'pair_embed.npz'))
+    g = {k: torch.from_numpy(d[k]) if d[k].ndim else d[k].item() for k in d.files}
+    W = PE.make_residue_state_dict(g['seed_w'] + 1, A)
+    inp = {k: g[k] for k in ('aa', 'res_nb', 'chain_nb', 'pos_atoms', 'mask_atoms')}
+    m = g['context_mask'] if masked else None
+    got = run_res(build_res(W, A), inp, g['fragment_type'], m, m)
+    torch.testing.assert_close(got.cpu(), g[f'x_a{A}_' + ('masked' if masked else 'plain')], rtol=1e-4, atol=2e-6)
+    check_res(got, W, inp, g['fragment_type'], m, m)
+
+
+@pytest.mark.parametrize('A,N,L', [(15, 3, 101), (4, 2, 7), (15, 1, 1), (5, 64, 256)])
+def test_residue_against_oracle(A, N, L):
+    """Row counts that are not multiples of the four-residue CTA pass, chain breaks and numbering gaps (termini), a residue
+    without CA, padding, structure-only and sequence-only masks; the last case is the C2 batch."""
+    W = PE.make_residue_state_dict(6, A)
+    inp = PE.synthetic_complex(40 + L, N, L)
+    ft = torch.randint(0, 10, (N, L), generator=torch.Generator().manual_seed(L))
+    mod = build_res(W, A)
+    m = inp['context_mask']
+    check_res(run_res(mod, inp, ft, m, None), W, inp, ft, m, None)
+    check_res(run_res(mod, inp, ft, None, m), W, inp, ft, None, m)
+    a, b = run_res(mod, inp, ft, m, m), run_res(mod, inp, ft, m, m)
+    assert torch.equal(a, b)

@@ -180,3 +180,17 @@ def test_pair_embedding_matches_reference(golden_dir, A, masked):
     # (geometry.py:268 with p0 == p3), i.e. rounding noise in the reference itself; +-0.0014 rad moves z by < 1e-3
     torch.testing.assert_close(z, ref, rtol=0, atol=2e-3)
     assert (z[~inp['mask_atoms'][:, :, 1]] == 0).all()
+
+
+@pytest.mark.parametrize('A', [15, 5])
+@pytest.mark.parametrize('masked', [False, True])
+def test_residue_embedding_matches_reference(golden_dir, A, masked):
+    """oracle.pair_embed.residue_embedding vs ResidueEmbedding.forward of the unmodified reference (same fixture file)."""
+    from oracle import pair_embed as PE
+    g = load(golden_dir, 'pair_embed.npz')
+    W = PE.make_residue_state_dict(g['seed_w'] + 1, A)
+    inp = PE.synthetic_complex(g['seed_in'], g['N'], g['L'])
+    m = inp['context_mask'] if masked else None
+    x = PE.residue_embedding(W, inp['aa'], inp['res_nb'], inp['chain_nb'], inp['pos_atoms'], inp['mask_atoms'], g['fragment_type'], m, m)
+    torch.testing.assert_close(x, g[f'x_a{A}_' + ('masked' if masked else 'plain')], rtol=1e-5, atol=1e-6)
+    assert (x[~inp['mask_atoms'][:, :, 1]] == 0).all()

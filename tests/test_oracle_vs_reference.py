@@ -160,3 +160,31 @@ def test_pair_embedding_trained_weights(ckpt, A):
         off = ~torch.eye(32, dtype=torch.bool)[None, :, :, None]
         torch.testing.assert_close(got * off, want * off, rtol=1e-5, atol=1e-5)
         torch.testing.assert_close(got, want, rtol=0, atol=5e-3)
+
+
+@torch.no_grad()
+@pytest.mark.parametrize('ckpt,A', [('dock_single_cdr/250000.pt', 15), ('seq_design/300000.pt', 5)])
+def test_residue_embedding_trained_weights(ckpt, A):
+    """oracle residue_embedding vs the reference ResidueEmbedding (encoders/residue.py:27-94) with the shipped `residue_embed.*` weights."""
+    path = os.path.join(REF_ROOT, 'AbDock/reproduction', ckpt)
+    if not os.path.exists(path):
+        pytest.skip('checkpoint missing')
+    if os.path.join(REF_ROOT, 'AbDock') not in sys.path:
+        sys.path.insert(0, os.path.join(REF_ROOT, 'AbDock'))
+    from src.modules.encoders.residue import ResidueEmbedding
+    from oracle import pair_embed as PE
+    _load_ckpt_state(path)
+    ck = torch.load(path, map_location='cpu', weights_only=False)
+    W = {k[len('residue_embed.'):]: v for k, v in ck['model'].items() if k.startswith('residue_embed.')}
+    proto = PE.make_residue_state_dict(0, A)
+    assert set(W) == set(proto) and all(W[k].shape == v.shape for k, v in proto.items())
+    ref = ResidueEmbedding(128, A)
+    ref.load_state_dict(W, strict=True)
+    ref.eval()
+    inp = PE.synthetic_complex(9, 2, 32)
+    ft = torch.randint(0, 4, (2, 32), generator=torch.Generator().manual_seed(9))
+    m = inp['context_mask']
+    args = (inp['aa'], inp['res_nb'], inp['chain_nb'], inp['pos_atoms'], inp['mask_atoms'], ft)
+    for sm, qm in ((None, None), (m, m), (m, None)):
+        torch.testing.assert_close(PE.residue_embedding(W, *args, sm, qm), ref(*args, structure_mask=sm, sequence_mask=qm),
+                                   rtol=1e-5, atol=1e-5)
