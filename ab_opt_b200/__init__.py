@@ -8,11 +8,14 @@ from . import _capi
 from ._capi import AboptError, launch_count
 from .modules.encoders.ga import GABlock, GAEncoder
 from .modules.encoders.pair import PairEmbedding, ResidueEmbedding
+from . import post
+from .post import reconstruct_backbone_partially, calc_per_rmsd, calc_avg_rmsd, rank_commoness
 from .modules.diffusion.dpm_full import EpsilonNet, FullDPM, FullDPMAbDesign
 from .modules.diffusion.transition import (VarianceSchedule, PositionTransition, RotationTransition,
                                            AminoacidCategoricalTransition)
 
-__all__ = ['GABlock', 'GAEncoder', 'PairEmbedding', 'ResidueEmbedding', 'EpsilonNet', 'FullDPM', 'FullDPMAbDesign', 'VarianceSchedule',
+__all__ = ['GABlock', 'GAEncoder', 'PairEmbedding', 'ResidueEmbedding', 'reconstruct_backbone_partially', 'calc_per_rmsd', 'calc_avg_rmsd',
+           'rank_commoness', 'EpsilonNet', 'FullDPM', 'FullDPMAbDesign', 'VarianceSchedule',
            'PositionTransition', 'RotationTransition', 'AminoacidCategoricalTransition', 'AboptError',
            'launch_count', 'install_into_reference']
 
@@ -33,4 +36,14 @@ def install_into_reference(package='src'):
     ga.GABlock = GABlock
     importlib.import_module(f'{package}.modules.encoders.pair').PairEmbedding = PairEmbedding      # models/diffab.py:28
     importlib.import_module(f'{package}.modules.encoders.residue').ResidueEmbedding = ResidueEmbedding  # models/diffab.py:27
+    # after the loop: geometry.reconstruct_backbone_partially with the reference's own ideal-backbone tables; the ranking helpers
+    # live in a runner module that needs lmdb / BioPython, so they are rebound only where that module imports
+    K = importlib.import_module(f'{package}.utils.protein.constants')
+    post.set_backbone_tables(K.backbone_atom_coordinates_tensor, K.bb_oxygen_coordinate_tensor)
+    importlib.import_module(f'{package}.modules.common.geometry').reconstruct_backbone_partially = reconstruct_backbone_partially
+    try:
+        runner = importlib.import_module(f'{package}.tools.runner.design_for_testset')
+        runner.calc_per_rmsd, runner.calc_avg_rmsd, runner.rank_commoness = calc_per_rmsd, calc_avg_rmsd, rank_commoness
+    except ImportError:
+        pass
     return dpm, ga

@@ -25,6 +25,7 @@ EXPORTS = (
     'abopt_loss_forward', 'abopt_pair_embed_create', 'abopt_pair_embed_destroy', 'abopt_pair_embed_set_tensor',
     'abopt_pair_embed_finalize', 'abopt_pair_embed_forward', 'abopt_res_embed_create', 'abopt_res_embed_destroy',
     'abopt_res_embed_set_tensor', 'abopt_res_embed_finalize', 'abopt_res_embed_forward',
+    'abopt_reconstruct_backbone_partially', 'abopt_pairwise_rmsd', 'abopt_rank_commoness',
 )
 
 
@@ -94,6 +95,9 @@ def lib():
         L.abopt_res_embed_set_tensor.argtypes = [vp, C.c_char_p, vp, C.c_size_t, ci]
         L.abopt_res_embed_finalize.argtypes = [vp]
         L.abopt_res_embed_forward.argtypes = [vp, ci, ci, ci] + [vp] * 10
+        L.abopt_reconstruct_backbone_partially.argtypes = [ci, ci, ci] + [vp] * 13
+        L.abopt_pairwise_rmsd.argtypes = [ci, ci] + [vp] * 5
+        L.abopt_rank_commoness.argtypes = [ci, ci, vp, ci, vp, vp, vp]
         _lib = L
     return _lib
 

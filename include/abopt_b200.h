@@ -277,6 +277,24 @@ int  abopt_res_embed_forward(abopt_res_embed* re, int N, int L, int num_atoms_in
                              const int64_t* fragment_type, const uint8_t* structure_mask, const uint8_t* sequence_mask,
                              float* res_feat, void* stream);
 
+/* ------------------------------------------------------------------ after the loop (stateless, DEVICE pointers, current device)
+ * reconstruct_backbone_partially, modules/common/geometry.py:450-480 (reconstruct_backbone :404-447): residues flagged in
+ * mask_recons get ideal N, CA, C placed by their frame (R_new, t_new) and O placed after the psi turn, all other atoms zeroed
+ * and masked out; the other residues pass through.  N may be frames x complexes (a whole trajectory in one launch).
+ *   pos_ctx (N,L,A,3)  R_new (N,L,3,3)  t_new (N,L,3)  aa, chain_nb, res_nb (N,L) i64  mask_atoms (N,L,A) u8  mask_recons (N,L) u8
+ *   bb_table (21,3,3), o_table (21,3): backbone_atom_coordinates_tensor / bb_oxygen_coordinate_tensor (utils/protein/constants.py:310-320)
+ *   -> pos_new (N,L,A,3)  mask_new (N,L,A) u8 */
+int abopt_reconstruct_backbone_partially(int N, int L, int A, const float* pos_ctx, const float* R_new, const float* t_new,
+                                         const int64_t* aa, const int64_t* chain_nb, const int64_t* res_nb,
+                                         const uint8_t* mask_atoms, const uint8_t* mask_recons, const float* bb_table,
+                                         const float* o_table, float* pos_new, uint8_t* mask_new, void* stream);
+/* calc_per_rmsd / calc_avg_rmsd, tools/runner/design_for_testset.py:556-570: structures (B,M,3) -> rmsd (B,B) (may be NULL),
+ * score (B,) = row sums / (B-1) (the quantity rank_commoness sorts), avg (1,) = rmsd.sum() / (B (B-1)) (may be NULL). */
+int abopt_pairwise_rmsd(int B, int M, const float* structures, float* rmsd, float* score, float* avg, void* stream);
+/* rank_commoness, design_for_testset.py:573-589: rank (k,) i64 = indices of the k smallest scores, best first (ties: lower index
+ * first); score (B,) scratch/out. */
+int abopt_rank_commoness(int B, int M, const float* structures, int k, float* score, int64_t* rank, void* stream);
+
 /* Size in bytes of the device scratch the model holds for (N, L); 0 if none allocated yet. */
 size_t abopt_workspace_bytes(const abopt_model* m);
 

@@ -89,6 +89,35 @@ def make_pair_embed():
 
 
 @torch.no_grad()
+def make_post_loop():
+    """The steps after the loop: reconstruct_backbone_partially (geometry.py:450-480) and calc_per_rmsd /
+    rank_commoness (tools/runner/design_for_testset.py:556-589) of the unmodified reference.  The ideal backbone tables
+    (utils/protein/constants.py:310-320) are stored with the fixture: they are inputs of the C ABI."""
+    torch.set_num_threads(1)
+    ref_root = os.path.join(os.environ.get('ABOPT_REFERENCE', '/root/reference'), 'AbDock')
+    if ref_root not in sys.path:
+        sys.path.insert(0, ref_root)
+    from src.modules.common.geometry import reconstruct_backbone_partially
+    from src.utils.protein import constants as K
+    from refload import load_reference_functions
+    from oracle import pair_embed as PE, geometry as G
+    fn = load_reference_functions('src/tools/runner/design_for_testset.py', ['calc_per_rmsd', 'calc_avg_rmsd', 'rank_commoness'])
+    N, L = 2, 20
+    inp = PE.synthetic_complex(5, N, L)
+    g = torch.Generator().manual_seed(17)
+    v = torch.randn(N, L, 3, generator=g)
+    t = inp['pos_atoms'][:, :, 1] + torch.randn(N, L, 3, generator=g)
+    aa = torch.randint(0, 24, (N, L), generator=g)                  # beyond 20: clamped to UNK by the reference
+    rec = ~inp['context_mask']
+    pos_new, mask_new = reconstruct_backbone_partially(inp['pos_atoms'], G.so3_exp(v), t, aa, inp['chain_nb'], inp['res_nb'],
+                                                       inp['mask_atoms'], rec)
+    S = torch.randn(12, 30, 3, generator=g) * 3 + torch.randn(1, 30, 3, generator=g) * 10
+    npz('post_loop.npz', bb_table=K.backbone_atom_coordinates_tensor, o_table=K.bb_oxygen_coordinate_tensor, v=v, t=t, aa=aa,
+        mask_recons=rec, pos_new=pos_new, mask_new=mask_new, structures=S, rmsd=fn['calc_per_rmsd'](S),
+        avg_rmsd=fn['calc_avg_rmsd'](S), rank=fn['rank_commoness'](S, 5))
+
+
+@torch.no_grad()
 def main():
     torch.set_num_threads(1)          # single-thread reference: reproducible reduction order
     # ---------------------------------------------------------------- GABlock / GAEncoder
@@ -170,7 +199,10 @@ if __name__ == '__main__':
         make_train_forward()
     elif len(sys.argv) > 1 and sys.argv[1] == 'pair_embed':       # only the pair-featurisation fixture
         make_pair_embed()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'post_loop':
+        make_post_loop()
     else:
         main()
         make_train_forward()
         make_pair_embed()
+        make_post_loop()

@@ -38,3 +38,17 @@ def build_reference_fulldpm(W, num_layers=6, obj='pred_x0', num_bins=40):
     missing = model.load_state_dict(W, strict=True)
     model.eval()
     return model, m
+
+
+def load_reference_functions(rel_path, names):
+    """Compile the named top-level functions of a reference source file WITHOUT importing the module (the runner modules pull
+    in lmdb / Bio / pyrosetta, which are absent here).  The function bodies are the reference's, unmodified."""
+    import ast
+    import torch
+    path = os.path.join(ABDOCK, rel_path)
+    tree = ast.parse(open(path).read())
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert len(keep) == len(names), f'{names} not all found in {path}'
+    ns = {'torch': torch}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, 'exec'), ns)
+    return {n: ns[n] for n in names}

@@ -194,3 +194,18 @@ def test_residue_embedding_matches_reference(golden_dir, A, masked):
     x = PE.residue_embedding(W, inp['aa'], inp['res_nb'], inp['chain_nb'], inp['pos_atoms'], inp['mask_atoms'], g['fragment_type'], m, m)
     torch.testing.assert_close(x, g[f'x_a{A}_' + ('masked' if masked else 'plain')], rtol=1e-5, atol=1e-6)
     assert (x[~inp['mask_atoms'][:, :, 1]] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------ after the loop
+def test_post_loop_matches_reference(golden_dir):
+    """oracle.post vs reconstruct_backbone_partially / calc_per_rmsd / calc_avg_rmsd / rank_commoness of the reference."""
+    from oracle import post, pair_embed as PE
+    g = load(golden_dir, 'post_loop.npz')
+    inp = PE.synthetic_complex(5, 2, 20)
+    pos_new, mask_new = post.reconstruct_backbone_partially(inp['pos_atoms'], G.so3_exp(g['v']), g['t'], g['aa'], inp['chain_nb'],
+                                                            inp['res_nb'], inp['mask_atoms'], g['mask_recons'], g['bb_table'], g['o_table'])
+    torch.testing.assert_close(pos_new, g['pos_new'], rtol=1e-6, atol=1e-5)
+    assert torch.equal(mask_new, g['mask_new'])
+    torch.testing.assert_close(post.pairwise_rmsd(g['structures']), g['rmsd'], rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(post.average_rmsd(g['structures']), torch.tensor(g['avg_rmsd']), rtol=1e-6, atol=0)
+    assert torch.equal(post.rank_commonness(g['structures'], 5), g['rank'])

@@ -188,3 +188,30 @@ def test_residue_embedding_trained_weights(ckpt, A):
     for sm, qm in ((None, None), (m, m), (m, None)):
         torch.testing.assert_close(PE.residue_embedding(W, *args, sm, qm), ref(*args, structure_mask=sm, sequence_mask=qm),
                                    rtol=1e-5, atol=1e-5)
+
+
+@torch.no_grad()
+def test_post_loop_functions():
+    """oracle.post vs the reference's reconstruct_backbone_partially (geometry.py:450-480) and the ranking helpers of
+    tools/runner/design_for_testset.py:556-589 (compiled from the source file: the module itself needs lmdb / BioPython)."""
+    if os.path.join(REF_ROOT, 'AbDock') not in sys.path:
+        sys.path.insert(0, os.path.join(REF_ROOT, 'AbDock'))
+    from src.modules.common.geometry import reconstruct_backbone_partially
+    from src.utils.protein import constants as K
+    from refload import load_reference_functions
+    from oracle import post, pair_embed as PE
+    fn = load_reference_functions('src/tools/runner/design_for_testset.py', ['calc_per_rmsd', 'calc_avg_rmsd', 'rank_commoness'])
+    inp = PE.synthetic_complex(12, 3, 50)
+    g = torch.Generator().manual_seed(4)
+    R, t = G.so3_exp(torch.randn(3, 50, 3, generator=g)), torch.randn(3, 50, 3, generator=g) * 20
+    aa = torch.randint(0, 21, (3, 50), generator=g)
+    for rec in (~inp['context_mask'], torch.ones(3, 50, dtype=torch.bool)):
+        args = (inp['pos_atoms'], R, t, aa, inp['chain_nb'], inp['res_nb'], inp['mask_atoms'], rec)
+        want = reconstruct_backbone_partially(*args)
+        got = post.reconstruct_backbone_partially(*args, K.backbone_atom_coordinates_tensor, K.bb_oxygen_coordinate_tensor)
+        torch.testing.assert_close(got[0], want[0], rtol=1e-6, atol=1e-5)
+        assert torch.equal(got[1], want[1])
+    S = torch.randn(40, 25, 3, generator=g) * 2 + torch.randn(1, 25, 3, generator=g) * 10
+    torch.testing.assert_close(post.pairwise_rmsd(S), fn['calc_per_rmsd'](S), rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(post.average_rmsd(S), fn['calc_avg_rmsd'](S), rtol=1e-6, atol=0)
+    assert torch.equal(post.rank_commonness(S, 7), fn['rank_commoness'](S, 7))
