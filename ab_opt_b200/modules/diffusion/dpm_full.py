@@ -328,9 +328,17 @@ class FullDPM(nn.Module, _native.NativeOwner):
         reference's per-step .cpu() synchronisations (dpm_full.py:299-300)."""
         abdock = self.flavour == 'abdock'
         slots = list(range(T0, 0, -1)) if keep else [T0]
-        hv, hp, hs = tv[1:].cpu(), tp[1:].cpu(), ts[1:].cpu()              # slots 1..T0
-        hpr = tpr.cpu() if abdock else None
-        hpl = tpl.cpu() if abdock else None
+        # fresh PINNED host tensors (torch's caching host allocator recycles the blocks of dropped trajectories), asynchronous
+        # copies and one stream synchronisation: a pageable .cpu() of the 52 MB block goes through the driver's bounce buffer and
+        # first-touch page faults (10-50 ms per sample, and the source of the run-to-run scatter of the bench line)
+        def to_host(x):
+            h = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+            h.copy_(x, non_blocking=True)
+            return h
+        hv, hp, hs = to_host(tv[1:]), to_host(tp[1:]), to_host(ts[1:])      # slots 1..T0
+        hpr = to_host(tpr) if abdock else None
+        hpl = to_host(tpl) if abdock else None
+        torch.cuda.current_stream(tv.device).synchronize()
         traj = {}
         for t in slots:
             ent = [hv[t - 1], hp[t - 1], hs[t - 1]]
