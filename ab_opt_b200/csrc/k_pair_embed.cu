@@ -12,8 +12,11 @@
 //   o1 = relu(T_aa[aa_i aa_j] + same_chain T_rel[clamp(res_i - res_j)] + W1[:,128:192] h2 + W1[:,192:218] ang + b1)
 //        (the aa-pair and relative-position embeddings go through the first out_mlp layer as pre-multiplied tables)  pair.py:65-74,97-98
 //   o2 = relu(W2 o1 + b2), z = (W3 o2 + b3) * has_CA_i has_CA_j                                        pair.py:98-99
-// The five dense layers are 64-pair x 64-channel register-tiled FP32 FFMA GEMMs (4 x 4 per thread, weights resident in shared
-// memory as [k][out]); fp32 end to end because the parity target is the reference's fp32 output.
+// The five dense layers are 64-pair x 64-channel GEMMs on the warp-level tensor-core path (mma.sync m16n8k8 tf32, fp32
+// accumulate) as 3xTF32 (a b + a_lo b + a b_lo, operands split in registers) because the parity target is the reference's
+// fp32 output.  Weights stay resident in shared memory as [k][out] with the out index XOR-swizzled by (k & 3) << 3, activations
+// as [k][pair] with a leading dimension of 72, so that every fragment load is bank-conflict free.  (The FP32-FFMA version of
+// these phases was shared-memory-bandwidth bound: two LDS.128 per 16 FFMA)
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -30,7 +33,9 @@ int api_fail(int code, const std::string& msg);      // api.cu: sets abopt_last_
 namespace {
 constexpr int PE_THREADS = 256;
 constexpr int PE_TILE = 64;          // pairs per tile
-constexpr int PE_KC = 75;            // distance entries per chunk of the first layer's K loop
+constexpr int PE_KC = 80;            // distance entries per chunk of the first layer's K loop (multiple of 8)
+constexpr int PE_LD = 72;            // leading dimension of the [k][pair] activation buffers (64 pairs + 8: conflict-free fragments)
+constexpr int PE_ANGP = 32;          // angle features padded to a multiple of 8 (zero rows)
 constexpr int PE_MAXA = 15;          // max_num_heavyatoms (utils/protein/constants.py:143)
 constexpr int PE_AA = 22;            // max_aa_types (pair.py:12)
 constexpr int PE_RELPOS = 32;        // max_relpos (pair.py:12)
@@ -58,29 +63,62 @@ struct PairEmbedArgs {
 
 // smem carve-up (floats); the host computes the same total
 __host__ __device__ inline int pe_smem_floats(int A2) {
-  return A2 * 64 + 4 * 4096 + PE_ANG * 64 + 5 * 64      // weights
-         + PE_KC * 64 + 4096 + PE_ANG * 64               // g chunk (aliased by hA), hB, angle features
+  const int A2p = (A2 + 7) & ~7;
+  return A2p * 64 + 4 * 4096 + PE_ANGP * 64 + 5 * 64    // weights
+         + PE_KC * PE_LD + 64 * PE_LD + PE_ANGP * PE_LD  // g chunk (aliased by hA), hB, angle features
          + ((PE_AA * A2 + 3) & ~3)                        // coefficient rows of aa_i
          + PE_TILE * PE_MAXA * 3 + 48                     // key atoms, query atoms
-         + 6 * PE_TILE + ((A2 + 3) & ~3);                 // per-pair ints, entry -> atom table
+         + 6 * PE_TILE + A2p;                             // per-pair ints, entry -> atom table
 }
 
-// acc[r][c] += sum_k act[k][pg*4 + r] * W[k][og*4 + c]
-template <int UNROLL>
-__device__ __forceinline__ void tile_gemm(float (&acc)[4][4], const float* __restrict__ act, const float* __restrict__ W, int K, int pg, int og) {
-  const float4* a4 = reinterpret_cast<const float4*>(act) + pg;
-  const float4* w4 = reinterpret_cast<const float4*>(W) + og;
-#pragma unroll UNROLL
-  for (int k = 0; k < K; ++k) {
-    const float4 a = a4[k * 16];
-    const float4 w = w4[k * 16];
-    const float av[4] = {a.x, a.y, a.z, a.w};
-    const float wv[4] = {w.x, w.y, w.z, w.w};
+// ---- warp-level tensor-core GEMM pieces.  Warp w owns pairs [16 (w & 3), +16) x channels [32 (w >> 2), +32) of the 64 x 64 tile:
+// four m16n8 accumulators acc[nt][0..3] = (pair g, ch 2t), (pair g, ch 2t+1), (pair g+8, ch 2t), (pair g+8, ch 2t+1) with
+// g = lane >> 2, t = lane & 3 (the PTX fragment layout of mma.m16n8k8).
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void split3(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xFFFFE000u;                 // tf32-exact high part
+  lo = __float_as_uint(x - __uint_as_float(hi));         // remainder (the MMA reads its top 19 bits)
+}
+// acc += act[k][pair] W[k][ch] over k in [0, 8 * k8): act has leading dimension PE_LD, W is [k][64] with ch ^ ((k & 3) << 3)
+__device__ __forceinline__ void tile_mma(float (&acc)[4][4], const float* __restrict__ act, const float* __restrict__ W, int k8, int p0, int n0,
+                                         int g, int t) {
+  const float* ap = act + t * PE_LD + p0 + g;
+  const float* wp = W + t * 64;
+  int col[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+  for (int nt = 0; nt < 4; ++nt) col[nt] = (n0 + nt * 8 + g) ^ (t << 3);
+  float lo[4][4];                                          // the two small terms accumulate apart from the main product: shorter
+#pragma unroll                                             // dependency chains for the in-order MMA issue and a cleaner sum
+  for (int nt = 0; nt < 4; ++nt) { lo[nt][0] = 0.f; lo[nt][1] = 0.f; lo[nt][2] = 0.f; lo[nt][3] = 0.f; }
+#pragma unroll 2
+  for (int s = 0; s < k8; ++s) {
+    uint32_t ah[4], al[4], bh[4][2], bl[4][2];
+    split3(ap[0], ah[0], al[0]);
+    split3(ap[8], ah[1], al[1]);
+    split3(ap[4 * PE_LD], ah[2], al[2]);
+    split3(ap[4 * PE_LD + 8], ah[3], al[3]);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], wv[c], acc[r][c]);
+    for (int nt = 0; nt < 4; ++nt) {
+      split3(wp[col[nt]], bh[nt][0], bl[nt][0]);
+      split3(wp[4 * 64 + col[nt]], bh[nt][1], bl[nt][1]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mma_tf32(lo[nt], al, bh[nt]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[nt], ah, bh[nt]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mma_tf32(lo[nt], ah, bl[nt]);
+    ap += 8 * PE_LD;
+    wp += 8 * 64;
   }
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[nt][c] += lo[nt][c];
 }
 
 __device__ __forceinline__ void zero_acc(float (&acc)[4][4]) {
@@ -90,22 +128,19 @@ __device__ __forceinline__ void zero_acc(float (&acc)[4][4]) {
     for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
 }
 
-// relu(acc + bias) [* scale[pair]] -> dst[o][pair]
-__device__ __forceinline__ void store_act(const float (&acc)[4][4], const float* __restrict__ b, float* dst, int pg, int og, const int* keep) {
-  float s[4] = {1.f, 1.f, 1.f, 1.f};
-  if (keep) {
+// relu(acc + bias) [* keep[pair]] -> dst[ch][pair] (leading dimension PE_LD)
+__device__ __forceinline__ void store_act(const float (&acc)[4][4], const float* __restrict__ b, float* dst, int p0, int n0, int g, int t,
+                                          const int* keep) {
+  const float s0 = keep ? (keep[p0 + g] ? 1.f : 0.f) : 1.f, s1 = keep ? (keep[p0 + g + 8] ? 1.f : 0.f) : 1.f;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) s[r] = keep[pg * 4 + r] ? 1.f : 0.f;
-  }
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const float bb = b[og * 4 + c];
-    float4 v;
-    v.x = fmaxf(acc[0][c] + bb, 0.f) * s[0];
-    v.y = fmaxf(acc[1][c] + bb, 0.f) * s[1];
-    v.z = fmaxf(acc[2][c] + bb, 0.f) * s[2];
-    v.w = fmaxf(acc[3][c] + bb, 0.f) * s[3];
-    *reinterpret_cast<float4*>(dst + (og * 4 + c) * 64 + pg * 4) = v;
+  for (int nt = 0; nt < 4; ++nt) {
+    const int ch = n0 + nt * 8 + 2 * t;
+    const float b0 = b[ch], b1 = b[ch + 1];
+    float* d = dst + ch * PE_LD + p0 + g;
+    d[0] = fmaxf(acc[nt][0] + b0, 0.f) * s0;
+    d[PE_LD] = fmaxf(acc[nt][1] + b1, 0.f) * s0;
+    d[8] = fmaxf(acc[nt][2] + b0, 0.f) * s1;
+    d[PE_LD + 8] = fmaxf(acc[nt][3] + b1, 0.f) * s1;
   }
 }
 
@@ -141,14 +176,15 @@ __device__ __forceinline__ float dihedral(const float* p0, const float* p1, cons
 __global__ void __launch_bounds__(PE_THREADS, 1) pair_embed_kernel(PairEmbedW w, PairEmbedArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int A = w.A, A2 = w.A2;
-  float* sWd1 = smem;                              // [A2][64]
-  float* sW64 = sWd1 + A2 * 64;                    // [4][64][64]
-  float* sW1h = sW64 + 4 * 4096;                   // [26][64]
-  float* sBias = sW1h + PE_ANG * 64;               // [5][64]
-  float* sG = sBias + 5 * 64;                      // [75][64] distance chunk; later hA [64][64]
-  float* sHB = sG + PE_KC * 64;                    // [64][64]
-  float* sAng = sHB + 4096;                        // [26][64]
-  float* sCoef = sAng + PE_ANG * 64;               // [22][A2]
+  const int A2p = (A2 + 7) & ~7;                   // K of the first layer, padded with zero rows
+  float* sWd1 = smem;                              // [A2p][64]
+  float* sW64 = sWd1 + A2p * 64;                   // [4][64][64]
+  float* sW1h = sW64 + 4 * 4096;                   // [32][64]
+  float* sBias = sW1h + PE_ANGP * 64;              // [5][64]
+  float* sG = sBias + 5 * 64;                      // [80][72] distance chunk; later hA [64][72]
+  float* sHB = sG + PE_KC * PE_LD;                 // [64][72]
+  float* sAng = sHB + 64 * PE_LD;                  // [32][72], rows 26..31 stay zero
+  float* sCoef = sAng + PE_ANGP * PE_LD;           // [22][A2]
   float* sPosJ = sCoef + ((PE_AA * A2 + 3) & ~3);  // [64][A*3]
   float* sPosI = sPosJ + PE_TILE * PE_MAXA * 3;    // [A*3] (48 slots)
   int* sAaJ = reinterpret_cast<int*>(sPosI + 48);  // [64] amino-acid slot of the key
@@ -157,20 +193,23 @@ __global__ void __launch_bounds__(PE_THREADS, 1) pair_embed_kernel(PairEmbedW w,
   int* sOk = sKeep + PE_TILE;                      // [64] has_CA_i & has_CA_j (& j < L)
   int* sBitsJ = sOk + PE_TILE;                     // [64] atom mask of the key, one bit per atom
   int* sMisc = sBitsJ + PE_TILE;                   // [64] scalars of the query residue
-  int* sAB = sMisc + PE_TILE;                      // [A2] atom indices of distance entry e = ia * A + ib (see the distance phase)
+  int* sAB = sMisc + PE_TILE;                      // [A2p] atom indices of distance entry e = ia * A + ib (see the distance phase)
 
   const int tid = threadIdx.x;
-  const int pg = tid & 15, og = tid >> 4;          // GEMM phases: 4 pairs x 4 channels per thread
+  const int lane = tid & 31, wid = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;           // mma fragment coordinates
+  const int p0 = (wid & 3) * 16, n0 = (wid >> 2) * 32;   // this warp's 16 pairs x 32 channels of the tile
   const int L = a.L, A_in = a.A_in;
 
   // ---- weights: once per CTA
-  for (int i = tid; i < A2 * 64; i += PE_THREADS) sWd1[i] = w.Wd1[i];
+  for (int i = tid; i < A2p * 64; i += PE_THREADS) sWd1[i] = w.Wd1[i];
   for (int i = tid; i < 4 * 4096; i += PE_THREADS) sW64[i] = w.W64[i];
-  for (int i = tid; i < PE_ANG * 64; i += PE_THREADS) sW1h[i] = w.W1h[i];
+  for (int i = tid; i < PE_ANGP * 64; i += PE_THREADS) sW1h[i] = w.W1h[i];
+  for (int i = tid; i < PE_ANGP * PE_LD; i += PE_THREADS) sAng[i] = 0.f;
   for (int i = tid; i < 5 * 64; i += PE_THREADS) sBias[i] = w.bias[i];
-  for (int e = tid; e < A2; e += PE_THREADS) {
+  for (int e = tid; e < A2p; e += PE_THREADS) {
     const int ia = e / A, ib = e - ia * A;
-    sAB[e] = (ia * 3) | ((ib * 3) << 8) | (ia << 16) | (ib << 24);
+    sAB[e] = e < A2 ? ((ia * 3) | ((ib * 3) << 8) | (ia << 16) | (ib << 24)) : -1;     // -1: padding entry, g = 0
   }
 
   const int n_tiles = (L + PE_TILE - 1) / PE_TILE;
@@ -235,23 +274,23 @@ __global__ void __launch_bounds__(PE_THREADS, 1) pair_embed_kernel(PairEmbedW w,
         const float* Nj = sPosJ + p * (A * 3); const float* CAj = Nj + 3; const float* Cj = Nj + 6;
         const float x = which == 0 ? dihedral(Ci, Nj, CAj, Cj) : dihedral(Ni, CAi, Ci, Nj);   // geometry.py:362-373
         const float s = sKeep[p] ? 1.f : 0.f;                                                 // pair.py:92-94
-        float* dst = sAng + which * 13 * 64 + p;
+        float* dst = sAng + which * 13 * PE_LD + p;
         if (half == 0) dst[0] = x * s;
 #pragma unroll
         for (int f = 0; f < 3; ++f) {
           const int ff = half * 3 + f;
           float sn, cs;
           sincosf(x * w.freq[ff], &sn, &cs);
-          dst[(1 + ff) * 64] = sn * s;
-          dst[(7 + ff) * 64] = cs * s;
+          dst[(1 + ff) * PE_LD] = sn * s;
+          dst[(7 + ff) * PE_LD] = cs * s;
         }
       }
 
       // ---- distance Gaussians -> first distance layer, K walked in chunks of 75
       float acc[4][4];
       zero_acc(acc);
-      for (int e0 = 0; e0 < A2; e0 += PE_KC) {
-        const int ne = min(PE_KC, A2 - e0);
+      for (int e0 = 0; e0 < A2p; e0 += PE_KC) {
+        const int ne = min(PE_KC, A2p - e0);
         {  // thread = (pair p, entry slot tid >> 6); entries e0 + slot, + 4, + 8, ...: independent chains, no integer division
           const int p = tid & 63;
           const float* xjb = sPosJ + p * (A * 3);
@@ -260,62 +299,72 @@ __global__ void __launch_bounds__(PE_THREADS, 1) pair_embed_kernel(PairEmbedW w,
 #pragma unroll 4
           for (int el = tid >> 6; el < ne; el += 4) {
             const int ab = sAB[e0 + el];                                                  // ia * 3 | ib * 3 << 8 | ia << 16 | ib << 24
-            const float* xi = sPosI + (ab & 255);
-            const float* xj = xjb + ((ab >> 8) & 255);
+            const int abx = ab < 0 ? 0 : ab;                                              // padding entry: any valid address
+            const float* xi = sPosI + (abx & 255);
+            const float* xj = xjb + ((abx >> 8) & 255);
             const float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
             // (|x_ia - x_jb| / 10)^2 (angstrom_to_nm, then squared; pair.py:77-82)
             const float d2 = (dx * dx + dy * dy + dz * dz) * 0.01f;
-            const bool on = ((bits_i >> ((ab >> 16) & 255)) & 1) && ((bits_j >> (ab >> 24)) & 1);
-            sG[el * 64 + p] = on ? expf(-cfp[el] * d2) : 0.f;                             // pair.py:82-84
+            const bool on = ab >= 0 && ((bits_i >> ((ab >> 16) & 255)) & 1) && ((bits_j >> ((ab >> 24) & 255)) & 1);
+            sG[el * PE_LD + p] = on ? expf(-cfp[el] * d2) : 0.f;                          // pair.py:82-84
           }
         }
         __syncthreads();
-        tile_gemm<5>(acc, sG, sWd1 + e0 * 64, ne, pg, og);
+        tile_mma(acc, sG, sWd1 + e0 * 64, ne >> 3, p0, n0, g, t);
         __syncthreads();
       }
-      store_act(acc, sBias, sHB, pg, og, nullptr);                                      // h1
+      store_act(acc, sBias, sHB, p0, n0, g, t, nullptr);                                // h1
       __syncthreads();
       zero_acc(acc);
-      tile_gemm<8>(acc, sHB, sW64, 64, pg, og);
-      store_act(acc, sBias + 64, sG, pg, og, sKeep);                                    // h2 * structure pair mask (pair.py:85-87)
+      tile_mma(acc, sHB, sW64, 8, p0, n0, g, t);
+      store_act(acc, sBias + 64, sG, p0, n0, g, t, sKeep);                                    // h2 * structure pair mask (pair.py:85-87)
       // table part of the first out_mlp layer: issued here so the gathers overlap the GEMM below
-      float tab[4][4];
+      float tab[4][4];                                 // same coordinates as the accumulators
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int p = pg * 4 + r;
-        const float4 ta = *reinterpret_cast<const float4*>(w.Taa + ((size_t)(aa_i * PE_AA + sAaJ[p])) * 64 + og * 4);
+      for (int h = 0; h < 2; ++h) {
+        const int p = p0 + g + 8 * h;
+        const float* ta = w.Taa + ((size_t)(aa_i * PE_AA + sAaJ[p])) * 64;
         const int rel = sRel[p];
-        float4 tr = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rel >= 0) tr = *reinterpret_cast<const float4*>(w.Trel + (size_t)rel * 64 + og * 4);
-        tab[r][0] = ta.x + tr.x; tab[r][1] = ta.y + tr.y; tab[r][2] = ta.z + tr.z; tab[r][3] = ta.w + tr.w;
+        const float* tr = w.Trel + (size_t)(rel < 0 ? 0 : rel) * 64;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int ch = n0 + nt * 8 + 2 * t;
+          const float2 va = *reinterpret_cast<const float2*>(ta + ch);
+          float2 vr = *reinterpret_cast<const float2*>(tr + ch);
+          if (rel < 0) vr = make_float2(0.f, 0.f);
+          tab[nt][2 * h] = va.x + vr.x;
+          tab[nt][2 * h + 1] = va.y + vr.y;
+        }
       }
       __syncthreads();
       zero_acc(acc);
-      tile_gemm<8>(acc, sG, sW64 + 4096, 64, pg, og);
-      tile_gemm<2>(acc, sAng, sW1h, PE_ANG, pg, og);
+      tile_mma(acc, sG, sW64 + 4096, 8, p0, n0, g, t);
+      tile_mma(acc, sAng, sW1h, PE_ANGP / 8, p0, n0, g, t);
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[r][c] += tab[r][c];
-      store_act(acc, sBias + 128, sHB, pg, og, nullptr);                                // o1 (sHB's readers passed the barrier above)
+      store_act(acc, sBias + 128, sHB, p0, n0, g, t, nullptr);                                // o1 (sHB's readers passed the barrier above)
       __syncthreads();
       zero_acc(acc);
-      tile_gemm<8>(acc, sHB, sW64 + 2 * 4096, 64, pg, og);
-      store_act(acc, sBias + 192, sG, pg, og, nullptr);                                 // o2
+      tile_mma(acc, sHB, sW64 + 2 * 4096, 8, p0, n0, g, t);
+      store_act(acc, sBias + 192, sG, p0, n0, g, t, nullptr);                                 // o2
       __syncthreads();
-      // ---- last layer with the roles of the lanes swapped: 16 lanes cover the 64 channels of one pair -> 256-byte rows
+      // ---- last layer: (W3 o2 + b3) * has_CA pair mask, straight from the accumulators (each quad writes 32 contiguous bytes)
       {
-        const int og2 = tid & 15, pg2 = tid >> 4;
         zero_acc(acc);
-        tile_gemm<8>(acc, sG, sW64 + 3 * 4096, 64, pg2, og2);
-        const float4 b3 = *reinterpret_cast<const float4*>(sBias + 256 + og2 * 4);
+        tile_mma(acc, sG, sW64 + 3 * 4096, 8, p0, n0, g, t);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int p = pg2 * 4 + r, j = j0 + p;
+        for (int h = 0; h < 2; ++h) {
+          const int p = p0 + g + 8 * h, j = j0 + p;
           if (j < L) {
-            const float s = sOk[p] ? 1.f : 0.f;                                        // pair.py:99
-            float4 v = make_float4((acc[r][0] + b3.x) * s, (acc[r][1] + b3.y) * s, (acc[r][2] + b3.z) * s, (acc[r][3] + b3.w) * s);
-            __stcs(reinterpret_cast<float4*>(a.out + ((size_t)row * L + j) * 64 + og2 * 4), v);
+            const float s = sOk[p] ? 1.f : 0.f;                                          // pair.py:99
+            float* dst = a.out + ((size_t)row * L + j) * 64;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              const int ch = n0 + nt * 8 + 2 * t;
+              __stcs(reinterpret_cast<float2*>(dst + ch), make_float2((acc[nt][2 * h] + sBias[256 + ch]) * s, (acc[nt][2 * h + 1] + sBias[256 + ch + 1]) * s));
+            }
           }
         }
       }
@@ -418,7 +467,7 @@ extern "C" int abopt_pair_embed_finalize(abopt_pair_embed* pe) {
   std::vector<float> img;
   auto reserve = [&](size_t n) { size_t off = (img.size() + 63) & ~size_t(63); img.resize(off + n, 0.f); return off; };
   const size_t o_coef = reserve((size_t)NP * A2), o_taa = reserve((size_t)NP * 64), o_trel = reserve((size_t)NR * 64),
-               o_wd1 = reserve((size_t)A2 * 64), o_w64 = reserve(4 * 4096), o_w1h = reserve(PE_ANG * 64), o_bias = reserve(5 * 64);
+               o_wd1 = reserve((size_t)((A2 + 7) & ~7) * 64), o_w64 = reserve(4 * 4096), o_w1h = reserve(PE_ANGP * 64), o_bias = reserve(5 * 64);
   {  // F.softplus (beta 1, threshold 20), pair.py:81
     const std::vector<float>& c = pe->sd["aapair_to_distcoef.weight"];
     for (size_t k = 0; k < c.size(); ++k) img[o_coef + k] = c[k] > 20.f ? c[k] : log1pf(expf(c[k]));
@@ -433,9 +482,9 @@ extern "C" int abopt_pair_embed_finalize(abopt_pair_embed* pe) {
   };
   premul(pe->sd["aa_pair_embed.weight"], NP, 0, o_taa);
   premul(pe->sd["relpos_embed.weight"], NR, 64, o_trel);
-  auto transpose = [&](const float* Wsrc, int ld, int col0, int K, size_t off) {        // dst[k][o] = W[o][col0 + k]
+  auto transpose = [&](const float* Wsrc, int ld, int col0, int K, size_t off) {        // dst[k][o ^ ((k & 3) << 3)] = W[o][col0 + k]; rows beyond K stay zero
     for (int k = 0; k < K; ++k)
-      for (int o = 0; o < 64; ++o) img[off + (size_t)k * 64 + o] = Wsrc[(size_t)o * ld + col0 + k];
+      for (int o = 0; o < 64; ++o) img[off + (size_t)k * 64 + (o ^ ((k & 3) << 3))] = Wsrc[(size_t)o * ld + col0 + k];     // swizzled
   };
   transpose(pe->sd["distance_embed.0.weight"].data(), A2, 0, A2, o_wd1);
   transpose(pe->sd["distance_embed.2.weight"].data(), 64, 0, 64, o_w64);
