@@ -68,7 +68,7 @@ __host__ __device__ inline int pe_smem_floats(int A2) {
          + PE_KC * PE_LD + 64 * PE_LD + PE_ANGP * PE_LD  // g chunk (aliased by hA), hB, angle features
          + ((PE_AA * A2 + 3) & ~3)                        // coefficient rows of aa_i
          + PE_TILE * PE_MAXA * 3 + 48                     // key atoms, query atoms
-         + 6 * PE_TILE + A2p;                             // per-pair ints, entry -> atom table
+         + 6 * PE_TILE;                                   // per-pair ints
 }
 
 // ---- warp-level tensor-core GEMM pieces.  Warp w owns pairs [16 (w & 3), +16) x channels [32 (w >> 2), +32) of the 64 x 64 tile:
@@ -94,7 +94,7 @@ __device__ __forceinline__ void tile_mma(float (&acc)[4][4], const float* __rest
   float lo[4][4];                                          // the two small terms accumulate apart from the main product: shorter
 #pragma unroll                                             // dependency chains for the in-order MMA issue and a cleaner sum
   for (int nt = 0; nt < 4; ++nt) { lo[nt][0] = 0.f; lo[nt][1] = 0.f; lo[nt][2] = 0.f; lo[nt][3] = 0.f; }
-#pragma unroll 2
+#pragma unroll 4
   for (int s = 0; s < k8; ++s) {
     uint32_t ah[4], al[4], bh[4][2], bl[4][2];
     split3(ap[0], ah[0], al[0]);
@@ -193,7 +193,6 @@ __global__ void __launch_bounds__(PE_THREADS, 1) pair_embed_kernel(PairEmbedW w,
   int* sOk = sKeep + PE_TILE;                      // [64] has_CA_i & has_CA_j (& j < L)
   int* sBitsJ = sOk + PE_TILE;                     // [64] atom mask of the key, one bit per atom
   int* sMisc = sBitsJ + PE_TILE;                   // [64] scalars of the query residue
-  int* sAB = sMisc + PE_TILE;                      // [A2p] atom indices of distance entry e = ia * A + ib (see the distance phase)
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, wid = tid >> 5;
@@ -207,10 +206,7 @@ __global__ void __launch_bounds__(PE_THREADS, 1) pair_embed_kernel(PairEmbedW w,
   for (int i = tid; i < PE_ANGP * 64; i += PE_THREADS) sW1h[i] = w.W1h[i];
   for (int i = tid; i < PE_ANGP * PE_LD; i += PE_THREADS) sAng[i] = 0.f;
   for (int i = tid; i < 5 * 64; i += PE_THREADS) sBias[i] = w.bias[i];
-  for (int e = tid; e < A2p; e += PE_THREADS) {
-    const int ia = e / A, ib = e - ia * A;
-    sAB[e] = e < A2 ? ((ia * 3) | ((ib * 3) << 8) | (ia << 16) | (ib << 24)) : -1;     // -1: padding entry, g = 0
-  }
+
 
   const int n_tiles = (L + PE_TILE - 1) / PE_TILE;
   const long long rows = (long long)a.N * L;
@@ -242,10 +238,10 @@ __global__ void __launch_bounds__(PE_THREADS, 1) pair_embed_kernel(PairEmbedW w,
       const int j0 = jt * PE_TILE;
       __syncthreads();                             // previous tile's readers done (sCoef fill ordered too)
       // ---- stage the 64 keys
-      for (int k = tid; k < PE_TILE * A * 3; k += PE_THREADS) {
-        const int p = k / (A * 3), c = k - p * (A * 3);
+      for (int p = tid >> 5; p < PE_TILE; p += PE_THREADS / 32) {                      // one warp per key residue, no divisions
         const int j = j0 + p;
-        sPosJ[p * (A * 3) + c] = j < L ? a.pos[(((size_t)n * L + j) * A_in) * 3 + c] : 0.f;
+        const float* src = a.pos + (((size_t)n * L + j) * A_in) * 3;
+        for (int c = tid & 31; c < A * 3; c += 32) sPosJ[p * (A * 3) + c] = j < L ? src[c] : 0.f;
       }
       if (tid < PE_TILE) {
         const int j = j0 + tid;
@@ -291,22 +287,26 @@ __global__ void __launch_bounds__(PE_THREADS, 1) pair_embed_kernel(PairEmbedW w,
       zero_acc(acc);
       for (int e0 = 0; e0 < A2p; e0 += PE_KC) {
         const int ne = min(PE_KC, A2p - e0);
-        {  // thread = (pair p, entry slot tid >> 6); entries e0 + slot, + 4, + 8, ...: independent chains, no integer division
+        {  // thread = (pair p, entry slot tid >> 6); entries e0 + slot, + 4, + 8, ...: independent chains; the atom indices
+           // (ia, ib) of entry e = ia * A + ib advance incrementally (one division per chunk, no table lookups in the loop)
           const int p = tid & 63;
           const float* xjb = sPosJ + p * (A * 3);
           const float* cfp = sCoef + sAaJ[p] * A2 + e0;
           const int bits_j = sBitsJ[p];
-#pragma unroll 4
+          int ia = (e0 + (tid >> 6)) / A, ib = (e0 + (tid >> 6)) - ia * A;
+#pragma unroll 5
           for (int el = tid >> 6; el < ne; el += 4) {
-            const int ab = sAB[e0 + el];                                                  // ia * 3 | ib * 3 << 8 | ia << 16 | ib << 24
-            const int abx = ab < 0 ? 0 : ab;                                              // padding entry: any valid address
-            const float* xi = sPosI + (abx & 255);
-            const float* xj = xjb + ((abx >> 8) & 255);
+            const float* xi = sPosI + ia * 3;                                             // ia <= 15 on padding entries: inside the 48 slots
+            const float* xj = xjb + ib * 3;
             const float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
             // (|x_ia - x_jb| / 10)^2 (angstrom_to_nm, then squared; pair.py:77-82)
             const float d2 = (dx * dx + dy * dy + dz * dz) * 0.01f;
-            const bool on = ab >= 0 && ((bits_i >> ((ab >> 16) & 255)) & 1) && ((bits_j >> ((ab >> 24) & 255)) & 1);
-            sG[el * PE_LD + p] = on ? expf(-cfp[el] * d2) : 0.f;                          // pair.py:82-84
+            const bool on = (e0 + el < A2) && ((bits_i >> ia) & 1) && ((bits_j >> ib) & 1);   // entries >= A2 pad K to a multiple of 8
+            const float gv = expf(-cfp[el] * d2);                                         // evaluated on every lane: no divergent branch
+            sG[el * PE_LD + p] = on ? gv : 0.f;                                           // pair.py:82-84
+            ib += 4;
+            if (ib >= A) { ib -= A; ++ia; }
+            if (ib >= A) { ib -= A; ++ia; }                                               // A = 3: two wraps per step
           }
         }
         __syncthreads();
