@@ -215,3 +215,51 @@ def test_post_loop_functions():
     torch.testing.assert_close(post.pairwise_rmsd(S), fn['calc_per_rmsd'](S), rtol=1e-6, atol=1e-6)
     torch.testing.assert_close(post.average_rmsd(S), fn['calc_avg_rmsd'](S), rtol=1e-6, atol=0)
     assert torch.equal(post.rank_commonness(S, 7), fn['rank_commoness'](S, 7))
+
+
+class _Cfg(dict):
+    """EasyDict stand-in (attribute access, nested): the reference's configs are EasyDicts (utils/misc.py load_config)."""
+    def __getattr__(self, k):
+        try:
+            v = self[k]
+        except KeyError:
+            raise AttributeError(k)
+        return _Cfg(v) if isinstance(v, dict) else v
+
+
+def test_drop_in_through_the_reference_registry():
+    """The boundary itself: after ab_opt_b200.install_into_reference('src'), the reference's own
+    `get_model(cfg.model)` (models/_base.py:12-13, models/diffab.py:19-37) builds the B200 classes from the reference's YAML, and
+    `load_state_dict(ckpt['model'])` (tools/runner/design_for_pdb.py:94) loads the shipped checkpoint STRICTLY into them.
+    Runs in a subprocess so that the rebinding does not leak into the other tests of this file.  CPU only: nothing is computed."""
+    import subprocess
+    import textwrap
+    path = os.path.join(REF_ROOT, 'AbDock/reproduction/dock_single_cdr/250000.pt')
+    if not os.path.exists(path):
+        pytest.skip('checkpoint missing')
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent(f'''
+        import sys, yaml, torch
+        sys.path[:0] = [{os.path.join(REF_ROOT, 'AbDock')!r}, {repo!r}, {os.path.join(repo, 'tests')!r}]
+        import ab_opt_b200
+        ab_opt_b200.install_into_reference('src')
+        from src.models import get_model
+        import src.modules.common.geometry as geo
+        from test_oracle_vs_reference import _Cfg, _load_ckpt_state
+        cfg = _Cfg(yaml.safe_load(open({os.path.join(REF_ROOT, 'AbDock/configs/train/dock_single.yml')!r})))
+        model = get_model(cfg.model)
+        assert type(model.diffusion) is ab_opt_b200.FullDPM and type(model.pair_embed) is ab_opt_b200.PairEmbedding
+        assert type(model.residue_embed) is ab_opt_b200.ResidueEmbedding
+        assert type(model.diffusion.eps_net.encoder) is ab_opt_b200.GAEncoder
+        assert geo.reconstruct_backbone_partially is ab_opt_b200.reconstruct_backbone_partially
+        _load_ckpt_state({path!r})
+        ck = torch.load({path!r}, map_location='cpu', weights_only=False)
+        res = model.load_state_dict(ck['model'], strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        try:                                     # and there is no CPU path behind the classes
+            model.pair_embed(*[torch.zeros(1, 2, dtype=torch.long)] * 3, torch.zeros(1, 2, 15, 3), torch.ones(1, 2, 15, dtype=torch.bool))
+        except ab_opt_b200.AboptError as e:
+            print('OK', len(ck['model']), 'tensors;', str(e)[:60])
+    ''')
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.startswith('OK'), out.stdout + out.stderr[-3000:]
