@@ -60,6 +60,36 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // x - trunc_tf32(x): the "lo" plane of the 3xTF32 operand split (the tensor core reads trunc_tf32(x) from the raw value)
 __device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
+// ---------------------------------------------------------------- dihedral_from_four_points (modules/common/geometry.py:254-271)
+// Signed angle between the planes (p0,p1,p2) and (p1,p2,p3), operation by operation as the reference evaluates it: products and
+// sums are rounded separately (no FMA contraction) because the sign of the result is the sign of a triple product, which can be
+// zero in exact arithmetic; cosine clamped to +-0.999999; NaN (degenerate normals: 0 / 0) -> 0 like torch.nan_to_num.
+__device__ __forceinline__ void cross3_rn(const float* a, const float* b, float* o) {
+  o[0] = __fsub_rn(__fmul_rn(a[1], b[2]), __fmul_rn(a[2], b[1]));
+  o[1] = __fsub_rn(__fmul_rn(a[2], b[0]), __fmul_rn(a[0], b[2]));
+  o[2] = __fsub_rn(__fmul_rn(a[0], b[1]), __fmul_rn(a[1], b[0]));
+}
+__device__ __forceinline__ float dot3_rn(const float* a, const float* b) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(a[0], b[0]), __fmul_rn(a[1], b[1])), __fmul_rn(a[2], b[2]));
+}
+__device__ __forceinline__ float dihedral4(const float* p0, const float* p1, const float* p2, const float* p3) {
+  float v0[3], v1[3], v2[3], u1[3], u2[3], w[3], n1[3], n2[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { v0[c] = p2[c] - p1[c]; v1[c] = p0[c] - p1[c]; v2[c] = p3[c] - p2[c]; }
+  cross3_rn(v0, v1, u1);
+  cross3_rn(v0, v2, u2);
+  const float l1 = sqrtf(dot3_rn(u1, u1)), l2 = sqrtf(dot3_rn(u2, u2));
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { n1[c] = u1[c] / l1; n2[c] = u2[c] / l2; }      // 0 / 0 -> NaN, as in the reference
+  cross3_rn(v1, v2, w);
+  const float tp = dot3_rn(w, v0);
+  const float sgn = tp > 0.f ? 1.f : (tp < 0.f ? -1.f : 0.f);
+  float cs = dot3_rn(n1, n2);
+  if (isnan(cs) || isnan(tp)) return 0.f;                                       // nan_to_num, geometry.py:270
+  cs = fminf(fmaxf(cs, -0.999999f), 0.999999f);
+  return sgn * acosf(cs);
+}
+
 // ---------------------------------------------------------------- 3x3 helpers (row-major R[9])
 struct Mat3 { float m[9]; };
 

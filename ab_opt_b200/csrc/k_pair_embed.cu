@@ -144,35 +144,6 @@ __device__ __forceinline__ void store_act(const float (&acc)[4][4], const float*
   }
 }
 
-// dihedral_from_four_points, geometry.py:254-271, operation by operation (no FMA contraction: the sign of the result is the sign
-// of a triple product, so the rounding of the products matters when it is close to zero).
-__device__ __forceinline__ void cross_rn(const float* a, const float* b, float* o) {
-  o[0] = __fsub_rn(__fmul_rn(a[1], b[2]), __fmul_rn(a[2], b[1]));
-  o[1] = __fsub_rn(__fmul_rn(a[2], b[0]), __fmul_rn(a[0], b[2]));
-  o[2] = __fsub_rn(__fmul_rn(a[0], b[1]), __fmul_rn(a[1], b[0]));
-}
-__device__ __forceinline__ float dot_rn(const float* a, const float* b) {
-  return __fadd_rn(__fadd_rn(__fmul_rn(a[0], b[0]), __fmul_rn(a[1], b[1])), __fmul_rn(a[2], b[2]));
-}
-__device__ __forceinline__ float dihedral(const float* p0, const float* p1, const float* p2, const float* p3) {
-  float v0[3], v1[3], v2[3], u1[3], u2[3], w[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) { v0[c] = p2[c] - p1[c]; v1[c] = p0[c] - p1[c]; v2[c] = p3[c] - p2[c]; }
-  cross_rn(v0, v1, u1);
-  cross_rn(v0, v2, u2);
-  const float l1 = sqrtf(dot_rn(u1, u1)), l2 = sqrtf(dot_rn(u2, u2));
-  float n1[3], n2[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) { n1[c] = u1[c] / l1; n2[c] = u2[c] / l2; }      // 0 / 0 -> NaN, as in the reference
-  cross_rn(v1, v2, w);
-  const float tp = dot_rn(w, v0);
-  const float sgn = tp > 0.f ? 1.f : (tp < 0.f ? -1.f : 0.f);
-  float cs = dot_rn(n1, n2);
-  if (isnan(cs) || isnan(tp)) return 0.f;                                       // nan_to_num, geometry.py:270
-  cs = fminf(fmaxf(cs, -0.999999f), 0.999999f);
-  return sgn * acosf(cs);
-}
-
 __global__ void __launch_bounds__(PE_THREADS, 1) pair_embed_kernel(PairEmbedW w, PairEmbedArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int A = w.A, A2 = w.A2;
@@ -211,7 +182,7 @@ __global__ void __launch_bounds__(PE_THREADS, 1) pair_embed_kernel(PairEmbedW w,
   const int n_tiles = (L + PE_TILE - 1) / PE_TILE;
   const long long rows = (long long)a.N * L;
   for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int n = (int)(row / L), i = (int)(row % L);
+    const int n = (int)(row / L);
     __syncthreads();                               // previous row fully consumed (also orders the weight fill)
     // ---- query residue
     if (tid < A * 3) sPosI[tid] = a.pos[((size_t)row * A_in) * 3 + tid];
@@ -268,7 +239,7 @@ __global__ void __launch_bounds__(PE_THREADS, 1) pair_embed_kernel(PairEmbedW w,
         const int p = tid & 63, which = (tid >> 6) & 1, half = tid >> 7;
         const float* Ni = sPosI; const float* CAi = sPosI + 3; const float* Ci = sPosI + 6;
         const float* Nj = sPosJ + p * (A * 3); const float* CAj = Nj + 3; const float* Cj = Nj + 6;
-        const float x = which == 0 ? dihedral(Ci, Nj, CAj, Cj) : dihedral(Ni, CAi, Ci, Nj);   // geometry.py:362-373
+        const float x = which == 0 ? dihedral4(Ci, Nj, CAj, Cj) : dihedral4(Ni, CAi, Ci, Nj);   // geometry.py:362-373
         const float s = sKeep[p] ? 1.f : 0.f;                                                 // pair.py:92-94
         float* dst = sAng + which * 13 * PE_LD + p;
         if (half == 0) dst[0] = x * s;

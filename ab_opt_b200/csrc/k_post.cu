@@ -18,32 +18,6 @@ namespace abopt {
 int api_fail(int code, const std::string& msg);
 
 namespace {
-__device__ __forceinline__ void cross3p(const float* a, const float* b, float* o) {
-  o[0] = __fsub_rn(__fmul_rn(a[1], b[2]), __fmul_rn(a[2], b[1]));
-  o[1] = __fsub_rn(__fmul_rn(a[2], b[0]), __fmul_rn(a[0], b[2]));
-  o[2] = __fsub_rn(__fmul_rn(a[0], b[1]), __fmul_rn(a[1], b[0]));
-}
-__device__ __forceinline__ float dot3p(const float* a, const float* b) {
-  return __fadd_rn(__fadd_rn(__fmul_rn(a[0], b[0]), __fmul_rn(a[1], b[1])), __fmul_rn(a[2], b[2]));
-}
-// dihedral_from_four_points, geometry.py:254-271
-__device__ __forceinline__ float dihedral4p(const float* p0, const float* p1, const float* p2, const float* p3) {
-  float v0[3], v1[3], v2[3], u1[3], u2[3], w[3], n1[3], n2[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) { v0[c] = p2[c] - p1[c]; v1[c] = p0[c] - p1[c]; v2[c] = p3[c] - p2[c]; }
-  cross3p(v0, v1, u1);
-  cross3p(v0, v2, u2);
-  const float l1 = sqrtf(dot3p(u1, u1)), l2 = sqrtf(dot3p(u2, u2));
-#pragma unroll
-  for (int c = 0; c < 3; ++c) { n1[c] = u1[c] / l1; n2[c] = u2[c] / l2; }
-  cross3p(v1, v2, w);
-  const float tp = dot3p(w, v0);
-  const float sgn = tp > 0.f ? 1.f : (tp < 0.f ? -1.f : 0.f);
-  float cs = dot3p(n1, n2);
-  if (isnan(cs) || isnan(tp)) return 0.f;
-  cs = fminf(fmaxf(cs, -0.999999f), 0.999999f);
-  return sgn * acosf(cs);
-}
 // q = R p + t (local_to_global, geometry.py:72-92); R row-major
 __device__ __forceinline__ void to_global(const float* R, const float* t, const float* p, float* q) {
 #pragma unroll
@@ -88,7 +62,7 @@ __global__ void __launch_bounds__(128) reconstruct_kernel(ReconArgs a) {
     const int aa2 = (int)(s2 < 0 ? 0 : (s2 > 20 ? 20 : s2));
     float n_next[3];
     to_global(a.R + (size_t)(row + 1) * 9, a.t + (size_t)(row + 1) * 3, a.bb + (aa2 * 3) * 3, n_next);
-    const float x = dihedral4p(q[0], q[1], q[2], n_next);
+    const float x = dihedral4(q[0], q[1], q[2], n_next);
     psi = bonded ? x : 0.f;
   }
   // O = R Rx(psi) o + t (geometry.py:427-444)

@@ -46,33 +46,6 @@ struct ResEmbedArgs {
   float* out;
 };
 
-__device__ __forceinline__ void cross3(const float* a, const float* b, float* o) {
-  o[0] = __fsub_rn(__fmul_rn(a[1], b[2]), __fmul_rn(a[2], b[1]));
-  o[1] = __fsub_rn(__fmul_rn(a[2], b[0]), __fmul_rn(a[0], b[2]));
-  o[2] = __fsub_rn(__fmul_rn(a[0], b[1]), __fmul_rn(a[1], b[0]));
-}
-__device__ __forceinline__ float dot3(const float* a, const float* b) {
-  return __fadd_rn(__fadd_rn(__fmul_rn(a[0], b[0]), __fmul_rn(a[1], b[1])), __fmul_rn(a[2], b[2]));
-}
-// dihedral_from_four_points, geometry.py:254-271
-__device__ __forceinline__ float dihedral4(const float* p0, const float* p1, const float* p2, const float* p3) {
-  float v0[3], v1[3], v2[3], u1[3], u2[3], w[3], n1[3], n2[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) { v0[c] = p2[c] - p1[c]; v1[c] = p0[c] - p1[c]; v2[c] = p3[c] - p2[c]; }
-  cross3(v0, v1, u1);
-  cross3(v0, v2, u2);
-  const float l1 = sqrtf(dot3(u1, u1)), l2 = sqrtf(dot3(u2, u2));
-#pragma unroll
-  for (int c = 0; c < 3; ++c) { n1[c] = u1[c] / l1; n2[c] = u2[c] / l2; }
-  cross3(v1, v2, w);
-  const float tp = dot3(w, v0);
-  const float sgn = tp > 0.f ? 1.f : (tp < 0.f ? -1.f : 0.f);
-  float cs = dot3(n1, n2);
-  if (isnan(cs) || isnan(tp)) return 0.f;
-  cs = fminf(fmaxf(cs, -0.999999f), 0.999999f);
-  return sgn * acosf(cs);
-}
-
 __global__ void __launch_bounds__(RE_THREADS) res_embed_kernel(ResEmbedW w, ResEmbedArgs a) {
   __shared__ float sCrd[RE_RT][RE_MAXA * 3 + 3];
   __shared__ float sAng[RE_RT][RE_ANG + 1];
