@@ -82,12 +82,33 @@ def so3_exp(w):
     return eye + b[..., None, None] * S + c[..., None, None] * (S @ S)
 
 
-def so3_log(R, grad_mode=False):
+GRAD_ENABLED_CLAMP = False      # see so3_log / grad_enabled_semantics
+
+
+class grad_enabled_semantics:
+    """Context manager: evaluate the oracle as the reference evaluates it while autograd is ENABLED (a training step).
+    The only numerical difference is log_rotation's clamp (so3.py:12-17: cos >= -0.999 instead of -1), which moves every
+    rotation within 0.045 rad of pi -- about 3 % of uniformly random rotations.  Sampling, optimize() and the validation loop
+    run under torch.no_grad() and use -1; that is the oracle's default."""
+
+    def __enter__(self):
+        global GRAD_ENABLED_CLAMP
+        self.prev, GRAD_ENABLED_CLAMP = GRAD_ENABLED_CLAMP, True
+
+    def __exit__(self, *exc):
+        global GRAD_ENABLED_CLAMP
+        GRAD_ENABLED_CLAMP = self.prev
+
+
+def so3_log(R, grad_mode=None):
     """Log map to the so(3) vector, replicated op-for-op (ill-conditioned near pi on purpose).
 
     so3.py:10-30,60-63.  `grad_mode` selects the -0.999 clamp the reference uses when autograd
-    is enabled (training); sampling runs under no_grad -> clamp at -1.
+    is enabled (training); sampling runs under no_grad -> clamp at -1.  None -> the module switch
+    (`grad_enabled_semantics`), which is off by default.
     """
+    if grad_mode is None:
+        grad_mode = GRAD_ENABLED_CLAMP
     tr = R[..., 0, 0] + R[..., 1, 1] + R[..., 2, 2]
     lo = -0.999 if grad_mode else -1.0
     cos_t = ((tr - 1) / 2).clamp_min(lo)

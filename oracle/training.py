@@ -101,3 +101,21 @@ def loss_forward(W, v_0, p_0, s_0, res_feat, pair_feat, mask_generate, mask_res,
     kl = F.kl_div(input=log_post_pred, target=post_true, reduction='none', log_target=False).sum(dim=-1)
     loss['seq'] = (kl * mg).sum() / denom
     return loss
+
+
+def loss_and_grads(W, v_0, p_0, s_0, res_feat, pair_feat, mask_generate, mask_res, denoise_structure, denoise_sequence, t, noise,
+                   loss_weights=None, **kw):
+    """One training step's forward AND backward as the reference runs it with autograd enabled (train.py: loss =
+    sum_k w_k loss_k; loss.backward()): `loss_forward` under `grad_enabled_semantics`, then torch autograd through the oracle.
+    Returns (loss dict, {state-dict key: gradient} for every floating parameter that receives one, d loss / d res_feat,
+    d loss / d pair_feat).  This is the target the CUDA backward will be held to."""
+    from .geometry import grad_enabled_semantics
+    buffers = ('trans_', 'position_', '_dummy', 'prmsd.tobin')
+    Wg = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and not k.startswith(buffers) else v) for k, v in W.items()}
+    rf, pf = res_feat.detach().clone().requires_grad_(True), pair_feat.detach().clone().requires_grad_(True)
+    with torch.enable_grad(), grad_enabled_semantics():
+        loss = loss_forward(Wg, v_0, p_0, s_0, rf, pf, mask_generate, mask_res, denoise_structure, denoise_sequence, t, noise, **kw)
+        total = sum((loss_weights or {}).get(k, 1.0) * v for k, v in loss.items())
+        total.backward()
+    grads = {k: v.grad for k, v in Wg.items() if torch.is_tensor(v) and v.requires_grad and v.grad is not None}
+    return {k: v.detach() for k, v in loss.items()}, grads, rf.grad, pf.grad

@@ -56,6 +56,42 @@ def make_train_forward():
         **{'noise_' + k: v for k, v in noise.items()})
 
 
+FULL_GRADS = ('eps_net.encoder.blocks.0.spatial_coef', 'eps_net.encoder.blocks.1.spatial_coef', 'eps_net.encoder.blocks.0.proj_pair_bias.weight',
+              'eps_net.encoder.blocks.1.layer_norm_2.gamma', 'eps_net.encoder.blocks.0.layer_norm_1.beta', 'eps_net.eps_crd_net.4.weight',
+              'eps_net.eps_rot_net.4.weight', 'eps_net.eps_seq_net.4.bias', 'eps_net.current_sequence_embedding.weight',
+              'eps_net.prmsd_predictor.linear_3.bias')
+
+
+def make_train_backward():
+    """One training step of the unmodified reference WITH autograd enabled (train.py: loss = sum of the loss dict, weights 1;
+    loss.backward()): the grad-enabled losses (log_rotation clamps at -0.999 there, so3.py:12-17), the gradient norm of every
+    parameter, the full gradient of a few small ones and d loss / d res_feat, d loss / d pair_feat.  Same inputs and noise as
+    train_forward.npz.  This pins oracle.training.loss_and_grads, the target of the CUDA backward."""
+    torch.set_num_threads(1)
+    seed_w, nl, seed_n = 13, 2, 77
+    W = weights.make_state_dict(seed=seed_w, num_layers=nl, flavour='abdock')
+    inp = weights.synthetic_inputs(23, 2, 12, gen_slices=((0, 5), (8, 10)), ragged=True)
+    t = torch.tensor([57, 3])
+    keep = {}
+    for obj in ('pred_x0', 'pred_noise'):
+        model, _ = build_reference_fulldpm(W, num_layers=nl, obj=obj)
+        rf, pf = inp['res_feat'].clone().requires_grad_(True), inp['pair_feat'].clone().requires_grad_(True)
+        torch.manual_seed(seed_n)
+        loss = model(inp['v'], inp['p'], inp['s'], rf, pf, inp['mask_generate'], inp['mask_res'], denoise_structure=True,
+                     denoise_sequence=True, t=t)
+        sum(loss.values()).backward()
+        for k, v in loss.items():
+            keep[f'{obj}_loss_{k}'] = v.detach()
+        names = sorted(k for k, _ in model.named_parameters())
+        keep[f'{obj}_param_names'] = np.array(names)
+        P = dict(model.named_parameters())
+        keep[f'{obj}_grad_norms'] = torch.stack([P[k].grad.double().norm() for k in names])
+        for k in FULL_GRADS:
+            keep[f'{obj}_grad_{k}'] = P[k].grad
+        keep[f'{obj}_grad_res_feat'], keep[f'{obj}_grad_pair_feat'] = rf.grad, pf.grad
+    npz('train_backward.npz', seed_w=seed_w, num_layers=nl, seed_in=23, N=2, L=12, seed_noise=seed_n, t=t, **keep)
+
+
 @torch.no_grad()
 def make_pair_embed():
     """PairEmbedding.forward (encoders/pair.py:37-101) of the unmodified reference: full-atom (A=15) and backbone+CB (A=5)
@@ -201,8 +237,11 @@ if __name__ == '__main__':
         make_pair_embed()
     elif len(sys.argv) > 1 and sys.argv[1] == 'post_loop':
         make_post_loop()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'train_backward':
+        make_train_backward()
     else:
         main()
         make_train_forward()
         make_pair_embed()
         make_post_loop()
+        make_train_backward()

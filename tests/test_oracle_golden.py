@@ -209,3 +209,38 @@ def test_post_loop_matches_reference(golden_dir):
     torch.testing.assert_close(post.pairwise_rmsd(g['structures']), g['rmsd'], rtol=1e-6, atol=1e-6)
     torch.testing.assert_close(post.average_rmsd(g['structures']), torch.tensor(g['avg_rmsd']), rtol=1e-6, atol=0)
     assert torch.equal(post.rank_commonness(g['structures'], 5), g['rank'])
+
+
+# ------------------------------------------------------------------------------------------ training step with autograd
+@pytest.mark.parametrize('obj', ['pred_x0', 'pred_noise'])
+def test_training_backward_matches_reference(golden_dir, obj):
+    """oracle.training.loss_and_grads vs one training step of the unmodified reference with autograd ENABLED
+    (tests/golden/train_backward.npz): the grad-enabled losses (log_rotation clamps at -0.999 there, so3.py:12-17 -- they differ
+    from the no_grad losses of train_forward.npz by up to 2 %), the gradient norm of all 71 parameters, the full gradient of ten
+    of them and the gradients with respect to res_feat / pair_feat."""
+    from oracle import training
+    d = np.load(os.path.join(golden_dir, 'train_backward.npz'))
+    g = {k: (torch.from_numpy(d[k]) if d[k].dtype.kind != 'U' and d[k].ndim else d[k]) for k in d.files}
+    W = weights.make_state_dict(seed=int(g['seed_w']), num_layers=int(g['num_layers']), flavour='abdock')
+    inp = weights.synthetic_inputs(int(g['seed_in']), int(g['N']), int(g['L']), gen_slices=((0, 5), (8, 10)), ragged=True)
+    noise = T.draw_step_noise(int(g['N']), int(g['L']), torch.Generator().manual_seed(int(g['seed_noise'])))
+    loss, grads, g_res, g_pair = training.loss_and_grads(W, inp['v'], inp['p'], inp['s'], inp['res_feat'], inp['pair_feat'],
+                                                         inp['mask_generate'], inp['mask_res'], True, True, g['t'], noise,
+                                                         flavour='abdock', obj=obj)
+    for k, v in loss.items():
+        torch.testing.assert_close(v, torch.as_tensor(g[f'{obj}_loss_{k}'].item()), rtol=2e-5, atol=2e-6, msg=lambda m, k=k: f'{k}: {m}')
+    names = [str(x) for x in g[f'{obj}_param_names']]
+    assert sorted(grads) == names
+    norms = torch.stack([grads[k].double().norm() for k in names])
+    torch.testing.assert_close(norms, g[f'{obj}_grad_norms'], rtol=1e-4, atol=1e-9)
+    for key in d.files:
+        if key.startswith(f'{obj}_grad_eps_net.'):
+            want = g[key]
+            got = grads[key[len(obj) + 6:]]
+            assert (got - want).abs().max() <= 2e-5 * want.abs().max() + 1e-9, key
+    for got, want in ((g_res, g[f'{obj}_grad_res_feat']), (g_pair, g[f'{obj}_grad_pair_feat'])):
+        assert (got - want).abs().max() <= 2e-5 * want.abs().max()
+    # and the no_grad losses are NOT these: the clamp matters
+    plain = training.loss_forward(W, inp['v'], inp['p'], inp['s'], inp['res_feat'], inp['pair_feat'], inp['mask_generate'],
+                                  inp['mask_res'], True, True, g['t'], noise, flavour='abdock', obj=obj)
+    assert abs(float(plain['rot']) - float(loss['rot'])) > 1e-3
