@@ -18,3 +18,5 @@ committed as fixtures under tests/golden/*.npz; tests/test_oracle_golden.py repl
 anywhere, and tests/test_oracle_vs_reference.py compares live when /root/reference exists.
 """
 from . import geometry, ipa, epsnet, transitions, sampler, weights  # noqa: F401
+# training.py (FullDPM.forward, losses + autograd step), pair_embed.py (PairEmbedding / ResidueEmbedding, the step before the
+# loop) and post.py (backbone reconstruction, RMSD ranking, the steps after it) are imported where they are used.

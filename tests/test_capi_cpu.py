@@ -75,3 +75,26 @@ def test_model_create_fails_loudly_without_gpu():
     h = ctypes.c_void_p()
     rc = _capi.lib().abopt_model_create(ctypes.byref(cfg), 0, ctypes.byref(h))
     assert rc != 0 and _capi.lib().abopt_last_error()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the behaviour on a machine WITHOUT a CUDA device')
+def test_callers_of_the_path_have_no_cpu_fallback():
+    """The mirrors of the steps before / after the loop (PairEmbedding, ResidueEmbedding, reconstruct_backbone_partially,
+    rank_commoness) accept CPU tensors like the reference's runners pass them, but only to move them to a GPU: without one they
+    raise instead of computing anything on the host."""
+    import ab_opt_b200
+    aa = torch.zeros(1, 4, dtype=torch.long)
+    pos, mask = torch.zeros(1, 4, 15, 3), torch.ones(1, 4, 15, dtype=torch.bool)
+    with pytest.raises(ab_opt_b200.AboptError):
+        ab_opt_b200.PairEmbedding(64, 15)(aa, aa, aa, pos, mask)
+    with pytest.raises(ab_opt_b200.AboptError):
+        ab_opt_b200.ResidueEmbedding(128, 15)(aa, aa, aa, pos, mask, aa)
+    with pytest.raises(ab_opt_b200.AboptError):
+        ab_opt_b200.rank_commoness(torch.zeros(3, 5, 3), 2)
+    with pytest.raises(ab_opt_b200.AboptError):
+        ab_opt_b200.reconstruct_backbone_partially(pos, torch.eye(3).expand(1, 4, 3, 3), torch.zeros(1, 4, 3), aa, aa, aa, mask,
+                                                   torch.ones(1, 4, dtype=torch.bool), bb_table=torch.zeros(21, 3, 3), o_table=torch.zeros(21, 3))
+    with pytest.raises(ValueError):                                     # the kernels are specialised for the reference configuration
+        ab_opt_b200.PairEmbedding(32, 15)
+    with pytest.raises(ValueError):
+        ab_opt_b200.ResidueEmbedding(128, 16)
