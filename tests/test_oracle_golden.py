@@ -244,3 +244,27 @@ def test_training_backward_matches_reference(golden_dir, obj):
     plain = training.loss_forward(W, inp['v'], inp['p'], inp['s'], inp['res_feat'], inp['pair_feat'], inp['mask_generate'],
                                   inp['mask_res'], True, True, g['t'], noise, flavour='abdock', obj=obj)
     assert abs(float(plain['rot']) - float(loss['rot'])) > 1e-3
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float64, 1e-9), (torch.float32, 2e-5)])
+def test_hand_written_block_backward_matches_autograd(dtype, tol):
+    """oracle.ipa_backward.ga_block_backward (the explicit formulas the CUDA backward will implement) vs torch autograd through
+    oracle.ipa.ga_block (pinned to the reference's GABlock): d x, d z and all 21 weight gradients of a block; ragged mask."""
+    from oracle import ipa_backward
+    W = weights.cast(weights.make_state_dict(seed=5, num_layers=1, flavour='abdesign'), dtype)
+    inp = weights.synthetic_inputs(9, 2, 20, gen_slices=((4, 9),), ragged=True, dtype=dtype)
+    prefix = 'eps_net.encoder.blocks.0.'
+    R, t = G.so3_exp(inp['v']), inp['p'] / 10
+    keys = [k for k in W if k.startswith(prefix)]
+    Wg = dict(W)
+    for k in keys:
+        Wg[k] = W[k].clone().requires_grad_(True)
+    x, z = inp['res_feat'].clone().requires_grad_(True), inp['pair_feat'].clone().requires_grad_(True)
+    out = ipa.ga_block(Wg, prefix, R, t, x, z, inp['mask_res'], materialize=False)
+    g_out = torch.randn(out.shape, dtype=dtype, generator=torch.Generator().manual_seed(1))
+    out.backward(g_out)
+    g_x, g_z, g_w = ipa_backward.ga_block_backward(W, prefix, R, t, inp['res_feat'], inp['pair_feat'], inp['mask_res'], g_out)
+    assert sorted(g_w) == sorted(keys)
+    for name, got, want in [('x', g_x, x.grad), ('z', g_z, z.grad)] + [(k, g_w[k], Wg[k].grad) for k in keys]:
+        assert (got - want).abs().max() <= tol * want.abs().max() + 1e-30, name
+    assert (g_z[~inp['mask_res']] == 0).all()                    # padded query rows receive no gradient
