@@ -268,3 +268,23 @@ def test_hand_written_block_backward_matches_autograd(dtype, tol):
     for name, got, want in [('x', g_x, x.grad), ('z', g_z, z.grad)] + [(k, g_w[k], Wg[k].grad) for k in keys]:
         assert (got - want).abs().max() <= tol * want.abs().max() + 1e-30, name
     assert (g_z[~inp['mask_res']] == 0).all()                    # padded query rows receive no gradient
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float64, 1e-9), (torch.float32, 2e-5)])
+def test_hand_written_training_step_matches_autograd(dtype, tol):
+    """oracle.epsnet_backward.training_step_abdesign -- losses, heads, quaternion update, encoder, mixer and embedding gradients
+    written out by hand -- vs oracle.training.loss_and_grads (= the reference's autograd step): the three losses, all 63
+    parameter gradients and d / d res_feat, d / d pair_feat of one AbDesign-flavour training step."""
+    from oracle import training, epsnet_backward
+    W = weights.cast(weights.make_state_dict(seed=13, num_layers=2, flavour='abdesign'), dtype)
+    inp = weights.synthetic_inputs(23, 2, 12, gen_slices=((0, 5), (8, 10)), ragged=True, dtype=dtype)
+    t = torch.tensor([57, 3])
+    noise = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in T.draw_step_noise(2, 12, torch.Generator().manual_seed(77)).items()}
+    a = (W, inp['v'], inp['p'], inp['s'], inp['res_feat'], inp['pair_feat'], inp['mask_generate'], inp['mask_res'])
+    loss, grads, g_res, g_pair = training.loss_and_grads(*a, True, True, t, noise, flavour='abdesign', obj='pred_noise')
+    loss2, grads2, g_res2, g_pair2 = epsnet_backward.training_step_abdesign(*a, t, noise)
+    assert sorted(loss) == sorted(loss2) and sorted(grads) == sorted(grads2)
+    for k in loss:
+        torch.testing.assert_close(loss2[k], loss[k], rtol=10 * tol, atol=0)
+    for name, got, want in [('res_feat', g_res2, g_res), ('pair_feat', g_pair2, g_pair)] + [(k, grads2[k], grads[k]) for k in grads]:
+        assert (got - want).abs().max() <= tol * want.abs().max() + 1e-30, name
