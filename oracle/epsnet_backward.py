@@ -1,21 +1,22 @@
-"""Oracle (TEST INFRASTRUCTURE ONLY): one whole training step of the AbDesign flavour -- FullDPM.forward and its backward --
-with every gradient written out by hand (no autograd): the losses' derivatives, the three heads, the quaternion update, the
+"""Oracle (TEST INFRASTRUCTURE ONLY): one whole training step -- FullDPM.forward and its backward -- with every gradient
+written out by hand (no autograd): the losses' derivatives, the heads (pRMSD predictor included), the quaternion update, the
 GAEncoder (oracle/ipa_backward.py per block) and the mixer / sequence embedding.  It is the blueprint of the CUDA backward
- and is checked against oracle.training.loss_and_grads, which equals the reference's own
-autograd step (tests/golden/train_backward.npz).
+ and is checked against the gradients the unmodified reference computes with autograd
+(tests/golden/train_backward.npz, AbDock flavour, both objectives) and against oracle.training.loss_and_grads.
 
-Forward being differentiated: /root/reference/AbDesign/diffab/modules/diffusion/dpm_full.py:62-102 (EpsilonNet.forward) and
-:138-190 (FullDPM.forward: rot / pos / seq losses, position loss on the predicted noise), evaluated with the reference's
-grad-enabled log_rotation clamp (so3.py:12-17).
+Forward being differentiated: EpsilonNet.forward and FullDPM.forward of
+  /root/reference/AbDock/src/modules/diffusion/dpm_full.py:70-112, 156-234   ('abdock': + pRMSD and, for obj pred_x0, distance loss)
+  /root/reference/AbDesign/diffab/modules/diffusion/dpm_full.py:62-102, 138-190   ('abdesign': rot / pos / seq)
+evaluated with the reference's grad-enabled log_rotation clamp (so3.py:12-17); the loss is the unweighted sum of the dict.
 """
 import torch
 import torch.nn.functional as F
 
 from . import transitions as T
 from .geometry import grad_enabled_semantics, quat_1ijk_to_rotation, so3_exp
-from .ipa_backward import _linear_backward, ga_block_backward
-from .ipa import ga_block
-from .epsnet import num_layers_of
+from .ipa_backward import _layer_norm_backward, _linear_backward, ga_block_backward
+from .ipa import ga_block, layer_norm
+from .epsnet import has_prmsd, num_layers_of
 
 
 def _mlp3_forward(W, p, x):
@@ -49,7 +50,12 @@ def _quat_1ijk_backward(o, G):
 
 
 def training_step_abdesign(W, v_0, p_0, s_0, res_feat, pair_feat, mask_generate, mask_res, t, noise):
-    """-> (loss dict, {key: gradient} for every parameter, d / d res_feat, d / d pair_feat) of loss = rot + pos + seq."""
+    return training_step(W, v_0, p_0, s_0, res_feat, pair_feat, mask_generate, mask_res, t, noise, flavour='abdesign')
+
+
+def training_step(W, v_0, p_0, s_0, res_feat, pair_feat, mask_generate, mask_res, t, noise, flavour='abdock', obj='pred_x0',
+                  dist_min=0.5, dist_max=19.5):
+    """-> (loss dict, {key: gradient} for every parameter, d / d res_feat, d / d pair_feat) of loss = sum of the loss dict."""
     N, L = mask_generate.shape
     dt = p_0.dtype
     grads = {}
@@ -89,9 +95,49 @@ def training_step_abdesign(W, v_0, p_0, s_0, res_feat, pair_feat, mask_generate,
     cos = (R_pred * R_0).sum(-2) / torch.sqrt(nx2 * ny2)
     loss = {'rot': (((1 - cos).sum(-1)) * mg).sum() / denom}
     g_Rpred = -(R_0 / torch.sqrt(nx2 * ny2)[..., None, :] - R_pred * (cos / nx2)[..., None, :]) * wgt[..., None]
-    # pos: |eps_pos - eps|^2
-    loss['pos'] = ((eps_pos - eps_p).pow(2).sum(-1) * mg).sum() / denom
-    g_eps_pos = 2 * (eps_pos - eps_p) * wgt
+    # pos: |prediction - target|^2; the target is the noise (AbDesign :176), p_0 (AbDock pred_x0 :186-188) or p_noisy (AbDock
+    # pred_noise, sic :189-191)
+    pos_target = eps_p if flavour == 'abdesign' else (p_0n if obj == 'pred_x0' else p_t)
+    loss['pos'] = ((eps_pos - pos_target).pow(2).sum(-1) * mg).sum() / denom
+    g_eps_pos = 2 * (eps_pos - pos_target) * wgt
+    g_hcat = torch.zeros_like(hcat)
+    if flavour == 'abdock' and obj == 'pred_x0':
+        # dist: SmoothL1 between the distance maps of p_pred and p_0 over rows of generated residues (dpm_full.py:369-378)
+        dvec = eps_pos[:, :, None] - eps_pos[:, None]
+        dp, dtrue = dvec.norm(dim=-1), torch.cdist(p_0n, p_0n)
+        sel = (mask_generate[:, :, None] & mask_res[:, :, None] & mask_res[:, None, :]).to(dt)
+        u = dp - dtrue
+        loss['dist'] = (torch.where(u.abs() < 1, 0.5 * u * u, u.abs() - 0.5) * sel).sum() / sel.sum()
+        g_dp = torch.where(u.abs() < 1, u, torch.sign(u)) * sel / sel.sum()
+        g_dp = (g_dp + g_dp.transpose(1, 2)) / dp.clamp_min(1e-30) * (dp > 0)                      # d |p_i - p_j| = (p_i - p_j) / |.|
+        g_eps_pos = g_eps_pos + (g_dp[..., None] * dvec).sum(2)
+    if flavour == 'abdock' and has_prmsd(W):
+        # pRMSD: cross entropy of the per-complex logits against the bin of the achieved RMSD (prmsd.py:53-69); the bin is an
+        # argmin, so nothing flows back through the RMSD itself
+        from .training import calc_rmsd
+        pp = 'eps_net.prmsd_predictor.'
+        ln = layer_norm(hcat, W[pp + 'layer_norm.gamma'], W[pp + 'layer_norm.beta'])
+        b0 = F.linear(ln, W[pp + 'linear_1.weight'], W[pp + 'linear_1.bias'])
+        b1 = F.linear(F.relu(b0), W[pp + 'linear_2.weight'], W[pp + 'linear_2.bias'])
+        logits = F.linear(F.relu(b1), W[pp + 'linear_3.weight'], W[pp + 'linear_3.bias']).mean(dim=1)
+        if obj == 'pred_x0':
+            pred_p0 = eps_pos
+        else:
+            c0 = W['trans_pos.var_sched.sqrt_recip_alphas_cumprod'].to(dt)[t].view(-1, 1, 1)
+            c1 = W['trans_pos.var_sched.sqrt_recipm1_alphas_cumprod'].to(dt)[t].view(-1, 1, 1)
+            pred_p0 = torch.where(mask_generate[..., None].expand_as(p_0n), c0 * p_0n - c1 * eps_pos, p_0n)
+        rmsd = calc_rmsd(pred_p0 * scale + mean, p_0n * scale + mean, mask_generate)
+        offset = torch.linspace(dist_min, dist_max, logits.shape[-1]).to(dt)
+        onehot = torch.zeros_like(logits).scatter_(-1, torch.argmin(torch.abs(rmsd.unsqueeze(-1) - offset), dim=-1, keepdim=True), 1.0)
+        m0 = mask_generate[:, 0].to(dt)
+        loss['prmsd'] = (-(onehot * F.log_softmax(logits, -1)).sum(-1) * m0).sum() / (m0.sum() + 1e-10)
+        g_logits = (torch.softmax(logits, -1) - onehot) * (m0 / (m0.sum() + 1e-10))[:, None]
+        g = (g_logits / L)[:, None, :].expand(N, L, -1)                                            # mean over ALL L rows
+        g, grads[pp + 'linear_3.weight'], grads[pp + 'linear_3.bias'] = _linear_backward(g, F.relu(b1), W[pp + 'linear_3.weight'])
+        g, grads[pp + 'linear_2.weight'], grads[pp + 'linear_2.bias'] = _linear_backward(g * (b1 > 0), F.relu(b0), W[pp + 'linear_2.weight'])
+        g, grads[pp + 'linear_1.weight'], grads[pp + 'linear_1.bias'] = _linear_backward(g * (b0 > 0), ln, W[pp + 'linear_1.weight'])
+        g, grads[pp + 'layer_norm.gamma'], grads[pp + 'layer_norm.beta'] = _layer_norm_backward(g, hcat, W[pp + 'layer_norm.gamma'])
+        g_hcat += g
     # seq: KL(posterior(s_t, s_0) || posterior(s_t, c_denoised)), transition.py:202-227
     c_t, c_0 = T.one_hot_clamped(s_t, T.NUM_AA, dt), T.one_hot_clamped(s_0, T.NUM_AA, dt)
     a = W['trans_seq.var_sched.alpha_bars'].to(dt)[t][:, None, None]
@@ -110,7 +156,6 @@ def training_step_abdesign(W, v_0, p_0, s_0, res_feat, pair_feat, mask_generate,
     g_seq = c_den * (g_cden - (c_den * g_cden).sum(-1, keepdim=True))                              # softmax
     g_crd = torch.einsum('nlba,nlb->nla', R, g_eps_pos * gen)                                      # eps_pos = R o, masked
     g_rot = _quat_1ijk_backward(heads['rot'][2], torch.einsum('nlba,nlbc->nlac', R, g_Rpred))      # R_pred = R U
-    g_hcat = torch.zeros_like(hcat)
     for h, g in (('crd', g_crd), ('rot', g_rot), ('seq', g_seq)):
         g_hcat += _mlp3_backward(W, f'eps_net.eps_{h}_net.', hcat, heads[h][0], heads[h][1], g, grads)
     # ------------------------------------------------------------------ encoder backward: one recompute-based block at a time

@@ -288,3 +288,29 @@ def test_hand_written_training_step_matches_autograd(dtype, tol):
         torch.testing.assert_close(loss2[k], loss[k], rtol=10 * tol, atol=0)
     for name, got, want in [('res_feat', g_res2, g_res), ('pair_feat', g_pair2, g_pair)] + [(k, grads2[k], grads[k]) for k in grads]:
         assert (got - want).abs().max() <= tol * want.abs().max() + 1e-30, name
+
+
+@pytest.mark.parametrize('obj', ['pred_x0', 'pred_noise'])
+def test_hand_written_training_step_matches_the_reference_gradients(golden_dir, obj):
+    """oracle.epsnet_backward.training_step (AbDock flavour: + pRMSD head and loss, distance loss; no autograd anywhere) vs the
+    gradients the UNMODIFIED REFERENCE computed with loss.backward() (tests/golden/train_backward.npz): losses, the gradient norm
+    of all 71 parameters, ten full gradients, d / d res_feat and d / d pair_feat."""
+    from oracle import epsnet_backward
+    d = np.load(os.path.join(golden_dir, 'train_backward.npz'))
+    g = {k: (torch.from_numpy(d[k]) if d[k].dtype.kind != 'U' and d[k].ndim else d[k]) for k in d.files}
+    W = weights.make_state_dict(seed=int(g['seed_w']), num_layers=int(g['num_layers']), flavour='abdock')
+    inp = weights.synthetic_inputs(int(g['seed_in']), int(g['N']), int(g['L']), gen_slices=((0, 5), (8, 10)), ragged=True)
+    noise = T.draw_step_noise(int(g['N']), int(g['L']), torch.Generator().manual_seed(int(g['seed_noise'])))
+    loss, grads, g_res, g_pair = epsnet_backward.training_step(W, inp['v'], inp['p'], inp['s'], inp['res_feat'], inp['pair_feat'],
+                                                               inp['mask_generate'], inp['mask_res'], g['t'], noise, flavour='abdock', obj=obj)
+    for k, v in loss.items():
+        torch.testing.assert_close(v, torch.as_tensor(g[f'{obj}_loss_{k}'].item()), rtol=2e-5, atol=2e-6, msg=lambda m, k=k: f'{k}: {m}')
+    names = [str(x) for x in g[f'{obj}_param_names']]
+    assert sorted(grads) == names
+    torch.testing.assert_close(torch.stack([grads[k].double().norm() for k in names]), g[f'{obj}_grad_norms'], rtol=1e-4, atol=1e-9)
+    for key in d.files:
+        if key.startswith(f'{obj}_grad_eps_net.'):
+            want, got = g[key], grads[key[len(obj) + 6:]]
+            assert (got - want).abs().max() <= 2e-5 * want.abs().max() + 1e-9, key
+    for got, want in ((g_res, g[f'{obj}_grad_res_feat']), (g_pair, g[f'{obj}_grad_pair_feat'])):
+        assert (got - want).abs().max() <= 2e-5 * want.abs().max()
