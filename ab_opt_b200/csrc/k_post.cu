@@ -131,12 +131,12 @@ __global__ void __launch_bounds__(256) rank_kernel(int B, int k, const float* __
 using namespace abopt;
 
 static int post_device_check() {
-  int dev = 0;
+  int dev = 0, major = 0;
   cudaError_t e = cudaGetDevice(&dev);
-  cudaDeviceProp prop;
-  if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);     // cheap: these run per call
   if (e != cudaSuccess) return api_fail(ABOPT_ERR_CUDA, std::string("no usable CUDA device: ") + cudaGetErrorString(e));
-  if (prop.major != 10) return api_fail(ABOPT_ERR_CUDA, std::string("libabopt_b200 needs a B200-class GPU (sm_100); found ") + prop.name);
+  if (major != 10) return api_fail(ABOPT_ERR_CUDA, "libabopt_b200 needs a B200-class GPU (sm_100); the current device has compute capability " +
+                                                       std::to_string(major) + ".x");
   return ABOPT_OK;
 }
 
