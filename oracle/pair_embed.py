@@ -209,7 +209,20 @@ def residue_embedding(W, aa, res_nb, chain_nb, pos_atoms, mask_atoms, fragment_t
     if structure_mask is not None:                                                                  # residue.py:77-86
         near = structure_mask & torch.roll(structure_mask, 1, 1) & torch.roll(structure_mask, -1, 1)
         f_ang = f_ang * near[:, :, None]
-    h = torch.cat([f_aa, f_crd, f_ang, W['type_embed.weight'][fragment_type]], dim=-1)              # residue.py:89-92
+    f_type = torch.nn.functional.embedding(fragment_type, W['type_embed.weight'], padding_idx=0)   # residue.py:17,89: row 0 gets no gradient
+    h = torch.cat([f_aa, f_crd, f_ang, f_type], dim=-1)                                             # residue.py:89-92
     for i in range(3):
         h = torch.relu(lin(f'mlp.{2 * i}', h))
     return lin('mlp.6', h) * has_ca[:, :, None]                                                     # residue.py:93
+
+
+def embedding_grads(which, W, g_out, *inputs):
+    """Backward target of the featurisation for the training step: gradients of sum(out * g_out) with
+    respect to every floating weight of `pair_embedding` (which='pair') or `residue_embedding` (which='residue'), by torch
+    autograd through the oracle; g_out is d loss / d pair_feat (resp. res_feat) as the hand-written step in
+    oracle/epsnet_backward.py returns it.  Pinned to the reference's own autograd by tests/golden/pair_embed.npz."""
+    fn = pair_embedding if which == 'pair' else residue_embedding
+    Wg = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and 'freq_bands' not in k else v) for k, v in W.items()}
+    with torch.enable_grad():
+        (fn(Wg, *inputs) * g_out).sum().backward()
+    return {k: v.grad for k, v in Wg.items() if v.requires_grad and v.grad is not None}

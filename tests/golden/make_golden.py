@@ -121,6 +121,22 @@ def make_pair_embed():
         args = (inp['aa'], inp['res_nb'], inp['chain_nb'], inp['pos_atoms'], inp['mask_atoms'], ft)
         keep[f'x_a{A}_plain'] = ref(*args)
         keep[f'x_a{A}_masked'] = ref(*args, structure_mask=inp['context_mask'], sequence_mask=inp['context_mask'])
+    # backward of both modules as the reference's autograd computes it (full-atom tables, masked call): d sum(out * G) / d weights
+    with torch.enable_grad():
+        gz = torch.randn(N, L, L, 64, generator=torch.Generator().manual_seed(31))
+        gx = torch.randn(N, L, 128, generator=torch.Generator().manual_seed(32))
+        ref = PairEmbedding(64, 15)
+        ref.load_state_dict(PE.make_state_dict(seed_w, 15), strict=True)
+        (ref(inp['aa'], inp['res_nb'], inp['chain_nb'], inp['pos_atoms'], inp['mask_atoms'], structure_mask=inp['context_mask'],
+             sequence_mask=inp['context_mask']) * gz).sum().backward()
+        for k, p_ in ref.named_parameters():
+            keep['gradz_' + k] = p_.grad
+        ref = ResidueEmbedding(128, 15)
+        ref.load_state_dict(PE.make_residue_state_dict(seed_w + 1, 15), strict=True)
+        (ref(inp['aa'], inp['res_nb'], inp['chain_nb'], inp['pos_atoms'], inp['mask_atoms'], ft, structure_mask=inp['context_mask'],
+             sequence_mask=inp['context_mask']) * gx).sum().backward()
+        for k, p_ in ref.named_parameters():
+            keep['gradx_' + k] = p_.grad
     npz('pair_embed.npz', seed_w=seed_w, seed_in=seed_in, N=N, L=L, fragment_type=ft, **inp, **keep)
 
 

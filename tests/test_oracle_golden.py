@@ -314,3 +314,25 @@ def test_hand_written_training_step_matches_the_reference_gradients(golden_dir, 
             assert (got - want).abs().max() <= 2e-5 * want.abs().max() + 1e-9, key
     for got, want in ((g_res, g[f'{obj}_grad_res_feat']), (g_pair, g[f'{obj}_grad_pair_feat'])):
         assert (got - want).abs().max() <= 2e-5 * want.abs().max()
+
+
+def test_embedding_backward_matches_reference(golden_dir):
+    """oracle.pair_embed.embedding_grads vs the reference's own autograd through PairEmbedding / ResidueEmbedding (weight
+    gradients of sum(out * G) stored in tests/golden/pair_embed.npz): the featurisation's share of a training step's backward."""
+    from oracle import pair_embed as PE
+    g = load(golden_dir, 'pair_embed.npz')
+    inp = PE.synthetic_complex(g['seed_in'], g['N'], g['L'])
+    m = inp['context_mask']
+    base = (inp['aa'], inp['res_nb'], inp['chain_nb'], inp['pos_atoms'], inp['mask_atoms'])
+    gz = torch.randn(g['N'], g['L'], g['L'], 64, generator=torch.Generator().manual_seed(31))
+    gx = torch.randn(g['N'], g['L'], 128, generator=torch.Generator().manual_seed(32))
+    got = PE.embedding_grads('pair', PE.make_state_dict(g['seed_w'], 15), gz, *base, m, m)
+    want = {k[len('gradz_'):]: v for k, v in g.items() if k.startswith('gradz_')}
+    assert sorted(got) == sorted(want) and len(want) == 13
+    for k in want:
+        assert (got[k] - want[k]).abs().max() <= 2e-5 * want[k].abs().max() + 1e-12, k
+    got = PE.embedding_grads('residue', PE.make_residue_state_dict(g['seed_w'] + 1, 15), gx, *base, g['fragment_type'], m, m)
+    want = {k[len('gradx_'):]: v for k, v in g.items() if k.startswith('gradx_')}
+    assert sorted(got) == sorted(want) and len(want) == 10
+    for k in want:
+        assert (got[k] - want[k]).abs().max() <= 2e-5 * want[k].abs().max() + 1e-12, k
