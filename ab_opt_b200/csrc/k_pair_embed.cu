@@ -367,7 +367,7 @@ struct abopt_pair_embed {
 
 extern "C" int abopt_pair_embed_create(int max_num_atoms, int device, abopt_pair_embed** out) {
   if (!out) return api_fail(ABOPT_ERR_ARG, "null argument");
-  if (max_num_atoms < 3 || max_num_atoms > PE_MAXA) return api_fail(ABOPT_ERR_ARG, "max_num_atoms must be in [3, 15] (N, CA, C are needed)");
+  if (max_num_atoms < 4 || max_num_atoms > PE_MAXA) return api_fail(ABOPT_ERR_ARG, "max_num_atoms must be in [4, 15] (backbone N, CA, C, O at least)");
   int ndev = 0;
   PE_CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return api_fail(ABOPT_ERR_ARG, "no such CUDA device");

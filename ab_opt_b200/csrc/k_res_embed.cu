@@ -217,7 +217,7 @@ struct abopt_res_embed {
 
 extern "C" int abopt_res_embed_create(int max_num_atoms, int device, abopt_res_embed** out) {
   if (!out) return api_fail(ABOPT_ERR_ARG, "null argument");
-  if (max_num_atoms < 3 || max_num_atoms > RE_MAXA) return api_fail(ABOPT_ERR_ARG, "max_num_atoms must be in [3, 15] (N, CA, C are needed)");
+  if (max_num_atoms < 4 || max_num_atoms > RE_MAXA) return api_fail(ABOPT_ERR_ARG, "max_num_atoms must be in [4, 15] (backbone N, CA, C, O at least)");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess) return api_fail(ABOPT_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));

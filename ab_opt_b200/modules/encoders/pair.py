@@ -86,9 +86,9 @@ class PairEmbedding(nn.Module):
 
     def __init__(self, feat_dim, max_num_atoms, max_aa_types=22, max_relpos=32):
         super().__init__()
-        if (feat_dim, max_aa_types, max_relpos) != (64, 22, 32) or not 3 <= max_num_atoms <= 15:
+        if (feat_dim, max_aa_types, max_relpos) != (64, 22, 32) or not 4 <= max_num_atoms <= 15:
             raise ValueError('the sm_100a kernel is specialised for the reference configuration: feat_dim 64, 22 amino-acid '
-                             'types, max_relpos 32, 3..15 atoms per residue')
+                             'types, max_relpos 32, 4..15 atoms per residue')
         self.max_num_atoms, self.max_aa_types, self.max_relpos = max_num_atoms, max_aa_types, max_relpos
         self.aa_pair_embed = nn.Embedding(max_aa_types * max_aa_types, feat_dim)
         self.relpos_embed = nn.Embedding(2 * max_relpos + 1, feat_dim)
@@ -124,9 +124,9 @@ class ResidueEmbedding(nn.Module):
 
     def __init__(self, feat_dim, max_num_atoms, max_aa_types=22):
         super().__init__()
-        if (feat_dim, max_aa_types) != (128, 22) or not 3 <= max_num_atoms <= 15:
+        if (feat_dim, max_aa_types) != (128, 22) or not 4 <= max_num_atoms <= 15:
             raise ValueError('the sm_100a kernel is specialised for the reference configuration: feat_dim 128, 22 amino-acid '
-                             'types, 3..15 atoms per residue')
+                             'types, 4..15 atoms per residue')
         self.max_num_atoms, self.max_aa_types = max_num_atoms, max_aa_types
         self.aatype_embed = nn.Embedding(max_aa_types, feat_dim)
         self.dihed_embed = AngularEncoding()
