@@ -11,21 +11,24 @@ from .modules.encoders.pair import PairEmbedding, ResidueEmbedding
 from . import post
 from .post import reconstruct_backbone_partially, calc_per_rmsd, calc_avg_rmsd, rank_commoness
 from .modules.diffusion.dpm_full import EpsilonNet, FullDPM, FullDPMAbDesign
+from .models.diffab import DiffusionAntibodyDesign
 from .modules.diffusion.transition import (VarianceSchedule, PositionTransition, RotationTransition,
                                            AminoacidCategoricalTransition)
 
 __all__ = ['GABlock', 'GAEncoder', 'PairEmbedding', 'ResidueEmbedding', 'reconstruct_backbone_partially', 'calc_per_rmsd', 'calc_avg_rmsd',
-           'rank_commoness', 'EpsilonNet', 'FullDPM', 'FullDPMAbDesign', 'VarianceSchedule',
+           'rank_commoness', 'EpsilonNet', 'FullDPM', 'FullDPMAbDesign', 'DiffusionAntibodyDesign', 'VarianceSchedule',
            'PositionTransition', 'RotationTransition', 'AminoacidCategoricalTransition', 'AboptError',
            'launch_count', 'install_into_reference']
 
 
-def install_into_reference(package='src'):
+def install_into_reference(package='src', fused=True):
     """Swap the reference's hot-path classes for the B200 ones so that its entry points
     (dock_pdb.py / design_pdb.py, configs/*.yml, checkpoints) run unchanged.
 
     package = 'src' (AbDock) or 'diffab' (AbDesign); the reference package must be importable.
     Must be called before the reference's `models/diffab.py` is imported.
+    fused=True additionally registers ab_opt_b200.DiffusionAntibodyDesign under the reference's model name 'diffab'
+    (models/_base.py:4-13), so `get_model(cfg.model).sample(batch)` is one device-resident encode + sample call.
     """
     import importlib
     dpm = importlib.import_module(f'{package}.modules.diffusion.dpm_full')
@@ -46,4 +49,12 @@ def install_into_reference(package='src'):
         runner.calc_per_rmsd, runner.calc_avg_rmsd, runner.rank_commoness = calc_per_rmsd, calc_avg_rmsd, rank_commoness
     except ImportError:
         pass
+    if fused:
+        try:
+            importlib.import_module(f'{package}.models')          # registers the reference's own class first ...
+            base = importlib.import_module(f'{package}.models._base')
+            flavour = 'abdock' if package == 'src' else 'abdesign'
+            base._MODEL_DICT['diffab'] = lambda cfg: DiffusionAntibodyDesign(cfg, flavour=flavour)      # ... then ours replaces it
+        except ImportError:
+            pass
     return dpm, ga

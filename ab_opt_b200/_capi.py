@@ -22,10 +22,10 @@ EXPORTS = (
     'abopt_ga_encoder_forward', 'abopt_ga_block_taps', 'abopt_eps_net_forward', 'abopt_rot_denoise',
     'abopt_pos_pred_noise_from_start', 'abopt_pos_denoise', 'abopt_seq_denoise', 'abopt_sample_device',
     'abopt_sample_host', 'abopt_workspace_bytes', 'abopt_sample_init', 'abopt_reverse_step', 'abopt_profile_enable', 'abopt_profile_collect', 'abopt_debug_gemm3x', 'abopt_debug_clocks',
-    'abopt_loss_forward', 'abopt_pair_embed_create', 'abopt_pair_embed_destroy', 'abopt_pair_embed_set_tensor',
+    'abopt_loss_forward', 'abopt_model_set_batch_offset', 'abopt_pair_embed_create', 'abopt_pair_embed_destroy', 'abopt_pair_embed_set_tensor',
     'abopt_pair_embed_finalize', 'abopt_pair_embed_forward', 'abopt_res_embed_create', 'abopt_res_embed_destroy',
     'abopt_res_embed_set_tensor', 'abopt_res_embed_finalize', 'abopt_res_embed_forward',
-    'abopt_reconstruct_backbone_partially', 'abopt_pairwise_rmsd', 'abopt_rank_commoness',
+    'abopt_reconstruct_backbone_partially', 'abopt_pairwise_rmsd', 'abopt_rank_commoness', 'abopt_design_device', 'abopt_design_host',
 )
 
 
@@ -67,6 +67,7 @@ def lib():
         L.abopt_model_destroy.restype = None
         L.abopt_model_set_tensor.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
         L.abopt_model_finalize.argtypes = [C.c_void_p]
+        L.abopt_model_set_batch_offset.argtypes = [C.c_void_p, C.c_int64]
         vp, ci = C.c_void_p, C.c_int
         L.abopt_ga_block_forward.argtypes = [vp, ci, ci, ci] + [vp] * 7
         L.abopt_ga_encoder_forward.argtypes = [vp, ci, ci] + [vp] * 7
@@ -98,6 +99,8 @@ def lib():
         L.abopt_reconstruct_backbone_partially.argtypes = [ci, ci, ci] + [vp] * 13
         L.abopt_pairwise_rmsd.argtypes = [ci, ci] + [vp] * 5
         L.abopt_rank_commoness.argtypes = [ci, ci, vp, ci, vp, vp, vp]
+        L.abopt_design_device.argtypes = [vp, vp, vp, ci, ci, ci] + [vp] * 8 + [C.c_uint32, ci, C.c_uint64] + [vp] * 6
+        L.abopt_design_host.argtypes = [vp, vp, vp, ci, ci, ci] + [vp] * 8 + [C.c_uint32, ci, C.c_uint64] + [vp] * 5
         _lib = L
     return _lib
 

@@ -63,7 +63,7 @@ struct Workspace {
   size_t bytes = 0;
   void* base = nullptr;
   AttnOperands op;
-  float *Rbuf, *pnorm, *xa, *xb, *xa_lo, *xb_lo, *xin_lo, *feat, *feat_lo, *outD, *alpha, *prmsd_rows, *prmsd_logits, *maxprob;
+  float *Rbuf, *pnorm, *xa, *xb, *xa_lo, *xb_lo, *xin_lo, *feat, *alpha, *prmsd_rows, *prmsd_logits, *maxprob;
   float *v_net, *eps_pos, *c_den, *R_next;
   int* bin_idx;
   long long* tvec_scratch;
@@ -98,6 +98,9 @@ struct abopt_model {
   HostIO io;
   cudaStream_t own_stream = nullptr;
   void* train_buf = nullptr; size_t train_bytes = 0;      // scratch of abopt_loss_forward
+  void* design_buf = nullptr; size_t design_bytes = 0;    // scratch of abopt_design_*: context mask, v_0, p_0, res_feat, pair_feat
+  void* design_io = nullptr; size_t design_io_bytes = 0;  // device staging of abopt_design_host
+  long long batch_offset = 0;                             // index of this handle's first complex in the global (unsharded) batch
 };
 
 static void add_key(abopt_model* m, const std::string& k, size_t numel, int dtype = 0, bool required = true) {
@@ -231,7 +234,10 @@ extern "C" int abopt_model_create(const abopt_config* cfg, int device, abopt_mod
   m->cfg = *cfg;
   m->device = device;
   build_spec(m);
-  CUDA_TRY(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+  {
+    const cudaError_t e = cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete m; return fail(ABOPT_ERR_CUDA, std::string("cudaStreamCreateWithFlags: ") + cudaGetErrorString(e)); }
+  }
   *out = m;
   return ABOPT_OK;
 }
@@ -243,8 +249,18 @@ extern "C" void abopt_model_destroy(abopt_model* m) {
   if (m->ws.base) cudaFree(m->ws.base);
   if (m->io.base) cudaFree(m->io.base);
   if (m->bias_buf) cudaFree(m->bias_buf);
+  if (m->train_buf) cudaFree(m->train_buf);
+  if (m->design_buf) cudaFree(m->design_buf);
+  if (m->design_io) cudaFree(m->design_io);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   delete m;
+}
+
+extern "C" int abopt_model_set_batch_offset(abopt_model* m, int64_t first_complex) {
+  if (!m) return fail(ABOPT_ERR_ARG, "null model");
+  if (first_complex < 0) return fail(ABOPT_ERR_ARG, "first_complex must be >= 0");
+  m->batch_offset = (long long)first_complex;
+  return ABOPT_OK;
 }
 
 extern "C" int abopt_model_set_tensor(abopt_model* m, const char* key, const void* data, size_t numel, int dtype, int on_device) {
@@ -473,7 +489,7 @@ static int ensure_workspace(abopt_model* m, int N, int L) {
                oAl = take((size_t)NB * H * L * Lp * 4), oPr = take(M * bins * 4), oPl = take((size_t)N * bins * 4),
                oMp = take(M * 4), oVn = take(M * 3 * 4), oEp = take(M * 3 * 4), oCd = take(M * NAA * 4), oRn = take(M * 9 * 4),
                oBi = take(M * 4), oTv = take((size_t)N * 8), oXal = take(M * F * 4), oXbl = take(M * F * 4), oXil = take(M * F * 4),
-               oFl = take(M * NFEAT * 4), oOd = take(M * F * 4), oQa = take(M * H * 64 * 4), oQl = take(M * H * 64 * 4),
+               oQa = take(M * H * 64 * 4), oQl = take(M * H * 64 * 4),
                oKb = take(M * H * 64 * 4), oKl = take(M * H * 64 * 4), oRq = take(M * H * 4), oRk = take(M * H * 4),
                oVt = take((size_t)N * H * 64 * Lp * 4), oVl = take((size_t)N * H * 64 * Lp * 4),
                oFc = take(M * 4), oFr = take(M * 4), oFw = take((size_t)N * (L / 64 + 2) * 8), oFn = take(64), oFs = take((size_t)N * 8),
@@ -486,8 +502,7 @@ static int ensure_workspace(abopt_model* m, int N, int L) {
   w.prmsd_rows = (float*)(b + oPr); w.prmsd_logits = (float*)(b + oPl); w.maxprob = (float*)(b + oMp);
   w.v_net = (float*)(b + oVn); w.eps_pos = (float*)(b + oEp); w.c_den = (float*)(b + oCd); w.R_next = (float*)(b + oRn);
   w.bin_idx = (int*)(b + oBi); w.tvec_scratch = (long long*)(b + oTv);
-  w.xa_lo = (float*)(b + oXal); w.xb_lo = (float*)(b + oXbl); w.xin_lo = (float*)(b + oXil); w.feat_lo = (float*)(b + oFl);
-  w.outD = (float*)(b + oOd);
+  w.xa_lo = (float*)(b + oXal); w.xb_lo = (float*)(b + oXbl); w.xin_lo = (float*)(b + oXil);
   w.op = AttnOperands{(float*)(b + oQa), (float*)(b + oQl), (float*)(b + oKb), (float*)(b + oKl), (float*)(b + oRq), (float*)(b + oRk),
                       (float*)(b + oVt), (float*)(b + oVl)};
   w.focus = Focus{(int*)(b + oFc), (int*)(b + oFr), (int2*)(b + oFw), (int*)(b + oFn), (int*)(b + oFs), (float*)(b + oFx), (uint8_t*)(b + oFm)};
@@ -539,9 +554,6 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
     return fail(ABOPT_ERR_ARG, "pair_bias_kernel: L too large for shared memory");
   // the six input projections: tcgen05 3xTF32 GEMM (x raw = "hi" plane, x_lo = "lo" plane)
   if (x_lo == nullptr) { launch_lo(x, w.xin_lo, (size_t)M * F, st); x_lo = w.xin_lo; }
-  // ABOPT_OUTT_LEGACY=1: materialise feat_lo and use the plain 3xTF32 GEMM for out_transform (A/B comparisons)
-  static const bool outt_legacy = [] { const char* ev = getenv("ABOPT_OUTT_LEGACY"); return ev && ev[0] == '1'; }();
-  float* flo = outt_legacy ? w.feat_lo : nullptr;
   for (int b0 = 0; b0 < N; b0 += w.NB) {
     const int nb = (N - b0 < w.NB) ? (N - b0) : w.NB;
     // one pass = as many complexes as the alpha buffer holds (normally the whole batch, see chunk_size): projections ->
@@ -556,28 +568,21 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
     // logits (node + spatial + pair bias, scaled, masked) and softmax on the tensor cores -> alpha
     if (!launch_attn_logits_tc(nb, b0, N, L, w.Lp, w.op, bias, mask, w.alpha, st, fc ? fc->windows : nullptr, fc ? fc->count : nullptr))
       return fail(ABOPT_ERR_CUDA, "attn_logits_tc launch failed");
-    if (!launch_pair_stream(nb, b0, L, w.Lp, z, mask, w.alpha, w.feat, flo, st, fc ? fc->cidx : nullptr))
+    if (!launch_pair_stream(nb, b0, L, w.Lp, z, mask, w.alpha, w.feat, st, fc ? fc->cidx : nullptr))
       return fail(ABOPT_ERR_ARG, "pair_stream_kernel: L too large for shared memory");
-    if (!launch_aggr_tc(nb, b0, N, L, w.Lp, w.alpha, w.op.VT, w.op.VT_lo, R, t, w.feat, flo, st, fc ? fc->windows : nullptr,
+    if (!launch_aggr_tc(nb, b0, N, L, w.Lp, w.alpha, w.op.VT, w.op.VT_lo, R, t, w.feat, st, fc ? fc->windows : nullptr,
                         fc ? fc->count : nullptr, fc ? fc->cidx : nullptr))
       return fail(ABOPT_ERR_CUDA, "aggr_tc launch failed");
     if (alpha_tap) launch_alpha_tap(nb, b0, L, w.Lp, w.alpha, alpha_tap, st);
   }
   if (x_out) {
-    // out_transform (K = 1824) on the tensor cores, then mask / residual / LN / MLP / LN
-    // ABOPT_TAIL_LEGACY=1: out_transform GEMM + CUDA-core tail_kernel instead of the fused tensor-core tail (A/B comparisons)
-    static const bool tail_legacy = [] { const char* ev = getenv("ABOPT_TAIL_LEGACY"); return ev && ev[0] == '1'; }();
+    // out_transform (K = 1824) on the tensor cores, then mask / residual / LN / MLP / LN, one kernel
     if (fc) {
       launch_focus_gather(fc->rows, fc->count, x, mask, fc->x_c, fc->mask_c, st);
       if (!launch_outT_tail(M, w.feat, fc->x_c, fc->mask_c, bw, x_out, nullptr, st, fc->count))
         return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (tail)");
-    } else if (!flo && !tail_legacy) {
-      if (!launch_outT_tail(M, w.feat, x, mask, bw, x_out, x_lo_out, st)) return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (tail)");
-    } else {
-      const bool ok = flo ? launch_gemm3x_plain(M, F, NFEAT, w.feat, flo, NFEAT, bw.Wout, bw.Wout_lo, NFEAT, w.outD, F, bw.bout, st)
-                          : launch_gemm3x_splitA(M, F, NFEAT, w.feat, NFEAT, bw.Wout, bw.Wout_lo, NFEAT, w.outD, F, bw.bout, st);
-      if (!ok) return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (out_transform)");
-      launch_tail(M, w.feat, w.outD, x, mask, bw, x_out, x_lo_out, st);
+    } else if (!launch_outT_tail(M, w.feat, x, mask, bw, x_out, x_lo_out, st)) {
+      return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (tail)");
     }
   }
   CHECK_LAUNCH();
@@ -652,13 +657,9 @@ static int run_eps_net(abopt_model* m, int N, int L, const float* v_t, const flo
   const int M = N * L;
   // "focus": the caller consumes the outputs on generated residues only (sampling loop, no pRMSD head), so the last
   // GABlock and the heads run on those rows alone.  Results on the consumed rows are unchanged.
-  static const bool focus_off = [] {
-    for (const char* k : {"ABOPT_NO_FOCUS", "ABOPT_ATTN_LEGACY", "ABOPT_AGGR_LEGACY", "ABOPT_TAIL_LEGACY", "ABOPT_OUTT_LEGACY"}) {
-      const char* ev = getenv(k);
-      if (ev && ev[0] == '1') return true;
-    }
-    return false;
-  }();
+  // ABOPT_NO_FOCUS=1 computes every row (read per call: the parity tests run both ways in one process)
+  const char* nf = getenv("ABOPT_NO_FOCUS");
+  const bool focus_off = nf && nf[0] == '1';
   const Focus* fc = nullptr;      // last block + heads on the generated rows (models without the pRMSD head)
   const Focus* hf = nullptr;      // crd / rot / seq heads on the generated rows (every model); the pRMSD head needs all rows
   if (focus && !focus_off && m->cfg.num_layers >= 1) {
@@ -754,7 +755,7 @@ static int run_init(abopt_model* m, int N, int L, const float* v, const float* p
   ia.has_prmsd = (m->cfg.has_prmsd && prmsd_out && ppl_out) ? 1 : 0;
   ia.v = v; ia.p_ang = p; ia.s = s; ia.mask_gen = mask_generate;
   ia.v_out = v_out; ia.p_out_ang = p_out; ia.s_out = s_out; ia.prmsd_out = prmsd_out; ia.ppl_out = ppl_out;
-  ia.seed = seed;
+  ia.seed = seed; ia.row0 = (uint32_t)(m->batch_offset * L);
   if (init_noise) {
     if (!optimize) {
       if (!init_noise->g4 || !init_noise->gp || !init_noise->s_rand) return fail(ABOPT_ERR_ARG, "init_noise for sample() needs g4, gp, s_rand");
@@ -792,7 +793,7 @@ static int run_step(abopt_model* m, int N, int L, int t, bool optimize, uint32_t
   sa.v_net = w.v_net; sa.p_pred = w.eps_pos; sa.c_den = w.c_den; sa.mask_gen = mask_generate;
   sa.v_out = v_out; sa.p_out_ang = p_out; sa.s_out = s_out;
   sa.maxprob_rows = prm ? w.maxprob : nullptr;
-  sa.seed = seed;
+  sa.seed = seed; sa.row0 = (uint32_t)(m->batch_offset * L);
   if (nz) {
     if (!nz->u || !nz->expo_ang || !nz->unif_ang || !nz->gauss_ang || !nz->z_pos || !nz->expo_seq)
       return fail(ABOPT_ERR_ARG, "incomplete abopt_step_noise record");
@@ -916,7 +917,7 @@ extern "C" int abopt_loss_forward(abopt_model* m, int N, int L, const float* v_0
   ia.sample_structure = ds ? 1 : 0; ia.sample_sequence = dq ? 1 : 0; ia.optimize = 1; ia.has_prmsd = 0;
   ia.v = v_0; ia.p_ang = p_0; ia.s = (const long long*)s_0; ia.mask_gen = mask_generate;
   ia.v_out = v_noisy; ia.p_out_ang = p_noisy; ia.s_out = s_noisy;
-  ia.seed = seed; ia.tvec = (const long long*)t; ia.seq_all_rows = 1; ia.z_out = ds ? zbuf : nullptr;
+  ia.seed = seed; ia.row0 = (uint32_t)(m->batch_offset * L); ia.tvec = (const long long*)t; ia.seq_all_rows = 1; ia.z_out = ds ? zbuf : nullptr;
   if (noise) {
     if (ds) launch_angle_argmax((int)M, L, (const long long*)t, 0, m->diff.ang_Y[0], noise->expo_ang, mask_generate, w.bin_idx, st);
     ia.add = NoisePtrs{noise->u, noise->unif_ang, noise->gauss_ang, noise->z_pos, noise->expo_seq, w.bin_idx};
@@ -991,6 +992,105 @@ extern "C" int abopt_sample_host(abopt_model* m, int N, int L, const float* v, c
     if (prm) {
       CUDA_TRY(cudaMemcpyAsync(traj_prmsd + (size_t)first * N, io.traj_prmsd + (size_t)first * N, (size_t)count * N * 4, cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaMemcpyAsync(traj_ppl + (size_t)first * N, io.traj_ppl + (size_t)first * N, (size_t)count * N * 4, cudaMemcpyDeviceToHost, st));
+    }
+    return ABOPT_OK;
+  };
+  if (keep) { rc = copy_slots(0, T0 + 1); if (rc) return rc; }
+  else { rc = copy_slots(0, 1); if (rc) return rc; rc = copy_slots(T0, 1); if (rc) return rc; }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return ABOPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------ encode + sample from atoms
+// DiffusionAntibodyDesign.sample / .optimize (models/diffab.py:115-141,143-171): encode() = ResidueEmbedding + PairEmbedding +
+// backbone frames, then FullDPM.sample / optimize -- one device-resident call, pair_feat (1.07 GB at B=64, L=256) never leaves
+// the device.
+static int grow(void** buf, size_t* have, size_t need) {
+  if (*have >= need) return ABOPT_OK;
+  if (*buf) { CUDA_TRY(cudaFree(*buf)); *buf = nullptr; *have = 0; }
+  CUDA_TRY(cudaMalloc(buf, need));
+  *have = need;
+  return ABOPT_OK;
+}
+
+extern "C" int abopt_design_device(abopt_model* m, abopt_pair_embed* pe, abopt_res_embed* re, int N, int L, int num_atoms_in,
+                                   const int64_t* aa, const int64_t* res_nb, const int64_t* chain_nb, const float* pos_heavyatom,
+                                   const uint8_t* mask_heavyatom, const int64_t* fragment_type, const uint8_t* generate_flag,
+                                   const uint8_t* mask, uint32_t flags, int opt_step, uint64_t seed, float* traj_v, float* traj_p,
+                                   int64_t* traj_s, float* traj_prmsd, float* traj_ppl, void* stream) {
+  int rc = check_ready(m, N, L, ABOPT_SCOPE_FULL); if (rc) return rc;
+  if (!pe || !re) return fail(ABOPT_ERR_ARG, "null embedding handle");
+  if (!aa || !res_nb || !chain_nb || !pos_heavyatom || !mask_heavyatom || !fragment_type || !generate_flag || !mask)
+    return fail(ABOPT_ERR_ARG, "null tensor");
+  if (num_atoms_in < 4) return fail(ABOPT_ERR_ARG, "need at least the backbone atoms N, CA, C, O");
+  DeviceGuard g(m->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t M = (size_t)N * L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+  const size_t oc = take(M), ov = take(M * 12), op = take(M * 12), orf = take(M * F * 4), opf = take(M * L * C * 4);
+  rc = grow(&m->design_buf, &m->design_bytes, off); if (rc) return rc;
+  unsigned char* b = static_cast<unsigned char*>(m->design_buf);
+  uint8_t* ctx = b + oc;
+  float *v0 = (float*)(b + ov), *p0 = (float*)(b + op), *res_feat = (float*)(b + orf), *pair_feat = (float*)(b + opf);
+  launch_design_prep((int)M, num_atoms_in, pos_heavyatom, mask_heavyatom, generate_flag, ctx, v0, p0, st);
+  CHECK_LAUNCH();
+  // remove_structure / remove_sequence follow sample_structure / sample_sequence (models/diffab.py:133-137)
+  const uint8_t* smask = (flags & ABOPT_SAMPLE_STRUCTURE) ? ctx : nullptr;
+  const uint8_t* qmask = (flags & ABOPT_SAMPLE_SEQUENCE) ? ctx : nullptr;
+  rc = abopt_res_embed_forward(re, N, L, num_atoms_in, aa, res_nb, chain_nb, pos_heavyatom, mask_heavyatom, fragment_type, smask, qmask,
+                               res_feat, stream);
+  if (rc) return rc;
+  rc = abopt_pair_embed_forward(pe, N, L, num_atoms_in, aa, res_nb, chain_nb, pos_heavyatom, mask_heavyatom, smask, qmask, pair_feat, stream);
+  if (rc) return rc;
+  return abopt_sample_device(m, N, L, v0, p0, aa, res_feat, pair_feat, generate_flag, mask, flags, opt_step, seed, nullptr, nullptr,
+                             traj_v, traj_p, traj_s, traj_prmsd, traj_ppl, stream);
+}
+
+extern "C" int abopt_design_host(abopt_model* m, abopt_pair_embed* pe, abopt_res_embed* re, int N, int L, int num_atoms_in,
+                                 const int64_t* aa, const int64_t* res_nb, const int64_t* chain_nb, const float* pos_heavyatom,
+                                 const uint8_t* mask_heavyatom, const int64_t* fragment_type, const uint8_t* generate_flag,
+                                 const uint8_t* mask, uint32_t flags, int opt_step, uint64_t seed, float* traj_v, float* traj_p,
+                                 int64_t* traj_s, float* traj_prmsd, float* traj_ppl) {
+  int rc = check_ready(m, N, L, ABOPT_SCOPE_FULL); if (rc) return rc;
+  if (!aa || !res_nb || !chain_nb || !pos_heavyatom || !mask_heavyatom || !fragment_type || !generate_flag || !mask || !traj_v ||
+      !traj_p || !traj_s)
+    return fail(ABOPT_ERR_ARG, "null tensor");
+  if (opt_step < 0 || opt_step > m->cfg.num_steps) return fail(ABOPT_ERR_ARG, "opt_step out of range");
+  DeviceGuard g(m->device);
+  const int T0 = opt_step > 0 ? opt_step : m->cfg.num_steps;
+  const size_t M = (size_t)N * L, S1 = (size_t)T0 + 1, A = (size_t)num_atoms_in;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+  const size_t oaa = take(M * 8), orn = take(M * 8), ocn = take(M * 8), opos = take(M * A * 12), oma = take(M * A), oft = take(M * 8),
+               ogen = take(M), omask = take(M), otv = take(S1 * M * 12), otp = take(S1 * M * 12), ots = take(S1 * M * 8),
+               opr = take(S1 * N * 4), opl = take(S1 * N * 4);
+  rc = grow(&m->design_io, &m->design_io_bytes, off); if (rc) return rc;
+  unsigned char* b = static_cast<unsigned char*>(m->design_io);
+  cudaStream_t st = m->own_stream;
+  CUDA_TRY(cudaMemcpyAsync(b + oaa, aa, M * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(b + orn, res_nb, M * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(b + ocn, chain_nb, M * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(b + opos, pos_heavyatom, M * A * 12, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(b + oma, mask_heavyatom, M * A, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(b + oft, fragment_type, M * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(b + ogen, generate_flag, M, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(b + omask, mask, M, cudaMemcpyHostToDevice, st));
+  float *dtv = (float*)(b + otv), *dtp = (float*)(b + otp), *dpr = (float*)(b + opr), *dpl = (float*)(b + opl);
+  int64_t* dts = (int64_t*)(b + ots);
+  rc = abopt_design_device(m, pe, re, N, L, num_atoms_in, (const int64_t*)(b + oaa), (const int64_t*)(b + orn), (const int64_t*)(b + ocn),
+                           (const float*)(b + opos), b + oma, (const int64_t*)(b + oft), b + ogen, b + omask, flags, opt_step, seed,
+                           dtv, dtp, dts, dpr, dpl, st);
+  if (rc) return rc;
+  const bool keep = (flags & ABOPT_KEEP_TRAJECTORY) != 0;
+  const bool prm = m->cfg.has_prmsd != 0 && traj_prmsd && traj_ppl;
+  auto copy_slots = [&](int first, int count) -> int {
+    CUDA_TRY(cudaMemcpyAsync(traj_v + (size_t)first * M * 3, dtv + (size_t)first * M * 3, (size_t)count * M * 12, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(traj_p + (size_t)first * M * 3, dtp + (size_t)first * M * 3, (size_t)count * M * 12, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(traj_s + (size_t)first * M, dts + (size_t)first * M, (size_t)count * M * 8, cudaMemcpyDeviceToHost, st));
+    if (prm) {
+      CUDA_TRY(cudaMemcpyAsync(traj_prmsd + (size_t)first * N, dpr + (size_t)first * N, (size_t)count * N * 4, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(traj_ppl + (size_t)first * N, dpl + (size_t)first * N, (size_t)count * N * 4, cudaMemcpyDeviceToHost, st));
     }
     return ABOPT_OK;
   };

@@ -59,9 +59,8 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
 
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(AL_EPI) : "memory"); }
 
-// REG: keys <= 256 -> each epilogue thread keeps its half row (<= 128 logits) in registers and alpha leaves through
-// TMA stores; otherwise the row is processed in three passes over TMEM.
-template <bool REG>
+// One tile per CTA, any key count up to 512: the row is processed in three passes over TMEM (serves 256 < L <= 512; shorter
+// complexes use attn_logits_persist_kernel below).
 __global__ void __launch_bounds__(AL_THREADS, 1)
 attn_logits_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
                       const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
@@ -191,72 +190,7 @@ attn_logits_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
     const float scale = 0.57735026918962576f;             // sqrt(1/3), ga.py:166
     const float l2e = 1.4426950408889634f;
 
-    if constexpr (REG) {
-      // ---- register-resident half row (ncols <= 256): TMEM is read exactly once, nothing is written back
-      float lg[128];
-      float m = -INFINITY;
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c0 = cbeg + cc * 32;
-        if (cc * 32 < ncols / 2) {
-          tmem_ld_32x32(trow + c0, *reinterpret_cast<float(*)[32]>(&lg[cc * 32]));      // accumulator chunk, in place
-#pragma unroll
-          for (int e0 = 0; e0 < 32; e0 += 8) {
-            float bv[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) bv[e] = (c0 + e0 + e < L) ? __ldg(bias_col + (c0 + e0 + e)) : 0.f;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int j = c0 + e0 + e;
-              const float lgt = ((lg[cc * 32 + e0 + e] + bv[e]) + (rqi + ck[j])) * scale - pen[j];
-              m = fmaxf(m, lgt);
-              lg[cc * 32 + e0 + e] = lgt;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) lg[cc * 32 + e] = -INFINITY;
-        }
-      }
-      xmax[half * 128 + te] = m;
-      if (te == 0 && half == 0) stamp(6);
-      epi_sync();
-      m = fmaxf(xmax[te], xmax[128 + te]);
-      // exp(l - m) = 2^((l - m) log2e): subtract FIRST (exact near the maximum, where the attention mass is), so the
-      // rounding error of the product scales with |l - m| and not with |l|
-      float sum = 0.f;
-#pragma unroll
-      for (int e = 0; e < 128; ++e) { lg[e] = exp2f((lg[e] - m) * l2e); sum += lg[e]; }
-      xsum[half * 128 + te] = sum;
-      if (te == 0 && half == 0) stamp(7);
-      epi_sync();                                         // (every MMA completed before tmem_full: operand smem is free)
-      const float inv = 1.0f / (xsum[te] + xsum[128 + te]);
-      // ---- alpha leaves through shared memory (128-byte swizzled boxes of 128 rows x 32 keys, 4 per half row = 128 KB
-      //      in the drained operand buffers) and TMA tensor stores: the hardware clips rows >= L and writes whole lines.
-      unsigned char* stg = smem;                          // [half][box k][16 KB]
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k * 32 < ncols / 2) {
-          unsigned char* box = stg + (half * 4 + k) * AL_BOX_BYTES + te * 128;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const int e = k * 32 + c * 4;
-            *reinterpret_cast<float4*>(box + ((c ^ (te & 7)) << 4)) = make_float4(lg[e] * inv, lg[e + 1] * inv, lg[e + 2] * inv, lg[e + 3] * inv);
-          }
-        }
-      }
-      fence_async_smem();
-      epi_sync();
-      if (te == 0 && half == 0) {
-        for (int hf = 0; hf < 2; ++hf)
-          for (int k = 0; k < 4; ++k) {
-            const int c0 = hf * (ncols / 2) + k * 32;
-            if (k * 32 < ncols / 2 && c0 < Lp) tma_store_3d(&tmAl, stg + (hf * 4 + k) * AL_BOX_BYTES, c0, i0, bl * H + h);
-          }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // smem must outlive the reads; the writes complete
-      }                                                                     // by the end of the grid
-    } else {
+    {
       float bv[32], bn[32];
       load_bias(cbeg, bv);
       // ---- pass 1: logits, running max.  The pair bias of the next 32 keys is in flight while this chunk is processed.
@@ -627,17 +561,13 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-static bool g_attn_legacy = false;      // ABOPT_ATTN_LEGACY=1: one-tile-per-CTA kernel (A/B comparisons)
-bool attn_needs_qk_lo(int L) { return g_attn_legacy || ((L + AL_BN - 1) / AL_BN) * AL_BN > 256; }
+bool attn_needs_qk_lo(int L) { return ((L + AL_BN - 1) / AL_BN) * AL_BN > 256; }
 cudaError_t attn_tc_init() {
-  { const char* ev = getenv("ABOPT_ATTN_LEGACY"); g_attn_legacy = ev && ev[0] == '1'; }
-  cudaError_t e = cudaFuncSetAttribute(attn_logits_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AL_SMEM);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(attn_logits_persist_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(attn_logits_persist_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(attn_logits_persist_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(attn_logits_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AL_SMEM);
+  return cudaFuncSetAttribute(attn_logits_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AL_SMEM);
 }
 
 bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOperands& op, const float* bias_layer, const uint8_t* mask,
@@ -657,7 +587,7 @@ bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOpera
   AttnLogitsArgs a{L, Lp, b0, op.rq, op.rk, bias_layer, mask, alpha};
   dim3 grid((L + AL_BM - 1) / AL_BM, H, nb);
   const int ncols = ((L + AL_BN - 1) / AL_BN) * AL_BN;
-  if (ncols <= 256 && !g_attn_legacy) {
+  if (ncols <= 256) {
     // key operands in groups of 64 residues; the pair bias [(b,h,i) rows][Lp keys] as swizzled [128 queries][32 keys] boxes
     CUtensorMap kh64, kl64, bm32;
     if (!make_tmap(&kh64, op.KB, rows, 64, 64, 64) || !make_tmap(&kl64, op.KB_lo, rows, 64, 64, 64) ||
@@ -669,197 +599,29 @@ bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOpera
     const AttnPersistArgs pa{windows, wcount, nb};
     if (ncols <= 128) attn_logits_persist_kernel<4><<<ntiles < sms ? ntiles : sms, AP_THREADS, AP_SMEM, st>>>(qh, ql, kh64, kl64, bm32, al, a, pa);
     else attn_logits_persist_kernel<8><<<ntiles < sms ? ntiles : sms, AP_THREADS, AP_SMEM, st>>>(qh, ql, kh64, kl64, bm32, al, a, pa);
-  } else if (ncols <= 256) attn_logits_tc_kernel<true><<<grid, AL_THREADS, AL_SMEM, st>>>(qh, ql, kh, kl, bm, al, a);
-  else attn_logits_tc_kernel<false><<<grid, AL_THREADS, AL_SMEM, st>>>(qh, ql, kh, kl, bm, al, a);
+  } else attn_logits_tc_kernel<<<grid, AL_THREADS, AL_SMEM, st>>>(qh, ql, kh, kl, bm, al, a);
   return true;
 }
 
 // ------------------------------------------------------------------------------------------ aggregation GEMM
-// aggr_tc_kernel: node and point aggregation  O[i][n] = sum_j alpha[i][j] V[j][n]  (ga.py:120-136) on the tensor cores,
-// followed by the local-frame features (ga.py:137-146).  V^T[b][h][n][j] = [ value channels (32) | global value points (24)
-// | 0 (8) ] comes K-major (key index contiguous) from the projection epilogue, alpha from attn_logits_tc_kernel.
-//   warp 0     TMA producer: key blocks of 32 through a 2-stage ring (alpha 128 x 32 raw fp32; V^T 64 x 32 hi and lo planes);
-//              two CTAs are resident per SM (2 x 97 KB smem, 2 x 256 TMEM columns) and hide each other's latencies
-//   warps 2-5  (a) during the main loop: "splitters" -- build the tf32 lo plane of each landed alpha box in shared memory
-//              (lo = x - trunc_tf32(x), same swizzled offsets), so alpha_lo never exists in global memory;
-//              (b) then the epilogue: thread = query row: 64 sums -> node aggregate, R_i^T (o - t_i), norms, directions,
-//              transposed through shared memory so that every global store instruction writes one contiguous row segment
-//   warp 1     MMA issuer: per key block 4 k-steps; hi*hi -> one of three 64-column TMEM accumulators (one per third of the
-//              keys), hi*lo + lo*hi -> a fourth (short accumulation chains: see the truncation note in k_tc.cu)
-constexpr int AG2_THREADS = 192, AG2_STAGES = 2;      // 2 stages x 48 KB: two CTAs per SM overlap each other's phases
+// Node and point aggregation  O[i][n] = sum_j alpha[i][j] V[j][n]  (ga.py:120-136) on the tensor cores, followed by the
+// local-frame features (ga.py:137-146).  V^T[b][h][n][j] = [ value channels (32) | global value points (24) | 0 (8) ] comes
+// K-major (key index contiguous) from the projection epilogue, alpha from the logits kernel.  Per key block of 32:
+// alpha 128 x 32 raw fp32 (its tf32 lo plane is built in shared memory), V^T 64 x 32 hi and lo planes; hi*hi goes to one of
+// three 64-column TMEM accumulators (one per third of the keys), hi*lo + lo*hi to a fourth (short accumulation chains: the
+// tensor core truncates the fp32 accumulator on every accumulation, see k_tc.cu).
 constexpr int AG2_A_BYTES = 128 * 32 * 4, AG2_B_BYTES = 64 * 32 * 4;
 constexpr int AG2_STAGE_BYTES = 2 * AG2_A_BYTES + 2 * AG2_B_BYTES;      // 48 KB: alpha raw | alpha lo | V^T hi | V^T lo
 constexpr int AG2_TX_BYTES = AG2_A_BYTES + 2 * AG2_B_BYTES;             // what TMA delivers per stage
-constexpr int AG2_SMEM = AG2_STAGES * AG2_STAGE_BYTES + 256 + 1024;
-constexpr int AG2_NOUT = 88, AG2_PITCH = 89;                            // staged outputs per row: node 32 | pts 24 | dist 8 | dir 24
 
 struct AggrArgs {
   int L, Lp, b0;
   const float* R; const float* t;        // [N][L][3][3], [N][L][3]
-  float* feat; float* feat_lo;           // [N][L][1824]
+  float* feat;                           // [N][L][1824]
 };
 
-__global__ void __launch_bounds__(AG2_THREADS, 2)
-aggr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmVh,
-               const __grid_constant__ CUtensorMap tmVl, const AggrArgs a) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + AG2_STAGES * AG2_STAGE_BYTES);
-  uint64_t* split = full + AG2_STAGES;
-  uint64_t* empty = split + AG2_STAGES;
-  uint64_t* tmem_full = empty + AG2_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int L = a.L;
-  const int i0 = blockIdx.x * 128, h = blockIdx.y, bl = blockIdx.z, b = a.b0 + bl;
-  const int nkb = (L + 31) / 32;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < AG2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 4); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
-    mbar_fence_init();
-    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmVh); tma_prefetch_desc(&tmVl);
-  }
-  // TMEM: three "main" accumulators of 64 columns, one per third of the key axis, + one correction accumulator
-  // (256 columns, so two CTAs fit the SM's 512).  The tensor core truncates the fp32 accumulator on every accumulation
-  // (k_tc.cu), so the long K = L chain is cut into short ones that are added in fp32 registers by the epilogue.
-  const int gsz = (nkb + 2) / 3;                         // key blocks per main accumulator
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (elect_one()) {
-      const int arow = (bl * H + h) * L + i0, vrow = (b * H + h) * 64;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % AG2_STAGES;
-        mbar_wait(&empty[s], ((kb / AG2_STAGES) & 1) ^ 1);
-        unsigned char* st = smem + s * AG2_STAGE_BYTES;
-        mbar_expect_tx(&full[s], AG2_TX_BYTES);
-        tma_load_2d(st, &tmA, kb * 32, arow, &full[s]);
-        tma_load_2d(st + 2 * AG2_A_BYTES, &tmVh, kb * 32, vrow, &full[s]);
-        tma_load_2d(st + 2 * AG2_A_BYTES + AG2_B_BYTES, &tmVl, kb * 32, vrow, &full[s]);
-      }
-    }
-  } else if (warp == 1) {
-    constexpr uint32_t idesc = idesc_tf32(128, 64);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % AG2_STAGES;
-      mbar_wait(&split[s], (kb / AG2_STAGES) & 1);          // TMA data landed AND the lo plane is built
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t a_hi = smem_u32(smem + s * AG2_STAGE_BYTES), a_lo = a_hi + AG2_A_BYTES;
-        const uint32_t b_hi = a_hi + 2 * AG2_A_BYTES, b_lo = b_hi + AG2_B_BYTES;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t dah = smem_desc_sw128(a_hi + k * 32), dal = smem_desc_sw128(a_lo + k * 32);
-          const uint64_t dbh = smem_desc_sw128(b_hi + k * 32), dbl = smem_desc_sw128(b_lo + k * 32);
-          mma_tf32(tmem_base + (kb / gsz) * 64, dah, dbh, idesc, (kb % gsz == 0 && k == 0) ? 0u : 1u);
-          mma_tf32(tmem_base + 192, dah, dbl, idesc, (kb == 0 && k == 0) ? 0u : 1u);
-          mma_tf32(tmem_base + 192, dal, dbh, idesc, 1u);
-        }
-        mma_commit(&empty[s]);
-        if (kb == nkb - 1) mma_commit(tmem_full);
-      }
-      __syncwarp();
-    }
-  } else {
-    const int q = warp & 3;
-    const int te = (warp - 2) * 32 + lane;                // 0..127 splitter index
-    // ---- (a) splitter: lo plane of every landed alpha box
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % AG2_STAGES;
-      mbar_wait(&full[s], (kb / AG2_STAGES) & 1);
-      const float4* src = reinterpret_cast<const float4*>(smem + s * AG2_STAGE_BYTES);
-      float4* dst = reinterpret_cast<float4*>(smem + s * AG2_STAGE_BYTES + AG2_A_BYTES);
-#pragma unroll
-      for (int m = 0; m < AG2_A_BYTES / 16 / 128; ++m) {
-        const float4 v = src[te + 128 * m];
-        dst[te + 128 * m] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
-      }
-      fence_async_smem();                                  // generic-proxy writes -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&split[s]);
-    }
-    // ---- (b) epilogue
-    const int i = i0 + q * 32 + lane;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    float o[64];
-    const int ngrp = (nkb + gsz - 1) / gsz;               // main accumulators actually used
-#pragma unroll
-    for (int c = 0; c < 64; c += 32) {
-      float v[32], w[32];
-      tmem_ld_32x32(trow + 192 + c, w);                   // corrections
-      tmem_ld_32x32(trow + c, v);
-#pragma unroll
-      for (int e = 0; e < 32; ++e) o[c + e] = v[e];
-      for (int g = 1; g < ngrp; ++g) {
-        tmem_ld_32x32(trow + g * 64 + c, v);
-#pragma unroll
-        for (int e = 0; e < 32; ++e) o[c + e] += v[e];
-      }
-#pragma unroll
-      for (int e = 0; e < 32; ++e) o[c + e] += w[e];
-    }
-    float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * 32 * AG2_PITCH;       // drained pipeline memory, per warp
-    float* mine = stage + lane * AG2_PITCH;
-    {
-      const size_t row = (size_t)b * L + (i < L ? i : 0);
-#pragma unroll
-      for (int d = 0; d < D; ++d) mine[d] = o[d];          // node aggregate (ga.py:120-125)
-      // point aggregate -> local frame p = R^T (q - t) (geometry.py:94-113), norm, direction (eps 1e-4, ga.py:139)
-      float Rm[9], tv[3];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) Rm[k] = __ldg(a.R + row * 9 + k);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) tv[k] = __ldg(a.t + row * 3 + k);
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-        const float gx = o[D + p * 3 + 0] - tv[0], gy = o[D + p * 3 + 1] - tv[1], gz = o[D + p * 3 + 2] - tv[2];
-        const float lx = Rm[0] * gx + Rm[3] * gy + Rm[6] * gz;
-        const float ly = Rm[1] * gx + Rm[4] * gy + Rm[7] * gz;
-        const float lz = Rm[2] * gx + Rm[5] * gy + Rm[8] * gz;
-        const float nrm = sqrtf(lx * lx + ly * ly + lz * lz);
-        const float den = nrm + 1e-4f;
-        mine[32 + p * 3 + 0] = lx; mine[32 + p * 3 + 1] = ly; mine[32 + p * 3 + 2] = lz;
-        mine[56 + p] = nrm;
-        mine[64 + p * 3 + 0] = lx / den; mine[64 + p * 3 + 1] = ly / den; mine[64 + p * 3 + 2] = lz / den;
-      }
-    }
-    __syncwarp();
-    // coalesced write-out: one instruction = up to 32 consecutive columns of one row
-    int col[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int c = lane + 32 * k;
-      col[k] = c < 32 ? FEAT_NODE + h * D + c : (c < 56 ? FEAT_PTS + h * P * 3 + (c - 32) : (c < 64 ? FEAT_DIST + h * P + (c - 56) : FEAT_DIR + h * P * 3 + (c - 64)));
-    }
-    for (int rr = 0; rr < 32; ++rr) {
-      const int ir = i0 + q * 32 + rr;
-      if (ir >= L) break;
-      const size_t base = ((size_t)b * L + ir) * NFEAT;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const int c = lane + 32 * k;
-        if (c < AG2_NOUT) {
-          const float v = stage[rr * AG2_PITCH + c];
-          a.feat[base + col[k]] = v;
-          if (a.feat_lo) a.feat_lo[base + col[k]] = tf32_lo(v);
-        }
-      }
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
-}
-
 // ------------------------------------------------------------------------------------------ persistent aggregation GEMM
-// aggr_persist_kernel: same arithmetic as aggr_tc_kernel, restructured like attn_logits_persist_kernel.  One CTA per SM walks
+// aggr_persist_kernel: structured like attn_logits_persist_kernel.  One CTA per SM walks
 // the (complex, head, 128-query tile) list; the k-block ring runs across tile boundaries and the epilogue of tile n overlaps
 // the main loop of tile n + 1 (two 256-column TMEM accumulator sets):
 //   warp 0      TMA producer: key blocks of 32 through a 4-stage ring (alpha 128 x 32 raw fp32; V^T 64 x 32 hi and lo planes)
@@ -1042,33 +804,24 @@ aggr_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-static bool g_aggr_legacy = false;      // ABOPT_AGGR_LEGACY=1: one-tile-per-CTA kernel (A/B comparisons)
 cudaError_t aggr_tc_init() {
-  { const char* ev = getenv("ABOPT_AGGR_LEGACY"); g_aggr_legacy = ev && ev[0] == '1'; }
-  cudaError_t e = cudaFuncSetAttribute(aggr_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AGP_SMEM);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(aggr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AG2_SMEM);
+  return cudaFuncSetAttribute(aggr_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AGP_SMEM);
 }
 
 // alpha: [chunk][H][L][Lp]; VT / VT_lo: [N][H][64][Lp]
 bool launch_aggr_tc(int nb, int b0, int N, int L, int Lp, const float* alpha, const float* VT, const float* VT_lo,
-                    const float* R, const float* t, float* feat, float* feat_lo, cudaStream_t st, const int2* windows, const int* wcount,
+                    const float* R, const float* t, float* feat, cudaStream_t st, const int2* windows, const int* wcount,
                     const int* cidx) {
   CUtensorMap ah, vh, vl;
   const uint64_t arows = (uint64_t)nb * H * L, vrows = (uint64_t)N * H * 64;
   if (!make_tmap(&ah, alpha, arows, Lp, Lp, 128) || !make_tmap(&vh, VT, vrows, Lp, Lp, 64) || !make_tmap(&vl, VT_lo, vrows, Lp, Lp, 64))
     return false;
   ProfScope prof__(KK_AGGR, st);
-  AggrArgs a{L, Lp, b0, R, t, feat, feat_lo};
-  if (!g_aggr_legacy && feat_lo == nullptr) {
-    const int ntiles = nb * H * ((L + 127) / 128);
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    aggr_persist_kernel<<<ntiles < sms ? ntiles : sms, AGP_THREADS, AGP_SMEM, st>>>(ah, vh, vl, a, nb, windows, wcount, cidx);
-    return true;
-  }
-  dim3 grid((L + 127) / 128, H, nb);
-  aggr_tc_kernel<<<grid, AG2_THREADS, AG2_SMEM, st>>>(ah, vh, vl, a);
+  AggrArgs a{L, Lp, b0, R, t, feat};
+  const int ntiles = nb * H * ((L + 127) / 128);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  aggr_persist_kernel<<<ntiles < sms ? ntiles : sms, AGP_THREADS, AGP_SMEM, st>>>(ah, vh, vl, a, nb, windows, wcount, cidx);
   return true;
 }
 

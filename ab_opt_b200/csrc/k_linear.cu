@@ -1,6 +1,5 @@
 // Small node-feature layers of the hot path on CUDA cores (FP32 FFMA, cp.async pipelined); the big GEMMs are in k_tc.cu.
 //   mixer_kernel  : EpsilonNet input mixer + R = exp(v_t)           dpm_full.py:86-89
-//   tail_kernel   : (out_transform on tensor cores, k_tc.cu) -> mask -> LN -> MLP -> LN        ga.py:173-178
 //   heads_kernel  : eps_crd / eps_rot / eps_seq / pRMSD heads + SO(3) update    dpm_full.py:92-110
 #include "rowtile.cuh"
 #include "params.cuh"
@@ -57,76 +56,6 @@ mixer_kernel(int M, const float* __restrict__ res_feat, const long long* __restr
       *reinterpret_cast<float4*>(x_out + (size_t)row * F + lane * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
       if (x_lo_out != nullptr)
         *reinterpret_cast<float4*>(x_lo_out + (size_t)row * F + lane * 4) = make_float4(tf32_lo(acc[r][0]), tf32_lo(acc[r][1]), tf32_lo(acc[r][2]), tf32_lo(acc[r][3]));
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------ block tail
-__global__ void __launch_bounds__(RT_THREADS, 2)
-tail_kernel(int M, const float* __restrict__ feat, const float* __restrict__ pre, const float* __restrict__ x,
-            const uint8_t* __restrict__ mask, BlockW w, float* __restrict__ x_out, float* __restrict__ x_lo_out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  RowTileSmem& s = *reinterpret_cast<RowTileSmem*>(smem_raw);
-  float* act = reinterpret_cast<float*>(smem_raw + sizeof(RowTileSmem));      // [64][RT_ACT_LD]
-  const int row0 = blockIdx.x * RT_ROWS;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  float acc[8][4], h[8][4];
-  rt_zero(acc);
-  if (pre != nullptr) {          // out_transform (+ bias) already done by the tcgen05 GEMM
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int row = row0 + warp * 8 + r;
-      if (row < M) {
-        const float4 v = *reinterpret_cast<const float4*>(pre + (size_t)row * F + lane * 4);
-        acc[r][0] = v.x; acc[r][1] = v.y; acc[r][2] = v.z; acc[r][3] = v.w;
-      }
-    }
-  } else {
-    rt_gemm_globalA(acc, s, [&](int r, int k) -> const float* {
-      return (row0 + r < M) ? feat + (size_t)(row0 + r) * NFEAT + k : nullptr;
-    }, w.Wout_t, NFEAT);
-    rt_add_bias(acc, w.bout);
-  }
-  // mask_zero (layers.py:6-7) then residual + LayerNorm 1
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int row = row0 + warp * 8 + r;
-    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-    bool mk = false;
-    if (row < M) { xv = *reinterpret_cast<const float4*>(x + (size_t)row * F + lane * 4); mk = mask[row] != 0; }
-    h[r][0] = xv.x + (mk ? acc[r][0] : 0.f); h[r][1] = xv.y + (mk ? acc[r][1] : 0.f);
-    h[r][2] = xv.z + (mk ? acc[r][2] : 0.f); h[r][3] = xv.w + (mk ? acc[r][3] : 0.f);
-  }
-  rt_layernorm(h, w.ln1_g, w.ln1_b, 1e-10f);
-  // 3-layer transition MLP
-  rt_store_act(h, act, RT_ACT_LD);
-  __syncthreads();
-  rt_zero(acc);
-  rt_gemm_smemA(acc, s, act, RT_ACT_LD, w.W1_t, F);
-  rt_add_bias(acc, w.b1); rt_relu(acc);
-  rt_store_act(acc, act, RT_ACT_LD);
-  __syncthreads();
-  rt_zero(acc);
-  rt_gemm_smemA(acc, s, act, RT_ACT_LD, w.W2_t, F);
-  rt_add_bias(acc, w.b2); rt_relu(acc);
-  rt_store_act(acc, act, RT_ACT_LD);
-  __syncthreads();
-  rt_zero(acc);
-  rt_gemm_smemA(acc, s, act, RT_ACT_LD, w.W3_t, F);
-  rt_add_bias(acc, w.b3);
-#pragma unroll
-  for (int r = 0; r < 8; ++r)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) h[r][c] += acc[r][c];
-  rt_layernorm(h, w.ln2_g, w.ln2_b, 1e-10f);
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int row = row0 + warp * 8 + r;
-    if (row < M) {
-      *reinterpret_cast<float4*>(x_out + (size_t)row * F + lane * 4) = make_float4(h[r][0], h[r][1], h[r][2], h[r][3]);
-      if (x_lo_out != nullptr)
-        *reinterpret_cast<float4*>(x_lo_out + (size_t)row * F + lane * 4) = make_float4(tf32_lo(h[r][0]), tf32_lo(h[r][1]), tf32_lo(h[r][2]), tf32_lo(h[r][3]));
     }
   }
 }
@@ -370,13 +299,11 @@ void launch_focus_gather(const int* rows, const int* count, const float* x, cons
 
 // ------------------------------------------------------------------------------------------ launchers
 size_t mixer_smem() { return sizeof(RowTileSmem) + RT_ROWS * RT_ACT_LD * sizeof(float); }
-size_t tail_smem() { return sizeof(RowTileSmem) + RT_ROWS * RT_ACT_LD * sizeof(float); }
 size_t heads_smem() { return sizeof(RowTileSmem) + (2 * RT_ROWS * RT_ACT_LD + RT_ROWS * HD_OUT_LD) * sizeof(float); }
 
 cudaError_t linear_kernels_init() {
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(mixer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mixer_smem())) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem())) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_smem())) != cudaSuccess) return e;
   return cudaSuccess;
 }
@@ -387,11 +314,6 @@ void launch_mixer(int M, const float* res_feat, const long long* s_t, const floa
   ProfScope prof__(KK_MIXER, st);
   mixer_kernel<<<(M + RT_ROWS - 1) / RT_ROWS, RT_THREADS, mixer_smem(), st>>>(M, res_feat, s_t, v_t, w, x_out, Rbuf, p_ang, p_norm,
                                                                            mean[0], mean[1], mean[2], scale, x_lo_out);
-}
-void launch_tail(int M, const float* feat, const float* pre, const float* x, const uint8_t* mask, const BlockW& w, float* x_out,
-                 float* x_lo_out, cudaStream_t st) {
-  ProfScope prof__(KK_TAIL, st);
-  tail_kernel<<<(M + RT_ROWS - 1) / RT_ROWS, RT_THREADS, tail_smem(), st>>>(M, feat, pre, x, mask, w, x_out, x_lo_out);
 }
 void launch_heads(int M, int L, const float* x, const float* beta, int beta_stride, const float* Rbuf, const float* v_t,
                   const uint8_t* mask_gen, const EpsW& w, float* v_next, float* R_next, float* eps_pos, float* c_den,

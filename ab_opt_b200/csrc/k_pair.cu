@@ -55,6 +55,7 @@ constexpr int PB_SMEM = PB_WARPS * PB_WARP_BYTES + PB_WARPS * PB_STAGES * 8 + 10
 
 struct PairBiasArgs {
   int L, Lp, b0, nrows, nchunk;   // nrows = complexes covered by this launch * L; nchunk = ceil(Lp / 32)
+  int box_bytes;                  // bytes one TMA box delivers (32 keys x 128 B, fewer rows when N*L*L < 32)
   float* bias;                    // [complex][h][i][Lp]
 };
 
@@ -85,7 +86,7 @@ pair_bias_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant
     if (lane == 0) {
       unsigned char* st = wst + ps * PB_STAGE_BYTES;
       const int grow = ((a.b0 + pbl) * L + pi) * L + pjc * PB_CJ;      // first row of the chunk in the (N*L*L, 64) view
-      mbar_expect_tx(&full[ps], PB_STAGE_BYTES);                        // rows past the end of the tensor arrive as zeros
+      mbar_expect_tx(&full[ps], 2 * a.box_bytes);                       // rows past the end of the tensor arrive as zeros
       tma_load_2d_hint(st, &zmap, 0, grow, &full[ps], pol);
       tma_load_2d_hint(st + PB_BOX_BYTES, &zmap, 32, grow, &full[ps], pol);
     }
@@ -148,7 +149,7 @@ pair_bias_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant
 //              per chunk 8 LDS.128 of z + 12 LDS.128 of alpha (4 distinct addresses) feed 192 FFMA2
 //              (scalar alpha x channel pair, 96 accumulators per lane)
 //   per row    the four quarters are combined with a 2-step shuffle reduce-scatter (each lane ends up with 3 heads x 8
-//              channels) and stored with their tf32 lo plane.
+//              channels) and stored.
 constexpr int PW_WARPS = 12, PW_THREADS = PW_WARPS * 32, PW_STAGES = 3;
 constexpr int PW_CJ = 16;                               // key residues per chunk
 constexpr int PW_Z_BYTES = PW_CJ * C * 4;               // 4096
@@ -162,7 +163,7 @@ struct PairRowsArgs {
   const float* z;                 // (N, L, L, 64)
   const uint8_t* mask;
   float* alpha;                   // [chunk complex][h][i][Lp]; rows of masked queries are zeroed here (ga.py:25)
-  float* feat; float* feat_lo;
+  float* feat;
   const int* cidx;                // optional (focus mode): compact output row of query row r, -1 = row not needed at all
 };
 
@@ -258,11 +259,10 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs 
     if (!need) continue;
     const size_t orow = a.cidx ? (size_t)a.cidx[(size_t)b * L + i] : (size_t)b * L + i;
     float* feat_row = a.feat + orow * NFEAT;
-    float* feat_lo_row = a.feat_lo + orow * NFEAT;
     if (!live) {
       // masked query: alpha row = 0 (ga.py:25) -> zero pair aggregate
       float* alpha_row0 = a.alpha + ((size_t)(bl * H) * L + i) * Lp;
-      for (int o = lane; o < H * C; o += 32) { feat_row[o] = 0.f; if (a.feat_lo) feat_lo_row[o] = 0.f; }
+      for (int o = lane; o < H * C; o += 32) feat_row[o] = 0.f;
       for (int o = lane; o < H * Lp; o += 32) {
         const int h = o / Lp, j = o - h * Lp;
         alpha_row0[(size_t)h * L * Lp + j] = 0.f;
@@ -327,10 +327,6 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs 
       const int off = (h0 + hh) * C + 4 * l;
       *reinterpret_cast<float4*>(feat_row + off) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
       *reinterpret_cast<float4*>(feat_row + off + 32) = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
-      if (a.feat_lo) {                                   // only the non-splitting out_transform GEMM reads a lo plane
-        *reinterpret_cast<float4*>(feat_lo_row + off) = make_float4(tf32_lo(o[0].x), tf32_lo(o[0].y), tf32_lo(o[1].x), tf32_lo(o[1].y));
-        *reinterpret_cast<float4*>(feat_lo_row + off + 32) = make_float4(tf32_lo(o[2].x), tf32_lo(o[2].y), tf32_lo(o[3].x), tf32_lo(o[3].y));
-      }
     }
   }
 }
@@ -352,9 +348,11 @@ cudaError_t pair_stream_init() {
 bool launch_pair_bias(int nb, int b0, int N, int L, int Lp, const float* z, const PairBiasPacked& pb, float* bias, cudaStream_t st) {
   CUtensorMap zmap;
   const uint64_t rows = (uint64_t)N * L * L;
-  if (!make_tmap(&zmap, z, rows, C, C, rows < (uint64_t)PB_CJ ? (uint32_t)rows : (uint32_t)PB_CJ)) return false;
+  const uint32_t box_rows = rows < (uint64_t)PB_CJ ? (uint32_t)rows : (uint32_t)PB_CJ;
+  if (!make_tmap(&zmap, z, rows, C, C, box_rows)) return false;
   ProfScope prof__(KK_OTHER, st);
   PairBiasArgs a{};
+  a.box_bytes = (int)box_rows * 128;
   a.L = L; a.Lp = Lp; a.b0 = b0; a.nrows = nb * L; a.nchunk = (Lp + PB_CJ - 1) / PB_CJ; a.bias = bias;
   int grid = g_sm_count > 0 ? g_sm_count : 148;
   const int need = (a.nrows + PB_WARPS - 1) / PB_WARPS;
@@ -364,14 +362,14 @@ bool launch_pair_bias(int nb, int b0, int N, int L, int Lp, const float* z, cons
 }
 
 bool launch_pair_stream(int nb, int b0, int L, int Lp, const float* z, const uint8_t* mask,
-                        float* alpha, float* feat, float* feat_lo, cudaStream_t st, const int* cidx) {
+                        float* alpha, float* feat, cudaStream_t st, const int* cidx) {
   CUtensorMap amap;
   // alpha as a plain 3-D tensor [nb * H][L queries][Lp keys]; box = [12 heads][1 query][16 keys]
   if (!make_tmap_3d_plain(&amap, alpha, (uint64_t)Lp, (uint64_t)L, (uint64_t)nb * H, PW_CJ, 1, H)) return false;
   ProfScope prof__(KK_PAIR, st);
   PairRowsArgs a{};
   a.L = L; a.Lp = Lp; a.b0 = b0; a.nrows = nb * L; a.nchunk = (L + PW_CJ - 1) / PW_CJ;
-  a.z = z; a.mask = mask; a.alpha = alpha; a.feat = feat; a.feat_lo = feat_lo; a.cidx = cidx;
+  a.z = z; a.mask = mask; a.alpha = alpha; a.feat = feat; a.cidx = cidx;
   int grid = g_sm_count > 0 ? g_sm_count : 148;
   const int need = (a.nrows + PW_WARPS - 1) / PW_WARPS;
   if (grid > need) grid = need;

@@ -144,6 +144,7 @@ step_kernel(StepArgs a, DiffW dw) {
   const bool parity = a.nz.u != nullptr;
   const bool noisy = t > 1;
   Philox ph(a.seed);
+  const uint32_t gr = (uint32_t)r + a.row0;      // Philox counter = row in the GLOBAL batch: a sharded run draws what the unsharded one draws
 
   // normalise positions exactly as the loop does on re-reading traj[t] (dpm_full.py:276,148-150)
   float pt[3], vt[3];
@@ -162,10 +163,10 @@ step_kernel(StepArgs a, DiffW dw) {
       u[0] = a.nz.u[(size_t)r * 3]; u[1] = a.nz.u[(size_t)r * 3 + 1]; u[2] = a.nz.u[(size_t)r * 3 + 2];
       unif = a.nz.unif_ang[r]; gauss = a.nz.gauss_ang[r];
     } else {
-      const uint4 x = ph(r, t, RS_U, 0);
+      const uint4 x = ph(gr, t, RS_U, 0);
       float g3;
       box_muller(x.x, x.y, u[0], u[1]); box_muller(x.z, x.w, u[2], g3);
-      const uint4 y = ph(r, t, RS_ANGLE, 0);
+      const uint4 y = ph(gr, t, RS_ANGLE, 0);
       float g1;
       ucdf = u01_half(y.x); unif = u01_half(y.y); box_muller(y.z, y.w, gauss, g1);
     }
@@ -178,7 +179,7 @@ step_kernel(StepArgs a, DiffW dw) {
   if (gen && a.sample_structure) {
     float z[3];
     if (parity) { z[0] = a.nz.z_pos[(size_t)r * 3]; z[1] = a.nz.z_pos[(size_t)r * 3 + 1]; z[2] = a.nz.z_pos[(size_t)r * 3 + 2]; }
-    else { const uint4 x = ph(r, t, RS_ZPOS, 0); float g3; box_muller(x.x, x.y, z[0], z[1]); box_muller(x.z, x.w, z[2], g3); }
+    else { const uint4 x = ph(gr, t, RS_ZPOS, 0); float g3; box_muller(x.x, x.y, z[0], z[1]); box_muller(x.z, x.w, z[2], g3); }
     const float alpha = fmaxf(dw.alphas[t], dw.alphas[dw.num_steps - 1]);   // clamp_min(alphas[-2])
     const float alpha_bar = dw.alpha_bars[t], sigma = dw.sigmas[t];
     const float c0 = div_(1.0f, sqrtf(add_(alpha, 1e-8f)));
@@ -198,7 +199,7 @@ step_kernel(StepArgs a, DiffW dw) {
 #pragma unroll
     for (int k = 0; k < NAA; ++k) q[k] = a.nz.expo_seq[(size_t)r * NAA + k];
   } else {
-    philox_exp20(ph, r, t, q);
+    philox_exp20(ph, gr, t, q);
   }
   float c0v[NAA];
 #pragma unroll
@@ -248,6 +249,42 @@ __global__ void complex_reduce_kernel(int N, int L, int bins, float dmin, float 
   }
 }
 
+// ---------------------------------------------------------------- DiffusionAntibodyDesign.encode, the per-residue part
+// models/diffab.py:46-50,78-84,138: context_mask = mask_heavyatom[:, :, CA] & ~generate_flag; R_0 = construct_3d_basis(CA, C, N)
+// (modules/common/geometry.py:47-69), v_0 = rotation_to_so3vec(R_0) (so3.py:10-30,60-63), p_0 = CA.  One thread per residue.
+__global__ void __launch_bounds__(128)
+design_prep_kernel(int M, int A_in, const float* __restrict__ pos, const uint8_t* __restrict__ mask_atoms,
+                   const uint8_t* __restrict__ gen, uint8_t* __restrict__ ctx, float* __restrict__ v0, float* __restrict__ p0) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= M) return;
+  const float* P = pos + (size_t)r * A_in * 3;                       // N 0..2, CA 3..5, C 6..8 (BBHeavyAtom order)
+  const float ca[3] = {P[3], P[4], P[5]};
+  float e1[3], v2[3], e2[3], e3[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { e1[c] = P[6 + c] - ca[c]; v2[c] = P[c] - ca[c]; }
+  const float n1 = sqrtf(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]) + 1e-6f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) e1[c] = e1[c] / n1;
+  const float pr = e1[0] * v2[0] + e1[1] * v2[1] + e1[2] * v2[2];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) e2[c] = v2[c] - pr * e1[c];
+  const float n2 = sqrtf(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]) + 1e-6f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) e2[c] = e2[c] / n2;
+  e3[0] = e1[1] * e2[2] - e1[2] * e2[1]; e3[1] = e1[2] * e2[0] - e1[0] * e2[2]; e3[2] = e1[0] * e2[1] - e1[1] * e2[0];
+  const Mat3 R = {{e1[0], e2[0], e3[0], e1[1], e2[1], e3[1], e1[2], e2[2], e3[2]}};       // columns e1 e2 e3
+  float x, y, z;
+  so3_log(R, x, y, z);
+  v0[(size_t)r * 3] = x; v0[(size_t)r * 3 + 1] = y; v0[(size_t)r * 3 + 2] = z;
+  p0[(size_t)r * 3] = ca[0]; p0[(size_t)r * 3 + 1] = ca[1]; p0[(size_t)r * 3 + 2] = ca[2];
+  ctx[r] = (mask_atoms[(size_t)r * A_in + 1] != 0 && gen[r] == 0) ? 1 : 0;
+}
+void launch_design_prep(int M, int A_in, const float* pos, const uint8_t* mask_atoms, const uint8_t* gen, uint8_t* ctx, float* v0,
+                        float* p0, cudaStream_t st) {
+  ProfScope prof__(KK_OTHER, st);
+  design_prep_kernel<<<(M + 127) / 128, 128, 0, st>>>(M, A_in, pos, mask_atoms, gen, ctx, v0, p0);
+}
+
 // ---------------------------------------------------------------- initial state
 
 __global__ void __launch_bounds__(128)
@@ -257,6 +294,7 @@ init_kernel(InitArgs a, DiffW dw) {
   if (r >= a.M) return;
   const bool gen = a.mask_gen[r] != 0;
   Philox ph(a.seed);
+  const uint32_t gr = (uint32_t)r + a.row0;
   const uint32_t tt = 0x7fffffffu;                 // "step" id of the initialisation draws
   float v[3], p[3];
 #pragma unroll
@@ -274,8 +312,8 @@ init_kernel(InitArgs a, DiffW dw) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) gp3[i] = a.gp[(size_t)r * 3 + i];
       } else {
-        const uint4 x = ph(r, tt, RS_INIT_G4, 0); box_muller(x.x, x.y, g[0], g[1]); box_muller(x.z, x.w, g[2], g[3]);
-        const uint4 y = ph(r, tt, RS_INIT_GP, 0); float g3; box_muller(y.x, y.y, gp3[0], gp3[1]); box_muller(y.z, y.w, gp3[2], g3);
+        const uint4 x = ph(gr, tt, RS_INIT_G4, 0); box_muller(x.x, x.y, g[0], g[1]); box_muller(x.z, x.w, g[2], g[3]);
+        const uint4 y = ph(gr, tt, RS_INIT_GP, 0); float g3; box_muller(y.x, y.y, gp3[0], gp3[1]); box_muller(y.z, y.w, gp3[2], g3);
       }
       const Mat3 Rq = quat_to_rot(g[0], g[1], g[2], g[3]);          // random_uniform_so3, so3.py:66-68
       so3_log(Rq, v[0], v[1], v[2]);
@@ -283,7 +321,7 @@ init_kernel(InitArgs a, DiffW dw) {
     }
     if (gen && a.sample_sequence) {
       if (a.s_rand) s = a.s_rand[r];
-      else { const uint4 x = ph(r, tt, RS_INIT_S, 0); s = (long long)(x.x % 19u); }   // randint_like(s, 0, 19): class 19 never drawn
+      else { const uint4 x = ph(gr, tt, RS_INIT_S, 0); s = (long long)(x.x % 19u); }   // randint_like(s, 0, 19): class 19 never drawn
     }
   } else {                                           // FullDPM.optimize, dpm_full.py:321-337
     const int t = a.tvec ? (int)a.tvec[r / a.L] : a.T0;
@@ -295,9 +333,9 @@ init_kernel(InitArgs a, DiffW dw) {
         unif = a.add.unif_ang[r]; gauss = a.add.gauss_ang[r];
         z[0] = a.add.z_pos[(size_t)r * 3]; z[1] = a.add.z_pos[(size_t)r * 3 + 1]; z[2] = a.add.z_pos[(size_t)r * 3 + 2];
       } else {
-        const uint4 x = ph(r, tt, RS_U, 0); float g3; box_muller(x.x, x.y, u[0], u[1]); box_muller(x.z, x.w, u[2], g3);
-        const uint4 y = ph(r, tt, RS_ANGLE, 0); float g1; ucdf = u01_half(y.x); unif = u01_half(y.y); box_muller(y.z, y.w, gauss, g1);
-        const uint4 w = ph(r, tt, RS_ZPOS, 0); box_muller(w.x, w.y, z[0], z[1]); box_muller(w.z, w.w, z[2], g3);
+        const uint4 x = ph(gr, tt, RS_U, 0); float g3; box_muller(x.x, x.y, u[0], u[1]); box_muller(x.z, x.w, u[2], g3);
+        const uint4 y = ph(gr, tt, RS_ANGLE, 0); float g1; ucdf = u01_half(y.x); unif = u01_half(y.y); box_muller(y.z, y.w, gauss, g1);
+        const uint4 w = ph(gr, tt, RS_ZPOS, 0); box_muller(w.x, w.y, z[0], z[1]); box_muller(w.z, w.w, z[2], g3);
       }
       const float abr = dw.alpha_bars_rot[t], ab = dw.alpha_bars[t];
       const float c0r = sqrtf(abr);
@@ -312,7 +350,7 @@ init_kernel(InitArgs a, DiffW dw) {
     if (a.z_out && a.sample_structure) {               // e_rand is returned for every row (transition.py:74-78)
       float z[3];
       if (parity) { z[0] = a.add.z_pos[(size_t)r * 3]; z[1] = a.add.z_pos[(size_t)r * 3 + 1]; z[2] = a.add.z_pos[(size_t)r * 3 + 2]; }
-      else { const uint4 w = ph(r, tt, RS_ZPOS, 0); float g3; box_muller(w.x, w.y, z[0], z[1]); box_muller(w.z, w.w, z[2], g3); }
+      else { const uint4 w = ph(gr, tt, RS_ZPOS, 0); float g3; box_muller(w.x, w.y, z[0], z[1]); box_muller(w.z, w.w, z[2], g3); }
       a.z_out[(size_t)r * 3] = z[0]; a.z_out[(size_t)r * 3 + 1] = z[1]; a.z_out[(size_t)r * 3 + 2] = z[2];
     }
     if (a.sample_sequence) {                          // transition.py:183-200 on every row; kept only where generated
@@ -320,7 +358,7 @@ init_kernel(InitArgs a, DiffW dw) {
       if (parity) {
 #pragma unroll
         for (int k = 0; k < NAA; ++k) q[k] = a.add.expo_seq[(size_t)r * NAA + k];
-      } else philox_exp20(ph, r, tt, q);
+      } else philox_exp20(ph, gr, tt, q);
       if (gen || a.seq_all_rows) {
         const float ab = gen ? dw.alpha_bars_seq[t] : 1.f;          // not generated: c_t = c_0 (transition.py:198)
         const float base = gen ? div_(add_(1.f, -ab), (float)NAA) : 0.f;

@@ -62,96 +62,6 @@ struct EpiProjPack {
   float* QA; float* QA_lo; float* KB; float* KB_lo; float* rq; float* rk; float* VT; float* VT_lo;
   int L, Lp;
   int qk_lo;            // 1: also write QA_lo / KB_lo (only the non-persistent logits kernels read them)
-  template <int BN>
-  __device__ __forceinline__ void operator()(int row, int n0, int N, float (&v)[BN]) const {
-    static_assert(BN == 96, "tile = 3 heads of 32 channels or 4 heads of 8 points");
-    const int b = row / L, r = row - b * L;
-    if (n0 < OFF_V) {                                   // q or k channels: heads n0 / 32 ...
-      const bool is_q = n0 < OFF_K;
-      const int h0 = (is_q ? n0 : n0 - OFF_K) / D;
-      const float sc = is_q ? 0.17677669529663687f : 1.f;               // 1 / sqrt(32) folded into q
-      float* dst = is_q ? QA : KB;
-      float* dlo = is_q ? QA_lo : KB_lo;
-#pragma unroll
-      for (int hh = 0; hh < 3; ++hh) {
-        const size_t o = ((size_t)(b * H + h0 + hh) * L + r) * 64;
-#pragma unroll
-        for (int c = 0; c < D; c += 4) {
-          const float4 w = make_float4(v[hh * D + c] * sc, v[hh * D + c + 1] * sc, v[hh * D + c + 2] * sc, v[hh * D + c + 3] * sc);
-          *reinterpret_cast<float4*>(dst + o + c) = w;
-          *reinterpret_cast<float4*>(dlo + o + c) = make_float4(tf32_lo(w.x), tf32_lo(w.y), tf32_lo(w.z), tf32_lo(w.w));
-        }
-      }
-      return;
-    }
-    if (n0 >= OFF_QP) {                                 // points: local -> global, q = R p + t (geometry.py:72-91)
-      float Rm[9], tv[3];
-#pragma unroll
-      for (int i = 0; i < 9; ++i) Rm[i] = __ldg(R + (size_t)row * 9 + i);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) tv[i] = __ldg(t + (size_t)row * 3 + i);
-#pragma unroll
-      for (int p = 0; p < BN; p += 3) {
-        const float x = v[p], y = v[p + 1], z = v[p + 2];
-        v[p + 0] = Rm[0] * x + Rm[1] * y + Rm[2] * z + tv[0];
-        v[p + 1] = Rm[3] * x + Rm[4] * y + Rm[5] * z + tv[1];
-        v[p + 2] = Rm[6] * x + Rm[7] * y + Rm[8] * z + tv[2];
-      }
-      if (n0 < OFF_VP) {                                // query / key points -> QA / KB columns 32..63 + norm terms
-        const bool is_q = n0 < OFF_KP;
-        const int h0 = (is_q ? n0 - OFF_QP : n0 - OFF_KP) / (P * 3);
-        float* dst = is_q ? QA : KB;
-        float* dlo = is_q ? QA_lo : KB_lo;
-        float* rn = is_q ? rq : rk;
-#pragma unroll
-        for (int hh = 0; hh < 4; ++hh) {
-          const float ch = __ldg(coef + h0 + hh);
-          const float sc = is_q ? 1.f : -2.f * ch;
-          float n2 = 0.f;
-#pragma unroll
-          for (int c = 0; c < P * 3; ++c) n2 = fmaf(v[hh * P * 3 + c], v[hh * P * 3 + c], n2);
-          rn[(size_t)(b * H + h0 + hh) * L + r] = ch * n2;
-          const size_t o = ((size_t)(b * H + h0 + hh) * L + r) * 64 + D;
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            float w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) w[e] = (c + e < P * 3) ? v[hh * P * 3 + c + e] * sc : 0.f;
-            *reinterpret_cast<float4*>(dst + o + c) = make_float4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<float4*>(dlo + o + c) = make_float4(tf32_lo(w[0]), tf32_lo(w[1]), tf32_lo(w[2]), tf32_lo(w[3]));
-          }
-        }
-        return;
-      }
-    }
-    // value channels (3 heads x 32) or global value points (4 heads x 24): one coalesced 4-byte store per column --
-    // the 32 lanes of the warp are 32 consecutive residues r of the same complex (or straddle two: still contiguous runs)
-    if (n0 >= OFF_VP) {
-      const int h0 = (n0 - OFF_VP) / (P * 3);
-#pragma unroll
-      for (int hh = 0; hh < 4; ++hh) {
-        const size_t o = ((size_t)(b * H + h0 + hh) * 64 + D) * Lp + r;
-#pragma unroll
-        for (int c = 0; c < P * 3; ++c) {
-          const float w = v[hh * P * 3 + c];
-          VT[o + (size_t)c * Lp] = w;
-          VT_lo[o + (size_t)c * Lp] = tf32_lo(w);
-        }
-      }
-    } else {
-      const int h0 = (n0 - OFF_V) / D;
-#pragma unroll
-      for (int hh = 0; hh < 3; ++hh) {
-        const size_t o = ((size_t)(b * H + h0 + hh) * 64) * Lp + r;
-#pragma unroll
-        for (int c = 0; c < D; ++c) {
-          const float w = v[hh * D + c];
-          VT[o + (size_t)c * Lp] = w;
-          VT_lo[o + (size_t)c * Lp] = tf32_lo(w);
-        }
-      }
-    }
-  }
 };
 
 // Accuracy note (measured on B200, scripts/debug_gemm.py): the tensor core TRUNCATES the fp32 accumulator on every
@@ -265,138 +175,6 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
   }
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
-}
-
-// ---------------------------------------------------------------- out_transform GEMM with the A lo plane built on chip
-// gemm3x_splitA_kernel: D[M][128] = A[M][K] * B[128][K]^T (+ bias) like gemm3x_kernel<128>, but only the RAW fp32 A operand
-// is read from global memory (it is the "hi" plane: the tensor core ignores the low 13 mantissa bits); its tf32 "lo" plane
-// is built in shared memory for every landed k-block.  For out_transform (K = 1824, A = feat) this halves the HBM stream
-// that bounds the kernel and removes feat_lo from the producers (pair_stream_kernel, aggr_tc_kernel).
-//   warp 0      TMA producer (A raw, B hi, B lo), warp 1 MMA issuer (waits for "split", not "full")
-//   warps 2-9   splitters + epilogue: each k-block they build A_lo (4 float4 per thread), and with a delay of two k-blocks they
-//               promote the finished 8-k-block chunk out of its TMEM buffer (fp32 adds in registers), so the tensor core never
-//               waits for a promotion; thread = (row, half of the 128 columns)
-constexpr int GS_THREADS = 320, GS_BN = 128, GS_ST = 3, GS_KCH = 8;
-
-template <class Epi>
-__global__ void __launch_bounds__(GS_THREADS, 1)
-gemm3x_splitA_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
-                     const __grid_constant__ CUtensorMap tmBl, int M, int N, int K, Epi epi) {
-  using S = GemmSmem<GS_BN, GS_ST>;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
-  uint64_t* empty = full + GS_ST;
-  uint64_t* split = empty + GS_ST;
-  uint64_t* tmem_full = split + GS_ST;         // [2]
-  uint64_t* tmem_empty = tmem_full + 2;        // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * GS_BN, m0 = blockIdx.y * G_BM;
-  const int nkb = K / G_BK;
-  const int nchunk = (nkb + GS_KCH - 1) / GS_KCH;
-  constexpr uint32_t ACC_COLS = 2 * GS_BN;                               // main | small
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < GS_ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&split[s], 8); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); }
-    mbar_fence_init();
-    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (elect_one()) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % GS_ST;
-        mbar_wait(&empty[s], ((kb / GS_ST) & 1) ^ 1);
-        unsigned char* st = smem + s * S::STAGE_BYTES;
-        mbar_expect_tx(&full[s], S::A_BYTES + 2 * S::B_BYTES);
-        tma_load_2d(st, &tmA, kb * G_BK, m0, &full[s]);
-        tma_load_2d(st + 2 * S::A_BYTES, &tmBh, kb * G_BK, n0, &full[s]);
-        tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &tmBl, kb * G_BK, n0, &full[s]);
-      }
-    }
-  } else if (warp == 1) {
-    constexpr uint32_t idesc = idesc_tf32(G_BM, GS_BN);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % GS_ST;
-      const int c = kb / GS_KCH, buf = c & 1;
-      const bool first = (kb % GS_KCH) == 0, last = (kb % GS_KCH) == GS_KCH - 1 || kb == nkb - 1;
-      if (first && c >= 2) mbar_wait(&tmem_empty[buf], ((c >> 1) - 1) & 1);         // chunk c - 2 was promoted out of this buffer
-      mbar_wait(&split[s], (kb / GS_ST) & 1);                                       // operands landed AND A_lo is built
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES), a_lo = a_hi + S::A_BYTES;
-        const uint32_t b_hi = a_hi + 2 * S::A_BYTES, b_lo = b_hi + S::B_BYTES;
-        const uint32_t d_main = tmem_base + buf * ACC_COLS, d_small = d_main + GS_BN;
-#pragma unroll
-        for (int k = 0; k < G_BK / 8; ++k) {
-          const uint64_t dah = smem_desc_sw128(a_hi + k * 32), dal = smem_desc_sw128(a_lo + k * 32);
-          const uint64_t dbh = smem_desc_sw128(b_hi + k * 32), dbl = smem_desc_sw128(b_lo + k * 32);
-          const uint32_t acc = (first && k == 0) ? 0u : 1u;
-          mma_tf32(d_main, dah, dbh, idesc, acc);
-          mma_tf32(d_small, dah, dbl, idesc, acc);
-          mma_tf32(d_small, dal, dbh, idesc, 1u);
-        }
-        mma_commit(&empty[s]);
-        if (last) mma_commit(&tmem_full[buf]);
-      }
-      __syncwarp();
-    }
-  } else {
-    const int q = warp & 3;                                            // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;                                  // which 64 of the 128 columns
-    const int et = (warp - 2) * 32 + lane;                             // 0..255
-    const int row = m0 + q * 32 + lane;
-    float v[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) v[i] = 0.f;
-    auto promote = [&](int c) {
-      const int buf = c & 1;
-      mbar_wait(&tmem_full[buf], (c >> 1) & 1);
-      tc_fence_after();
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + half * 64;
-#pragma unroll
-      for (int cc = 0; cc < 64; cc += 32) {
-        float tm[32], ts[32];
-        tmem_ld_32x32(tbase + cc, tm);
-        tmem_ld_32x32(tbase + GS_BN + cc, ts);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[cc + i] += tm[i] + ts[i];
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-    };
-    int promoted = 0;
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % GS_ST;
-      mbar_wait(&full[s], (kb / GS_ST) & 1);
-      const float4* src = reinterpret_cast<const float4*>(smem + s * S::STAGE_BYTES);
-      float4* dst = reinterpret_cast<float4*>(smem + s * S::STAGE_BYTES + S::A_BYTES);
-#pragma unroll
-      for (int m = 0; m < S::A_BYTES / 16 / 256; ++m) {
-        const float4 x = src[et + 256 * m];
-        dst[et + 256 * m] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
-      }
-      fence_async_smem();                                              // generic-proxy writes -> visible to the tensor core
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&split[s]);
-      // chunk c is complete once k-block (c + 1) * KCH - 1 has been multiplied; promote it two k-blocks later so that the
-      // tensor core already has split operands of chunk c + 1 queued
-      if (kb % GS_KCH == 2 && kb / GS_KCH - 1 == promoted && kb >= GS_KCH) { promote(promoted); ++promoted; }
-    }
-    while (promoted < nchunk) { promote(promoted); ++promoted; }
-    if (row < M) epi.template operator()<64>(row, n0 + half * 64, N, v);
-  }
-  __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 // ---------------------------------------------------------------- persistent projection GEMM
@@ -651,7 +429,6 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_encodeTiled g_encode = nullptr;
 
-static bool g_proj_legacy = false;       // ABOPT_PROJ_LEGACY=1: one-tile-per-CTA projection GEMM (A/B comparisons)
 cudaError_t tc_init() {
   if (!g_encode) {
     void* fn = nullptr;
@@ -663,10 +440,7 @@ cudaError_t tc_init() {
   }
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(gemm3x_kernel<128, 3, 8, EpiPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<128, 3>::TOTAL)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(gemm3x_kernel<96, 3, 8, EpiProjPack>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<96, 3>::TOTAL)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(proj_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(gemm3x_splitA_kernel<EpiPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<GS_BN, GS_ST>::TOTAL)) != cudaSuccess) return e;
-  { const char* ev = getenv("ABOPT_PROJ_LEGACY"); g_proj_legacy = ev && ev[0] == '1'; }
   return cudaSuccess;
 }
 
@@ -802,17 +576,6 @@ bool launch_gemm3x_plain(int M, int N, int K, const float* Ah, const float* Al, 
   return true;
 }
 
-// D[M][128-column tiles] = A * B^T (+bias); A raw fp32 only (its lo plane is built on chip), B as hi / lo planes
-bool launch_gemm3x_splitA(int M, int N, int K, const float* A, int lda, const float* Bh, const float* Bl, int ldb,
-                          float* D, int ldd, const float* bias, cudaStream_t st) {
-  CUtensorMap a_h, b_h, b_l;
-  if (!make_tmap(&a_h, A, M, K, lda, G_BM) || !make_tmap(&b_h, Bh, N, K, ldb, 128) || !make_tmap(&b_l, Bl, N, K, ldb, 128)) return false;
-  ProfScope prof__(KK_TAIL, st);
-  dim3 grid((N + 127) / 128, (M + G_BM - 1) / G_BM);
-  gemm3x_splitA_kernel<EpiPlain><<<grid, GS_THREADS, GemmSmem<GS_BN, GS_ST>::TOTAL, st>>>(a_h, b_h, b_l, M, N, K, EpiPlain{D, ldd, bias});
-  return true;
-}
-
 // the six GABlock projections as one GEMM, outputs packed for the tensor-core attention kernels (see EpiProjPack)
 bool launch_proj_pack(int M, int L, int Lp, const float* xh, const float* xl, const float* Wh, const float* Wl, const float* R, const float* t,
                       const float* coef, const AttnOperands& op, cudaStream_t st) {
@@ -822,16 +585,10 @@ bool launch_proj_pack(int M, int L, int Lp, const float* xh, const float* xl, co
     return false;
   ProfScope prof__(KK_PROJ, st);
   const EpiProjPack ep{R, t, coef, op.QA, op.QA_lo, op.KB, op.KB_lo, op.rq, op.rk, op.VT, op.VT_lo, L, Lp, attn_needs_qk_lo(L) ? 1 : 0};
-  if (!g_proj_legacy) {
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    const int nmt = (M + G_BM - 1) / G_BM;
-    proj_persist_kernel<<<nmt < sms ? nmt : sms, PP_THREADS, PP_SMEM, st>>>(a_h, a_l, b_h, b_l, M, ep);
-    return true;
-  }
-  dim3 grid(NPROJ / 96, (M + G_BM - 1) / G_BM);
-  gemm3x_kernel<96, 3, 8, EpiProjPack><<<grid, G_THREADS, GemmSmem<96, 3>::TOTAL, st>>>(
-      a_h, a_l, b_h, b_l, M, NPROJ, F, EpiProjPack{R, t, coef, op.QA, op.QA_lo, op.KB, op.KB_lo, op.rq, op.rk, op.VT, op.VT_lo, L, Lp, 1});
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int nmt = (M + G_BM - 1) / G_BM;
+  proj_persist_kernel<<<nmt < sms ? nmt : sms, PP_THREADS, PP_SMEM, st>>>(a_h, a_l, b_h, b_l, M, ep);
   return true;
 }
 

@@ -20,6 +20,7 @@ struct StepArgs {
   float* maxprob_rows;
   NoisePtrs nz;
   uint64_t seed;
+  uint32_t row0;                // first row of this batch in the global (unsharded) batch: Philox counters are global rows
 };
 struct InitArgs {
   int M, L, T0;
@@ -30,6 +31,7 @@ struct InitArgs {
   float* v_out; float* p_out_ang; long long* s_out;
   float* prmsd_out; float* ppl_out;
   uint64_t seed;
+  uint32_t row0;                // see StepArgs
   // FullDPM.forward (training): per-complex steps, the sequence draw on every row, the position noise kept
   const long long* tvec;        // (N,) steps; nullptr -> T0 for every complex
   int seq_all_rows;             // 1: _sample(c_t) also where nothing is generated (transition.py:198-199)
@@ -57,9 +59,6 @@ void launch_lo(const float* in, float* lo, size_t n, cudaStream_t st);
 bool launch_gemm3x_plain(int M, int N, int K, const float* Ah, const float* Al, int lda, const float* Bh, const float* Bl, int ldb,
                          float* D, int ldd, const float* bias, cudaStream_t st);
 
-bool launch_gemm3x_splitA(int M, int N, int K, const float* A, int lda, const float* Bh, const float* Bl, int ldb,
-                          float* D, int ldd, const float* bias, cudaStream_t st);
-
 cudaError_t tail_tc_init();
 void tail_debug_clocks(long long* out6);
 bool launch_outT_tail(int M, const float* feat, const float* x, const uint8_t* mask, const BlockW& w, float* x_out,
@@ -76,7 +75,7 @@ bool launch_proj_pack(int M, int L, int Lp, const float* xh, const float* xl, co
                       const float* coef, const AttnOperands& op, cudaStream_t st);
 cudaError_t aggr_tc_init();
 bool launch_aggr_tc(int nb, int b0, int N, int L, int Lp, const float* alpha, const float* VT, const float* VT_lo,
-                    const float* R, const float* t, float* feat, float* feat_lo, cudaStream_t st, const int2* windows = nullptr,
+                    const float* R, const float* t, float* feat, cudaStream_t st, const int2* windows = nullptr,
                     const int* wcount = nullptr, const int* cidx = nullptr);
 bool make_tmap(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 bool make_tmap_plain(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
@@ -91,8 +90,6 @@ bool make_tmap_3d(CUtensorMap* m, const float* base, uint64_t d0, uint64_t d1, u
 void launch_mixer(int M, const float* res_feat, const long long* s_t, const float* v_t, const EpsW& w,
                   float* x_out, float* Rbuf, const float* p_ang, float* p_norm, const float* mean, float scale,
                   float* x_lo_out, cudaStream_t st);
-void launch_tail(int M, const float* feat, const float* pre, const float* x, const uint8_t* mask, const BlockW& w, float* x_out,
-                 float* x_lo_out, cudaStream_t st);
 void launch_heads(int M, int L, const float* x, const float* beta, int beta_stride, const float* Rbuf, const float* v_t,
                   const uint8_t* mask_gen, const EpsW& w, float* v_next, float* R_next, float* eps_pos, float* c_den,
                   float* prmsd_rows, float* prmsd_logits, cudaStream_t st, const int* rows = nullptr, const int* count = nullptr,
@@ -118,7 +115,7 @@ cudaError_t pair_stream_init();
 bool make_tmap_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
 bool launch_pair_bias(int nb, int b0, int N, int L, int Lp, const float* z, const PairBiasPacked& pb, float* bias, cudaStream_t st);
 bool launch_pair_stream(int nb, int b0, int L, int Lp, const float* z, const uint8_t* mask,
-                        float* alpha, float* feat, float* feat_lo, cudaStream_t st, const int* cidx = nullptr);
+                        float* alpha, float* feat, cudaStream_t st, const int* cidx = nullptr);
 bool make_tmap_3d_plain(CUtensorMap* m, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1, uint32_t box2);
 
 void launch_angle_argmax(int M, int L, const long long* tvec, int t_uniform, const float* Y, const float* expo,
@@ -127,6 +124,8 @@ void launch_step(const StepArgs& a, const DiffW& dw, cudaStream_t st);
 void launch_complex_reduce(int N, int L, int bins, float dmin, float dmax, int masked_ppl, const float* prmsd_logits,
                            const float* maxprob_rows, const uint8_t* mask_gen, float* prmsd_out, float* ppl_out, cudaStream_t st);
 void launch_init(const InitArgs& a, const DiffW& dw, cudaStream_t st);
+void launch_design_prep(int M, int A_in, const float* pos, const uint8_t* mask_atoms, const uint8_t* gen, uint8_t* ctx, float* v0,
+                        float* p0, cudaStream_t st);
 void launch_rot_denoise(int M, int L, const float* v_t, const float* v_net, const uint8_t* mask_gen, const long long* tvec,
                         const NoisePtrs& nz, const DiffW& dw, float* v_out, cudaStream_t st);
 void launch_pos(int M, int L, int mode, const float* p_t, const float* other, const uint8_t* mask_gen, const long long* tvec,

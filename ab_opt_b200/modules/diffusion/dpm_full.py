@@ -13,7 +13,6 @@ RNG modes of sample()/optimize():
 """
 import ctypes
 import os
-import weakref
 
 import torch
 import torch.nn as nn
@@ -52,7 +51,7 @@ class pRMSDCa(nn.Module):
         self.tobin = DistanceToBins(dist_min, dist_max, num_bins)
 
 
-class EpsilonNet(nn.Module, _native.NativeOwner):
+class EpsilonNet(_native.NativeOwner, nn.Module):
     _native_scope = _capi.SCOPE_EPSNET
 
     def __init__(self, res_feat_dim, pair_feat_dim, num_layers, no_bins=None, encoder_opt={}):
@@ -113,7 +112,7 @@ class EpsilonNet(nn.Module, _native.NativeOwner):
         return v_next, R_next, eps_pos, c_den
 
 
-class FullDPM(nn.Module, _native.NativeOwner):
+class FullDPM(_native.NativeOwner, nn.Module):
     _native_scope = _capi.SCOPE_FULL
 
     def __init__(self, res_feat_dim, pair_feat_dim, num_steps, eps_net_opt={}, trans_rot_opt={}, trans_pos_opt={},
@@ -137,9 +136,10 @@ class FullDPM(nn.Module, _native.NativeOwner):
         if flavour == 'abdock':
             self.prmsd = pRMSDCa(num_bins, dist_min=dist_min, dist_max=dist_max)
         self.rng = rng or os.environ.get('ABOPT_RNG', 'philox')
-        ref = weakref.ref(self)
-        for child in (self.eps_net, self.trans_rot, self.trans_pos, self.trans_seq):
-            child.__dict__['_abopt_owner'] = ref
+        self._rebind_children()
+
+    def _rebind_children(self):
+        _native.bind_owner(self, (self.eps_net, self.trans_rot, self.trans_pos, self.trans_seq))
 
     # ---------------------------------------------------------------- native handle
     def _native_config(self):
@@ -156,9 +156,15 @@ class FullDPM(nn.Module, _native.NativeOwner):
     def _unnormalize_position(self, p_norm):
         return p_norm * self.position_scale + self.position_mean
 
-    @torch.no_grad()
     def forward(self, v_0, p_0, s_0, res_feat, pair_feat, mask_generate, mask_res, denoise_structure, denoise_sequence,
                 t=None, noise=None, rng=None):
+        _native.forbid_training_graph(self, 'FullDPM.forward')
+        with torch.no_grad():
+            return self._loss_forward(v_0, p_0, s_0, res_feat, pair_feat, mask_generate, mask_res, denoise_structure,
+                                      denoise_sequence, t, noise, rng)
+
+    def _loss_forward(self, v_0, p_0, s_0, res_feat, pair_feat, mask_generate, mask_res, denoise_structure, denoise_sequence,
+                      t=None, noise=None, rng=None):
         """dpm_full.py:156-234 (AbDesign :138-190): the loss dict of one training step, FORWARD ONLY -- the values are
         computed by the sm_100a kernels (abopt_loss_forward) and carry no autograd graph; the backward pass is not part
         of the native path yet.  `noise` (dict of the six draws of one step) replays given draws; otherwise rng='torch'
@@ -174,6 +180,13 @@ class FullDPM(nn.Module, _native.NativeOwner):
         mg, mr = _capi.cuda_mask(mask_generate, 'mask_generate'), _capi.cuda_mask(mask_res, 'mask_res')
         if res_feat.shape != (N, L, 128) or pair_feat.shape != (N, L, L, 64) or t.shape != (N,):
             raise ValueError('bad input shapes')
+        for nm_, x in (('v_0', v_0), ('p_0', p_0), ('s_0', s_0), ('res_feat', res_feat), ('pair_feat', pair_feat), ('t', t),
+                       ('mask_generate', mg), ('mask_res', mr)):
+            if x.device != dev:
+                raise ValueError(f'{nm_} lives on {x.device}, the model on {dev}')
+        # the reference indexes its (T+1)-entry schedules with t and raises IndexError outside [0, T]; a kernel would read out of bounds
+        if N and (int(t.min()) < 0 or int(t.max()) > self.num_steps):
+            raise IndexError(f't must be in [0, {self.num_steps}]')
         flags = (_capi.SAMPLE_STRUCTURE if denoise_structure else 0) | (_capi.SAMPLE_SEQUENCE if denoise_sequence else 0)
         rng = rng or self.rng
         M = N * L
@@ -212,7 +225,8 @@ class FullDPM(nn.Module, _native.NativeOwner):
         """dpm_full.py:236-302.  Returns {t: [v, p_angstrom, s, prmsd, perplexity]} (AbDock flavour) or
         {t: (v, p_angstrom, s)} (AbDesign), t = num_steps..0; entries for t >= 1 live on the CPU, traj[0] on the device."""
         return self._run(v, p, s, 0, res_feat, pair_feat, mask_generate, mask_res, sample_structure, sample_sequence,
-                         kwargs.get('rng', self.rng), kwargs.get('keep_trajectory', True))
+                         kwargs.get('rng', self.rng), kwargs.get('keep_trajectory', True), kwargs.get('seed'),
+                         kwargs.get('batch_offset', 0), kwargs.get('batch_total'))
 
     @torch.no_grad()
     def optimize(self, v, p, s, opt_step: int, res_feat, pair_feat, mask_generate, mask_res, sample_structure=True,
@@ -221,13 +235,23 @@ class FullDPM(nn.Module, _native.NativeOwner):
         if not 1 <= int(opt_step) <= self.num_steps:
             raise ValueError('opt_step must be in [1, num_steps]')
         return self._run(v, p, s, int(opt_step), res_feat, pair_feat, mask_generate, mask_res, sample_structure,
-                         sample_sequence, kwargs.get('rng', self.rng), kwargs.get('keep_trajectory', True))
+                         sample_sequence, kwargs.get('rng', self.rng), kwargs.get('keep_trajectory', True), kwargs.get('seed'),
+                         kwargs.get('batch_offset', 0), kwargs.get('batch_total'))
 
     def _run(self, v, p, s, opt_step, res_feat, pair_feat, mask_generate, mask_res, sample_structure, sample_sequence,
-             rng, keep):
+             rng, keep, seed=None, batch_offset=0, batch_total=None):
+        """Extra keyword arguments of sample() / optimize() (batch sharding): `batch_offset` = index of v[0]
+        in the global batch and `batch_total` = its size; `seed` = the Philox seed (default: drawn from torch's generator).
+        With the same seed / generator state on every rank, the ranks' slices equal the unsharded run: the Philox counters
+        are global rows, and rng='torch' draws the reference's full-batch tensors on every rank and uses its rows."""
         nm = self.native()
         L_ = _capi.lib()
         N, L = v.shape[:2]
+        NT = int(batch_total) if batch_total is not None else N
+        off = int(batch_offset)
+        if off < 0 or off + N > NT:
+            raise ValueError('batch_offset / batch_total do not contain this batch')
+        _capi.check(L_.abopt_model_set_batch_offset(nm.handle, off))
         v, p = _capi.cuda_f32(v, 'v'), _capi.cuda_f32(p, 'p')
         s = _capi.cuda_i64(s, 's')
         res_feat, pair_feat = _capi.cuda_f32(res_feat, 'res_feat'), _capi.cuda_f32(pair_feat, 'pair_feat')
@@ -250,7 +274,7 @@ class FullDPM(nn.Module, _native.NativeOwner):
         tpl = torch.zeros(T0 + 1, N, device=dev) if abdock else None
         st = _capi.stream_ptr(dev)
         if rng == 'philox':
-            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if seed is None else int(seed)
             _capi.check(L_.abopt_sample_device(nm.handle, N, L, _capi.ptr(v), _capi.ptr(p), _capi.ptr(s), _capi.ptr(res_feat),
                                                _capi.ptr(pair_feat), _capi.ptr(mg), _capi.ptr(mr), flags, opt_step, seed, None,
                                                None, _capi.ptr(tv), _capi.ptr(tp), _capi.ptr(ts), _capi.ptr(tpr), _capi.ptr(tpl), st))
@@ -258,26 +282,38 @@ class FullDPM(nn.Module, _native.NativeOwner):
             flags |= _capi.KEEP_TRAJECTORY
             keep = True
             M = N * L
+            MT = NT * L
+            rows = slice(off * L, (off + N) * L)
 
-            def step_draws():     # so3.py:143,123,126,131 ; transition.py:95 ; transition.py:179
-                d = dict(u=torch.randn(N, L, 3, device=dev), expo_ang=torch.empty(M, 8191, device=dev).exponential_(1),
-                         unif_ang=torch.rand(M, device=dev), gauss_ang=torch.randn(M, device=dev),
-                         z_pos=torch.randn(N, L, 3, device=dev), expo_seq=torch.empty(M, 20, device=dev).exponential_(1))
+            def mine(x, per_row=False):      # the full-batch draw of the reference -> the rows of this shard
+                if NT == N:
+                    return x
+                return (x[rows] if per_row else x[off:off + N]).contiguous()
+
+            def add_noise_draws():    # so3.py:143,123,126,131 ; transition.py:95 / :74 ; transition.py:179 / :199
+                return dict(u=mine(torch.randn(NT, L, 3, device=dev)),
+                            expo_ang=mine(torch.empty(MT, 8191, device=dev).exponential_(1), True),
+                            unif_ang=mine(torch.rand(MT, device=dev), True), gauss_ang=mine(torch.randn(MT, device=dev), True),
+                            z_pos=mine(torch.randn(NT, L, 3, device=dev)))
+
+            def step_draws():
+                d = add_noise_draws()
+                d['expo_seq'] = mine(torch.empty(MT, 20, device=dev).exponential_(1), True)
                 return d, _capi.StepNoise(*[d[k].data_ptr() for k in ('u', 'expo_ang', 'unif_ang', 'gauss_ang', 'z_pos', 'expo_seq')])
             if not optimize:          # dpm_full.py:255-267 (draws only happen for the enabled parts)
-                g4 = torch.randn(N, L, 4, device=dev) if sample_structure else torch.zeros(N, L, 4, device=dev)
-                gp = torch.randn_like(p) if sample_structure else torch.zeros_like(p)
-                sr = torch.randint_like(s, low=0, high=19) if sample_sequence else torch.zeros_like(s)
+                g4 = mine(torch.randn(NT, L, 4, device=dev)) if sample_structure else torch.zeros(N, L, 4, device=dev)
+                gp = mine(torch.randn(NT, L, 3, device=dev)) if sample_structure else torch.zeros_like(p)
+                sr = (torch.randint_like(s, low=0, high=19) if NT == N else mine(torch.randint(0, 19, (NT, L), device=dev, dtype=s.dtype))) \
+                    if sample_sequence else torch.zeros_like(s)
                 init = _capi.InitNoise(g4.data_ptr(), gp.data_ptr(), sr.data_ptr(), None)
             else:                     # dpm_full.py:321-337
                 d = {}
                 if sample_structure:
-                    d.update(u=torch.randn(N, L, 3, device=dev), expo_ang=torch.empty(M, 8191, device=dev).exponential_(1),
-                             unif_ang=torch.rand(M, device=dev), gauss_ang=torch.randn(M, device=dev), z_pos=torch.randn_like(p))
+                    d.update(add_noise_draws())
                 else:
                     d.update(u=torch.zeros(N, L, 3, device=dev), expo_ang=torch.ones(M, 8191, device=dev),
                              unif_ang=torch.zeros(M, device=dev), gauss_ang=torch.zeros(M, device=dev), z_pos=torch.zeros_like(p))
-                d['expo_seq'] = torch.empty(M, 20, device=dev).exponential_(1) if sample_sequence else torch.ones(M, 20, device=dev)
+                d['expo_seq'] = mine(torch.empty(MT, 20, device=dev).exponential_(1), True) if sample_sequence else torch.ones(M, 20, device=dev)
                 add = _capi.StepNoise(*[d[k].data_ptr() for k in ('u', 'expo_ang', 'unif_ang', 'gauss_ang', 'z_pos', 'expo_seq')])
                 init = _capi.InitNoise(None, None, None, ctypes.pointer(add))
             _capi.check(L_.abopt_sample_init(nm.handle, N, L, _capi.ptr(v), _capi.ptr(p), _capi.ptr(s), _capi.ptr(mg), flags, opt_step,

@@ -7,6 +7,7 @@ import torch
 import torch.nn as nn
 
 from ... import _capi
+from .. import _native
 from ..common.so3 import ApproxAngularDistribution
 
 
@@ -31,7 +32,7 @@ class VarianceSchedule(nn.Module):
         self.register_buffer('sqrt_recipm1_alphas_cumprod', torch.sqrt(1. / alpha_bars - 1))
 
 
-class _Transition(nn.Module):
+class _Transition(_native.Owned, nn.Module):
     """Transitions are leaves of FullDPM; the owner injects itself so they can reach its handle."""
 
     def _owner(self):

@@ -10,7 +10,7 @@ from ... import _capi
 from ..common.layers import LayerNorm
 
 
-class GABlock(nn.Module, _native.NativeOwner):
+class GABlock(_native.NativeOwner, nn.Module):
     _native_scope = _capi.SCOPE_ENCODER
 
     def __init__(self, node_feat_dim, pair_feat_dim, value_dim=32, query_key_dim=32, num_query_points=8,
@@ -71,7 +71,7 @@ def _run_block(nm, layer, R, t, x, z, mask):
     return out
 
 
-class GAEncoder(nn.Module, _native.NativeOwner):
+class GAEncoder(_native.NativeOwner, nn.Module):
     _native_scope = _capi.SCOPE_ENCODER
 
     def __init__(self, node_feat_dim, pair_feat_dim, num_layers, ga_block_opt={}):

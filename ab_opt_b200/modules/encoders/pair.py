@@ -7,6 +7,7 @@ import torch
 import torch.nn as nn
 
 from ... import _capi
+from .. import _native
 
 
 class AngularEncoding(nn.Module):
@@ -104,10 +105,14 @@ class PairEmbedding(nn.Module):
     def native(self):
         return _native_embed(self, 'pair')
 
-    @torch.no_grad()
     def forward(self, aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask=None, sequence_mask=None):
         """aa, res_nb, chain_nb (N,L); pos_atoms (N,L,A,3); mask_atoms (N,L,A); structure_mask, sequence_mask (N,L) or None
         -> (N,L,L,feat_dim).  pair.py:37-101."""
+        _native.forbid_training_graph(self, 'PairEmbedding.forward')
+        with torch.no_grad():
+            return self._forward(aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask, sequence_mask)
+
+    def _forward(self, aa, res_nb, chain_nb, pos_atoms, mask_atoms, structure_mask, sequence_mask):
         nm = self.native()
         aa, res_nb, chain_nb, pos, mask, sm, qm, N, L, A = _common_inputs(aa, res_nb, chain_nb, pos_atoms, mask_atoms,
                                                                           structure_mask, sequence_mask)
@@ -138,9 +143,13 @@ class ResidueEmbedding(nn.Module):
     def native(self):
         return _native_embed(self, 'res')
 
-    @torch.no_grad()
     def forward(self, aa, res_nb, chain_nb, pos_atoms, mask_atoms, fragment_type, structure_mask=None, sequence_mask=None):
         """-> (N, L, feat_dim).  residue.py:27-94."""
+        _native.forbid_training_graph(self, 'ResidueEmbedding.forward')
+        with torch.no_grad():
+            return self._forward(aa, res_nb, chain_nb, pos_atoms, mask_atoms, fragment_type, structure_mask, sequence_mask)
+
+    def _forward(self, aa, res_nb, chain_nb, pos_atoms, mask_atoms, fragment_type, structure_mask, sequence_mask):
         nm = self.native()
         aa, res_nb, chain_nb, pos, mask, sm, qm, N, L, A = _common_inputs(aa, res_nb, chain_nb, pos_atoms, mask_atoms,
                                                                           structure_mask, sequence_mask)

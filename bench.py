@@ -7,8 +7,10 @@
 One "step" = one complete FullDPM.sample() (T=100 reverse steps) over one synthetic batch per GPU.
 Metric: sampled CDR residues / s = (#GPUs x B x n_gen x K) / time, whole job.
   ours      : ab_opt_b200.FullDPM.sample -> libabopt_b200 (sm_100a kernels), inputs resident in HBM (`value`);
-              `e2e` = the C-ABI host entry point abopt_sample_host with pinned HOST buffers, H2D + D2H inside
-              the timed region.
+              `e2e` = the C-ABI host entry point abopt_design_host (atoms in pinned HOST buffers -> featurisation + loop ->
+              101-frame trajectory in host memory), H2D + D2H inside the timed region;
+              `gpu_eager_baseline` = the reference's eager-PyTorch evaluation (its port) on the same GPU, `cpu_baseline` on
+              the host cores (N=1 only).
   reference : the reference's CPU path (oracle port, evaluation order of the reference: broadcast-multiply-sum
               with full temporaries) on the host cores, on a bounded sample of the same workload.
 Prints ONE JSON line on rank 0.
@@ -179,6 +181,116 @@ def workload_name(cfg):
             f"{NUM_LAYERS} IPA layers, T={T_STEPS}")
 
 
+# ------------------------------------------------------------------------------------------ baseline legs on the GPU box
+def gpu_eager_baseline(cfg, dev, n_reverse_steps=3):
+    """The bar SURVEY.md finding 1 / BASELINE.md 4.2 name: the reference's eager-PyTorch evaluation ON THE SAME B200.  The
+    reference tree does not travel to the GPU box, so this leg runs its line-by-line port (oracle/, materialize=True = the
+    reference's broadcast-multiply-sum order with the full (B,L,L,H,.) temporaries, cuBLAS fp32 linears, ATen softmax) on cuda
+    at the FULL batch for a few reverse steps and scales linearly to T.  A baseline leg, never the product path."""
+    from oracle import weights as ow, sampler as osamp, transitions as OT
+    W = {k: v.to(dev) for k, v in ow.make_state_dict(seed=1234, num_layers=NUM_LAYERS, flavour=cfg['flavour']).items()}
+    inp = synthetic_batch(cfg, 1234, dev)
+    B, L = cfg['B'], cfg['L']
+    n_gen = int(inp['mask_generate'][0].sum())
+    gen = torch.Generator(device=dev).manual_seed(0)
+
+    def steps(k):
+        v, p, s = inp['v'], inp['p'] / 10.0, inp['s']
+        for i in range(k):
+            nz = OT.draw_step_noise(B, L, gen, device=dev)
+            st = osamp.reverse_step(W, T_STEPS - i, v, p, s, inp['res_feat'], inp['pair_feat'], inp['mask_generate'], inp['mask_res'],
+                                    nz, obj=cfg['obj'], materialize=True)
+            v, p, s = st['v_next'], st['p_next'], st['s_next']
+        return v
+    with torch.no_grad():
+        steps(1)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        steps(n_reverse_steps)
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms_step = e0.elapsed_time(e1) / n_reverse_steps
+    peak_gb = torch.cuda.max_memory_allocated(dev) / 1e9
+    del W, inp
+    torch.cuda.empty_cache()
+    return {'value': B * n_gen / (ms_step * T_STEPS / 1e3), 'unit': 'residues/s', 'ms_per_sample': ms_step * T_STEPS,
+            'ms_per_reverse_step': ms_step, 'kind': 'port of the reference evaluated eagerly with PyTorch on the same GPU',
+            'sample': f'{n_reverse_steps} reverse steps at the full batch B={B}, L={L}, {NUM_LAYERS} layers, fp32 (allow_tf32 off as in the '
+                      f'reference runners), scaled linearly to T={T_STEPS}; peak memory {peak_gb:.1f} GB'}
+
+
+def synthetic_atoms(cfg, seed, B=None):
+    """Seeded protein-like batch fields of the reference's data loader (host tensors): a noisy CA walk (~3.8 A steps), heavy atoms
+    around it, two chains, consecutive numbering; generate_flag = the config's CDR segments."""
+    B = B or cfg['B']
+    L, A = cfg['L'], 15
+    g = torch.Generator().manual_seed(seed)
+    ca = torch.cumsum(torch.randn(B, L, 3, generator=g) * 2.2, dim=1)
+    ca = ca - ca.mean(1, keepdim=True)
+    pos = ca[:, :, None, :] + 1.6 * torch.randn(B, L, A, 3, generator=g)
+    pos[:, :, 1] = ca
+    mask_atoms = torch.rand(B, L, A, generator=g) < 0.8
+    mask_atoms[:, :, :4] = True
+    chain_nb = torch.zeros(B, L, dtype=torch.long)
+    chain_nb[:, L // 2:] = 1
+    res_nb = torch.arange(1, L + 1).expand(B, L).contiguous()
+    gen = torch.zeros(B, L, dtype=torch.bool)
+    for a, b in cfg['gen']:
+        gen[:, a:b] = True
+    ft = torch.ones(B, L, dtype=torch.long)
+    ft[:, L // 2:] = 2
+    return dict(aa=torch.randint(0, 20, (B, L), generator=g), res_nb=res_nb, chain_nb=chain_nb, pos_heavyatom=pos.contiguous(),
+                mask_heavyatom=mask_atoms, fragment_type=ft, generate_flag=gen, mask=torch.ones(B, L, dtype=torch.bool))
+
+
+def timed_config(cfg, dev, rank, world, steps, warmup, init_calls=2):
+    """`value` leg of one configuration: W warm-up + K timed FullDPM.sample calls on this rank's complexes through
+    ab_opt_b200.sharding.sample_shard (N > 1: the loop on the shard + the one packed gather).  -> (ms per step max over ranks,
+    launches, last trajectory, model, inputs)."""
+    import torch.distributed as dist
+    import ab_opt_b200
+    from ab_opt_b200 import sharding
+    model = build_model(cfg, dev)
+    inp = synthetic_batch(cfg, 1000 + rank, dev)          # each rank owns its own complexes (weak scaling, no exchange)
+    B = cfg['B']
+    kw = dict(sample_structure=cfg['sample_structure'], sample_sequence=cfg['sample_sequence'])
+    a = (inp['v'], inp['p'], inp['s'], inp['res_feat'], inp['pair_feat'], inp['mask_generate'], inp['mask_res'])
+
+    def step():
+        if world > 1:
+            return sharding.sample_shard(model, inp, rank * B, world * B, **kw)[1]
+        return model.sample(*a, **kw)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    torch.manual_seed(rank)
+    # initialisation, not warm-up: the first calls pay one-off costs (3 GB workspace cudaMalloc + memset, TMA descriptor
+    # encodes, first-touch page faults of the host-side trajectory buffers) that measured 150-190 ms each on B200
+    for _ in range(init_calls):
+        step()
+    for _ in range(warmup):
+        step()
+    barrier()
+    l0 = ab_opt_b200.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        traj = step()
+    e1.record()
+    barrier()
+    launches = ab_opt_b200.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    assert torch.isfinite(traj[0][1]).all()
+    return ms / steps, launches, traj, model, inp, a, kw, barrier
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args, cfg, rank, world, local_rank):
     import torch.distributed as dist
@@ -188,86 +300,54 @@ def run_ours(args, cfg, rank, world, local_rank):
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    model = build_model(cfg, dev)
-    inp = synthetic_batch(cfg, 1000 + rank, dev)          # each rank owns its own complexes (weak scaling, no exchange)
     B, L = cfg['B'], cfg['L']
-    n_gen = int(inp['mask_generate'][0].sum())
-    a = (inp['v'], inp['p'], inp['s'], inp['res_feat'], inp['pair_feat'], inp['mask_generate'], inp['mask_res'])
-    kw = dict(sample_structure=cfg['sample_structure'], sample_sequence=cfg['sample_sequence'])
-    gathered = None
-
-    def step():
-        nonlocal gathered
-        traj = model.sample(*a, **kw)
-        if world > 1:     # the one collective of the path: gather the finished structures
-            fin = torch.cat([traj[0][0], traj[0][1], traj[0][2].float()[..., None]], -1).contiguous()
-            gathered = torch.empty(world * B, L, 7, device=dev)
-            dist.all_gather_into_tensor(gathered, fin)
-        return traj
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    torch.manual_seed(rank)
-    # initialisation, not warm-up: the first two calls pay one-off costs (3 GB workspace cudaMalloc + memset, TMA descriptor
-    # encodes, first-touch page faults of the host-side trajectory buffers) that measured 150-190 ms each on B200
-    for _ in range(2):
-        step()
-    for _ in range(args.warmup):
-        step()
-    barrier()
     clocks = ClockSampler(local_rank) if rank == 0 else None
-    l0 = ab_opt_b200.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        traj = step()
-    e1.record()
-    barrier()
-    launches = ab_opt_b200.launch_count() - l0
-    ms = e0.elapsed_time(e1)
+    ms_per_step, launches, traj, model, inp, a, kw, barrier = timed_config(cfg, dev, rank, world, args.steps, args.warmup)
     clk = clocks.stop() if clocks else None
-    if world > 1:
-        tms = torch.tensor([ms], device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
-    ms_per_step = ms / args.steps
+    n_gen = int(inp['mask_generate'][0].sum())
     value = world * B * n_gen / (ms_per_step / 1e3)
-    assert torch.isfinite(traj[0][1]).all()
 
-    # ---- end to end through the C ABI with HOST buffers (pinned), H2D + D2H inside the timed region
+    # ---- end to end through the C ABI with HOST buffers, the job the reference's runner does per batch (models/diffab.py:115-141):
+    #      atoms in (pinned host memory) -> ResidueEmbedding + PairEmbedding + frames + 100 reverse steps on the device -> the whole
+    #      101-frame trajectory back in host memory.  H2D and D2H are inside the timed region.
     nm = model.native()
-    host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in inp.items()}
+    torch.manual_seed(4321)
+    pe = ab_opt_b200.PairEmbedding(64, 15).to(dev).eval()
+    re_ = ab_opt_b200.ResidueEmbedding(128, 15).to(dev).eval()
+    atoms = synthetic_atoms(cfg, 2000 + rank)
+    host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in atoms.items()}
     T0 = T_STEPS
     abdock = cfg['flavour'] == 'abdock'
     otv = torch.empty(T0 + 1, B, L, 3, pin_memory=True); otp = torch.empty(T0 + 1, B, L, 3, pin_memory=True)
     ots = torch.empty(T0 + 1, B, L, dtype=torch.int64, pin_memory=True)
     opr = torch.empty(T0 + 1, B, pin_memory=True) if abdock else None
     opl = torch.empty(T0 + 1, B, pin_memory=True) if abdock else None
-    flags = (_capi.SAMPLE_STRUCTURE if cfg['sample_structure'] else 0) | (_capi.SAMPLE_SEQUENCE if cfg['sample_sequence'] else 0)
+    flags = (_capi.SAMPLE_STRUCTURE if cfg['sample_structure'] else 0) | (_capi.SAMPLE_SEQUENCE if cfg['sample_sequence'] else 0) | \
+        _capi.KEEP_TRAJECTORY
+    peh, reh = pe.native().handle, re_.native().handle
+    _capi.check(_capi.lib().abopt_model_set_batch_offset(nm.handle, rank * B))
 
     def e2e_step(seed):
-        _capi.check(_capi.lib().abopt_sample_host(nm.handle, B, L, _capi.ptr(host['v']), _capi.ptr(host['p']), _capi.ptr(host['s']),
-                                                  _capi.ptr(host['res_feat']), _capi.ptr(host['pair_feat']), _capi.ptr(host['mask_generate']),
-                                                  _capi.ptr(host['mask_res']), flags, 0, seed, _capi.ptr(otv), _capi.ptr(otp), _capi.ptr(ots),
-                                                  _capi.ptr(opr), _capi.ptr(opl)))
+        _capi.check(_capi.lib().abopt_design_host(
+            nm.handle, peh, reh, B, L, 15, _capi.ptr(host['aa']), _capi.ptr(host['res_nb']), _capi.ptr(host['chain_nb']),
+            _capi.ptr(host['pos_heavyatom']), _capi.ptr(host['mask_heavyatom']), _capi.ptr(host['fragment_type']),
+            _capi.ptr(host['generate_flag']), _capi.ptr(host['mask']), flags, 0, seed, _capi.ptr(otv), _capi.ptr(otp), _capi.ptr(ots),
+            _capi.ptr(opr), _capi.ptr(opl)))
     e2e_step(1)
     barrier()
-    n_e2e = max(1, min(args.steps, 3))
     t0 = time.perf_counter()
-    for i in range(n_e2e):
+    for i in range(args.steps):
         e2e_step(2 + i)
-    dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev)
+    dt = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    assert torch.isfinite(otp[0]).all() and torch.isfinite(otp[T0 // 2]).all()
     e2e_value = world * B * n_gen / float(dt.item())
     h2d = sum(v.numel() * v.element_size() for v in host.values())
-    d2h = 2 * (B * L * 3 * 4 * 2 + B * L * 8) + (4 * B * 4 if abdock else 0)       # slots 0 and T0 of v, p, s (+ prmsd, ppl)
+    d2h = otv.numel() * 4 + otp.numel() * 4 + ots.numel() * 8 + (2 * (T0 + 1) * B * 4 if abdock else 0)
 
     # ---- per-kernel timing pass (CUDA events around every launch, outside the timed region) -> roofline
-    roof, breakdown = None, None
+    roof, breakdown, feat_line = None, None, None
     if rank == 0:
         _capi.profile_enable(True)
         torch.manual_seed(0)
@@ -282,7 +362,7 @@ def run_ours(args, cfg, rank, world, local_rank):
         # Focus mode: for models without the pRMSD head the LAST block streams z only for the generated
         # query rows, so that launch has fewer algorithmic bytes.  The kernel-level roofline is bytes-weighted over all
         # pair_stream_kernel launches of a sample; whole_step_* keep SURVEY 8d's fixed denominator (z once per layer).
-        focus = cfg['flavour'] == 'abdesign' and L <= 256 and os.environ.get('ABOPT_NO_FOCUS', '0') != '1'
+        focus = cfg['flavour'] == 'abdesign' and os.environ.get('ABOPT_NO_FOCUS', '0') != '1'
         alg_full = per_launch_complexes * algorithmic_bytes_per_complex_layer(L)
         alg_focus = per_launch_complexes * (n_gen * L * 64 * 4 + L * (2 * 128 * 4 + 36 + 12 + 1))
         alg_bytes = ((NUM_LAYERS - 1) * alg_full + (alg_focus if focus else alg_full)) / NUM_LAYERS      # mean per launch
@@ -293,6 +373,7 @@ def run_ours(args, cfg, rank, world, local_rank):
             tj = json.load(open(tpath))
             if tj.get('L') == L:
                 traffic = tj['dram_bytes_per_complex'] * per_launch_complexes * alg_bytes / alg_full
+        whole = B * NUM_LAYERS * T_STEPS * algorithmic_bytes_per_complex_layer(L) / (ms_per_step * 1e-3) / 1e9
         roof = {'bound': 'hbm', 'kernel': 'pair_stream_kernel (streams pair_feat once per IPA layer: softmax-weighted pair aggregation)',
                 'achieved': achieved, 'peak': peak,
                 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
@@ -300,15 +381,38 @@ def run_ours(args, cfg, rank, world, local_rank):
                 'focus': ('last of %d layers streams only the %d generated query rows per complex; achieved / traffic / '
                           'algorithmic bytes are means over all launches of a sample' % (NUM_LAYERS, n_gen)) if focus else None,
                 'share_of_gpu_time': pair_ms / total_ms,
-                'whole_step_achieved': B * NUM_LAYERS * T_STEPS * algorithmic_bytes_per_complex_layer(L) / (ms_per_step * 1e-3) / 1e9,
-                'whole_step_frac': B * NUM_LAYERS * T_STEPS * algorithmic_bytes_per_complex_layer(L) / (ms_per_step * 1e-3) / 1e9 / peak}
+                'whole_step_achieved': whole, 'whole_step_frac': whole / peak}
         breakdown = {k: {'ms': round(v[0], 3), 'launches': v[1]} for k, v in prof.items() if v[1]}
+        # the step before the loop, part of the e2e job: PairEmbedding / ResidueEmbedding at this shape
+        dat = {k: v.to(dev) for k, v in atoms.items()}
+        ctx = dat['mask_heavyatom'][:, :, 1] & ~dat['generate_flag']
+        pa = (dat['aa'], dat['res_nb'], dat['chain_nb'], dat['pos_heavyatom'], dat['mask_heavyatom'])
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        tp_, tr_ = 0.0, 0.0
+        for i in range(4):
+            flush.zero_()
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record(); z = pe(*pa, ctx, ctx); e[1].record(); x = re_(*pa, dat['fragment_type'], ctx, ctx); e[2].record()
+            torch.cuda.synchronize()
+            if i:
+                tp_ += e[0].elapsed_time(e[1]) / 3; tr_ += e[1].elapsed_time(e[2]) / 3
+        feat_line = {'pair_embed_ms': tp_, 'res_embed_ms': tr_, 'pairs_per_s': B * L * L / (tp_ / 1e3),
+                     'note': 'PairEmbedding / ResidueEmbedding.forward at this shape, 15 atoms, L2 flushed between iterations'}
+        del dat, z, x, flush
 
     if rank == 0:
-        cpu = None
+        cpu, eager = None, None
         if world == 1 and not args.no_cpu_baseline:
             cv, cdt, cores, sample, _ = cpu_reference_run(cfg, steps=2, warmup=1, n_reverse_steps=4, B_cpu=4)
             cpu = {'value': cv, 'unit': 'residues/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+        if world == 1 and not args.no_gpu_eager:
+            del inp, a, traj, nm
+            model.invalidate_native()
+            torch.cuda.empty_cache()
+            try:
+                eager = gpu_eager_baseline(cfg, dev)
+            except Exception as ex:         # e.g. out of memory for the eager temporaries: report, do not fail the bench line
+                eager = {'unavailable': str(ex)[:200]}
         line = {
             'metric': 'sampled CDR residues/sec', 'value': value, 'unit': 'residues/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -316,15 +420,31 @@ def run_ours(args, cfg, rank, world, local_rank):
             'config': {'workload': workload_name(cfg), 'B_per_gpu': B, 'L': L, 'n_gen': n_gen, 'T': T_STEPS, 'layers': NUM_LAYERS,
                        'flavour': cfg['flavour'], 'rng': 'philox (in-kernel)', 'weights': 'seeded random init',
                        'l2': 'inputs larger than L2 (pair_feat %.2f GB per GPU)' % (B * L * L * 64 * 4 / 1e9),
-                       'value_includes': 'init noise, 100 reverse steps, trajectory D2H, final gather (N>1)',
+                       'value_includes': 'init noise, 100 reverse steps, 101-frame trajectory D2H, final packed gather (N>1)',
                        'init_calls_before_warmup': 2,
-                       'e2e_result': 'traj[0] and traj[T] (v, p, s) read back; full trajectory not copied'},
+                       'e2e_job': 'abopt_design_host: atoms (pinned host) -> residue + pair featurisation + frames + 100 reverse steps '
+                                  '-> whole 101-frame trajectory in host memory (models/diffab.py:115-141)'},
             'clocks': clk,
             'e2e': {'value': e2e_value, 'unit': 'residues/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': float(dt.item()) * 1e3},
             'gpu_launches': int(launches),
-            'roofline': roof, 'cpu_baseline': cpu, 'kernel_breakdown_ms_per_sample': breakdown,
+            'roofline': roof, 'cpu_baseline': cpu, 'gpu_eager_baseline': eager, 'featurisation': feat_line,
+            'kernel_breakdown_ms_per_sample': breakdown,
         }
+    if world == 8 and args.config == 'c2' and not args.no_c4:
+        # BASELINE config 4 as configured: B=256, L=320 sharded 32 per GPU over the 8 GPUs, six generated segments, one gather
+        c4 = CONFIGS['c4']
+        del model
+        torch.cuda.empty_cache()
+        ms4, _, _, _, inp4, _, _, _ = timed_config(c4, dev, rank, world, steps=2, warmup=1, init_calls=1)
+        if rank == 0:
+            ng4 = int(inp4['mask_generate'][0].sum())
+            peak, _ = measured_peak_gbs()
+            whole4 = c4['B'] * NUM_LAYERS * T_STEPS * algorithmic_bytes_per_complex_layer(c4['L']) / (ms4 * 1e-3) / 1e9
+            line['c4'] = {'workload': workload_name(c4) + f', {world} GPUs (B={world * c4["B"]} in total)', 'ms_per_step': ms4,
+                          'value': world * c4['B'] * ng4 / (ms4 / 1e3), 'unit': 'residues/s', 'steps': 2, 'warmup': 1,
+                          'whole_step_achieved_per_gpu': whole4, 'whole_step_frac': whole4 / peak}
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -436,6 +556,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='c2', choices=sorted(CONFIGS) + ['c5', 'f1'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-gpu-eager', action='store_true', help='skip the eager-PyTorch-on-GPU baseline leg')
+    ap.add_argument('--no-c4', action='store_true', help='at 8 GPUs: skip the additional C4 record')
     args = ap.parse_args()
     if args.config == 'c5':
         if not torch.cuda.is_available():

@@ -122,6 +122,11 @@ int abopt_model_set_tensor(abopt_model* m, const char* key, const void* data, si
                            int dtype, int on_device);
 /* Verify that every tensor is present and build the packed device layout. */
 int abopt_model_finalize(abopt_model* m);
+/* Batch sharding (the reference has no counterpart -- it runs one process on one device): index of this
+ * handle's first complex inside the global, unsharded batch.  The in-kernel Philox counters are keyed by the GLOBAL residue
+ * row, so N ranks that each run their contiguous slice (same seed, offset = first complex of the slice) reproduce the
+ * single-device run of the whole batch bit for bit.  Default 0. */
+int abopt_model_set_batch_offset(abopt_model* m, int64_t first_complex);
 
 /* ------------------------------------------------------------------ encoder (device pointers) */
 /* GABlock.forward, modules/encoders/ga.py:149-178.
@@ -296,6 +301,27 @@ int abopt_pairwise_rmsd(int B, int M, const float* structures, float* rmsd, floa
 /* rank_commoness, design_for_testset.py:573-589: rank (k,) i64 = indices of the k smallest scores, best first (ties: lower index
  * first); score (B,) scratch/out. */
 int abopt_rank_commoness(int B, int M, const float* structures, int k, float* score, int64_t* rank, void* stream);
+
+/* ------------------------------------------------------------------ encode + sample: atoms in, structures out
+ * DiffusionAntibodyDesign.sample (models/diffab.py:115-141) / .optimize (:143-171; opt_step > 0): encode() -- context_mask =
+ * mask_heavyatom[:, :, CA] & ~generate_flag (:46-50), ResidueEmbedding and PairEmbedding with structure_mask / sequence_mask =
+ * context_mask where sample_structure / sample_sequence (:52-76,133-137), R_0 = construct_3d_basis(CA, C, N), p_0 = CA (:78-84),
+ * v_0 = rotation_to_so3vec(R_0), s_0 = aa (:138-139) -- then FullDPM.sample / optimize, as ONE device-resident call: res_feat
+ * and pair_feat (1.07 GB at N=64, L=256) are produced and consumed on the device.  Inputs are the reference's batch fields:
+ *   aa, res_nb, chain_nb, fragment_type (N,L) i64; pos_heavyatom (N,L,num_atoms_in,3) f32 Angstrom; mask_heavyatom
+ *   (N,L,num_atoms_in) u8; generate_flag, mask (N,L) u8.  pe / re: finalised embedding handles of the same device.
+ * Trajectory outputs, flags, opt_step, seed as abopt_sample_device (Philox mode).  _device: DEVICE pointers, enqueues on `stream`;
+ * _host: HOST pointers, the call design_pdb.py / dock_pdb.py make per batch (about 3 MB in; the trajectory out). */
+int abopt_design_device(abopt_model* m, abopt_pair_embed* pe, abopt_res_embed* re, int N, int L, int num_atoms_in,
+                        const int64_t* aa, const int64_t* res_nb, const int64_t* chain_nb, const float* pos_heavyatom,
+                        const uint8_t* mask_heavyatom, const int64_t* fragment_type, const uint8_t* generate_flag,
+                        const uint8_t* mask, uint32_t flags, int opt_step, uint64_t seed, float* traj_v, float* traj_p,
+                        int64_t* traj_s, float* traj_prmsd, float* traj_ppl, void* stream);
+int abopt_design_host(abopt_model* m, abopt_pair_embed* pe, abopt_res_embed* re, int N, int L, int num_atoms_in,
+                      const int64_t* aa, const int64_t* res_nb, const int64_t* chain_nb, const float* pos_heavyatom,
+                      const uint8_t* mask_heavyatom, const int64_t* fragment_type, const uint8_t* generate_flag,
+                      const uint8_t* mask, uint32_t flags, int opt_step, uint64_t seed, float* traj_v, float* traj_p,
+                      int64_t* traj_s, float* traj_prmsd, float* traj_ppl);
 
 /* Size in bytes of the device scratch the model holds for (N, L); 0 if none allocated yet. */
 size_t abopt_workspace_bytes(const abopt_model* m);

@@ -67,7 +67,7 @@ def eps_net(W, v_t, p_t, s_t, res_feat, pair_feat, beta, mask_generate, mask_res
 
 def prmsd_score(logits, dist_min=0.5, dist_max=19.5):
     """pRMSDCa.compute_prmsd.  common/prmsd.py:31-47."""
-    bounds = torch.linspace(dist_min, dist_max, logits.shape[-1], dtype=logits.dtype)
+    bounds = torch.linspace(dist_min, dist_max, logits.shape[-1], dtype=logits.dtype, device=logits.device)
     return (torch.softmax(logits, -1) * bounds).sum(-1)
 
 

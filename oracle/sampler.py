@@ -28,7 +28,7 @@ def reverse_step(W, t, v_t, p_t, s_t, res_feat, pair_feat, mask_generate, mask_r
     N, L = mask_res.shape
     dt = v_t.dtype
     beta = W['trans_pos.var_sched.betas'].to(dt)[t].expand(N)
-    tt = torch.full((N,), t, dtype=torch.long)
+    tt = torch.full((N,), t, dtype=torch.long, device=v_t.device)
     net = eps_net(W, v_t, p_t, s_t, res_feat, pair_feat, beta, mask_generate, mask_res, materialize)
     v_net, R_net, p_pred, c_den = net[:4]
     eps_p = T.pos_pred_noise_from_start(W, p_t, p_pred, mask_generate, tt) if obj == 'pred_x0' else p_pred
@@ -69,7 +69,7 @@ def sample(W, v, p, s, res_feat, pair_feat, mask_generate, mask_res, num_steps=1
         s_init = torch.where(mask_generate, nz['s_rand'], s) if sample_sequence else s
     else:                                                                       # optimize(): :321-337
         T0 = start_step
-        tt = torch.full((N,), T0, dtype=torch.long)
+        tt = torch.full((N,), T0, dtype=torch.long, device=v.device)
         nz = tape['init'] if tape is not None else T.draw_step_noise(N, L, gen, dtype=dt)
         if sample_structure:
             v_noisy, _ = T.rot_add_noise(W, v, mask_generate, tt, nz)

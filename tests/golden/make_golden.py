@@ -169,6 +169,69 @@ def make_post_loop():
         avg_rmsd=fn['calc_avg_rmsd'](S), rank=fn['rank_commoness'](S, 5))
 
 
+TRAINED_CKPT = 'AbDock/reproduction/dock_single_cdr/250000.pt'
+
+
+@torch.no_grad()
+def make_trained_slice():
+    """A slice of a TRAINED checkpoint of the reference (dock_single_cdr/250000.pt: GABlocks 0-1, the input mixer and the four
+    heads of its EpsilonNet, fp32, a few MB) together with what the unmodified reference computes with it: res_feat / pair_feat
+    of a synthetic complex through the checkpoint's own residue_embed / pair_embed, then GABlock taps and EpsilonNet.forward of a
+    2-layer reference model carrying the slice (parity at trained activation scales, not random-init ones).
+    The GPU test loads the same slice into ab_opt_b200.FullDPM (tests/test_gpu_fullsize.py)."""
+    torch.set_num_threads(1)
+    from test_oracle_vs_reference import _load_ckpt_state
+    ref_root = os.environ.get('ABOPT_REFERENCE', '/root/reference')
+    if os.path.join(ref_root, 'AbDock') not in sys.path:
+        sys.path.insert(0, os.path.join(ref_root, 'AbDock'))
+    path = os.path.join(ref_root, TRAINED_CKPT)
+    _load_ckpt_state(path)                                  # installs the unpickling stubs
+    ck = torch.load(path, map_location='cpu', weights_only=False)['model']
+    from src.modules.encoders.pair import PairEmbedding
+    from src.modules.encoders.residue import ResidueEmbedding
+    from oracle import pair_embed as PE
+    N, L, nl, seed_in = 2, 48, 2, 61
+    cx = PE.synthetic_complex(seed_in, N, L)
+    pe, re_ = PairEmbedding(64, 15), ResidueEmbedding(128, 15)
+    pe.load_state_dict({k[len('pair_embed.'):]: v for k, v in ck.items() if k.startswith('pair_embed.')}, strict=True)
+    re_.load_state_dict({k[len('residue_embed.'):]: v for k, v in ck.items() if k.startswith('residue_embed.')}, strict=True)
+    ft = torch.randint(1, 4, (N, L), generator=torch.Generator().manual_seed(seed_in))
+    a = (cx['aa'], cx['res_nb'], cx['chain_nb'], cx['pos_atoms'], cx['mask_atoms'])
+    ctx = cx['context_mask']
+    res_feat = re_.eval()(*a, ft, structure_mask=ctx, sequence_mask=ctx)
+    pair_feat = pe.eval()(*a, structure_mask=ctx, sequence_mask=ctx)
+    mask_res = cx['mask_atoms'][:, :, 1]
+    mask_gen = (~ctx) & mask_res
+    # the slice: everything of `diffusion.eps_net` except blocks >= nl (+ the diffusion buffers, regenerated by the oracle)
+    W = weights.make_state_dict(seed=0, num_layers=nl, flavour='abdock')
+    sl = {}
+    for k in W:
+        if k.startswith('eps_net.'):
+            sl[k] = ck['diffusion.' + k].float().contiguous()
+            assert sl[k].shape == W[k].shape, k
+    W.update(sl)
+    model, m = build_reference_fulldpm(W, num_layers=nl, obj='pred_x0')
+    g = torch.Generator().manual_seed(7)
+    from oracle.geometry import uniform_so3_from_gauss4
+    v = uniform_so3_from_gauss4(torch.randn(N, L, 4, generator=g))
+    p = cx['pos_atoms'][:, :, 1] - cx['pos_atoms'][:, :, 1][mask_res].mean(0)          # CA, roughly centred, Angstrom
+    s = cx['aa'].clamp(max=19)
+    s = torch.where(mask_res, s, torch.full_like(s, 21))
+    R, tpos = m['so3'].so3vec_to_rotation(v), p / 10.0
+    blk = model.eps_net.encoder.blocks[0]
+    logits = blk._node_logits(res_feat) + blk._pair_logits(pair_feat) + blk._spatial_logits(R, tpos, res_feat)
+    alpha = m['ga']._alpha_from_logits(logits * np.sqrt(1 / 3), mask_res)
+    feat = torch.cat([blk._pair_aggregation(alpha, pair_feat), blk._node_aggregation(alpha, res_feat),
+                      blk._spatial_aggregation(alpha, R, tpos, res_feat)], -1)
+    tstep = 35
+    beta = W['trans_pos.var_sched.betas'][tstep].expand(N)
+    out = model.eps_net(v, tpos, s, res_feat, pair_feat, beta, mask_gen, mask_res)
+    npz('trained_slice.npz', N=N, L=L, num_layers=nl, t=tstep, ckpt=TRAINED_CKPT, v=v, p=p, s=s, res_feat=res_feat, pair_feat=pair_feat,
+        mask_generate=mask_gen, mask_res=mask_res, alpha=alpha, feat=feat, x_out=blk(R, tpos, res_feat, pair_feat, mask_res),
+        enc_out=model.eps_net.encoder(R, tpos, res_feat, pair_feat, mask_res), v_next=out[0], R_next=out[1], eps_pos=out[2],
+        c_denoised=out[3], prmsd_logits=out[4], **{'W.' + k: v_ for k, v_ in sl.items()})
+
+
 @torch.no_grad()
 def main():
     torch.set_num_threads(1)          # single-thread reference: reproducible reduction order
@@ -255,9 +318,12 @@ if __name__ == '__main__':
         make_post_loop()
     elif len(sys.argv) > 1 and sys.argv[1] == 'train_backward':
         make_train_backward()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'trained_slice':
+        make_trained_slice()
     else:
         main()
         make_train_forward()
         make_pair_embed()
         make_post_loop()
         make_train_backward()
+        make_trained_slice()

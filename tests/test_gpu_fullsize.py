@@ -1,0 +1,338 @@
+"""GPU parity at the BENCHMARKED shapes (BASELINE.json configs 2-5): the persistent kernels walk ~10 tiles per CTA there, which
+the small-shape tests of test_gpu_parity.py never do.  Three kinds of evidence, all through the C ABI:
+
+  (i)   independence -- complex k computed alone gives the SAME BITS as complex k inside the full batch (k = first, middle,
+        last): tile walks, ring phase wraps, TMEM double buffering and per-warp row strides cannot leak between tiles;
+  (ii)  the same complexes against the CPU oracle, arbitrated by its fp64 evaluation (err_cuda <= 2 err_oracle_fp32 + floor);
+  (iii) trained weights (a slice of dock_single_cdr/250000.pt, fixture written by the unmodified reference) and a
+        replayed-noise optimize() run against oracle.sampler.
+
+Run on the B200 box:  pytest tests -m gpu
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ab_opt_b200
+from oracle import weights, ipa, epsnet, sampler, transitions as T, geometry as G
+from test_gpu_parity import assert_vs_fp64, build_model, cu, to64, DEV
+from test_oracle_golden import trained_slice
+
+pytestmark = pytest.mark.gpu
+
+SIX = ((20, 30), (50, 60), (95, 105), (160, 170), (190, 200), (230, 240))
+CONFIGS = {      # bench.py CONFIGS / SURVEY.md 8d
+    'c2': dict(B=64, L=256, gen=((120, 136),), flavour='abdesign', obj='pred_noise', structure=True, sequence=True),
+    'c3': dict(B=64, L=256, gen=((120, 136),), flavour='abdock', obj='pred_x0', structure=True, sequence=False),
+    'c4': dict(B=32, L=320, gen=SIX, flavour='abdesign', obj='pred_noise', structure=True, sequence=True),
+}
+LAYERS = 6
+
+
+def device_batch(cfg, seed, ragged_tail=True):
+    """Seeded synthetic batch on the device.  The last complex is ragged (padding tail) so that the key mask
+    and the masked-row paths run at full size as well."""
+    B, L = cfg['B'], cfg['L']
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=g, device=DEV)
+    v = G.uniform_so3_from_gauss4(rn(B, L, 4).cpu()).to(DEV)
+    mask_generate = torch.zeros(B, L, dtype=torch.bool, device=DEV)
+    for a, b in cfg['gen']:
+        mask_generate[:, a:b] = True
+    mask_res = torch.ones(B, L, dtype=torch.bool, device=DEV)
+    s = torch.randint(0, 20, (B, L), generator=g, device=DEV)
+    if ragged_tail:
+        mask_res[-1, L - 9:] = False
+        s[-1, L - 9:] = 21
+        mask_generate &= mask_res
+    return dict(v=v.contiguous(), p=rn(B, L, 3) * 10.0, s=s, res_feat=rn(B, L, 128), pair_feat=rn(B, L, L, 64),
+                mask_generate=mask_generate, mask_res=mask_res)
+
+
+def pick(d, k):
+    return {n: t[k:k + 1].contiguous() for n, t in d.items()}
+
+
+def noise_rows(nz, k, L):
+    out = {}
+    for n, t in nz.items():
+        out[n] = (t[k:k + 1] if t.dim() == 3 else t[k * L:(k + 1) * L]).contiguous()
+    return out
+
+
+def device_step_noise(N, L, seed):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    M = N * L
+    return dict(u=torch.randn(N, L, 3, generator=g, device=DEV), expo_ang=torch.empty(M, 8191, device=DEV).exponential_(1, generator=g),
+                unif_ang=torch.rand(M, generator=g, device=DEV), gauss_ang=torch.randn(M, generator=g, device=DEV),
+                z_pos=torch.randn(N, L, 3, generator=g, device=DEV), expo_seq=torch.empty(M, 20, device=DEV).exponential_(1, generator=g))
+
+
+def cpu(d):
+    return {k: v.cpu() for k, v in d.items()}
+
+
+@pytest.fixture(scope='module')
+def models():
+    cache = {}
+
+    def get(flavour, obj):
+        if (flavour, obj) not in cache:
+            W = weights.make_state_dict(seed=29, num_layers=LAYERS, flavour=flavour)
+            cache[(flavour, obj)] = (W, build_model(W, LAYERS, flavour=flavour, obj=obj))
+        return cache[(flavour, obj)]
+    return get
+
+
+@pytest.fixture(autouse=True)
+def _restore_focus_env():
+    old = os.environ.get('ABOPT_NO_FOCUS')
+    yield
+    if old is None:
+        os.environ.pop('ABOPT_NO_FOCUS', None)
+    else:
+        os.environ['ABOPT_NO_FOCUS'] = old
+
+
+def ks_of(B):
+    return (0, B // 2 - 1, B - 1)
+
+
+# ------------------------------------------------------------------------------------------ (i) + (ii): one GABlock
+@pytest.mark.parametrize('name,layer', [('c2', 0), ('c2', 5), ('c4', 3)])
+def test_block_taps_full_batch(models, name, layer):
+    """alpha (N,L,L,12) and the 1824-wide aggregate of one GABlock over the FULL batch: ~10 tiles per CTA in the logits /
+    aggregation kernels, ~9 query rows per warp in pair_stream_kernel."""
+    cfg = CONFIGS[name]
+    W, model = models(cfg['flavour'], cfg['obj'])
+    d = device_batch(cfg, 300 + layer)
+    B, L = cfg['B'], cfg['L']
+    R, t = G.so3_exp(d['v'].cpu()).to(DEV), d['p'] / 10.0
+    enc = model.eps_net.encoder
+    alpha, feat = enc.block_taps(layer, R, t, d['res_feat'], d['pair_feat'], d['mask_res'])
+    out = enc.blocks[layer](R, t, d['res_feat'], d['pair_feat'], d['mask_res'])
+    assert torch.isfinite(alpha).all() and torch.isfinite(feat).all() and torch.isfinite(out).all()
+    pre = f'eps_net.encoder.blocks.{layer}.'
+    W64 = weights.cast(W, torch.double)
+    for k in ks_of(B):
+        a1, f1 = enc.block_taps(layer, R[k:k + 1].contiguous(), t[k:k + 1].contiguous(), d['res_feat'][k:k + 1].contiguous(),
+                                d['pair_feat'][k:k + 1].contiguous(), d['mask_res'][k:k + 1].contiguous())
+        o1 = enc.blocks[layer](R[k:k + 1].contiguous(), t[k:k + 1].contiguous(), d['res_feat'][k:k + 1].contiguous(),
+                               d['pair_feat'][k:k + 1].contiguous(), d['mask_res'][k:k + 1].contiguous())
+        assert torch.equal(a1[0], alpha[k]), f'alpha of complex {k} depends on the batch it is computed in'
+        mr = d['mask_res'][k]
+        assert torch.equal(f1[0][mr], feat[k][mr]), f'aggregate of complex {k} depends on the batch'
+        assert torch.equal(o1[0], out[k]), f'block output of complex {k} depends on the batch'
+        c = cpu(pick(d, k))
+        Rk, tk = G.so3_exp(c['v']), c['p'] / 10.0
+        o32, p32 = ipa.ga_block(W, pre, Rk, tk, c['res_feat'], c['pair_feat'], c['mask_res'], materialize=False, return_parts=True)
+        c64 = to64(c)
+        o64, p64 = ipa.ga_block(W64, pre, G.so3_exp(c64['v']), c64['p'] / 10.0, c64['res_feat'], c64['pair_feat'], c64['mask_res'],
+                                materialize=False, return_parts=True)
+        assert_vs_fp64(f'alpha[{k}]', alpha[k:k + 1], p32['alpha'], p64['alpha'], 5e-6)
+        m = c['mask_res']
+        fg, f32, f64 = feat[k:k + 1].cpu()[m], p32['feat'][m], p64['feat'][m]
+        assert_vs_fp64(f'feat[{k}]', fg[:, :1536], f32[:, :1536], f64[:, :1536], 3e-5)
+        assert_vs_fp64(f'feat.dir[{k}]', fg[:, 1536:], f32[:, 1536:], f64[:, 1536:], 2e-4)
+        assert_vs_fp64(f'x_out[{k}]', out[k:k + 1], o32, o64, 3e-5)
+        a = alpha[k].cpu()
+        torch.testing.assert_close(a[m[0]].sum(1), torch.ones_like(a[m[0]].sum(1)), rtol=0, atol=1e-5)
+        if (~m).any():
+            assert a[~m[0]].abs().max() == 0 and a.transpose(0, 1)[~m[0]].abs().max() == 0
+
+
+# ------------------------------------------------------------------------------------------ (i) + (ii): EpsilonNet, 6 layers
+@pytest.mark.parametrize('name', ['c2', 'c3', 'c4'])
+def test_eps_net_full_batch(models, name):
+    cfg = CONFIGS[name]
+    W, model = models(cfg['flavour'], cfg['obj'])
+    d = device_batch(cfg, 400)
+    B, L = cfg['B'], cfg['L']
+    tsteps = torch.randint(1, 100, (B,), generator=torch.Generator().manual_seed(4))
+    beta = W['trans_pos.var_sched.betas'][tsteps].contiguous()
+    a = lambda x, bt: (x['v'], x['p'] / 10.0, x['s'], x['res_feat'], x['pair_feat'], bt, x['mask_generate'], x['mask_res'])
+    got = model.eps_net(*a(d, beta.to(DEV)))
+    W64 = weights.cast(W, torch.double)
+    floors = (None, 5e-6, 5e-6, 5e-7, 5e-6)
+    for k in ks_of(B):
+        alone = model.eps_net(*a(pick(d, k), beta[k:k + 1].to(DEV)))
+        for i in range(len(got)):
+            assert torch.equal(alone[i][0], got[i][k]), f'output {i} of complex {k} depends on the batch'
+        c = cpu(pick(d, k))
+        o32 = epsnet.eps_net(W, *a(c, beta[k:k + 1]), materialize=False)
+        o64 = epsnet.eps_net(W64, *a(to64(c), beta[k:k + 1].double()), materialize=False)
+        for i in range(1, len(got)):
+            assert_vs_fp64(f'{name} out{i}[{k}]', got[i][k:k + 1], o32[i], o64[i], floors[i])
+
+
+# ------------------------------------------------------------------------------------------ one reverse step, replayed noise
+@pytest.mark.parametrize('name,no_focus', [('c2', False), ('c2', True), ('c3', False), ('c4', False)])
+def test_reverse_step_full_batch(models, name, no_focus):
+    """One iteration of the sampling loop at the benchmarked shape (focus mode on and off for C2): independence bit for bit,
+    then positions 1e-4 relative, rotations arbitrated by the fp64 oracle, sampled amino-acid indices BIT-EXACT."""
+    cfg = CONFIGS[name]
+    os.environ['ABOPT_NO_FOCUS'] = '1' if no_focus else '0'
+    W, model = models(cfg['flavour'], cfg['obj'])
+    d = device_batch(cfg, 500)
+    B, L = cfg['B'], cfg['L']
+    t = 61
+    nz = device_step_noise(B, L, 77)
+    kw = dict(sample_structure=cfg['structure'], sample_sequence=cfg['sequence'])
+    run = lambda x, n: model.reverse_step(t, x['v'], x['p'], x['s'], x['res_feat'], x['pair_feat'], x['mask_generate'], x['mask_res'],
+                                          noise=n, **kw)
+    got = run(d, nz)
+    assert all(torch.isfinite(x).all() for x in got if x.is_floating_point())
+    keep = ~d['mask_generate']
+    assert torch.equal(got[0][keep], d['v'][keep]) and torch.equal(got[1][keep], d['p'][keep])
+    W64 = weights.cast(W, torch.double)
+    for k in ks_of(B):
+        alone = run(pick(d, k), noise_rows(nz, k, L))
+        for i in range(len(got)):
+            assert torch.equal(alone[i][0], got[i][k]), f'{name}: output {i} of complex {k} depends on the batch (focus off={no_focus})'
+        c, cn = cpu(pick(d, k)), cpu(noise_rows(nz, k, L))
+        ref = sampler.reverse_step(W, t, c['v'], c['p'] / 10.0, c['s'], c['res_feat'], c['pair_feat'], c['mask_generate'], c['mask_res'],
+                                   cn, obj=cfg['obj'], materialize=False)
+        c64 = to64(c)
+        ref64 = sampler.reverse_step(W64, t, c64['v'], c64['p'] / 10.0, c64['s'], c64['res_feat'], c64['pair_feat'], c64['mask_generate'],
+                                     c64['mask_res'], to64(cn), obj=cfg['obj'], materialize=False)
+        v_o, p_o, s_o = got[0][k:k + 1].cpu(), got[1][k:k + 1].cpu(), got[2][k:k + 1].cpu()
+        live = c['mask_res']
+        torch.testing.assert_close(p_o[live], (ref['p_next'] * 10.0)[live], rtol=1e-4, atol=2e-4)
+        R64 = G.so3_exp(ref64['v_next'])
+        e_cuda = (G.so3_exp(v_o.double()) - R64).abs().amax(dim=(-1, -2))
+        e_o32 = (G.so3_exp(ref['v_next'].double()) - R64).abs().amax(dim=(-1, -2))
+        gap = (np.pi - ref64['v_next'].norm(dim=-1)).clamp_min(1e-9)
+        ok = live & (gap > 0.05) & (e_o32 < 1e-3)
+        bad = ok & (e_cuda > 4 * e_o32 + 3e-5 + 3e-6 / gap ** 2)
+        assert ok[c['mask_generate']].float().mean() > 0.7
+        assert not bad.any(), f'{name} v_next[{k}]: cuda {e_cuda[bad].max().item():.3e} oracle32 {e_o32[bad].max().item():.3e}'
+        if cfg['sequence']:
+            assert torch.equal(s_o[live], ref['s_next'][live]), f'{name}: sampled amino acids of complex {k} differ from the oracle'
+        else:
+            assert torch.equal(s_o, c['s'])
+        if cfg['flavour'] == 'abdock':
+            torch.testing.assert_close(got[3][k:k + 1].cpu(), ref['prmsd'], rtol=1e-4, atol=2e-4)
+
+
+# ------------------------------------------------------------------------------------------ sampling loop properties at C2
+def test_sample_loop_c2_sharded_equals_whole():
+    """Philox mode at B=64, L=256, 6 layers, 4 steps of optimize(): deterministic for a seed, context untouched, and a slice of
+    the batch run on its own with batch_offset reproduces the whole-batch run BIT FOR BIT (what the N-rank run relies on)."""
+    cfg = CONFIGS['c2']
+    W = weights.make_state_dict(seed=29, num_layers=LAYERS, flavour='abdesign')
+    model = build_model(W, LAYERS, flavour='abdesign', obj='pred_noise')
+    d = device_batch(cfg, 600)
+    a = lambda x: (x['v'], x['p'], x['s'], 4, x['res_feat'], x['pair_feat'], x['mask_generate'], x['mask_res'])
+    whole = model.optimize(*a(d), seed=1234)
+    again = model.optimize(*a(d), seed=1234)
+    other = model.optimize(*a(d), seed=1235)
+    for i in range(3):
+        assert torch.equal(whole[0][i], again[0][i]) and torch.equal(whole[2][i], again[2][i].to(whole[2][i].device))
+    assert not torch.equal(whole[0][1], other[0][1])
+    keep = ~d['mask_generate']
+    assert torch.equal(whole[0][0][keep], d['v'][keep]) and torch.equal(whole[0][2][keep & d['mask_res']], d['s'][keep & d['mask_res']])
+    lo, hi = 40, 56                                      # "rank 5 of 8" in a contiguous split of 64... any slice will do
+    part = {n: t[lo:hi].contiguous() for n, t in d.items()}
+    sl = model.optimize(*a(part), seed=1234, batch_offset=lo, batch_total=cfg['B'])
+    for t_ in (4, 2, 0):
+        for i in range(3):
+            assert torch.equal(sl[t_][i].cpu(), whole[t_][i][lo:hi].cpu()), f'slice differs from the whole batch at t={t_}, field {i}'
+
+
+def test_optimize_replayed_noise_matches_oracle():
+    """FullDPM.optimize(opt_step=3) in parity mode (rng='torch'): the same CUDA draws replayed through oracle.sampler.sample
+    (start_step=3) reproduce the noised start and the three reverse steps (dpm_full.py:304-367)."""
+    W = weights.make_state_dict(seed=11, num_layers=2, flavour='abdock')
+    model = build_model(W, 2)
+    inp = weights.synthetic_inputs(21, 2, 40, gen_slices=((8, 18),), ragged=True)
+    N, L, T0 = 2, 40, 3
+    M = N * L
+    ci = cu(inp)
+    torch.manual_seed(321)
+    traj = model.optimize(ci['v'], ci['p'], ci['s'], T0, ci['res_feat'], ci['pair_feat'], ci['mask_generate'], ci['mask_res'], rng='torch')
+    torch.manual_seed(321)
+
+    def draws():      # the reference's order: so3.py:143,123,126,131 ; transition.py:74/95 ; transition.py:199/179
+        return {'u': torch.randn(N, L, 3, device=DEV).cpu(), 'expo_ang': torch.empty(M, 8191, device=DEV).exponential_(1).cpu(),
+                'unif_ang': torch.rand(M, device=DEV).cpu(), 'gauss_ang': torch.randn(M, device=DEV).cpu(),
+                'z_pos': torch.randn(N, L, 3, device=DEV).cpu(), 'expo_seq': torch.empty(M, 20, device=DEV).exponential_(1).cpu()}
+    tape = {'init': draws()}
+    for t in range(T0, 0, -1):
+        tape[t] = draws()
+    ref = sampler.sample(W, inp['v'], inp['p'], inp['s'], inp['res_feat'], inp['pair_feat'], inp['mask_generate'], inp['mask_res'],
+                         obj='pred_x0', tape=tape, materialize=False, start_step=T0)
+    assert sorted(traj) == [0, 1, 2, 3] and isinstance(traj[2], tuple)
+    live = inp['mask_res']
+    for t in (3, 2, 1, 0):
+        assert torch.equal(traj[t][2].cpu()[live], ref[t][2][live]), f'sequence differs at t={t}'
+        torch.testing.assert_close(traj[t][1].cpu()[live], ref[t][1][live], rtol=1e-4, atol=2e-3)
+        gap = (np.pi - ref[t][0].norm(dim=-1)).clamp_min(1e-9)
+        err = (G.so3_exp(traj[t][0].cpu()) - G.so3_exp(ref[t][0])).abs().amax(dim=(-1, -2))
+        assert not (live & (gap > 0.1) & (err > 2e-4 + 1e-5 / gap ** 2)).any(), f'rotations differ at t={t}'
+    torch.testing.assert_close(traj[2][3].cpu(), ref[2][3], rtol=1e-4, atol=1e-4)       # pRMSD
+    torch.testing.assert_close(traj[2][4].cpu(), ref[2][4], rtol=1e-4, atol=1e-5)       # perplexity (no mask in optimize)
+
+
+# ------------------------------------------------------------------------------------------ (iii) trained weights
+def test_trained_checkpoint_slice(golden_dir):
+    """Blocks 0-1, mixer and heads of the reference's dock_single_cdr/250000.pt on features produced by the checkpoint's own
+    embeddings: the 3xTF32 tensor-core path at trained activation scales, against what the UNMODIFIED reference computed."""
+    W, g = trained_slice(golden_dir)
+    model = build_model(W, g['num_layers'])
+    N, L = g['N'], g['L']
+    d = cu({k: g[k] for k in ('v', 'p', 's', 'res_feat', 'pair_feat', 'mask_generate', 'mask_res')})
+    R, t = G.so3_exp(g['v']).to(DEV), d['p'] / 10.0
+    enc = model.eps_net.encoder
+    alpha, feat = enc.block_taps(0, R, t, d['res_feat'], d['pair_feat'], d['mask_res'])
+    torch.testing.assert_close(alpha.cpu(), g['alpha'], rtol=1e-4, atol=2e-6)
+    mr = g['mask_res']
+    torch.testing.assert_close(feat.cpu()[mr][:, :1536], g['feat'][mr][:, :1536], rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(enc.blocks[0](R, t, d['res_feat'], d['pair_feat'], d['mask_res']).cpu(), g['x_out'], rtol=1e-4, atol=5e-5)
+    torch.testing.assert_close(enc(R, t, d['res_feat'], d['pair_feat'], d['mask_res']).cpu(), g['enc_out'], rtol=1e-4, atol=5e-5)
+    beta = W['trans_pos.var_sched.betas'][g['t']].expand(N).contiguous()
+    got = model.eps_net(d['v'], t, d['s'], d['res_feat'], d['pair_feat'], beta.to(DEV), d['mask_generate'], d['mask_res'])
+    W64 = weights.cast(W, torch.double)
+    g64 = to64({k: g[k] for k in ('v', 'p', 's', 'res_feat', 'pair_feat', 'mask_generate', 'mask_res')})
+    o64 = epsnet.eps_net(W64, g64['v'], g64['p'] / 10.0, g64['s'], g64['res_feat'], g64['pair_feat'], beta.double(), g64['mask_generate'],
+                         g64['mask_res'], materialize=False)
+    for i, (key, floor) in enumerate((('v_next', None), ('R_next', 5e-6), ('eps_pos', 2e-6), ('c_denoised', 5e-7), ('prmsd_logits', 1e-5))):
+        if floor is None:
+            continue
+        assert_vs_fp64(key, got[i], g[key], o64[i], floor)             # "ref32" here IS the unmodified reference's fp32 result
+
+
+# ------------------------------------------------------------------------------------------ training forward at C5 size
+def test_training_forward_c5_is_the_mean_of_its_halves():
+    """FullDPM.forward at B=128, L=256, 6 layers: every loss is a masked mean with the same number of generated residues per
+    complex, so the loss of the batch equals the mean of the losses of its two halves (a size-independent property), and a
+    two-complex slice agrees with the oracle."""
+    from oracle import training
+    cfg = dict(B=128, L=256, gen=((120, 136),))
+    W = weights.make_state_dict(seed=29, num_layers=LAYERS, flavour='abdesign')
+    model = build_model(W, LAYERS, flavour='abdesign', obj='pred_noise')
+    d = device_batch(cfg, 700, ragged_tail=False)
+    B, L = cfg['B'], cfg['L']
+    t = torch.randint(1, 100, (B,), generator=torch.Generator().manual_seed(8)).to(DEV)
+    nz = device_step_noise(B, L, 88)
+    f = lambda x, tt, n: model(x['v'], x['p'], x['s'], x['res_feat'], x['pair_feat'], x['mask_generate'], x['mask_res'], True, True,
+                               t=tt, noise=n)
+    whole = f(d, t, nz)
+    h = B // 2
+    halves = []
+    for lo in (0, h):
+        part = {n: x[lo:lo + h].contiguous() for n, x in d.items()}
+        pn = {n: (x[lo:lo + h] if x.dim() == 3 else x[lo * L:(lo + h) * L]).contiguous() for n, x in nz.items()}
+        halves.append(f(part, t[lo:lo + h].contiguous(), pn))
+    for k in whole:
+        want = 0.5 * (halves[0][k].double() + halves[1][k].double())
+        torch.testing.assert_close(whole[k].double(), want, rtol=2e-5, atol=1e-6, msg=lambda m, k=k: f'{k}: {m}')
+    two = {n: x[B - 2:].contiguous() for n, x in d.items()}
+    n2 = {n: (x[B - 2:] if x.dim() == 3 else x[(B - 2) * L:]).contiguous() for n, x in nz.items()}
+    got = f(two, t[B - 2:].contiguous(), n2)
+    c, cn = cpu(two), cpu(n2)
+    ref = training.loss_forward(W, c['v'], c['p'], c['s'], c['res_feat'], c['pair_feat'], c['mask_generate'], c['mask_res'], True, True,
+                                t[B - 2:].cpu(), cn, flavour='abdesign', obj='pred_noise')
+    for k in ref:
+        torch.testing.assert_close(got[k].cpu(), ref[k], rtol=2e-4, atol=1e-5, msg=lambda m, k=k: f'{k}: {m}')

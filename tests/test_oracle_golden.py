@@ -336,3 +336,29 @@ def test_embedding_backward_matches_reference(golden_dir):
     assert sorted(got) == sorted(want) and len(want) == 10
     for k in want:
         assert (got[k] - want[k]).abs().max() <= 2e-5 * want[k].abs().max() + 1e-12, k
+
+
+def trained_slice(golden_dir):
+    """The trained-checkpoint slice fixture -> (state dict of a 2-layer AbDock-flavour FullDPM, tensors)."""
+    g = load(golden_dir, 'trained_slice.npz')
+    W = weights.make_state_dict(seed=0, num_layers=g['num_layers'], flavour='abdock')
+    W.update({k[2:]: v for k, v in g.items() if k.startswith('W.')})
+    return W, g
+
+
+def test_trained_checkpoint_slice_matches_reference(golden_dir):
+    """The oracle with TRAINED weights (blocks 0-1, mixer and heads of dock_single_cdr/250000.pt) on res_feat / pair_feat produced
+    by the checkpoint's own embeddings, against what the unmodified reference computed."""
+    W, g = trained_slice(golden_dir)
+    R, t = G.so3_exp(g['v']), g['p'] / 10.0
+    out, parts = ipa.ga_block(W, 'eps_net.encoder.blocks.0.', R, t, g['res_feat'], g['pair_feat'], g['mask_res'],
+                              materialize=False, return_parts=True)
+    torch.testing.assert_close(parts['alpha'], g['alpha'], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(parts['feat'], g['feat'], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(out, g['x_out'], rtol=1e-4, atol=2e-5)
+    beta = W['trans_pos.var_sched.betas'][g['t']].expand(g['N'])
+    o = epsnet.eps_net(W, g['v'], t, g['s'], g['res_feat'], g['pair_feat'], beta, g['mask_generate'], g['mask_res'], materialize=False)
+    torch.testing.assert_close(o[1], g['R_next'], rtol=0, atol=2e-5)
+    torch.testing.assert_close(o[2], g['eps_pos'], rtol=1e-4, atol=5e-6)
+    torch.testing.assert_close(o[3], g['c_denoised'], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(o[4], g['prmsd_logits'], rtol=1e-4, atol=2e-5)

@@ -248,6 +248,7 @@ def test_drop_in_through_the_reference_registry():
         from test_oracle_vs_reference import _Cfg, _load_ckpt_state
         cfg = _Cfg(yaml.safe_load(open({os.path.join(REF_ROOT, 'AbDock/configs/train/dock_single.yml')!r})))
         model = get_model(cfg.model)
+        assert type(model) is ab_opt_b200.DiffusionAntibodyDesign          # the fused encode + sample class, same state-dict keys
         assert type(model.diffusion) is ab_opt_b200.FullDPM and type(model.pair_embed) is ab_opt_b200.PairEmbedding
         assert type(model.residue_embed) is ab_opt_b200.ResidueEmbedding
         assert type(model.diffusion.eps_net.encoder) is ab_opt_b200.GAEncoder

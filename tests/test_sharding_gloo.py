@@ -20,6 +20,18 @@ def test_shard_bounds_cover_the_batch():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_pack_unpack_is_bit_exact():
+    g = torch.Generator().manual_seed(1)
+    v, p = torch.randn(5, 7, 3, generator=g), torch.randn(5, 7, 3, generator=g) * 1e3
+    s = torch.randint(-2 ** 62, 2 ** 62, (5, 7), generator=g)          # int64 travels as two float32 words, bit for bit
+    packed = sharding.pack_results([v, p, s])
+    assert packed.dtype == torch.float32 and packed.shape == (5, 7 * 3 + 7 * 3 + 7 * 2)
+    v2, p2, s2 = sharding.unpack_results(packed, [v, p, s])
+    assert torch.equal(v, v2) and torch.equal(p, p2) and torch.equal(s, s2) and s2.dtype == torch.int64
+    e = sharding.unpack_results(packed[:0], [v, p, s])
+    assert e[2].shape == (0, 7)
+
+
 class _FakeDPM(torch.nn.Module):
     """Stands in for FullDPM on CPU: a per-complex deterministic 'sample' (no batch mixing, like the real loop)."""
 
@@ -27,7 +39,10 @@ class _FakeDPM(torch.nn.Module):
         super().__init__()
         self.w = torch.nn.Parameter(torch.ones(1))
 
+    calls = []
+
     def sample(self, v, p, s, res_feat, pair_feat, mask_generate, mask_res, **kw):
+        _FakeDPM.calls.append(kw)
         g = mask_generate[..., None]
         v0 = torch.where(g, v + res_feat[..., :3].tanh(), v)
         p0 = torch.where(g, p + pair_feat.mean(dim=(2, 3))[..., None], p)
@@ -47,6 +62,11 @@ def _worker(rank, world, port, n, L, ret):
     a, b = sharding.shard_bounds(n, world, rank)
     assert mine['v'].shape[0] == b - a and torch.equal(mine['s'], batch['s'][a:b])
     got = sharding.sample_sharded(model, **batch)
+    kw = _FakeDPM.calls[-1]                        # the loop call carries the shard's place in the global batch and a common seed
+    assert kw['batch_offset'] == a and kw['batch_total'] == n and isinstance(kw['seed'], int)
+    seeds = [None, None]
+    dist.all_gather_object(seeds, kw['seed'])
+    assert seeds[0] == seeds[1]
     ref = model.sample(**batch)[0]
     ok = all(torch.equal(x, y) for x, y in zip(got, ref))
     ret[rank] = bool(ok) and got[0].shape[0] == n
