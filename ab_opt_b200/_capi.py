@@ -21,7 +21,7 @@ EXPORTS = (
     'abopt_model_destroy', 'abopt_model_set_tensor', 'abopt_model_finalize', 'abopt_ga_block_forward',
     'abopt_ga_encoder_forward', 'abopt_ga_block_taps', 'abopt_eps_net_forward', 'abopt_rot_denoise',
     'abopt_pos_pred_noise_from_start', 'abopt_pos_denoise', 'abopt_seq_denoise', 'abopt_sample_device',
-    'abopt_sample_host', 'abopt_workspace_bytes', 'abopt_sample_init', 'abopt_reverse_step', 'abopt_profile_enable', 'abopt_profile_collect', 'abopt_debug_gemm3x', 'abopt_debug_clocks',
+    'abopt_sample_host', 'abopt_workspace_bytes', 'abopt_sample_init', 'abopt_reverse_step', 'abopt_profile_enable', 'abopt_profile_collect', 'abopt_debug_gemm3x', 'abopt_debug_clocks', 'abopt_debug_copy',
     'abopt_loss_forward', 'abopt_model_set_batch_offset', 'abopt_pair_embed_create', 'abopt_pair_embed_destroy', 'abopt_pair_embed_set_tensor',
     'abopt_pair_embed_finalize', 'abopt_pair_embed_forward', 'abopt_res_embed_create', 'abopt_res_embed_destroy',
     'abopt_res_embed_set_tensor', 'abopt_res_embed_finalize', 'abopt_res_embed_forward',
@@ -82,6 +82,7 @@ def lib():
         L.abopt_sample_init.argtypes = [vp, ci, ci] + [vp] * 4 + [C.c_uint32, ci, C.c_uint64, C.POINTER(InitNoise)] + [vp] * 4
         L.abopt_reverse_step.argtypes = [vp, ci, ci, ci, ci] + [vp] * 7 + [C.c_uint32, C.c_uint64, C.POINTER(StepNoise)] + [vp] * 6
         L.abopt_debug_gemm3x.argtypes = [ci, ci, ci, ci] + [vp] * 5
+        L.abopt_debug_copy.argtypes = [vp, ci, vp, C.c_size_t, C.POINTER(C.c_size_t), vp]
         L.abopt_loss_forward.argtypes = [vp, ci, ci] + [vp] * 7 + [C.c_uint32, vp, C.c_uint64, C.POINTER(StepNoise), vp, vp]
         L.abopt_sample_host.argtypes = [vp, ci, ci] + [vp] * 7 + [C.c_uint32, ci, C.c_uint64] + [vp] * 5
         L.abopt_pair_embed_create.argtypes = [ci, ci, C.POINTER(C.c_void_p)]

@@ -188,6 +188,33 @@ extern "C" int abopt_debug_clocks(long long* out16) {
   tail_debug_clocks(out16 + 10);            // slots 10..14: outT_tail_kernel CTA 0: start, phase 1 done, LN1 done, MLP done, end
   return ABOPT_OK;
 }
+// Debug hook: copy one internal workspace tensor of the LAST block call into `dst` (device memory, room for `max_floats`):
+// which = 0 QA, 1 KB, 2 rq, 3 rk, 4 VT, 5 pair bias slot 0, 6 alpha, 7 feat.  Returns the number of floats copied in *numel.
+extern "C" int abopt_debug_copy(abopt_model* m, int which, float* dst, size_t max_floats, size_t* numel, void* stream) {
+  if (!m || !dst || !numel) return fail(ABOPT_ERR_ARG, "null argument");
+  Workspace& w = m->ws;
+  if (!w.base) return fail(ABOPT_ERR_STATE, "no workspace yet");
+  const size_t M = (size_t)w.N * w.L;
+  const float* src = nullptr; size_t n = 0;
+  switch (which) {
+    case 0: src = w.op.QA; n = M * H * 64; break;
+    case 1: src = w.op.KB; n = M * H * 64; break;
+    case 2: src = w.op.rq; n = M * H; break;
+    case 3: src = w.op.rk; n = M * H; break;
+    case 4: src = w.op.VT; n = (size_t)w.N * H * 64 * w.Lp; break;
+    case 5: src = m->bias_buf; n = m->bias_slot_floats; break;
+    case 6: src = w.alpha; n = (size_t)w.NB * H * w.L * w.Lp; break;
+    case 7: src = w.feat; n = M * NFEAT; break;
+    default: return fail(ABOPT_ERR_ARG, "unknown tensor");
+  }
+  if (!src) return fail(ABOPT_ERR_STATE, "tensor not allocated");
+  if (n > max_floats) n = max_floats;
+  DeviceGuard g(m->device);
+  CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  *numel = n;
+  return ABOPT_OK;
+}
+
 extern "C" int abopt_profile_enable(int on) {
   for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   g_prof.clear();

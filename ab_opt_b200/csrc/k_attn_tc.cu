@@ -509,8 +509,6 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
         const float4 b0v = *reinterpret_cast<const float4*>(bs + (((2 * kq) ^ (te & 7)) << 4));
         const float4 b1v = *reinterpret_cast<const float4*>(bs + (((2 * kq + 1) ^ (te & 7)) << 4));
         const float bv[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bias_empty[s]);       // values are in registers: the producer may refill the slot
         const int j0 = m * 32 + kq * 8;
         const float4 c0 = *reinterpret_cast<const float4*>(ck + j0), c1 = *reinterpret_cast<const float4*>(ck + j0 + 4);
         const float4 p0 = *reinterpret_cast<const float4*>(pen + j0), p1 = *reinterpret_cast<const float4*>(pen + j0 + 4);
@@ -522,6 +520,12 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
           mx = fmaxf(mx, lgt);
           lg[m * 8 + e] = lgt;
         }
+        // Release the slot only AFTER the bias values have been consumed.  An arrive issued right behind the two LDS does not
+        // wait for their data (the scoreboard wait sits at the first use), and mbarrier operations are not ordered behind
+        // queued shared-memory loads: the producer's refill of this slot was observed to overtake the loads of the last
+        // arriving warp (round 2: ~0.5 % of the tiles of a full C2 batch came out with one stale 16-byte bias piece per row).
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bias_empty[s]);
       }
       xmax[kq * 128 + te] = mx;
       epi_sync512();

@@ -110,6 +110,11 @@ int abopt_debug_gemm3x(int device, int M, int N, int K, const float* A, const fl
 /* Debug hook: SM-clock timestamps of the phases of one CTA of the last attention-logits kernel (16 slots). */
 int abopt_debug_clocks(long long* out16);
 
+/* Debug hook (parity bisection): copy one internal workspace tensor of the last GABlock call into `dst` (device memory with room
+ * for max_floats): which = 0 QA, 1 KB, 2 rq, 3 rk, 4 VT (packed attention operands), 5 pair bias (slot 0), 6 alpha, 7 aggregate.
+ * *numel receives the number of floats copied.  Enqueues on `stream`. */
+int abopt_debug_copy(abopt_model* m, int which, float* dst, size_t max_floats, size_t* numel, void* stream);
+
 /* FullDPM.__init__ : allocate an empty model on CUDA device `device`. */
 int  abopt_model_create(const abopt_config* cfg, int device, abopt_model** out);
 void abopt_model_destroy(abopt_model* m);

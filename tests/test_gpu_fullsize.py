@@ -297,7 +297,8 @@ def test_trained_checkpoint_slice(golden_dir):
     g64 = to64({k: g[k] for k in ('v', 'p', 's', 'res_feat', 'pair_feat', 'mask_generate', 'mask_res')})
     o64 = epsnet.eps_net(W64, g64['v'], g64['p'] / 10.0, g64['s'], g64['res_feat'], g64['pair_feat'], beta.double(), g64['mask_generate'],
                          g64['mask_res'], materialize=False)
-    for i, (key, floor) in enumerate((('v_next', None), ('R_next', 5e-6), ('eps_pos', 2e-6), ('c_denoised', 5e-7), ('prmsd_logits', 1e-5))):
+    # floors: a few ulp of the 3xTF32 products at trained activation scales (|x| up to 4, logits up to 20)
+    for i, (key, floor) in enumerate((('v_next', None), ('R_next', 1e-5), ('eps_pos', 5e-6), ('c_denoised', 2e-5), ('prmsd_logits', 3e-5))):
         if floor is None:
             continue
         assert_vs_fp64(key, got[i], g[key], o64[i], floor)             # "ref32" here IS the unmodified reference's fp32 result
@@ -332,7 +333,73 @@ def test_training_forward_c5_is_the_mean_of_its_halves():
     n2 = {n: (x[B - 2:] if x.dim() == 3 else x[(B - 2) * L:]).contiguous() for n, x in nz.items()}
     got = f(two, t[B - 2:].contiguous(), n2)
     c, cn = cpu(two), cpu(n2)
-    ref = training.loss_forward(W, c['v'], c['p'], c['s'], c['res_feat'], c['pair_feat'], c['mask_generate'], c['mask_res'], True, True,
-                                t[B - 2:].cpu(), cn, flavour='abdesign', obj='pred_noise')
+    la = lambda WW, x, n: training.loss_forward(WW, x['v'], x['p'], x['s'], x['res_feat'], x['pair_feat'], x['mask_generate'], x['mask_res'],
+                                                True, True, t[B - 2:].cpu(), n, flavour='abdesign', obj='pred_noise')
+    ref, ref64 = la(W, c, cn), la(weights.cast(W, torch.double), to64(c), to64(cn))
+    # the fp64 oracle arbitrates: noised rotations near pi make the fp32 oracle itself uncertain at the 1e-3 level on `rot`
     for k in ref:
-        torch.testing.assert_close(got[k].cpu(), ref[k], rtol=2e-4, atol=1e-5, msg=lambda m, k=k: f'{k}: {m}')
+        e_got, e_ref = abs(got[k].double().item() - ref64[k].item()), abs(ref[k].double().item() - ref64[k].item())
+        assert e_got <= 2 * e_ref + 2e-5 * max(1.0, abs(ref64[k].item())), f'{k}: cuda {got[k].item()} oracle32 {ref[k].item()} oracle64 {ref64[k].item()}'
+
+
+# ------------------------------------------------------------------------------------------ encode + sample from atoms
+def test_design_entry_points_from_atoms():
+    """DiffusionAntibodyDesign.sample / optimize (models/diffab.py:115-171) as one device-resident call: the trajectory's
+    context rows carry v_0 = log(construct_3d_basis(CA, C, N)), p_0 = CA, s_0 = aa of the oracle; the composed path (module
+    mirrors + FullDPM with the same seed) agrees on the first frames; host and device entry points give the same bits."""
+    from oracle import pair_embed as PE
+    C = ab_opt_b200._capi
+    N, L, A = 3, 40, 15
+    cfg = dict(res_feat_dim=128, pair_feat_dim=64, num_bins=40, dist_min=0.5, dist_max=19.5,
+               diffusion=dict(num_steps=100, eps_net_opt=dict(num_layers=2), obj='pred_x0'))
+    model = ab_opt_b200.DiffusionAntibodyDesign(cfg)
+    model.diffusion.load_state_dict(weights.make_state_dict(seed=11, num_layers=2, flavour='abdock'), strict=True)
+    model.pair_embed.load_state_dict(PE.make_state_dict(2, A), strict=True)
+    model.residue_embed.load_state_dict(PE.make_residue_state_dict(3, A), strict=True)
+    model = model.to(DEV).eval()
+    cx = PE.synthetic_complex(8, N, L)
+    gen = ~cx['context_mask'] & cx['mask_atoms'][:, :, 1]
+    batch = dict(aa=cx['aa'].clamp(max=19), res_nb=cx['res_nb'], chain_nb=cx['chain_nb'], pos_heavyatom=cx['pos_atoms'],
+                 mask_heavyatom=cx['mask_atoms'], fragment_type=torch.randint(1, 4, (N, L), generator=torch.Generator().manual_seed(2)),
+                 generate_flag=gen, mask=cx['mask_atoms'][:, :, 1].clone())
+    dbatch = cu(batch)
+    T0 = 4
+    traj = model.optimize(dict(dbatch), T0, {'sample_structure': True, 'sample_sequence': True, 'seed': 99})
+    again = model.optimize(dict(dbatch), T0, {'sample_structure': True, 'sample_sequence': True, 'seed': 99})
+    assert sorted(traj) == list(range(T0 + 1))
+    for i in range(3):
+        assert torch.equal(traj[0][i], again[0][i])
+    # context rows of every frame = the encoded input state
+    R0 = PE.backbone_frames(cx['pos_atoms'][:, :, 1], cx['pos_atoms'][:, :, 2], cx['pos_atoms'][:, :, 0])
+    v0 = G.so3_log(R0)
+    keep = ~gen & batch['mask']
+    gap = (np.pi - v0.norm(dim=-1)).clamp_min(1e-9)                   # the log map is ill-conditioned near pi (SURVEY finding 4)
+    err = (G.so3_exp(traj[T0][0].cpu()) - G.so3_exp(v0)).abs().amax(dim=(-1, -2))
+    assert not (keep & (gap > 0.05) & (err > 2e-5 + 3e-6 / gap ** 2)).any(), err[keep].max()
+    # positions are re-normalised / un-normalised on every step (dpm_full.py:276,297): equal to rounding, not bit for bit
+    torch.testing.assert_close(traj[0][1].cpu()[keep], cx['pos_atoms'][:, :, 1][keep], rtol=1e-5, atol=1e-4)
+    assert torch.equal(traj[0][2].cpu()[keep], batch['aa'][keep])
+    assert torch.isfinite(traj[0][1]).all() and (traj[0][0].cpu()[gen] != v0[gen]).any()
+    # the composed path of the reference (encode, then diffusion.optimize) with the same seed: same noised start, close after one step
+    res_feat, pair_feat, R, p = model.encode(dict(dbatch), True, True)
+    comp = model.diffusion.optimize(model._so3vec(R), p, dbatch['aa'], T0, res_feat, pair_feat, dbatch['generate_flag'], dbatch['mask'],
+                                    seed=99)
+    live = batch['mask']
+    assert torch.equal(comp[T0][2][live], traj[T0][2][live])
+    torch.testing.assert_close(comp[T0][1][live], traj[T0][1][live], rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(comp[T0 - 1][1][live], traj[T0 - 1][1][live], rtol=1e-3, atol=5e-3)
+    # host entry point: same bits as the device one
+    nm, pe, re_ = model.diffusion.native(), model.pair_embed.native(), model.residue_embed.native()
+    flags = C.SAMPLE_STRUCTURE | C.SAMPLE_SEQUENCE | C.KEEP_TRAJECTORY
+    tv, tp, ts = torch.empty(T0 + 1, N, L, 3), torch.empty(T0 + 1, N, L, 3), torch.empty(T0 + 1, N, L, dtype=torch.int64)
+    pr, pl = torch.empty(T0 + 1, N), torch.empty(T0 + 1, N)
+    h = {k: v.contiguous() for k, v in batch.items()}
+    C.check(C.lib().abopt_design_host(nm.handle, pe.handle, re_.handle, N, L, A, C.ptr(h['aa']), C.ptr(h['res_nb']), C.ptr(h['chain_nb']),
+                                      C.ptr(h['pos_heavyatom']), C.ptr(h['mask_heavyatom']), C.ptr(h['fragment_type']),
+                                      C.ptr(h['generate_flag']), C.ptr(h['mask']), flags, T0, 99, C.ptr(tv), C.ptr(tp), C.ptr(ts),
+                                      C.ptr(pr), C.ptr(pl)))
+    assert torch.equal(tv[0], traj[0][0].cpu()) and torch.equal(tp[0], traj[0][1].cpu()) and torch.equal(ts[0], traj[0][2].cpu())
+    assert torch.equal(tv[2], traj[2][0]) and torch.equal(ts[T0], traj[T0][2])
+    # sample() through the reference-shaped call
+    out = model.sample(dict(dbatch), {'sample_structure': True, 'sample_sequence': True, 'contig': '', 'seed': 5})
+    assert sorted(out) == list(range(101)) and isinstance(out[3], list) and len(out[3]) == 5 and out[0][0].is_cuda
