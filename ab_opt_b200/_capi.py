@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, '_lib', 'libabopt_b200.so')
+LIB_PATH = os.environ.get('ABOPT_LIB') or os.path.join(_HERE, '_lib', 'libabopt_b200.so')      # ABOPT_LIB: a variant build (A/B measurements)
 
 OK = 0
 SCOPE_FULL, SCOPE_ENCODER, SCOPE_EPSNET = 0, 1, 2

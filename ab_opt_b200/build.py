@@ -26,21 +26,27 @@ def _header_mtime():
     return max(os.path.getmtime(p) for p in paths)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, defines=()):
     """Compile every CUDA source into ab_opt_b200/_lib/libabopt_b200.so; returns the path.
     One nvcc process per translation unit, run concurrently; objects are reused when neither the
-    source nor any header is newer."""
-    os.makedirs(OBJ_DIR, exist_ok=True)
+    source nor any header is newer.
+    variant / defines: an A/B build with extra -D macros into _lib/variants/<variant>/ (select it with ABOPT_LIB=<path>)."""
+    obj_dir, lib_path = OBJ_DIR, LIB_PATH
+    if variant:
+        vdir = os.path.join(LIB_DIR, 'variants', variant)
+        obj_dir, lib_path = os.path.join(vdir, 'obj'), os.path.join(vdir, 'libabopt_b200.so')
+        force = True
+    os.makedirs(obj_dir, exist_ok=True)
     nvcc = os.environ.get('NVCC', 'nvcc')
     hdr = _header_mtime()
     jobs, objs, logs = [], [], []
     for s in SOURCES:
         src = os.path.join(CSRC, s)
-        obj = os.path.join(OBJ_DIR, s[:-3] + '.o')
+        obj = os.path.join(obj_dir, s[:-3] + '.o')
         objs.append(obj)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), hdr):
             continue
-        cmd = [nvcc] + COMPILE_FLAGS + ['-c', src, '-o', obj]
+        cmd = [nvcc] + COMPILE_FLAGS + ['-D' + d for d in defines] + ['-c', src, '-o', obj]
         jobs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = None
     for cmd, proc in jobs:
@@ -53,15 +59,17 @@ def build(force=False, verbose=False):
             f.write('\n'.join(logs))
     if failed is not None:
         raise RuntimeError('nvcc failed:\n' + failed[-4000:])
-    if jobs or not os.path.exists(LIB_PATH):
-        cmd = [nvcc] + LINK_FLAGS + objs + ['-o', LIB_PATH]
+    if jobs or not os.path.exists(lib_path):
+        cmd = [nvcc] + LINK_FLAGS + objs + ['-o', lib_path]
         proc = subprocess.run(cmd, capture_output=True, text=True)
         if proc.returncode != 0:
             raise RuntimeError('link failed:\n' + (proc.stdout + proc.stderr)[-4000:])
     if verbose:
         print('\n'.join(logs))
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))
+    var = [a.split('=', 1)[1] for a in sys.argv if a.startswith('--variant=')]
+    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv, variant=var[0] if var else None,
+                defines=[a[2:] for a in sys.argv if a.startswith('-D')]))

@@ -269,16 +269,32 @@ attn_logits_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
 //               the swizzled box) -> logits; max / exp / sum exchanged through shared memory; alpha stored with 256-bit
 //               global stores (one full 32-byte sector each)
 constexpr int AP_THREADS = 640, AP_EPI = 512, AP_SPLIT = 64;      // (18 warps are allocated registers as 20 anyway)
-constexpr int AP_BST = 2, AP_BGRP_BYTES = 4 * 64 * 32 * 4;            // key-group stage: 64 keys x (hi k0 | hi k1 | lo k0 | lo k1) = 32 KB
+// Shared memory (217 KB): query operand hi | lo (64 KB), two key-group stages (64 KB), a 3-deep pair-bias ring (48 KB), 2 alpha
+// staging boxes (32 KB), double-buffered per-key tables, barriers.  Measured on B200 (round 2, scripts/kbench.py with variant
+// builds, us per full-batch launch): stages / bias slots / staging boxes = 2/3/2: 123.8, 1/4/3: 131.7 (the epilogue then waits for
+// the MMA stream: 18 % of its stall samples on tmem_full), 2/2/3: 131.1; mbarrier.test_wait instead of try_wait in the
+// producer's event loop: no change.  DRAM is idle 56 % of the time (dram__cycles_active), i.e. the kernel is bound by the serial
+// bias -> softmax -> store phases of a tile, not by bandwidth or by DRAM page locality.
+#ifndef ABOPT_AP_BST
+#define ABOPT_AP_BST 2
+#endif
+#ifndef ABOPT_AP_NBIAS
+#define ABOPT_AP_NBIAS 3
+#endif
+#ifndef ABOPT_AP_NSTG
+#define ABOPT_AP_NSTG 2
+#endif
+constexpr int AP_BST = ABOPT_AP_BST, AP_BGRP_BYTES = 4 * 64 * 32 * 4; // key-group stage: 64 keys x (hi k0 | hi k1 | lo k0 | lo k1) = 32 KB
 constexpr int AP_KBOX = 64 * 32 * 4;                                  // one key box: 64 rows x 32 floats
-constexpr int AP_NBIAS = 3, AP_BIAS_BYTES = 128 * 32 * 4;             // bias chunk: 128 queries x 32 keys
+constexpr int AP_NBIAS = ABOPT_AP_NBIAS, AP_BIAS_BYTES = 128 * 32 * 4;    // bias chunk: 128 queries x 32 keys
+constexpr int AP_NSTG = ABOPT_AP_NSTG, AP_STG_BYTES = 128 * 32 * 4;       // alpha staging boxes of [128 queries][32 keys], 128-byte swizzle
 constexpr int AP_B_OFF = 2 * AL_OPER_BYTES;
 constexpr int AP_BIAS_OFF = AP_B_OFF + AP_BST * AP_BGRP_BYTES;
-constexpr int AP_STG_OFF = AP_BIAS_OFF + AP_NBIAS * AP_BIAS_BYTES;    // alpha staging: 2 boxes of [128 queries][32 keys], 128-byte swizzle
-constexpr int AP_STG_BYTES = 128 * 32 * 4;
-constexpr int AP_TAB_OFF = AP_STG_OFF + 2 * AP_STG_BYTES;             // ck[256] | pen[256] | xmax[4][128] | xsum[4][128]
-constexpr int AP_BAR_OFF = AP_TAB_OFF + 2 * 256 * 4 + 8 * 128 * 4;
+constexpr int AP_STG_OFF = AP_BIAS_OFF + AP_NBIAS * AP_BIAS_BYTES;
+constexpr int AP_TAB_OFF = AP_STG_OFF + AP_NSTG * AP_STG_BYTES;       // ck[2][256] | pen[2][256] | xmax[4][128] | xsum[4][128]
+constexpr int AP_BAR_OFF = AP_TAB_OFF + 4 * 256 * 4 + 8 * 128 * 4;
 constexpr int AP_SMEM = AP_BAR_OFF + 256 + 1024;
+static_assert(AP_SMEM <= 227 * 1024, "attn_logits_persist_kernel: shared memory");
 
 // 2^x, x <= 0 (MUFU.EX2, 2 ulp; results below the normal range flush to zero -- attention weights < 1e-38)
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -308,6 +324,19 @@ __device__ __forceinline__ TileRef tile_ref(int tile, int nit, const int2* windo
   return t;
 }
 
+// non-blocking phase test for the producer's event loop (try_wait may suspend the thread for a system-dependent time slice)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+#ifdef ABOPT_AP_TESTWAIT
+#define AP_POLL mbar_test_wait
+#else
+#define AP_POLL mbar_try_wait
+#endif
+
 template <int NCH>                                      // 32-key chunks per row: 4 (keys <= 128) or 8 (keys <= 256)
 __global__ void __launch_bounds__(AP_THREADS, 1)
 attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
@@ -318,9 +347,9 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
   constexpr int NLG = NCH * 8;                          // logits per epilogue thread
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  float* ck = reinterpret_cast<float*>(smem + AP_TAB_OFF);
-  float* pen = ck + 256;
-  float* xmax = pen + 256;                // [4][128]
+  float* ck_tab = reinterpret_cast<float*>(smem + AP_TAB_OFF);      // [2][256]  rk of the tile's keys (double-buffered over tiles)
+  float* pen_tab = ck_tab + 2 * 256;                                 // [2][256]  mask penalty of the tile's keys
+  float* xmax = pen_tab + 2 * 256;        // [4][128]
   float* xsum = xmax + 4 * 128;           // [4][128]
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + AP_BAR_OFF);
   uint64_t* a_empty = a_full + 1;
@@ -365,7 +394,7 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
           const TileRef tr = tile_ref(otile, nit, pa.windows);
           const int row_base = ((a.b0 + tr.bl) * H + tr.h) * L;
           if (ostep == 0) {
-            if (mbar_try_wait(a_empty, (on & 1) ^ 1)) {
+            if (AP_POLL(a_empty, (on & 1) ^ 1)) {
               unsigned char* A = smem + AL_A_OFF;
               const int r0 = row_base + tr.i0;
               mbar_expect_tx(a_full, AL_OPER_BYTES);          // raw fp32 = the "hi" plane; the splitters add the lo plane
@@ -375,7 +404,7 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
             }
           } else {
             const int s = og % AP_BST;
-            if (mbar_try_wait(&b_empty[s], ((og / AP_BST) & 1) ^ 1)) {
+            if (AP_POLL(&b_empty[s], ((og / AP_BST) & 1) ^ 1)) {
               unsigned char* B = smem + AP_B_OFF + s * AP_BGRP_BYTES;
               const int r0 = row_base + (ostep - 1) * 64;
               mbar_expect_tx(&b_full[s], 2 * AP_KBOX);
@@ -388,7 +417,7 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
         }
         if (btile < ntiles) {
           const int s = bc % AP_NBIAS;
-          if (mbar_try_wait(&bias_empty[s], ((bc / AP_NBIAS) & 1) ^ 1)) {
+          if (AP_POLL(&bias_empty[s], ((bc / AP_NBIAS) & 1) ^ 1)) {
             const TileRef tr = tile_ref(btile, nit, pa.windows);
             const int row_base = ((a.b0 + tr.bl) * H + tr.h) * L;
             mbar_expect_tx(&bias_full[s], AP_BIAS_BYTES);
@@ -466,22 +495,34 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
     const int et = (warp - 2) * 32 + lane;                // 0..511
     const float scale = 0.57735026918962576f;             // sqrt(1/3), ga.py:166
     const float l2e = 1.4426950408889634f;
-    int n = 0, bc = 0;
+    // per-key tables of a tile (rk[j], and the mask penalty: 1e5 for masked keys, +inf beyond the end -> alpha = 0) and the
+    // row's rq: loaded one tile AHEAD into registers (threads et < 32 NCH own one key each), parked in the other table buffer at
+    // the end of the tile, so that no tile starts by waiting on global loads
+    auto key_tables = [&](const TileRef& tr, float& ckv, float& penv, float& rqv) {
+      const int b = a.b0 + tr.bl, row_base = (b * H + tr.h) * L;
+      if (et < NCH * 32) {
+        ckv = (et < L) ? __ldg(a.rk + (size_t)row_base + et) : 0.f;
+        penv = (et < L) ? (a.mask[(size_t)b * L + et] != 0 ? 0.f : 1e5f) : INFINITY;
+      }
+      rqv = (tr.i0 + te < L) ? __ldg(a.rq + (size_t)row_base + tr.i0 + te) : 0.f;
+    };
+    int n = 0, bc = 0, sc = 0;
+    float rqi = 0.f;
+    if ((int)blockIdx.x < ntiles) {
+      float ckv = 0.f, penv = 0.f;
+      key_tables(tile_ref(blockIdx.x, nit, pa.windows), ckv, penv, rqi);
+      if (et < NCH * 32) { ck_tab[et] = ckv; pen_tab[et] = penv; }
+    }
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
       const TileRef tr = tile_ref(tile, nit, pa.windows);
-      const int h = tr.h, bl = tr.bl, b = a.b0 + bl, i0 = tr.i0;
-      const int row_base = (b * H + h) * L;
+      const int h = tr.h, bl = tr.bl, i0 = tr.i0;
       const int buf = n & 1;
-      const int i = i0 + te;
-      const bool valid = i < L;
-      // per-key tables: rk[j] and the mask penalty (1e5 for masked keys, +inf beyond the end -> alpha = 0)
-      if (et < NCH * 32) {
-        ck[et] = (et < L) ? __ldg(a.rk + (size_t)row_base + et) : 0.f;
-        pen[et] = (et < L) ? (a.mask[(size_t)b * L + et] != 0 ? 0.f : 1e5f) : INFINITY;
-      }
-      const float rqi = valid ? __ldg(a.rq + (size_t)row_base + i) : 0.f;
-      float* alpha_row = a.alpha + ((size_t)(bl * H + h) * L + (valid ? i : 0)) * Lp;
-      epi_sync512();                                      // tables visible; also: every warp is done with the previous tile
+      const float* ck = ck_tab + buf * 256;
+      const float* pen = pen_tab + buf * 256;
+      epi_sync512();                                      // this tile's tables visible; also: every warp is done with the previous tile
+      float ck_n = 0.f, pen_n = 0.f, rq_n = 0.f;
+      const bool more = tile + (int)gridDim.x < ntiles;
+      if (more) key_tables(tile_ref(tile + gridDim.x, nit, pa.windows), ck_n, pen_n, rq_n);      // in flight during this tile
       mbar_wait(&tmem_full[buf], (n >> 1) & 1);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + kq * 8;
@@ -535,25 +576,29 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
 #pragma unroll
       for (int e = 0; e < NLG; ++e) { lg[e] = ex2_approx((lg[e] - mx) * l2e); sum += lg[e]; }
       xsum[kq * 128 + te] = sum;
+      // the next tile's tables: the other buffer was last read in the bias phase of the previous tile
+      if (more && et < NCH * 32) { ck_tab[(buf ^ 1) * 256 + et] = ck_n; pen_tab[(buf ^ 1) * 256 + et] = pen_n; }
+      rqi = rq_n;
       epi_sync512();
       const float inv = 1.0f / ((xsum[te] + xsum[128 + te]) + (xsum[256 + te] + xsum[384 + te]));
-      // alpha leaves chunk by chunk through two staging boxes ([128 queries][32 keys], 128-byte swizzle) and TMA tensor
+      // alpha leaves chunk by chunk through AP_NSTG staging boxes ([128 queries][32 keys], 128-byte swizzle) and TMA tensor
       // stores: whole lines, rows >= L and keys >= Lp clipped by the hardware.  (Per-lane 256-bit global stores of a
       // row-per-lane layout cost 32 sector requests per instruction and kept the LSU the bottleneck of this kernel.)
+      // Box sc % AP_NSTG was last read by the store of chunk sc - AP_NSTG; thread 0 waited for every store but the AP_NSTG - 2
+      // most recent ones BEFORE the previous barrier, so the box is free.
 #pragma unroll
-      for (int m = 0; m < NCH; ++m) {
-        unsigned char* stg = smem + AP_STG_OFF + (m & 1) * AP_STG_BYTES;
-        // the store that last read this box (chunk m - 2) was waited for by thread 0 BEFORE the previous barrier
+      for (int m = 0; m < NCH; ++m, ++sc) {
+        unsigned char* stg = smem + AP_STG_OFF + (sc % AP_NSTG) * AP_STG_BYTES;
         unsigned char* rowp = stg + te * 128;
         *reinterpret_cast<float4*>(rowp + (((2 * kq) ^ (te & 7)) << 4)) =
             make_float4(lg[m * 8] * inv, lg[m * 8 + 1] * inv, lg[m * 8 + 2] * inv, lg[m * 8 + 3] * inv);
         *reinterpret_cast<float4*>(rowp + (((2 * kq + 1) ^ (te & 7)) << 4)) =
             make_float4(lg[m * 8 + 4] * inv, lg[m * 8 + 5] * inv, lg[m * 8 + 6] * inv, lg[m * 8 + 7] * inv);
         fence_async_smem();
-        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // store of chunk m - 1 has read its box
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(AP_NSTG - 2) : "memory");
         epi_sync512();
-        if (et == 0 && m * 32 < Lp) {
-          tma_store_3d(&tmAl, stg, m * 32, i0, bl * H + h);
+        if (et == 0) {                                     // (an empty group when the chunk lies beyond Lp keeps the count in step)
+          if (m * 32 < Lp) tma_store_3d(&tmAl, stg, m * 32, i0, bl * H + h);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }

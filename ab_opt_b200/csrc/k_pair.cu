@@ -9,6 +9,7 @@
 // 3xTF32 split of z; splitting the 64 KB row block in shared memory plus the operand reads of three MMAs cost ~7 passes
 // over the tile (~3600 clk/row of shared-memory bandwidth) against 1536 clk/row of FFMA issue per contraction -- no gain,
 // so the tensor cores are kept for the dense GEMMs.
+#include <cstdlib>
 #include <type_traits>
 #include "tc.cuh"
 #include "params.cuh"
@@ -160,6 +161,8 @@ constexpr int PW_SMEM = PW_WARPS * PW_WARP_BYTES + PW_WARPS * PW_STAGES * 8 + 10
 
 struct PairRowsArgs {
   int L, Lp, b0, nrows, nchunk;   // nrows = complexes covered by this launch * L; b0 = first complex; nchunk = ceil(L / 16)
+  int rev;                        // 1: walk the rows from the LAST complex to the first.  The logits kernel has just written alpha in
+                                  // forward order; the tail of it (what fits the 126 MB L2) is still resident, the head is not
   const float* z;                 // (N, L, L, 64)
   const uint8_t* mask;
   float* alpha;                   // [chunk complex][h][i][Lp]; rows of masked queries are zeroed here (ga.py:25)
@@ -198,6 +201,7 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs 
 
   const int stride = gridDim.x * PW_WARPS;
   const int first = warp * gridDim.x + blockIdx.x;      // consecutive rows go to different SMs
+  const int nbm1 = a.nrows / L - 1;
   // (complex, residue) of a row advance incrementally: no integer division in the loops
   const int dbl = stride / L, di = stride - dbl * L;
   auto advance = [&](int& bl, int& i) { bl += dbl; i += di; if (i >= L) { i -= L; ++bl; } };
@@ -205,9 +209,10 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs 
   // producer nor the consumer ever waits on a global load per row
   // need_word: rows this launch has to produce at all (focus mode skips the others without touching anything)
   auto live_word = [&](int row, unsigned& need_word) {
-    const long long r = (long long)row + (long long)lane * stride;
+    const long long vr = (long long)row + (long long)lane * stride;
     bool live = false, need = false;
-    if (r < a.nrows) {
+    if (vr < a.nrows) {
+      const long long r = a.rev ? (long long)a.nrows - 1 - vr : vr;
       const int bl = (int)(r / L);
       const size_t gr = (size_t)(a.b0 + bl) * L + (int)(r - (long long)bl * L);
       need = a.cidx ? a.cidx[gr] >= 0 : true;
@@ -231,10 +236,11 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs 
     const int j0 = pjc * PW_CJ;
     const int nj = (L - j0 < PW_CJ) ? (L - j0) : PW_CJ;
     if (lane == 0) {
+      const int rbl = a.rev ? nbm1 - pbl : pbl, ri = a.rev ? L - 1 - pi : pi;      // (complex, residue) of the virtual row
       unsigned char* st = wst + ps * PW_STAGE_BYTES;
       mbar_expect_tx(&full[ps], (uint32_t)(nj * C * 4 + PW_A_BYTES));
-      bulk_load_1d_hint(st, a.z + (((size_t)(a.b0 + pbl) * L + pi) * L + j0) * C, (uint32_t)(nj * C * 4), &full[ps], pol);
-      tma_load_3d(st + PW_Z_BYTES, &amap, j0, pi, pbl * H, &full[ps]);
+      bulk_load_1d_hint(st, a.z + (((size_t)(a.b0 + rbl) * L + ri) * L + j0) * C, (uint32_t)(nj * C * 4), &full[ps], pol);
+      tma_load_3d(st + PW_Z_BYTES, &amap, j0, ri, rbl * H, &full[ps]);
     }
     if (++ps == PW_STAGES) ps = 0;
     if (++pjc == a.nchunk) {
@@ -253,15 +259,16 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs 
   unsigned cword = live_word(first, cneed);
   int bl = first / L, i = first - bl * L;
   for (int row = first; row < a.nrows; row += stride, advance(bl, i)) {
-    const int b = a.b0 + bl;
+    const int rbl = a.rev ? nbm1 - bl : bl, ri = a.rev ? L - 1 - i : i;
+    const int b = a.b0 + rbl;
     const bool live = (cword >> ck) & 1u, need = (cneed >> ck) & 1u;
     if (++ck == 32) { ck = 0; cword = live_word(row + stride, cneed); }
     if (!need) continue;
-    const size_t orow = a.cidx ? (size_t)a.cidx[(size_t)b * L + i] : (size_t)b * L + i;
+    const size_t orow = a.cidx ? (size_t)a.cidx[(size_t)b * L + ri] : (size_t)b * L + ri;
     float* feat_row = a.feat + orow * NFEAT;
     if (!live) {
       // masked query: alpha row = 0 (ga.py:25) -> zero pair aggregate
-      float* alpha_row0 = a.alpha + ((size_t)(bl * H) * L + i) * Lp;
+      float* alpha_row0 = a.alpha + ((size_t)(rbl * H) * L + ri) * Lp;
       for (int o = lane; o < H * C; o += 32) feat_row[o] = 0.f;
       for (int o = lane; o < H * Lp; o += 32) {
         const int h = o / Lp, j = o - h * Lp;
@@ -370,6 +377,7 @@ bool launch_pair_stream(int nb, int b0, int L, int Lp, const float* z, const uin
   PairRowsArgs a{};
   a.L = L; a.Lp = Lp; a.b0 = b0; a.nrows = nb * L; a.nchunk = (L + PW_CJ - 1) / PW_CJ;
   a.z = z; a.mask = mask; a.alpha = alpha; a.feat = feat; a.cidx = cidx;
+  { const char* ev = getenv("ABOPT_PAIR_FWD"); a.rev = (ev && ev[0] == '1') ? 0 : 1; }      // ABOPT_PAIR_FWD=1: forward walk (A/B measurement)
   int grid = g_sm_count > 0 ? g_sm_count : 148;
   const int need = (a.nrows + PW_WARPS - 1) / PW_WARPS;
   if (grid > need) grid = need;
