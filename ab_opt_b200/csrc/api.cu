@@ -516,8 +516,8 @@ static int ensure_workspace(abopt_model* m, int N, int L) {
                oAl = take((size_t)NB * H * L * Lp * 4), oPr = take(M * bins * 4), oPl = take((size_t)N * bins * 4),
                oMp = take(M * 4), oVn = take(M * 3 * 4), oEp = take(M * 3 * 4), oCd = take(M * NAA * 4), oRn = take(M * 9 * 4),
                oBi = take(M * 4), oTv = take((size_t)N * 8), oXal = take(M * F * 4), oXbl = take(M * F * 4), oXil = take(M * F * 4),
-               oQa = take(M * H * 64 * 4), oQl = take(M * H * 64 * 4),
-               oKb = take(M * H * 64 * 4), oKl = take(M * H * 64 * 4), oRq = take(M * H * 4), oRk = take(M * H * 4),
+               oQa = take(M * H * 64 * 4), oQl = take(256),
+               oKb = take(M * H * 64 * 4), oKl = take(256), oRq = take(M * H * 4), oRk = take(M * H * 4),
                oVt = take((size_t)N * H * 64 * Lp * 4), oVl = take((size_t)N * H * 64 * Lp * 4),
                oFc = take(M * 4), oFr = take(M * 4), oFw = take((size_t)N * (L / 64 + 2) * 8), oFn = take(64), oFs = take((size_t)N * 8),
                oFx = take(M * F * 4), oFm = take(M);
@@ -587,7 +587,8 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
     // packed attention operands -> alpha -> aggregates; every tensor between two kernels travels through HBM / L2 once
     {
       const size_t r0 = (size_t)b0 * L, o64 = (size_t)b0 * H * L * 64, o1 = (size_t)b0 * H * L, ov = (size_t)b0 * H * 64 * w.Lp;
-      const AttnOperands opc{w.op.QA + o64, w.op.QA_lo + o64, w.op.KB + o64, w.op.KB_lo + o64, w.op.rq + o1, w.op.rk + o1,
+      // (QA_lo / KB_lo are placeholders: every logits kernel builds the lo planes of its operands on chip)
+      const AttnOperands opc{w.op.QA + o64, w.op.QA_lo, w.op.KB + o64, w.op.KB_lo, w.op.rq + o1, w.op.rk + o1,
                              w.op.VT + ov, w.op.VT_lo + ov};
       if (!launch_proj_pack(nb * L, L, w.Lp, x + r0 * F, x_lo + r0 * F, bw.Wcat, bw.Wcat_lo, R + r0 * 9, t + r0 * 3, bw.coef, opc, st))
         return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (proj)");
@@ -694,7 +695,7 @@ static int run_eps_net(abopt_model* m, int N, int L, const float* v_t, const flo
       launch_focus_build(N, L, mask_gen, w.focus.cidx, w.focus.rows, w.focus.windows, w.focus.count, w.focus.scratch, st);
     if (m->bias_hoisted) m->focus_built = true;           // the sampling loop: mask_generate is a loop invariant
     hf = &w.focus;
-    if (!m->cfg.has_prmsd && L <= 256 && w.NB >= N) fc = &w.focus;
+    if (!m->cfg.has_prmsd && w.NB >= N) fc = &w.focus;
   }
   launch_mixer(M, res_feat, s_t, v_t, m->eps, w.xa, w.Rbuf, p_ang, w.pnorm, m->diff.pos_mean, m->diff.pos_scale, w.xa_lo, st);
   const float* tpos = p_ang ? w.pnorm : p_t;

@@ -1,20 +1,12 @@
-// attn_logits_tc_kernel: final attention logits and the softmax over key residues on the 5th-gen tensor cores.
+// Attention logits and the softmax over key residues on the 5th-gen tensor cores (attn_logits_persist_kernel), and the
+// node / point aggregation GEMM (aggr_persist_kernel).
 //
-// For one (complex b, head h, tile of 128 query residues) the CTA computes
+// For one (complex b, head h, tile of 128 query residues) the logits kernel computes
 //   D[i][j] = QA[i] . KB[j]            64-wide contraction: q.k / sqrt(32)  and  -2 c_h qp_i . kp_j   (3xTF32, TMEM accumulator)
 //   l[i][j] = ((D + pair_bias(i, j)) + (rq[i] + rk[j])) * sqrt(1/3) - 1e5 [key j masked]              ga.py:81-112,166,23
 //   alpha[i][:] = softmax_j l[i][:]                                                                       ga.py:24
 // QA / KB / rq / rk come packed from the projection GEMM epilogue (k_tc.cu: EpiProjPack); pair_bias is the hoisted
 // z . W_b (k_pair.cu: pair_bias_kernel).
-//
-// Warp roles (320 threads):
-//   warp 0     TMA producer: the 128 x 64 query operand once, then key blocks of 128 residues through a 2-stage ring
-//   warp 1     TMEM allocator + MMA issuer: per key block 8 k-steps x 3 products (hi*hi, hi*lo, lo*hi) of
-//              tcgen05.mma.kind::tf32 M=128 N=128 K=8 into TMEM columns [128 nb, 128 nb + 128)
-//   warps 2-9  epilogue: two threads per query row (TMEM lane), each owning half of the keys.  Three passes over the
-//              row in TMEM, 32 columns at a time: (1) logits -> running max, written back with tcgen05.st,
-//              (2) exp -> running sum, written back, (3) normalise and store alpha.  The only cross-thread traffic is
-//              the exchange of the two half-row maxima / sums through shared memory.
 #include <cstdlib>
 #include "tc.cuh"
 #include "params.cuh"
@@ -24,17 +16,11 @@ namespace abopt {
 
 using namespace tc;
 
-constexpr int AL_THREADS = 320;                        // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int AL_EPI = 256;                            // epilogue threads: two per query row (each takes half of the keys)
 constexpr int AL_BM = 128, AL_BN = 128, AL_K = 64;
 constexpr int AL_BOX_BYTES = 128 * 32 * 4;             // one TMA box: 128 rows x 32 floats = 16 KB
 constexpr int AL_OPER_BYTES = 2 * AL_BOX_BYTES;        // 128 rows x 64 floats (two boxes along K)
-constexpr int AL_MAXCOLS = 512;                        // TMEM columns = longest key axis
-constexpr int AL_A_OFF = 0;                            // A hi | A lo
-constexpr int AL_B_OFF = 2 * AL_OPER_BYTES;            // 2 stages x (B hi | B lo)
-constexpr int AL_TAB_OFF = AL_B_OFF + 2 * 2 * AL_OPER_BYTES;   // rk[512] | pen[512] | row max [2][128] | row sum [2][128]
-constexpr int AL_BAR_OFF = AL_TAB_OFF + 2 * AL_MAXCOLS * 4 + 4 * 128 * 4;
-constexpr int AL_SMEM = AL_BAR_OFF + 128 + 1024;
+constexpr int AL_MAXCOLS = 512;                        // longest key axis (two CTAs x 256 TMEM columns)
+constexpr int AL_A_OFF = 0;                            // query operand: hi | lo
 
 struct AttnLogitsArgs {
   int L, Lp, b0;
@@ -44,12 +30,7 @@ struct AttnLogitsArgs {
   float* alpha;                          // [chunk][H][L][Lp]
 };
 
-// phase timestamps of CTA (0,0,0) (SM clock), read back by abopt_debug_clocks(): a poor man's timeline
-__device__ long long g_attn_clk[16];
-__device__ __forceinline__ void stamp(int slot) {
-  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_attn_clk[slot] = clock64();
-}
-void attn_debug_clocks(long long* out16) { cudaMemcpyFromSymbol(out16, g_attn_clk, sizeof(long long) * 16); }
+void attn_debug_clocks(long long* out16) { for (int i = 0; i < 10; ++i) out16[i] = 0; }      // (the timeline hook of the retired one-tile kernel)
 
 // smem box -> global through a 3-D tensor map (c0 = key, c1 = query row, c2 = (complex, head)); bulk async group
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
@@ -57,203 +38,8 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
                ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(AL_EPI) : "memory"); }
-
-// One tile per CTA, any key count up to 512: the row is processed in three passes over TMEM (serves 256 < L <= 512; shorter
-// complexes use attn_logits_persist_kernel below).
-__global__ void __launch_bounds__(AL_THREADS, 1)
-attn_logits_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
-                      const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
-                      const __grid_constant__ CUtensorMap tmBias, const __grid_constant__ CUtensorMap tmAl,
-                      const AttnLogitsArgs a) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  float* ck = reinterpret_cast<float*>(smem + AL_TAB_OFF);
-  float* pen = ck + AL_MAXCOLS;
-  float* xmax = pen + AL_MAXCOLS;         // [2][128]
-  float* xsum = xmax + 2 * 128;           // [2][128]
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + AL_BAR_OFF);
-  uint64_t* b_full = a_full + 1;          // [2]
-  uint64_t* b_empty = b_full + 2;         // [2]
-  uint64_t* tmem_full = b_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int L = a.L, Lp = a.Lp;
-  const int i0 = blockIdx.x * AL_BM, h = blockIdx.y, bl = blockIdx.z, b = a.b0 + bl;
-  const int nblk = (L + AL_BN - 1) / AL_BN;
-  const int ncols = nblk * AL_BN;
-  const uint32_t tmem_cols = ncols <= 128 ? 128u : (ncols <= 256 ? 256u : 512u);
-  const int row_base = (b * H + h) * L;                 // first row of this (b, h) in the [N*H*L][*] views
-
-  if (threadIdx.x == 0) {
-    mbar_init(a_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    mbar_init(tmem_full, 1);
-    mbar_fence_init();
-    tma_prefetch_desc(&tmQh); tma_prefetch_desc(&tmQl); tma_prefetch_desc(&tmKh); tma_prefetch_desc(&tmKl);
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) stamp(0);
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (elect_one()) {
-      unsigned char* A = smem + AL_A_OFF;
-      mbar_expect_tx(a_full, 2 * AL_OPER_BYTES);
-      tma_load_2d(A, &tmQh, 0, row_base + i0, a_full);
-      tma_load_2d(A + AL_BOX_BYTES, &tmQh, 32, row_base + i0, a_full);
-      tma_load_2d(A + AL_OPER_BYTES, &tmQl, 0, row_base + i0, a_full);
-      tma_load_2d(A + AL_OPER_BYTES + AL_BOX_BYTES, &tmQl, 32, row_base + i0, a_full);
-      for (int nb = 0; nb < nblk; ++nb) {
-        const int s = nb & 1;
-        mbar_wait(&b_empty[s], ((nb >> 1) & 1) ^ 1);
-        unsigned char* B = smem + AL_B_OFF + s * 2 * AL_OPER_BYTES;
-        mbar_expect_tx(&b_full[s], 2 * AL_OPER_BYTES);
-        const int r0 = row_base + nb * AL_BN;
-        tma_load_2d(B, &tmKh, 0, r0, &b_full[s]);
-        tma_load_2d(B + AL_BOX_BYTES, &tmKh, 32, r0, &b_full[s]);
-        tma_load_2d(B + AL_OPER_BYTES, &tmKl, 0, r0, &b_full[s]);
-        tma_load_2d(B + AL_OPER_BYTES + AL_BOX_BYTES, &tmKl, 32, r0, &b_full[s]);
-        if (nb == (nblk > 1 ? 1 : 0)) {
-          // once the first operand loads are queued: pull this tile of the (HBM-resident) pair bias into L2 while the
-          // MMAs run -- boxes of [<= 256 keys][128 queries] of the [N*H*L keys][Lp queries] view
-          for (int j0 = 0; j0 < L; j0 += 256)
-            asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(&tmBias), "r"(j0), "r"(row_base + i0) : "memory");
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = idesc_tf32(AL_BM, AL_BN);
-    mbar_wait(a_full, 0);
-    if (lane == 0) stamp(1);
-    for (int nb = 0; nb < nblk; ++nb) {
-      const int s = nb & 1;
-      mbar_wait(&b_full[s], (nb >> 1) & 1);
-      if (lane == 0) stamp(2 + (nb & 1));
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t a_hi = smem_u32(smem + AL_A_OFF), a_lo = a_hi + AL_OPER_BYTES;
-        const uint32_t b_hi = smem_u32(smem + AL_B_OFF + s * 2 * AL_OPER_BYTES), b_lo = b_hi + AL_OPER_BYTES;
-        const uint32_t d = tmem_base + nb * AL_BN;
-        // The tensor core truncates the fp32 accumulator on every accumulation (error ~ 2^-24 |running sum| each).  Issue
-        // the 16 small correction products FIRST, while the running sum is tiny, then the 8 large hi*hi products: the
-        // accumulated truncation is that of 8 accumulations instead of 24 -- same effect as a separate accumulator.
-#pragma unroll
-        for (int kk = 0; kk < AL_K / 8; ++kk) {          // UMMA_K = 8 tf32 = 32 B inside a 128 B swizzle row; 4 steps per box
-          const uint32_t ko = (kk >> 2) * AL_BOX_BYTES + (kk & 3) * 32;
-          mma_tf32(d, smem_desc_sw128(a_hi + ko), smem_desc_sw128(b_lo + ko), idesc, kk == 0 ? 0u : 1u);
-          mma_tf32(d, smem_desc_sw128(a_lo + ko), smem_desc_sw128(b_hi + ko), idesc, 1u);
-        }
-#pragma unroll
-        for (int kk = 0; kk < AL_K / 8; ++kk) {
-          const uint32_t ko = (kk >> 2) * AL_BOX_BYTES + (kk & 3) * 32;
-          mma_tf32(d, smem_desc_sw128(a_hi + ko), smem_desc_sw128(b_hi + ko), idesc, 1u);
-        }
-        mma_commit(&b_empty[s]);
-        if (nb == nblk - 1) mma_commit(tmem_full);
-      }
-      __syncwarp();
-    }
-  } else {
-    // ===================== epilogue (warps 2..9) =====================
-    const int q = warp & 3;                               // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;                     // which half of the key axis this thread handles
-    const int te = q * 32 + lane;                         // 0..127: query row in the tile
-    const int i = i0 + te;
-    const bool valid = i < L;
-    const int cbeg = half * (ncols / 2), cend = cbeg + ncols / 2;
-    // per-key tables: rk[j] and the mask penalty (1e5 for masked keys, +inf beyond the end -> alpha = 0)
-    for (int j = te + half * 128; j < ncols; j += AL_EPI) {
-      ck[j] = (j < L) ? __ldg(a.rk + (size_t)row_base + j) : 0.f;
-      pen[j] = (j < L) ? (a.mask[(size_t)b * L + j] != 0 ? 0.f : 1e5f) : INFINITY;
-    }
-    const float rqi = valid ? __ldg(a.rq + (size_t)row_base + i) : 0.f;
-    const float* bias_col = a.bias + ((size_t)row_base + (valid ? i : 0)) * Lp;      // + j: bias is stored [i][j]
-    float* alpha_row = a.alpha + ((size_t)(bl * H + h) * L + (valid ? i : 0)) * Lp;
-    (void)alpha_row; (void)cend;
-    auto load_bias = [&](int c0, float (&dst)[32]) {
-#pragma unroll
-      for (int e = 0; e < 32; ++e) dst[e] = (c0 + e < L) ? __ldg(bias_col + (c0 + e)) : 0.f;
-    };
-    epi_sync();                                           // tables visible to all epilogue warps
-    if (te == 0 && half == 0) stamp(4);
-    mbar_wait(tmem_full, 0);
-    if (te == 0 && half == 0) stamp(5);
-    tc_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    const float scale = 0.57735026918962576f;             // sqrt(1/3), ga.py:166
-    const float l2e = 1.4426950408889634f;
-
-    {
-      float bv[32], bn[32];
-      load_bias(cbeg, bv);
-      // ---- pass 1: logits, running max.  The pair bias of the next 32 keys is in flight while this chunk is processed.
-      float m = -INFINITY;
-      for (int c0 = cbeg; c0 < cend; c0 += 32) {
-        if (c0 + 32 < cend) load_bias(c0 + 32, bn);
-        float v[32];
-        tmem_ld_32x32(trow + c0, v);
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float lgt = ((v[e] + bv[e]) + (rqi + ck[c0 + e])) * scale - pen[c0 + e];
-          m = fmaxf(m, lgt);
-          v[e] = lgt;
-        }
-        tmem_st_32x32(trow + c0, v);
-#pragma unroll
-        for (int e = 0; e < 32; ++e) bv[e] = bn[e];
-      }
-      xmax[half * 128 + te] = m;
-      epi_sync();
-      m = fmaxf(xmax[te], xmax[128 + te]);
-      // ---- pass 2: exp(l - m) = 2^((l - m) log2e), running sum
-      float sum = 0.f;
-      for (int c0 = cbeg; c0 < cend; c0 += 32) {
-        float v[32];
-        tmem_ld_32x32(trow + c0, v);
-#pragma unroll
-        for (int e = 0; e < 32; ++e) { v[e] = exp2f((v[e] - m) * l2e); sum += v[e]; }
-        tmem_st_32x32(trow + c0, v);
-      }
-      xsum[half * 128 + te] = sum;
-      epi_sync();
-      sum = xsum[te] + xsum[128 + te];
-      // ---- pass 3: normalise, store alpha and its tf32 "lo" plane
-      const float inv = 1.0f / sum;
-      for (int c0 = cbeg; c0 < cend; c0 += 32) {
-        float v[32];
-        tmem_ld_32x32(trow + c0, v);
-        if (valid) {
-          // 256-bit stores (rows are 32-byte aligned, Lp % 8 == 0): every store fills a whole 32 B sector
-#pragma unroll
-          for (int e = 0; e < 32; e += 8)
-            if (c0 + e < Lp) {
-              float o[8];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) o[u] = v[e + u] * inv;
-              asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(alpha_row + c0 + e), "f"(o[0]),
-                           "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
-            }
-        }
-      }
-    }
-    if (te == 0 && half == 0) stamp(8);
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) stamp(9);
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
-}
-
-// ------------------------------------------------------------------------------------------ persistent variant (keys <= 256)
-// attn_logits_persist_kernel: same arithmetic as attn_logits_tc_kernel<true>, restructured so that the phases of consecutive
-// tiles overlap and no thread ever waits on a global load.  One CTA per SM walks the (complex, head, 128-query tile) list;
+// ------------------------------------------------------------------------------------------ logits + softmax
+// attn_logits_persist_kernel: the phases of consecutive tiles overlap and no thread ever waits on a global load.  One CTA per SM walks the (complex, head, 128-query tile) list;
 // 18 warps:
 //   warp 0      TMA producer, one thread running a small event loop over two independent streams:
 //                 operands -- the query operand (single buffer, released by the MMA warp) and key groups of 64 residues
@@ -293,7 +79,7 @@ constexpr int AP_BIAS_OFF = AP_B_OFF + AP_BST * AP_BGRP_BYTES;
 constexpr int AP_STG_OFF = AP_BIAS_OFF + AP_NBIAS * AP_BIAS_BYTES;
 constexpr int AP_TAB_OFF = AP_STG_OFF + AP_NSTG * AP_STG_BYTES;       // ck[2][256] | pen[2][256] | xmax[4][128] | xsum[4][128]
 constexpr int AP_BAR_OFF = AP_TAB_OFF + 4 * 256 * 4 + 8 * 128 * 4;
-constexpr int AP_SMEM = AP_BAR_OFF + 256 + 1024;
+constexpr int AP_SMEM = AP_BAR_OFF + 256 + 4 * 128 * 4 + 1024;         // barriers (<= 31 x 8 B + slot) | SPLIT exchange [2][2][128] floats
 static_assert(AP_SMEM <= 227 * 1024, "attn_logits_persist_kernel: shared memory");
 
 // 2^x, x <= 0 (MUFU.EX2, 2 ulp; results below the normal range flush to zero -- attention weights < 1e-38)
@@ -337,13 +123,44 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 #define AP_POLL mbar_try_wait
 #endif
 
-template <int NCH>                                      // 32-key chunks per row: 4 (keys <= 128) or 8 (keys <= 256)
+// ---- thread-block-cluster helpers (key-split variant: two CTAs share one tile's softmax)
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `p` (own shared memory) inside CTA `rank` of the cluster, as a shared::cluster address
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t raddr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t raddr) {      // release at cluster scope: the store above is visible to the waiter
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t it = 0; !ok; ++it) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (it > 50000000u) __trap();
+  }
+}
+
+// NCH: 32-key chunks per CTA and row (4: keys <= 128, 8: keys <= 256; SPLIT: 5..8 per half).
+// SPLIT (256 < keys <= 512): the kernel runs as clusters of TWO CTAs; CTA `rank` of a cluster handles keys [rank * 32 NCH, ...) of
+// the cluster's tile with exactly the single-CTA pipeline, and the two halves of a row exchange their maximum and their sum of
+// exponentials through distributed shared memory (one remote store + one remote mbarrier arrive per row and quantity).
+template <int NCH, bool SPLIT>
 __global__ void __launch_bounds__(AP_THREADS, 1)
 attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
                            const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
                            const __grid_constant__ CUtensorMap tmBias, const __grid_constant__ CUtensorMap tmAl,
                            const AttnLogitsArgs a, const AttnPersistArgs pa) {
-  constexpr int NGRP = NCH / 2;                         // 64-key MMA groups
+  constexpr int NGRP = (NCH + 1) / 2;                   // MMA groups of 64 keys (the last one has 32 when NCH is odd)
   constexpr int NLG = NCH * 8;                          // logits per epilogue thread
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -361,12 +178,18 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
   uint64_t* tmem_empty = tmem_full + 2;   // [2]
   uint64_t* a_split = tmem_empty + 2;
   uint64_t* b_split = a_split + 1;        // [AP_BST]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_split + AP_BST);
+  uint64_t* xch_bar = b_split + AP_BST;   // [2 kinds][2 tile parities]  SPLIT: the partner's row maxima / sums have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xch_bar + 4);
+  float* xch = reinterpret_cast<float*>(smem + AP_BAR_OFF + 256);      // [2 kinds][2 parities][128 rows], written by the partner CTA
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = a.L, Lp = a.Lp;
   const int nit = (L + AL_BM - 1) / AL_BM;              // query tiles per (complex, head)
   const int ntiles = pa.windows ? pa.wcount[1] * H : pa.nb_complex * H * nit;
+  const uint32_t crank = SPLIT ? cluster_ctarank() : 0u;
+  const int key0 = (int)crank * NCH * 32;               // first key of this CTA
+  const int tfirst = SPLIT ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // the tile walk of this CTA (SPLIT: of its cluster)
+  const int tstride = SPLIT ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     mbar_init(a_full, 1); mbar_init(a_empty, 1);
@@ -374,6 +197,7 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
     for (int s = 0; s < AP_BST; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); mbar_init(&b_split[s], AP_SPLIT); }
     for (int s = 0; s < AP_NBIAS; ++s) { mbar_init(&bias_full[s], 1); mbar_init(&bias_empty[s], AP_EPI / 32); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], AP_EPI / 32); }
+    for (int s = 0; s < 4; ++s) mbar_init(&xch_bar[s], 128);
     mbar_fence_init();
     tma_prefetch_desc(&tmQh); tma_prefetch_desc(&tmQl); tma_prefetch_desc(&tmKh); tma_prefetch_desc(&tmKl); tma_prefetch_desc(&tmBias);
     tma_prefetch_desc(&tmAl);
@@ -381,14 +205,15 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  if constexpr (SPLIT) cluster_sync_all();              // the partner's barriers are initialised before anyone arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ===================== TMA producer: event loop over the operand stream and the bias stream =====================
     if (elect_one()) {
-      int otile = blockIdx.x, on = 0, og = 0, ostep = 0;        // operand stream: tile, tile count, key-group count, step in tile
-      int btile = blockIdx.x, bc = 0, bm = 0;                   // bias stream: tile, chunk count, chunk in tile
+      int otile = tfirst, on = 0, og = 0, ostep = 0;        // operand stream: tile, tile count, key-group count, step in tile
+      int btile = tfirst, bc = 0, bm = 0;                   // bias stream: tile, chunk count, chunk in tile
       while (otile < ntiles || btile < ntiles) {
         if (otile < ntiles) {
           const TileRef tr = tile_ref(otile, nit, pa.windows);
@@ -406,12 +231,12 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
             const int s = og % AP_BST;
             if (AP_POLL(&b_empty[s], ((og / AP_BST) & 1) ^ 1)) {
               unsigned char* B = smem + AP_B_OFF + s * AP_BGRP_BYTES;
-              const int r0 = row_base + (ostep - 1) * 64;
+              const int r0 = row_base + key0 + (ostep - 1) * 64;
               mbar_expect_tx(&b_full[s], 2 * AP_KBOX);
               tma_load_2d(B, &tmKh, 0, r0, &b_full[s]);
               tma_load_2d(B + AP_KBOX, &tmKh, 32, r0, &b_full[s]);
               ++og;
-              if (++ostep > NGRP) { ostep = 0; ++on; otile += gridDim.x; }
+              if (++ostep > NGRP) { ostep = 0; ++on; otile += tstride; }
             }
           }
         }
@@ -421,18 +246,18 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
             const TileRef tr = tile_ref(btile, nit, pa.windows);
             const int row_base = ((a.b0 + tr.bl) * H + tr.h) * L;
             mbar_expect_tx(&bias_full[s], AP_BIAS_BYTES);
-            tma_load_2d(smem + AP_BIAS_OFF + s * AP_BIAS_BYTES, &tmBias, bm * 32, row_base + tr.i0, &bias_full[s]);
+            tma_load_2d(smem + AP_BIAS_OFF + s * AP_BIAS_BYTES, &tmBias, key0 + bm * 32, row_base + tr.i0, &bias_full[s]);
             ++bc;
-            if (++bm == NCH) { bm = 0; btile += gridDim.x; }
+            if (++bm == NCH) { bm = 0; btile += tstride; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = idesc_tf32(AL_BM, 64);
+    constexpr uint32_t idesc64 = idesc_tf32(AL_BM, 64), idesc32 = idesc_tf32(AL_BM, 32);
     int n = 0, g = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+    for (int tile = tfirst; tile < ntiles; tile += tstride, ++n) {
       const int buf = n & 1;
       mbar_wait(&tmem_empty[buf], ((n >> 1) & 1) ^ 1);    // the epilogue has read this TMEM buffer (tile n - 2)
       mbar_wait(a_split, n & 1);                          // query operand landed AND its lo plane is built
@@ -444,6 +269,7 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
           const uint32_t a_hi = smem_u32(smem + AL_A_OFF), a_lo = a_hi + AL_OPER_BYTES;
           const uint32_t b_hi = smem_u32(smem + AP_B_OFF + s * AP_BGRP_BYTES), b_lo = b_hi + 2 * AP_KBOX;
           const uint32_t d = tmem_base + buf * 256 + gi * 64;
+          const uint32_t idesc = ((NCH & 1) && gi == NGRP - 1) ? idesc32 : idesc64;      // 32-key tail group (its stage holds 64 rows)
 #pragma unroll
           for (int kk = 0; kk < AL_K / 8; ++kk) {
             const uint32_t ka = (kk >> 2) * AL_BOX_BYTES + (kk & 3) * 32, kb = (kk >> 2) * AP_KBOX + (kk & 3) * 32;
@@ -475,7 +301,7 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
       fence_async_smem();                                 // generic-proxy writes -> visible to the tensor core (async proxy)
     };
     int n = 0, g = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+    for (int tile = tfirst; tile < ntiles; tile += tstride, ++n) {
       mbar_wait(a_full, n & 1);
       split(smem + AL_A_OFF, smem + AL_A_OFF + AL_OPER_BYTES, AL_OPER_BYTES / 16);
       mbar_arrive(a_split);
@@ -501,19 +327,20 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
     auto key_tables = [&](const TileRef& tr, float& ckv, float& penv, float& rqv) {
       const int b = a.b0 + tr.bl, row_base = (b * H + tr.h) * L;
       if (et < NCH * 32) {
-        ckv = (et < L) ? __ldg(a.rk + (size_t)row_base + et) : 0.f;
-        penv = (et < L) ? (a.mask[(size_t)b * L + et] != 0 ? 0.f : 1e5f) : INFINITY;
+        const int j = key0 + et;
+        ckv = (j < L) ? __ldg(a.rk + (size_t)row_base + j) : 0.f;
+        penv = (j < L) ? (a.mask[(size_t)b * L + j] != 0 ? 0.f : 1e5f) : INFINITY;
       }
       rqv = (tr.i0 + te < L) ? __ldg(a.rq + (size_t)row_base + tr.i0 + te) : 0.f;
     };
     int n = 0, bc = 0, sc = 0;
     float rqi = 0.f;
-    if ((int)blockIdx.x < ntiles) {
+    if (tfirst < ntiles) {
       float ckv = 0.f, penv = 0.f;
-      key_tables(tile_ref(blockIdx.x, nit, pa.windows), ckv, penv, rqi);
+      key_tables(tile_ref(tfirst, nit, pa.windows), ckv, penv, rqi);
       if (et < NCH * 32) { ck_tab[et] = ckv; pen_tab[et] = penv; }
     }
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+    for (int tile = tfirst; tile < ntiles; tile += tstride, ++n) {
       const TileRef tr = tile_ref(tile, nit, pa.windows);
       const int h = tr.h, bl = tr.bl, i0 = tr.i0;
       const int buf = n & 1;
@@ -521,8 +348,8 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
       const float* pen = pen_tab + buf * 256;
       epi_sync512();                                      // this tile's tables visible; also: every warp is done with the previous tile
       float ck_n = 0.f, pen_n = 0.f, rq_n = 0.f;
-      const bool more = tile + (int)gridDim.x < ntiles;
-      if (more) key_tables(tile_ref(tile + gridDim.x, nit, pa.windows), ck_n, pen_n, rq_n);      // in flight during this tile
+      const bool more = tile + tstride < ntiles;
+      if (more) key_tables(tile_ref(tile + tstride, nit, pa.windows), ck_n, pen_n, rq_n);      // in flight during this tile
       mbar_wait(&tmem_full[buf], (n >> 1) & 1);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + kq * 8;
@@ -571,6 +398,16 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
       xmax[kq * 128 + te] = mx;
       epi_sync512();
       mx = fmaxf(fmaxf(xmax[te], xmax[128 + te]), fmaxf(xmax[256 + te], xmax[384 + te]));
+      if constexpr (SPLIT) {
+        // the row maximum over BOTH key halves: send ours to the partner CTA, take the partner's (buffer / barrier phase by tile
+        // parity: the partner cannot be more than one tile ahead, it needs our value of the tile in between)
+        if (kq == 0) {
+          st_cluster_f32(mapa_u32(&xch[(0 * 2 + buf) * 128 + te], crank ^ 1u), mx);
+          mbar_arrive_cluster(mapa_u32(&xch_bar[0 * 2 + buf], crank ^ 1u));
+        }
+        mbar_wait_cluster(&xch_bar[0 * 2 + buf], (n >> 1) & 1);
+        mx = fmaxf(mx, xch[(0 * 2 + buf) * 128 + te]);
+      }
       // exp(l - m) = 2^((l - m) log2e): subtract FIRST (exact near the maximum, where the attention mass is)
       float sum = 0.f;
 #pragma unroll
@@ -580,7 +417,17 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
       if (more && et < NCH * 32) { ck_tab[(buf ^ 1) * 256 + et] = ck_n; pen_tab[(buf ^ 1) * 256 + et] = pen_n; }
       rqi = rq_n;
       epi_sync512();
-      const float inv = 1.0f / ((xsum[te] + xsum[128 + te]) + (xsum[256 + te] + xsum[384 + te]));
+      float rowsum = (xsum[te] + xsum[128 + te]) + (xsum[256 + te] + xsum[384 + te]);
+      if constexpr (SPLIT) {
+        if (kq == 0) {
+          st_cluster_f32(mapa_u32(&xch[(1 * 2 + buf) * 128 + te], crank ^ 1u), rowsum);
+          mbar_arrive_cluster(mapa_u32(&xch_bar[1 * 2 + buf], crank ^ 1u));
+        }
+        mbar_wait_cluster(&xch_bar[1 * 2 + buf], (n >> 1) & 1);
+        const float other = xch[(1 * 2 + buf) * 128 + te];
+        rowsum = crank == 0 ? rowsum + other : other + rowsum;      // same order of the two halves in both CTAs
+      }
+      const float inv = 1.0f / rowsum;
       // alpha leaves chunk by chunk through AP_NSTG staging boxes ([128 queries][32 keys], 128-byte swizzle) and TMA tensor
       // stores: whole lines, rows >= L and keys >= Lp clipped by the hardware.  (Per-lane 256-bit global stores of a
       // row-per-lane layout cost 32 sector requests per instruction and kept the LSU the bottleneck of this kernel.)
@@ -598,7 +445,7 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
         if (et == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(AP_NSTG - 2) : "memory");
         epi_sync512();
         if (et == 0) {                                     // (an empty group when the chunk lies beyond Lp keeps the count in step)
-          if (m * 32 < Lp) tma_store_3d(&tmAl, stg, m * 32, i0, bl * H + h);
+          if (key0 + m * 32 < Lp) tma_store_3d(&tmAl, stg, key0 + m * 32, i0, bl * H + h);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
@@ -607,49 +454,64 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
     tc_fence_before();
   }
   __syncthreads();
+  if constexpr (SPLIT) cluster_sync_all();              // the partner may still be writing our exchange buffers
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-bool attn_needs_qk_lo(int L) { return ((L + AL_BN - 1) / AL_BN) * AL_BN > 256; }
+bool attn_needs_qk_lo(int) { return false; }      // the lo planes of QA / KB are built on chip for every length
 cudaError_t attn_tc_init() {
-  cudaError_t e = cudaFuncSetAttribute(attn_logits_persist_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(attn_logits_persist_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(attn_logits_persist_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM);
+  e = cudaFuncSetAttribute(attn_logits_persist_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(attn_logits_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AL_SMEM);
+  if ((e = cudaFuncSetAttribute(attn_logits_persist_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(attn_logits_persist_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(attn_logits_persist_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(attn_logits_persist_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM)) != cudaSuccess) return e;
+  return cudaSuccess;
 }
 
 bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOperands& op, const float* bias_layer, const uint8_t* mask,
                            float* alpha, cudaStream_t st, const int2* windows, const int* wcount) {
   if (L > AL_MAXCOLS) return false;
-  CUtensorMap qh, ql, kh, kl, bm, al;
+  CUtensorMap qh, kh64, bm32, al;
   const uint64_t rows = (uint64_t)N * H * L;
-  if (!make_tmap(&qh, op.QA, rows, 64, 64, 128) || !make_tmap(&ql, op.QA_lo, rows, 64, 64, 128) ||
-      !make_tmap(&kh, op.KB, rows, 64, 64, 128) || !make_tmap(&kl, op.KB_lo, rows, 64, 64, 128))
+  // query operand boxes of 128 rows, key operands in groups of 64 residues (raw fp32 = the "hi" plane; the lo planes are built on
+  // chip); the pair bias [(b,h,i) rows][Lp keys] as swizzled [128 queries][32 keys] boxes
+  if (!make_tmap(&qh, op.QA, rows, 64, 64, 128) || !make_tmap(&kh64, op.KB, rows, 64, 64, 64) ||
+      !make_tmap(&bm32, bias_layer, rows, (uint64_t)Lp, (uint64_t)Lp, 128))
     return false;
-  // pair bias as a plain (unswizzled) 2-D tensor for L2 prefetches: [N*H*L queries][Lp keys], box [<=128][<=256]
-  if (!make_tmap_plain(&bm, bias_layer, rows, (uint64_t)Lp, (uint64_t)Lp, rows < 128 ? (uint32_t)rows : 128u, Lp < 256 ? (uint32_t)Lp : 256u))
-    return false;
-  // alpha / alpha_lo as 3-D tensors [chunk * H][L queries][Lp keys] for the TMA stores (rows >= L are clipped)
+  // alpha as a 3-D tensor [chunk * H][L queries][Lp keys] for the TMA stores (rows >= L are clipped)
   if (!make_tmap_3d(&al, alpha, Lp, L, (uint64_t)nb * H, 32, 128)) return false;
   ProfScope prof__(KK_LOGITS, st);
   AttnLogitsArgs a{L, Lp, b0, op.rq, op.rk, bias_layer, mask, alpha};
-  dim3 grid((L + AL_BM - 1) / AL_BM, H, nb);
   const int ncols = ((L + AL_BN - 1) / AL_BN) * AL_BN;
+  const int ntiles = nb * H * ((L + AL_BM - 1) / AL_BM);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const AttnPersistArgs pa{windows, wcount, nb};
   if (ncols <= 256) {
-    // key operands in groups of 64 residues; the pair bias [(b,h,i) rows][Lp keys] as swizzled [128 queries][32 keys] boxes
-    CUtensorMap kh64, kl64, bm32;
-    if (!make_tmap(&kh64, op.KB, rows, 64, 64, 64) || !make_tmap(&kl64, op.KB_lo, rows, 64, 64, 64) ||
-        !make_tmap(&bm32, bias_layer, rows, (uint64_t)Lp, (uint64_t)Lp, 128))
-      return false;
-    const int ntiles = nb * H * ((L + AL_BM - 1) / AL_BM);
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    const AttnPersistArgs pa{windows, wcount, nb};
-    if (ncols <= 128) attn_logits_persist_kernel<4><<<ntiles < sms ? ntiles : sms, AP_THREADS, AP_SMEM, st>>>(qh, ql, kh64, kl64, bm32, al, a, pa);
-    else attn_logits_persist_kernel<8><<<ntiles < sms ? ntiles : sms, AP_THREADS, AP_SMEM, st>>>(qh, ql, kh64, kl64, bm32, al, a, pa);
-  } else attn_logits_tc_kernel<<<grid, AL_THREADS, AL_SMEM, st>>>(qh, ql, kh, kl, bm, al, a);
-  return true;
+    if (ncols <= 128) attn_logits_persist_kernel<4, false><<<ntiles < sms ? ntiles : sms, AP_THREADS, AP_SMEM, st>>>(qh, qh, kh64, kh64, bm32, al, a, pa);
+    else attn_logits_persist_kernel<8, false><<<ntiles < sms ? ntiles : sms, AP_THREADS, AP_SMEM, st>>>(qh, qh, kh64, kh64, bm32, al, a, pa);
+    return true;
+  }
+  // 256 < keys <= 512: clusters of two CTAs, each takes half of the keys of a tile (NCH 32-key chunks)
+  const int nch = ((Lp + 31) / 32 + 1) / 2;
+  const int nclusters = ntiles < sms / 2 ? ntiles : sms / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * nclusters); cfg.blockDim = dim3(AP_THREADS); cfg.dynamicSmemBytes = AP_SMEM; cfg.stream = st;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  cudaError_t e;
+  switch (nch) {
+    case 5: e = cudaLaunchKernelEx(&cfg, attn_logits_persist_kernel<5, true>, qh, qh, kh64, kh64, bm32, al, a, pa); break;
+    case 6: e = cudaLaunchKernelEx(&cfg, attn_logits_persist_kernel<6, true>, qh, qh, kh64, kh64, bm32, al, a, pa); break;
+    case 7: e = cudaLaunchKernelEx(&cfg, attn_logits_persist_kernel<7, true>, qh, qh, kh64, kh64, bm32, al, a, pa); break;
+    default: e = cudaLaunchKernelEx(&cfg, attn_logits_persist_kernel<8, true>, qh, qh, kh64, kh64, bm32, al, a, pa); break;
+  }
+  return e == cudaSuccess;
 }
 
 // ------------------------------------------------------------------------------------------ aggregation GEMM

@@ -377,7 +377,7 @@ bool launch_pair_stream(int nb, int b0, int L, int Lp, const float* z, const uin
   PairRowsArgs a{};
   a.L = L; a.Lp = Lp; a.b0 = b0; a.nrows = nb * L; a.nchunk = (L + PW_CJ - 1) / PW_CJ;
   a.z = z; a.mask = mask; a.alpha = alpha; a.feat = feat; a.cidx = cidx;
-  { const char* ev = getenv("ABOPT_PAIR_FWD"); a.rev = (ev && ev[0] == '1') ? 0 : 1; }      // ABOPT_PAIR_FWD=1: forward walk (A/B measurement)
+  { const char* ev = getenv("ABOPT_PAIR_REV"); a.rev = (ev && ev[0] == '1') ? 1 : 0; }      // ABOPT_PAIR_REV=1: reverse walk (measured neutral on B200)
   int grid = g_sm_count > 0 ? g_sm_count : 148;
   const int need = (a.nrows + PW_WARPS - 1) / PW_WARPS;
   if (grid > need) grid = need;
