@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get('ABOPT_LIB') or os.path.join(_HERE, '_lib', 'libabopt_
 
 OK = 0
 SCOPE_FULL, SCOPE_ENCODER, SCOPE_EPSNET = 0, 1, 2
-SAMPLE_STRUCTURE, SAMPLE_SEQUENCE, KEEP_TRAJECTORY = 1, 2, 4
+SAMPLE_STRUCTURE, SAMPLE_SEQUENCE, KEEP_TRAJECTORY, GRAD_SEMANTICS = 1, 2, 4, 8
 
 # every symbol include/abopt_b200.h declares (tests check the library exports all of them)
 EXPORTS = (
@@ -25,7 +25,7 @@ EXPORTS = (
     'abopt_loss_forward', 'abopt_model_set_batch_offset', 'abopt_pair_embed_create', 'abopt_pair_embed_destroy', 'abopt_pair_embed_set_tensor',
     'abopt_pair_embed_finalize', 'abopt_pair_embed_forward', 'abopt_res_embed_create', 'abopt_res_embed_destroy',
     'abopt_res_embed_set_tensor', 'abopt_res_embed_finalize', 'abopt_res_embed_forward',
-    'abopt_reconstruct_backbone_partially', 'abopt_pairwise_rmsd', 'abopt_rank_commoness', 'abopt_design_device', 'abopt_design_host',
+    'abopt_reconstruct_backbone_partially', 'abopt_pairwise_rmsd', 'abopt_rank_commoness', 'abopt_design_device', 'abopt_design_host', 'abopt_loss_backward', 'abopt_model_get_grad', 'abopt_ga_block_backward',
 )
 
 
@@ -84,6 +84,9 @@ def lib():
         L.abopt_debug_gemm3x.argtypes = [ci, ci, ci, ci] + [vp] * 5
         L.abopt_debug_copy.argtypes = [vp, ci, vp, C.c_size_t, C.POINTER(C.c_size_t), vp]
         L.abopt_loss_forward.argtypes = [vp, ci, ci] + [vp] * 7 + [C.c_uint32, vp, C.c_uint64, C.POINTER(StepNoise), vp, vp]
+        L.abopt_loss_backward.argtypes = [vp, ci, ci] + [vp] * 7 + [C.c_uint32, vp, C.c_uint64, C.POINTER(StepNoise), vp, vp, vp, vp, vp]
+        L.abopt_model_get_grad.argtypes = [vp, C.c_char_p, vp, C.c_size_t, vp]
+        L.abopt_ga_block_backward.argtypes = [vp, ci, ci, ci] + [vp] * 9
         L.abopt_sample_host.argtypes = [vp, ci, ci] + [vp] * 7 + [C.c_uint32, ci, C.c_uint64] + [vp] * 5
         L.abopt_pair_embed_create.argtypes = [ci, ci, C.POINTER(C.c_void_p)]
         L.abopt_pair_embed_destroy.argtypes = [vp]

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, '_lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libabopt_b200.so')
-SOURCES = ['api.cu', 'k_linear.cu', 'k_attn.cu', 'k_attn_tc.cu', 'k_pair.cu', 'k_step.cu', 'k_tc.cu', 'k_tail_tc.cu', 'k_pair_embed.cu', 'k_res_embed.cu', 'k_post.cu']
+SOURCES = ['api.cu', 'k_linear.cu', 'k_attn.cu', 'k_attn_tc.cu', 'k_pair.cu', 'k_step.cu', 'k_tc.cu', 'k_tail_tc.cu', 'k_pair_embed.cu', 'k_res_embed.cu', 'k_post.cu', 'k_backward.cu']
 ARCH_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a']
 COMPILE_FLAGS = ARCH_FLAGS + ['-lineinfo', '-O3', '--std=c++17', '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 LINK_FLAGS = ARCH_FLAGS + ['-shared', '-Xcompiler', '-fPIC']

@@ -100,6 +100,12 @@ struct abopt_model {
   void* train_buf = nullptr; size_t train_bytes = 0;      // scratch of abopt_loss_forward
   void* design_buf = nullptr; size_t design_bytes = 0;    // scratch of abopt_design_*: context mask, v_0, p_0, res_feat, pair_feat
   void* design_io = nullptr; size_t design_io_bytes = 0;  // device staging of abopt_design_host
+  // ---- training step (abopt_loss_backward): raw weights as stored by nn.Linear, gradient buffer, scratch
+  struct RawHead { const float* W0; const float* b0; const float* W2; const float* b2; const float* W4; const float* b4; int nout; };
+  struct RawEps { const float* Wm0; const float* bm0; const float* Wm2; const float* bm2; RawHead head[4]; const float* prm_g; const float* prm_b; } raw{};
+  std::map<std::string, std::pair<size_t, size_t>> grad_off;      // trainable key -> (offset, numel) in grad_buf
+  float* grad_buf = nullptr; size_t grad_floats = 0;
+  void* tws = nullptr; size_t tws_bytes = 0;
   long long batch_offset = 0;                             // index of this handle's first complex in the global (unsharded) batch
 };
 
@@ -257,6 +263,7 @@ extern "C" int abopt_model_create(const abopt_config* cfg, int device, abopt_mod
   CUDA_TRY(attn_tc_init());
   CUDA_TRY(aggr_tc_init());
   CUDA_TRY(tail_tc_init());
+  CUDA_TRY(backward_kernels_init());
   abopt_model* m = new abopt_model();
   m->cfg = *cfg;
   m->device = device;
@@ -279,6 +286,8 @@ extern "C" void abopt_model_destroy(abopt_model* m) {
   if (m->train_buf) cudaFree(m->train_buf);
   if (m->design_buf) cudaFree(m->design_buf);
   if (m->design_io) cudaFree(m->design_io);
+  if (m->grad_buf) cudaFree(m->grad_buf);
+  if (m->tws) cudaFree(m->tws);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   delete m;
 }
@@ -371,6 +380,8 @@ extern "C" int abopt_model_finalize(abopt_model* m) {
     const float* wb = F32(m, p + "proj_pair_bias.weight");         // [12][64]
     std::vector<float> wbt = transpose(wb, H, C);                    // [64][12]
     reg(&b.Wb, pk.put(wbt));
+    reg(&b.Wb_raw, pk.put(wb, H * C * 4));
+    reg(&b.sc_raw, pk.put(F32(m, p + "spatial_coef"), H * 4));
     memcpy(m->pb[l].Wb, wbt.data(), sizeof(float) * C * H);
     for (int c = 0; c < C; ++c)
       for (int hp = 0; hp < H / 2; ++hp) m->pbp[l].w[hp / 3][c][hp % 3] = make_float2(wb[(2 * hp) * C + c], wb[(2 * hp + 1) * C + c]);
@@ -432,6 +443,28 @@ extern "C" int abopt_model_finalize(abopt_model* m) {
             "eps_net.eps_rot_net.2.bias", "eps_net.eps_rot_net.4.weight", "eps_net.eps_rot_net.4.bias", 3);
   pack_head(e.seq, "eps_net.eps_seq_net.0.weight", "eps_net.eps_seq_net.0.bias", "eps_net.eps_seq_net.2.weight",
             "eps_net.eps_seq_net.2.bias", "eps_net.eps_seq_net.4.weight", "eps_net.eps_seq_net.4.bias", NAA);
+  {
+    auto rawt = [&](const float** slot, const std::string& k) { const HostTensor& t = m->sd[k]; reg(slot, pk.put(t.bytes.data(), t.numel * 4)); };
+    rawt(&m->raw.Wm0, "eps_net.res_feat_mixer.0.weight"); rawt(&m->raw.bm0, "eps_net.res_feat_mixer.0.bias");
+    rawt(&m->raw.Wm2, "eps_net.res_feat_mixer.2.weight"); rawt(&m->raw.bm2, "eps_net.res_feat_mixer.2.bias");
+    const char* hn[3] = {"eps_net.eps_crd_net.", "eps_net.eps_rot_net.", "eps_net.eps_seq_net."};
+    const int no[3] = {3, 3, NAA};
+    for (int hh = 0; hh < 3; ++hh) {
+      auto& rh = m->raw.head[hh];
+      rh.nout = no[hh];
+      rawt(&rh.W0, std::string(hn[hh]) + "0.weight"); rawt(&rh.b0, std::string(hn[hh]) + "0.bias");
+      rawt(&rh.W2, std::string(hn[hh]) + "2.weight"); rawt(&rh.b2, std::string(hn[hh]) + "2.bias");
+      rawt(&rh.W4, std::string(hn[hh]) + "4.weight"); rawt(&rh.b4, std::string(hn[hh]) + "4.bias");
+    }
+    if (m->cfg.has_prmsd) {
+      const std::string p = "eps_net.prmsd_predictor.";
+      auto& rh = m->raw.head[3];
+      rh.nout = m->cfg.prmsd_bins;
+      rawt(&rh.W0, p + "linear_1.weight"); rawt(&rh.b0, p + "linear_1.bias"); rawt(&rh.W2, p + "linear_2.weight"); rawt(&rh.b2, p + "linear_2.bias");
+      rawt(&rh.W4, p + "linear_3.weight"); rawt(&rh.b4, p + "linear_3.bias");
+      rawt(&m->raw.prm_g, p + "layer_norm.gamma"); rawt(&m->raw.prm_b, p + "layer_norm.beta");
+    }
+  }
   if (m->cfg.has_prmsd) {
     const std::string p = "eps_net.prmsd_predictor.";
     pack_head(e.prm, p + "linear_1.weight", p + "linear_1.bias", p + "linear_2.weight", p + "linear_2.bias",
@@ -482,6 +515,24 @@ extern "C" int abopt_model_finalize(abopt_model* m) {
   for (auto& f : fix) *f.slot = reinterpret_cast<const float*>(static_cast<unsigned char*>(m->wbase) + f.off);
   if (m->cfg.scope == ABOPT_SCOPE_FULL)
     for (int tab = 0; tab < 2; ++tab) d.ang_flag[tab] = static_cast<const uint8_t*>(m->wbase) + flag_off[tab];
+  // gradient buffer: one slot per trainable tensor; the six projection weights of a block are contiguous in the order of
+  // Wcat (q | k | v | query points | key points | value points) so that one (2016 x 128) weight-gradient GEMM fills them
+  m->grad_off.clear();
+  size_t goff = 0;
+  auto gslot = [&](const std::string& k) { const size_t n = m->sd[k].numel; m->grad_off[k] = {goff, n}; goff += (n + 3) & ~size_t(3); };
+  for (int l = 0; l < NL; ++l) {
+    const std::string p = "eps_net.encoder.blocks." + std::to_string(l) + ".";
+    for (const char* nm : {"proj_query", "proj_key", "proj_value", "proj_query_point", "proj_key_point", "proj_value_point"}) gslot(p + nm + ".weight");
+  }
+  for (auto& kv : m->spec) {
+    const std::string& k = kv.first;
+    if (!kv.second.required || kv.second.dtype != 0 || m->grad_off.count(k)) continue;
+    if (k.rfind("trans_", 0) == 0 || k.rfind("position_", 0) == 0 || k.rfind("prmsd.", 0) == 0 || k.rfind("_dummy", 0) == 0) continue;
+    gslot(k);
+  }
+  if (m->grad_buf) { CUDA_TRY(cudaFree(m->grad_buf)); m->grad_buf = nullptr; }
+  m->grad_floats = goff;
+  if (goff) { CUDA_TRY(cudaMalloc(&m->grad_buf, goff * sizeof(float))); CUDA_TRY(cudaMemset(m->grad_buf, 0, goff * sizeof(float))); }
   m->finalized = true;
   return ABOPT_OK;
 }
@@ -946,6 +997,7 @@ extern "C" int abopt_loss_forward(abopt_model* m, int N, int L, const float* v_0
   ia.v = v_0; ia.p_ang = p_0; ia.s = (const long long*)s_0; ia.mask_gen = mask_generate;
   ia.v_out = v_noisy; ia.p_out_ang = p_noisy; ia.s_out = s_noisy;
   ia.seed = seed; ia.row0 = (uint32_t)(m->batch_offset * L); ia.tvec = (const long long*)t; ia.seq_all_rows = 1; ia.z_out = ds ? zbuf : nullptr;
+  ia.grad_clamp = (flags & ABOPT_GRAD_SEMANTICS) ? 1 : 0;
   if (noise) {
     if (ds) launch_angle_argmax((int)M, L, (const long long*)t, 0, m->diff.ang_Y[0], noise->expo_ang, mask_generate, w.bin_idx, st);
     ia.add = NoisePtrs{noise->u, noise->unif_ang, noise->gauss_ang, noise->z_pos, noise->expo_seq, w.bin_idx};
@@ -1125,5 +1177,275 @@ extern "C" int abopt_design_host(abopt_model* m, abopt_pair_embed* pe, abopt_res
   if (keep) { rc = copy_slots(0, T0 + 1); if (rc) return rc; }
   else { rc = copy_slots(0, 1); if (rc) return rc; rc = copy_slots(T0, 1); if (rc) return rc; }
   CUDA_TRY(cudaStreamSynchronize(st));
+  return ABOPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------ training step: backward
+// loss.backward() of AbDock/train.py:104-113 through FullDPM.forward / EpsilonNet / GAEncoder, recompute-based (csrc/k_backward.cu,
+// formulas of oracle/ipa_backward.py and oracle/epsnet_backward.py).  Parameter gradients accumulate nowhere: every call overwrites
+// the handle's gradient buffer (abopt_model_get_grad reads it); d res_feat / d pair_feat go to caller buffers.
+namespace {
+struct TrainWS {
+  float *xs, *Pm, *PG, *G, *gfeat, *s1, *h, *a0, *a1, *s2, *t1, *t2, *t3, *gagg, *glog, *part, *scr, *gx, *hcat, *ghcat, *cat0, *gcat, *GO, *GP,
+      *lnb, *orot, *stats, *glogit, *tmp;
+  size_t scr_floats;
+};
+}
+static int ensure_train_ws(abopt_model* m, int N, int L, int Lp, TrainWS& t) {
+  const size_t M = (size_t)N * L;
+  const int bins = m->cfg.has_prmsd ? m->cfg.prmsd_bins : 1;
+  size_t off = 0;
+  auto take = [&](size_t floats) { size_t o = off; off = (off + floats * 4 + 255) & ~size_t(255); return o; };
+  const size_t scr_floats = (size_t)64 * NPROJ * F;
+  const size_t o_xs = take(M * F * (m->cfg.num_layers + 1)), o_P = take(M * NPROJ), o_PG = take(M * 864), o_G = take(M * NPROJ),
+               o_gf = take(M * NFEAT), o_s1 = take(M * F), o_h = take(M * F), o_a0 = take(M * F), o_a1 = take(M * F), o_s2 = take(M * F),
+               o_t1 = take(M * F), o_t2 = take(M * F), o_t3 = take(M * F), o_ga = take(M * 288), o_gl = take((size_t)N * H * L * Lp),
+               o_pt = take(M * 780), o_sc = take(scr_floats), o_gx = take(M * F), o_hc = take(M * (F + 3)), o_gh = take(M * (F + 3)),
+               o_c0 = take(M * 2 * F), o_gc = take(M * 2 * F), o_go = take(M * 26), o_gp = take(M * bins), o_ln = take(M * (F + 3)),
+               o_or = take(M * 4), o_st = take(16), o_gg = take((size_t)N * bins), o_tm = take(4096);
+  if (m->tws_bytes < off) {
+    if (m->tws) { CUDA_TRY(cudaFree(m->tws)); m->tws = nullptr; m->tws_bytes = 0; }
+    CUDA_TRY(cudaMalloc(&m->tws, off));
+    m->tws_bytes = off;
+  }
+  unsigned char* b = static_cast<unsigned char*>(m->tws);
+  auto P_ = [&](size_t o) { return reinterpret_cast<float*>(b + o); };
+  t = TrainWS{P_(o_xs), P_(o_P), P_(o_PG), P_(o_G), P_(o_gf), P_(o_s1), P_(o_h), P_(o_a0), P_(o_a1), P_(o_s2), P_(o_t1), P_(o_t2), P_(o_t3),
+              P_(o_ga), P_(o_gl), P_(o_pt), P_(o_sc), P_(o_gx), P_(o_hc), P_(o_gh), P_(o_c0), P_(o_gc), P_(o_go), P_(o_gp), P_(o_ln), P_(o_or),
+              P_(o_st), P_(o_gg), P_(o_tm), scr_floats};
+  return ABOPT_OK;
+}
+static float* grad_of(abopt_model* m, const std::string& key) {
+  auto it = m->grad_off.find(key);
+  return it == m->grad_off.end() ? nullptr : m->grad_buf + it->second.first;
+}
+__global__ void coef_grad_kernel(const float* __restrict__ gc, const float* __restrict__ sc, float* __restrict__ out) {
+  const int h = threadIdx.x;
+  if (h >= H) return;
+  const float cP = sqrtf(2.f / (9.f * P)) / 2.f;                       // ga.py:109-111: coef = -softplus(sc) cP
+  out[h] = gc[h] * (-cP) * (1.f / (1.f + expf(-sc[h])));               // d softplus = sigmoid
+}
+__global__ void strided_copy_kernel(int M, int K, const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)M * K) return;
+  const int r = (int)(i / K), c = (int)(i - (size_t)r * K);
+  dst[(size_t)r * ldd + c] = src[(size_t)r * lds + c];
+}
+
+// one GABlock, backward.  x = block input; gx: in = d loss / d block output, out = d loss / d x.  d z written (or accumulated) to dz.
+static int block_backward(abopt_model* m, TrainWS& T, int l, int N, int L, const float* R, const float* t, const float* x, const float* z,
+                          const uint8_t* mask, float* gx, float* dz, bool dz_accumulate, cudaStream_t st) {
+  Workspace& w = m->ws;
+  const int M = N * L;
+  const BlockW& bw = m->blocks[l];
+  const std::string p = "eps_net.encoder.blocks." + std::to_string(l) + ".";
+  if (w.NB < N) return fail(ABOPT_ERR_ARG, "backward: the batch does not fit one attention pass (alpha > 2 GiB)");
+  // ---- recompute: alpha and the aggregate by the forward kernels, the plain projections, the tail's activations
+  int rc = run_block(m, l, N, L, R, t, x, nullptr, z, mask, nullptr, nullptr, nullptr, st); if (rc) return rc;
+  bwd_gemm_nt(M, NPROJ, F, x, F, false, bw.Wcat, F, nullptr, T.Pm, NPROJ, st);
+  bwd_points_global(M, T.Pm, R, t, T.PG, st);
+  const float *W1 = bw.Wmlp, *W2 = bw.Wmlp + F * F, *W3 = bw.Wmlp + 2 * F * F;
+  bwd_gemm_nt(M, F, NFEAT, w.feat, NFEAT, false, bw.Wout, NFEAT, bw.bout, T.t1, F, st);                 // y = out_transform(feat)
+  bwd_add_ln_fwd(M, x, T.t1, mask, bw.ln1_g, bw.ln1_b, T.s1, T.h, st);                                  // s1 = x + mask y ; h = LN1
+  bwd_gemm_nt(M, F, F, T.h, F, false, W1, F, bw.b1, T.a0, F, st);
+  bwd_gemm_nt(M, F, F, T.a0, F, true, W2, F, bw.b2, T.a1, F, st);
+  bwd_gemm_nt(M, F, F, T.a1, F, true, W3, F, bw.b3, T.t1, F, st);                                       // m3
+  bwd_add_ln_fwd(M, T.h, T.t1, nullptr, nullptr, nullptr, T.s2, nullptr, st);                           // s2 = h + m3
+  // ---- tail backward (ga.py:173-178)
+  bwd_ln(M, gx, nullptr, T.s2, bw.ln2_g, T.t2, T.t1, nullptr, st);                                      // t2 = g_s2, t1 = g * xhat
+  bwd_colsum(M, F, T.t1, F, nullptr, 0, grad_of(m, p + "layer_norm_2.gamma"), T.scr, st, 1.f);
+  bwd_colsum(M, F, gx, F, nullptr, 0, grad_of(m, p + "layer_norm_2.beta"), T.scr, st, 1.f);
+  bwd_wgrad(M, F, F, T.t2, F, T.a1, F, true, grad_of(m, p + "mlp_transition.4.weight"), T.scr, T.scr_floats, st);
+  bwd_colsum(M, F, T.t2, F, nullptr, 0, grad_of(m, p + "mlp_transition.4.bias"), T.scr, st, 1.f);
+  bwd_gemm_nn(M, F, F, T.t2, F, W3, F, T.t3, F, false, st);
+  bwd_relu((size_t)M * F, T.t3, T.a1, st);                                                              // t3 = g_r1
+  bwd_wgrad(M, F, F, T.t3, F, T.a0, F, true, grad_of(m, p + "mlp_transition.2.weight"), T.scr, T.scr_floats, st);
+  bwd_colsum(M, F, T.t3, F, nullptr, 0, grad_of(m, p + "mlp_transition.2.bias"), T.scr, st, 1.f);
+  bwd_gemm_nn(M, F, F, T.t3, F, W2, F, T.t1, F, false, st);
+  bwd_relu((size_t)M * F, T.t1, T.a0, st);                                                              // t1 = g_r0
+  bwd_wgrad(M, F, F, T.t1, F, T.h, F, false, grad_of(m, p + "mlp_transition.0.weight"), T.scr, T.scr_floats, st);
+  bwd_colsum(M, F, T.t1, F, nullptr, 0, grad_of(m, p + "mlp_transition.0.bias"), T.scr, st, 1.f);
+  bwd_gemm_nn(M, F, F, T.t1, F, W1, F, T.t3, F, false, st);                                             // t3 = g_h (through the MLP)
+  bwd_ln(M, T.t3, T.t2, T.s1, bw.ln1_g, gx, T.t1, T.a1, st);                                            // gx = g_s1 ; a1 = g_h + g_s2
+  bwd_colsum(M, F, T.t1, F, nullptr, 0, grad_of(m, p + "layer_norm_1.gamma"), T.scr, st, 1.f);
+  bwd_colsum(M, F, T.a1, F, nullptr, 0, grad_of(m, p + "layer_norm_1.beta"), T.scr, st, 1.f);
+  bwd_add_mask(M, F, gx, nullptr, mask, T.t2, st);                                                      // t2 = g_s1 * mask
+  bwd_gemm_nn(M, F, NFEAT, T.t2, F, bw.Wout, NFEAT, T.gfeat, NFEAT, false, st);
+  bwd_wgrad(M, F, NFEAT, T.t2, F, w.feat, NFEAT, false, grad_of(m, p + "out_transform.weight"), T.scr, T.scr_floats, st);
+  bwd_colsum(M, F, T.t2, F, nullptr, 0, grad_of(m, p + "out_transform.bias"), T.scr, st, 1.f);
+  // ---- aggregate, softmax, logits (ga.py:81-147)
+  bwd_aggregate(M, T.gfeat, w.feat, R, T.gagg, st);
+  PairBwdArgs pa{};
+  pa.N = N; pa.L = L; pa.Lp = w.Lp; pa.z = z; pa.alpha = w.alpha; pa.mask = mask; pa.gfeat = T.gfeat; pa.g_agg = T.gagg; pa.Pm = T.Pm;
+  pa.PG = T.PG; pa.R = R; pa.Wb = bw.Wb_raw; pa.coef = bw.coef; pa.g_log = T.glog; pa.G = T.G; pa.dz = dz;
+  pa.dz_accumulate = dz_accumulate ? 1 : 0; pa.part = T.part;
+  launch_pair_bwd(pa, st);
+  bwd_colsum(M, 780, T.part, 780, nullptr, 0, T.tmp, T.scr, st, 1.f);
+  CUDA_TRY(cudaMemcpyAsync(grad_of(m, p + "proj_pair_bias.weight"), T.tmp, H * C * 4, cudaMemcpyDeviceToDevice, st));
+  coef_grad_kernel<<<1, 32, 0, st>>>(T.tmp + 768, bw.sc_raw, grad_of(m, p + "spatial_coef"));
+  // ---- projections (ga.py:82-83,96-105,122,129-132)
+  bwd_gemm_nn(M, NPROJ, F, T.G, NPROJ, bw.Wcat, F, gx, F, true, st);
+  bwd_wgrad(M, NPROJ, F, T.G, NPROJ, x, F, false, grad_of(m, p + "proj_query.weight"), T.scr, T.scr_floats, st);
+  CHECK_LAUNCH();
+  return ABOPT_OK;
+}
+
+extern "C" int abopt_ga_block_backward(abopt_model* m, int layer, int N, int L, const float* R, const float* t, const float* x,
+                                       const float* z, const uint8_t* mask, const float* g_out, float* g_x, float* g_z, void* stream) {
+  int rc = check_ready(m, N, L); if (rc) return rc;
+  if (layer < 0 || layer >= m->cfg.num_layers) return fail(ABOPT_ERR_ARG, "layer out of range");
+  if (!R || !t || !x || !z || !mask || !g_out || !g_x || !g_z) return fail(ABOPT_ERR_ARG, "null tensor");
+  DeviceGuard g(m->device);
+  rc = ensure_workspace(m, N, L); if (rc) return rc;
+  TrainWS T;
+  rc = ensure_train_ws(m, N, L, m->ws.Lp, T); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemcpyAsync(T.gx, g_out, (size_t)N * L * F * 4, cudaMemcpyDeviceToDevice, st));
+  rc = block_backward(m, T, layer, N, L, R, t, x, z, mask, T.gx, g_z, false, st); if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(g_x, T.gx, (size_t)N * L * F * 4, cudaMemcpyDeviceToDevice, st));
+  return ABOPT_OK;
+}
+
+extern "C" int abopt_model_get_grad(abopt_model* m, const char* key, float* dst, size_t numel, void* stream) {
+  if (!m || !key || !dst) return fail(ABOPT_ERR_ARG, "null argument");
+  auto it = m->grad_off.find(key);
+  if (it == m->grad_off.end()) return fail(ABOPT_ERR_KEY, std::string("no gradient for key: ") + key);
+  if (it->second.second != numel) return fail(ABOPT_ERR_KEY, std::string("size mismatch for ") + key);
+  DeviceGuard g(m->device);
+  CUDA_TRY(cudaMemcpyAsync(dst, m->grad_buf + it->second.first, numel * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return ABOPT_OK;
+}
+
+// one 3-layer head (dpm_full.py:45-62; PerResiduePredictor, common/nn.py:164-188): recompute its activations from `in`
+// (M, 131), backpropagate g (M, nout; row pitch ldg) and add d loss / d in to g_in (M, 131)
+static void head_backward(abopt_model* m, TrainWS& T, int M, const abopt_model::RawHead& rh, const std::string& k0, const std::string& k2,
+                          const std::string& k4, const float* in, const float* g, int ldg, float* g_in, float* out_raw, cudaStream_t st) {
+  const int K0 = F + 3;
+  bwd_gemm_nt(M, F, K0, in, K0, false, rh.W0, K0, rh.b0, T.a0, F, st);
+  bwd_gemm_nt(M, F, F, T.a0, F, true, rh.W2, F, rh.b2, T.a1, F, st);
+  if (out_raw) { bwd_gemm_nt(M, rh.nout, F, T.a1, F, true, rh.W4, F, rh.b4, out_raw, rh.nout, st); return; }
+  bwd_wgrad(M, rh.nout, F, g, ldg, T.a1, F, true, grad_of(m, k4 + ".weight"), T.scr, T.scr_floats, st);
+  bwd_colsum(M, rh.nout, g, ldg, nullptr, 0, grad_of(m, k4 + ".bias"), T.scr, st, 1.f);
+  bwd_gemm_nn(M, rh.nout, F, g, ldg, rh.W4, F, T.t1, F, false, st);
+  bwd_relu((size_t)M * F, T.t1, T.a1, st);
+  bwd_wgrad(M, F, F, T.t1, F, T.a0, F, true, grad_of(m, k2 + ".weight"), T.scr, T.scr_floats, st);
+  bwd_colsum(M, F, T.t1, F, nullptr, 0, grad_of(m, k2 + ".bias"), T.scr, st, 1.f);
+  bwd_gemm_nn(M, F, F, T.t1, F, rh.W2, F, T.t2, F, false, st);
+  bwd_relu((size_t)M * F, T.t2, T.a0, st);
+  bwd_wgrad(M, F, K0, T.t2, F, in, K0, false, grad_of(m, k0 + ".weight"), T.scr, T.scr_floats, st);
+  bwd_colsum(M, F, T.t2, F, nullptr, 0, grad_of(m, k0 + ".bias"), T.scr, st, 1.f);
+  bwd_gemm_nn(M, F, K0, T.t2, F, rh.W0, K0, g_in, K0, true, st);
+}
+
+extern "C" int abopt_loss_backward(abopt_model* m, int N, int L, const float* v_0, const float* p_0, const int64_t* s_0,
+                                   const float* res_feat, const float* pair_feat, const uint8_t* mask_generate,
+                                   const uint8_t* mask_res, uint32_t flags, const int64_t* t, uint64_t seed,
+                                   const abopt_step_noise* noise, const float* loss_weights, float* losses_out, float* d_res_feat,
+                                   float* d_pair_feat, void* stream) {
+  int rc = check_ready(m, N, L, ABOPT_SCOPE_FULL); if (rc) return rc;
+  if (!v_0 || !p_0 || !s_0 || !res_feat || !pair_feat || !mask_generate || !mask_res || !t || !losses_out || !d_res_feat || !d_pair_feat)
+    return fail(ABOPT_ERR_ARG, "null tensor");
+  if (noise && (!noise->u || !noise->expo_ang || !noise->unif_ang || !noise->gauss_ang || !noise->z_pos || !noise->expo_seq))
+    return fail(ABOPT_ERR_ARG, "incomplete abopt_step_noise record");
+  DeviceGuard g(m->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = ensure_workspace(m, N, L); if (rc) return rc;
+  Workspace& w = m->ws;
+  TrainWS T;
+  rc = ensure_train_ws(m, N, L, w.Lp, T); if (rc) return rc;
+  const size_t M = (size_t)N * L;
+  const int nl = m->cfg.num_layers;
+  const size_t need = M * (3 + 3 + 3 + 6) * sizeof(float) + M * sizeof(long long) + (size_t)N * sizeof(float) + 256;
+  if (m->train_bytes < need) {
+    if (m->train_buf) { CUDA_TRY(cudaFree(m->train_buf)); m->train_buf = nullptr; m->train_bytes = 0; }
+    CUDA_TRY(cudaMalloc(&m->train_buf, need));
+    m->train_bytes = need;
+  }
+  long long* s_noisy = reinterpret_cast<long long*>(m->train_buf);
+  float* v_noisy = reinterpret_cast<float*>(s_noisy + M);
+  float* p_noisy = v_noisy + M * 3;
+  float* zbuf = p_noisy + M * 3;
+  float* rows = zbuf + M * 3;
+  float* beta = rows + M * 6;
+  const bool ds = (flags & ABOPT_SAMPLE_STRUCTURE) != 0, dq = (flags & ABOPT_SAMPLE_SEQUENCE) != 0;
+  // ---- forward (dpm_full.py:156-234), evaluated as with autograd enabled: log_rotation clamps at -0.999 (so3.py:12-17)
+  InitArgs ia{};
+  ia.M = (int)M; ia.L = L; ia.T0 = 0;
+  ia.sample_structure = ds ? 1 : 0; ia.sample_sequence = dq ? 1 : 0; ia.optimize = 1; ia.has_prmsd = 0;
+  ia.v = v_0; ia.p_ang = p_0; ia.s = (const long long*)s_0; ia.mask_gen = mask_generate;
+  ia.v_out = v_noisy; ia.p_out_ang = p_noisy; ia.s_out = s_noisy;
+  ia.seed = seed; ia.row0 = (uint32_t)(m->batch_offset * L); ia.tvec = (const long long*)t; ia.seq_all_rows = 1; ia.z_out = ds ? zbuf : nullptr;
+  ia.grad_clamp = 1;
+  if (noise) {
+    if (ds) launch_angle_argmax((int)M, L, (const long long*)t, 0, m->diff.ang_Y[0], noise->expo_ang, mask_generate, w.bin_idx, st);
+    ia.add = NoisePtrs{noise->u, noise->unif_ang, noise->gauss_ang, noise->z_pos, noise->expo_seq, w.bin_idx};
+  }
+  launch_init(ia, m->diff, st);
+  launch_gather_beta(N, (const long long*)t, m->diff.betas, beta, st);
+  launch_mixer((int)M, res_feat, s_noisy, v_noisy, m->eps, T.xs, w.Rbuf, p_noisy, w.pnorm, m->diff.pos_mean, m->diff.pos_scale, nullptr, st);
+  for (int l = 0; l < nl; ++l) {                                  // only the block INPUTS are kept
+    rc = run_block(m, l, N, L, w.Rbuf, w.pnorm, T.xs + (size_t)l * M * F, nullptr, pair_feat, mask_res, T.xs + (size_t)(l + 1) * M * F, nullptr,
+                   nullptr, st);
+    if (rc) return rc;
+  }
+  const float* xL = T.xs + (size_t)nl * M * F;
+  launch_heads((int)M, L, xL, beta, 1, w.Rbuf, v_noisy, mask_generate, m->eps, w.v_net, w.R_next, w.eps_pos, w.c_den, w.prmsd_rows,
+               m->cfg.has_prmsd ? w.prmsd_logits : nullptr, st);
+  LossArgs la{};
+  la.N = N; la.L = L; la.abdock = m->cfg.has_prmsd ? 1 : 0; la.pred_x0 = m->cfg.obj_pred_x0 ? 1 : 0;
+  la.has_prmsd = m->cfg.has_prmsd; la.bins = m->cfg.prmsd_bins; la.dmin = m->cfg.prmsd_min; la.dmax = m->cfg.prmsd_max;
+  la.v_0 = v_0; la.p_0_ang = p_0; la.s_0 = (const long long*)s_0;
+  la.p_noisy_ang = p_noisy; la.s_noisy = s_noisy; la.z = ds ? zbuf : nullptr;
+  la.R_pred = w.R_next; la.p_pred = w.eps_pos; la.c_den = w.c_den; la.prmsd_logits = w.prmsd_logits;
+  la.mask_gen = mask_generate; la.mask_res = mask_res; la.tvec = (const long long*)t;
+  la.rows = rows; la.out = losses_out;
+  launch_loss(la, m->diff, st);
+  // ---- backward: losses -> heads
+  const int K0 = F + 3;
+  bwd_heads_cat((int)M, L, xL, beta, T.hcat, st);
+  CUDA_TRY(cudaMemsetAsync(T.ghcat, 0, M * K0 * 4, st));
+  head_backward(m, T, (int)M, m->raw.head[1], "", "", "", T.hcat, nullptr, 0, nullptr, T.orot, st);      // raw eps_rot_net output (M, 3)
+  LossBwdArgs lb{};
+  lb.N = N; lb.L = L; lb.abdock = la.abdock; lb.pred_x0 = la.pred_x0; lb.has_prmsd = la.has_prmsd; lb.bins = m->cfg.has_prmsd ? m->cfg.prmsd_bins : 1;
+  lb.dmin = la.dmin; lb.dmax = la.dmax;
+  for (int k = 0; k < 5; ++k) lb.lw[k] = loss_weights ? loss_weights[k] : 1.f;
+  lb.v_0 = v_0; lb.p_0_ang = p_0; lb.s_0 = (const long long*)s_0; lb.p_noisy_ang = p_noisy; lb.s_noisy = s_noisy; lb.z = la.z;
+  lb.R = w.Rbuf; lb.R_pred = w.R_next; lb.eps_pos = w.eps_pos; lb.c_den = w.c_den; lb.o_rot = T.orot; lb.ld_orot = 3;
+  lb.prmsd_logits = w.prmsd_logits; lb.mask_gen = mask_generate; lb.mask_res = mask_res; lb.tvec = (const long long*)t; lb.rows = rows;
+  lb.stats = T.stats; lb.glog = T.glogit; lb.GO = T.GO; lb.GP = m->cfg.has_prmsd ? T.GP : nullptr;
+  launch_loss_bwd(lb, m->diff, st);
+  const char* hn[3] = {"eps_net.eps_crd_net.", "eps_net.eps_rot_net.", "eps_net.eps_seq_net."};
+  const int hoff[3] = {0, 3, 6};
+  for (int hh = 0; hh < 3; ++hh)
+    head_backward(m, T, (int)M, m->raw.head[hh], std::string(hn[hh]) + "0", std::string(hn[hh]) + "2", std::string(hn[hh]) + "4", T.hcat,
+                  T.GO + hoff[hh], 26, T.ghcat, nullptr, st);
+  if (m->cfg.has_prmsd) {                                          // pRMSD head: LayerNorm(131) -> three linears, mean over all L rows
+    const std::string p = "eps_net.prmsd_predictor.";
+    bwd_ln131_fwd((int)M, T.hcat, m->raw.prm_g, m->raw.prm_b, T.lnb, st);
+    CUDA_TRY(cudaMemsetAsync(T.gcat, 0, M * K0 * 4, st));           // gcat doubles as d loss / d LayerNorm output here
+    head_backward(m, T, (int)M, m->raw.head[3], p + "linear_1", p + "linear_2", p + "linear_3", T.lnb, T.GP, lb.bins, T.gcat, nullptr, st);
+    bwd_colsum((int)M, K0, T.gcat, K0, nullptr, 0, grad_of(m, p + "layer_norm.beta"), T.scr, st, 1.f);
+    bwd_ln131_bwd((int)M, T.gcat, T.hcat, m->raw.prm_g, T.ghcat, T.lnb, st);
+    bwd_colsum((int)M, K0, T.lnb, K0, nullptr, 0, grad_of(m, p + "layer_norm.gamma"), T.scr, st, 1.f);
+  }
+  strided_copy_kernel<<<(unsigned)((M * F + 255) / 256), 256, 0, st>>>((int)M, F, T.ghcat, K0, T.gx, F);
+  // ---- encoder, last block first
+  for (int l = nl - 1; l >= 0; --l) {
+    rc = block_backward(m, T, l, N, L, w.Rbuf, w.pnorm, T.xs + (size_t)l * M * F, pair_feat, mask_res, T.gx, d_pair_feat, l != nl - 1, st);
+    if (rc) return rc;
+  }
+  // ---- mixer and sequence embedding (dpm_full.py:86-88)
+  bwd_mixer_cat((int)M, res_feat, s_noisy, m->eps.emb, T.cat0, st);
+  bwd_gemm_nt((int)M, F, 2 * F, T.cat0, 2 * F, false, m->raw.Wm0, 2 * F, m->raw.bm0, T.a0, F, st);          // m_a
+  bwd_wgrad((int)M, F, F, T.gx, F, T.a0, F, true, grad_of(m, "eps_net.res_feat_mixer.2.weight"), T.scr, T.scr_floats, st);
+  bwd_colsum((int)M, F, T.gx, F, nullptr, 0, grad_of(m, "eps_net.res_feat_mixer.2.bias"), T.scr, st, 1.f);
+  bwd_gemm_nn((int)M, F, F, T.gx, F, m->raw.Wm2, F, T.t1, F, false, st);
+  bwd_relu(M * F, T.t1, T.a0, st);
+  bwd_wgrad((int)M, F, 2 * F, T.t1, F, T.cat0, 2 * F, false, grad_of(m, "eps_net.res_feat_mixer.0.weight"), T.scr, T.scr_floats, st);
+  bwd_colsum((int)M, F, T.t1, F, nullptr, 0, grad_of(m, "eps_net.res_feat_mixer.0.bias"), T.scr, st, 1.f);
+  bwd_gemm_nn((int)M, F, 2 * F, T.t1, F, m->raw.Wm0, 2 * F, T.gcat, 2 * F, false, st);
+  strided_copy_kernel<<<(unsigned)((M * F + 255) / 256), 256, 0, st>>>((int)M, F, T.gcat, 2 * F, d_res_feat, F);
+  bwd_embed_grad((int)M, s_noisy, T.gcat, grad_of(m, "eps_net.current_sequence_embedding.weight"), st);
+  CHECK_LAUNCH();
   return ABOPT_OK;
 }

@@ -119,9 +119,10 @@ __device__ __forceinline__ Mat3 so3_exp(float x, float y, float z) {
 
 // Log map, op-for-op as the reference under no_grad (modules/common/so3.py:10-30): the
 // sqrt(1 - cos^2) / acos formulation is kept on purpose (ill-conditioned near pi, SURVEY finding 4).
-__device__ __forceinline__ void so3_log(const Mat3& R, float& x, float& y, float& z) {
+// `lo`: the cosine clamp, -1 under torch.no_grad() (sampling, validation) and -0.999 with autograd enabled (training), so3.py:12-17.
+__device__ __forceinline__ void so3_log(const Mat3& R, float& x, float& y, float& z, float lo = -1.f) {
   const float tr = R.m[0] + R.m[4] + R.m[8];
-  const float cos_t = fmaxf((tr - 1.f) / 2.f, -1.f);
+  const float cos_t = fmaxf((tr - 1.f) / 2.f, lo);
   const float sin_t = sqrtf(1.f - cos_t * cos_t);
   const float theta = acosf(cos_t);
   const float coef = (theta + 1e-8f) / (2.f * sin_t + 2e-8f);

@@ -80,14 +80,14 @@ __device__ __forceinline__ float sample_angle(const DiffW& dw, int tab, int t, i
 
 // e = normalize(u) * theta  (so3.py:141-146);  returns log( exp(e) * exp(base) )
 __device__ __forceinline__ void compose_noise_rotation(float ux, float uy, float uz, float theta, bool add_noise,
-                                                       float bx, float by, float bz, float& ox, float& oy, float& oz) {
+                                                       float bx, float by, float bz, float& ox, float& oy, float& oz, float lo = -1.f) {
   const float n = fmaxf(sqrtf(ux * ux + uy * uy + uz * uz), 1e-12f);     // F.normalize eps
   float ex = ux / n * theta, ey = uy / n * theta, ez = uz / n * theta;
   if (!add_noise) { ex = 0.f; ey = 0.f; ez = 0.f; }                        // transition.py:149-153
   const Mat3 E = so3_exp(ex, ey, ez);
   const Mat3 B = so3_exp(bx, by, bz);
   const Mat3 Rn = matmul3(E, B);
-  so3_log(Rn, ox, oy, oz);
+  so3_log(Rn, ox, oy, oz, lo);
 }
 
 // ---------------------------------------------------------------- categorical posterior + sample
@@ -342,7 +342,8 @@ init_kernel(InitArgs a, DiffW dw) {
       const float c0 = sqrtf(ab), c1 = sqrtf(add_(1.f, -ab));
       const float theta = sample_angle(dw, 0, t, parity ? a.add.bin_idx[r] : 0, ucdf, unif, gauss, parity);
       float nv[3];                                   // transition.py:120-144: log( exp(e) exp(c0 v_0) )
-      compose_noise_rotation(u[0], u[1], u[2], theta, true, mul_(c0r, v[0]), mul_(c0r, v[1]), mul_(c0r, v[2]), nv[0], nv[1], nv[2]);
+      compose_noise_rotation(u[0], u[1], u[2], theta, true, mul_(c0r, v[0]), mul_(c0r, v[1]), mul_(c0r, v[2]), nv[0], nv[1], nv[2],
+                             a.grad_clamp ? -0.999f : -1.f);
       v[0] = nv[0]; v[1] = nv[1]; v[2] = nv[2];
 #pragma unroll
       for (int i = 0; i < 3; ++i) p[i] = add_(mul_(c0, p[i]), mul_(c1, z[i]));     // transition.py:62-78

@@ -36,6 +36,7 @@ struct InitArgs {
   const long long* tvec;        // (N,) steps; nullptr -> T0 for every complex
   int seq_all_rows;             // 1: _sample(c_t) also where nothing is generated (transition.py:198-199)
   float* z_out;                 // (M,3) the position noise e_rand (transition.py:74), may be nullptr
+  int grad_clamp;               // 1: log_rotation as evaluated with autograd enabled (cosine clamped at -0.999, so3.py:12-17)
 };
 // FullDPM.forward losses (dpm_full.py:156-234; AbDesign :138-190)
 struct LossArgs {
@@ -132,5 +133,59 @@ void launch_pos(int M, int L, int mode, const float* p_t, const float* other, co
                 const float* z_pos, const DiffW& dw, float* out, cudaStream_t st);
 void launch_seq_denoise(int M, int L, const long long* s_t, const float* c0, const uint8_t* mask_gen, const long long* tvec,
                         const float* expo_seq, const DiffW& dw, float* post, long long* s_out, cudaStream_t st);
+
+// ---- k_backward.cu: the backward pass of the training step (fp32 CUDA-core GEMMs + row / pair kernels)
+cudaError_t backward_kernels_init();
+void bwd_gemm_nt(int M, int N, int K, const float* x, int ldx, bool relu_x, const float* W, int ldw, const float* bias, float* y, int ldy,
+                 cudaStream_t st);
+void bwd_gemm_nn(int M, int N, int K, const float* g, int ldg, const float* W, int ldw, float* dx, int lddx, bool accumulate, cudaStream_t st);
+void bwd_wgrad(int M, int N, int K, const float* g, int ldg, const float* x, int ldx, bool relu_x, float* dW, float* scratch,
+               size_t scratch_floats, cudaStream_t st);
+void bwd_colsum(int M, int K, const float* A, int lda, const float* B, int ldb, float* out, float* scratch, cudaStream_t st, float scale);
+void bwd_add_ln_fwd(int M, const float* a, const float* b, const uint8_t* mask, const float* gamma, const float* beta, float* s_out,
+                    float* h_out, cudaStream_t st);
+void bwd_ln(int M, const float* g, const float* g2, const float* s, const float* gamma, float* ds, float* gxh, float* gsum, cudaStream_t st);
+void bwd_relu(size_t n, float* g, const float* a, cudaStream_t st);
+void bwd_add_mask(int M, int K, const float* a, const float* b, const uint8_t* mask, float* out, cudaStream_t st);
+void bwd_points_global(int M, const float* Pm, const float* R, const float* t, float* PG, cudaStream_t st);
+void bwd_aggregate(int M, const float* gfeat, const float* feat, const float* R, float* g_agg, cudaStream_t st);
+struct PairBwdArgs {
+  int N, L, Lp;
+  const float* z; const float* alpha; const uint8_t* mask;
+  const float* gfeat;            // (M, 1824): cols 0..767 = g_p2n, 768..1151 = g_node
+  const float* g_agg;            // (M, 288)
+  const float* Pm;               // (M, 2016) plain projections (q | k | v | local points)
+  const float* PG;               // (M, 864) global points q | k | v
+  const float* R;                // (M, 9)
+  const float* Wb;               // [12][64] proj_pair_bias.weight
+  const float* coef;             // [12]
+  float* g_log;                  // [N][H][L][Lp]
+  float* G;                      // (M, 2016) gradient of the plain projections
+  float* dz; int dz_accumulate;  // (N, L, L, 64)
+  float* part;                   // (M, 780): per-row partial d W_b (768) | d coef (12)
+};
+void launch_pair_bwd(const PairBwdArgs& a, cudaStream_t st);
+void bwd_mixer_cat(int M, const float* res_feat, const long long* s_t, const float* emb, float* cat0, cudaStream_t st);
+void bwd_heads_cat(int M, int L, const float* x, const float* beta, float* hcat, cudaStream_t st);
+void bwd_embed_grad(int M, const long long* s_t, const float* g_cat, float* dE, cudaStream_t st);
+void bwd_ln131_fwd(int M, const float* h, const float* gamma, const float* beta, float* out, cudaStream_t st);
+void bwd_ln131_bwd(int M, const float* g, const float* h, const float* gamma, float* dh_acc, float* gxh, cudaStream_t st);
+struct LossBwdArgs {
+  int N, L, abdock, pred_x0, has_prmsd, bins;
+  float dmin, dmax;
+  float lw[5];                   // loss weights: rot, pos, seq, prmsd, dist
+  const float* v_0; const float* p_0_ang; const long long* s_0;
+  const float* p_noisy_ang; const long long* s_noisy; const float* z;
+  const float* R; const float* R_pred; const float* eps_pos; const float* c_den;
+  const float* o_rot; int ld_orot;          // raw output of eps_rot_net (M, 3)
+  const float* prmsd_logits;
+  const uint8_t* mask_gen; const uint8_t* mask_res; const long long* tvec;
+  const float* rows;             // [6][M] per-residue terms written by the forward loss kernel
+  float* stats;                  // [4]: n_gen + 1e-8 | dist count | sum mask_generate[:, 0] + 1e-10
+  float* glog;                   // (N, bins) d prmsd loss / d logits / L
+  float* GO;                     // (M, 26): d loss / d (eps_crd_net | eps_rot_net | eps_seq_net) outputs
+  float* GP;                     // (M, bins) d loss / d prmsd head rows (may be null)
+};
+void launch_loss_bwd(const LossBwdArgs& a, const DiffW& dw, cudaStream_t st);
 
 }  // namespace abopt

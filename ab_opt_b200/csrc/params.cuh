@@ -21,6 +21,8 @@ struct BlockW {
   const float* Wmlp;       // [3 * 128][128]  mlp_transition.{0,2,4}.weight stacked as stored by nn.Linear (K-major B operands)
   const float* Wmlp_lo;    // [3 * 128][128]  tf32 lo plane
   const float* ln2_g; const float* ln2_b;
+  const float* Wb_raw;     // [12][64]     proj_pair_bias.weight as stored (backward pass)
+  const float* sc_raw;     // [12]         spatial_coef as stored (backward pass: sigmoid)
 };
 
 // pair-bias weight + spatial coefficients as BY-VALUE kernel parameters: they land in the constant

@@ -158,13 +158,21 @@ class FullDPM(_native.NativeOwner, nn.Module):
 
     def forward(self, v_0, p_0, s_0, res_feat, pair_feat, mask_generate, mask_res, denoise_structure, denoise_sequence,
                 t=None, noise=None, rng=None):
-        _native.forbid_training_graph(self, 'FullDPM.forward')
-        with torch.no_grad():
-            return self._loss_forward(v_0, p_0, s_0, res_feat, pair_feat, mask_generate, mask_res, denoise_structure,
-                                      denoise_sequence, t, noise, rng)
+        """dpm_full.py:156-234 (AbDesign :138-190).  Under torch.no_grad() (validate(), AbDock/train.py:141-149): the loss
+        dict, values only.  With autograd enabled (train(), train.py:104-113): the same dict carrying a graph -- one
+        autograd node whose backward is the hand-written sm_100a backward pass (abopt_loss_backward): `loss.backward()`
+        fills .grad of every parameter and flows into res_feat / pair_feat."""
+        needs_graph = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or res_feat.requires_grad
+                                                   or pair_feat.requires_grad)
+        if not needs_graph:
+            with torch.no_grad():
+                return self._loss_forward(v_0, p_0, s_0, res_feat, pair_feat, mask_generate, mask_res, denoise_structure,
+                                          denoise_sequence, t, noise, rng)
+        return self._train_forward(v_0, p_0, s_0, res_feat, pair_feat, mask_generate, mask_res, denoise_structure, denoise_sequence,
+                                   t, noise, rng)
 
     def _loss_forward(self, v_0, p_0, s_0, res_feat, pair_feat, mask_generate, mask_res, denoise_structure, denoise_sequence,
-                      t=None, noise=None, rng=None):
+                      t=None, noise=None, rng=None, _prepared=None):
         """dpm_full.py:156-234 (AbDesign :138-190): the loss dict of one training step, FORWARD ONLY -- the values are
         computed by the sm_100a kernels (abopt_loss_forward) and carry no autograd graph; the backward pass is not part
         of the native path yet.  `noise` (dict of the six draws of one step) replays given draws; otherwise rng='torch'
@@ -205,11 +213,18 @@ class FullDPM(_native.NativeOwner, nn.Module):
             nz = ctypes.byref(_capi.StepNoise(*[keep[k].data_ptr() for k in ('u', 'expo_ang', 'unif_ang', 'gauss_ang', 'z_pos', 'expo_seq')]))
         else:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        if _prepared is not None:          # the training path: hand the prepared call to the caller
+            _prepared.update(nm=nm, N=N, L=L, v_0=v_0, p_0=p_0, s_0=s_0, res_feat=res_feat, pair_feat=pair_feat, mg=mg, mr=mr, flags=flags,
+                             t=t, seed=seed, keep=keep, dev=dev)
+            return None
         out = torch.zeros(5, device=dev)
         _capi.check(_capi.lib().abopt_loss_forward(
             nm.handle, N, L, _capi.ptr(v_0), _capi.ptr(p_0), _capi.ptr(s_0), _capi.ptr(res_feat), _capi.ptr(pair_feat),
             _capi.ptr(mg), _capi.ptr(mr), flags, _capi.ptr(t), seed, nz, _capi.ptr(out), _capi.stream_ptr(dev)))
         del keep
+        return self._loss_dict(out)
+
+    def _loss_dict(self, out):
         loss = {}
         if self.flavour == 'abdock':
             loss['prmsd'] = out[3]
@@ -217,6 +232,59 @@ class FullDPM(_native.NativeOwner, nn.Module):
                 loss['dist'] = out[4]
         loss['rot'], loss['pos'], loss['seq'] = out[0], out[1], out[2]
         return loss
+
+    # ---------------------------------------------------------------- training step
+    def _noise_struct(self, prep):
+        keep = prep['keep']
+        if keep is None:
+            return None
+        return ctypes.byref(_capi.StepNoise(*[keep[k].data_ptr() for k in ('u', 'expo_ang', 'unif_ang', 'gauss_ang', 'z_pos', 'expo_seq')]))
+
+    def _trainable(self):
+        """[(FullDPM state-dict key, parameter)] of the parameters the backward pass produces gradients for."""
+        return [(k, p) for k, p in self.named_parameters()]
+
+    @torch.no_grad()
+    def loss_and_grads(self, v_0, p_0, s_0, res_feat, pair_feat, mask_generate, mask_res, denoise_structure, denoise_sequence,
+                       t=None, noise=None, rng=None, loss_weights=None):
+        """One training step's forward AND backward in one call into the library (abopt_loss_backward): returns
+        (loss dict, {state-dict key: gradient of sum_k w_k loss_k}, d / d res_feat, d / d pair_feat).  loss_weights: dict by
+        loss name (configs/train/*.yml loss_weights), default all 1."""
+        prep = {}
+        self._loss_forward(v_0, p_0, s_0, res_feat, pair_feat, mask_generate, mask_res, denoise_structure, denoise_sequence, t, noise,
+                           rng, _prepared=prep)
+        return self._backward_call(prep, loss_weights)
+
+    def _backward_call(self, prep, loss_weights=None, want_param_grads=True):
+        nm, N, L, dev = prep['nm'], prep['N'], prep['L'], prep['dev']
+        order = ('rot', 'pos', 'seq', 'prmsd', 'dist')
+        lw = (ctypes.c_float * 5)(*[float((loss_weights or {}).get(k, 1.0)) for k in order])
+        out = torch.zeros(5, device=dev)
+        d_res, d_pair = torch.empty_like(prep['res_feat']), torch.empty_like(prep['pair_feat'])
+        st = _capi.stream_ptr(dev)
+        _capi.check(_capi.lib().abopt_loss_backward(
+            nm.handle, N, L, _capi.ptr(prep['v_0']), _capi.ptr(prep['p_0']), _capi.ptr(prep['s_0']), _capi.ptr(prep['res_feat']),
+            _capi.ptr(prep['pair_feat']), _capi.ptr(prep['mg']), _capi.ptr(prep['mr']), prep['flags'], _capi.ptr(prep['t']), prep['seed'],
+            self._noise_struct(prep), lw, _capi.ptr(out), _capi.ptr(d_res), _capi.ptr(d_pair), st))
+        grads = {}
+        if want_param_grads:
+            for k, p in self._trainable():
+                g = torch.empty(p.numel(), device=dev)
+                _capi.check(_capi.lib().abopt_model_get_grad(nm.handle, k.encode(), _capi.ptr(g), p.numel(), st))
+                grads[k] = g.view(p.shape)
+        return self._loss_dict(out), grads, d_res, d_pair
+
+    def _train_forward(self, v_0, p_0, s_0, res_feat, pair_feat, mask_generate, mask_res, denoise_structure, denoise_sequence, t, noise, rng):
+        prep = {}
+        with torch.no_grad():
+            self._loss_forward(v_0, p_0, s_0, res_feat, pair_feat, mask_generate, mask_res, denoise_structure, denoise_sequence, t, noise,
+                               rng, _prepared=prep)
+        prep['flags'] |= _capi.GRAD_SEMANTICS
+        params = [p for _, p in self._trainable()]
+        outs = _TrainStep.apply(self, prep, res_feat, pair_feat, *params)
+        names = ('rot', 'pos', 'seq', 'prmsd', 'dist')
+        have = self._loss_dict(torch.zeros(5))
+        return {k: outs[i] for i, k in enumerate(names) if k in have}
 
     # ---------------------------------------------------------------- sampling
     @torch.no_grad()
@@ -389,6 +457,32 @@ class FullDPM(_native.NativeOwner, nn.Module):
             last += [hpr[0], hpl[0]] if not optimize else [tpr[0], tpl[0]]
         traj[0] = last if (abdock and not optimize) else tuple(last)
         return traj
+
+
+class _TrainStep(torch.autograd.Function):
+    """FullDPM.forward as one autograd node.  forward: the loss dict, evaluated as the reference evaluates it with autograd
+    enabled (abopt_loss_forward + ABOPT_GRAD_SEMANTICS).  backward: abopt_loss_backward with the incoming gradients of the five
+    losses as loss weights (so any weighted sum of the dict differentiates correctly); it recomputes the forward from the saved
+    inputs and replays the same noise (Philox seed, or the drawn tensors in parity mode)."""
+
+    @staticmethod
+    def forward(ctx, model, prep, res_feat, pair_feat, *params):
+        out = torch.zeros(5, device=prep['dev'])
+        _capi.check(_capi.lib().abopt_loss_forward(
+            prep['nm'].handle, prep['N'], prep['L'], _capi.ptr(prep['v_0']), _capi.ptr(prep['p_0']), _capi.ptr(prep['s_0']),
+            _capi.ptr(prep['res_feat']), _capi.ptr(prep['pair_feat']), _capi.ptr(prep['mg']), _capi.ptr(prep['mr']), prep['flags'],
+            _capi.ptr(prep['t']), prep['seed'], model._noise_struct(prep), _capi.ptr(out), _capi.stream_ptr(prep['dev'])))
+        ctx.model, ctx.prep = model, prep
+        return tuple(out[i] for i in range(5))
+
+    @staticmethod
+    def backward(ctx, *g):
+        model, prep = ctx.model, ctx.prep
+        w = torch.stack([x if x is not None else torch.zeros((), device=prep['dev']) for x in g]).float().cpu().tolist()
+        names = ('rot', 'pos', 'seq', 'prmsd', 'dist')
+        _, grads, d_res, d_pair = model._backward_call(prep, {k: w[i] for i, k in enumerate(names)})
+        pg = [grads[k] for k, _ in model._trainable()]
+        return (None, None, d_res, d_pair, *pg)
 
 
 class FullDPMAbDesign(FullDPM):

@@ -106,3 +106,23 @@ class GAEncoder(_native.NativeOwner, nn.Module):
                                                     _capi.ptr(z), _capi.ptr(mask), _capi.ptr(alpha), _capi.ptr(feat),
                                                     _capi.stream_ptr(x.device)))
         return alpha, feat
+
+    @torch.no_grad()
+    def block_backward(self, layer, R, t, x, z, mask, g_out):
+        """Backward of one GABlock (ga.py:149-178 under autograd; csrc/k_backward.cu): g_out = d loss / d block output ->
+        (d loss / d x, d loss / d z, {state-dict key of the block: gradient})."""
+        nm = self.native()
+        R, t, x, z, mask, N, L = _prep(R, t, x, z, mask)
+        g_out = _capi.cuda_f32(g_out, 'g_out')
+        g_x, g_z = torch.empty_like(x), torch.empty_like(z)
+        st = _capi.stream_ptr(x.device)
+        _capi.check(_capi.lib().abopt_ga_block_backward(nm.handle, layer, N, L, _capi.ptr(R), _capi.ptr(t), _capi.ptr(x), _capi.ptr(z),
+                                                        _capi.ptr(mask), _capi.ptr(g_out), _capi.ptr(g_x), _capi.ptr(g_z), st))
+        grads = {}
+        pre = f'blocks.{layer}.'
+        for k, v in self.state_dict().items():
+            if k.startswith(pre):
+                g = torch.empty(v.numel(), device=x.device)
+                _capi.check(_capi.lib().abopt_model_get_grad(nm.handle, ('eps_net.encoder.' + k).encode(), _capi.ptr(g), v.numel(), st))
+                grads[k] = g.view(v.shape)
+        return g_x, g_z, grads

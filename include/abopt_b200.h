@@ -69,6 +69,7 @@ typedef struct abopt_config {
 #define ABOPT_SAMPLE_STRUCTURE   1u   /* sample_structure=True                               */
 #define ABOPT_SAMPLE_SEQUENCE    2u   /* sample_sequence=True                                */
 #define ABOPT_KEEP_TRAJECTORY    4u   /* fill every trajectory slot (else only slot 0 and T0) */
+#define ABOPT_GRAD_SEMANTICS     8u   /* abopt_loss_forward: evaluate as with autograd enabled (log_rotation clamp -0.999) */
 
 /* Per-step noise for replayed ("parity") runs; every pointer is a DEVICE pointer holding the
  * draw the reference makes at that point (RNG draw order):
@@ -246,6 +247,27 @@ int abopt_loss_forward(abopt_model* m, int N, int L, const float* v_0, const flo
                        const float* res_feat, const float* pair_feat, const uint8_t* mask_generate,
                        const uint8_t* mask_res, uint32_t flags, const int64_t* t, uint64_t seed,
                        const abopt_step_noise* noise, float* losses_out, void* stream);
+
+/* ------------------------------------------------------------------ training step: forward + backward
+ * One iteration of AbDock/train.py:104-113 (AbDesign/train.py likewise) up to the optimiser: loss_dict = model(batch); loss =
+ * sum_k w_k loss_k; loss.backward().  The reference differentiates FullDPM.forward (dpm_full.py:156-234) with torch autograd; here
+ * the backward pass is written out (csrc/k_backward.cu), recompute-based: only the inputs of the GABlocks are kept.  The forward
+ * is evaluated as the reference evaluates it WITH autograd enabled (log_rotation clamps the cosine at -0.999, so3.py:12-17), so
+ * losses_out may differ from abopt_loss_forward (the torch.no_grad() evaluation) on rotations within 0.045 rad of pi.
+ *   loss_weights  HOST pointer to 5 floats (rot, pos, seq, prmsd, dist; configs/train/*.yml loss_weights) or NULL (all 1)
+ *   losses_out    DEVICE, 5 floats, the unweighted loss dict as abopt_loss_forward
+ *   d_res_feat (N,L,128), d_pair_feat (N,L,L,64)   DEVICE, d loss / d inputs (they come from trainable embeddings)
+ * Parameter gradients stay inside the handle (overwritten by every call); abopt_model_get_grad copies the one of a state-dict key
+ * (same keys as abopt_model_set_tensor; buffers have none) to `dst` (DEVICE, `numel` floats).  Other arguments as abopt_loss_forward.
+ * abopt_ga_block_backward is the same for one GABlock (ga.py:149-178): g_out = d loss / d block output -> g_x, g_z (+ the block's
+ * parameter gradients in the handle). */
+int abopt_loss_backward(abopt_model* m, int N, int L, const float* v_0, const float* p_0, const int64_t* s_0,
+                        const float* res_feat, const float* pair_feat, const uint8_t* mask_generate, const uint8_t* mask_res,
+                        uint32_t flags, const int64_t* t, uint64_t seed, const abopt_step_noise* noise, const float* loss_weights,
+                        float* losses_out, float* d_res_feat, float* d_pair_feat, void* stream);
+int abopt_model_get_grad(abopt_model* m, const char* key, float* dst, size_t numel, void* stream);
+int abopt_ga_block_backward(abopt_model* m, int layer, int N, int L, const float* R, const float* t, const float* x,
+                            const float* z, const uint8_t* mask, const float* g_out, float* g_x, float* g_z, void* stream);
 
 /* ------------------------------------------------------------------ pair featurisation (the step before the loop)
  * PairEmbedding, modules/encoders/pair.py:10-101 (AbDesign: diffab/modules/encoders/pair.py, same lines), including
