@@ -21,12 +21,15 @@ __all__ = ['GABlock', 'GAEncoder', 'PairEmbedding', 'ResidueEmbedding', 'reconst
            'launch_count', 'install_into_reference']
 
 
-def install_into_reference(package='src', fused=True):
+def install_into_reference(package='src', fused=True, embeddings=True):
     """Swap the reference's hot-path classes for the B200 ones so that its entry points
     (dock_pdb.py / design_pdb.py, configs/*.yml, checkpoints) run unchanged.
 
     package = 'src' (AbDock) or 'diffab' (AbDesign); the reference package must be importable.
     Must be called before the reference's `models/diffab.py` is imported.
+    embeddings=False keeps the reference's own PairEmbedding / ResidueEmbedding (torch autograd): the configuration for
+    train.py -- FullDPM.forward differentiates on the sm_100a path and hands d res_feat / d pair_feat to autograd, the embeddings'
+    own backward is not part of the library (and fused is then off: the fused class contains the B200 embeddings).
     fused=True additionally registers ab_opt_b200.DiffusionAntibodyDesign under the reference's model name 'diffab'
     (models/_base.py:4-13), so `get_model(cfg.model).sample(batch)` is one device-resident encode + sample call.
     """
@@ -37,8 +40,11 @@ def install_into_reference(package='src', fused=True):
     dpm.EpsilonNet = EpsilonNet
     ga.GAEncoder = GAEncoder
     ga.GABlock = GABlock
-    importlib.import_module(f'{package}.modules.encoders.pair').PairEmbedding = PairEmbedding      # models/diffab.py:28
-    importlib.import_module(f'{package}.modules.encoders.residue').ResidueEmbedding = ResidueEmbedding  # models/diffab.py:27
+    if embeddings:
+        importlib.import_module(f'{package}.modules.encoders.pair').PairEmbedding = PairEmbedding      # models/diffab.py:28
+        importlib.import_module(f'{package}.modules.encoders.residue').ResidueEmbedding = ResidueEmbedding  # models/diffab.py:27
+    else:
+        fused = False
     # after the loop: geometry.reconstruct_backbone_partially with the reference's own ideal-backbone tables; the ranking helpers
     # live in a runner module that needs lmdb / BioPython, so they are rebound only where that module imports
     K = importlib.import_module(f'{package}.utils.protein.constants')

@@ -40,8 +40,8 @@ CONFIGS = {
                gen=((20, 30), (50, 60), (95, 105), (160, 170), (190, 200), (230, 240)), flavour='abdesign',
                sample_structure=True, sample_sequence=True, obj='pred_noise'),
 }
-# c5: SURVEY.md 8d config 5, FORWARD ONLY (FullDPM.forward losses on the CUDA path; the backward pass is not implemented)
-TRAIN_CFG = dict(name='C5 AbDesign train.py FullDPM.forward (losses only, no backward)', B=128, L=256, gen=((120, 136),),
+# c5: SURVEY.md 8d config 5: one training iteration (forward + backward) on the CUDA path
+TRAIN_CFG = dict(name='C5 AbDesign train.py FullDPM.forward + backward', B=128, L=256, gen=((120, 136),),
                  flavour='abdesign', obj='pred_noise')
 NUM_LAYERS, T_STEPS = 6, 100
 
@@ -451,8 +451,10 @@ def run_ours(args, cfg, rank, world, local_rank):
 
 
 def run_train_forward(args):
-    """--config c5: ms per FullDPM.forward call (add_noise, one EpsilonNet evaluation, loss reductions; no autograd) and
-    residues/s = B * L / time, as SURVEY.md 8d defines config 5.  One GPU, not a bench line of the headline metric."""
+    """--config c5: BASELINE config 5, `AbDesign train.py forward+backward EpsilonNet step, batch=128, N=256`: one training
+    iteration up to the optimiser -- FullDPM.forward and loss.backward() (abopt_loss_backward: forward, hand-written backward,
+    gradients of all parameters and of res_feat / pair_feat) -- and the forward alone (validate()).  residues/s = B * L / time.
+    One GPU, not a bench line of the headline metric."""
     cfg = TRAIN_CFG
     dev = torch.device('cuda', 0)
     model = build_model(cfg, dev)
@@ -460,28 +462,51 @@ def run_train_forward(args):
     B, L = cfg['B'], cfg['L']
     t = torch.randint(1, T_STEPS, (B,), device=dev)
     a = (inp['v'], inp['p'], inp['s'], inp['res_feat'], inp['pair_feat'], inp['mask_generate'], inp['mask_res'], True, True)
-    for _ in range(2 + args.warmup):
-        loss = model(*a, t=t)
-    torch.cuda.synchronize()
+    steps = max(args.steps, 5)
+
+    def timed(fn):
+        for _ in range(2 + args.warmup):
+            out = fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, out
     clocks = ClockSampler(0)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(max(args.steps, 10)):
-        loss = model(*a, t=t)
-    e1.record()
+    with torch.no_grad():
+        ms_fwd, loss = timed(lambda: model(*a, t=t))
+    ms_step, (loss_b, grads, d_res, d_pair) = timed(lambda: model.loss_and_grads(*a, t=t))
+    ck = clocks.stop()
+    assert all(torch.isfinite(v) for v in loss_b.values()) and torch.isfinite(d_pair).all()
+    assert all(torch.isfinite(g).all() for g in grads.values())
+    from ab_opt_b200 import _capi
+    _capi.profile_enable(True)
+    model.loss_and_grads(*a, t=t)
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / max(args.steps, 10)
-    assert all(torch.isfinite(v) for v in loss.values())
+    prof = _capi.profile_collect()
+    _capi.profile_enable(False)
     peak, peak_src = measured_peak_gbs()
-    alg = B * NUM_LAYERS * algorithmic_bytes_per_complex_layer(L)
-    print(json.dumps({'metric': 'training forward residues/sec (FullDPM.forward, losses only)', 'value': B * L / (ms / 1e3),
-                      'unit': 'residues/s', 'n_gpus': 1, 'steps': max(args.steps, 10), 'warmup': args.warmup, 'ms_per_step': ms,
+    alg_f = B * NUM_LAYERS * algorithmic_bytes_per_complex_layer(L)
+    # backward: z is read once more per layer by the recompute and once by the pair backward, d z is written (first layer) or
+    # read + written (the others): (2 + 2 - 1/6) z-passes on top of the forward's one
+    zl = B * L * L * 64 * 4
+    alg_b = alg_f + NUM_LAYERS * 3 * zl + (NUM_LAYERS - 1) * zl
+    print(json.dumps({'metric': 'training step residues/sec (FullDPM.forward + backward)', 'value': B * L / (ms_step / 1e3),
+                      'unit': 'residues/s', 'n_gpus': 1, 'steps': steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
                       'higher_is_better': True, 'dtype': 'f32', 'data': 'synthetic',
-                      'config': {'workload': f"{cfg['name']}: B={B}, L={L}, n_gen=16, {NUM_LAYERS} IPA layers", 'backward': 'not implemented'},
-                      'losses': {k: float(v) for k, v in loss.items()}, 'clocks': clocks.stop(),
-                      'roofline': {'bound': 'hbm', 'achieved': alg / (ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
-                                   'frac': alg / (ms * 1e-3) / 1e9 / peak, 'peak_source': peak_src,
-                                   'note': 'whole forward against SURVEY 8d algorithmic bytes (z once per layer + node state)'}}), flush=True)
+                      'config': {'workload': f"{cfg['name']}: B={B}, L={L}, n_gen=16, {NUM_LAYERS} IPA layers; forward + backward, "
+                                             'gradients of all 63 parameters + d res_feat + d pair_feat', 'l2': 'inputs larger than L2'},
+                      'forward_only_ms': ms_fwd, 'losses': {k: float(v) for k, v in loss_b.items()}, 'clocks': ck,
+                      'grad_norm': float(torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values()))),
+                      'kernel_breakdown_ms': {k: {'ms': round(v[0], 3), 'launches': v[1]} for k, v in prof.items() if v[1]},
+                      'roofline': {'bound': 'hbm', 'achieved': alg_b / (ms_step * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                                   'frac': alg_b / (ms_step * 1e-3) / 1e9 / peak, 'peak_source': peak_src,
+                                   'algorithmic_bytes': alg_b, 'forward_frac': alg_f / (ms_fwd * 1e-3) / 1e9 / peak,
+                                   'note': 'whole step against streaming z: forward once per layer; backward: recompute (1), pair '
+                                           'backward read (1), d z write (1) + read-modify (5/6) per layer'}}), flush=True)
 
 
 def run_pair_embed(args):

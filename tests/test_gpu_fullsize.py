@@ -305,6 +305,7 @@ def test_trained_checkpoint_slice(golden_dir):
 
 
 # ------------------------------------------------------------------------------------------ training forward at C5 size
+@torch.no_grad()      # the validate() evaluation; the grad-enabled step is covered by test_gpu_backward.py
 def test_training_forward_c5_is_the_mean_of_its_halves():
     """FullDPM.forward at B=128, L=256, 6 layers: every loss is a masked mean with the same number of generated residues per
     complex, so the loss of the batch equals the mean of the losses of its two halves (a size-independent property), and a

@@ -365,8 +365,9 @@ def test_training_forward_against_reference_fixture(golden_dir, obj):
     model = build_model(W, g['num_layers'], obj=obj)
     ci = cu(inp)
     noise = {k[len('noise_'):]: v.to(DEV) for k, v in g.items() if k.startswith('noise_')}
-    got = model(ci['v'], ci['p'], ci['s'], ci['res_feat'], ci['pair_feat'], ci['mask_generate'], ci['mask_res'], True, True,
-                t=g['t'].to(DEV), noise=noise)
+    with torch.no_grad():      # the fixture holds the validate() evaluation (torch.no_grad: log_rotation clamps at -1, so3.py:12-17)
+        got = model(ci['v'], ci['p'], ci['s'], ci['res_feat'], ci['pair_feat'], ci['mask_generate'], ci['mask_res'], True, True,
+                    t=g['t'].to(DEV), noise=noise)
     want = {k[len(obj) + 1:]: v for k, v in g.items() if k.startswith(obj + '_')}
     assert sorted(got) == sorted(want)
     for k in want:
@@ -391,18 +392,20 @@ def test_training_forward_vs_oracle(flavour, ds, dq):
     ref64 = training.loss_forward(W64, *a64, to64(noise), flavour=flavour, obj=obj)
     model = build_model(W, 2, flavour=flavour, obj=obj)
     ci = cu(inp)
-    got = model(ci['v'], ci['p'], ci['s'], ci['res_feat'], ci['pair_feat'], ci['mask_generate'], ci['mask_res'], ds, dq,
-                t=t.to(DEV), noise=cu(noise))
+    with torch.no_grad():
+        got = model(ci['v'], ci['p'], ci['s'], ci['res_feat'], ci['pair_feat'], ci['mask_generate'], ci['mask_res'], ds, dq,
+                    t=t.to(DEV), noise=cu(noise))
     assert sorted(got) == sorted(ref32)
     for k in ref32:
         e_got = abs(got[k].double().item() - ref64[k].item())
         e_ref = abs(ref32[k].double().item() - ref64[k].item())
         assert e_got <= 2 * e_ref + 1e-5 * max(1.0, abs(ref64[k].item())), f'{k}: cuda {got[k].item()} oracle64 {ref64[k].item()}'
     # Philox mode: finite, deterministic under torch.manual_seed
-    torch.manual_seed(3)
-    a = model(ci['v'], ci['p'], ci['s'], ci['res_feat'], ci['pair_feat'], ci['mask_generate'], ci['mask_res'], ds, dq, t=t.to(DEV))
-    torch.manual_seed(3)
-    b = model(ci['v'], ci['p'], ci['s'], ci['res_feat'], ci['pair_feat'], ci['mask_generate'], ci['mask_res'], ds, dq, t=t.to(DEV))
+    with torch.no_grad():
+        torch.manual_seed(3)
+        a = model(ci['v'], ci['p'], ci['s'], ci['res_feat'], ci['pair_feat'], ci['mask_generate'], ci['mask_res'], ds, dq, t=t.to(DEV))
+        torch.manual_seed(3)
+        b = model(ci['v'], ci['p'], ci['s'], ci['res_feat'], ci['pair_feat'], ci['mask_generate'], ci['mask_res'], ds, dq, t=t.to(DEV))
     for k in a:
         assert torch.isfinite(a[k]).all() and torch.equal(a[k], b[k])
 
