@@ -68,6 +68,7 @@ struct Workspace {
   int* bin_idx;
   long long* tvec_scratch;
   Focus focus;
+  PairRows prows[2];            // row lists of pair_stream_kernel: [0] every row, [1] focus mode (generated rows)
 };
 
 struct HostIO {       // device staging for abopt_sample_host
@@ -92,6 +93,7 @@ struct abopt_model {
   // layers (z and the weights are loop invariants of the T reverse steps); elsewhere slot 0 is recomputed per block call.
   float* bias_buf = nullptr; size_t bias_slots = 0, bias_slot_floats = 0; bool bias_hoisted = false;
   bool focus_built = false;     // inside abopt_sample_*: the focus lists of mask_generate were built once for the whole run
+  bool prows_built[2] = {false, false};      // likewise the row lists of pair_stream_kernel (mask_res / the focus list are loop invariants)
   EpsW eps;
   DiffW diff;
   Workspace ws;
@@ -571,7 +573,7 @@ static int ensure_workspace(abopt_model* m, int N, int L) {
                oKb = take(M * H * 64 * 4), oKl = take(256), oRq = take(M * H * 4), oRk = take(M * H * 4),
                oVt = take((size_t)N * H * 64 * Lp * 4), oVl = take((size_t)N * H * 64 * Lp * 4),
                oFc = take(M * 4), oFr = take(M * 4), oFw = take((size_t)N * (L / 64 + 2) * 8), oFn = take(64), oFs = take((size_t)N * 8),
-               oFx = take(M * F * 4), oFm = take(M);
+               oFx = take(M * F * 4), oFm = take(M), oPr0 = take(M * 16), oPr1 = take(M * 16), oPrc = take(64);
   CUDA_TRY(cudaMalloc(&w.base, off));
   CUDA_TRY(cudaMemset(w.base, 0, off));        // the padding rows / columns of the packed attention operands must stay zero
   unsigned char* b = static_cast<unsigned char*>(w.base);
@@ -584,6 +586,8 @@ static int ensure_workspace(abopt_model* m, int N, int L) {
   w.op = AttnOperands{(float*)(b + oQa), (float*)(b + oQl), (float*)(b + oKb), (float*)(b + oKl), (float*)(b + oRq), (float*)(b + oRk),
                       (float*)(b + oVt), (float*)(b + oVl)};
   w.focus = Focus{(int*)(b + oFc), (int*)(b + oFr), (int2*)(b + oFw), (int*)(b + oFn), (int*)(b + oFs), (float*)(b + oFx), (uint8_t*)(b + oFm)};
+  w.prows[0] = PairRows{(int4*)(b + oPr0), (int*)(b + oPrc)};
+  w.prows[1] = PairRows{(int4*)(b + oPr1), (int*)(b + oPrc) + 2};
   w.N = N; w.L = L; w.Lp = Lp; w.NB = NB; w.bytes = off;
   return ABOPT_OK;
 }
@@ -647,8 +651,13 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
     // logits (node + spatial + pair bias, scaled, masked) and softmax on the tensor cores -> alpha
     if (!launch_attn_logits_tc(nb, b0, N, L, w.Lp, w.op, bias, mask, w.alpha, st, fc ? fc->windows : nullptr, fc ? fc->count : nullptr))
       return fail(ABOPT_ERR_CUDA, "attn_logits_tc launch failed");
-    if (!launch_pair_stream(nb, b0, L, w.Lp, z, mask, w.alpha, w.feat, st, fc ? fc->cidx : nullptr))
-      return fail(ABOPT_ERR_ARG, "pair_stream_kernel: L too large for shared memory");
+    {
+      const int which = fc ? 1 : 0;
+      if (!m->prows_built[which]) launch_pair_rows_build(nb, b0, L, mask, fc ? fc->cidx : nullptr, w.prows[which], st);
+      if (m->bias_hoisted && nb == N) m->prows_built[which] = true;      // the sampling loop: the masks are loop invariants
+      if (!launch_pair_stream(nb, b0, L, w.Lp, z, w.alpha, w.feat, w.prows[which], st))
+        return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (pair)");
+    }
     if (!launch_aggr_tc(nb, b0, N, L, w.Lp, w.alpha, w.op.VT, w.op.VT_lo, R, t, w.feat, st, fc ? fc->windows : nullptr,
                         fc ? fc->count : nullptr, fc ? fc->cidx : nullptr))
       return fail(ABOPT_ERR_CUDA, "aggr_tc launch failed");
@@ -952,11 +961,13 @@ extern "C" int abopt_sample_device(abopt_model* m, int N, int L, const float* v,
       return fail(ABOPT_ERR_ARG, "pair_bias_kernel: L too large for shared memory");
   m->bias_hoisted = true;
   m->focus_built = false;
+  m->prows_built[0] = m->prows_built[1] = false;
   for (int t = T0; t >= 1 && rc == ABOPT_OK; --t)
     rc = run_step(m, N, L, t, optimize, flags, seed, V(t), Pp(t), S(t), res_feat, pair_feat, mask_generate, mask_res,
                   noise ? &noise[T0 - t] : nullptr, V(t - 1), Pp(t - 1), S(t - 1), PR(t - 1), PL(t - 1), st);
   m->bias_hoisted = false;
   m->focus_built = false;
+  m->prows_built[0] = m->prows_built[1] = false;
   return rc;
 }
 

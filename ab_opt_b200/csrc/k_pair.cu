@@ -29,6 +29,18 @@ __device__ __forceinline__ float2 ffma2(float a, float2 b, float2 c) {
   return *reinterpret_cast<float2*>(&rd);
 }
 
+// the same, not reorderable against the TMA / mbarrier instructions (also volatile): used where an FFMA2 stands for "the
+// shared-memory loads feeding it have completed"
+__device__ __forceinline__ float2 ffma2_ordered(float a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  float2 aa = make_float2(a, a);
+  ra = *reinterpret_cast<unsigned long long*>(&aa);
+  rb = *reinterpret_cast<unsigned long long*>(&b);
+  rc = *reinterpret_cast<unsigned long long*>(&c);
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc) : "memory");
+  return *reinterpret_cast<float2*>(&rd);
+}
+
 __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -140,7 +152,7 @@ pair_bias_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------ pair aggregation
-// pair_stream_kernel: out[b,i,h,c] = sum_j alpha[b,i,j,h] z[b,i,j,c]  (ga.py:114-118), alpha from attn_logits_tc_kernel.
+// pair_stream_kernel: out[b,i,h,c] = sum_j alpha[b,i,j,h] z[b,i,j,c]  (ga.py:114-118), alpha from attn_logits_persist_kernel.
 // One persistent CTA per SM, 12 fully independent warps -- no block barrier anywhere.  Each WARP owns whole query rows
 // (b, i) and streams its row block z[b,i,:,:] through a private 3-stage shared-memory ring in chunks of 16 key residues:
 //   lane 0     producer: per chunk one 1-D bulk copy of z (4 KB contiguous, L2 evict-first) + one 3-D tensor-map box of
@@ -151,32 +163,70 @@ pair_bias_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant
 //              (scalar alpha x channel pair, 96 accumulators per lane)
 //   per row    the four quarters are combined with a 2-step shuffle reduce-scatter (each lane ends up with 3 heads x 8
 //              channels) and stored.
+// EARLY RELEASE: the z chunk is moved to registers (32 per lane) as the first thing, and the refill of its slot is issued
+// right after the first head's FFMA2s (which cannot issue before those loads have returned) -- not after all twelve -- so all
+// three z slots of a warp are in flight while it computes.  alpha is read head by head during the chunk, so it lives in its
+// own ring with one slot more; the refill issued inside chunk c lands in the alpha slot of chunk c - 1.  Both copies of a
+// chunk still complete on one mbarrier (the one of the z slot).
+// The rows to visit come from a ROW LIST (pair_rows_build_kernel: live rows from the front, masked-but-needed rows from the
+// back), so neither the producer nor the consumer evaluates masks, focus lists or integer divisions in the loop: round 1's
+// version spent ~300 of its ~500 instructions per chunk (and 144 bytes of spills) on that bookkeeping.
 constexpr int PW_WARPS = 12, PW_THREADS = PW_WARPS * 32, PW_STAGES = 3;
 constexpr int PW_CJ = 16;                               // key residues per chunk
 constexpr int PW_Z_BYTES = PW_CJ * C * 4;               // 4096
 constexpr int PW_A_BYTES = H * PW_CJ * 4;               // 768
-constexpr int PW_STAGE_BYTES = PW_Z_BYTES + PW_A_BYTES; // 4864 (a multiple of 128)
-constexpr int PW_WARP_BYTES = PW_STAGES * PW_STAGE_BYTES;
+constexpr int PW_ASTAGES = PW_STAGES + 1;                // alpha ring: one slot more, see "early release" below
+constexpr int PW_ZRING = PW_STAGES * PW_Z_BYTES, PW_ARING = PW_ASTAGES * PW_A_BYTES;
+constexpr int PW_WARP_BYTES = PW_ZRING + PW_ARING;      // 15360 (a multiple of 128)
 constexpr int PW_SMEM = PW_WARPS * PW_WARP_BYTES + PW_WARPS * PW_STAGES * 8 + 1024;
 
 struct PairRowsArgs {
   int L, Lp, b0, nrows, nchunk;   // nrows = complexes covered by this launch * L; b0 = first complex; nchunk = ceil(L / 16)
-  int rev;                        // 1: walk the rows from the LAST complex to the first.  The logits kernel has just written alpha in
-                                  // forward order; the tail of it (what fits the 126 MB L2) is still resident, the head is not
   const float* z;                 // (N, L, L, 64)
-  const uint8_t* mask;
   float* alpha;                   // [chunk complex][h][i][Lp]; rows of masked queries are zeroed here (ga.py:25)
   float* feat;
-  const int* cidx;                // optional (focus mode): compact output row of query row r, -1 = row not needed at all
+  const int4* list;               // [nrows] (complex within the launch, residue, output row, -)
+  const int* count;               // [2] live rows (list front) | masked rows that still need their zeros (list back)
 };
 
-__device__ __forceinline__ void bulk_load_1d_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, int c0, int c1, int c2, uint64_t* bar) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-               ::"r"(smem_u32(dst)), "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+// Row list of one launch, in row order: a row is NEEDED when the caller consumes it (focus mode: cidx[row] >= 0 = its compact
+// output row; otherwise every row), LIVE when it is needed and its query residue is unmasked.  One CTA; runs once per sampling
+// run (the masks are loop invariants) or once per stand-alone block call.
+__global__ void __launch_bounds__(1024)
+pair_rows_build_kernel(int nrows, int L, int b0, const uint8_t* __restrict__ mask, const int* __restrict__ cidx,
+                       int4* __restrict__ list, int* __restrict__ count) {
+  __shared__ int wl[32], wd[32], base[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { base[0] = 0; base[1] = 0; }
+  __syncthreads();
+  for (int r0 = 0; r0 < nrows; r0 += 1024) {
+    const int r = r0 + tid;
+    bool live = false, dead = false;
+    int bl = 0, i = 0, orow = 0;
+    if (r < nrows) {
+      bl = r / L; i = r - bl * L;
+      const size_t gr = (size_t)(b0 + bl) * L + i;
+      orow = cidx ? cidx[gr] : (int)gr;
+      live = orow >= 0 && mask[gr] != 0;
+      dead = orow >= 0 && !live;
+    }
+    const unsigned ml = __ballot_sync(0xffffffffu, live), md = __ballot_sync(0xffffffffu, dead);
+    if (lane == 0) { wl[warp] = __popc(ml); wd[warp] = __popc(md); }
+    __syncthreads();
+    int pl = base[0], pd = base[1];
+    for (int w = 0; w < warp; ++w) { pl += wl[w]; pd += wd[w]; }
+    const unsigned lt = (1u << lane) - 1u;
+    if (live) list[pl + __popc(ml & lt)] = make_int4(bl, i, orow, 0);
+    if (dead) list[nrows - 1 - (pd + __popc(md & lt))] = make_int4(bl, i, orow, 0);
+    __syncthreads();
+    if (tid == 0) {
+      int sl = 0, sd = 0;
+      for (int w = 0; w < 32; ++w) { sl += wl[w]; sd += wd[w]; }
+      base[0] += sl; base[1] += sd;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) { count[0] = base[0]; count[1] = base[1]; }
 }
 
 __global__ void __launch_bounds__(PW_THREADS, 1)
@@ -201,81 +251,56 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs 
 
   const int stride = gridDim.x * PW_WARPS;
   const int first = warp * gridDim.x + blockIdx.x;      // consecutive rows go to different SMs
-  const int nbm1 = a.nrows / L - 1;
-  // (complex, residue) of a row advance incrementally: no integer division in the loops
-  const int dbl = stride / L, di = stride - dbl * L;
-  auto advance = [&](int& bl, int& i) { bl += dbl; i += di; if (i >= L) { i -= L; ++bl; } };
-  // query mask of the warp's next 32 rows as one ballot word (lane k <-> the k-th row from `row`), so that neither the
-  // producer nor the consumer ever waits on a global load per row
-  // need_word: rows this launch has to produce at all (focus mode skips the others without touching anything)
-  auto live_word = [&](int row, unsigned& need_word) {
-    const long long vr = (long long)row + (long long)lane * stride;
-    bool live = false, need = false;
-    if (vr < a.nrows) {
-      const long long r = a.rev ? (long long)a.nrows - 1 - vr : vr;
-      const int bl = (int)(r / L);
-      const size_t gr = (size_t)(a.b0 + bl) * L + (int)(r - (long long)bl * L);
-      need = a.cidx ? a.cidx[gr] >= 0 : true;
-      live = need && a.mask[gr] != 0;
-    }
-    need_word = __ballot_sync(0xffffffffu, need);
-    return __ballot_sync(0xffffffffu, live);
-  };
+  const int nlive = a.count[0], ndead = a.count[1];
 
-  // ---- producer cursor (lane 0 issues): the warp's live rows, chunk by chunk, up to PW_STAGES chunks ahead of the consumer
-  int prow = first, pbl = first / L, pi = first - pbl * L, pjc = 0, ps = 0, pk = 0;
-  unsigned pneed_unused;
-  unsigned pword = live_word(first, pneed_unused);
+  // ---- producer cursor (lane 0 issues): this warp's rows of the list, chunk by chunk, PW_STAGES chunks ahead of the consumer
+  int pn = first, pjc = 0;
+  const uint32_t z_beg = smem_u32(wst), a_beg = z_beg + PW_ZRING, a_end = a_beg + PW_ARING;
+  uint32_t pst = z_beg, pal = a_beg, pbar = smem_u32(full);      // z slot / alpha slot / barrier the next chunk goes to
+  int4 pe = pn < nlive ? a.list[pn] : make_int4(0, 0, 0, 0);
   const uint64_t pol = policy_evict_first();
   auto issue = [&]() {                                  // executed by the whole warp (uniform control flow)
-    while (prow < a.nrows && !((pword >> pk) & 1u)) {    // skip masked query rows
-      prow += stride; advance(pbl, pi);
-      if (++pk == 32) { pk = 0; pword = live_word(prow, pneed_unused); }
-    }
-    if (prow >= a.nrows) return;
-    const int j0 = pjc * PW_CJ;
-    const int nj = (L - j0 < PW_CJ) ? (L - j0) : PW_CJ;
+    if (pn >= nlive) return;
     if (lane == 0) {
-      const int rbl = a.rev ? nbm1 - pbl : pbl, ri = a.rev ? L - 1 - pi : pi;      // (complex, residue) of the virtual row
-      unsigned char* st = wst + ps * PW_STAGE_BYTES;
-      mbar_expect_tx(&full[ps], (uint32_t)(nj * C * 4 + PW_A_BYTES));
-      bulk_load_1d_hint(st, a.z + (((size_t)(a.b0 + rbl) * L + ri) * L + j0) * C, (uint32_t)(nj * C * 4), &full[ps], pol);
-      tma_load_3d(st + PW_Z_BYTES, &amap, j0, ri, rbl * H, &full[ps]);
+      const int j0 = pjc * PW_CJ;
+      const int nj = (L - j0 < PW_CJ) ? (L - j0) : PW_CJ;
+      const uint32_t zb = (uint32_t)(nj * C * 4);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pbar), "r"(zb + PW_A_BYTES) : "memory");
+      const float* src = a.z + (((size_t)(a.b0 + pe.x) * L + pe.y) * L + j0) * C;
+      asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                   ::"r"(pst), "l"(src), "r"(zb), "r"(pbar), "l"(pol) : "memory");
+      asm volatile("cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                   ::"r"(pal), "l"(&amap), "r"(j0), "r"(pe.y), "r"(pe.x * H), "r"(pbar) : "memory");
     }
-    if (++ps == PW_STAGES) ps = 0;
+    pst += PW_Z_BYTES; pbar += 8; pal += PW_A_BYTES;
+    if (pst == a_beg) { pst = z_beg; pbar -= 8 * PW_STAGES; }
+    if (pal == a_end) pal = a_beg;
     if (++pjc == a.nchunk) {
-      pjc = 0; prow += stride; advance(pbl, pi);
-      if (++pk == 32) { pk = 0; pword = live_word(prow, pneed_unused); }
+      pjc = 0; pn += stride;
+      if (pn < nlive) pe = a.list[pn];
     }
   };
   for (int s = 0; s < PW_STAGES; ++s) issue();
 
+  // ---- masked query rows that are needed: alpha row = 0 (ga.py:25) -> zero pair aggregate
+  for (int n = first; n < ndead; n += stride) {
+    const int4 e = a.list[a.nrows - 1 - n];
+    float* feat_row = a.feat + (size_t)e.z * NFEAT;
+    float* alpha_row0 = a.alpha + ((size_t)(e.x * H) * L + e.y) * Lp;
+    for (int o = lane; o < H * C; o += 32) feat_row[o] = 0.f;
+    for (int h = 0; h < H; ++h)
+      for (int j = lane; j < Lp; j += 32) alpha_row0[(size_t)h * L * Lp + j] = 0.f;
+  }
+
   const int q = lane >> 3, l = lane & 7;
   const uint32_t zoff0 = (uint32_t)(q * 4 * (C * 4) + l * 16);          // row 4q of the chunk, 16-byte group l
-  const uint32_t aoff0 = (uint32_t)(PW_Z_BYTES + q * 16);               // alpha[h][4q..4q+3] at + h * 64
-  int cs = 0, ck = 0;
+  const uint32_t aoff0 = (uint32_t)(q * 16);                            // alpha[h][4q..4q+3] at + h * 64
+  const unsigned char* cst = wst;                                       // z slot / alpha slot the consumer reads next
+  const unsigned char* cal = wst + PW_ZRING;
+  uint64_t* cbar = full;
   uint32_t cph = 0;
-  unsigned cneed;
-  unsigned cword = live_word(first, cneed);
-  int bl = first / L, i = first - bl * L;
-  for (int row = first; row < a.nrows; row += stride, advance(bl, i)) {
-    const int rbl = a.rev ? nbm1 - bl : bl, ri = a.rev ? L - 1 - i : i;
-    const int b = a.b0 + rbl;
-    const bool live = (cword >> ck) & 1u, need = (cneed >> ck) & 1u;
-    if (++ck == 32) { ck = 0; cword = live_word(row + stride, cneed); }
-    if (!need) continue;
-    const size_t orow = a.cidx ? (size_t)a.cidx[(size_t)b * L + ri] : (size_t)b * L + ri;
-    float* feat_row = a.feat + orow * NFEAT;
-    if (!live) {
-      // masked query: alpha row = 0 (ga.py:25) -> zero pair aggregate
-      float* alpha_row0 = a.alpha + ((size_t)(rbl * H) * L + ri) * Lp;
-      for (int o = lane; o < H * C; o += 32) feat_row[o] = 0.f;
-      for (int o = lane; o < H * Lp; o += 32) {
-        const int h = o / Lp, j = o - h * Lp;
-        alpha_row0[(size_t)h * L * Lp + j] = 0.f;
-      }
-      continue;
-    }
+  for (int n = first; n < nlive; n += stride) {
+    const int orow = a.list[n].z;
     float2 acc[H][4];
 #pragma unroll
     for (int h = 0; h < H; ++h)
@@ -283,17 +308,31 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs 
       for (int p = 0; p < 4; ++p) acc[h][p] = make_float2(0.f, 0.f);
 
     for (int jc = 0; jc < a.nchunk; ++jc) {
-      mbar_wait(&full[cs], cph);
-      const unsigned char* st = wst + cs * PW_STAGE_BYTES;
+      mbar_wait(cbar, cph);
       float4 z0[4], z1[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        z0[k] = *reinterpret_cast<const float4*>(st + zoff0 + k * (C * 4));
-        z1[k] = *reinterpret_cast<const float4*>(st + zoff0 + k * (C * 4) + 128);
+        z0[k] = *reinterpret_cast<const float4*>(cst + zoff0 + k * (C * 4));
+        z1[k] = *reinterpret_cast<const float4*>(cst + zoff0 + k * (C * 4) + 128);
       }
+      {
+        // head 0 with ordered FFMA2s: once they have issued, every z load of this lane (and, the loads of a warp completing
+        // in order, every alpha load of the previous chunk) has returned -> the z slot can be refilled
+        const float4 av = *reinterpret_cast<const float4*>(cal + aoff0);
+        const float aj[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
-      for (int h = 0; h < H; ++h) {
-        const float4 av = *reinterpret_cast<const float4*>(st + aoff0 + h * (PW_CJ * 4));
+        for (int k = 0; k < 4; ++k) {
+          acc[0][0] = ffma2_ordered(aj[k], make_float2(z0[k].x, z0[k].y), acc[0][0]);
+          acc[0][1] = ffma2_ordered(aj[k], make_float2(z0[k].z, z0[k].w), acc[0][1]);
+          acc[0][2] = ffma2_ordered(aj[k], make_float2(z1[k].x, z1[k].y), acc[0][2]);
+          acc[0][3] = ffma2_ordered(aj[k], make_float2(z1[k].z, z1[k].w), acc[0][3]);
+        }
+      }
+      __syncwarp();                                      // every lane is past its loads of the z slot -> refill it
+      issue();
+#pragma unroll
+      for (int h = 1; h < H; ++h) {
+        const float4 av = *reinterpret_cast<const float4*>(cal + aoff0 + h * (PW_CJ * 4));
         const float aj[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -303,12 +342,13 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs 
           acc[h][3] = ffma2(aj[k], make_float2(z1[k].z, z1[k].w), acc[h][3]);
         }
       }
-      __syncwarp();                                      // every lane's reads of the stage have completed -> refill it
-      issue();
-      if (++cs == PW_STAGES) { cs = 0; cph ^= 1u; }
+      cst += PW_Z_BYTES; ++cbar; cal += PW_A_BYTES;
+      if (cst == wst + PW_ZRING) { cst = wst; cbar = full; cph ^= 1u; }
+      if (cal == wst + PW_WARP_BYTES) cal = wst + PW_ZRING;
     }
 
     // ---- combine the four quarters: reduce-scatter over lane bits 4 and 3, so lane (q, l) ends with heads 3q'..3q'+2
+    float* feat_row = a.feat + (size_t)orow * NFEAT;
     const bool up = (lane & 16) != 0, odd = (lane & 8) != 0;
     float2 r[6][4];
 #pragma unroll
@@ -368,16 +408,19 @@ bool launch_pair_bias(int nb, int b0, int N, int L, int Lp, const float* z, cons
   return true;
 }
 
-bool launch_pair_stream(int nb, int b0, int L, int Lp, const float* z, const uint8_t* mask,
-                        float* alpha, float* feat, cudaStream_t st, const int* cidx) {
+void launch_pair_rows_build(int nb, int b0, int L, const uint8_t* mask, const int* cidx, const PairRows& pr, cudaStream_t st) {
+  ProfScope prof__(KK_OTHER, st);
+  pair_rows_build_kernel<<<1, 1024, 0, st>>>(nb * L, L, b0, mask, cidx, pr.list, pr.count);
+}
+
+bool launch_pair_stream(int nb, int b0, int L, int Lp, const float* z, float* alpha, float* feat, const PairRows& pr, cudaStream_t st) {
   CUtensorMap amap;
   // alpha as a plain 3-D tensor [nb * H][L queries][Lp keys]; box = [12 heads][1 query][16 keys]
   if (!make_tmap_3d_plain(&amap, alpha, (uint64_t)Lp, (uint64_t)L, (uint64_t)nb * H, PW_CJ, 1, H)) return false;
   ProfScope prof__(KK_PAIR, st);
   PairRowsArgs a{};
   a.L = L; a.Lp = Lp; a.b0 = b0; a.nrows = nb * L; a.nchunk = (L + PW_CJ - 1) / PW_CJ;
-  a.z = z; a.mask = mask; a.alpha = alpha; a.feat = feat; a.cidx = cidx;
-  { const char* ev = getenv("ABOPT_PAIR_REV"); a.rev = (ev && ev[0] == '1') ? 1 : 0; }      // ABOPT_PAIR_REV=1: reverse walk (measured neutral on B200)
+  a.z = z; a.alpha = alpha; a.feat = feat; a.list = pr.list; a.count = pr.count;
   int grid = g_sm_count > 0 ? g_sm_count : 148;
   const int need = (a.nrows + PW_WARPS - 1) / PW_WARPS;
   if (grid > need) grid = need;

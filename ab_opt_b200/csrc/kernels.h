@@ -115,8 +115,14 @@ void launch_alpha_tap(int nb, int b0, int L, int Lp, const float* alpha, float* 
 cudaError_t pair_stream_init();
 bool make_tmap_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
 bool launch_pair_bias(int nb, int b0, int N, int L, int Lp, const float* z, const PairBiasPacked& pb, float* bias, cudaStream_t st);
-bool launch_pair_stream(int nb, int b0, int L, int Lp, const float* z, const uint8_t* mask,
-                        float* alpha, float* feat, cudaStream_t st, const int* cidx = nullptr);
+// row list of one pair_stream launch (pair_rows_build_kernel): live rows from the front, masked-but-needed rows from the back
+struct PairRows {
+  int4* list;         // [nb * L]  (complex within the launch, residue, output row, -)
+  int* count;         // [2]  live rows | masked rows that still need their zeros (device)
+};
+// cidx (focus mode): compact output row of residue row r, -1 = row not needed at all
+void launch_pair_rows_build(int nb, int b0, int L, const uint8_t* mask, const int* cidx, const PairRows& pr, cudaStream_t st);
+bool launch_pair_stream(int nb, int b0, int L, int Lp, const float* z, float* alpha, float* feat, const PairRows& pr, cudaStream_t st);
 bool make_tmap_3d_plain(CUtensorMap* m, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1, uint32_t box2);
 
 void launch_angle_argmax(int M, int L, const long long* tvec, int t_uniform, const float* Y, const float* expo,

@@ -276,13 +276,16 @@ def timed_config(cfg, dev, rank, world, steps, warmup, init_calls=2):
     barrier()
     l0 = ab_opt_b200.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     e0.record()
-    for _ in range(steps):
+    for k in range(steps):
         traj = step()
+        marks[k].record()
     e1.record()
     barrier()
     launches = ab_opt_b200.launch_count() - l0
     ms = e0.elapsed_time(e1)
+    timed_config.each_ms = [round(a_.elapsed_time(b_), 2) for a_, b_ in zip([e0] + marks[:-1], marks)]
     if world > 1:
         tms = torch.tensor([ms], device=dev)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -424,7 +427,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                        'init_calls_before_warmup': 2,
                        'e2e_job': 'abopt_design_host: atoms (pinned host) -> residue + pair featurisation + frames + 100 reverse steps '
                                   '-> whole 101-frame trajectory in host memory (models/diffab.py:115-141)'},
-            'clocks': clk,
+            'clocks': clk, 'ms_each_step': getattr(timed_config, 'each_ms', None),
             'e2e': {'value': e2e_value, 'unit': 'residues/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': float(dt.item()) * 1e3},
             'gpu_launches': int(launches),
