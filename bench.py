@@ -100,6 +100,11 @@ class ClockSampler:
                                           '-i', str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
+            # wait for the first sample: nvidia-smi's start-up (NVML initialisation over all GPUs of the box) takes seconds and was
+            # seen to stall kernel submission for 0.1-0.2 s when it fell into the timed region; the periodic queries do not
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 15.0 and self.proc.poll() is None:
+                time.sleep(0.05)
         except OSError:
             self.proc = None
 
