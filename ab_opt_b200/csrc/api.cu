@@ -571,7 +571,7 @@ static int ensure_workspace(abopt_model* m, int N, int L) {
                oBi = take(M * 4), oTv = take((size_t)N * 8), oXal = take(M * F * 4), oXbl = take(M * F * 4), oXil = take(M * F * 4),
                oQa = take(M * H * 64 * 4), oQl = take(256),
                oKb = take(M * H * 64 * 4), oKl = take(256), oRq = take(M * H * 4), oRk = take(M * H * 4),
-               oVt = take((size_t)N * H * 64 * Lp * 4), oVl = take((size_t)N * H * 64 * Lp * 4),
+               oVt = take((size_t)N * H * 64 * Lp * 4),
                oFc = take(M * 4), oFr = take(M * 4), oFw = take((size_t)N * (L / 64 + 2) * 8), oFn = take(64), oFs = take((size_t)N * 8),
                oFx = take(M * F * 4), oFm = take(M), oPr0 = take(M * 16), oPr1 = take(M * 16), oPrc = take(64);
   CUDA_TRY(cudaMalloc(&w.base, off));
@@ -584,7 +584,7 @@ static int ensure_workspace(abopt_model* m, int N, int L) {
   w.bin_idx = (int*)(b + oBi); w.tvec_scratch = (long long*)(b + oTv);
   w.xa_lo = (float*)(b + oXal); w.xb_lo = (float*)(b + oXbl); w.xin_lo = (float*)(b + oXil);
   w.op = AttnOperands{(float*)(b + oQa), (float*)(b + oQl), (float*)(b + oKb), (float*)(b + oKl), (float*)(b + oRq), (float*)(b + oRk),
-                      (float*)(b + oVt), (float*)(b + oVl)};
+                      (float*)(b + oVt)};
   w.focus = Focus{(int*)(b + oFc), (int*)(b + oFr), (int2*)(b + oFw), (int*)(b + oFn), (int*)(b + oFs), (float*)(b + oFx), (uint8_t*)(b + oFm)};
   w.prows[0] = PairRows{(int4*)(b + oPr0), (int*)(b + oPrc)};
   w.prows[1] = PairRows{(int4*)(b + oPr1), (int*)(b + oPrc) + 2};
@@ -644,7 +644,7 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
       const size_t r0 = (size_t)b0 * L, o64 = (size_t)b0 * H * L * 64, o1 = (size_t)b0 * H * L, ov = (size_t)b0 * H * 64 * w.Lp;
       // (QA_lo / KB_lo are placeholders: every logits kernel builds the lo planes of its operands on chip)
       const AttnOperands opc{w.op.QA + o64, w.op.QA_lo, w.op.KB + o64, w.op.KB_lo, w.op.rq + o1, w.op.rk + o1,
-                             w.op.VT + ov, w.op.VT_lo + ov};
+                             w.op.VT + ov};
       if (!launch_proj_pack(nb * L, L, w.Lp, x + r0 * F, x_lo + r0 * F, bw.Wcat, bw.Wcat_lo, R + r0 * 9, t + r0 * 3, bw.coef, opc, st))
         return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (proj)");
     }
@@ -658,7 +658,7 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
       if (!launch_pair_stream(nb, b0, L, w.Lp, z, w.alpha, w.feat, w.prows[which], st))
         return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (pair)");
     }
-    if (!launch_aggr_tc(nb, b0, N, L, w.Lp, w.alpha, w.op.VT, w.op.VT_lo, R, t, w.feat, st, fc ? fc->windows : nullptr,
+    if (!launch_aggr_tc(nb, b0, N, L, w.Lp, w.alpha, w.op.VT, R, t, w.feat, st, fc ? fc->windows : nullptr,
                         fc ? fc->count : nullptr, fc ? fc->cidx : nullptr))
       return fail(ABOPT_ERR_CUDA, "aggr_tc launch failed");
     if (alpha_tap) launch_alpha_tap(nb, b0, L, w.Lp, w.alpha, alpha_tap, st);

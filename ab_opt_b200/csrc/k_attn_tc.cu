@@ -523,7 +523,7 @@ bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOpera
 // tensor core truncates the fp32 accumulator on every accumulation, see k_tc.cu).
 constexpr int AG2_A_BYTES = 128 * 32 * 4, AG2_B_BYTES = 64 * 32 * 4;
 constexpr int AG2_STAGE_BYTES = 2 * AG2_A_BYTES + 2 * AG2_B_BYTES;      // 48 KB: alpha raw | alpha lo | V^T hi | V^T lo
-constexpr int AG2_TX_BYTES = AG2_A_BYTES + 2 * AG2_B_BYTES;             // what TMA delivers per stage
+constexpr int AG2_TX_BYTES = AG2_A_BYTES + AG2_B_BYTES;                 // what TMA delivers per stage (the lo planes are built on chip)
 
 struct AggrArgs {
   int L, Lp, b0;
@@ -535,9 +535,10 @@ struct AggrArgs {
 // aggr_persist_kernel: structured like attn_logits_persist_kernel.  One CTA per SM walks
 // the (complex, head, 128-query tile) list; the k-block ring runs across tile boundaries and the epilogue of tile n overlaps
 // the main loop of tile n + 1 (two 256-column TMEM accumulator sets):
-//   warp 0      TMA producer: key blocks of 32 through a 4-stage ring (alpha 128 x 32 raw fp32; V^T 64 x 32 hi and lo planes)
+//   warp 0      TMA producer: key blocks of 32 through a 4-stage ring (alpha 128 x 32 and V^T 64 x 32, raw fp32 = the hi planes)
 //   warp 1      MMA issuer (waits for "split")
-//   warps 2-5   splitters: tf32 lo plane of every landed alpha box, in shared memory
+//   warps 2-5   splitters: tf32 lo planes of every landed alpha and V^T box, in shared memory (no VT_lo in global memory:
+//               50 MB per layer less to write in the projection kernel and to read here)
 //   warps 6-9   epilogue: thread = query row: 64 sums -> node aggregate, R_i^T (o - t_i), norms, directions; every feature
 //               group of a row is a 32-byte-aligned run, stored with 256-bit stores (full sectors, no staging buffer)
 constexpr int AGP_THREADS = 320, AGP_ST = 4;
@@ -550,7 +551,7 @@ __device__ __forceinline__ void st_v8f(float* p, float a0, float a1, float a2, f
 
 __global__ void __launch_bounds__(AGP_THREADS, 1)
 aggr_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmVh,
-                    const __grid_constant__ CUtensorMap tmVl, const AggrArgs a, const int nb_complex,
+                    const AggrArgs a, const int nb_complex,
                     const int2* windows, const int* wcount, const int* cidx) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -571,7 +572,7 @@ aggr_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int s = 0; s < AGP_ST; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 4); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
     mbar_fence_init();
-    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmVh); tma_prefetch_desc(&tmVl);
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmVh);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -592,7 +593,6 @@ aggr_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_expect_tx(&full[s], AG2_TX_BYTES);
           tma_load_2d(st, &tmA, kb * 32, arow, &full[s]);
           tma_load_2d(st + 2 * AG2_A_BYTES, &tmVh, kb * 32, vrow, &full[s]);
-          tma_load_2d(st + 2 * AG2_A_BYTES + AG2_B_BYTES, &tmVl, kb * 32, vrow, &full[s]);
         }
       }
     }
@@ -625,7 +625,7 @@ aggr_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp < 6) {
-    // ---- splitters: lo plane of every landed alpha box
+    // ---- splitters: lo planes of every landed alpha and V^T box
     const int te = (warp - 2) * 32 + lane;
     int g = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
@@ -638,6 +638,13 @@ aggr_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int m = 0; m < AG2_A_BYTES / 16 / 128; ++m) {
           const float4 v = src[te + 128 * m];
           dst[te + 128 * m] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+        }
+        const float4* vsrc = reinterpret_cast<const float4*>(smem + s * AG2_STAGE_BYTES + 2 * AG2_A_BYTES);
+        float4* vdst = reinterpret_cast<float4*>(smem + s * AG2_STAGE_BYTES + 2 * AG2_A_BYTES + AG2_B_BYTES);
+#pragma unroll
+        for (int m = 0; m < AG2_B_BYTES / 16 / 128; ++m) {
+          const float4 v = vsrc[te + 128 * m];
+          vdst[te + 128 * m] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
         }
         fence_async_smem();
         __syncwarp();
@@ -719,20 +726,19 @@ cudaError_t aggr_tc_init() {
   return cudaFuncSetAttribute(aggr_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AGP_SMEM);
 }
 
-// alpha: [chunk][H][L][Lp]; VT / VT_lo: [N][H][64][Lp]
-bool launch_aggr_tc(int nb, int b0, int N, int L, int Lp, const float* alpha, const float* VT, const float* VT_lo,
+// alpha: [chunk][H][L][Lp]; VT: [N][H][64][Lp]
+bool launch_aggr_tc(int nb, int b0, int N, int L, int Lp, const float* alpha, const float* VT,
                     const float* R, const float* t, float* feat, cudaStream_t st, const int2* windows, const int* wcount,
                     const int* cidx) {
-  CUtensorMap ah, vh, vl;
+  CUtensorMap ah, vh;
   const uint64_t arows = (uint64_t)nb * H * L, vrows = (uint64_t)N * H * 64;
-  if (!make_tmap(&ah, alpha, arows, Lp, Lp, 128) || !make_tmap(&vh, VT, vrows, Lp, Lp, 64) || !make_tmap(&vl, VT_lo, vrows, Lp, Lp, 64))
-    return false;
+  if (!make_tmap(&ah, alpha, arows, Lp, Lp, 128) || !make_tmap(&vh, VT, vrows, Lp, Lp, 64)) return false;
   ProfScope prof__(KK_AGGR, st);
   AggrArgs a{L, Lp, b0, R, t, feat};
   const int ntiles = nb * H * ((L + 127) / 128);
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  aggr_persist_kernel<<<ntiles < sms ? ntiles : sms, AGP_THREADS, AGP_SMEM, st>>>(ah, vh, vl, a, nb, windows, wcount, cidx);
+  aggr_persist_kernel<<<ntiles < sms ? ntiles : sms, AGP_THREADS, AGP_SMEM, st>>>(ah, vh, a, nb, windows, wcount, cidx);
   return true;
 }
 

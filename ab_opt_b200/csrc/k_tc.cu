@@ -54,12 +54,13 @@ struct EpiPlain {            // D = acc (+ bias)
 //   QA[b][h][r][64] = [ q / sqrt(32) (32) | global query points (24) | 0 (8) ]                    ga.py:82-85,96-99
 //   KB[b][h][r][64] = [ k (32)            | -2 c_h * global key points (24) | 0 (8) ]             ga.py:83,102-105
 //   rq[b][h][r] = c_h |query points|^2,  rk[b][h][r] = c_h |key points|^2,   c_h = -softplus(coef_h) sqrt(2/(9*8)) / 2
-// so that  QA . KB + rq + rk = node logits + spatial logits  (|q - k|^2 expanded; ga.py:108-111).  Every tensor also gets
-// its tf32 "lo" plane.  Values go out TRANSPOSED (key index contiguous), the K-major B operand of aggr_tc_kernel:
+// so that  QA . KB + rq + rk = node logits + spatial logits  (|q - k|^2 expanded; ga.py:108-111).  The tf32 "lo"
+// planes of all of them are built on chip by their consumers.  Values go out TRANSPOSED (key index contiguous), the K-major B
+// operand of aggr_persist_kernel:
 //   VT[b][h][n][r] = value channel n (n < 32) | global value point coordinate n - 32 (32 <= n < 56); rows 56..63 stay 0.
 struct EpiProjPack {
   const float* R; const float* t; const float* coef;
-  float* QA; float* QA_lo; float* KB; float* KB_lo; float* rq; float* rk; float* VT; float* VT_lo;
+  float* QA; float* QA_lo; float* KB; float* KB_lo; float* rq; float* rk; float* VT;
   int L, Lp;
   int qk_lo;            // 1: also write QA_lo / KB_lo (only the non-persistent logits kernels read them)
 };
@@ -186,7 +187,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
 //   * two epilogue warp groups (4 warps each) take alternate column tiles, so two tiles are packed concurrently;
 //   * the packed rows leave as 256-bit stores (one full 32-byte sector per lane) instead of 128-bit ones.
 // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 / 6-9 = epilogue groups 0 / 1.
-constexpr int PP_THREADS = 320, PP_BN = 96, PP_NT = NPROJ / PP_BN, PP_KB = F / G_BK, PP_ST = 3;
+constexpr int PP_THREADS = 320, PP_BN = 96, PP_NT = NPROJ / PP_BN, PP_KB = F / G_BK, PP_ST = 3;      // (4 stages measured identical: the weight ring is not what bounds it)
 constexpr int PP_A_BYTES = G_BM * G_BK * 4;                 // 16 KB: 128 rows x 32 tf32
 constexpr int PP_B_BYTES = PP_BN * G_BK * 4;                // 12 KB
 constexpr int PP_A_TOTAL = PP_KB * 2 * PP_A_BYTES;          // 128 KB: [k-block][hi | lo]
@@ -366,7 +367,7 @@ proj_persist_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
             if (valid) {
               const size_t o = ((size_t)(b * H + h0 + hh) * 64) * Lp + r;
 #pragma unroll
-              for (int c = 0; c < D; ++c) { ep.VT[o + (size_t)c * Lp] = v[c]; ep.VT_lo[o + (size_t)c * Lp] = tf32_lo(v[c]); }
+              for (int c = 0; c < D; ++c) ep.VT[o + (size_t)c * Lp] = v[c];
             }
           }
         } else {
@@ -408,7 +409,7 @@ proj_persist_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
               } else {
                 const size_t o = ((size_t)(b * H + h) * 64 + D) * Lp + r;
 #pragma unroll
-                for (int c = 0; c < P * 3; ++c) { ep.VT[o + (size_t)c * Lp] = v[c]; ep.VT_lo[o + (size_t)c * Lp] = tf32_lo(v[c]); }
+                for (int c = 0; c < P * 3; ++c) ep.VT[o + (size_t)c * Lp] = v[c];
               }
             }
           }
@@ -584,7 +585,7 @@ bool launch_proj_pack(int M, int L, int Lp, const float* xh, const float* xl, co
       !make_tmap(&b_l, Wl, NPROJ, F, F, 96))
     return false;
   ProfScope prof__(KK_PROJ, st);
-  const EpiProjPack ep{R, t, coef, op.QA, op.QA_lo, op.KB, op.KB_lo, op.rq, op.rk, op.VT, op.VT_lo, L, Lp, attn_needs_qk_lo(L) ? 1 : 0};
+  const EpiProjPack ep{R, t, coef, op.QA, op.QA_lo, op.KB, op.KB_lo, op.rq, op.rk, op.VT, L, Lp, attn_needs_qk_lo(L) ? 1 : 0};
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const int nmt = (M + G_BM - 1) / G_BM;

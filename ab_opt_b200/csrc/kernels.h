@@ -70,12 +70,12 @@ struct AttnOperands {
   float* QA; float* QA_lo;      // [N][H][L][64]
   float* KB; float* KB_lo;      // [N][H][L][64]
   float* rq; float* rk;         // [N][H][L]
-  float* VT; float* VT_lo;      // [N][H][64][Lp]  values, key index contiguous (rows 56..63 and columns >= L stay zero)
+  float* VT;                    // [N][H][64][Lp]  values, key index contiguous (rows 56..63 and columns >= L stay zero)
 };
 bool launch_proj_pack(int M, int L, int Lp, const float* xh, const float* xl, const float* Wh, const float* Wl, const float* R, const float* t,
                       const float* coef, const AttnOperands& op, cudaStream_t st);
 cudaError_t aggr_tc_init();
-bool launch_aggr_tc(int nb, int b0, int N, int L, int Lp, const float* alpha, const float* VT, const float* VT_lo,
+bool launch_aggr_tc(int nb, int b0, int N, int L, int Lp, const float* alpha, const float* VT,
                     const float* R, const float* t, float* feat, cudaStream_t st, const int2* windows = nullptr,
                     const int* wcount = nullptr, const int* cidx = nullptr);
 bool make_tmap(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
