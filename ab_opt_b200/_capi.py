@@ -114,7 +114,7 @@ def check(rc):
         raise AboptError(f'libabopt_b200 error {rc}: {lib().abopt_last_error().decode()}')
 
 
-KERNEL_KINDS = ('mixer', 'proj', 'logits', 'pair', 'aggr', 'tail', 'heads', 'step', 'other')
+KERNEL_KINDS = ('mixer', 'proj', 'logits', 'pair', 'aggr', 'tail', 'heads', 'step', 'other', 'ctx', 'pair_part')
 
 
 def profile_enable(on):

@@ -68,7 +68,10 @@ struct Workspace {
   int* bin_idx;
   long long* tvec_scratch;
   Focus focus;
-  PairRows prows[2];            // row lists of pair_stream_kernel: [0] every row, [1] focus mode (generated rows)
+  PairRows prows[3];            // row lists of pair_stream_kernel: [0] every row, [1] focus mode (generated rows, compact output),
+                                // [2] generated rows in place (first block with the context cache)
+  float* ctx_cache;             // [N * L][768]  context part of the first block's pair aggregate (k_pair.cu: ctx_delta_kernel)
+  float2 *ctx_stats, *step_stats;      // [N][H][L] softmax statistics: context keys only (once per run) / all keys (this step)
 };
 
 struct HostIO {       // device staging for abopt_sample_host
@@ -93,7 +96,8 @@ struct abopt_model {
   // layers (z and the weights are loop invariants of the T reverse steps); elsewhere slot 0 is recomputed per block call.
   float* bias_buf = nullptr; size_t bias_slots = 0, bias_slot_floats = 0; bool bias_hoisted = false;
   bool focus_built = false;     // inside abopt_sample_*: the focus lists of mask_generate were built once for the whole run
-  bool prows_built[2] = {false, false};      // likewise the row lists of pair_stream_kernel (mask_res / the focus list are loop invariants)
+  bool prows_built[3] = {false, false, false};      // likewise the row lists of pair_stream_kernel (mask_res / the focus list are loop invariants)
+  bool ctx_built = false;       // ... and the context cache of the first block
   EpsW eps;
   DiffW diff;
   Workspace ws;
@@ -573,7 +577,8 @@ static int ensure_workspace(abopt_model* m, int N, int L) {
                oKb = take(M * H * 64 * 4), oKl = take(256), oRq = take(M * H * 4), oRk = take(M * H * 4),
                oVt = take((size_t)N * H * 64 * Lp * 4),
                oFc = take(M * 4), oFr = take(M * 4), oFw = take((size_t)N * (L / 64 + 2) * 8), oFn = take(64), oFs = take((size_t)N * 8),
-               oFx = take(M * F * 4), oFm = take(M), oPr0 = take(M * 16), oPr1 = take(M * 16), oPrc = take(64);
+               oFx = take(M * F * 4), oFm = take(M), oPr0 = take(M * 16), oPr1 = take(M * 16), oPr2 = take(M * 16), oPrc = take(64),
+               oCc = take(M * H * C * 4), oCs = take(M * H * 8), oCt = take(M * H * 8);
   CUDA_TRY(cudaMalloc(&w.base, off));
   CUDA_TRY(cudaMemset(w.base, 0, off));        // the padding rows / columns of the packed attention operands must stay zero
   unsigned char* b = static_cast<unsigned char*>(w.base);
@@ -588,6 +593,8 @@ static int ensure_workspace(abopt_model* m, int N, int L) {
   w.focus = Focus{(int*)(b + oFc), (int*)(b + oFr), (int2*)(b + oFw), (int*)(b + oFn), (int*)(b + oFs), (float*)(b + oFx), (uint8_t*)(b + oFm)};
   w.prows[0] = PairRows{(int4*)(b + oPr0), (int*)(b + oPrc)};
   w.prows[1] = PairRows{(int4*)(b + oPr1), (int*)(b + oPrc) + 2};
+  w.prows[2] = PairRows{(int4*)(b + oPr2), (int*)(b + oPrc) + 4};
+  w.ctx_cache = (float*)(b + oCc); w.ctx_stats = (float2*)(b + oCs); w.step_stats = (float2*)(b + oCt);
   w.N = N; w.L = L; w.Lp = Lp; w.NB = NB; w.bytes = off;
   return ABOPT_OK;
 }
@@ -626,7 +633,7 @@ static int ensure_pair_inputs(abopt_model* m, int N, int L, const float* z, size
 // fc != nullptr ("focus", last block inside the sampling loop): only the rows listed in fc are produced, x_out is COMPACT
 static int run_block(abopt_model* m, int layer, int N, int L, const float* R, const float* t, const float* x, const float* x_lo,
                      const float* z, const uint8_t* mask, float* x_out, float* x_lo_out, float* alpha_tap, cudaStream_t st,
-                     const Focus* fc = nullptr) {
+                     const Focus* fc = nullptr, const uint8_t* ctx_cache_gen = nullptr) {
   Workspace& w = m->ws;
   const int M = N * L;
   const BlockW& bw = m->blocks[layer];
@@ -648,14 +655,34 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
       if (!launch_proj_pack(nb * L, L, w.Lp, x + r0 * F, x_lo + r0 * F, bw.Wcat, bw.Wcat_lo, R + r0 * 9, t + r0 * 3, bw.coef, opc, st))
         return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (proj)");
     }
+    // Context cache (k_pair.cu): inside the sampling loop the first block's logits between context residues are loop invariants,
+    // so the context part of its pair aggregate is computed once per run and only the generated keys' share is streamed per step.
+    const bool ctx = layer == 0 && ctx_cache_gen != nullptr && nb == N && fc == nullptr;
+    if (ctx && !m->ctx_built) {
+      // once per run: softmax over the context keys alone (+ its statistics) and the pair aggregate of every query row with it
+      if (!launch_attn_logits_tc(nb, b0, N, L, w.Lp, w.op, bias, mask, w.alpha, st, nullptr, nullptr, ctx_cache_gen, w.ctx_stats))
+        return fail(ABOPT_ERR_CUDA, "attn_logits_tc launch failed");
+      if (!m->prows_built[0]) { launch_pair_rows_build(nb, b0, L, mask, nullptr, w.prows[0], st); m->prows_built[0] = true; }
+      if (!launch_pair_stream(nb, b0, L, w.Lp, z, w.alpha, w.ctx_cache, w.prows[0], st, H * C))
+        return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (pair)");
+      launch_pair_rows_build(nb, b0, L, mask, w.focus.cidx, w.prows[2], st, /*compact=*/false);
+      m->ctx_built = true;
+    }
     // logits (node + spatial + pair bias, scaled, masked) and softmax on the tensor cores -> alpha
-    if (!launch_attn_logits_tc(nb, b0, N, L, w.Lp, w.op, bias, mask, w.alpha, st, fc ? fc->windows : nullptr, fc ? fc->count : nullptr))
+    if (!launch_attn_logits_tc(nb, b0, N, L, w.Lp, w.op, bias, mask, w.alpha, st, fc ? fc->windows : nullptr, fc ? fc->count : nullptr,
+                               nullptr, ctx ? w.step_stats : nullptr))
       return fail(ABOPT_ERR_CUDA, "attn_logits_tc launch failed");
-    {
+    if (ctx) {
+      // generated query rows: all of their z rows; context query rows: cached context part + the generated keys
+      if (!launch_pair_stream(nb, b0, L, w.Lp, z, w.alpha, w.feat, w.prows[2], st, NFEAT, /*partial=*/true))
+        return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (pair)");
+      launch_ctx_delta(N, L, w.Lp, z, mask, w.alpha, w.ctx_cache, w.ctx_stats, w.step_stats, w.focus.cidx, w.focus.rows, w.focus.scratch,
+                       w.focus.count, w.feat, st);
+    } else {
       const int which = fc ? 1 : 0;
       if (!m->prows_built[which]) launch_pair_rows_build(nb, b0, L, mask, fc ? fc->cidx : nullptr, w.prows[which], st);
       if (m->bias_hoisted && nb == N) m->prows_built[which] = true;      // the sampling loop: the masks are loop invariants
-      if (!launch_pair_stream(nb, b0, L, w.Lp, z, w.alpha, w.feat, w.prows[which], st))
+      if (!launch_pair_stream(nb, b0, L, w.Lp, z, w.alpha, w.feat, w.prows[which], st, NFEAT, /*partial=*/fc != nullptr))
         return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (pair)");
     }
     if (!launch_aggr_tc(nb, b0, N, L, w.Lp, w.alpha, w.op.VT, R, t, w.feat, st, fc ? fc->windows : nullptr,
@@ -706,7 +733,8 @@ extern "C" int abopt_ga_block_taps(abopt_model* m, int layer, int N, int L, cons
 
 // all layers; result lands in *result (one of the two workspace ping-pong buffers)
 static int run_encoder(abopt_model* m, int N, int L, const float* R, const float* t, const float* x, const float* x_lo,
-                       const float* z, const uint8_t* mask, float** result, cudaStream_t st, const Focus* fc = nullptr) {
+                       const float* z, const uint8_t* mask, float** result, cudaStream_t st, const Focus* fc = nullptr,
+                       const uint8_t* ctx_cache_gen = nullptr) {
   Workspace& w = m->ws;
   const float* cur = x;
   const float* cur_lo = x_lo;
@@ -715,7 +743,9 @@ static int run_encoder(abopt_model* m, int N, int L, const float* R, const float
   int which = (x == w.xa) ? 1 : 0;
   for (int l = 0; l < m->cfg.num_layers; ++l) {
     const bool last = l == m->cfg.num_layers - 1;
-    int rc = run_block(m, l, N, L, R, t, cur, cur_lo, z, mask, bufs[which], bufs_lo[which], nullptr, st, last ? fc : nullptr); if (rc) return rc;
+    int rc = run_block(m, l, N, L, R, t, cur, cur_lo, z, mask, bufs[which], bufs_lo[which], nullptr, st, last ? fc : nullptr,
+                       l == 0 ? ctx_cache_gen : nullptr);
+    if (rc) return rc;
     cur = bufs[which]; cur_lo = bufs_lo[which]; which ^= 1;
   }
   *result = const_cast<float*>(cur);
@@ -760,7 +790,12 @@ static int run_eps_net(abopt_model* m, int N, int L, const float* v_t, const flo
   launch_mixer(M, res_feat, s_t, v_t, m->eps, w.xa, w.Rbuf, p_ang, w.pnorm, m->diff.pos_mean, m->diff.pos_scale, w.xa_lo, st);
   const float* tpos = p_ang ? w.pnorm : p_t;
   float* enc = nullptr;
-  int rc = run_encoder(m, N, L, w.Rbuf, tpos, w.xa, w.xa_lo, pair_feat, mask_res, &enc, st, fc); if (rc) return rc;
+  // context cache of the first block: only inside the sampling loop (everything a context residue feeds into the first block is
+  // a loop invariant there), with the focus lists built.  ABOPT_NO_CTXCACHE=1 disables it (read per call, like ABOPT_NO_FOCUS).
+  const char* nc = getenv("ABOPT_NO_CTXCACHE");
+  const bool ctx_on = hf != nullptr && m->bias_hoisted && m->focus_built && w.NB >= N && m->cfg.num_layers >= 2 && !(nc && nc[0] == '1');
+  int rc = run_encoder(m, N, L, w.Rbuf, tpos, w.xa, w.xa_lo, pair_feat, mask_res, &enc, st, fc, ctx_on ? mask_gen : nullptr);
+  if (rc) return rc;
   launch_heads(M, L, enc, beta, beta_stride, w.Rbuf, v_t, mask_gen, m->eps, v_next, R_next, eps_pos, c_den, w.prmsd_rows,
                m->cfg.has_prmsd ? (prmsd_logits ? prmsd_logits : w.prmsd_logits) : nullptr, st, hf ? hf->rows : nullptr,
                hf ? hf->count : nullptr, /*x_compact=*/fc != nullptr);
@@ -962,12 +997,14 @@ extern "C" int abopt_sample_device(abopt_model* m, int N, int L, const float* v,
   m->bias_hoisted = true;
   m->focus_built = false;
   m->prows_built[0] = m->prows_built[1] = false;
+  m->ctx_built = false;
   for (int t = T0; t >= 1 && rc == ABOPT_OK; --t)
     rc = run_step(m, N, L, t, optimize, flags, seed, V(t), Pp(t), S(t), res_feat, pair_feat, mask_generate, mask_res,
                   noise ? &noise[T0 - t] : nullptr, V(t - 1), Pp(t - 1), S(t - 1), PR(t - 1), PL(t - 1), st);
   m->bias_hoisted = false;
   m->focus_built = false;
   m->prows_built[0] = m->prows_built[1] = false;
+  m->ctx_built = false;
   return rc;
 }
 

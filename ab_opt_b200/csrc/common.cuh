@@ -28,7 +28,7 @@ constexpr int NBINS = 8192;
 
 // launch bookkeeping (abopt_kernel_launch_count) and the optional per-kernel event profiler
 extern unsigned long long g_launches;
-enum KernelKind { KK_MIXER = 0, KK_PROJ, KK_LOGITS, KK_PAIR, KK_AGGR, KK_TAIL, KK_HEADS, KK_STEP, KK_OTHER, KK_COUNT };
+enum KernelKind { KK_MIXER = 0, KK_PROJ, KK_LOGITS, KK_PAIR, KK_AGGR, KK_TAIL, KK_HEADS, KK_STEP, KK_OTHER, KK_CTX, KK_PAIR_PART, KK_COUNT };
 void prof_begin(int kind, cudaStream_t st);     // no-ops unless abopt_profile_enable(1)
 void prof_end(int kind, cudaStream_t st);
 struct ProfScope {

@@ -28,6 +28,8 @@ struct AttnLogitsArgs {
   const float* bias;                     // [N][H][L queries][Lp] (key index contiguous, like alpha)
   const uint8_t* mask;                   // [N][L]
   float* alpha;                          // [chunk][H][L][Lp]
+  const uint8_t* exclude;                // optional [N][L]: keys left out of the softmax altogether (context cache, k_pair.cu)
+  float2* stats;                         // optional [N][H][L]: (row maximum, sum of exp(l - maximum)) of every query row
 };
 
 void attn_debug_clocks(long long* out16) { for (int i = 0; i < 10; ++i) out16[i] = 0; }      // (the timeline hook of the retired one-tile kernel)
@@ -330,6 +332,7 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
         const int j = key0 + et;
         ckv = (j < L) ? __ldg(a.rk + (size_t)row_base + j) : 0.f;
         penv = (j < L) ? (a.mask[(size_t)b * L + j] != 0 ? 0.f : 1e5f) : INFINITY;
+        if (a.exclude && j < L && a.exclude[(size_t)b * L + j] != 0) penv = INFINITY;
       }
       rqv = (tr.i0 + te < L) ? __ldg(a.rq + (size_t)row_base + tr.i0 + te) : 0.f;
     };
@@ -408,6 +411,7 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
         mbar_wait_cluster(&xch_bar[0 * 2 + buf], (n >> 1) & 1);
         mx = fmaxf(mx, xch[(0 * 2 + buf) * 128 + te]);
       }
+      if (a.exclude && mx == -INFINITY) mx = 0.f;         // every key excluded: alpha = 0 (and stats = (0, 0)), not NaN
       // exp(l - m) = 2^((l - m) log2e): subtract FIRST (exact near the maximum, where the attention mass is)
       float sum = 0.f;
 #pragma unroll
@@ -427,7 +431,9 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
         const float other = xch[(1 * 2 + buf) * 128 + te];
         rowsum = crank == 0 ? rowsum + other : other + rowsum;      // same order of the two halves in both CTAs
       }
-      const float inv = 1.0f / rowsum;
+      const float inv = (a.exclude && rowsum == 0.f) ? 0.f : 1.0f / rowsum;
+      if (a.stats && kq == 0 && crank == 0 && i0 + te < L)
+        a.stats[(size_t)((a.b0 + bl) * H + h) * L + i0 + te] = make_float2(mx, rowsum);
       // alpha leaves chunk by chunk through AP_NSTG staging boxes ([128 queries][32 keys], 128-byte swizzle) and TMA tensor
       // stores: whole lines, rows >= L and keys >= Lp clipped by the hardware.  (Per-lane 256-bit global stores of a
       // row-per-lane layout cost 32 sector requests per instruction and kept the LSU the bottleneck of this kernel.)
@@ -472,7 +478,7 @@ cudaError_t attn_tc_init() {
 }
 
 bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOperands& op, const float* bias_layer, const uint8_t* mask,
-                           float* alpha, cudaStream_t st, const int2* windows, const int* wcount) {
+                           float* alpha, cudaStream_t st, const int2* windows, const int* wcount, const uint8_t* exclude, float2* stats) {
   if (L > AL_MAXCOLS) return false;
   CUtensorMap qh, kh64, bm32, al;
   const uint64_t rows = (uint64_t)N * H * L;
@@ -484,7 +490,7 @@ bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOpera
   // alpha as a 3-D tensor [chunk * H][L queries][Lp keys] for the TMA stores (rows >= L are clipped)
   if (!make_tmap_3d(&al, alpha, Lp, L, (uint64_t)nb * H, 32, 128)) return false;
   ProfScope prof__(KK_LOGITS, st);
-  AttnLogitsArgs a{L, Lp, b0, op.rq, op.rk, bias_layer, mask, alpha};
+  AttnLogitsArgs a{L, Lp, b0, op.rq, op.rk, bias_layer, mask, alpha, exclude, stats};
   const int ncols = ((L + AL_BN - 1) / AL_BN) * AL_BN;
   const int ntiles = nb * H * ((L + AL_BM - 1) / AL_BM);
   int sms = 148;

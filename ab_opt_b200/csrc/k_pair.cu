@@ -184,7 +184,7 @@ struct PairRowsArgs {
   int L, Lp, b0, nrows, nchunk;   // nrows = complexes covered by this launch * L; b0 = first complex; nchunk = ceil(L / 16)
   const float* z;                 // (N, L, L, 64)
   float* alpha;                   // [chunk complex][h][i][Lp]; rows of masked queries are zeroed here (ga.py:25)
-  float* feat;
+  float* feat; int feat_ld;       // output rows of H * C floats, row pitch feat_ld (the 1824-wide feature rows, or a 768-wide cache)
   const int4* list;               // [nrows] (complex within the launch, residue, output row, -)
   const int* count;               // [2] live rows (list front) | masked rows that still need their zeros (list back)
 };
@@ -193,7 +193,7 @@ struct PairRowsArgs {
 // output row; otherwise every row), LIVE when it is needed and its query residue is unmasked.  One CTA; runs once per sampling
 // run (the masks are loop invariants) or once per stand-alone block call.
 __global__ void __launch_bounds__(1024)
-pair_rows_build_kernel(int nrows, int L, int b0, const uint8_t* __restrict__ mask, const int* __restrict__ cidx,
+pair_rows_build_kernel(int nrows, int L, int b0, const uint8_t* __restrict__ mask, const int* __restrict__ cidx, int compact,
                        int4* __restrict__ list, int* __restrict__ count) {
   __shared__ int wl[32], wd[32], base[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -209,6 +209,7 @@ pair_rows_build_kernel(int nrows, int L, int b0, const uint8_t* __restrict__ mas
       orow = cidx ? cidx[gr] : (int)gr;
       live = orow >= 0 && mask[gr] != 0;
       dead = orow >= 0 && !live;
+      if (!compact) orow = (int)gr;               // the listed rows keep their place in the full-size output
     }
     const unsigned ml = __ballot_sync(0xffffffffu, live), md = __ballot_sync(0xffffffffu, dead);
     if (lane == 0) { wl[warp] = __popc(ml); wd[warp] = __popc(md); }
@@ -285,7 +286,7 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs 
   // ---- masked query rows that are needed: alpha row = 0 (ga.py:25) -> zero pair aggregate
   for (int n = first; n < ndead; n += stride) {
     const int4 e = a.list[a.nrows - 1 - n];
-    float* feat_row = a.feat + (size_t)e.z * NFEAT;
+    float* feat_row = a.feat + (size_t)e.z * a.feat_ld;
     float* alpha_row0 = a.alpha + ((size_t)(e.x * H) * L + e.y) * Lp;
     for (int o = lane; o < H * C; o += 32) feat_row[o] = 0.f;
     for (int h = 0; h < H; ++h)
@@ -348,7 +349,7 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs 
     }
 
     // ---- combine the four quarters: reduce-scatter over lane bits 4 and 3, so lane (q, l) ends with heads 3q'..3q'+2
-    float* feat_row = a.feat + (size_t)orow * NFEAT;
+    float* feat_row = a.feat + (size_t)orow * a.feat_ld;
     const bool up = (lane & 16) != 0, odd = (lane & 8) != 0;
     float2 r[6][4];
 #pragma unroll
@@ -408,19 +409,122 @@ bool launch_pair_bias(int nb, int b0, int N, int L, int Lp, const float* z, cons
   return true;
 }
 
-void launch_pair_rows_build(int nb, int b0, int L, const uint8_t* mask, const int* cidx, const PairRows& pr, cudaStream_t st) {
+void launch_pair_rows_build(int nb, int b0, int L, const uint8_t* mask, const int* cidx, const PairRows& pr, cudaStream_t st,
+                            bool compact) {
   ProfScope prof__(KK_OTHER, st);
-  pair_rows_build_kernel<<<1, 1024, 0, st>>>(nb * L, L, b0, mask, cidx, pr.list, pr.count);
+  pair_rows_build_kernel<<<1, 1024, 0, st>>>(nb * L, L, b0, mask, cidx, compact ? 1 : 0, pr.list, pr.count);
 }
 
-bool launch_pair_stream(int nb, int b0, int L, int Lp, const float* z, float* alpha, float* feat, const PairRows& pr, cudaStream_t st) {
+// ------------------------------------------------------------------------------------------ context cache (first block)
+// Inside the sampling loop the input of the FIRST GABlock changes only on the generated residues: x_0 = mixer(res_feat, s_t) and
+// the frames (R_t, p_t) of a context residue are the same at every step (dpm_full.py:86-89, transition.py:99,158,176 keep the
+// context).  For a context query i the logits against context keys are therefore loop invariants, and so is
+//     P_i[h][c] = sum_{j context} a~_ij z_ijc ,   a~ = softmax over the context keys alone, with row maximum m~_i and sum S~_i
+// (computed once per run: the logits kernel with the generated keys excluded, then pair_stream_kernel into a 768-wide cache).
+// At a step with row maximum m_i and sum S_i over ALL keys, alpha_ij = a~_ij S~_i exp(m~_i - m_i) / S_i for context keys j, so
+//     sum_j alpha_ij z_ij = P_i * [S~_i exp(m~_i - m_i) / S_i]  +  sum_{g generated} alpha_ig z_ig
+// -- 16 instead of 256 rows of z per context query in C2 (m_i >= m~_i, so the factor never overflows).  ctx_delta_kernel does
+// that for every context query row; the generated query rows go through pair_stream_kernel as usual (row list of the generated
+// rows).  Same numbers up to fp32 reassociation; ABOPT_NO_CTXCACHE=1 streams all of z in the first block as well.
+struct CtxDeltaArgs {
+  int N, L, Lp;
+  const float* z; const uint8_t* mask;
+  float* alpha;                   // [N][H][L][Lp] of this step; rows of masked context queries are zeroed here (ga.py:25)
+  const float* cache;             // [N * L][768]  P_i
+  const float2* stats_ctx;        // [N][H][L]  (m~, S~)
+  const float2* stats;            // [N][H][L]  (m, S) of this step
+  const int* cidx;                // [N * L]  >= 0: generated row (handled by pair_stream_kernel)
+  const int* rows;                // generated rows, complex by complex
+  const int* first;               // [N] index of the complex's first generated row in `rows`
+  const int* count;               // count[0] = number of generated rows
+  float* feat;                    // [N * L][1824]
+};
+
+__global__ void __launch_bounds__(256, 3)
+ctx_delta_kernel(const CtxDeltaArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+  const int L = a.L, Lp = a.Lp;
+  const float l2e = 1.4426950408889634f;
+  for (int r = warp; r < a.N * L; r += nwarp) {
+    if (a.cidx[r] >= 0) continue;
+    const int b = r / L, i = r - b * L;
+    float* feat_row = a.feat + (size_t)r * NFEAT;
+    float* alpha_row0 = a.alpha + ((size_t)(b * H) * L + i) * Lp;
+    if (a.mask[r] == 0) {
+      for (int o = lane; o < H * C; o += 32) feat_row[o] = 0.f;
+      for (int h = 0; h < H; ++h)
+        for (int j = lane; j < Lp; j += 32) alpha_row0[(size_t)h * L * Lp + j] = 0.f;
+      continue;
+    }
+    // per head: weight of the cached context part
+    float wl = 0.f;
+    if (lane < H) {
+      const size_t si = (size_t)(b * H + lane) * L + i;
+      const float2 sc = a.stats_ctx[si], st = a.stats[si];
+      float e;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((sc.x - st.x) * l2e));
+      wl = sc.y * e / st.y;
+    }
+    float2 acc[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      const float w = __shfl_sync(0xffffffffu, wl, h);
+      const float2 p = *reinterpret_cast<const float2*>(a.cache + (size_t)r * (H * C) + h * C + 2 * lane);
+      acc[h] = make_float2(p.x * w, p.y * w);
+    }
+    const int k0 = a.first[b], k1 = (b + 1 < a.N) ? a.first[b + 1] : a.count[0];
+    for (int kb = k0; kb < k1; kb += 32) {
+      const int nk = (k1 - kb < 32) ? (k1 - kb) : 32;
+      const int g = (lane < nk) ? a.rows[kb + lane] - b * L : 0;       // lane l holds the l-th generated key of this pass
+      float al[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) al[h] = (lane < nk) ? alpha_row0[(size_t)h * L * Lp + g] : 0.f;
+      // eight z rows in flight per warp (the kernel is latency-, not bandwidth-bound: ~11 KB per query row)
+      for (int k8 = 0; k8 < nk; k8 += 8) {
+        float2 zv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int gk = __shfl_sync(0xffffffffu, g, (k8 + u) & 31);
+          // (beyond nk: lane's g is 0, a valid row, and its weight below is 0 -- an unconditional load keeps all eight in flight)
+          zv[u] = __ldg(reinterpret_cast<const float2*>(a.z + (((size_t)b * L + i) * L + gk) * C + 2 * lane));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            const float w = __shfl_sync(0xffffffffu, al[h], (k8 + u) & 31);      // (0 beyond nk)
+            acc[h].x = fmaf(w, zv[u].x, acc[h].x);
+            acc[h].y = fmaf(w, zv[u].y, acc[h].y);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) *reinterpret_cast<float2*>(feat_row + h * C + 2 * lane) = acc[h];
+  }
+}
+
+void launch_ctx_delta(int N, int L, int Lp, const float* z, const uint8_t* mask, float* alpha, const float* cache,
+                      const float2* stats_ctx, const float2* stats, const int* cidx, const int* rows, const int* first,
+                      const int* count, float* feat, cudaStream_t st) {
+  ProfScope prof__(KK_CTX, st);
+  const CtxDeltaArgs a{N, L, Lp, z, mask, alpha, cache, stats_ctx, stats, cidx, rows, first, count, feat};
+  int grid = (N * L + 7) / 8;
+  const int cap = (g_sm_count > 0 ? g_sm_count : 148) * 3;      // one resident wave (3 CTAs per SM), rows strided over the warps
+  if (grid > cap) grid = cap;
+  ctx_delta_kernel<<<grid, 256, 0, st>>>(a);
+}
+
+bool launch_pair_stream(int nb, int b0, int L, int Lp, const float* z, float* alpha, float* feat, const PairRows& pr, cudaStream_t st,
+                        int feat_ld, bool partial) {
   CUtensorMap amap;
   // alpha as a plain 3-D tensor [nb * H][L queries][Lp keys]; box = [12 heads][1 query][16 keys]
   if (!make_tmap_3d_plain(&amap, alpha, (uint64_t)Lp, (uint64_t)L, (uint64_t)nb * H, PW_CJ, 1, H)) return false;
-  ProfScope prof__(KK_PAIR, st);
+  ProfScope prof__(partial ? KK_PAIR_PART : KK_PAIR, st);
   PairRowsArgs a{};
   a.L = L; a.Lp = Lp; a.b0 = b0; a.nrows = nb * L; a.nchunk = (L + PW_CJ - 1) / PW_CJ;
-  a.z = z; a.alpha = alpha; a.feat = feat; a.list = pr.list; a.count = pr.count;
+  a.z = z; a.alpha = alpha; a.feat = feat; a.feat_ld = feat_ld; a.list = pr.list; a.count = pr.count;
   int grid = g_sm_count > 0 ? g_sm_count : 148;
   const int need = (a.nrows + PW_WARPS - 1) / PW_WARPS;
   if (grid > need) grid = need;

@@ -85,7 +85,8 @@ bool attn_needs_qk_lo(int L);      // true when the logits kernel for this lengt
 void attn_debug_clocks(long long* out16);
 // final logits + softmax on the tensor cores: alpha[chunk][h][i][Lp] for complexes [b0, b0 + nb)
 bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOperands& op, const float* bias_layer, const uint8_t* mask,
-                           float* alpha, cudaStream_t st, const int2* windows = nullptr, const int* wcount = nullptr);
+                           float* alpha, cudaStream_t st, const int2* windows = nullptr, const int* wcount = nullptr,
+                           const uint8_t* exclude = nullptr, float2* stats = nullptr);
 bool make_tmap_3d(CUtensorMap* m, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1);
 
 void launch_mixer(int M, const float* res_feat, const long long* s_t, const float* v_t, const EpsW& w,
@@ -121,8 +122,15 @@ struct PairRows {
   int* count;         // [2]  live rows | masked rows that still need their zeros (device)
 };
 // cidx (focus mode): compact output row of residue row r, -1 = row not needed at all
-void launch_pair_rows_build(int nb, int b0, int L, const uint8_t* mask, const int* cidx, const PairRows& pr, cudaStream_t st);
-bool launch_pair_stream(int nb, int b0, int L, int Lp, const float* z, float* alpha, float* feat, const PairRows& pr, cudaStream_t st);
+// compact: the output row of a listed row is cidx[row] (focus mode); otherwise the row itself
+void launch_pair_rows_build(int nb, int b0, int L, const uint8_t* mask, const int* cidx, const PairRows& pr, cudaStream_t st,
+                            bool compact = true);
+bool launch_pair_stream(int nb, int b0, int L, int Lp, const float* z, float* alpha, float* feat, const PairRows& pr, cudaStream_t st,
+                        int feat_ld = NFEAT, bool partial = false);      // partial: the list holds the generated rows only (profile kind)
+// context cache of the first GABlock inside the sampling loop (k_pair.cu: ctx_delta_kernel)
+void launch_ctx_delta(int N, int L, int Lp, const float* z, const uint8_t* mask, float* alpha, const float* cache,
+                      const float2* stats_ctx, const float2* stats, const int* cidx, const int* rows, const int* first,
+                      const int* count, float* feat, cudaStream_t st);
 bool make_tmap_3d_plain(CUtensorMap* m, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1, uint32_t box2);
 
 void launch_angle_argmax(int M, int L, const long long* tvec, int t_uniform, const float* Y, const float* expo,

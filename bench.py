@@ -367,31 +367,40 @@ def run_ours(args, cfg, rank, world, local_rank):
         torch.cuda.synchronize()
         prof = _capi.profile_collect()
         _capi.profile_enable(False)
-        pair_ms, pair_n = prof['pair']
+        full_ms, full_n = prof['pair']                    # full-stream launches of pair_stream_kernel
+        part_ms, part_n = prof['pair_part']               # launches that visit the generated query rows only
+        pair_ms, pair_n = full_ms + part_ms, full_n + part_n
         total_ms = sum(v[0] for v in prof.values())
         peak, peak_src = measured_peak_gbs()
-        per_launch_complexes = B * NUM_LAYERS * T_STEPS / max(pair_n, 1)
-        # Focus mode: for models without the pRMSD head the LAST block streams z only for the generated
-        # query rows, so that launch has fewer algorithmic bytes.  The kernel-level roofline is bytes-weighted over all
-        # pair_stream_kernel launches of a sample; whole_step_* keep SURVEY 8d's fixed denominator (z once per layer).
-        focus = cfg['flavour'] == 'abdesign' and os.environ.get('ABOPT_NO_FOCUS', '0') != '1'
-        alg_full = per_launch_complexes * algorithmic_bytes_per_complex_layer(L)
-        alg_focus = per_launch_complexes * (n_gen * L * 64 * 4 + L * (2 * 128 * 4 + 36 + 12 + 1))
-        alg_bytes = ((NUM_LAYERS - 1) * alg_full + (alg_focus if focus else alg_full)) / NUM_LAYERS      # mean per launch
-        achieved = alg_bytes / (pair_ms / pair_n * 1e-3) / 1e9
+        # pair_stream_kernel: one launch per layer and step.  Inside the loop up to two of the six layers stream z for the GENERATED
+        # query rows only: the last block of a model without the pRMSD head (focus mode) and the first block
+        # (context cache: the context queries take the context part of their aggregate from a per-run cache and read only the
+        # generated keys' z rows, in ctx_delta_kernel, timed as its own kind).  `frac` is bytes-weighted over ALL launches of the
+        # kernel (total algorithmic bytes / total time); `full_stream` is the same for the full-stream launches alone;
+        # whole_step_* keep SURVEY 8d's fixed denominator (z once per layer).
+        alg_full = B * algorithmic_bytes_per_complex_layer(L)
+        alg_part = B * (n_gen * L * 64 * 4 + L * (2 * 128 * 4 + 36 + 12 + 1))
+        alg_bytes = (full_n * alg_full + part_n * alg_part) / max(pair_n, 1)      # mean per launch
+        achieved = alg_bytes / (pair_ms / max(pair_n, 1) * 1e-3) / 1e9
+        full_achieved = alg_full / (full_ms / max(full_n, 1) * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, 'profiles', 'pair_kernel_traffic.json')
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             if tj.get('L') == L:
-                traffic = tj['dram_bytes_per_complex'] * per_launch_complexes * alg_bytes / alg_full
+                traffic = tj['dram_bytes_per_complex'] * B * alg_bytes / alg_full
         whole = B * NUM_LAYERS * T_STEPS * algorithmic_bytes_per_complex_layer(L) / (ms_per_step * 1e-3) / 1e9
         roof = {'bound': 'hbm', 'kernel': 'pair_stream_kernel (streams pair_feat once per IPA layer: softmax-weighted pair aggregation)',
                 'achieved': achieved, 'peak': peak,
                 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                'algorithmic_bytes_per_launch': alg_bytes, 'avg_launch_ms': pair_ms / pair_n, 'launches_per_sample': pair_n,
-                'focus': ('last of %d layers streams only the %d generated query rows per complex; achieved / traffic / '
-                          'algorithmic bytes are means over all launches of a sample' % (NUM_LAYERS, n_gen)) if focus else None,
+                'algorithmic_bytes_per_launch': alg_bytes, 'avg_launch_ms': pair_ms / max(pair_n, 1), 'launches_per_sample': pair_n,
+                'full_stream': {'launches': full_n, 'avg_launch_ms': full_ms / max(full_n, 1), 'algorithmic_bytes_per_launch': alg_full,
+                                'achieved': full_achieved, 'frac': full_achieved / peak},
+                'generated_rows_only': {'launches': part_n, 'avg_launch_ms': part_ms / max(part_n, 1),
+                                        'algorithmic_bytes_per_launch': alg_part,
+                                        'note': 'last block (focus mode) and first block (context cache; ctx_delta_kernel beside it: '
+                                                '%d launches, %.1f us each)' % (prof['ctx'][1], 1e3 * prof['ctx'][0] / max(prof['ctx'][1], 1))}
+                if part_n else None,
                 'share_of_gpu_time': pair_ms / total_ms,
                 'whole_step_achieved': whole, 'whole_step_frac': whole / peak}
         breakdown = {k: {'ms': round(v[0], 3), 'launches': v[1]} for k, v in prof.items() if v[1]}

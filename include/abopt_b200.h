@@ -98,8 +98,9 @@ uint64_t    abopt_kernel_launch_count(void);
  * library is bracketed by a CUDA event pair on its stream.  abopt_profile_collect() synchronises,
  * sums milliseconds and launch counts per kernel kind and clears the records.  Kinds, in order:
  * 0 mixer, 1 projections, 2 logits, 3 pair stream, 4 aggregation, 5 block tail, 6 heads,
- * 7 transition step, 8 other.  Not for use inside timed regions (events perturb the pipeline). */
-#define ABOPT_KERNEL_KINDS 9
+ * 7 transition step, 8 other, 9 context-cache delta (first block inside the sampling loop), 10 pair stream launches that visit
+ * the generated query rows only (3 = the full-stream launches).  Not for use inside timed regions (events perturb the pipeline). */
+#define ABOPT_KERNEL_KINDS 11
 int abopt_profile_enable(int on);
 int abopt_profile_collect(double* ms_per_kind, uint64_t* launches_per_kind, int n_kinds);
 

@@ -281,6 +281,42 @@ def test_optimize_replayed_noise_matches_oracle():
     torch.testing.assert_close(traj[2][4].cpu(), ref[2][4], rtol=1e-4, atol=1e-5)       # perplexity (no mask in optimize)
 
 
+@pytest.mark.parametrize('name,B', [('c2', 16), ('c4', 5), ('c3', 6)])
+def test_context_cache_matches_full_stream(name, B):
+    """Inside the sampling loop the first GABlock reuses the context part of its pair aggregate (k_pair.cu: ctx_delta_kernel)
+    instead of streaming all of z: the same numbers up to fp32 reassociation.  Philox mode, same seed, with the cache and with
+    ABOPT_NO_CTXCACHE=1; one reverse step apart the states agree to rounding, three steps apart to what rounding grows into."""
+    cfg = dict(CONFIGS[name]); cfg['B'] = B
+    W = weights.make_state_dict(seed=31, num_layers=3, flavour=cfg['flavour'])
+    model = build_model(W, 3, flavour=cfg['flavour'], obj=cfg['obj'])
+    d = device_batch(cfg, 700)
+    d['mask_res'][0, 3:7] = False                         # masked context queries / keys in the first complex as well
+    d['mask_generate'] &= d['mask_res']
+    a = lambda x: (x['v'], x['p'], x['s'], 3, x['res_feat'], x['pair_feat'], x['mask_generate'], x['mask_res'])
+    kw = dict(seed=77, sample_structure=cfg['structure'], sample_sequence=cfg['sequence'])
+    old = os.environ.get('ABOPT_NO_CTXCACHE')
+    try:
+        os.environ.pop('ABOPT_NO_CTXCACHE', None)
+        fast = model.optimize(*a(d), **kw)
+        os.environ['ABOPT_NO_CTXCACHE'] = '1'
+        full = model.optimize(*a(d), **kw)
+    finally:
+        if old is None:
+            os.environ.pop('ABOPT_NO_CTXCACHE', None)
+        else:
+            os.environ['ABOPT_NO_CTXCACHE'] = old
+    live = d['mask_res'].cpu()
+    for t_, tol in ((3, 0.0), (2, 2e-4), (0, 5e-3)):
+        pf, pu = fast[t_][1].cpu()[live], full[t_][1].cpu()[live]
+        assert torch.isfinite(pf).all()
+        assert (pf - pu).abs().max() <= tol, f'positions differ at t={t_}: {(pf - pu).abs().max()}'
+        rf, ru = G.so3_exp(fast[t_][0].cpu())[live], G.so3_exp(full[t_][0].cpu())[live]
+        bad = ((rf - ru).abs().amax(dim=(-1, -2)) > 10 * tol + 1e-6)
+        assert int(bad.sum()) <= (0 if t_ == 3 else 2), f'rotations differ at t={t_}'
+        flips = int((fast[t_][2].cpu()[live] != full[t_][2].cpu()[live]).sum())
+        assert flips <= (0 if t_ == 3 else 2), f'{flips} sequence flips at t={t_}'
+
+
 # ------------------------------------------------------------------------------------------ (iii) trained weights
 def test_trained_checkpoint_slice(golden_dir):
     """Blocks 0-1, mixer and heads of the reference's dock_single_cdr/250000.pt on features produced by the checkpoint's own
