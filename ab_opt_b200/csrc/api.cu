@@ -70,6 +70,10 @@ struct Workspace {
   Focus focus;
   PairRows prows[3];            // row lists of pair_stream_kernel: [0] every row, [1] focus mode (generated rows, compact output),
                                 // [2] generated rows in place (first block with the context cache)
+  // loop invariants of the sampling loop (context residues): mixer output and the first block's packed operands keep their own
+  // buffers, so that per step only the generated rows are recomputed (x0_c / x0_c_lo: those rows, compact, the projection's input)
+  float *x0, *x0_lo, *x0_c, *x0_c_lo;
+  AttnOperands op0;
   float* ctx_cache;             // [N * L][768]  context part of the first block's pair aggregate (k_pair.cu: ctx_delta_kernel)
   float2 *ctx_stats, *step_stats;      // [N][H][L] softmax statistics: context keys only (once per run) / all keys (this step)
 };
@@ -98,6 +102,7 @@ struct abopt_model {
   bool focus_built = false;     // inside abopt_sample_*: the focus lists of mask_generate were built once for the whole run
   bool prows_built[3] = {false, false, false};      // likewise the row lists of pair_stream_kernel (mask_res / the focus list are loop invariants)
   bool ctx_built = false;       // ... and the context cache of the first block
+  bool x0_built = false;        // ... and the mixer output / first-block operands of the context rows
   EpsW eps;
   DiffW diff;
   Workspace ws;
@@ -578,7 +583,10 @@ static int ensure_workspace(abopt_model* m, int N, int L) {
                oVt = take((size_t)N * H * 64 * Lp * 4),
                oFc = take(M * 4), oFr = take(M * 4), oFw = take((size_t)N * (L / 64 + 2) * 8), oFn = take(64), oFs = take((size_t)N * 8),
                oFx = take(M * F * 4), oFm = take(M), oPr0 = take(M * 16), oPr1 = take(M * 16), oPr2 = take(M * 16), oPrc = take(64),
-               oCc = take(M * H * C * 4), oCs = take(M * H * 8), oCt = take(M * H * 8);
+               oCc = take(M * H * C * 4), oCs = take(M * H * 8), oCt = take(M * H * 8),
+               oX0 = take(M * F * 4), oX0l = take(M * F * 4), oX0c = take(M * F * 4), oX0cl = take(M * F * 4),
+               oQa0 = take(M * H * 64 * 4), oKb0 = take(M * H * 64 * 4), oRq0 = take(M * H * 4), oRk0 = take(M * H * 4),
+               oVt0 = take((size_t)N * H * 64 * Lp * 4);
   CUDA_TRY(cudaMalloc(&w.base, off));
   CUDA_TRY(cudaMemset(w.base, 0, off));        // the padding rows / columns of the packed attention operands must stay zero
   unsigned char* b = static_cast<unsigned char*>(w.base);
@@ -595,6 +603,9 @@ static int ensure_workspace(abopt_model* m, int N, int L) {
   w.prows[1] = PairRows{(int4*)(b + oPr1), (int*)(b + oPrc) + 2};
   w.prows[2] = PairRows{(int4*)(b + oPr2), (int*)(b + oPrc) + 4};
   w.ctx_cache = (float*)(b + oCc); w.ctx_stats = (float2*)(b + oCs); w.step_stats = (float2*)(b + oCt);
+  w.x0 = (float*)(b + oX0); w.x0_lo = (float*)(b + oX0l); w.x0_c = (float*)(b + oX0c); w.x0_c_lo = (float*)(b + oX0cl);
+  w.op0 = AttnOperands{(float*)(b + oQa0), (float*)(b + oQl), (float*)(b + oKb0), (float*)(b + oKl), (float*)(b + oRq0), (float*)(b + oRk0),
+                       (float*)(b + oVt0)};
   w.N = N; w.L = L; w.Lp = Lp; w.NB = NB; w.bytes = off;
   return ABOPT_OK;
 }
@@ -647,20 +658,26 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
     const int nb = (N - b0 < w.NB) ? (N - b0) : w.NB;
     // one pass = as many complexes as the alpha buffer holds (normally the whole batch, see chunk_size): projections ->
     // packed attention operands -> alpha -> aggregates; every tensor between two kernels travels through HBM / L2 once
-    {
+    // Loop invariance of the first block inside the sampling loop (context cache, k_pair.cu): everything a context residue feeds
+    // into it is the same at every step.  Its packed operands live in their own buffers (w.op0: the other layers reuse w.op), so
+    // after the first step only the generated rows are projected; the context part of the pair aggregate is computed once per
+    // run and only the generated keys' share of z is streamed per step.
+    const bool ctx = layer == 0 && ctx_cache_gen != nullptr && nb == N && fc == nullptr;
+    const AttnOperands& ops = ctx ? w.op0 : w.op;
+    if (ctx && m->ctx_built) {
+      // x = w.x0 here; w.x0_c / w.x0_c_lo hold its generated rows, compact (mixer_kernel)
+      if (!launch_proj_pack(N * L, L, w.Lp, w.x0_c, w.x0_c_lo, bw.Wcat, bw.Wcat_lo, R, t, bw.coef, ops, st, w.focus.rows, w.focus.count))
+        return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (proj)");
+    } else {
       const size_t r0 = (size_t)b0 * L, o64 = (size_t)b0 * H * L * 64, o1 = (size_t)b0 * H * L, ov = (size_t)b0 * H * 64 * w.Lp;
       // (QA_lo / KB_lo are placeholders: every logits kernel builds the lo planes of its operands on chip)
-      const AttnOperands opc{w.op.QA + o64, w.op.QA_lo, w.op.KB + o64, w.op.KB_lo, w.op.rq + o1, w.op.rk + o1,
-                             w.op.VT + ov};
+      const AttnOperands opc{ops.QA + o64, ops.QA_lo, ops.KB + o64, ops.KB_lo, ops.rq + o1, ops.rk + o1, ops.VT + ov};
       if (!launch_proj_pack(nb * L, L, w.Lp, x + r0 * F, x_lo + r0 * F, bw.Wcat, bw.Wcat_lo, R + r0 * 9, t + r0 * 3, bw.coef, opc, st))
         return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (proj)");
     }
-    // Context cache (k_pair.cu): inside the sampling loop the first block's logits between context residues are loop invariants,
-    // so the context part of its pair aggregate is computed once per run and only the generated keys' share is streamed per step.
-    const bool ctx = layer == 0 && ctx_cache_gen != nullptr && nb == N && fc == nullptr;
     if (ctx && !m->ctx_built) {
       // once per run: softmax over the context keys alone (+ its statistics) and the pair aggregate of every query row with it
-      if (!launch_attn_logits_tc(nb, b0, N, L, w.Lp, w.op, bias, mask, w.alpha, st, nullptr, nullptr, ctx_cache_gen, w.ctx_stats))
+      if (!launch_attn_logits_tc(nb, b0, N, L, w.Lp, ops, bias, mask, w.alpha, st, nullptr, nullptr, ctx_cache_gen, w.ctx_stats))
         return fail(ABOPT_ERR_CUDA, "attn_logits_tc launch failed");
       if (!m->prows_built[0]) { launch_pair_rows_build(nb, b0, L, mask, nullptr, w.prows[0], st); m->prows_built[0] = true; }
       if (!launch_pair_stream(nb, b0, L, w.Lp, z, w.alpha, w.ctx_cache, w.prows[0], st, H * C))
@@ -669,7 +686,7 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
       m->ctx_built = true;
     }
     // logits (node + spatial + pair bias, scaled, masked) and softmax on the tensor cores -> alpha
-    if (!launch_attn_logits_tc(nb, b0, N, L, w.Lp, w.op, bias, mask, w.alpha, st, fc ? fc->windows : nullptr, fc ? fc->count : nullptr,
+    if (!launch_attn_logits_tc(nb, b0, N, L, w.Lp, ops, bias, mask, w.alpha, st, fc ? fc->windows : nullptr, fc ? fc->count : nullptr,
                                nullptr, ctx ? w.step_stats : nullptr))
       return fail(ABOPT_ERR_CUDA, "attn_logits_tc launch failed");
     if (ctx) {
@@ -685,7 +702,7 @@ static int run_block(abopt_model* m, int layer, int N, int L, const float* R, co
       if (!launch_pair_stream(nb, b0, L, w.Lp, z, w.alpha, w.feat, w.prows[which], st, NFEAT, /*partial=*/fc != nullptr))
         return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (pair)");
     }
-    if (!launch_aggr_tc(nb, b0, N, L, w.Lp, w.alpha, w.op.VT, R, t, w.feat, st, fc ? fc->windows : nullptr,
+    if (!launch_aggr_tc(nb, b0, N, L, w.Lp, w.alpha, ops.VT, R, t, w.feat, st, fc ? fc->windows : nullptr,
                         fc ? fc->count : nullptr, fc ? fc->cidx : nullptr))
       return fail(ABOPT_ERR_CUDA, "aggr_tc launch failed");
     if (alpha_tap) launch_alpha_tap(nb, b0, L, w.Lp, w.alpha, alpha_tap, st);
@@ -787,14 +804,24 @@ static int run_eps_net(abopt_model* m, int N, int L, const float* v_t, const flo
     hf = &w.focus;
     if (!m->cfg.has_prmsd && w.NB >= N) fc = &w.focus;
   }
-  launch_mixer(M, res_feat, s_t, v_t, m->eps, w.xa, w.Rbuf, p_ang, w.pnorm, m->diff.pos_mean, m->diff.pos_scale, w.xa_lo, st);
+  // context invariance inside the sampling loop (everything a context residue feeds into the mixer and the first block is a loop
+  // invariant there): with the focus lists built.  ABOPT_NO_CTXCACHE=1 disables it (read per call, like ABOPT_NO_FOCUS).
+  const char* nc = getenv("ABOPT_NO_CTXCACHE");
+  const bool ctx_on = hf != nullptr && m->bias_hoisted && m->focus_built && w.NB >= N && m->cfg.num_layers >= 2 && p_ang != nullptr &&
+                      !(nc && nc[0] == '1');
+  float* x0 = ctx_on ? w.x0 : w.xa;
+  float* x0_lo = ctx_on ? w.x0_lo : w.xa_lo;
+  if (ctx_on && m->x0_built) {
+    // generated rows only: in place, and compact for the first block's projection
+    launch_mixer(M, res_feat, s_t, v_t, m->eps, x0, w.Rbuf, p_ang, w.pnorm, m->diff.pos_mean, m->diff.pos_scale, x0_lo, st,
+                 w.focus.rows, w.focus.count, w.x0_c, w.x0_c_lo);
+  } else {
+    launch_mixer(M, res_feat, s_t, v_t, m->eps, x0, w.Rbuf, p_ang, w.pnorm, m->diff.pos_mean, m->diff.pos_scale, x0_lo, st);
+    if (ctx_on) m->x0_built = true;
+  }
   const float* tpos = p_ang ? w.pnorm : p_t;
   float* enc = nullptr;
-  // context cache of the first block: only inside the sampling loop (everything a context residue feeds into the first block is
-  // a loop invariant there), with the focus lists built.  ABOPT_NO_CTXCACHE=1 disables it (read per call, like ABOPT_NO_FOCUS).
-  const char* nc = getenv("ABOPT_NO_CTXCACHE");
-  const bool ctx_on = hf != nullptr && m->bias_hoisted && m->focus_built && w.NB >= N && m->cfg.num_layers >= 2 && !(nc && nc[0] == '1');
-  int rc = run_encoder(m, N, L, w.Rbuf, tpos, w.xa, w.xa_lo, pair_feat, mask_res, &enc, st, fc, ctx_on ? mask_gen : nullptr);
+  int rc = run_encoder(m, N, L, w.Rbuf, tpos, x0, x0_lo, pair_feat, mask_res, &enc, st, fc, ctx_on ? mask_gen : nullptr);
   if (rc) return rc;
   launch_heads(M, L, enc, beta, beta_stride, w.Rbuf, v_t, mask_gen, m->eps, v_next, R_next, eps_pos, c_den, w.prmsd_rows,
                m->cfg.has_prmsd ? (prmsd_logits ? prmsd_logits : w.prmsd_logits) : nullptr, st, hf ? hf->rows : nullptr,
@@ -998,6 +1025,7 @@ extern "C" int abopt_sample_device(abopt_model* m, int N, int L, const float* v,
   m->focus_built = false;
   m->prows_built[0] = m->prows_built[1] = false;
   m->ctx_built = false;
+  m->x0_built = false;
   for (int t = T0; t >= 1 && rc == ABOPT_OK; --t)
     rc = run_step(m, N, L, t, optimize, flags, seed, V(t), Pp(t), S(t), res_feat, pair_feat, mask_generate, mask_res,
                   noise ? &noise[T0 - t] : nullptr, V(t - 1), Pp(t - 1), S(t - 1), PR(t - 1), PL(t - 1), st);
@@ -1005,6 +1033,7 @@ extern "C" int abopt_sample_device(abopt_model* m, int N, int L, const float* v,
   m->focus_built = false;
   m->prows_built[0] = m->prows_built[1] = false;
   m->ctx_built = false;
+  m->x0_built = false;
   return rc;
 }
 

@@ -548,6 +548,13 @@ struct AggrArgs {
 //   warps 6-9   epilogue: thread = query row: 64 sums -> node aggregate, R_i^T (o - t_i), norms, directions; every feature
 //               group of a row is a 32-byte-aligned run, stored with 256-bit stores (full sectors, no staging buffer)
 constexpr int AGP_THREADS = 320, AGP_ST = 4;
+// Tile walk from the LAST complex to the first: pair_stream_kernel has just read alpha in forward order, so what is still in the
+// 126 MB L2 is the tail of it -- and this kernel is bound by the latency of its ring, not by bandwidth.
+#ifndef ABOPT_AGP_FWD
+#define AGP_TILE(t) (ntiles - 1 - (t))
+#else
+#define AGP_TILE(t) (t)
+#endif
 constexpr int AGP_SMEM = AGP_ST * AG2_STAGE_BYTES + 256 + 1024;
 
 __device__ __forceinline__ void st_v8f(float* p, float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
@@ -590,7 +597,7 @@ aggr_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (elect_one()) {
       int g = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const TileRef tr = tile_ref(tile, nit, windows);
+        const TileRef tr = tile_ref(AGP_TILE(tile), nit, windows);
         const int arow = (tr.bl * H + tr.h) * L + tr.i0, vrow = ((a.b0 + tr.bl) * H + tr.h) * 64;
         for (int kb = 0; kb < nkb; ++kb, ++g) {
           const int s = g % AGP_ST;
@@ -662,7 +669,7 @@ aggr_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int ngrp = (nkb + gsz - 1) / gsz;
     int n = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
-      const TileRef tr = tile_ref(tile, nit, windows);
+      const TileRef tr = tile_ref(AGP_TILE(tile), nit, windows);
       const int h = tr.h, b = a.b0 + tr.bl;
       const int buf = n & 1;
       const int i = tr.i0 + q * 32 + lane;

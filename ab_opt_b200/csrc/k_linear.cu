@@ -8,26 +8,35 @@
 namespace abopt {
 
 // ------------------------------------------------------------------------------------------ mixer
+// rows / count (optional, inside the sampling loop): only the listed rows are evaluated -- everything the mixer reads of a context
+// residue is a loop invariant there (res_feat, its sequence, its frame), so after the first step only the generated rows change.
+// Results go to their place in x_out / x_lo_out / Rbuf / p_norm and, compact (row k of the list), to x_c / x_c_lo.
 __global__ void __launch_bounds__(RT_THREADS, 2)
 mixer_kernel(int M, const float* __restrict__ res_feat, const long long* __restrict__ s_t,
              const float* __restrict__ v_t, EpsW w, float* __restrict__ x_out, float* __restrict__ Rbuf,
              const float* __restrict__ p_ang, float* __restrict__ p_norm, float mean0, float mean1, float mean2, float scale,
-             float* __restrict__ x_lo_out) {
+             float* __restrict__ x_lo_out, const int* __restrict__ rows, const int* __restrict__ count,
+             float* __restrict__ x_c, float* __restrict__ x_c_lo) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RowTileSmem& s = *reinterpret_cast<RowTileSmem*>(smem_raw);
   float* act = reinterpret_cast<float*>(smem_raw + sizeof(RowTileSmem));      // [64][RT_ACT_LD]
   __shared__ int aa[RT_ROWS];
+  __shared__ int ridx[RT_ROWS];         // residue row of tile row r, -1 = none
   const int row0 = blockIdx.x * RT_ROWS;
+  const int nrows = rows ? count[0] : M;
+  if (row0 >= nrows) return;
   if (threadIdx.x < RT_ROWS) {
-    const int r = row0 + threadIdx.x;
-    long long a = (r < M) ? s_t[r] : 0;
+    const int k = row0 + threadIdx.x;
+    const int r = (k < nrows) ? (rows ? rows[k] : k) : -1;
+    ridx[threadIdx.x] = r;
+    long long a = (r >= 0) ? s_t[r] : 0;
     aa[threadIdx.x] = (int)(a < 0 ? 0 : (a > 24 ? 24 : a));
-    if (r < M && p_ang != nullptr) {     // FullDPM._normalize_position (dpm_full.py:148-150)
+    if (r >= 0 && p_ang != nullptr) {     // FullDPM._normalize_position (dpm_full.py:148-150)
       p_norm[(size_t)r * 3 + 0] = __fdiv_rn(__fadd_rn(p_ang[(size_t)r * 3 + 0], -mean0), scale);
       p_norm[(size_t)r * 3 + 1] = __fdiv_rn(__fadd_rn(p_ang[(size_t)r * 3 + 1], -mean1), scale);
       p_norm[(size_t)r * 3 + 2] = __fdiv_rn(__fadd_rn(p_ang[(size_t)r * 3 + 2], -mean2), scale);
     }
-    if (r < M && Rbuf != nullptr) {
+    if (r >= 0 && Rbuf != nullptr) {
       const Mat3 R = so3_exp(v_t[r * 3 + 0], v_t[r * 3 + 1], v_t[r * 3 + 2]);
 #pragma unroll
       for (int i = 0; i < 9; ++i) Rbuf[(size_t)r * 9 + i] = R.m[i];
@@ -38,8 +47,8 @@ mixer_kernel(int M, const float* __restrict__ res_feat, const long long* __restr
   rt_zero(acc);
   // layer 0: [res_feat | embedding(s_t)] (K = 256) -> 128, ReLU
   rt_gemm_globalA(acc, s, [&](int r, int k) -> const float* {
-    if (row0 + r >= M) return nullptr;
-    return (k < F) ? res_feat + (size_t)(row0 + r) * F + k : w.emb + (size_t)aa[r] * F + (k - F);
+    if (ridx[r] < 0) return nullptr;
+    return (k < F) ? res_feat + (size_t)ridx[r] * F + k : w.emb + (size_t)aa[r] * F + (k - F);
   }, w.Wm0_t, 2 * F);
   rt_add_bias(acc, w.bm0);
   rt_relu(acc);
@@ -51,11 +60,17 @@ mixer_kernel(int M, const float* __restrict__ res_feat, const long long* __restr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
-    const int row = row0 + warp * 8 + r;
-    if (row < M) {
-      *reinterpret_cast<float4*>(x_out + (size_t)row * F + lane * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-      if (x_lo_out != nullptr)
-        *reinterpret_cast<float4*>(x_lo_out + (size_t)row * F + lane * 4) = make_float4(tf32_lo(acc[r][0]), tf32_lo(acc[r][1]), tf32_lo(acc[r][2]), tf32_lo(acc[r][3]));
+    const int row = ridx[warp * 8 + r];
+    if (row >= 0) {
+      const float4 hi = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      const float4 lo = make_float4(tf32_lo(acc[r][0]), tf32_lo(acc[r][1]), tf32_lo(acc[r][2]), tf32_lo(acc[r][3]));
+      *reinterpret_cast<float4*>(x_out + (size_t)row * F + lane * 4) = hi;
+      if (x_lo_out != nullptr) *reinterpret_cast<float4*>(x_lo_out + (size_t)row * F + lane * 4) = lo;
+      if (x_c != nullptr) {
+        const size_t kc = (size_t)(row0 + warp * 8 + r) * F + lane * 4;
+        *reinterpret_cast<float4*>(x_c + kc) = hi;
+        *reinterpret_cast<float4*>(x_c_lo + kc) = lo;
+      }
     }
   }
 }
@@ -310,10 +325,11 @@ cudaError_t linear_kernels_init() {
 
 void launch_mixer(int M, const float* res_feat, const long long* s_t, const float* v_t, const EpsW& w,
                   float* x_out, float* Rbuf, const float* p_ang, float* p_norm, const float* mean, float scale,
-                  float* x_lo_out, cudaStream_t st) {
+                  float* x_lo_out, cudaStream_t st, const int* rows, const int* count, float* x_c, float* x_c_lo) {
   ProfScope prof__(KK_MIXER, st);
   mixer_kernel<<<(M + RT_ROWS - 1) / RT_ROWS, RT_THREADS, mixer_smem(), st>>>(M, res_feat, s_t, v_t, w, x_out, Rbuf, p_ang, p_norm,
-                                                                           mean[0], mean[1], mean[2], scale, x_lo_out);
+                                                                           mean[0], mean[1], mean[2], scale, x_lo_out, rows, count,
+                                                                           x_c, x_c_lo);
 }
 void launch_heads(int M, int L, const float* x, const float* beta, int beta_stride, const float* Rbuf, const float* v_t,
                   const uint8_t* mask_gen, const EpsW& w, float* v_next, float* R_next, float* eps_pos, float* c_den,

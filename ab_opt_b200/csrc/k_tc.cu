@@ -63,6 +63,10 @@ struct EpiProjPack {
   float* QA; float* QA_lo; float* KB; float* KB_lo; float* rq; float* rk; float* VT;
   int L, Lp;
   int qk_lo;            // 1: also write QA_lo / KB_lo (only the non-persistent logits kernels read them)
+  const int* rows;      // optional: the A operand holds a compact list of residue rows (row k of it = residue row rows[k],
+  const int* count;     //           count[0] of them, device side); the packed outputs go to the residues' own places
+  int nsplit;           // work unit = (row tile, 1 / nsplit of the 21 column tiles): 1 for a full batch (x stays resident over all
+                        // column tiles), 7 for a short row list, where one CTA per row tile would leave most SMs idle
 };
 
 // Accuracy note (measured on B200, scripts/debug_gemm.py): the tensor core TRUNCATES the fp32 accumulator on every
@@ -239,7 +243,9 @@ proj_persist_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nmt = (M + G_BM - 1) / G_BM;
+  const int Mrows = ep.rows ? min(M, ep.count[0]) : M;      // (compact list: the row count lives on the device)
+  const int nmt = (Mrows + G_BM - 1) / G_BM;
+  const int nunits = nmt * ep.nsplit;
   constexpr uint32_t ACC_COLS = 2 * PP_BN;                  // main | corrections
 
   if (threadIdx.x == 0) {
@@ -259,14 +265,16 @@ proj_persist_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
     // ===================== TMA producer =====================
     if (elect_one()) {
       int na = 0, g = 0;
-      for (int mt = blockIdx.x; mt < nmt; mt += gridDim.x, ++na) {
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++na) {
+        const int mt = u / ep.nsplit, part = u - mt * ep.nsplit;
+        const int nt0 = part * PP_NT / ep.nsplit, nt1 = (part + 1) * PP_NT / ep.nsplit;
         mbar_wait(a_empty, (na & 1) ^ 1);
         mbar_expect_tx(a_full, PP_A_TOTAL);
         for (int kb = 0; kb < PP_KB; ++kb) {
           tma_load_2d(smem + kb * 2 * PP_A_BYTES, &tmAh, kb * G_BK, mt * G_BM, a_full);
           tma_load_2d(smem + kb * 2 * PP_A_BYTES + PP_A_BYTES, &tmAl, kb * G_BK, mt * G_BM, a_full);
         }
-        for (int nt = 0; nt < PP_NT; ++nt)
+        for (int nt = nt0; nt < nt1; ++nt)
           for (int kb = 0; kb < PP_KB; ++kb, ++g) {
             const int s = g % PP_ST;
             mbar_wait(&b_empty[s], ((g / PP_ST) & 1) ^ 1);
@@ -281,9 +289,11 @@ proj_persist_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = idesc_tf32(G_BM, PP_BN);
     int na = 0, g = 0, n = 0;
-    for (int mt = blockIdx.x; mt < nmt; mt += gridDim.x, ++na) {
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++na) {
+      const int part = u % ep.nsplit;
+      const int nt0 = part * PP_NT / ep.nsplit, nt1 = (part + 1) * PP_NT / ep.nsplit;
       mbar_wait(a_full, na & 1);
-      for (int nt = 0; nt < PP_NT; ++nt, ++n) {
+      for (int nt = nt0; nt < nt1; ++nt, ++n) {
         const int buf = n & 1;
         mbar_wait(&tmem_empty[buf], ((n >> 1) & 1) ^ 1);              // epilogue group `buf` drained tile n - 2
         for (int kb = 0; kb < PP_KB; ++kb, ++g) {
@@ -306,7 +316,7 @@ proj_persist_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
             mma_commit(&b_empty[s]);
             if (kb == PP_KB - 1) {
               mma_commit(&tmem_full[buf]);
-              if (nt == PP_NT - 1) mma_commit(a_empty);
+              if (nt == nt1 - 1) mma_commit(a_empty);
             }
           }
           __syncwarp();
@@ -319,17 +329,19 @@ proj_persist_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
     const int gp = (warp - 2) >> 2;                                    // group: takes the tiles with n % 2 == gp
     const int L = ep.L, Lp = ep.Lp;
     int n = 0;
-    for (int mt = blockIdx.x; mt < nmt; mt += gridDim.x) {
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+      const int mt = u / ep.nsplit, part = u - mt * ep.nsplit;
+      const int nt0 = part * PP_NT / ep.nsplit, nt1 = (part + 1) * PP_NT / ep.nsplit;
       const int row = mt * G_BM + q * 32 + lane;
-      const bool valid = row < M;
-      const int rr = valid ? row : 0;
+      const bool valid = row < Mrows;
+      const int rr = valid ? (ep.rows ? ep.rows[row] : row) : 0;
       const int b = rr / L, r = rr - b * L;
       float Rm[9], tv[3];
 #pragma unroll
       for (int i = 0; i < 9; ++i) Rm[i] = __ldg(ep.R + (size_t)rr * 9 + i);
 #pragma unroll
       for (int i = 0; i < 3; ++i) tv[i] = __ldg(ep.t + (size_t)rr * 3 + i);
-      for (int nt = 0; nt < PP_NT; ++nt, ++n) {
+      for (int nt = nt0; nt < nt1; ++nt, ++n) {
         if ((n & 1) != gp) continue;
         mbar_wait(&tmem_full[gp], (n >> 1) & 1);
         tc_fence_after();
@@ -579,17 +591,17 @@ bool launch_gemm3x_plain(int M, int N, int K, const float* Ah, const float* Al, 
 
 // the six GABlock projections as one GEMM, outputs packed for the tensor-core attention kernels (see EpiProjPack)
 bool launch_proj_pack(int M, int L, int Lp, const float* xh, const float* xl, const float* Wh, const float* Wl, const float* R, const float* t,
-                      const float* coef, const AttnOperands& op, cudaStream_t st) {
+                      const float* coef, const AttnOperands& op, cudaStream_t st, const int* rows, const int* count) {
   CUtensorMap a_h, a_l, b_h, b_l;
   if (!make_tmap(&a_h, xh, M, F, F, G_BM) || !make_tmap(&a_l, xl, M, F, F, G_BM) || !make_tmap(&b_h, Wh, NPROJ, F, F, 96) ||
       !make_tmap(&b_l, Wl, NPROJ, F, F, 96))
     return false;
   ProfScope prof__(KK_PROJ, st);
-  const EpiProjPack ep{R, t, coef, op.QA, op.QA_lo, op.KB, op.KB_lo, op.rq, op.rk, op.VT, L, Lp, attn_needs_qk_lo(L) ? 1 : 0};
+  const EpiProjPack ep{R, t, coef, op.QA, op.QA_lo, op.KB, op.KB_lo, op.rq, op.rk, op.VT, L, Lp, attn_needs_qk_lo(L) ? 1 : 0, rows, count, rows ? 7 : 1};
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  const int nmt = (M + G_BM - 1) / G_BM;
-  proj_persist_kernel<<<nmt < sms ? nmt : sms, PP_THREADS, PP_SMEM, st>>>(a_h, a_l, b_h, b_l, M, ep);
+  const int nunits = ((M + G_BM - 1) / G_BM) * ep.nsplit;
+  proj_persist_kernel<<<nunits < sms ? nunits : sms, PP_THREADS, PP_SMEM, st>>>(a_h, a_l, b_h, b_l, M, ep);
   return true;
 }
 

@@ -73,7 +73,7 @@ struct AttnOperands {
   float* VT;                    // [N][H][64][Lp]  values, key index contiguous (rows 56..63 and columns >= L stay zero)
 };
 bool launch_proj_pack(int M, int L, int Lp, const float* xh, const float* xl, const float* Wh, const float* Wl, const float* R, const float* t,
-                      const float* coef, const AttnOperands& op, cudaStream_t st);
+                      const float* coef, const AttnOperands& op, cudaStream_t st, const int* rows = nullptr, const int* count = nullptr);
 cudaError_t aggr_tc_init();
 bool launch_aggr_tc(int nb, int b0, int N, int L, int Lp, const float* alpha, const float* VT,
                     const float* R, const float* t, float* feat, cudaStream_t st, const int2* windows = nullptr,
@@ -91,7 +91,8 @@ bool make_tmap_3d(CUtensorMap* m, const float* base, uint64_t d0, uint64_t d1, u
 
 void launch_mixer(int M, const float* res_feat, const long long* s_t, const float* v_t, const EpsW& w,
                   float* x_out, float* Rbuf, const float* p_ang, float* p_norm, const float* mean, float scale,
-                  float* x_lo_out, cudaStream_t st);
+                  float* x_lo_out, cudaStream_t st, const int* rows = nullptr, const int* count = nullptr, float* x_c = nullptr,
+                  float* x_c_lo = nullptr);
 void launch_heads(int M, int L, const float* x, const float* beta, int beta_stride, const float* Rbuf, const float* v_t,
                   const uint8_t* mask_gen, const EpsW& w, float* v_next, float* R_next, float* eps_pos, float* c_den,
                   float* prmsd_rows, float* prmsd_logits, cudaStream_t st, const int* rows = nullptr, const int* count = nullptr,
