@@ -523,13 +523,17 @@ bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOpera
 // ------------------------------------------------------------------------------------------ aggregation GEMM
 // Node and point aggregation  O[i][n] = sum_j alpha[i][j] V[j][n]  (ga.py:120-136) on the tensor cores, followed by the
 // local-frame features (ga.py:137-146).  V^T[b][h][n][j] = [ value channels (32) | global value points (24) | 0 (8) ] comes
-// K-major (key index contiguous) from the projection epilogue, alpha from the logits kernel.  Per key block of 32:
-// alpha 128 x 32 raw fp32 (its tf32 lo plane is built in shared memory), V^T 64 x 32 hi and lo planes; hi*hi goes to one of
-// three 64-column TMEM accumulators (one per third of the keys), hi*lo + lo*hi to a fourth (short accumulation chains: the
-// tensor core truncates the fp32 accumulator on every accumulation, see k_tc.cu).
+// K-major (key index contiguous) from the projection epilogue, alpha from the logits kernel.  Per key block of 32: alpha 128 x 32
+// and V^T 64 x 32 arrive raw (fp32 = the tf32 "hi" plane); hi*hi goes to one of two 64-column TMEM accumulators (one per half of
+// the keys), hi*lo + lo*hi to a third (short accumulation chains: the tensor core truncates the fp32 accumulator on every
+// accumulation, see k_tc.cu).
+// The A operand (alpha) is fed from TENSOR MEMORY (TS-mode MMAs): the splitter threads (thread = query row) move each landed alpha
+// box from shared memory into a 2-slot TMEM ring as hi | lo planes, so the MMAs read only V^T from shared memory (2 KB instead of
+// 6 KB per instruction) and a stage of the shared-memory ring shrinks from 48 to 32 KB (6 stages in flight instead of 4).
 constexpr int AG2_A_BYTES = 128 * 32 * 4, AG2_B_BYTES = 64 * 32 * 4;
-constexpr int AG2_STAGE_BYTES = 2 * AG2_A_BYTES + 2 * AG2_B_BYTES;      // 48 KB: alpha raw | alpha lo | V^T hi | V^T lo
+constexpr int AG2_STAGE_BYTES = AG2_A_BYTES + 2 * AG2_B_BYTES;          // 32 KB: alpha raw | V^T hi | V^T lo
 constexpr int AG2_TX_BYTES = AG2_A_BYTES + AG2_B_BYTES;                 // what TMA delivers per stage (the lo planes are built on chip)
+constexpr uint32_t AG2_TM_A = 0, AG2_TM_ACC = 128, AG2_ACC_COLS = 192;  // TMEM: 2 x (alpha hi 32 | lo 32) | 2 x (main 64 | main 64 | corrections 64)
 
 struct AggrArgs {
   int L, Lp, b0;
@@ -540,26 +544,27 @@ struct AggrArgs {
 // ------------------------------------------------------------------------------------------ persistent aggregation GEMM
 // aggr_persist_kernel: structured like attn_logits_persist_kernel.  One CTA per SM walks
 // the (complex, head, 128-query tile) list; the k-block ring runs across tile boundaries and the epilogue of tile n overlaps
-// the main loop of tile n + 1 (two 256-column TMEM accumulator sets):
-//   warp 0      TMA producer: key blocks of 32 through a 4-stage ring (alpha 128 x 32 and V^T 64 x 32, raw fp32 = the hi planes)
-//   warp 1      MMA issuer (waits for "split")
-//   warps 2-5   splitters: tf32 lo planes of every landed alpha and V^T box, in shared memory (no VT_lo in global memory:
-//               50 MB per layer less to write in the projection kernel and to read here)
+// the main loop of tile n + 1 (two TMEM accumulator sets):
+//   warp 0      TMA producer: key blocks of 32 through a 6-stage ring (alpha 128 x 32 and V^T 64 x 32, raw fp32 = the hi planes)
+//   warp 1      MMA issuer (waits for "split"), A from tensor memory
+//   warps 2-5   splitters, thread = query row: alpha box -> TMEM hi | lo (tcgen05.st); tf32 lo plane of the V^T box in shared
+//               memory (no VT_lo in global memory: 50 MB per layer less to write in the projection kernel and to read here)
 //   warps 6-9   epilogue: thread = query row: 64 sums -> node aggregate, R_i^T (o - t_i), norms, directions; every feature
 //               group of a row is a 32-byte-aligned run, stored with 256-bit stores (full sectors, no staging buffer)
-constexpr int AGP_THREADS = 320, AGP_ST = 4;
+constexpr int AGP_THREADS = 320, AGP_ST = 6;
 // Tile walk from the LAST complex to the first: pair_stream_kernel has just read alpha in forward order, so what is still in the
 // 126 MB L2 is the tail of it -- and this kernel is bound by the latency of its ring, not by bandwidth.
-#ifndef ABOPT_AGP_FWD
 #define AGP_TILE(t) (ntiles - 1 - (t))
-#else
-#define AGP_TILE(t) (t)
-#endif
 constexpr int AGP_SMEM = AGP_ST * AG2_STAGE_BYTES + 256 + 1024;
 
 __device__ __forceinline__ void st_v8f(float* p, float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a0), "f"(a1), "f"(a2), "f"(a3), "f"(a4),
                "f"(a5), "f"(a6), "f"(a7) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]; one thread issues
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 __global__ void __launch_bounds__(AGP_THREADS, 1)
@@ -573,17 +578,18 @@ aggr_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* empty = split + AGP_ST;
   uint64_t* tmem_full = empty + AGP_ST;      // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* ta_free = tmem_empty + 2;        // [2]  the MMAs that read TMEM alpha slot s have completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ta_free + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = a.L;
   const int nkb = (L + 31) / 32;
-  const int gsz = (nkb + 2) / 3;                        // key blocks per main accumulator (three short accumulation chains)
+  const int gsz = (nkb + 1) / 2;                        // key blocks per main accumulator (two short accumulation chains)
   const int nit = (L + 127) / 128;
   const int ntiles = windows ? wcount[1] * H : nb_complex * H * nit;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < AGP_ST; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 4); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); mbar_init(&ta_free[b], 1); }
     mbar_fence_init();
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmVh);
   }
@@ -605,7 +611,7 @@ aggr_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           unsigned char* st = smem + s * AG2_STAGE_BYTES;
           mbar_expect_tx(&full[s], AG2_TX_BYTES);
           tma_load_2d(st, &tmA, kb * 32, arow, &full[s]);
-          tma_load_2d(st + 2 * AG2_A_BYTES, &tmVh, kb * 32, vrow, &full[s]);
+          tma_load_2d(st + AG2_A_BYTES, &tmVh, kb * 32, vrow, &full[s]);
         }
       }
     }
@@ -615,51 +621,62 @@ aggr_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
       const int buf = n & 1;
       mbar_wait(&tmem_empty[buf], ((n >> 1) & 1) ^ 1);
-      const uint32_t tb = tmem_base + buf * 256;
+      const uint32_t tb = tmem_base + AG2_TM_ACC + buf * AG2_ACC_COLS;
       for (int kb = 0; kb < nkb; ++kb, ++g) {
         const int s = g % AGP_ST;
-        mbar_wait(&split[s], (g / AGP_ST) & 1);             // TMA data landed AND the lo plane is built
+        mbar_wait(&split[s], (g / AGP_ST) & 1);             // TMA data landed, alpha moved to TMEM, V^T lo plane built
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t a_hi = smem_u32(smem + s * AG2_STAGE_BYTES), a_lo = a_hi + AG2_A_BYTES;
-          const uint32_t b_hi = a_hi + 2 * AG2_A_BYTES, b_lo = b_hi + AG2_B_BYTES;
+          const uint32_t b_hi = smem_u32(smem + s * AG2_STAGE_BYTES + AG2_A_BYTES), b_lo = b_hi + AG2_B_BYTES;
+          const uint32_t ta = tmem_base + AG2_TM_A + (g & 1) * 64;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t dah = smem_desc_sw128(a_hi + k * 32), dal = smem_desc_sw128(a_lo + k * 32);
+            const uint32_t ah = ta + k * 8, al = ah + 32;
             const uint64_t dbh = smem_desc_sw128(b_hi + k * 32), dbl = smem_desc_sw128(b_lo + k * 32);
-            mma_tf32(tb + (kb / gsz) * 64, dah, dbh, idesc, (kb % gsz == 0 && k == 0) ? 0u : 1u);
-            mma_tf32(tb + 192, dah, dbl, idesc, (kb == 0 && k == 0) ? 0u : 1u);
-            mma_tf32(tb + 192, dal, dbh, idesc, 1u);
+            mma_tf32_ts(tb + (kb / gsz) * 64, ah, dbh, idesc, (kb % gsz == 0 && k == 0) ? 0u : 1u);
+            mma_tf32_ts(tb + 128, ah, dbl, idesc, (kb == 0 && k == 0) ? 0u : 1u);
+            mma_tf32_ts(tb + 128, al, dbh, idesc, 1u);
           }
           mma_commit(&empty[s]);
+          mma_commit(&ta_free[g & 1]);
           if (kb == nkb - 1) mma_commit(&tmem_full[buf]);
         }
         __syncwarp();
       }
     }
   } else if (warp < 6) {
-    // ---- splitters: lo planes of every landed alpha and V^T box
-    const int te = (warp - 2) * 32 + lane;
+    // ---- splitters: thread = query row of the tile
+    const int te = (warp - 2) * 32 + lane;                // 0..127: position in the V^T split
+    const int row = (warp & 3) * 32 + lane;               // TMEM lane = query row this thread may write
+    const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + AG2_TM_A;
     int g = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
       for (int kb = 0; kb < nkb; ++kb, ++g) {
         const int s = g % AGP_ST;
         mbar_wait(&full[s], (g / AGP_ST) & 1);
-        const float4* src = reinterpret_cast<const float4*>(smem + s * AG2_STAGE_BYTES);
-        float4* dst = reinterpret_cast<float4*>(smem + s * AG2_STAGE_BYTES + AG2_A_BYTES);
+        mbar_wait(&ta_free[g & 1], ((g >> 1) & 1) ^ 1);     // the MMAs of key block g - 2 have read this TMEM slot
+        tc_fence_after();
+        // alpha box [128 queries][32 keys], 128-byte swizzle: row `row`, 16-byte unit u sits at u ^ (row & 7)
+        const unsigned char* ar = smem + s * AG2_STAGE_BYTES + row * 128;
+        float hi[32], lo[32];
 #pragma unroll
-        for (int m = 0; m < AG2_A_BYTES / 16 / 128; ++m) {
-          const float4 v = src[te + 128 * m];
-          dst[te + 128 * m] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+        for (int u = 0; u < 8; ++u) {
+          const float4 v = *reinterpret_cast<const float4*>(ar + ((u ^ (row & 7)) << 4));
+          hi[4 * u] = v.x; hi[4 * u + 1] = v.y; hi[4 * u + 2] = v.z; hi[4 * u + 3] = v.w;
         }
-        const float4* vsrc = reinterpret_cast<const float4*>(smem + s * AG2_STAGE_BYTES + 2 * AG2_A_BYTES);
-        float4* vdst = reinterpret_cast<float4*>(smem + s * AG2_STAGE_BYTES + 2 * AG2_A_BYTES + AG2_B_BYTES);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) lo[e] = tf32_lo(hi[e]);
+        tmem_st_32x32(trow + (g & 1) * 64, hi);             // (raw fp32: the tensor core ignores the low 13 mantissa bits)
+        tmem_st_32x32(trow + (g & 1) * 64 + 32, lo);
+        const float4* vsrc = reinterpret_cast<const float4*>(smem + s * AG2_STAGE_BYTES + AG2_A_BYTES);
+        float4* vdst = reinterpret_cast<float4*>(smem + s * AG2_STAGE_BYTES + AG2_A_BYTES + AG2_B_BYTES);
 #pragma unroll
         for (int m = 0; m < AG2_B_BYTES / 16 / 128; ++m) {
           const float4 v = vsrc[te + 128 * m];
           vdst[te + 128 * m] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
         }
         fence_async_smem();
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&split[s]);
       }
@@ -675,17 +692,17 @@ aggr_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int i = tr.i0 + q * 32 + lane;
       mbar_wait(&tmem_full[buf], (n >> 1) & 1);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + AG2_TM_ACC + buf * AG2_ACC_COLS;
       float o[64];
 #pragma unroll
       for (int c = 0; c < 64; c += 32) {
         float v[32], w[32];
-        tmem_ld_32x32(trow + 192 + c, w);                   // corrections
+        tmem_ld_32x32(trow + 128 + c, w);                   // corrections
         tmem_ld_32x32(trow + c, v);
 #pragma unroll
         for (int e = 0; e < 32; ++e) o[c + e] = v[e];
-        for (int gq = 1; gq < ngrp; ++gq) {
-          tmem_ld_32x32(trow + gq * 64 + c, v);
+        if (ngrp > 1) {
+          tmem_ld_32x32(trow + 64 + c, v);
 #pragma unroll
           for (int e = 0; e < 32; ++e) o[c + e] += v[e];
         }

@@ -183,22 +183,34 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------- persistent projection GEMM
-// proj_persist_kernel: the six GABlock projections, (B*L, 128) x (128, 2016), with the EpiProjPack packing, restructured
-// around what bounds it -- the 235 MB of packed operands it writes per layer:
-//   * one CTA per 128-row tile keeps x (hi + lo, 128 KB) RESIDENT in shared memory and walks the 21 column tiles of 96,
-//     streaming only the weights (24 KB per k-block, L2 resident) through a 3-stage ring;
-//   * two 192-column TMEM accumulator sets: while the tensor core fills one, the other is being packed;
-//   * two epilogue warp groups (4 warps each) take alternate column tiles, so two tiles are packed concurrently;
-//   * the packed rows leave as 256-bit stores (one full 32-byte sector per lane) instead of 128-bit ones.
-// warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 / 6-9 = epilogue groups 0 / 1.
-constexpr int PP_THREADS = 320, PP_BN = 96, PP_NT = NPROJ / PP_BN, PP_KB = F / G_BK, PP_ST = 3;      // (4 stages measured identical: the weight ring is not what bounds it)
-constexpr int PP_A_BYTES = G_BM * G_BK * 4;                 // 16 KB: 128 rows x 32 tf32
-constexpr int PP_B_BYTES = PP_BN * G_BK * 4;                // 12 KB
-constexpr int PP_A_TOTAL = PP_KB * 2 * PP_A_BYTES;          // 128 KB: [k-block][hi | lo]
-constexpr int PP_STAGE = 2 * PP_B_BYTES;                    // 24 KB: weights hi | lo of one k-block
-constexpr int PP_BAR_OFF = PP_A_TOTAL + PP_ST * PP_STAGE;
+// proj_ts_kernel: the six GABlock projections, (B*L, 128) x (128, 2016), with the EpsProjPack packing.  What bounded its
+// predecessor (round 2 timeline: one k-block of 12 SS-mode tcgen05.mma every ~1200 cycles, ~100 cycles per 128x96x8 instruction
+// against the 48 of the issue formula) was the shared-memory operand traffic of the MMAs: A and B were both read from shared
+// memory, 7 KB per instruction.  Here the A operand lives in TENSOR MEMORY:
+//   * x of the CTA's 128-row tile is loaded ONCE from global memory into registers by the first epilogue group (thread = row),
+//     split into its tf32 hi / lo planes on the fly and stored to TMEM columns [0,128) | [128,256) (tcgen05.st); no x in shared
+//     memory, no x_lo in global memory;
+//   * the MMAs are issued in TS mode (A from TMEM, B from shared memory): 2-3 KB of shared-memory reads per instruction;
+//   * shared memory is all weight ring: 8 stages of [64 columns][32 k] hi | lo (16 KB), streamed from L2 by TMA;
+//   * column tiles of 64 (q / k / v: two heads) and 48 (points: two heads x 8 points x 3), 36 per row tile, two 128-column
+//     TMEM accumulator sets (main | corrections) filled alternately, two epilogue groups packing them.
+// warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 / 6-9 = epilogue groups 0 / 1 (group 0 also loads A).
+constexpr int PP_THREADS = 320, PP_KB = F / G_BK, PP_ST = 8;
+constexpr int PP_NT64 = 3 * H * D / 64, PP_NT48 = 3 * H * P * 3 / 48, PP_NT = PP_NT64 + PP_NT48;      // 18 + 18 column tiles
+constexpr int PP_B_BYTES = 64 * G_BK * 4;                   // 8 KB: 64 weight rows x 32 tf32 (the 48-wide tiles use the first 48)
+constexpr int PP_STAGE = 2 * PP_B_BYTES;                    // 16 KB: weights hi | lo of one k-block
+constexpr int PP_BAR_OFF = PP_ST * PP_STAGE;
 constexpr int PP_SMEM = PP_BAR_OFF + 256 + 1024;
-static_assert(PP_NT * PP_BN == NPROJ && PP_KB * G_BK == F, "projection tiling");
+constexpr uint32_t PP_TM_A = 0, PP_TM_ACC = 256;            // TMEM columns: x hi (128) | x lo (128) | 2 x (main 64 | corrections 64)
+static_assert(PP_NT64 * 64 == 3 * H * D && PP_NT48 * 48 == 3 * H * P * 3 && PP_KB * G_BK == F, "projection tiling");
+
+__device__ __forceinline__ int pp_tile_n0(int nt) { return nt < PP_NT64 ? nt * 64 : OFF_QP + (nt - PP_NT64) * 48; }
+
+// D[tmem] (+)= A[tmem] * B[smem]; one thread issues
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 
 __device__ __forceinline__ void tmem_ld_32x8_nw(uint32_t taddr, float* v) {
   uint32_t r[8];
@@ -231,8 +243,8 @@ __device__ __forceinline__ void st_v8_hi_lo(float* hi, float* lo, const float (&
 }
 
 __global__ void __launch_bounds__(PP_THREADS, 1)
-proj_persist_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
-                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, int M, EpiProjPack ep) {
+proj_ts_kernel(const float* __restrict__ xg, const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+               int M, EpiProjPack ep) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + PP_BAR_OFF);
@@ -246,14 +258,13 @@ proj_persist_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   const int Mrows = ep.rows ? min(M, ep.count[0]) : M;      // (compact list: the row count lives on the device)
   const int nmt = (Mrows + G_BM - 1) / G_BM;
   const int nunits = nmt * ep.nsplit;
-  constexpr uint32_t ACC_COLS = 2 * PP_BN;                  // main | corrections
 
   if (threadIdx.x == 0) {
-    mbar_init(a_full, 1); mbar_init(a_empty, 1);
+    mbar_init(a_full, 4); mbar_init(a_empty, 1);
     for (int s = 0; s < PP_ST; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
     mbar_fence_init();
-    tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
+    tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -262,56 +273,53 @@ proj_persist_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer: the weight stream =====================
     if (elect_one()) {
-      int na = 0, g = 0;
-      for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++na) {
-        const int mt = u / ep.nsplit, part = u - mt * ep.nsplit;
+      int g = 0;
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+        const int part = u % ep.nsplit;
         const int nt0 = part * PP_NT / ep.nsplit, nt1 = (part + 1) * PP_NT / ep.nsplit;
-        mbar_wait(a_empty, (na & 1) ^ 1);
-        mbar_expect_tx(a_full, PP_A_TOTAL);
-        for (int kb = 0; kb < PP_KB; ++kb) {
-          tma_load_2d(smem + kb * 2 * PP_A_BYTES, &tmAh, kb * G_BK, mt * G_BM, a_full);
-          tma_load_2d(smem + kb * 2 * PP_A_BYTES + PP_A_BYTES, &tmAl, kb * G_BK, mt * G_BM, a_full);
-        }
-        for (int nt = nt0; nt < nt1; ++nt)
+        for (int nt = nt0; nt < nt1; ++nt) {
+          const int n0 = pp_tile_n0(nt);
           for (int kb = 0; kb < PP_KB; ++kb, ++g) {
             const int s = g % PP_ST;
             mbar_wait(&b_empty[s], ((g / PP_ST) & 1) ^ 1);
-            unsigned char* st = smem + PP_A_TOTAL + s * PP_STAGE;
-            mbar_expect_tx(&b_full[s], PP_STAGE);
-            tma_load_2d(st, &tmBh, kb * G_BK, nt * PP_BN, &b_full[s]);
-            tma_load_2d(st + PP_B_BYTES, &tmBl, kb * G_BK, nt * PP_BN, &b_full[s]);
+            unsigned char* st = smem + s * PP_STAGE;
+            mbar_expect_tx(&b_full[s], PP_STAGE);                       // (rows past the end of W arrive as zeros, and count)
+            tma_load_2d(st, &tmBh, kb * G_BK, n0, &b_full[s]);
+            tma_load_2d(st + PP_B_BYTES, &tmBl, kb * G_BK, n0, &b_full[s]);
           }
+        }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = idesc_tf32(G_BM, PP_BN);
+    // ===================== MMA issuer (A from tensor memory) =====================
+    constexpr uint32_t idesc64 = idesc_tf32(G_BM, 64), idesc48 = idesc_tf32(G_BM, 48);
     int na = 0, g = 0, n = 0;
     for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++na) {
       const int part = u % ep.nsplit;
       const int nt0 = part * PP_NT / ep.nsplit, nt1 = (part + 1) * PP_NT / ep.nsplit;
-      mbar_wait(a_full, na & 1);
+      mbar_wait(a_full, na & 1);                                        // x hi | lo of this row tile are in TMEM
+      tc_fence_after();
       for (int nt = nt0; nt < nt1; ++nt, ++n) {
         const int buf = n & 1;
+        const uint32_t idesc = nt < PP_NT64 ? idesc64 : idesc48;
         mbar_wait(&tmem_empty[buf], ((n >> 1) & 1) ^ 1);              // epilogue group `buf` drained tile n - 2
         for (int kb = 0; kb < PP_KB; ++kb, ++g) {
           const int s = g % PP_ST;
           mbar_wait(&b_full[s], (g / PP_ST) & 1);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t a_hi = smem_u32(smem + kb * 2 * PP_A_BYTES), a_lo = a_hi + PP_A_BYTES;
-            const uint32_t b_hi = smem_u32(smem + PP_A_TOTAL + s * PP_STAGE), b_lo = b_hi + PP_B_BYTES;
-            const uint32_t d_main = tmem_base + buf * ACC_COLS, d_small = d_main + PP_BN;
+            const uint32_t b_hi = smem_u32(smem + s * PP_STAGE), b_lo = b_hi + PP_B_BYTES;
+            const uint32_t d_main = tmem_base + PP_TM_ACC + buf * 128, d_small = d_main + 64;
 #pragma unroll
             for (int k = 0; k < G_BK / 8; ++k) {
-              const uint64_t dah = smem_desc_sw128(a_hi + k * 32), dal = smem_desc_sw128(a_lo + k * 32);
+              const uint32_t ah = tmem_base + PP_TM_A + kb * G_BK + k * 8, al = ah + F;
               const uint64_t dbh = smem_desc_sw128(b_hi + k * 32), dbl = smem_desc_sw128(b_lo + k * 32);
               const uint32_t acc = (kb == 0 && k == 0) ? 0u : 1u;
-              mma_tf32(d_main, dah, dbh, idesc, acc);
-              mma_tf32(d_small, dah, dbl, idesc, acc);
-              mma_tf32(d_small, dal, dbh, idesc, 1u);
+              mma_tf32_ts(d_main, ah, dbh, idesc, acc);
+              mma_tf32_ts(d_small, ah, dbl, idesc, acc);
+              mma_tf32_ts(d_small, al, dbh, idesc, 1u);
             }
             mma_commit(&b_empty[s]);
             if (kb == PP_KB - 1) {
@@ -328,12 +336,35 @@ proj_persist_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
     const int q = warp & 3;                                            // TMEM lane quarter this warp may access
     const int gp = (warp - 2) >> 2;                                    // group: takes the tiles with n % 2 == gp
     const int L = ep.L, Lp = ep.Lp;
-    int n = 0;
-    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+    int n = 0, na = 0;
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++na) {
       const int mt = u / ep.nsplit, part = u - mt * ep.nsplit;
       const int nt0 = part * PP_NT / ep.nsplit, nt1 = (part + 1) * PP_NT / ep.nsplit;
       const int row = mt * G_BM + q * 32 + lane;
       const bool valid = row < Mrows;
+      if (gp == 0) {
+        // ---- A operand: this thread's row of x -> tf32 hi | lo planes in TMEM (lane = row, column = k)
+        mbar_wait(a_empty, (na & 1) ^ 1);                               // the MMAs of the previous unit have read it
+        tc_fence_after();
+        const float4* xr = reinterpret_cast<const float4*>(xg + (size_t)(valid ? row : 0) * F);
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + PP_TM_A;
+#pragma unroll 1
+        for (int c = 0; c < F; c += 32) {
+          float hi[32], lo[32];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float4 v = valid ? __ldg(xr + (c >> 2) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            hi[4 * e] = v.x; hi[4 * e + 1] = v.y; hi[4 * e + 2] = v.z; hi[4 * e + 3] = v.w;
+          }
+#pragma unroll
+          for (int e = 0; e < 32; ++e) lo[e] = tf32_lo(hi[e]);
+          tmem_st_32x32(ta + c, hi);                                    // (raw fp32: the tensor core ignores the low 13 mantissa bits)
+          tmem_st_32x32(ta + F + c, lo);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full);
+      }
       const int rr = valid ? (ep.rows ? ep.rows[row] : row) : 0;
       const int b = rr / L, r = rr - b * L;
       float Rm[9], tv[3];
@@ -345,17 +376,17 @@ proj_persist_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
         if ((n & 1) != gp) continue;
         mbar_wait(&tmem_full[gp], (n >> 1) & 1);
         tc_fence_after();
-        const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + gp * ACC_COLS, ts = tm + PP_BN;
-        const int n0 = nt * PP_BN;
+        const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + PP_TM_ACC + gp * 128, ts = tm + 64;
+        const int n0 = pp_tile_n0(nt);
         if (n0 < OFF_V) {
-          // ---- q or k channels: 3 heads x 32                                      ga.py:82-85
+          // ---- q or k channels: 2 heads x 32                                      ga.py:82-85
           const bool is_q = n0 < OFF_K;
           const int h0 = (is_q ? n0 : n0 - OFF_K) / D;
           const float sc = is_q ? 0.17677669529663687f : 1.f;          // 1 / sqrt(32) folded into q
           float* dst = is_q ? ep.QA : ep.KB;
           float* dlo = is_q ? ep.QA_lo : ep.KB_lo;
 #pragma unroll 1
-          for (int hh = 0; hh < 3; ++hh) {
+          for (int hh = 0; hh < 2; ++hh) {
             float v[32];
             tmem_ld_sum<32>(tm + hh * D, ts + hh * D, v);
             if (valid) {
@@ -370,10 +401,10 @@ proj_persist_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
             }
           }
         } else if (n0 < OFF_QP) {
-          // ---- value channels: 3 heads x 32, stored transposed (key index contiguous)  ga.py:122
+          // ---- value channels: 2 heads x 32, stored transposed (key index contiguous)  ga.py:122
           const int h0 = (n0 - OFF_V) / D;
 #pragma unroll 1
-          for (int hh = 0; hh < 3; ++hh) {
+          for (int hh = 0; hh < 2; ++hh) {
             float v[32];
             tmem_ld_sum<32>(tm + hh * D, ts + hh * D, v);
             if (valid) {
@@ -383,11 +414,11 @@ proj_persist_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
             }
           }
         } else {
-          // ---- points: 4 heads x 8 points x 3, local -> global q = R p + t      geometry.py:72-91
+          // ---- points: 2 heads x 8 points x 3, local -> global q = R p + t      geometry.py:72-91
           const int kind = n0 < OFF_KP ? 0 : (n0 < OFF_VP ? 1 : 2);      // query / key / value points
           const int h0 = (n0 - (kind == 0 ? OFF_QP : (kind == 1 ? OFF_KP : OFF_VP))) / (P * 3);
 #pragma unroll 1
-          for (int hh = 0; hh < 4; ++hh) {
+          for (int hh = 0; hh < 2; ++hh) {
             float v[24];
             tmem_ld_sum<24>(tm + hh * P * 3, ts + hh * P * 3, v);
             if (valid) {
@@ -453,7 +484,7 @@ cudaError_t tc_init() {
   }
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(gemm3x_kernel<128, 3, 8, EpiPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<128, 3>::TOTAL)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(proj_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(proj_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -592,16 +623,15 @@ bool launch_gemm3x_plain(int M, int N, int K, const float* Ah, const float* Al, 
 // the six GABlock projections as one GEMM, outputs packed for the tensor-core attention kernels (see EpiProjPack)
 bool launch_proj_pack(int M, int L, int Lp, const float* xh, const float* xl, const float* Wh, const float* Wl, const float* R, const float* t,
                       const float* coef, const AttnOperands& op, cudaStream_t st, const int* rows, const int* count) {
-  CUtensorMap a_h, a_l, b_h, b_l;
-  if (!make_tmap(&a_h, xh, M, F, F, G_BM) || !make_tmap(&a_l, xl, M, F, F, G_BM) || !make_tmap(&b_h, Wh, NPROJ, F, F, 96) ||
-      !make_tmap(&b_l, Wl, NPROJ, F, F, 96))
-    return false;
+  CUtensorMap b_h, b_l;
+  (void)xl;      // (the lo plane of x is built on chip)
+  if (!make_tmap(&b_h, Wh, NPROJ, F, F, 64) || !make_tmap(&b_l, Wl, NPROJ, F, F, 64)) return false;
   ProfScope prof__(KK_PROJ, st);
-  const EpiProjPack ep{R, t, coef, op.QA, op.QA_lo, op.KB, op.KB_lo, op.rq, op.rk, op.VT, L, Lp, attn_needs_qk_lo(L) ? 1 : 0, rows, count, rows ? 7 : 1};
+  const EpiProjPack ep{R, t, coef, op.QA, op.QA_lo, op.KB, op.KB_lo, op.rq, op.rk, op.VT, L, Lp, attn_needs_qk_lo(L) ? 1 : 0, rows, count, rows ? 9 : 1};
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const int nunits = ((M + G_BM - 1) / G_BM) * ep.nsplit;
-  proj_persist_kernel<<<nunits < sms ? nunits : sms, PP_THREADS, PP_SMEM, st>>>(a_h, a_l, b_h, b_l, M, ep);
+  proj_ts_kernel<<<nunits < sms ? nunits : sms, PP_THREADS, PP_SMEM, st>>>(xh, b_h, b_l, M, ep);
   return true;
 }
 
