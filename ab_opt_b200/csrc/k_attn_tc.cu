@@ -566,6 +566,21 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, ui
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
                ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// registers -> 32 lanes x 32 consecutive fp32 columns (thread = lane); the caller waits (tcgen05.wait::st) once for a batch
+__device__ __forceinline__ void tmem_st32_nowait(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+      "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+        "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+        "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+        "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+}
 
 __global__ void __launch_bounds__(AGP_THREADS, 1)
 aggr_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmVh,
@@ -654,8 +669,14 @@ aggr_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int kb = 0; kb < nkb; ++kb, ++g) {
         const int s = g % AGP_ST;
         mbar_wait(&full[s], (g / AGP_ST) & 1);
-        mbar_wait(&ta_free[g & 1], ((g >> 1) & 1) ^ 1);     // the MMAs of key block g - 2 have read this TMEM slot
-        tc_fence_after();
+        // everything that needs only the landed stage first: V^T lo plane, this row of the alpha box and its lo plane
+        const float4* vsrc = reinterpret_cast<const float4*>(smem + s * AG2_STAGE_BYTES + AG2_A_BYTES);
+        float4* vdst = reinterpret_cast<float4*>(smem + s * AG2_STAGE_BYTES + AG2_A_BYTES + AG2_B_BYTES);
+#pragma unroll
+        for (int m = 0; m < AG2_B_BYTES / 16 / 128; ++m) {
+          const float4 v = vsrc[te + 128 * m];
+          vdst[te + 128 * m] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+        }
         // alpha box [128 queries][32 keys], 128-byte swizzle: row `row`, 16-byte unit u sits at u ^ (row & 7)
         const unsigned char* ar = smem + s * AG2_STAGE_BYTES + row * 128;
         float hi[32], lo[32];
@@ -666,15 +687,11 @@ aggr_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
 #pragma unroll
         for (int e = 0; e < 32; ++e) lo[e] = tf32_lo(hi[e]);
-        tmem_st_32x32(trow + (g & 1) * 64, hi);             // (raw fp32: the tensor core ignores the low 13 mantissa bits)
-        tmem_st_32x32(trow + (g & 1) * 64 + 32, lo);
-        const float4* vsrc = reinterpret_cast<const float4*>(smem + s * AG2_STAGE_BYTES + AG2_A_BYTES);
-        float4* vdst = reinterpret_cast<float4*>(smem + s * AG2_STAGE_BYTES + AG2_A_BYTES + AG2_B_BYTES);
-#pragma unroll
-        for (int m = 0; m < AG2_B_BYTES / 16 / 128; ++m) {
-          const float4 v = vsrc[te + 128 * m];
-          vdst[te + 128 * m] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
-        }
+        mbar_wait(&ta_free[g & 1], ((g >> 1) & 1) ^ 1);     // the MMAs of key block g - 2 have read this TMEM slot
+        tc_fence_after();
+        tmem_st32_nowait(trow + (g & 1) * 64, hi);          // (raw fp32: the tensor core ignores the low 13 mantissa bits)
+        tmem_st32_nowait(trow + (g & 1) * 64 + 32, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         fence_async_smem();
         tc_fence_before();
         __syncwarp();
