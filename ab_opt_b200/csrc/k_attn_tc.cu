@@ -24,6 +24,7 @@ constexpr int AL_A_OFF = 0;                            // query operand: hi | lo
 
 struct AttnLogitsArgs {
   int L, Lp, b0;
+  const float* QA;                       // [N][H][L][64] packed query operand (read row by row into tensor memory)
   const float* rq; const float* rk;      // [N][H][L]
   const float* bias;                     // [N][H][L queries][Lp] (key index contiguous, like alpha)
   const uint8_t* mask;                   // [N][L]
@@ -42,41 +43,46 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
 
 // ------------------------------------------------------------------------------------------ logits + softmax
 // attn_logits_persist_kernel: the phases of consecutive tiles overlap and no thread ever waits on a global load.  One CTA per SM walks the (complex, head, 128-query tile) list;
-// 18 warps:
+// 20 warps:
 //   warp 0      TMA producer, one thread running a small event loop over two independent streams:
-//                 operands -- the query operand (single buffer, released by the MMA warp) and key groups of 64 residues
-//                             through a 3-stage ring;
-//                 bias     -- the tile's pair bias in chunks of [128 queries][32 keys] (16 KB, swizzled) through a 3-stage ring,
-//                             running ahead of the epilogue (the bias is the HBM stream of this kernel)
-//   warp 1      MMA issuer -- accumulates tile n into TMEM buffer n & 1 (2 x 256 columns) while the epilogue warps are still
-//               busy with tile n - 1; per key group 16 correction products first, then the 8 hi*hi ones (truncation note above)
-//   warps 18-19 splitters  -- build the tf32 "lo" plane (x - trunc_tf32(x)) of every landed operand box in shared memory,
+//                 operands -- key groups of 64 residues through a 2-stage ring;
+//                 bias     -- the tile's pair bias in chunks of [128 queries][32 keys] (16 KB, swizzled) through a 6-slot ring,
+//                             running ahead of the epilogue (the bias is the HBM read stream of this kernel)
+//   warp 1      MMA issuer -- TS mode: the QUERY operand is read from tensor memory (2 slots of tf32 hi 64 | lo 64 columns, written
+//               by the epilogue threads), the key operand from shared memory; one 256-column accumulator, released as soon as the
+//               epilogue has moved it to registers, so tile n + 1 accumulates while the epilogue is busy with tile n; per key group
+//               16 correction products first, then the 8 hi*hi ones (truncation note above)
+//   warps 18-19 splitters  -- build the tf32 "lo" plane (x - trunc_tf32(x)) of every landed key group in shared memory,
 //               so QA_lo / KB_lo never exist in global memory (saves their write in the projection kernel and their read here)
 //   warps 2-17  epilogue   -- 4 threads per query row; thread (row, kq) owns keys 32 m + 8 kq + (0..7) of every chunk m:
-//               TMEM -> registers (buffer released at once), per chunk bias from shared memory (two conflict-free LDS.128 of
-//               the swizzled box) -> logits; max / exp / sum exchanged through shared memory; alpha stored with 256-bit
-//               global stores (one full 32-byte sector each)
-constexpr int AP_THREADS = 640, AP_EPI = 512, AP_SPLIT = 64;      // (18 warps are allocated registers as 20 anyway)
-// Shared memory (217 KB): query operand hi | lo (64 KB), two key-group stages (64 KB), a 3-deep pair-bias ring (48 KB), 2 alpha
-// staging boxes (32 KB), double-buffered per-key tables, barriers.  Measured on B200 (round 2, scripts/kbench.py with variant
-// builds, us per full-batch launch): stages / bias slots / staging boxes = 2/3/2: 123.8, 1/4/3: 131.7 (the epilogue then waits for
-// the MMA stream: 18 % of its stall samples on tmem_full), 2/2/3: 131.1; mbarrier.test_wait instead of try_wait in the
-// producer's event loop: no change.  DRAM is idle 56 % of the time (dram__cycles_active), i.e. the kernel is bound by the serial
-// bias -> softmax -> store phases of a tile, not by bandwidth or by DRAM page locality.
+//               TMEM -> registers (accumulator released at once), per chunk bias from shared memory (two conflict-free LDS.128
+//               of the swizzled box) -> logits; max / exp / sum exchanged through shared memory; alpha leaves through swizzled
+//               staging boxes and TMA tensor stores; the same threads load the query operand of tile n + 2 (16 floats each)
+//               before the store phase and store it to TMEM after it
+constexpr int AP_THREADS = 640, AP_EPI = 512, AP_SPLIT = 64;      // producer, MMA issuer, 16 epilogue warps, 2 splitter warps
+// Shared memory (214 KB): two key-group stages (64 KB), a 6-deep pair-bias ring (96 KB), 3 alpha staging boxes (48 KB),
+// double-buffered per-key tables, barriers.  Measured on B200 (round 2, scripts/kbench.py with variant builds, us per full-batch
+// launch).  With the query operand in shared memory (64 KB): stages / bias slots / staging boxes = 2/3/2: 123.8, 1/4/3: 131.7 (the
+// epilogue then waits for the MMA stream), 2/2/3: 131.1.  With it in tensor memory: 2/7/2: 123.3, 2/5/4: 123.4, 2/6/3: 120.0;
+// staggering the odd CTAs by 3 or 5 us (to break the lockstep of the read-only bias phases and write-only store phases across
+// the SMs): 120.  mbarrier.test_wait instead of try_wait in the producer's event loop: no change.  Neither ring depth nor phase
+// alignment is what bounds it: DRAM is idle about half of the time (dram__cycles_active), the kernel is bound by the serial
+// bias -> softmax -> store phases of a tile in its 16 epilogue warps.
 #ifndef ABOPT_AP_BST
 #define ABOPT_AP_BST 2
 #endif
 #ifndef ABOPT_AP_NBIAS
-#define ABOPT_AP_NBIAS 3
+#define ABOPT_AP_NBIAS 6
 #endif
 #ifndef ABOPT_AP_NSTG
-#define ABOPT_AP_NSTG 2
+#define ABOPT_AP_NSTG 3
 #endif
 constexpr int AP_BST = ABOPT_AP_BST, AP_BGRP_BYTES = 4 * 64 * 32 * 4; // key-group stage: 64 keys x (hi k0 | hi k1 | lo k0 | lo k1) = 32 KB
 constexpr int AP_KBOX = 64 * 32 * 4;                                  // one key box: 64 rows x 32 floats
 constexpr int AP_NBIAS = ABOPT_AP_NBIAS, AP_BIAS_BYTES = 128 * 32 * 4;    // bias chunk: 128 queries x 32 keys
 constexpr int AP_NSTG = ABOPT_AP_NSTG, AP_STG_BYTES = 128 * 32 * 4;       // alpha staging boxes of [128 queries][32 keys], 128-byte swizzle
-constexpr int AP_B_OFF = 2 * AL_OPER_BYTES;
+constexpr int AP_B_OFF = 0;                                           // (the query operand lives in tensor memory)
+constexpr uint32_t AP_TM_Q = 0, AP_TM_ACC = 256;                      // TMEM columns: 2 x (query hi 64 | lo 64) | accumulator (<= 256)
 constexpr int AP_BIAS_OFF = AP_B_OFF + AP_BST * AP_BGRP_BYTES;
 constexpr int AP_STG_OFF = AP_BIAS_OFF + AP_NBIAS * AP_BIAS_BYTES;
 constexpr int AP_TAB_OFF = AP_STG_OFF + AP_NSTG * AP_STG_BYTES;       // ck[2][256] | pen[2][256] | xmax[4][128] | xsum[4][128]
@@ -84,6 +90,20 @@ constexpr int AP_BAR_OFF = AP_TAB_OFF + 4 * 256 * 4 + 8 * 128 * 4;
 constexpr int AP_SMEM = AP_BAR_OFF + 256 + 4 * 128 * 4 + 1024;         // barriers (<= 31 x 8 B + slot) | SPLIT exchange [2][2][128] floats
 static_assert(AP_SMEM <= 227 * 1024, "attn_logits_persist_kernel: shared memory");
 
+// D[tmem] (+)= A[tmem] * B[smem]; one thread issues ("TS" mode: the A operand is read from tensor memory, lane = row, column = k)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// registers -> 32 lanes x 16 consecutive fp32 columns (thread = lane); the caller waits (tcgen05.wait::st) once for a batch
+__device__ __forceinline__ void tmem_st16_nowait(uint32_t taddr, const float (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                 "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                 "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+               : "memory");
+}
 // 2^x, x <= 0 (MUFU.EX2, 2 ulp; results below the normal range flush to zero -- attention weights < 1e-38)
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -170,16 +190,14 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
   float* pen_tab = ck_tab + 2 * 256;                                 // [2][256]  mask penalty of the tile's keys
   float* xmax = pen_tab + 2 * 256;        // [4][128]
   float* xsum = xmax + 4 * 128;           // [4][128]
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + AP_BAR_OFF);
-  uint64_t* a_empty = a_full + 1;
-  uint64_t* b_full = a_empty + 1;         // [AP_BST]
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(smem + AP_BAR_OFF);      // [AP_BST]
   uint64_t* b_empty = b_full + AP_BST;    // [AP_BST]
   uint64_t* bias_full = b_empty + AP_BST;       // [AP_NBIAS]
   uint64_t* bias_empty = bias_full + AP_NBIAS;  // [AP_NBIAS]
   uint64_t* tmem_full = bias_empty + AP_NBIAS;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;   // [2]
-  uint64_t* a_split = tmem_empty + 2;
-  uint64_t* b_split = a_split + 1;        // [AP_BST]
+  uint64_t* q_ready = tmem_empty + 2;     // [2]  the query operand of tile n is in TMEM slot n & 1
+  uint64_t* b_split = q_ready + 2;        // [AP_BST]
   uint64_t* xch_bar = b_split + AP_BST;   // [2 kinds][2 tile parities]  SPLIT: the partner's row maxima / sums have landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xch_bar + 4);
   float* xch = reinterpret_cast<float*>(smem + AP_BAR_OFF + 256);      // [2 kinds][2 parities][128 rows], written by the partner CTA
@@ -194,8 +212,7 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
   const int tstride = SPLIT ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
-    mbar_init(a_full, 1); mbar_init(a_empty, 1);
-    mbar_init(a_split, AP_SPLIT);
+    mbar_init(&q_ready[0], AP_EPI / 32); mbar_init(&q_ready[1], AP_EPI / 32);
     for (int s = 0; s < AP_BST; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); mbar_init(&b_split[s], AP_SPLIT); }
     for (int s = 0; s < AP_NBIAS; ++s) { mbar_init(&bias_full[s], 1); mbar_init(&bias_empty[s], AP_EPI / 32); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], AP_EPI / 32); }
@@ -221,14 +238,7 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
           const TileRef tr = tile_ref(otile, nit, pa.windows);
           const int row_base = ((a.b0 + tr.bl) * H + tr.h) * L;
           if (ostep == 0) {
-            if (AP_POLL(a_empty, (on & 1) ^ 1)) {
-              unsigned char* A = smem + AL_A_OFF;
-              const int r0 = row_base + tr.i0;
-              mbar_expect_tx(a_full, AL_OPER_BYTES);          // raw fp32 = the "hi" plane; the splitters add the lo plane
-              tma_load_2d(A, &tmQh, 0, r0, a_full);
-              tma_load_2d(A + AL_BOX_BYTES, &tmQh, 32, r0, a_full);
-              ostep = 1;
-            }
+            ostep = 1;                                      // (the query operand is loaded by the splitter warps, into TMEM)
           } else {
             const int s = og % AP_BST;
             if (AP_POLL(&b_empty[s], ((og / AP_BST) & 1) ^ 1)) {
@@ -260,37 +270,36 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
     constexpr uint32_t idesc64 = idesc_tf32(AL_BM, 64), idesc32 = idesc_tf32(AL_BM, 32);
     int n = 0, g = 0;
     for (int tile = tfirst; tile < ntiles; tile += tstride, ++n) {
-      const int buf = n & 1;
-      mbar_wait(&tmem_empty[buf], ((n >> 1) & 1) ^ 1);    // the epilogue has read this TMEM buffer (tile n - 2)
-      mbar_wait(a_split, n & 1);                          // query operand landed AND its lo plane is built
+      mbar_wait(&tmem_empty[0], (n & 1) ^ 1);             // the epilogue has moved the accumulator of tile n - 1 to registers
+      mbar_wait(&q_ready[n & 1], (n >> 1) & 1);           // query operand hi | lo of this tile are in TMEM slot n & 1
       for (int gi = 0; gi < NGRP; ++gi, ++g) {
         const int s = g % AP_BST;
         mbar_wait(&b_split[s], (g / AP_BST) & 1);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t a_hi = smem_u32(smem + AL_A_OFF), a_lo = a_hi + AL_OPER_BYTES;
+          const uint32_t a_hi = tmem_base + AP_TM_Q + (n & 1) * 128, a_lo = a_hi + 64;      // TS mode: A from tensor memory, column = k
           const uint32_t b_hi = smem_u32(smem + AP_B_OFF + s * AP_BGRP_BYTES), b_lo = b_hi + 2 * AP_KBOX;
-          const uint32_t d = tmem_base + buf * 256 + gi * 64;
+          const uint32_t d = tmem_base + AP_TM_ACC + gi * 64;
           const uint32_t idesc = ((NCH & 1) && gi == NGRP - 1) ? idesc32 : idesc64;      // 32-key tail group (its stage holds 64 rows)
 #pragma unroll
           for (int kk = 0; kk < AL_K / 8; ++kk) {
-            const uint32_t ka = (kk >> 2) * AL_BOX_BYTES + (kk & 3) * 32, kb = (kk >> 2) * AP_KBOX + (kk & 3) * 32;
-            mma_tf32(d, smem_desc_sw128(a_hi + ka), smem_desc_sw128(b_lo + kb), idesc, kk == 0 ? 0u : 1u);
-            mma_tf32(d, smem_desc_sw128(a_lo + ka), smem_desc_sw128(b_hi + kb), idesc, 1u);
+            const uint32_t kb = (kk >> 2) * AP_KBOX + (kk & 3) * 32;
+            mma_tf32_ts(d, a_hi + kk * 8, smem_desc_sw128(b_lo + kb), idesc, kk == 0 ? 0u : 1u);
+            mma_tf32_ts(d, a_lo + kk * 8, smem_desc_sw128(b_hi + kb), idesc, 1u);
           }
 #pragma unroll
           for (int kk = 0; kk < AL_K / 8; ++kk) {
-            const uint32_t ka = (kk >> 2) * AL_BOX_BYTES + (kk & 3) * 32, kb = (kk >> 2) * AP_KBOX + (kk & 3) * 32;
-            mma_tf32(d, smem_desc_sw128(a_hi + ka), smem_desc_sw128(b_hi + kb), idesc, 1u);
+            const uint32_t kb = (kk >> 2) * AP_KBOX + (kk & 3) * 32;
+            mma_tf32_ts(d, a_hi + kk * 8, smem_desc_sw128(b_hi + kb), idesc, 1u);
           }
           mma_commit(&b_empty[s]);
-          if (gi == NGRP - 1) { mma_commit(a_empty); mma_commit(&tmem_full[buf]); }
+          if (gi == NGRP - 1) mma_commit(&tmem_full[0]);
         }
         __syncwarp();
       }
     }
   } else if (warp >= 18) {
-    // ===================== splitters: lo = x - trunc_tf32(x), same swizzled offsets as the hi plane =====================
+    // ===================== splitters (warps 18-19): lo = x - trunc_tf32(x) of every landed key group =====================
     const int st = threadIdx.x - 18 * 32;                 // 0..63
     auto split = [&](const unsigned char* hi, unsigned char* lo, int n16) {
       const float4* src = reinterpret_cast<const float4*>(hi);
@@ -302,11 +311,8 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
       }
       fence_async_smem();                                 // generic-proxy writes -> visible to the tensor core (async proxy)
     };
-    int n = 0, g = 0;
-    for (int tile = tfirst; tile < ntiles; tile += tstride, ++n) {
-      mbar_wait(a_full, n & 1);
-      split(smem + AL_A_OFF, smem + AL_A_OFF + AL_OPER_BYTES, AL_OPER_BYTES / 16);
-      mbar_arrive(a_split);
+    int g = 0;
+    for (int tile = tfirst; tile < ntiles; tile += tstride)
       for (int gi = 0; gi < NGRP; ++gi, ++g) {
         const int s = g % AP_BST;
         mbar_wait(&b_full[s], (g / AP_BST) & 1);
@@ -314,7 +320,6 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
         split(B, B + 2 * AP_KBOX, 2 * AP_KBOX / 16);
         mbar_arrive(&b_split[s]);
       }
-    }
   } else {
     // ===================== epilogue (warps 2..17) =====================
     const int q = warp & 3;                               // TMEM lane quarter this warp may access
@@ -338,10 +343,38 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
     };
     int n = 0, bc = 0, sc = 0;
     float rqi = 0.f;
+    // The query operand lives in TENSOR MEMORY (TS-mode MMAs; its 64 KB of shared memory went to the pair-bias ring): thread
+    // (row, kq) owns 16 of the row's 64 floats, reads them from global memory and stores tf32 hi | lo to columns 16 kq.. of the
+    // hi / lo halves of TMEM slot (tile count & 1).  The loads of tile n + 2 are issued before the store phase of tile n and
+    // stored after it (slot n & 1 is free: the MMAs of tile n completed before this epilogue started).
+    auto q_load = [&](int tile, float4 (&qv)[4]) {
+      const TileRef tr = tile_ref(tile, nit, pa.windows);
+      const int qi = tr.i0 + te;
+      const float4* qrow = reinterpret_cast<const float4*>(a.QA + ((size_t)((a.b0 + tr.bl) * H + tr.h) * L + (qi < L ? qi : 0)) * 64) + kq * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) qv[e] = qi < L ? __ldg(qrow + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto q_store = [&](int slot, const float4 (&qv)[4]) {
+      const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + AP_TM_Q + slot * 128 + kq * 16;
+      float hi[16], lo[16];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { hi[4 * e] = qv[e].x; hi[4 * e + 1] = qv[e].y; hi[4 * e + 2] = qv[e].z; hi[4 * e + 3] = qv[e].w; }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) lo[e] = tf32_lo(hi[e]);
+      tmem_st16_nowait(tq, hi);                           // (raw fp32: the tensor core ignores the low 13 mantissa bits)
+      tmem_st16_nowait(tq + 64, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&q_ready[slot]);
+    };
     if (tfirst < ntiles) {
       float ckv = 0.f, penv = 0.f;
       key_tables(tile_ref(tfirst, nit, pa.windows), ckv, penv, rqi);
       if (et < NCH * 32) { ck_tab[et] = ckv; pen_tab[et] = penv; }
+      float4 qv[4];
+      q_load(tfirst, qv); q_store(0, qv);
+      if (tfirst + tstride < ntiles) { q_load(tfirst + tstride, qv); q_store(1, qv); }
     }
     for (int tile = tfirst; tile < ntiles; tile += tstride, ++n) {
       const TileRef tr = tile_ref(tile, nit, pa.windows);
@@ -353,9 +386,9 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
       float ck_n = 0.f, pen_n = 0.f, rq_n = 0.f;
       const bool more = tile + tstride < ntiles;
       if (more) key_tables(tile_ref(tile + tstride, nit, pa.windows), ck_n, pen_n, rq_n);      // in flight during this tile
-      mbar_wait(&tmem_full[buf], (n >> 1) & 1);
+      mbar_wait(&tmem_full[0], n & 1);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + kq * 8;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + AP_TM_ACC + kq * 8;
       float lg[NLG];
       {
         uint32_t raw[NCH][8];
@@ -369,7 +402,7 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[buf]);       // the accumulator is in registers: the MMA warp may reuse the buffer
+      if (lane == 0) mbar_arrive(&tmem_empty[0]);         // the accumulator is in registers: the MMA warp may start the next tile
       float mx = -INFINITY;
 #pragma unroll
       for (int m = 0; m < NCH; ++m, ++bc) {
@@ -434,6 +467,9 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
       const float inv = (a.exclude && rowsum == 0.f) ? 0.f : 1.0f / rowsum;
       if (a.stats && kq == 0 && crank == 0 && i0 + te < L)
         a.stats[(size_t)((a.b0 + bl) * H + h) * L + i0 + te] = make_float2(mx, rowsum);
+      float4 qnext[4];
+      const bool more2 = tile + 2 * tstride < ntiles;
+      if (more2) q_load(tile + 2 * tstride, qnext);       // in flight during the store phase
       // alpha leaves chunk by chunk through AP_NSTG staging boxes ([128 queries][32 keys], 128-byte swizzle) and TMA tensor
       // stores: whole lines, rows >= L and keys >= Lp clipped by the hardware.  (Per-lane 256-bit global stores of a
       // row-per-lane layout cost 32 sector requests per instruction and kept the LSU the bottleneck of this kernel.)
@@ -455,6 +491,7 @@ attn_logits_persist_kernel(const __grid_constant__ CUtensorMap tmQh, const __gri
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
+      if (more2) q_store(n & 1, qnext);
     }
     if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");          // smem must outlive the reads
     tc_fence_before();
@@ -490,7 +527,7 @@ bool launch_attn_logits_tc(int nb, int b0, int N, int L, int Lp, const AttnOpera
   // alpha as a 3-D tensor [chunk * H][L queries][Lp keys] for the TMA stores (rows >= L are clipped)
   if (!make_tmap_3d(&al, alpha, Lp, L, (uint64_t)nb * H, 32, 128)) return false;
   ProfScope prof__(KK_LOGITS, st);
-  AttnLogitsArgs a{L, Lp, b0, op.rq, op.rk, bias_layer, mask, alpha, exclude, stats};
+  AttnLogitsArgs a{L, Lp, b0, op.QA, op.rq, op.rk, bias_layer, mask, alpha, exclude, stats};
   const int ncols = ((L + AL_BN - 1) / AL_BN) * AL_BN;
   const int ntiles = nb * H * ((L + AL_BM - 1) / AL_BM);
   int sms = 148;
@@ -560,11 +597,6 @@ constexpr int AGP_SMEM = AGP_ST * AG2_STAGE_BYTES + 256 + 1024;
 __device__ __forceinline__ void st_v8f(float* p, float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a0), "f"(a1), "f"(a2), "f"(a3), "f"(a4),
                "f"(a5), "f"(a6), "f"(a7) : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]; one thread issues
-__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-               ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // registers -> 32 lanes x 32 consecutive fp32 columns (thread = lane); the caller waits (tcgen05.wait::st) once for a batch
 __device__ __forceinline__ void tmem_st32_nowait(uint32_t taddr, const float (&v)[32]) {
