@@ -1,0 +1,15 @@
+import os, sys, ctypes, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import bench
+from ab_opt_b200 import _capi
+cfg = dict(bench.CONFIGS['c2']); dev = torch.device('cuda', 0)
+model = bench.build_model(cfg, dev); inp = bench.synthetic_batch(cfg, 1000, dev)
+os.environ['ABOPT_NO_FOCUS'] = '1'
+for k in range(2):
+    out = model.reverse_step(100 - k, inp['v'], inp['p'], inp['s'], inp['res_feat'], inp['pair_feat'], inp['mask_generate'], inp['mask_res'], seed=7)
+torch.cuda.synchronize()
+clk = (ctypes.c_longlong * 16)()
+_capi.check(_capi.lib().abopt_debug_clocks(clk))
+names = ['tile start', 'accumulator ready', 'accumulator in registers', 'bias phase done', 'max exchanged', 'exp done', 'sum exchanged', 'stores issued', 'next query operand stored']
+print({n: int(clk[i] - clk[0]) for i, n in enumerate(names)})

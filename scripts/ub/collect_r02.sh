@@ -5,5 +5,5 @@ python bench.py > gpurun_out/r02_final_bench_c2.json 2> gpurun_out/r02_final_ben
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_final_bench_reference.json 2>/dev/null
 for c in c3 c4 c5 f1; do python bench.py --config $c --no-cpu-baseline --no-gpu-eager > gpurun_out/r02_final_bench_$c.json 2>/dev/null; done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_final_launches_c2.csv python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-gpu-eager > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on --kernel-name regex:'pair_stream|attn_logits|aggr_persist|outT_tail|proj_persist' -c 15 -o gpurun_out/r02_final_prof -f python scripts/profile_step.py --config c2 --steps 1 > gpurun_out/r02_final_ncu.log 2>&1
-tail -3 gpurun_out/r02_final_pytest_gpu.log; head -c 600 gpurun_out/r02_final_bench_c2.json
+ncu --set full --clock-control none --import-source on --kernel-name regex:'pair_stream|attn_logits|aggr_persist|outT_tail|proj_ts|ctx_delta' --launch-skip 64 --launch-count 32 -o gpurun_out/r02_final_prof -f python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-gpu-eager > gpurun_out/r02_final_ncu.log 2>&1
+tail -3 gpurun_out/r02_final_pytest_gpu.log; head -c 400 gpurun_out/r02_final_bench_c2.json
