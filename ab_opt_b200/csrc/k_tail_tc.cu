@@ -15,9 +15,12 @@ namespace abopt {
 
 using namespace tc;
 
-constexpr int OT_THREADS = 320, OT_ST = 3, OT_KCH = 8, OT_BK = 32;
+constexpr int OT_THREADS = 320, OT_ST = 4, OT_KCH = 8, OT_BK = 32;
 constexpr int OT_A = 128 * OT_BK * 4;                     // 16 KB: 128 rows x 32 tf32
-constexpr int OT_STAGE = 4 * OT_A;                        // 64 KB: A raw | A lo | B hi | B lo
+constexpr int OT_STAGE = 3 * OT_A;                        // 48 KB: A raw | B hi | B lo (the A operand is fed from tensor memory)
+// TMEM columns of phase 1: main accumulator x 2 (promotion double buffer) | corrections (one, never promoted: its terms are 2^-11
+// of the main ones, their truncation is irrelevant) | A ring: 2 slots x (feat hi 32 | lo 32)
+constexpr uint32_t OT_TM_CORR = 256, OT_TM_A = 384;
 constexpr int OT_ACT_KB = 2 * OT_A;                       // phase 2: one activation k-block, hi | lo
 constexpr int OT_W_OFF = 4 * OT_ACT_KB;                   // phase 2: weight stages start behind the 4 activation k-blocks
 constexpr int OT_BAR_OFF = OT_ST * OT_STAGE;              // 192 KB
@@ -39,6 +42,20 @@ __device__ __forceinline__ void tstamp(int slot) { if (blockIdx.x == 0) g_tail_c
 void tail_debug_clocks(long long* out6) { cudaMemcpyFromSymbol(out6, g_tail_clk, sizeof(long long) * 6); }
 
 __device__ __forceinline__ void epi_sync256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]; one thread issues ("TS" mode: the A operand is read from tensor memory, lane = row, column = k)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// registers -> 32 lanes x 16 consecutive fp32 columns (thread = lane); the caller waits (tcgen05.wait::st) once for a batch
+__device__ __forceinline__ void tmem_st16_nw(uint32_t taddr, const float (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                 "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                 "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+               : "memory");
+}
 
 __global__ void __launch_bounds__(OT_THREADS, 1)
 outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
@@ -62,7 +79,8 @@ outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* act_ready = w_empty + 2;
   uint64_t* acc_full = act_ready + 1;
   uint64_t* x_full = acc_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 1);
+  uint64_t* ta_free = x_full + 1;              // [2]  the MMAs that read TMEM A slot s have completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ta_free + 2);
   float* exch_sum = reinterpret_cast<float*>(smem + OT_EXCH_OFF);      // [2][128]
   float* exch_sq = exch_sum + 256;                                     // [2][128]
 
@@ -76,6 +94,7 @@ outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < OT_ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&split[s], 8); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); mbar_init(&w_full[b], 1); mbar_init(&w_empty[b], 1); }
     mbar_init(act_ready, 8); mbar_init(acc_full, 1); mbar_init(x_full, 1);
+    mbar_init(&ta_free[0], 1); mbar_init(&ta_free[1], 1);
     mbar_fence_init();
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl); tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWl);
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmXo); tma_prefetch_desc(&tmXl);
@@ -101,8 +120,8 @@ outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         unsigned char* st = smem + s * OT_STAGE;
         mbar_expect_tx(&full[s], 3 * OT_A);
         tma_load_2d(st, &tmA, kb * OT_BK, m0, &full[s]);
-        tma_load_2d(st + 2 * OT_A, &tmBh, kb * OT_BK, 0, &full[s]);
-        tma_load_2d(st + 3 * OT_A, &tmBl, kb * OT_BK, 0, &full[s]);
+        tma_load_2d(st + OT_A, &tmBh, kb * OT_BK, 0, &full[s]);
+        tma_load_2d(st + 2 * OT_A, &tmBl, kb * OT_BK, 0, &full[s]);
       }
       // phase 2: the pipeline memory is free once every out_transform MMA has retired
       mbar_wait(&tmem_full[last_c & 1], (last_c >> 1) & 1);
@@ -130,17 +149,18 @@ outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&split[s], (kb / OT_ST) & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t a_hi = smem_u32(smem + s * OT_STAGE), a_lo = a_hi + OT_A, b_hi = a_hi + 2 * OT_A, b_lo = a_hi + 3 * OT_A;
-        const uint32_t d_main = tmem_base + buf * ACC_COLS, d_small = d_main + 128;
+        const uint32_t b_hi = smem_u32(smem + s * OT_STAGE) + OT_A, b_lo = b_hi + OT_A;
+        const uint32_t d_main = tmem_base + buf * 128, d_small = tmem_base + OT_TM_CORR;
+        const uint32_t ta = tmem_base + OT_TM_A + (kb & 1) * 64;
 #pragma unroll
         for (int k = 0; k < OT_BK / 8; ++k) {
-          const uint64_t dah = smem_desc_sw128(a_hi + k * 32), dal = smem_desc_sw128(a_lo + k * 32);
+          const uint32_t ah = ta + k * 8, al = ah + 32;      // TS mode: A from tensor memory, column = k
           const uint64_t dbh = smem_desc_sw128(b_hi + k * 32), dbl = smem_desc_sw128(b_lo + k * 32);
-          const uint32_t acc = (first && k == 0) ? 0u : 1u;
-          mma_tf32(d_main, dah, dbh, idesc, acc);
-          mma_tf32(d_small, dah, dbl, idesc, acc);
-          mma_tf32(d_small, dal, dbh, idesc, 1u);
+          mma_tf32_ts(d_main, ah, dbh, idesc, (first && k == 0) ? 0u : 1u);
+          mma_tf32_ts(d_small, ah, dbl, idesc, (kb == 0 && k == 0) ? 0u : 1u);
+          mma_tf32_ts(d_small, al, dbh, idesc, 1u);
         }
+        mma_commit(&ta_free[kb & 1]);
         mma_commit(&empty[s]);
         if (last) mma_commit(&tmem_full[buf]);
       }
@@ -188,14 +208,13 @@ outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int buf = c & 1;
       mbar_wait(&tmem_full[buf], (c >> 1) & 1);
       tc_fence_after();
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + c0;
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + c0;
 #pragma unroll
       for (int cc = 0; cc < 64; cc += 32) {
-        float tm[32], ts[32];
+        float tm[32];
         tmem_ld_32x32(tbase + cc, tm);
-        tmem_ld_32x32(tbase + 128 + cc, ts);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[cc + i] += tm[i] + ts[i];
+        for (int i = 0; i < 32; ++i) v[cc + i] += tm[i];
       }
       tc_fence_before();
       __syncwarp();
@@ -205,19 +224,40 @@ outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % OT_ST;
       mbar_wait(&full[s], (kb / OT_ST) & 1);
-      const float4* src = reinterpret_cast<const float4*>(smem + s * OT_STAGE);
-      float4* dst = reinterpret_cast<float4*>(smem + s * OT_STAGE + OT_A);
+      // this thread's 16 floats of its feat row (k-block box [128 rows][32 k], 128-byte swizzle: 16-byte unit u sits at
+      // u ^ (te & 7)) -> tf32 hi | lo in TMEM A slot kb & 1 (lane = row, column = k)
+      const unsigned char* ar = smem + s * OT_STAGE + te * 128;
+      float hi[16], lo[16];
 #pragma unroll
-      for (int m = 0; m < OT_A / 16 / 256; ++m) {
-        const float4 x = src[et + 256 * m];
-        dst[et + 256 * m] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+      for (int u = 0; u < 4; ++u) {
+        const float4 x = *reinterpret_cast<const float4*>(ar + (((half * 4 + u) ^ (te & 7)) << 4));
+        hi[4 * u] = x.x; hi[4 * u + 1] = x.y; hi[4 * u + 2] = x.z; hi[4 * u + 3] = x.w;
       }
-      fence_async_smem();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) lo[i] = tf32_lo(hi[i]);
+      mbar_wait(&ta_free[kb & 1], ((kb >> 1) & 1) ^ 1);    // the MMAs of k-block kb - 2 have read this slot
+      tc_fence_after();
+      const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + OT_TM_A + (kb & 1) * 64 + half * 16;
+      tmem_st16_nw(ta, hi);                                // (raw fp32: the tensor core ignores the low 13 mantissa bits)
+      tmem_st16_nw(ta + 32, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&split[s]);
       if (kb % OT_KCH == 2 && kb / OT_KCH - 1 == promoted && kb >= OT_KCH) { promote(promoted); ++promoted; }
     }
     while (promoted < nchunk) { promote(promoted); ++promoted; }
+    {
+      // the correction accumulator (hi*lo + lo*hi of all k-blocks), once: every MMA has completed (last tmem_full)
+      const uint32_t tcorr = tmem_base + ((uint32_t)(q * 32) << 16) + OT_TM_CORR + c0;
+#pragma unroll
+      for (int cc = 0; cc < 64; cc += 32) {
+        float ts[32];
+        tmem_ld_32x32(tcorr + cc, ts);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[cc + i] += ts[i];
+      }
+    }
     if (et == 0) tstamp(1);
 
     // ---------------- phase 2 ----------------
