@@ -140,9 +140,10 @@ def test_transitions_against_reference_fixture(golden_dir, tstep):
 
 
 # ------------------------------------------------------------------------------------------ oracle, more shapes
-@pytest.mark.parametrize('N,L,ragged', [(2, 24, True), (3, 100, True), (1, 300, False), (2, 64, False)])
+@pytest.mark.parametrize('N,L,ragged', [(2, 24, True), (3, 100, True), (1, 300, False), (2, 64, False), (1, 400, True), (1, 512, False)])
 def test_block_vs_oracle_shapes(N, L, ragged):
-    """Tile-edge cases: L not a multiple of 64 / 4-row tiles, L > 256 (two keys per thread), ragged masks."""
+    """Tile-edge cases: L not a multiple of 64 / 4-row tiles, L > 256 (two-CTA clusters splitting the keys: 5, 7 and 8 chunks per
+    half up to the maximum length 512), ragged masks."""
     W = weights.make_state_dict(seed=5, num_layers=1, flavour='abdesign')
     model = build_model(W, 1, flavour='abdesign')
     inp = weights.synthetic_inputs(100 + L, N, L, gen_slices=((2, 6),), ragged=ragged)
