@@ -21,6 +21,9 @@ constexpr int OT_STAGE = 3 * OT_A;                        // 48 KB: A raw | B hi
 // TMEM columns of phase 1: main accumulator x 2 (promotion double buffer) | corrections (one, never promoted: its terms are 2^-11
 // of the main ones, their truncation is irrelevant) | A ring: 2 slots x (feat hi 32 | lo 32)
 constexpr uint32_t OT_TM_CORR = 256, OT_TM_A = 384;
+// TMEM columns of phase 2: main accumulator | corrections | the layer's input activations hi (128) | lo (128) -- the three MLP
+// layers run in TS mode too; the LayerNorm 1 output needed for the final residual is parked in (idle) shared memory instead
+constexpr uint32_t OT_TM_ACT = 256;
 constexpr int OT_ACT_KB = 2 * OT_A;                       // phase 2: one activation k-block, hi | lo
 constexpr int OT_W_OFF = 4 * OT_ACT_KB;                   // phase 2: weight stages start behind the 4 activation k-blocks
 constexpr int OT_BAR_OFF = OT_ST * OT_STAGE;              // 192 KB
@@ -175,17 +178,16 @@ outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&w_full[s], (g >> 1) & 1);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t a_hi = smem_u32(smem + kb * OT_ACT_KB), a_lo = a_hi + OT_A;
           const uint32_t b_hi = smem_u32(smem + OT_W_OFF + s * OT_ACT_KB), b_lo = b_hi + OT_A;
           const uint32_t d_main = tmem_base, d_small = tmem_base + 128;
 #pragma unroll
           for (int k = 0; k < OT_BK / 8; ++k) {
-            const uint64_t dah = smem_desc_sw128(a_hi + k * 32), dal = smem_desc_sw128(a_lo + k * 32);
+            const uint32_t ah = tmem_base + OT_TM_ACT + kb * OT_BK + k * 8, al = ah + 128;      // TS mode
             const uint64_t dbh = smem_desc_sw128(b_hi + k * 32), dbl = smem_desc_sw128(b_lo + k * 32);
             const uint32_t acc = (kb == 0 && k == 0) ? 0u : 1u;
-            mma_tf32(d_main, dah, dbh, idesc, acc);
-            mma_tf32(d_small, dah, dbl, idesc, acc);
-            mma_tf32(d_small, dal, dbh, idesc, 1u);
+            mma_tf32_ts(d_main, ah, dbh, idesc, acc);
+            mma_tf32_ts(d_small, ah, dbl, idesc, acc);
+            mma_tf32_ts(d_small, al, dbh, idesc, 1u);
           }
           mma_commit(&w_empty[s]);
           if (kb == 3) mma_commit(acc_full);
@@ -299,11 +301,23 @@ outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       fence_async_smem();                                              // generic-proxy writes -> visible to the async proxy
     };
+    // the input of an MLP layer: this thread's 64 values as tf32 hi | lo into the TMEM activation columns (lane = row)
     auto store_act = [&](const float (&h)[64]) {
-      store_planes(h);
+      const uint32_t ta_ = tmem_base + ((uint32_t)(q * 32) << 16) + OT_TM_ACT + c0;
+#pragma unroll
+      for (int cc = 0; cc < 64; cc += 16) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { hi[i] = h[cc + i]; lo[i] = tf32_lo(h[cc + i]); }
+        tmem_st16_nw(ta_ + cc, hi);
+        tmem_st16_nw(ta_ + 128 + cc, lo);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(act_ready);
     };
+    float* park = reinterpret_cast<float*>(smem);                      // [64][256]: value i of thread et (idle pipeline memory)
     const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + c0;
     // out_transform bias, mask_zero (layers.py:6-7), residual (x from the TMA-loaded tile), LayerNorm 1
     {
@@ -323,10 +337,10 @@ outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     layer_norm(v, ta.ln1_g, ta.ln1_b);
-    // the LayerNorm 1 output is needed again for the residual at the end: park it in the idle TMEM buffer 1
-    tmem_st_32x32(tbase + ACC_COLS, *reinterpret_cast<const float(*)[32]>(&v[0]));
-    tmem_st_32x32(tbase + ACC_COLS + 32, *reinterpret_cast<const float(*)[32]>(&v[32]));
-    tc_fence_before();
+    // the LayerNorm 1 output is needed again for the residual at the end: park it in shared memory (every thread has read its
+    // row of the x tile before the barriers inside layer_norm, so the region is free)
+#pragma unroll
+    for (int i = 0; i < 64; ++i) park[i * 256 + et] = v[i];
     store_act(v);
     if (et == 0) tstamp(2);
     for (int l = 0; l < 3; ++l) {
@@ -353,14 +367,10 @@ outT_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     if (et == 0) tstamp(3);
-    // residual (LayerNorm 1 output from TMEM) + LayerNorm 2
+    // residual (LayerNorm 1 output, parked in shared memory) + LayerNorm 2 (its barriers separate these reads from the output
+    // planes written into the same region below)
 #pragma unroll
-    for (int cc = 0; cc < 64; cc += 32) {
-      float y[32];
-      tmem_ld_32x32(tbase + ACC_COLS + cc, y);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[cc + i] += y[i];
-    }
+    for (int i = 0; i < 64; ++i) v[i] += park[i * 256 + et];
     tc_fence_before();
     layer_norm(v, ta.ln2_g, ta.ln2_b);
     // x_out and its tf32 lo plane leave through the (drained) activation slots and TMA tensor stores: whole 128-byte
