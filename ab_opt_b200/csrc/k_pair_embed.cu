@@ -26,6 +26,7 @@
 
 #include "../../include/abopt_b200.h"
 #include "kernels.h"
+#include "tc.cuh"
 
 namespace abopt {
 int api_fail(int code, const std::string& msg);      // api.cu: sets abopt_last_error()
@@ -52,6 +53,11 @@ struct PairEmbedW {                  // device pointers into one packed allocati
   const float* W1h;                  // [26][64]    out_mlp.0[:,192:218]^T
   const float* bias;                 // [5][64]     bd1, bd2, b1, b2, b3
   float freq[6];                     // dihedral_embed.freq_bands
+  // tcgen05 path: B-operand boxes [64 out][32 k] (128-byte rows, 16-byte units XOR-swizzled by out & 7), hi plane | lo plane,
+  // 16 KB each: kb1 boxes of distance_embed.0, then 9 resident ones (distance_embed.2: 2, out_mlp.0 h2 part: 2, angle part: 1
+  // with the two angles' 13 features at k 0..12 and 16..28, out_mlp.2: 2, out_mlp.4: 2)
+  const float* boxes;
+  int kb1;
 };
 
 struct PairEmbedArgs {
@@ -342,6 +348,369 @@ __global__ void __launch_bounds__(PE_THREADS, 1) pair_embed_kernel(PairEmbedW w,
     }
   }
 }
+
+// ------------------------------------------------------------------------------------------ tcgen05 version (round 2)
+// pair_embed_tc_kernel: the same computation on the 5th-gen tensor cores.  Tile = one query residue x 128 keys; the five dense
+// layers are 128 x 64 x K GEMMs as 3xTF32 tcgen05.mma in TS mode: the A operand (activations, tf32 hi | lo) lives in TENSOR MEMORY
+// and is written by the threads that produce it (thread = pair x half of the columns: tcgen05.st), the B operand (weights) comes
+// from shared memory as pre-swizzled K-major boxes [64 out][32 k] hi | lo packed at finalize(): distance_embed.2 and the three
+// out_mlp layers are resident (9 boxes, 144 KB), distance_embed.0 (K = A^2, 8 boxes for 15 atoms) streams from L2 through a 2-stage
+// bulk-copy ring.  10 warps: TMA producer, MMA issuer, 8 compute warps; accumulators (main | corrections) in TMEM.
+//   layer 1  per k-block of 32 distance entries: 16 Gaussians per thread -> TMEM A ring (2 slots) -> 12 MMAs
+//   layers 2-5  acc -> bias / ReLU / masks (+ tables, angular features) in registers -> TMEM activations -> 24-36 MMAs -> acc
+constexpr int PT_THREADS = 320, PT_TILE = 128, PT_NST = 2, PT_NRES = 9;
+constexpr int PT_BOX = 64 * 32 * 4, PT_BOX2 = 2 * PT_BOX;      // one plane of a weight box (8 KB); hi | lo
+constexpr int PT_RES_OFF = 0, PT_RING_OFF = PT_NRES * PT_BOX2, PT_COEF_OFF = PT_RING_OFF + PT_NST * PT_BOX2;
+constexpr int PT_POSJ_OFF = PT_COEF_OFF + 19840, PT_POSI_OFF = PT_POSJ_OFF + PT_TILE * PE_MAXA * 3 * 4;
+constexpr int PT_INT_OFF = PT_POSI_OFF + 192, PT_BIAS_OFF = PT_INT_OFF + 5 * PT_TILE * 4 + 64, PT_BAR_OFF = PT_BIAS_OFF + 5 * 64 * 4;
+constexpr int PT_SMEM = PT_BAR_OFF + 160 + 1024;
+static_assert(PE_AA * PE_MAXA * PE_MAXA * 4 <= 19840 && PT_SMEM <= 227 * 1024, "pair_embed_tc_kernel: shared memory");
+constexpr uint32_t PT_TM_A1 = 0, PT_TM_ACC = 128, PT_TM_ACT = 256, PT_TM_ACTLO = 352;   // TMEM columns
+
+__device__ __forceinline__ void pt_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void pt_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void pt_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                 "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                 "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+               : "memory");
+}
+// hi | lo planes of 16 values -> TMEM columns col.. of the activation (or A-ring) region; lo_off = distance of the lo plane
+__device__ __forceinline__ void pt_store16(uint32_t t_hi, uint32_t lo_off, const float (&v)[16]) {
+  float lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) lo[i] = tf32_lo(v[i]);
+  pt_st16(t_hi, v);
+  pt_st16(t_hi + lo_off, lo);
+}
+// main + corrections, 16 columns
+__device__ __forceinline__ void pt_ld16_sum(uint32_t t_main, float (&v)[16]) {
+  uint32_t m[16], c[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(m[3]), "=r"(m[4]), "=r"(m[5]), "=r"(m[6]), "=r"(m[7]), "=r"(m[8]),
+                 "=r"(m[9]), "=r"(m[10]), "=r"(m[11]), "=r"(m[12]), "=r"(m[13]), "=r"(m[14]), "=r"(m[15]) : "r"(t_main));
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7]), "=r"(c[8]),
+                 "=r"(c[9]), "=r"(c[10]), "=r"(c[11]), "=r"(c[12]), "=r"(c[13]), "=r"(c[14]), "=r"(c[15]) : "r"(t_main + 64));
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(m[0]), "+r"(m[1]), "+r"(m[2]), "+r"(m[3]), "+r"(m[4]), "+r"(m[5]), "+r"(m[6]), "+r"(m[7]), "+r"(m[8]),
+                 "+r"(m[9]), "+r"(m[10]), "+r"(m[11]), "+r"(m[12]), "+r"(m[13]), "+r"(m[14]), "+r"(m[15]) :: "memory");
+  asm volatile("" : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]), "+r"(c[7]), "+r"(c[8]),
+                    "+r"(c[9]), "+r"(c[10]), "+r"(c[11]), "+r"(c[12]), "+r"(c[13]), "+r"(c[14]), "+r"(c[15]) :: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(m[i]) + __uint_as_float(c[i]);
+}
+
+__global__ void __launch_bounds__(PT_THREADS, 1) pair_embed_tc_kernel(PairEmbedW w, PairEmbedArgs a) {
+  using namespace tc;
+  extern __shared__ unsigned char pt_smem_raw[];
+  unsigned char* smem = pt_smem_raw + ((1024u - (smem_u32(pt_smem_raw) & 1023u)) & 1023u);
+  float* sCoef = reinterpret_cast<float*>(smem + PT_COEF_OFF);      // [22][A2]
+  float* sPosJ = reinterpret_cast<float*>(smem + PT_POSJ_OFF);      // [128][A*3]
+  float* sPosI = reinterpret_cast<float*>(smem + PT_POSI_OFF);      // [A*3] (48 slots)
+  int* sAaJ = reinterpret_cast<int*>(smem + PT_INT_OFF);            // [128] amino-acid slot of the key
+  int* sRel = sAaJ + PT_TILE;                                       // [128] row of T_rel, -1 = other chain
+  int* sKeep = sRel + PT_TILE;                                      // [128] structure_mask_i & structure_mask_j
+  int* sOk = sKeep + PT_TILE;                                       // [128] has_CA_i & has_CA_j (& j < L)
+  int* sBitsJ = sOk + PT_TILE;                                      // [128] atom mask of the key, one bit per atom
+  int* sMisc = sBitsJ + PT_TILE;                                    // [16] scalars of the query residue
+  float* sBias = reinterpret_cast<float*>(smem + PT_BIAS_OFF);      // [5][64]
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + PT_BAR_OFF);      // [2]
+  uint64_t* w_empty = w_full + 2;       // [2]
+  uint64_t* a_ready = w_empty + 2;      // [2]  the compute warps have written A-ring slot s
+  uint64_t* ta_free = a_ready + 2;      // [2]  the MMAs that read A-ring slot s have completed
+  uint64_t* act_ready = ta_free + 2;    // the next layer's activations are in TMEM
+  uint64_t* acc_full = act_ready + 1;   // a layer's MMAs have completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int A = w.A, A2 = w.A2, kb1 = w.kb1;
+  const int L = a.L, A_in = a.A_in;
+  const int n_tiles = (L + PT_TILE - 1) / PT_TILE;
+  const long long rows = (long long)a.N * L;
+
+  // ---- resident weight boxes (already in the UMMA layout) and biases: once per CTA
+  {
+    const float4* src = reinterpret_cast<const float4*>(w.boxes + (size_t)kb1 * (PT_BOX2 / 4));
+    float4* dst = reinterpret_cast<float4*>(smem + PT_RES_OFF);
+    for (int i = tid; i < PT_NRES * PT_BOX2 / 16; i += PT_THREADS) dst[i] = src[i];
+    for (int i = tid; i < 5 * 64; i += PT_THREADS) sBias[i] = w.bias[i];
+    fence_async_smem();
+  }
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); mbar_init(&a_ready[s], 8); mbar_init(&ta_free[s], 1); }
+    mbar_init(act_ready, 8); mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== producer: the boxes of distance_embed.0, one per k-block and tile =====================
+    if (elect_one()) {
+      int g = 0;
+      for (long long row = blockIdx.x; row < rows; row += gridDim.x)
+        for (int jt = 0; jt < n_tiles; ++jt)
+          for (int kb = 0; kb < kb1; ++kb, ++g) {
+            const int s = g & 1;
+            mbar_wait(&w_empty[s], ((g >> 1) & 1) ^ 1);
+            mbar_expect_tx(&w_full[s], PT_BOX2);
+            asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(smem + PT_RING_OFF + s * PT_BOX2)), "l"(w.boxes + (size_t)kb * (PT_BOX2 / 4)), "r"(PT_BOX2),
+                           "r"(smem_u32(&w_full[s])) : "memory");
+          }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = idesc_tf32(128, 64);
+    const uint32_t d_main = tmem_base + PT_TM_ACC, d_corr = d_main + 64;
+    int g = 0, ac = 0;
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x)
+      for (int jt = 0; jt < n_tiles; ++jt) {
+        for (int kb = 0; kb < kb1; ++kb, ++g) {
+          const int s = g & 1;
+          mbar_wait(&a_ready[s], (g >> 1) & 1);
+          mbar_wait(&w_full[s], (g >> 1) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t b_hi = smem_u32(smem + PT_RING_OFF + s * PT_BOX2), b_lo = b_hi + PT_BOX;
+            const uint32_t ta = tmem_base + PT_TM_A1 + s * 64;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t ah = ta + k * 8, al = ah + 32;
+              const uint64_t dbh = smem_desc_sw128(b_hi + k * 32), dbl = smem_desc_sw128(b_lo + k * 32);
+              const uint32_t acc = (kb == 0 && k == 0) ? 0u : 1u;
+              pt_mma_ts(d_main, ah, dbh, idesc, acc);
+              pt_mma_ts(d_corr, ah, dbl, idesc, acc);
+              pt_mma_ts(d_corr, al, dbh, idesc, 1u);
+            }
+            mma_commit(&ta_free[s]);
+            mma_commit(&w_empty[s]);
+            if (kb == kb1 - 1) mma_commit(acc_full);
+          }
+          __syncwarp();
+        }
+#pragma unroll 1
+        for (int l = 0; l < 4; ++l, ++ac) {
+          const int nkb = l == 1 ? 3 : 2, box0 = l == 0 ? 0 : (l == 1 ? 2 : (l == 2 ? 5 : 7));
+          mbar_wait(act_ready, ac & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            for (int kb = 0; kb < nkb; ++kb) {
+              const uint32_t b_hi = smem_u32(smem + PT_RES_OFF + (box0 + kb) * PT_BOX2), b_lo = b_hi + PT_BOX;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t ah = tmem_base + PT_TM_ACT + kb * 32 + k * 8, al = tmem_base + PT_TM_ACTLO + kb * 32 + k * 8;
+                const uint64_t dbh = smem_desc_sw128(b_hi + k * 32), dbl = smem_desc_sw128(b_lo + k * 32);
+                const uint32_t acc = (kb == 0 && k == 0) ? 0u : 1u;
+                pt_mma_ts(d_main, ah, dbh, idesc, acc);
+                pt_mma_ts(d_corr, ah, dbl, idesc, acc);
+                pt_mma_ts(d_corr, al, dbh, idesc, 1u);
+              }
+            }
+            mma_commit(acc_full);
+          }
+          __syncwarp();
+        }
+      }
+  } else {
+    // ===================== compute warps (2..9): thread = (pair p of the tile, half of the columns) =====================
+    const int ct = tid - 64;                              // 0..255
+    const int cw = warp - 2;                              // 0..7
+    const int q = warp & 3;                               // TMEM lane quarter this warp may access
+    const int p = q * 32 + lane;                          // pair of the tile = TMEM lane
+    const int half = cw >> 2;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    int g = 0, af = 0;                                    // A-ring slot uses, acc_full completions consumed
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+      const int n = (int)(row / L);
+      pt_bar();                                           // previous row fully consumed
+      // ---- query residue
+      if (ct < A * 3) sPosI[ct] = a.pos[((size_t)row * A_in) * 3 + ct];
+      if (ct == 64) {
+        long long aa = a.aa[row];
+        if (a.sequence_mask && !a.sequence_mask[row]) aa = PE_UNK;                     // pair.py:62-64
+        aa = aa < 0 ? 0 : (aa >= PE_AA ? PE_AA - 1 : aa);
+        int bits = 0;
+        for (int k = 0; k < A; ++k) bits |= (a.mask_atoms[(size_t)row * A_in + k] ? 1 : 0) << k;
+        sMisc[0] = (int)aa;
+        sMisc[1] = bits;
+        sMisc[2] = a.structure_mask ? (a.structure_mask[row] ? 1 : 0) : 1;
+      }
+      pt_bar();
+      const int aa_i = sMisc[0], bits_i = sMisc[1], keep_i = sMisc[2];
+      const int ok_i = (bits_i >> 1) & 1;                                              // BBHeavyAtom.CA = 1, pair.py:57
+      {
+        const float* src = w.coef + (size_t)aa_i * PE_AA * A2;
+        const int total = PE_AA * A2;
+        for (int k0 = ct; k0 < total; k0 += 4 * 256) {
+          float val[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) val[u] = k0 + u * 256 < total ? __ldg(src + k0 + u * 256) : 0.f;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (k0 + u * 256 < total) sCoef[k0 + u * 256] = val[u];
+        }
+      }
+      const long long res_i = a.res_nb[row], chain_i = a.chain_nb[row];
+
+      for (int jt = 0; jt < n_tiles; ++jt) {
+        const int j0 = jt * PT_TILE;
+        pt_bar();                                         // previous tile's readers done (sCoef fill ordered too)
+        // ---- stage the 128 keys: all 256 threads over the tile's coordinates, four independent loads in flight per thread
+        {
+          const int nf = A * 3, total = PT_TILE * nf;
+          const float* src0 = a.pos + (((size_t)n * L + j0) * A_in) * 3;
+          for (int e0 = ct; e0 < total; e0 += 4 * 256) {
+            float val[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int e = e0 + u * 256;
+              const int key = e / nf, c = e - key * nf;
+              val[u] = (e < total && j0 + key < L) ? __ldg(src0 + (size_t)key * A_in * 3 + c) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (e0 + u * 256 < total) sPosJ[e0 + u * 256] = val[u];
+          }
+        }
+        if (ct < PT_TILE) {
+          const int j = j0 + ct;
+          int aaj = 0, rel = -1, keep = 0, ok = 0, bits = 0;
+          if (j < L) {
+            const size_t rj = (size_t)n * L + j;
+            long long aa = a.aa[rj];
+            if (a.sequence_mask && !a.sequence_mask[rj]) aa = PE_UNK;
+            aaj = (int)(aa < 0 ? 0 : (aa >= PE_AA ? PE_AA - 1 : aa));
+            for (int k = 0; k < A; ++k) bits |= (a.mask_atoms[rj * A_in + k] ? 1 : 0) << k;
+            long long d = res_i - a.res_nb[rj];                                        // pair.py:70-73
+            d = d < -PE_RELPOS ? -PE_RELPOS : (d > PE_RELPOS ? PE_RELPOS : d);
+            rel = (a.chain_nb[rj] == chain_i) ? (int)d + PE_RELPOS : -1;
+            keep = keep_i && (a.structure_mask ? (a.structure_mask[rj] != 0) : 1);
+            ok = ok_i && ((bits >> 1) & 1);
+          }
+          sAaJ[ct] = aaj; sRel[ct] = rel; sKeep[ct] = keep; sOk[ct] = ok; sBitsJ[ct] = bits;
+        }
+        pt_bar();
+        const int aa_j = sAaJ[p], rel = sRel[p], bits_j = sBitsJ[p];
+        const float keepf = sKeep[p] ? 1.f : 0.f;
+        const float* xjb = sPosJ + p * (A * 3);
+
+        // ---- layer 1: distance Gaussians, 16 entries of a 32-entry k-block per thread, -> TMEM A ring -> distance_embed.0
+        const float* cfp = sCoef + aa_j * A2;
+        for (int kb = 0; kb < kb1; ++kb, ++g) {
+          const int e0 = kb * 32 + half * 16;
+          int ia = e0 / A, ib = e0 - ia * A;
+          float gv[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int e = e0 + u;
+            const float* xi = sPosI + (ia < 16 ? ia : 15) * 3;
+            const float* xj = xjb + ib * 3;
+            const float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
+            const float d2 = (dx * dx + dy * dy + dz * dz) * 0.01f;                     // (|x_ia - x_jb| / 10)^2, pair.py:77-82
+            const bool on = (e < A2) && ((bits_i >> ia) & 1) && ((bits_j >> ib) & 1);
+            const float v = expf(-cfp[e < A2 ? e : 0] * d2);
+            gv[u] = on ? v : 0.f;                                                         // pair.py:82-84
+            if (++ib == A) { ib = 0; ++ia; }
+          }
+          const int s = g & 1;
+          mbar_wait(&ta_free[s], ((g >> 1) & 1) ^ 1);     // the MMAs of the k-block two before have read this slot
+          tc_fence_after();
+          pt_store16(tlane + PT_TM_A1 + s * 64 + half * 16, 32, gv);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_ready[s]);
+        }
+        // ---- inter-residue dihedral of this thread's angle (half 0: phi, half 1: psi) + angular encoding (13 values)
+        float ang[16];
+        {
+          const float* Ni = sPosI; const float* CAi = sPosI + 3; const float* Ci = sPosI + 6;
+          const float* Nj = xjb; const float* CAj = Nj + 3; const float* Cj = Nj + 6;
+          const float x = half == 0 ? dihedral4(Ci, Nj, CAj, Cj) : dihedral4(Ni, CAi, Ci, Nj);   // geometry.py:362-373
+          ang[0] = x * keepf;                                                                    // pair.py:92-94
+#pragma unroll
+          for (int f = 0; f < 6; ++f) {
+            float sn, cs;
+            sincosf(x * w.freq[f], &sn, &cs);
+            ang[1 + f] = sn * keepf;
+            ang[7 + f] = cs * keepf;
+          }
+          ang[13] = 0.f; ang[14] = 0.f; ang[15] = 0.f;
+        }
+        // table part of the first out_mlp layer (gathers in flight during the two layers before it)
+        float tab[32];
+        {
+          const float4* ta4 = reinterpret_cast<const float4*>(w.Taa + ((size_t)(aa_i * PE_AA + aa_j)) * 64 + half * 32);
+          const float4* tr4 = reinterpret_cast<const float4*>(w.Trel + (size_t)(rel < 0 ? 0 : rel) * 64 + half * 32);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 va = __ldg(ta4 + c);
+            float4 vr = __ldg(tr4 + c);
+            if (rel < 0) vr = make_float4(0.f, 0.f, 0.f, 0.f);
+            tab[4 * c] = va.x + vr.x; tab[4 * c + 1] = va.y + vr.y; tab[4 * c + 2] = va.z + vr.z; tab[4 * c + 3] = va.w + vr.w;
+          }
+        }
+        const uint32_t t_acc = tlane + PT_TM_ACC + half * 32, t_act = tlane + PT_TM_ACT + half * 32;
+        // ---- layers 2-5: accumulator -> registers -> next activations in TMEM
+#pragma unroll 1
+        for (int l = 0; l < 5; ++l, ++af) {
+          mbar_wait(acc_full, af & 1);
+          tc_fence_after();
+          float v[2][16];
+          pt_ld16_sum(t_acc, v[0]);
+          pt_ld16_sum(t_acc + 16, v[1]);
+          const float* b = sBias + l * 64 + half * 32;
+          if (l < 4) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                float x = v[hh][c] + b[hh * 16 + c];
+                if (l == 2) x += tab[hh * 16 + c];                     // o1 = relu(tables + W1 [h2 | ang] + b1)
+                x = fmaxf(x, 0.f);
+                if (l == 1) x *= keepf;                                // h2 * structure pair mask (pair.py:85-87)
+                v[hh][c] = x;
+              }
+            pt_store16(t_act, PT_TM_ACTLO - PT_TM_ACT, v[0]);
+            pt_store16(t_act + 16, PT_TM_ACTLO - PT_TM_ACT, v[1]);
+            if (l == 1) pt_store16(tlane + PT_TM_ACT + 64 + half * 16, PT_TM_ACTLO - PT_TM_ACT, ang);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(act_ready);
+          } else {
+            // last layer: (W3 o2 + b3) * has_CA pair mask, 128 contiguous bytes per thread
+            const int j = j0 + p;
+            if (j < L) {
+              const float s = sOk[p] ? 1.f : 0.f;                                        // pair.py:99
+              float4* dst = reinterpret_cast<float4*>(a.out + ((size_t)row * L + j) * 64 + half * 32);
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int c = 0; c < 16; c += 4)
+                  __stcs(dst + hh * 4 + (c >> 2), make_float4((v[hh][c] + b[hh * 16 + c]) * s, (v[hh][c + 1] + b[hh * 16 + c + 1]) * s,
+                                                               (v[hh][c + 2] + b[hh * 16 + c + 2]) * s, (v[hh][c + 3] + b[hh * 16 + c + 3]) * s));
+            }
+            tc_fence_before();
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
+}
+
 }  // namespace
 }  // namespace abopt
 
@@ -390,6 +759,7 @@ extern "C" int abopt_pair_embed_create(int max_num_atoms, int device, abopt_pair
   // the attribute is per function, not per handle: always opt in for the full-atom size (206 KB)
   cudaError_t e = cudaFuncSetAttribute(pair_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(pe_smem_floats(PE_MAXA * PE_MAXA) * sizeof(float)));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(pair_embed_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM);
   cudaSetDevice(cur);
   if (e != cudaSuccess) { delete pe; return api_fail(ABOPT_ERR_CUDA, std::string("pair_embed_kernel shared memory: ") + cudaGetErrorString(e)); }
   *out = pe;
@@ -463,6 +833,43 @@ extern "C" int abopt_pair_embed_finalize(abopt_pair_embed* pe) {
   transpose(pe->sd["out_mlp.2.weight"].data(), 64, 0, 64, o_w64 + 2 * 4096);
   transpose(pe->sd["out_mlp.4.weight"].data(), 64, 0, 64, o_w64 + 3 * 4096);
   transpose(W1.data(), K1, 192, PE_ANG, o_w1h);
+  // ---- tcgen05 path: pre-swizzled K-major boxes, hi | lo planes
+  const int kb1 = (A2 + 31) / 32;
+  const size_t o_box = reserve((size_t)(kb1 + 9) * 4096);
+  auto pack_box = [&](size_t box, auto val) {             // val(k, n) for k in [0, 32), n in [0, 64)
+    float* hi = &img[o_box + box * 4096];
+    float* lo = hi + 2048;
+    for (int n = 0; n < 64; ++n)
+      for (int k = 0; k < 32; ++k) {
+        const float v = val(k, n);
+        uint32_t bits;
+        memcpy(&bits, &v, 4);
+        bits &= 0xFFFFE000u;
+        float h;
+        memcpy(&h, &bits, 4);
+        const size_t at = (size_t)n * 32 + (size_t)(((k >> 2) ^ (n & 7)) << 2) + (k & 3);
+        hi[at] = v;                                        // raw fp32: the tensor core ignores the low 13 mantissa bits
+        lo[at] = v - h;
+      }
+  };
+  {
+    const std::vector<float>& Wd1 = pe->sd["distance_embed.0.weight"];      // [64][A2]
+    for (int kb = 0; kb < kb1; ++kb)
+      pack_box(kb, [&](int k, int n) { const int e = kb * 32 + k; return e < A2 ? Wd1[(size_t)n * A2 + e] : 0.f; });
+    const std::vector<float>& Wd2 = pe->sd["distance_embed.2.weight"];
+    const std::vector<float>& W2 = pe->sd["out_mlp.2.weight"];
+    const std::vector<float>& W3 = pe->sd["out_mlp.4.weight"];
+    for (int kb = 0; kb < 2; ++kb) {
+      pack_box(kb1 + 0 + kb, [&](int k, int n) { return Wd2[(size_t)n * 64 + kb * 32 + k]; });
+      pack_box(kb1 + 2 + kb, [&](int k, int n) { return W1[(size_t)n * K1 + 128 + kb * 32 + k]; });
+      pack_box(kb1 + 5 + kb, [&](int k, int n) { return W2[(size_t)n * 64 + kb * 32 + k]; });
+      pack_box(kb1 + 7 + kb, [&](int k, int n) { return W3[(size_t)n * 64 + kb * 32 + k]; });
+    }
+    pack_box(kb1 + 4, [&](int k, int n) {
+      const int which = k >> 4, idx = k & 15;
+      return idx < 13 ? W1[(size_t)n * K1 + 192 + which * 13 + idx] : 0.f;
+    });
+  }
   const char* bkeys[5] = {"distance_embed.0.bias", "distance_embed.2.bias", "out_mlp.0.bias", "out_mlp.2.bias", "out_mlp.4.bias"};
   for (int b = 0; b < 5; ++b) memcpy(&img[o_bias + b * 64], pe->sd[bkeys[b]].data(), 64 * sizeof(float));
 
@@ -477,6 +884,7 @@ extern "C" int abopt_pair_embed_finalize(abopt_pair_embed* pe) {
   pe->w.A = pe->A; pe->w.A2 = A2;
   pe->w.coef = base + o_coef; pe->w.Taa = base + o_taa; pe->w.Trel = base + o_trel; pe->w.Wd1 = base + o_wd1;
   pe->w.W64 = base + o_w64; pe->w.W1h = base + o_w1h; pe->w.bias = base + o_bias;
+  pe->w.boxes = base + o_box; pe->w.kb1 = kb1;
   memcpy(pe->w.freq, pe->sd["dihedral_embed.freq_bands"].data(), 6 * sizeof(float));
   pe->finalized = true;
   return ABOPT_OK;
@@ -501,7 +909,9 @@ extern "C" int abopt_pair_embed_forward(abopt_pair_embed* pe, int N, int L, int 
   cudaStream_t st = (cudaStream_t)stream;
   {
     ProfScope ps(KK_OTHER, st);
-    pair_embed_kernel<<<grid, PE_THREADS, pe->smem_bytes, st>>>(pe->w, a);
+    static const bool legacy = [] { const char* e = getenv("ABOPT_PAIR_EMBED_MMASYNC"); return e && e[0] == '1'; }();
+    if (legacy) pair_embed_kernel<<<grid, PE_THREADS, pe->smem_bytes, st>>>(pe->w, a);
+    else pair_embed_tc_kernel<<<grid, PT_THREADS, PT_SMEM, st>>>(pe->w, a);
   }
   cudaError_t e = cudaGetLastError();
   if (cur != pe->device) cudaSetDevice(cur);
