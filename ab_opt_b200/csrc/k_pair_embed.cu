@@ -58,6 +58,7 @@ struct PairEmbedW {                  // device pointers into one packed allocati
   // with the two angles' 13 features at k 0..12 and 16..28, out_mlp.2: 2, out_mlp.4: 2)
   const float* boxes;
   int kb1;
+  const float* coefT;                // [484][A][16]  the same coefficients as [aa pair][key atom][query atom, padded to 16]
 };
 
 struct PairEmbedArgs {
@@ -356,15 +357,16 @@ __global__ void __launch_bounds__(PE_THREADS, 1) pair_embed_kernel(PairEmbedW w,
 // from shared memory as pre-swizzled K-major boxes [64 out][32 k] hi | lo packed at finalize(): distance_embed.2 and the three
 // out_mlp layers are resident (9 boxes, 144 KB), distance_embed.0 (K = A^2, 8 boxes for 15 atoms) streams from L2 through a 2-stage
 // bulk-copy ring.  10 warps: TMA producer, MMA issuer, 8 compute warps; accumulators (main | corrections) in TMEM.
-//   layer 1  per k-block of 32 distance entries: 16 Gaussians per thread -> TMEM A ring (2 slots) -> 12 MMAs
+//   layer 1  K order = [key atom b][query atom a, padded to 16]: a k-block of 32 entries is two key atoms, a thread evaluates the
+//            16 Gaussians of ONE key atom of its pair against the query atoms it keeps in registers -> TMEM A ring (2 slots) -> 12 MMAs
 //   layers 2-5  acc -> bias / ReLU / masks (+ tables, angular features) in registers -> TMEM activations -> 24-36 MMAs -> acc
 constexpr int PT_THREADS = 320, PT_TILE = 128, PT_NST = 2, PT_NRES = 9;
 constexpr int PT_BOX = 64 * 32 * 4, PT_BOX2 = 2 * PT_BOX;      // one plane of a weight box (8 KB); hi | lo
 constexpr int PT_RES_OFF = 0, PT_RING_OFF = PT_NRES * PT_BOX2, PT_COEF_OFF = PT_RING_OFF + PT_NST * PT_BOX2;
-constexpr int PT_POSJ_OFF = PT_COEF_OFF + 19840, PT_POSI_OFF = PT_POSJ_OFF + PT_TILE * PE_MAXA * 3 * 4;
+constexpr int PT_POSJ_OFF = PT_COEF_OFF + PE_AA * PE_MAXA * 16 * 4, PT_POSI_OFF = PT_POSJ_OFF + PT_TILE * PE_MAXA * 3 * 4;
 constexpr int PT_INT_OFF = PT_POSI_OFF + 192, PT_BIAS_OFF = PT_INT_OFF + 5 * PT_TILE * 4 + 64, PT_BAR_OFF = PT_BIAS_OFF + 5 * 64 * 4;
 constexpr int PT_SMEM = PT_BAR_OFF + 160 + 1024;
-static_assert(PE_AA * PE_MAXA * PE_MAXA * 4 <= 19840 && PT_SMEM <= 227 * 1024, "pair_embed_tc_kernel: shared memory");
+static_assert(PT_SMEM <= 227 * 1024, "pair_embed_tc_kernel: shared memory");
 constexpr uint32_t PT_TM_A1 = 0, PT_TM_ACC = 128, PT_TM_ACT = 256, PT_TM_ACTLO = 352;   // TMEM columns
 
 __device__ __forceinline__ void pt_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -410,7 +412,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pair_embed_tc_kernel(PairEmbedW
   using namespace tc;
   extern __shared__ unsigned char pt_smem_raw[];
   unsigned char* smem = pt_smem_raw + ((1024u - (smem_u32(pt_smem_raw) & 1023u)) & 1023u);
-  float* sCoef = reinterpret_cast<float*>(smem + PT_COEF_OFF);      // [22][A2]
+  float* sCoef = reinterpret_cast<float*>(smem + PT_COEF_OFF);      // [22][A][16]
   float* sPosJ = reinterpret_cast<float*>(smem + PT_POSJ_OFF);      // [128][A*3]
   float* sPosI = reinterpret_cast<float*>(smem + PT_POSI_OFF);      // [A*3] (48 slots)
   int* sAaJ = reinterpret_cast<int*>(smem + PT_INT_OFF);            // [128] amino-acid slot of the key
@@ -549,8 +551,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pair_embed_tc_kernel(PairEmbedW
       const int aa_i = sMisc[0], bits_i = sMisc[1], keep_i = sMisc[2];
       const int ok_i = (bits_i >> 1) & 1;                                              // BBHeavyAtom.CA = 1, pair.py:57
       {
-        const float* src = w.coef + (size_t)aa_i * PE_AA * A2;
-        const int total = PE_AA * A2;
+        const float* src = w.coefT + (size_t)aa_i * PE_AA * A * 16;
+        const int total = PE_AA * A * 16;
         for (int k0 = ct; k0 < total; k0 += 4 * 256) {
           float val[4];
 #pragma unroll
@@ -604,23 +606,32 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pair_embed_tc_kernel(PairEmbedW
         const float keepf = sKeep[p] ? 1.f : 0.f;
         const float* xjb = sPosJ + p * (A * 3);
 
-        // ---- layer 1: distance Gaussians, 16 entries of a 32-entry k-block per thread, -> TMEM A ring -> distance_embed.0
-        const float* cfp = sCoef + aa_j * A2;
+        // ---- layer 1: distance Gaussians -> TMEM A ring -> distance_embed.0.  k-block kb = key atoms 2 kb, 2 kb + 1; this thread:
+        //      key atom ib = 2 kb + half of its pair against the 16 (padded) query atoms
+        float xq[16][3];                                  // query atoms (registers; zero beyond A)
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const bool in = u < A;
+          xq[u][0] = in ? sPosI[u * 3] : 0.f; xq[u][1] = in ? sPosI[u * 3 + 1] : 0.f; xq[u][2] = in ? sPosI[u * 3 + 2] : 0.f;
+        }
+        const float* cfp = sCoef + aa_j * (A * 16);
         for (int kb = 0; kb < kb1; ++kb, ++g) {
-          const int e0 = kb * 32 + half * 16;
-          int ia = e0 / A, ib = e0 - ia * A;
+          const int ib = 2 * kb + half;
+          const bool bon = ib < A && ((bits_j >> ib) & 1);
+          const int ibc = ib < A ? ib : 0;
+          const float xj0 = xjb[ibc * 3], xj1 = xjb[ibc * 3 + 1], xj2 = xjb[ibc * 3 + 2];
+          const float4* c4 = reinterpret_cast<const float4*>(cfp + ibc * 16);
+          float cf[16];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { const float4 c = c4[u]; cf[4 * u] = c.x; cf[4 * u + 1] = c.y; cf[4 * u + 2] = c.z; cf[4 * u + 3] = c.w; }
           float gv[16];
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
-            const int e = e0 + u;
-            const float* xi = sPosI + (ia < 16 ? ia : 15) * 3;
-            const float* xj = xjb + ib * 3;
-            const float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
+            const float dx = xq[u][0] - xj0, dy = xq[u][1] - xj1, dz = xq[u][2] - xj2;
             const float d2 = (dx * dx + dy * dy + dz * dz) * 0.01f;                     // (|x_ia - x_jb| / 10)^2, pair.py:77-82
-            const bool on = (e < A2) && ((bits_i >> ia) & 1) && ((bits_j >> ib) & 1);
-            const float v = expf(-cfp[e < A2 ? e : 0] * d2);
+            const bool on = bon && u < A && ((bits_i >> u) & 1);
+            const float v = expf(-cf[u] * d2);
             gv[u] = on ? v : 0.f;                                                         // pair.py:82-84
-            if (++ib == A) { ib = 0; ++ia; }
           }
           const int s = g & 1;
           mbar_wait(&ta_free[s], ((g >> 1) & 1) ^ 1);     // the MMAs of the k-block two before have read this slot
@@ -834,8 +845,12 @@ extern "C" int abopt_pair_embed_finalize(abopt_pair_embed* pe) {
   transpose(pe->sd["out_mlp.4.weight"].data(), 64, 0, 64, o_w64 + 3 * 4096);
   transpose(W1.data(), K1, 192, PE_ANG, o_w1h);
   // ---- tcgen05 path: pre-swizzled K-major boxes, hi | lo planes
-  const int kb1 = (A2 + 31) / 32;
+  const int kb1 = (pe->A + 1) / 2;                        // layer-1 K order: [key atom][query atom padded to 16], 2 key atoms per k-block
   const size_t o_box = reserve((size_t)(kb1 + 9) * 4096);
+  const size_t o_coefT = reserve((size_t)NP * pe->A * 16);
+  for (int r = 0; r < NP; ++r)
+    for (int ib = 0; ib < pe->A; ++ib)
+      for (int ia = 0; ia < pe->A; ++ia) img[o_coefT + ((size_t)r * pe->A + ib) * 16 + ia] = img[o_coef + (size_t)r * A2 + ia * pe->A + ib];
   auto pack_box = [&](size_t box, auto val) {             // val(k, n) for k in [0, 32), n in [0, 64)
     float* hi = &img[o_box + box * 4096];
     float* lo = hi + 2048;
@@ -855,7 +870,10 @@ extern "C" int abopt_pair_embed_finalize(abopt_pair_embed* pe) {
   {
     const std::vector<float>& Wd1 = pe->sd["distance_embed.0.weight"];      // [64][A2]
     for (int kb = 0; kb < kb1; ++kb)
-      pack_box(kb, [&](int k, int n) { const int e = kb * 32 + k; return e < A2 ? Wd1[(size_t)n * A2 + e] : 0.f; });
+      pack_box(kb, [&](int k, int n) {
+        const int ib = 2 * kb + (k >> 4), ia = k & 15;
+        return (ib < pe->A && ia < pe->A) ? Wd1[(size_t)n * A2 + ia * pe->A + ib] : 0.f;
+      });
     const std::vector<float>& Wd2 = pe->sd["distance_embed.2.weight"];
     const std::vector<float>& W2 = pe->sd["out_mlp.2.weight"];
     const std::vector<float>& W3 = pe->sd["out_mlp.4.weight"];
@@ -884,7 +902,7 @@ extern "C" int abopt_pair_embed_finalize(abopt_pair_embed* pe) {
   pe->w.A = pe->A; pe->w.A2 = A2;
   pe->w.coef = base + o_coef; pe->w.Taa = base + o_taa; pe->w.Trel = base + o_trel; pe->w.Wd1 = base + o_wd1;
   pe->w.W64 = base + o_w64; pe->w.W1h = base + o_w1h; pe->w.bias = base + o_bias;
-  pe->w.boxes = base + o_box; pe->w.kb1 = kb1;
+  pe->w.boxes = base + o_box; pe->w.kb1 = kb1; pe->w.coefT = base + o_coefT;
   memcpy(pe->w.freq, pe->sd["dihedral_embed.freq_bands"].data(), 6 * sizeof(float));
   pe->finalized = true;
   return ABOPT_OK;
