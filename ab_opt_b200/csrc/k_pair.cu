@@ -379,6 +379,231 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs 
   }
 }
 
+// ------------------------------------------------------------------------------------------ pair aggregation on tcgen05
+// pair_stream_tc_kernel: the same contraction with the arithmetic on the tensor cores, the z row blocks as the A operand
+// read from TENSOR MEMORY (TS-mode MMAs).  A tile is TWO query rows of the row list:
+//     D[m = row * 64 + channel][n = row' * 16 + head] = sum_j z[row][j][channel] * alpha[row'][head][j]
+// (M = 128, N = 32, the two diagonal blocks are the result, the off-diagonal ones are never read), K = the keys in chunks of 32.
+//   warp 0        producer: per chunk two 8 KB bulk copies of z (L2 evict-first) and two alpha boxes [12 heads][32 keys]
+//                 (128-byte swizzle = the K-major B operand as it lands; heads 12..15 of a row stay zero) through an 8-stage ring
+//   warps 6-17    three transposer groups of four warps, chunk g goes to group g % 3: thread = TMEM lane = (row, channel)
+//                 reads its column of the chunk from shared memory (32 conflict-free scalar loads), and stores it into one of
+//                 four TMEM operand slots as raw | tf32-lo planes (the tensor core ignores the low 13 mantissa bits of the raw
+//                 plane); the group also builds the lo plane of the alpha tile
+//   warp 1        MMA issuer: per chunk 4 k-steps x (hi*hi, hi*lo, lo*hi) of 128 x 32 x 8 -- hi*hi into one of two main
+//                 accumulators (one per half of the keys), the corrections into a third (short chains, see k_tc.cu)
+//   warps 2-5     epilogue: thread = (row, channel) adds the three 12-head sums and stores them (a warp writes 128
+//                 contiguous bytes per head); also zeroes the masked rows of the list
+// What the CUDA-core version does per float4 of z (1 LDS.128 + 24 FFMA2 with 96 live accumulators, 3 warps per scheduler)
+// becomes 4 LDS + 4 LOP + 4 FADD and 1/4 tcgen05.st here, nothing stays in registers between chunks, and the tensor-pipe
+// floor (12 MMAs x 16 clk per chunk = 192 clk against ~840 clk of HBM time per chunk) is far below the memory time.
+constexpr int PX_CJ = 32;                                 // keys per chunk
+constexpr int PX_ZROW = PX_CJ * C * 4;                    // 8192: one query row's chunk of z
+constexpr int PX_AB = 32 * 128;                           // 4096: alpha tile [2 rows x 16 heads][32 keys]
+constexpr int PX_STAGE = 2 * PX_ZROW + 2 * PX_AB;         // z row 0 | z row 1 | alpha raw | alpha lo
+constexpr int PX_TX_A = H * PX_CJ * 4;                    // 1536: what one alpha box delivers
+#ifndef ABOPT_PX_NST
+#define ABOPT_PX_NST 8
+#endif
+constexpr int PX_NST = ABOPT_PX_NST, PX_NSLOT = 4, PX_NG = 3;
+constexpr int PX_TW0 = 6;                                 // first transposer warp
+constexpr int PX_THREADS = (PX_TW0 + 4 * PX_NG) * 32;     // 576
+constexpr int PX_BAR_OFF = PX_NST * PX_STAGE;
+constexpr int PX_SMEM = PX_BAR_OFF + 512 + 1024;
+constexpr uint32_t PX_TM_A = 0, PX_TM_ACC = 256, PX_ACC_COLS = 96;      // TMEM: 4 x (raw 32 | lo 32) | 2 x (main 32 | main 32 | corrections 32)
+static_assert(PX_SMEM <= 227 * 1024, "pair_stream_tc_kernel: shared memory");
+static_assert((3 * PX_NST + PX_NSLOT + 4) * 8 + 4 <= 512, "pair_stream_tc_kernel: barrier block");
+
+__device__ __forceinline__ void px_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void px_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+      "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+        "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+        "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+        "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+}
+
+__global__ void __launch_bounds__(PX_THREADS, 1)
+pair_stream_tc_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + PX_BAR_OFF);
+  uint64_t* ready = full + PX_NST;           // z chunk in its TMEM slot, alpha lo plane built
+  uint64_t* empty = ready + PX_NST;          // the MMAs reading the stage have completed
+  uint64_t* ta_free = empty + PX_NST;        // [PX_NSLOT] the MMAs reading the TMEM operand slot have completed
+  uint64_t* acc_full = ta_free + PX_NSLOT;   // [2]
+  uint64_t* acc_empty = acc_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = a.L, nkb = a.nchunk, gsz = (nkb + 1) / 2;
+  const int nlive = a.count[0], ndead = a.count[1];
+  const int ntiles = (nlive + 1) >> 1;
+
+  // a short last chunk leaves the rest of its z slot untouched, a single-row tile its second half, and heads 12..15 of the
+  // alpha tile are never written: start from zeros so that whatever is stale is finite (it meets alpha = 0 or unused columns)
+  for (int o = threadIdx.x; o < PX_NST * PX_STAGE / 16; o += PX_THREADS) reinterpret_cast<float4*>(smem)[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PX_NST; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 4); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < PX_NSLOT; ++s) mbar_init(&ta_free[s], 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    mbar_fence_init();
+    tma_prefetch_desc(&amap);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint64_t pol = policy_evict_first();
+      int g = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int4 e0 = a.list[2 * tile];
+        const bool two = 2 * tile + 1 < nlive;
+        const int4 e1 = two ? a.list[2 * tile + 1] : e0;
+        const float* z0 = a.z + ((size_t)(a.b0 + e0.x) * L + e0.y) * L * C;
+        const float* z1 = a.z + ((size_t)(a.b0 + e1.x) * L + e1.y) * L * C;
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const int s = g % PX_NST;
+          mbar_wait(&empty[s], ((g / PX_NST) & 1) ^ 1);
+          const uint32_t st = smem_u32(smem + s * PX_STAGE), bar = smem_u32(&full[s]);
+          const int j0 = kb * PX_CJ;
+          const int nj = (L - j0 < PX_CJ) ? (L - j0) : PX_CJ;
+          const uint32_t zb = (uint32_t)(nj * C * 4);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((two ? 2u : 1u) * (zb + PX_TX_A)) : "memory");
+          asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                       ::"r"(st), "l"(z0 + (size_t)j0 * C), "r"(zb), "r"(bar), "l"(pol) : "memory");
+          asm volatile("cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                       ::"r"(st + 2 * PX_ZROW), "l"(&amap), "r"(j0), "r"(e0.y), "r"(e0.x * H), "r"(bar) : "memory");
+          if (two) {
+            asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                         ::"r"(st + PX_ZROW), "l"(z1 + (size_t)j0 * C), "r"(zb), "r"(bar), "l"(pol) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(st + 2 * PX_ZROW + 2048), "l"(&amap), "r"(j0), "r"(e1.y), "r"(e1.x * H), "r"(bar) : "memory");
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = idesc_tf32(128, 32);
+    int g = 0, n = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+      const int buf = n & 1;
+      mbar_wait(&acc_empty[buf], ((n >> 1) & 1) ^ 1);
+      const uint32_t tb = tmem_base + PX_TM_ACC + buf * PX_ACC_COLS;
+      for (int kb = 0; kb < nkb; ++kb, ++g) {
+        const int s = g % PX_NST;
+        mbar_wait(&ready[s], (g / PX_NST) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t b_hi = smem_u32(smem + s * PX_STAGE + 2 * PX_ZROW), b_lo = b_hi + PX_AB;
+          const uint32_t ta = tmem_base + PX_TM_A + (g % PX_NSLOT) * 64;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t ah = ta + k * 8, al = ah + 32;
+            const uint64_t dbh = smem_desc_sw128(b_hi + k * 32), dbl = smem_desc_sw128(b_lo + k * 32);
+            px_mma_ts(tb + (kb / gsz) * 32, ah, dbh, idesc, (kb % gsz == 0 && k == 0) ? 0u : 1u);
+            px_mma_ts(tb + 64, ah, dbl, idesc, (kb == 0 && k == 0) ? 0u : 1u);
+            px_mma_ts(tb + 64, al, dbh, idesc, 1u);
+          }
+          mma_commit(&empty[s]);
+          mma_commit(&ta_free[g % PX_NSLOT]);
+          if (kb == nkb - 1) mma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < PX_TW0) {
+    // ---- epilogue warps; first the masked query rows that are needed: alpha row = 0 (ga.py:25) -> zero pair aggregate
+    const int te = (warp - 2) * 32 + lane;
+    for (int n = blockIdx.x; n < ndead; n += gridDim.x) {
+      const int4 e = a.list[a.nrows - 1 - n];
+      float* feat_row = a.feat + (size_t)e.z * a.feat_ld;
+      float* alpha_row0 = a.alpha + ((size_t)(e.x * H) * L + e.y) * a.Lp;
+      for (int o = te; o < H * C; o += 128) feat_row[o] = 0.f;
+      for (int h = 0; h < H; ++h)
+        for (int j = te; j < a.Lp; j += 128) alpha_row0[(size_t)h * L * a.Lp + j] = 0.f;
+    }
+    const int q = warp & 3, r = q >> 1, c = (q & 1) * 32 + lane;
+    const int ngrp = (nkb + gsz - 1) / gsz;
+    int n = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+      const int buf = n & 1;
+      mbar_wait(&acc_full[buf], (n >> 1) & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + PX_TM_ACC + buf * PX_ACC_COLS + r * 16;
+      float v[16], w[16];
+      tmem_ld_32x16(trow, v);
+      if (ngrp > 1) {
+        tmem_ld_32x16(trow + 32, w);
+#pragma unroll
+        for (int h = 0; h < H; ++h) v[h] += w[h];
+      }
+      tmem_ld_32x16(trow + 64, w);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      const int idx = 2 * tile + r;
+      if (idx < nlive) {
+        float* feat_row = a.feat + (size_t)a.list[idx].z * a.feat_ld + c;
+#pragma unroll
+        for (int h = 0; h < H; ++h) feat_row[h * C] = v[h] + w[h];
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ---- transposers: thread = TMEM lane = (row of the tile, channel)
+    const int gi = (warp - PX_TW0) >> 2, q = warp & 3, r = q >> 1, c = (q & 1) * 32 + lane;
+    const int tg = ((warp - PX_TW0) & 3) * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + PX_TM_A;
+    const int total = ((ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * nkb;      // chunks of this CTA
+    for (int g = gi; g < total; g += PX_NG) {
+      const int s = g % PX_NST, slot = g % PX_NSLOT;
+      unsigned char* st = smem + s * PX_STAGE;
+      mbar_wait(&full[s], (g / PX_NST) & 1);
+      const float* zs = reinterpret_cast<const float*>(st + r * PX_ZROW) + c;
+      float raw[32], lo[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) raw[k] = zs[k * C];
+      {
+        const float4* asrc = reinterpret_cast<const float4*>(st + 2 * PX_ZROW);
+        float4* adst = reinterpret_cast<float4*>(st + 2 * PX_ZROW + PX_AB);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          const float4 v = asrc[tg + 128 * m];
+          adst[tg + 128 * m] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 32; ++k) lo[k] = tf32_lo(raw[k]);
+      mbar_wait(&ta_free[slot], ((g / PX_NSLOT) & 1) ^ 1);      // the MMAs of chunk g - 4 have read this TMEM slot
+      tc_fence_after();
+      px_st32(trow + slot * 64, raw);
+      px_st32(trow + slot * 64 + 32, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ready[s]);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 static int g_sm_count = 0;
 
@@ -389,6 +614,7 @@ cudaError_t pair_stream_init() {
   if ((e = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(pair_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(pair_bias_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PB_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(pair_stream_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PX_SMEM)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -518,17 +744,29 @@ void launch_ctx_delta(int N, int L, int Lp, const float* z, const uint8_t* mask,
 
 bool launch_pair_stream(int nb, int b0, int L, int Lp, const float* z, float* alpha, float* feat, const PairRows& pr, cudaStream_t st,
                         int feat_ld, bool partial) {
+  static const bool ffma = getenv("ABOPT_PAIR_FFMA") != nullptr;      // A/B switch: the CUDA-core kernel
   CUtensorMap amap;
-  // alpha as a plain 3-D tensor [nb * H][L queries][Lp keys]; box = [12 heads][1 query][16 keys]
-  if (!make_tmap_3d_plain(&amap, alpha, (uint64_t)Lp, (uint64_t)L, (uint64_t)nb * H, PW_CJ, 1, H)) return false;
-  ProfScope prof__(partial ? KK_PAIR_PART : KK_PAIR, st);
   PairRowsArgs a{};
-  a.L = L; a.Lp = Lp; a.b0 = b0; a.nrows = nb * L; a.nchunk = (L + PW_CJ - 1) / PW_CJ;
+  a.L = L; a.Lp = Lp; a.b0 = b0; a.nrows = nb * L;
   a.z = z; a.alpha = alpha; a.feat = feat; a.feat_ld = feat_ld; a.list = pr.list; a.count = pr.count;
   int grid = g_sm_count > 0 ? g_sm_count : 148;
-  const int need = (a.nrows + PW_WARPS - 1) / PW_WARPS;
+  if (ffma) {
+    // alpha as a plain 3-D tensor [nb * H][L queries][Lp keys]; box = [12 heads][1 query][16 keys]
+    if (!make_tmap_3d_plain(&amap, alpha, (uint64_t)Lp, (uint64_t)L, (uint64_t)nb * H, PW_CJ, 1, H)) return false;
+    ProfScope prof__(partial ? KK_PAIR_PART : KK_PAIR, st);
+    a.nchunk = (L + PW_CJ - 1) / PW_CJ;
+    const int need = (a.nrows + PW_WARPS - 1) / PW_WARPS;
+    if (grid > need) grid = need;
+    pair_stream_kernel<<<grid, PW_THREADS, PW_SMEM, st>>>(amap, a);
+    return true;
+  }
+  // the same tensor, 128-byte swizzle; box = [12 heads][1 query][32 keys] = 12 rows of the K-major B operand
+  if (!make_tmap_3d_sw128(&amap, alpha, (uint64_t)Lp, (uint64_t)L, (uint64_t)nb * H, PX_CJ, 1, H)) return false;
+  ProfScope prof__(partial ? KK_PAIR_PART : KK_PAIR, st);
+  a.nchunk = (L + PX_CJ - 1) / PX_CJ;
+  const int need = (a.nrows + 1) / 2;
   if (grid > need) grid = need;
-  pair_stream_kernel<<<grid, PW_THREADS, PW_SMEM, st>>>(amap, a);
+  pair_stream_tc_kernel<<<grid, PX_THREADS, PX_SMEM, st>>>(amap, a);
   return true;
 }
 

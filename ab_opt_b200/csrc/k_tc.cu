@@ -562,6 +562,26 @@ bool make_tmap_3d_plain(CUtensorMap* m, const float* base, uint64_t d0, uint64_t
   return true;
 }
 
+// the same 3-D tensor with the 128-byte swizzle (box0 * 4 bytes <= 128): rows of box [box2][box1] land 128 B apart
+bool make_tmap_3d_sw128(CUtensorMap* m, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1, uint32_t box2) {
+  std::lock_guard<std::mutex> lk(g_tmaps_mu);
+  const TmapKey key{base, d1 * 4096 + d2, d0, ((uint64_t)box0 << 32) | ((uint64_t)box2 << 8) | 0x3C, box1};
+  auto it = g_tmaps.find(key);
+  if (it != g_tmaps.end()) { *m = it->second; return true; }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0 * sizeof(float), d0 * d1 * sizeof(float)};
+  cuuint32_t box[3] = {box0, d1 < box1 ? (cuuint32_t)d1 : box1, d2 < box2 ? (cuuint32_t)d2 : box2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if (!g_encode) return false;
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  if (g_tmaps.size() > 4096) g_tmaps.clear();
+  g_tmaps[key] = *m;
+  return true;
+}
+
 // plain (unswizzled) 2-D fp32 tensor map, used for L2 prefetches only
 bool make_tmap_plain(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
   cuuint64_t dims[2] = {cols, rows};

@@ -133,6 +133,7 @@ void launch_ctx_delta(int N, int L, int Lp, const float* z, const uint8_t* mask,
                       const float2* stats_ctx, const float2* stats, const int* cidx, const int* rows, const int* first,
                       const int* count, float* feat, cudaStream_t st);
 bool make_tmap_3d_plain(CUtensorMap* m, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1, uint32_t box2);
+bool make_tmap_3d_sw128(CUtensorMap* m, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1, uint32_t box2);
 
 void launch_angle_argmax(int M, int L, const long long* tvec, int t_uniform, const float* Y, const float* expo,
                          const uint8_t* mask_gen, int* bin_idx, cudaStream_t st);
