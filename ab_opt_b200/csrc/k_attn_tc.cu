@@ -589,9 +589,9 @@ struct AggrArgs {
 //   warps 6-9   epilogue: thread = query row: 64 sums -> node aggregate, R_i^T (o - t_i), norms, directions; every feature
 //               group of a row is a 32-byte-aligned run, stored with 256-bit stores (full sectors, no staging buffer)
 constexpr int AGP_THREADS = 320, AGP_ST = 6;
-// Tile walk from the LAST complex to the first: pair_stream_kernel has just read alpha in forward order, so what is still in the
-// 126 MB L2 is the tail of it -- and this kernel is bound by the latency of its ring, not by bandwidth.
-#define AGP_TILE(t) (ntiles - 1 - (t))
+// Tile walk from the FIRST complex to the last: pair_stream_kernel has just read alpha from the last row to the first, so what is
+// still in the 126 MB L2 is the head of it -- and this kernel is bound by the latency of its ring, not by bandwidth.
+#define AGP_TILE(t) (t)
 constexpr int AGP_SMEM = AGP_ST * AG2_STAGE_BYTES + 256 + 1024;
 
 __device__ __forceinline__ void st_v8f(float* p, float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {

@@ -3,12 +3,10 @@
 //                       weights do not change over the T reverse steps (the hoist is in api.cu)
 //   pair_stream_kernel  the kernel that streams z once per GABlock: sum_j alpha_ijh z_ijc (ga.py:114-118); alpha comes from
 //                       attn_logits_persist_kernel (k_attn_tc.cu)
-// Both are persistent and barrier-free: every warp owns whole query rows and streams its row block through a private TMA
-// ring (mbarrier expect_tx, L2 evict-first); the arithmetic is packed FFMA2 (fma.rn.f32x2) on the CUDA cores.
-// Why CUDA cores and not tcgen05 here: the contractions are skinny (N = 12 heads) and need fp32-grade accuracy, i.e. a
-// 3xTF32 split of z; splitting the 64 KB row block in shared memory plus the operand reads of three MMAs cost ~7 passes
-// over the tile (~3600 clk/row of shared-memory bandwidth) against 1536 clk/row of FFMA issue per contraction -- no gain,
-// so the tensor cores are kept for the dense GEMMs.
+// pair_bias_kernel is barrier-free (every warp owns whole query rows and streams its row block through a private TMA ring,
+// packed FFMA2 on the CUDA cores: it runs 6 times per sampling run).  pair_stream_kernel, which runs 600 times per run, puts
+// the contraction on tcgen05 with z as the TMEM-resident A operand; ctx_delta_kernel is the context-cache companion of the
+// first GABlock (see each kernel's header).
 #include <cstdlib>
 #include <type_traits>
 #include "tc.cuh"
@@ -29,18 +27,6 @@ __device__ __forceinline__ float2 ffma2(float a, float2 b, float2 c) {
   return *reinterpret_cast<float2*>(&rd);
 }
 
-// the same, not reorderable against the TMA / mbarrier instructions (also volatile): used where an FFMA2 stands for "the
-// shared-memory loads feeding it have completed"
-__device__ __forceinline__ float2 ffma2_ordered(float a, float2 b, float2 c) {
-  unsigned long long ra, rb, rc, rd;
-  float2 aa = make_float2(a, a);
-  ra = *reinterpret_cast<unsigned long long*>(&aa);
-  rb = *reinterpret_cast<unsigned long long*>(&b);
-  rc = *reinterpret_cast<unsigned long long*>(&c);
-  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc) : "memory");
-  return *reinterpret_cast<float2*>(&rd);
-}
-
 __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -55,7 +41,7 @@ __device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* m
 // pair_bias_kernel: bias[b,h,i,j] = z[b,i,j,:] . W_b[h,:]   (ga.py:88-90), stored like alpha: [b][h][i][Lp], key index
 // contiguous.  z and W_b do not change over the T reverse steps, so FullDPM.sample runs this ONCE per layer per sampling run
 // (api.cu); a training step runs it once per layer.
-// Same barrier-free structure as pair_stream_kernel: 12 independent warps per SM, each owns whole query rows (b, i) and
+// Barrier-free: 12 independent warps per SM, each owns whole query rows (b, i) and
 // streams the row block z[b,i,:,:] through a private 2-stage ring of 32-key chunks (two TMA boxes of [32 keys][32 channels],
 // 128-byte swizzle, L2 evict-first).  lane = key residue: 16 conflict-free LDS.128 of its z row feed 384 FFMA2
 // (scalar z  x  (W[c][h], W[c][h+1]) head pairs that live in the constant bank -> uniform registers); the 12 results per lane
@@ -152,36 +138,11 @@ pair_bias_kernel(const __grid_constant__ CUtensorMap zmap, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------ pair aggregation
-// pair_stream_kernel: out[b,i,h,c] = sum_j alpha[b,i,j,h] z[b,i,j,c]  (ga.py:114-118), alpha from attn_logits_persist_kernel.
-// One persistent CTA per SM, 12 fully independent warps -- no block barrier anywhere.  Each WARP owns whole query rows
-// (b, i) and streams its row block z[b,i,:,:] through a private 3-stage shared-memory ring in chunks of 16 key residues:
-//   lane 0     producer: per chunk one 1-D bulk copy of z (4 KB contiguous, L2 evict-first) + one 3-D tensor-map box of
-//              alpha [12 heads][1 query][16 keys] (768 B; out-of-range keys arrive as zeros), mbarrier expect_tx
-//   all lanes  quarter-warp q = 4 keys of the chunk, lane l of the quarter = channels 4l..4l+3 and 32+4l..32+4l+3
-//              (conflict-free LDS.128: a quarter reads one whole 128-byte line, the four quarters four rows);
-//              per chunk 8 LDS.128 of z + 12 LDS.128 of alpha (4 distinct addresses) feed 192 FFMA2
-//              (scalar alpha x channel pair, 96 accumulators per lane)
-//   per row    the four quarters are combined with a 2-step shuffle reduce-scatter (each lane ends up with 3 heads x 8
-//              channels) and stored.
-// EARLY RELEASE: the z chunk is moved to registers (32 per lane) as the first thing, and the refill of its slot is issued
-// right after the first head's FFMA2s (which cannot issue before those loads have returned) -- not after all twelve -- so all
-// three z slots of a warp are in flight while it computes.  alpha is read head by head during the chunk, so it lives in its
-// own ring with one slot more; the refill issued inside chunk c lands in the alpha slot of chunk c - 1.  Both copies of a
-// chunk still complete on one mbarrier (the one of the z slot).
+// out[b,i,h,c] = sum_j alpha[b,i,j,h] z[b,i,j,c]  (ga.py:114-118), alpha from attn_logits_persist_kernel.
 // The rows to visit come from a ROW LIST (pair_rows_build_kernel: live rows from the front, masked-but-needed rows from the
-// back), so neither the producer nor the consumer evaluates masks, focus lists or integer divisions in the loop: round 1's
-// version spent ~300 of its ~500 instructions per chunk (and 144 bytes of spills) on that bookkeeping.
-constexpr int PW_WARPS = 12, PW_THREADS = PW_WARPS * 32, PW_STAGES = 3;
-constexpr int PW_CJ = 16;                               // key residues per chunk
-constexpr int PW_Z_BYTES = PW_CJ * C * 4;               // 4096
-constexpr int PW_A_BYTES = H * PW_CJ * 4;               // 768
-constexpr int PW_ASTAGES = PW_STAGES + 1;                // alpha ring: one slot more, see "early release" below
-constexpr int PW_ZRING = PW_STAGES * PW_Z_BYTES, PW_ARING = PW_ASTAGES * PW_A_BYTES;
-constexpr int PW_WARP_BYTES = PW_ZRING + PW_ARING;      // 15360 (a multiple of 128)
-constexpr int PW_SMEM = PW_WARPS * PW_WARP_BYTES + PW_WARPS * PW_STAGES * 8 + 1024;
-
+// back), so the kernel evaluates no masks, focus lists or integer divisions in its loops.
 struct PairRowsArgs {
-  int L, Lp, b0, nrows, nchunk;   // nrows = complexes covered by this launch * L; b0 = first complex; nchunk = ceil(L / 16)
+  int L, Lp, b0, nrows, nchunk;   // nrows = complexes covered by this launch * L; b0 = first complex; nchunk = ceil(L / 32)
   const float* z;                 // (N, L, L, 64)
   float* alpha;                   // [chunk complex][h][i][Lp]; rows of masked queries are zeroed here (ga.py:25)
   float* feat; int feat_ld;       // output rows of H * C floats, row pitch feat_ld (the 1824-wide feature rows, or a 768-wide cache)
@@ -230,158 +191,8 @@ pair_rows_build_kernel(int nrows, int L, int b0, const uint8_t* __restrict__ mas
   if (tid == 0) { count[0] = base[0]; count[1] = base[1]; }
 }
 
-__global__ void __launch_bounds__(PW_THREADS, 1)
-pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs a) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int L = a.L, Lp = a.Lp;
-  unsigned char* wst = base + warp * PW_WARP_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(base + PW_WARPS * PW_WARP_BYTES) + warp * PW_STAGES;
-
-  // a short last chunk leaves the rest of its stage untouched: start from zeros so that stale data is always finite
-  // (it is multiplied by alpha = 0)
-  for (int o = lane; o < PW_WARP_BYTES / 16; o += 32) reinterpret_cast<float4*>(wst)[o] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (lane == 0) {
-    for (int s = 0; s < PW_STAGES; ++s) mbar_init(&full[s], 1);
-    mbar_fence_init();
-    tma_prefetch_desc(&amap);
-  }
-  fence_async_smem();                                   // the generic-proxy zeroes are ordered before the first TMA writes
-  __syncwarp();
-
-  const int stride = gridDim.x * PW_WARPS;
-  const int first = warp * gridDim.x + blockIdx.x;      // consecutive rows go to different SMs
-  const int nlive = a.count[0], ndead = a.count[1];
-
-  // ---- producer cursor (lane 0 issues): this warp's rows of the list, chunk by chunk, PW_STAGES chunks ahead of the consumer
-  int pn = first, pjc = 0;
-  const uint32_t z_beg = smem_u32(wst), a_beg = z_beg + PW_ZRING, a_end = a_beg + PW_ARING;
-  uint32_t pst = z_beg, pal = a_beg, pbar = smem_u32(full);      // z slot / alpha slot / barrier the next chunk goes to
-  int4 pe = pn < nlive ? a.list[pn] : make_int4(0, 0, 0, 0);
-  const uint64_t pol = policy_evict_first();
-  auto issue = [&]() {                                  // executed by the whole warp (uniform control flow)
-    if (pn >= nlive) return;
-    if (lane == 0) {
-      const int j0 = pjc * PW_CJ;
-      const int nj = (L - j0 < PW_CJ) ? (L - j0) : PW_CJ;
-      const uint32_t zb = (uint32_t)(nj * C * 4);
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pbar), "r"(zb + PW_A_BYTES) : "memory");
-      const float* src = a.z + (((size_t)(a.b0 + pe.x) * L + pe.y) * L + j0) * C;
-      asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                   ::"r"(pst), "l"(src), "r"(zb), "r"(pbar), "l"(pol) : "memory");
-      asm volatile("cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                   ::"r"(pal), "l"(&amap), "r"(j0), "r"(pe.y), "r"(pe.x * H), "r"(pbar) : "memory");
-    }
-    pst += PW_Z_BYTES; pbar += 8; pal += PW_A_BYTES;
-    if (pst == a_beg) { pst = z_beg; pbar -= 8 * PW_STAGES; }
-    if (pal == a_end) pal = a_beg;
-    if (++pjc == a.nchunk) {
-      pjc = 0; pn += stride;
-      if (pn < nlive) pe = a.list[pn];
-    }
-  };
-  for (int s = 0; s < PW_STAGES; ++s) issue();
-
-  // ---- masked query rows that are needed: alpha row = 0 (ga.py:25) -> zero pair aggregate
-  for (int n = first; n < ndead; n += stride) {
-    const int4 e = a.list[a.nrows - 1 - n];
-    float* feat_row = a.feat + (size_t)e.z * a.feat_ld;
-    float* alpha_row0 = a.alpha + ((size_t)(e.x * H) * L + e.y) * Lp;
-    for (int o = lane; o < H * C; o += 32) feat_row[o] = 0.f;
-    for (int h = 0; h < H; ++h)
-      for (int j = lane; j < Lp; j += 32) alpha_row0[(size_t)h * L * Lp + j] = 0.f;
-  }
-
-  const int q = lane >> 3, l = lane & 7;
-  const uint32_t zoff0 = (uint32_t)(q * 4 * (C * 4) + l * 16);          // row 4q of the chunk, 16-byte group l
-  const uint32_t aoff0 = (uint32_t)(q * 16);                            // alpha[h][4q..4q+3] at + h * 64
-  const unsigned char* cst = wst;                                       // z slot / alpha slot the consumer reads next
-  const unsigned char* cal = wst + PW_ZRING;
-  uint64_t* cbar = full;
-  uint32_t cph = 0;
-  for (int n = first; n < nlive; n += stride) {
-    const int orow = a.list[n].z;
-    float2 acc[H][4];
-#pragma unroll
-    for (int h = 0; h < H; ++h)
-#pragma unroll
-      for (int p = 0; p < 4; ++p) acc[h][p] = make_float2(0.f, 0.f);
-
-    for (int jc = 0; jc < a.nchunk; ++jc) {
-      mbar_wait(cbar, cph);
-      float4 z0[4], z1[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        z0[k] = *reinterpret_cast<const float4*>(cst + zoff0 + k * (C * 4));
-        z1[k] = *reinterpret_cast<const float4*>(cst + zoff0 + k * (C * 4) + 128);
-      }
-      {
-        // head 0 with ordered FFMA2s: once they have issued, every z load of this lane (and, the loads of a warp completing
-        // in order, every alpha load of the previous chunk) has returned -> the z slot can be refilled
-        const float4 av = *reinterpret_cast<const float4*>(cal + aoff0);
-        const float aj[4] = {av.x, av.y, av.z, av.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          acc[0][0] = ffma2_ordered(aj[k], make_float2(z0[k].x, z0[k].y), acc[0][0]);
-          acc[0][1] = ffma2_ordered(aj[k], make_float2(z0[k].z, z0[k].w), acc[0][1]);
-          acc[0][2] = ffma2_ordered(aj[k], make_float2(z1[k].x, z1[k].y), acc[0][2]);
-          acc[0][3] = ffma2_ordered(aj[k], make_float2(z1[k].z, z1[k].w), acc[0][3]);
-        }
-      }
-      __syncwarp();                                      // every lane is past its loads of the z slot -> refill it
-      issue();
-#pragma unroll
-      for (int h = 1; h < H; ++h) {
-        const float4 av = *reinterpret_cast<const float4*>(cal + aoff0 + h * (PW_CJ * 4));
-        const float aj[4] = {av.x, av.y, av.z, av.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          acc[h][0] = ffma2(aj[k], make_float2(z0[k].x, z0[k].y), acc[h][0]);
-          acc[h][1] = ffma2(aj[k], make_float2(z0[k].z, z0[k].w), acc[h][1]);
-          acc[h][2] = ffma2(aj[k], make_float2(z1[k].x, z1[k].y), acc[h][2]);
-          acc[h][3] = ffma2(aj[k], make_float2(z1[k].z, z1[k].w), acc[h][3]);
-        }
-      }
-      cst += PW_Z_BYTES; ++cbar; cal += PW_A_BYTES;
-      if (cst == wst + PW_ZRING) { cst = wst; cbar = full; cph ^= 1u; }
-      if (cal == wst + PW_WARP_BYTES) cal = wst + PW_ZRING;
-    }
-
-    // ---- combine the four quarters: reduce-scatter over lane bits 4 and 3, so lane (q, l) ends with heads 3q'..3q'+2
-    float* feat_row = a.feat + (size_t)orow * a.feat_ld;
-    const bool up = (lane & 16) != 0, odd = (lane & 8) != 0;
-    float2 r[6][4];
-#pragma unroll
-    for (int hh = 0; hh < 6; ++hh)
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const float2 keep = up ? acc[hh + 6][p] : acc[hh][p];
-        const float2 send = up ? acc[hh][p] : acc[hh + 6][p];
-        r[hh][p].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, 16);
-        r[hh][p].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, 16);
-      }
-    const int h0 = (up ? 6 : 0) + (odd ? 3 : 0);
-#pragma unroll
-    for (int hh = 0; hh < 3; ++hh) {
-      float2 o[4];
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const float2 keep = odd ? r[hh + 3][p] : r[hh][p];
-        const float2 send = odd ? r[hh][p] : r[hh + 3][p];
-        o[p].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, 8);
-        o[p].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, 8);
-      }
-      const int off = (h0 + hh) * C + 4 * l;
-      *reinterpret_cast<float4*>(feat_row + off) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
-      *reinterpret_cast<float4*>(feat_row + off + 32) = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------ pair aggregation on tcgen05
-// pair_stream_tc_kernel: the same contraction with the arithmetic on the tensor cores, the z row blocks as the A operand
-// read from TENSOR MEMORY (TS-mode MMAs).  A tile is TWO query rows of the row list:
+// pair_stream_kernel: the contraction on the tensor cores (3xTF32), the z row blocks as the A operand read from TENSOR MEMORY
+// (TS-mode MMAs).  One persistent CTA per SM; a tile is TWO query rows of the row list:
 //     D[m = row * 64 + channel][n = row' * 16 + head] = sum_j z[row][j][channel] * alpha[row'][head][j]
 // (M = 128, N = 32, the two diagonal blocks are the result, the off-diagonal ones are never read), K = the keys in chunks of 32.
 //   warp 0        producer: per chunk two 8 KB bulk copies of z (L2 evict-first) and two alpha boxes [12 heads][32 keys]
@@ -394,9 +205,14 @@ pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs 
 //                 accumulators (one per half of the keys), the corrections into a third (short chains, see k_tc.cu)
 //   warps 2-5     epilogue: thread = (row, channel) adds the three 12-head sums and stores them (a warp writes 128
 //                 contiguous bytes per head); also zeroes the masked rows of the list
-// What the CUDA-core version does per float4 of z (1 LDS.128 + 24 FFMA2 with 96 live accumulators, 3 warps per scheduler)
-// becomes 4 LDS + 4 LOP + 4 FADD and 1/4 tcgen05.st here, nothing stays in registers between chunks, and the tensor-pipe
-// floor (12 MMAs x 16 clk per chunk = 192 clk against ~840 clk of HBM time per chunk) is far below the memory time.
+// Round 1 and most of round 2 ran this contraction on the CUDA cores (12 barrier-free warps per SM, per float4 of z one LDS.128 +
+// 24 FFMA2 into 96 live accumulators, 168 registers, 3 warps per scheduler): 242-249 us per full C2 launch = 0.67-0.70 of the HBM
+// peak, bound by FFMA2 issue latency, not by memory.  Here a float4 of z costs 4 LDS + 4 LOP + 4 FADD and 1/4 of a
+// tcgen05.st, nothing stays in registers between chunks, and the tensor-pipe floor (12 MMAs x 16 clk per chunk = 192 clk against
+// ~840 clk of HBM time per chunk) is far below the memory time: 207 us, i.e. z + alpha + the output rows move at 0.99 of the
+// measured copy bandwidth.  Ring depth 8 measured best (9: 221 us); L2-sized batch chunks lose (2 x 109 / 4 x 57 us).
+// Tiles are walked from the LAST list entry to the first: the logits kernel has just written alpha in forward order, so the tail
+// of it is what the 126 MB L2 still holds (211 -> 207 us); aggr_persist_kernel then walks forward for the same reason.
 constexpr int PX_CJ = 32;                                 // keys per chunk
 constexpr int PX_ZROW = PX_CJ * C * 4;                    // 8192: one query row's chunk of z
 constexpr int PX_AB = 32 * 128;                           // 4096: alpha tile [2 rows x 16 heads][32 keys]
@@ -406,13 +222,14 @@ constexpr int PX_TX_A = H * PX_CJ * 4;                    // 1536: what one alph
 #define ABOPT_PX_NST 8
 #endif
 constexpr int PX_NST = ABOPT_PX_NST, PX_NSLOT = 4, PX_NG = 3;
+#define PX_TILE(t) (ntiles - 1 - (t))
 constexpr int PX_TW0 = 6;                                 // first transposer warp
 constexpr int PX_THREADS = (PX_TW0 + 4 * PX_NG) * 32;     // 576
 constexpr int PX_BAR_OFF = PX_NST * PX_STAGE;
 constexpr int PX_SMEM = PX_BAR_OFF + 512 + 1024;
 constexpr uint32_t PX_TM_A = 0, PX_TM_ACC = 256, PX_ACC_COLS = 96;      // TMEM: 4 x (raw 32 | lo 32) | 2 x (main 32 | main 32 | corrections 32)
-static_assert(PX_SMEM <= 227 * 1024, "pair_stream_tc_kernel: shared memory");
-static_assert((3 * PX_NST + PX_NSLOT + 4) * 8 + 4 <= 512, "pair_stream_tc_kernel: barrier block");
+static_assert(PX_SMEM <= 227 * 1024, "pair_stream_kernel: shared memory");
+static_assert((3 * PX_NST + PX_NSLOT + 4) * 8 + 4 <= 512, "pair_stream_kernel: barrier block");
 
 __device__ __forceinline__ void px_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
@@ -434,7 +251,7 @@ __device__ __forceinline__ void px_st32(uint32_t taddr, const float (&v)[32]) {
 }
 
 __global__ void __launch_bounds__(PX_THREADS, 1)
-pair_stream_tc_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs a) {
+pair_stream_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + PX_BAR_OFF);
@@ -471,9 +288,10 @@ pair_stream_tc_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsAr
       const uint64_t pol = policy_evict_first();
       int g = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int4 e0 = a.list[2 * tile];
-        const bool two = 2 * tile + 1 < nlive;
-        const int4 e1 = two ? a.list[2 * tile + 1] : e0;
+        const int pt = PX_TILE(tile);
+        const int4 e0 = a.list[2 * pt];
+        const bool two = 2 * pt + 1 < nlive;
+        const int4 e1 = two ? a.list[2 * pt + 1] : e0;
         const float* z0 = a.z + ((size_t)(a.b0 + e0.x) * L + e0.y) * L * C;
         const float* z1 = a.z + ((size_t)(a.b0 + e1.x) * L + e1.y) * L * C;
         for (int kb = 0; kb < nkb; ++kb, ++g) {
@@ -556,7 +374,7 @@ pair_stream_tc_kernel(const __grid_constant__ CUtensorMap amap, const PairRowsAr
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
-      const int idx = 2 * tile + r;
+      const int idx = 2 * PX_TILE(tile) + r;
       if (idx < nlive) {
         float* feat_row = a.feat + (size_t)a.list[idx].z * a.feat_ld + c;
 #pragma unroll
@@ -612,9 +430,8 @@ cudaError_t pair_stream_init() {
   int dev = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(pair_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(pair_bias_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PB_SMEM)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(pair_stream_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PX_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(pair_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PX_SMEM)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -744,29 +561,18 @@ void launch_ctx_delta(int N, int L, int Lp, const float* z, const uint8_t* mask,
 
 bool launch_pair_stream(int nb, int b0, int L, int Lp, const float* z, float* alpha, float* feat, const PairRows& pr, cudaStream_t st,
                         int feat_ld, bool partial) {
-  static const bool ffma = getenv("ABOPT_PAIR_FFMA") != nullptr;      // A/B switch: the CUDA-core kernel
   CUtensorMap amap;
-  PairRowsArgs a{};
-  a.L = L; a.Lp = Lp; a.b0 = b0; a.nrows = nb * L;
-  a.z = z; a.alpha = alpha; a.feat = feat; a.feat_ld = feat_ld; a.list = pr.list; a.count = pr.count;
-  int grid = g_sm_count > 0 ? g_sm_count : 148;
-  if (ffma) {
-    // alpha as a plain 3-D tensor [nb * H][L queries][Lp keys]; box = [12 heads][1 query][16 keys]
-    if (!make_tmap_3d_plain(&amap, alpha, (uint64_t)Lp, (uint64_t)L, (uint64_t)nb * H, PW_CJ, 1, H)) return false;
-    ProfScope prof__(partial ? KK_PAIR_PART : KK_PAIR, st);
-    a.nchunk = (L + PW_CJ - 1) / PW_CJ;
-    const int need = (a.nrows + PW_WARPS - 1) / PW_WARPS;
-    if (grid > need) grid = need;
-    pair_stream_kernel<<<grid, PW_THREADS, PW_SMEM, st>>>(amap, a);
-    return true;
-  }
-  // the same tensor, 128-byte swizzle; box = [12 heads][1 query][32 keys] = 12 rows of the K-major B operand
+  // alpha as a 3-D tensor [nb * H][L queries][Lp keys], 128-byte swizzle; box = [12 heads][1 query][32 keys] = 12 rows of the
+  // K-major B operand (out-of-range keys arrive as zeros)
   if (!make_tmap_3d_sw128(&amap, alpha, (uint64_t)Lp, (uint64_t)L, (uint64_t)nb * H, PX_CJ, 1, H)) return false;
   ProfScope prof__(partial ? KK_PAIR_PART : KK_PAIR, st);
-  a.nchunk = (L + PX_CJ - 1) / PX_CJ;
+  PairRowsArgs a{};
+  a.L = L; a.Lp = Lp; a.b0 = b0; a.nrows = nb * L; a.nchunk = (L + PX_CJ - 1) / PX_CJ;
+  a.z = z; a.alpha = alpha; a.feat = feat; a.feat_ld = feat_ld; a.list = pr.list; a.count = pr.count;
+  int grid = g_sm_count > 0 ? g_sm_count : 148;
   const int need = (a.nrows + 1) / 2;
   if (grid > need) grid = need;
-  pair_stream_tc_kernel<<<grid, PX_THREADS, PX_SMEM, st>>>(amap, a);
+  pair_stream_kernel<<<grid, PX_THREADS, PX_SMEM, st>>>(amap, a);
   return true;
 }
 

@@ -5,18 +5,16 @@
 // (N,L,L,A*A) distance tensor (3.8 GB at N=64, L=256, A=15), the (N,L,L,218) concatenation or any MLP intermediate.
 //
 // Work unit = one query residue (n, i): its atoms, its 22 rows of the softplus'd distance-coefficient table and its scalars are
-// staged once, then the L keys are walked in tiles of 64 pairs.  Per tile, all in shared memory / registers:
+// staged once, then the L keys are walked in tiles of 128 pairs.  Per tile, on chip only:
 //   g[ab][pair] = mask_a mask_b exp(-softplus(coef[aa_i aa_j][ab]) (|x_ia - x_jb| / 10)^2)          pair.py:77-84
 //   h1 = relu(Wd1 g + b), h2 = relu(Wd2 h1 + b) * structure_pair                                      pair.py:84-87
 //   phi/psi -> [x, sin(x f), cos(x f)] * structure_pair                                               pair.py:90-94
 //   o1 = relu(T_aa[aa_i aa_j] + same_chain T_rel[clamp(res_i - res_j)] + W1[:,128:192] h2 + W1[:,192:218] ang + b1)
 //        (the aa-pair and relative-position embeddings go through the first out_mlp layer as pre-multiplied tables)  pair.py:65-74,97-98
 //   o2 = relu(W2 o1 + b2), z = (W3 o2 + b3) * has_CA_i has_CA_j                                        pair.py:98-99
-// The five dense layers are 64-pair x 64-channel GEMMs on the warp-level tensor-core path (mma.sync m16n8k8 tf32, fp32
-// accumulate) as 3xTF32 (a b + a_lo b + a b_lo, operands split in registers) because the parity target is the reference's
-// fp32 output.  Weights stay resident in shared memory as [k][out] with the out index XOR-swizzled by (k & 3) << 3, activations
-// as [k][pair] with a leading dimension of 72, so that every fragment load is bank-conflict free.  (The FP32-FFMA version of
-// these phases was shared-memory-bandwidth bound: two LDS.128 per 16 FFMA)
+// The five dense layers run on the 5th-gen tensor cores as 3xTF32 (a b + a_lo b + a b_lo) because the parity target is the
+// reference's fp32 output; see pair_embed_tc_kernel below.  History: FP32 FFMA 18.4 ms -> mma.sync m16n8k8 tf32
+// 10.2 ms (round 1) -> tcgen05 TS mode 4.1 ms at B=64, L=256, 15 atoms.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -32,11 +30,6 @@ namespace abopt {
 int api_fail(int code, const std::string& msg);      // api.cu: sets abopt_last_error()
 
 namespace {
-constexpr int PE_THREADS = 256;
-constexpr int PE_TILE = 64;          // pairs per tile
-constexpr int PE_KC = 80;            // distance entries per chunk of the first layer's K loop (multiple of 8)
-constexpr int PE_LD = 72;            // leading dimension of the [k][pair] activation buffers (64 pairs + 8: conflict-free fragments)
-constexpr int PE_ANGP = 32;          // angle features padded to a multiple of 8 (zero rows)
 constexpr int PE_MAXA = 15;          // max_num_heavyatoms (utils/protein/constants.py:143)
 constexpr int PE_AA = 22;            // max_aa_types (pair.py:12)
 constexpr int PE_RELPOS = 32;        // max_relpos (pair.py:12)
@@ -45,20 +38,16 @@ constexpr int PE_ANG = 26;           // AngularEncoding.get_out_dim(2) (layers.p
 
 struct PairEmbedW {                  // device pointers into one packed allocation
   int A, A2;
-  const float* coef;                 // [484][A2]   softplus(aapair_to_distcoef)
   const float* Taa;                  // [484][64]   aa_pair_embed . W1[:, 0:64]^T
   const float* Trel;                 // [65][64]    relpos_embed  . W1[:, 64:128]^T
-  const float* Wd1;                  // [A2][64]    distance_embed.0.weight^T
-  const float* W64;                  // [4][64][64] distance_embed.2, out_mlp.0[:,128:192], out_mlp.2, out_mlp.4 (all [k][out])
-  const float* W1h;                  // [26][64]    out_mlp.0[:,192:218]^T
   const float* bias;                 // [5][64]     bd1, bd2, b1, b2, b3
   float freq[6];                     // dihedral_embed.freq_bands
-  // tcgen05 path: B-operand boxes [64 out][32 k] (128-byte rows, 16-byte units XOR-swizzled by out & 7), hi plane | lo plane,
+  // B-operand boxes [64 out][32 k] (128-byte rows, 16-byte units XOR-swizzled by out & 7), hi plane | lo plane,
   // 16 KB each: kb1 boxes of distance_embed.0, then 9 resident ones (distance_embed.2: 2, out_mlp.0 h2 part: 2, angle part: 1
   // with the two angles' 13 features at k 0..12 and 16..28, out_mlp.2: 2, out_mlp.4: 2)
   const float* boxes;
   int kb1;
-  const float* coefT;                // [484][A][16]  the same coefficients as [aa pair][key atom][query atom, padded to 16]
+  const float* coefT;                // [484][A][16]  softplus(aapair_to_distcoef) as [aa pair][key atom][query atom, padded to 16]
 };
 
 struct PairEmbedArgs {
@@ -68,290 +57,8 @@ struct PairEmbedArgs {
   float* out;
 };
 
-// smem carve-up (floats); the host computes the same total
-__host__ __device__ inline int pe_smem_floats(int A2) {
-  const int A2p = (A2 + 7) & ~7;
-  return A2p * 64 + 4 * 4096 + PE_ANGP * 64 + 5 * 64    // weights
-         + PE_KC * PE_LD + 64 * PE_LD + PE_ANGP * PE_LD  // g chunk (aliased by hA), hB, angle features
-         + ((PE_AA * A2 + 3) & ~3)                        // coefficient rows of aa_i
-         + PE_TILE * PE_MAXA * 3 + 48                     // key atoms, query atoms
-         + 6 * PE_TILE;                                   // per-pair ints
-}
-
-// ---- warp-level tensor-core GEMM pieces.  Warp w owns pairs [16 (w & 3), +16) x channels [32 (w >> 2), +32) of the 64 x 64 tile:
-// four m16n8 accumulators acc[nt][0..3] = (pair g, ch 2t), (pair g, ch 2t+1), (pair g+8, ch 2t), (pair g+8, ch 2t+1) with
-// g = lane >> 2, t = lane & 3 (the PTX fragment layout of mma.m16n8k8).
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-__device__ __forceinline__ void split3(float x, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(x) & 0xFFFFE000u;                 // tf32-exact high part
-  lo = __float_as_uint(x - __uint_as_float(hi));         // remainder (the MMA reads its top 19 bits)
-}
-// acc += act[k][pair] W[k][ch] over k in [0, 8 * k8): act has leading dimension PE_LD, W is [k][64] with ch ^ ((k & 3) << 3)
-__device__ __forceinline__ void tile_mma(float (&acc)[4][4], const float* __restrict__ act, const float* __restrict__ W, int k8, int p0, int n0,
-                                         int g, int t) {
-  const float* ap = act + t * PE_LD + p0 + g;
-  const float* wp = W + t * 64;
-  int col[4];
-#pragma unroll
-  for (int nt = 0; nt < 4; ++nt) col[nt] = (n0 + nt * 8 + g) ^ (t << 3);
-  float lo[4][4];                                          // the two small terms accumulate apart from the main product: shorter
-#pragma unroll                                             // dependency chains for the in-order MMA issue and a cleaner sum
-  for (int nt = 0; nt < 4; ++nt) { lo[nt][0] = 0.f; lo[nt][1] = 0.f; lo[nt][2] = 0.f; lo[nt][3] = 0.f; }
-#pragma unroll 4
-  for (int s = 0; s < k8; ++s) {
-    uint32_t ah[4], al[4], bh[4][2], bl[4][2];
-    split3(ap[0], ah[0], al[0]);
-    split3(ap[8], ah[1], al[1]);
-    split3(ap[4 * PE_LD], ah[2], al[2]);
-    split3(ap[4 * PE_LD + 8], ah[3], al[3]);
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      split3(wp[col[nt]], bh[nt][0], bl[nt][0]);
-      split3(wp[4 * 64 + col[nt]], bh[nt][1], bl[nt][1]);
-    }
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) mma_tf32(lo[nt], al, bh[nt]);
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[nt], ah, bh[nt]);
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) mma_tf32(lo[nt], ah, bl[nt]);
-    ap += 8 * PE_LD;
-    wp += 8 * 64;
-  }
-#pragma unroll
-  for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[nt][c] += lo[nt][c];
-}
-
-__device__ __forceinline__ void zero_acc(float (&acc)[4][4]) {
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-}
-
-// relu(acc + bias) [* keep[pair]] -> dst[ch][pair] (leading dimension PE_LD)
-__device__ __forceinline__ void store_act(const float (&acc)[4][4], const float* __restrict__ b, float* dst, int p0, int n0, int g, int t,
-                                          const int* keep) {
-  const float s0 = keep ? (keep[p0 + g] ? 1.f : 0.f) : 1.f, s1 = keep ? (keep[p0 + g + 8] ? 1.f : 0.f) : 1.f;
-#pragma unroll
-  for (int nt = 0; nt < 4; ++nt) {
-    const int ch = n0 + nt * 8 + 2 * t;
-    const float b0 = b[ch], b1 = b[ch + 1];
-    float* d = dst + ch * PE_LD + p0 + g;
-    d[0] = fmaxf(acc[nt][0] + b0, 0.f) * s0;
-    d[PE_LD] = fmaxf(acc[nt][1] + b1, 0.f) * s0;
-    d[8] = fmaxf(acc[nt][2] + b0, 0.f) * s1;
-    d[PE_LD + 8] = fmaxf(acc[nt][3] + b1, 0.f) * s1;
-  }
-}
-
-__global__ void __launch_bounds__(PE_THREADS, 1) pair_embed_kernel(PairEmbedW w, PairEmbedArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  const int A = w.A, A2 = w.A2;
-  const int A2p = (A2 + 7) & ~7;                   // K of the first layer, padded with zero rows
-  float* sWd1 = smem;                              // [A2p][64]
-  float* sW64 = sWd1 + A2p * 64;                   // [4][64][64]
-  float* sW1h = sW64 + 4 * 4096;                   // [32][64]
-  float* sBias = sW1h + PE_ANGP * 64;              // [5][64]
-  float* sG = sBias + 5 * 64;                      // [80][72] distance chunk; later hA [64][72]
-  float* sHB = sG + PE_KC * PE_LD;                 // [64][72]
-  float* sAng = sHB + 64 * PE_LD;                  // [32][72], rows 26..31 stay zero
-  float* sCoef = sAng + PE_ANGP * PE_LD;           // [22][A2]
-  float* sPosJ = sCoef + ((PE_AA * A2 + 3) & ~3);  // [64][A*3]
-  float* sPosI = sPosJ + PE_TILE * PE_MAXA * 3;    // [A*3] (48 slots)
-  int* sAaJ = reinterpret_cast<int*>(sPosI + 48);  // [64] amino-acid slot of the key
-  int* sRel = sAaJ + PE_TILE;                      // [64] row of T_rel, -1 = other chain
-  int* sKeep = sRel + PE_TILE;                     // [64] structure_mask_i & structure_mask_j
-  int* sOk = sKeep + PE_TILE;                      // [64] has_CA_i & has_CA_j (& j < L)
-  int* sBitsJ = sOk + PE_TILE;                     // [64] atom mask of the key, one bit per atom
-  int* sMisc = sBitsJ + PE_TILE;                   // [64] scalars of the query residue
-
-  const int tid = threadIdx.x;
-  const int lane = tid & 31, wid = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;           // mma fragment coordinates
-  const int p0 = (wid & 3) * 16, n0 = (wid >> 2) * 32;   // this warp's 16 pairs x 32 channels of the tile
-  const int L = a.L, A_in = a.A_in;
-
-  // ---- weights: once per CTA
-  for (int i = tid; i < A2p * 64; i += PE_THREADS) sWd1[i] = w.Wd1[i];
-  for (int i = tid; i < 4 * 4096; i += PE_THREADS) sW64[i] = w.W64[i];
-  for (int i = tid; i < PE_ANGP * 64; i += PE_THREADS) sW1h[i] = w.W1h[i];
-  for (int i = tid; i < PE_ANGP * PE_LD; i += PE_THREADS) sAng[i] = 0.f;
-  for (int i = tid; i < 5 * 64; i += PE_THREADS) sBias[i] = w.bias[i];
-
-
-  const int n_tiles = (L + PE_TILE - 1) / PE_TILE;
-  const long long rows = (long long)a.N * L;
-  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int n = (int)(row / L);
-    __syncthreads();                               // previous row fully consumed (also orders the weight fill)
-    // ---- query residue
-    if (tid < A * 3) sPosI[tid] = a.pos[((size_t)row * A_in) * 3 + tid];
-    if (tid == 32) {
-      long long aa = a.aa[row];
-      if (a.sequence_mask && !a.sequence_mask[row]) aa = PE_UNK;                     // pair.py:62-64
-      aa = aa < 0 ? 0 : (aa >= PE_AA ? PE_AA - 1 : aa);
-      int bits = 0;
-      for (int k = 0; k < A; ++k) bits |= (a.mask_atoms[(size_t)row * A_in + k] ? 1 : 0) << k;
-      sMisc[0] = (int)aa;
-      sMisc[1] = bits;
-      sMisc[2] = a.structure_mask ? (a.structure_mask[row] ? 1 : 0) : 1;
-    }
-    __syncthreads();
-    const int aa_i = sMisc[0], bits_i = sMisc[1], keep_i = sMisc[2];
-    const int ok_i = (bits_i >> 1) & 1;                                              // BBHeavyAtom.CA = 1, pair.py:57
-    {
-      const float* src = w.coef + (size_t)aa_i * PE_AA * A2;
-      for (int k = tid; k < PE_AA * A2; k += PE_THREADS) sCoef[k] = src[k];
-    }
-    const long long res_i = a.res_nb[row], chain_i = a.chain_nb[row];
-
-    for (int jt = 0; jt < n_tiles; ++jt) {
-      const int j0 = jt * PE_TILE;
-      __syncthreads();                             // previous tile's readers done (sCoef fill ordered too)
-      // ---- stage the 64 keys
-      for (int p = tid >> 5; p < PE_TILE; p += PE_THREADS / 32) {                      // one warp per key residue, no divisions
-        const int j = j0 + p;
-        const float* src = a.pos + (((size_t)n * L + j) * A_in) * 3;
-        for (int c = tid & 31; c < A * 3; c += 32) sPosJ[p * (A * 3) + c] = j < L ? src[c] : 0.f;
-      }
-      if (tid < PE_TILE) {
-        const int j = j0 + tid;
-        int aaj = 0, rel = -1, keep = 0, ok = 0, bits = 0;
-        if (j < L) {
-          const size_t rj = (size_t)n * L + j;
-          long long aa = a.aa[rj];
-          if (a.sequence_mask && !a.sequence_mask[rj]) aa = PE_UNK;
-          aaj = (int)(aa < 0 ? 0 : (aa >= PE_AA ? PE_AA - 1 : aa));
-          for (int k = 0; k < A; ++k) bits |= (a.mask_atoms[rj * A_in + k] ? 1 : 0) << k;
-          long long d = res_i - a.res_nb[rj];                                        // pair.py:70-73
-          d = d < -PE_RELPOS ? -PE_RELPOS : (d > PE_RELPOS ? PE_RELPOS : d);
-          rel = (a.chain_nb[rj] == chain_i) ? (int)d + PE_RELPOS : -1;
-          keep = keep_i && (a.structure_mask ? (a.structure_mask[rj] != 0) : 1);
-          ok = ok_i && ((bits >> 1) & 1);
-        }
-        sAaJ[tid] = aaj; sRel[tid] = rel; sKeep[tid] = keep; sOk[tid] = ok; sBitsJ[tid] = bits;
-      }
-      __syncthreads();
-
-      // ---- inter-residue dihedrals + angular encoding: every thread evaluates the angle of (pair, phi|psi); the two halves
-      //      of the CTA split the six frequencies between them
-      {
-        const int p = tid & 63, which = (tid >> 6) & 1, half = tid >> 7;
-        const float* Ni = sPosI; const float* CAi = sPosI + 3; const float* Ci = sPosI + 6;
-        const float* Nj = sPosJ + p * (A * 3); const float* CAj = Nj + 3; const float* Cj = Nj + 6;
-        const float x = which == 0 ? dihedral4(Ci, Nj, CAj, Cj) : dihedral4(Ni, CAi, Ci, Nj);   // geometry.py:362-373
-        const float s = sKeep[p] ? 1.f : 0.f;                                                 // pair.py:92-94
-        float* dst = sAng + which * 13 * PE_LD + p;
-        if (half == 0) dst[0] = x * s;
-#pragma unroll
-        for (int f = 0; f < 3; ++f) {
-          const int ff = half * 3 + f;
-          float sn, cs;
-          sincosf(x * w.freq[ff], &sn, &cs);
-          dst[(1 + ff) * PE_LD] = sn * s;
-          dst[(7 + ff) * PE_LD] = cs * s;
-        }
-      }
-
-      // ---- distance Gaussians -> first distance layer, K walked in chunks of 75
-      float acc[4][4];
-      zero_acc(acc);
-      for (int e0 = 0; e0 < A2p; e0 += PE_KC) {
-        const int ne = min(PE_KC, A2p - e0);
-        {  // thread = (pair p, entry slot tid >> 6); entries e0 + slot, + 4, + 8, ...: independent chains; the atom indices
-           // (ia, ib) of entry e = ia * A + ib advance incrementally (one division per chunk, no table lookups in the loop)
-          const int p = tid & 63;
-          const float* xjb = sPosJ + p * (A * 3);
-          const float* cfp = sCoef + sAaJ[p] * A2 + e0;
-          const int bits_j = sBitsJ[p];
-          int ia = (e0 + (tid >> 6)) / A, ib = (e0 + (tid >> 6)) - ia * A;
-#pragma unroll 5
-          for (int el = tid >> 6; el < ne; el += 4) {
-            const float* xi = sPosI + ia * 3;                                             // ia <= 15 on padding entries: inside the 48 slots
-            const float* xj = xjb + ib * 3;
-            const float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
-            // (|x_ia - x_jb| / 10)^2 (angstrom_to_nm, then squared; pair.py:77-82)
-            const float d2 = (dx * dx + dy * dy + dz * dz) * 0.01f;
-            const bool on = (e0 + el < A2) && ((bits_i >> ia) & 1) && ((bits_j >> ib) & 1);   // entries >= A2 pad K to a multiple of 8
-            const float gv = expf(-cfp[el] * d2);                                         // evaluated on every lane: no divergent branch
-            sG[el * PE_LD + p] = on ? gv : 0.f;                                           // pair.py:82-84
-            ib += 4;
-            if (ib >= A) { ib -= A; ++ia; }
-            if (ib >= A) { ib -= A; ++ia; }                                               // A = 3: two wraps per step
-          }
-        }
-        __syncthreads();
-        tile_mma(acc, sG, sWd1 + e0 * 64, ne >> 3, p0, n0, g, t);
-        __syncthreads();
-      }
-      store_act(acc, sBias, sHB, p0, n0, g, t, nullptr);                                // h1
-      __syncthreads();
-      zero_acc(acc);
-      tile_mma(acc, sHB, sW64, 8, p0, n0, g, t);
-      store_act(acc, sBias + 64, sG, p0, n0, g, t, sKeep);                                    // h2 * structure pair mask (pair.py:85-87)
-      // table part of the first out_mlp layer: issued here so the gathers overlap the GEMM below
-      float tab[4][4];                                 // same coordinates as the accumulators
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int p = p0 + g + 8 * h;
-        const float* ta = w.Taa + ((size_t)(aa_i * PE_AA + sAaJ[p])) * 64;
-        const int rel = sRel[p];
-        const float* tr = w.Trel + (size_t)(rel < 0 ? 0 : rel) * 64;
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          const int ch = n0 + nt * 8 + 2 * t;
-          const float2 va = *reinterpret_cast<const float2*>(ta + ch);
-          float2 vr = *reinterpret_cast<const float2*>(tr + ch);
-          if (rel < 0) vr = make_float2(0.f, 0.f);
-          tab[nt][2 * h] = va.x + vr.x;
-          tab[nt][2 * h + 1] = va.y + vr.y;
-        }
-      }
-      __syncthreads();
-      zero_acc(acc);
-      tile_mma(acc, sG, sW64 + 4096, 8, p0, n0, g, t);
-      tile_mma(acc, sAng, sW1h, PE_ANGP / 8, p0, n0, g, t);
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] += tab[r][c];
-      store_act(acc, sBias + 128, sHB, p0, n0, g, t, nullptr);                                // o1 (sHB's readers passed the barrier above)
-      __syncthreads();
-      zero_acc(acc);
-      tile_mma(acc, sHB, sW64 + 2 * 4096, 8, p0, n0, g, t);
-      store_act(acc, sBias + 192, sG, p0, n0, g, t, nullptr);                                 // o2
-      __syncthreads();
-      // ---- last layer: (W3 o2 + b3) * has_CA pair mask, straight from the accumulators (each quad writes 32 contiguous bytes)
-      {
-        zero_acc(acc);
-        tile_mma(acc, sG, sW64 + 3 * 4096, 8, p0, n0, g, t);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int p = p0 + g + 8 * h, j = j0 + p;
-          if (j < L) {
-            const float s = sOk[p] ? 1.f : 0.f;                                          // pair.py:99
-            float* dst = a.out + ((size_t)row * L + j) * 64;
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-              const int ch = n0 + nt * 8 + 2 * t;
-              __stcs(reinterpret_cast<float2*>(dst + ch), make_float2((acc[nt][2 * h] + sBias[256 + ch]) * s, (acc[nt][2 * h + 1] + sBias[256 + ch + 1]) * s));
-            }
-          }
-        }
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------ tcgen05 version (round 2)
-// pair_embed_tc_kernel: the same computation on the 5th-gen tensor cores.  Tile = one query residue x 128 keys; the five dense
+// ------------------------------------------------------------------------------------------ the kernel
+// pair_embed_tc_kernel.  Tile = one query residue x 128 keys; the five dense
 // layers are 128 x 64 x K GEMMs as 3xTF32 tcgen05.mma in TS mode: the A operand (activations, tf32 hi | lo) lives in TENSOR MEMORY
 // and is written by the threads that produce it (thread = pair x half of the columns: tcgen05.st), the B operand (weights) comes
 // from shared memory as pre-swizzled K-major boxes [64 out][32 k] hi | lo packed at finalize(): distance_embed.2 and the three
@@ -736,7 +443,6 @@ struct abopt_pair_embed {
   void* wbase = nullptr;
   PairEmbedW w;
   int sm_count = 148;
-  size_t smem_bytes = 0;
 };
 
 #define PE_CUDA_TRY(expr)                                                                       \
@@ -763,16 +469,12 @@ extern "C" int abopt_pair_embed_create(int max_num_atoms, int device, abopt_pair
               {"distance_embed.2.weight", 64 * 64}, {"distance_embed.2.bias", 64},
               {"out_mlp.0.weight", (size_t)64 * (192 + PE_ANG)}, {"out_mlp.0.bias", 64},
               {"out_mlp.2.weight", 64 * 64}, {"out_mlp.2.bias", 64}, {"out_mlp.4.weight", 64 * 64}, {"out_mlp.4.bias", 64}};
-  pe->smem_bytes = (size_t)pe_smem_floats((int)A2) * sizeof(float);
   int cur = 0;
   cudaGetDevice(&cur);
   cudaSetDevice(device);
-  // the attribute is per function, not per handle: always opt in for the full-atom size (206 KB)
-  cudaError_t e = cudaFuncSetAttribute(pair_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(pe_smem_floats(PE_MAXA * PE_MAXA) * sizeof(float)));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(pair_embed_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(pair_embed_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM);
   cudaSetDevice(cur);
-  if (e != cudaSuccess) { delete pe; return api_fail(ABOPT_ERR_CUDA, std::string("pair_embed_kernel shared memory: ") + cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { delete pe; return api_fail(ABOPT_ERR_CUDA, std::string("pair_embed_tc_kernel shared memory: ") + cudaGetErrorString(e)); }
   *out = pe;
   return ABOPT_OK;
 }
@@ -818,11 +520,11 @@ extern "C" int abopt_pair_embed_finalize(abopt_pair_embed* pe) {
   const std::vector<float>& W1 = pe->sd["out_mlp.0.weight"];
   std::vector<float> img;
   auto reserve = [&](size_t n) { size_t off = (img.size() + 63) & ~size_t(63); img.resize(off + n, 0.f); return off; };
-  const size_t o_coef = reserve((size_t)NP * A2), o_taa = reserve((size_t)NP * 64), o_trel = reserve((size_t)NR * 64),
-               o_wd1 = reserve((size_t)((A2 + 7) & ~7) * 64), o_w64 = reserve(4 * 4096), o_w1h = reserve(PE_ANGP * 64), o_bias = reserve(5 * 64);
+  const size_t o_taa = reserve((size_t)NP * 64), o_trel = reserve((size_t)NR * 64), o_bias = reserve(5 * 64);
+  std::vector<float> coef((size_t)NP * A2);
   {  // F.softplus (beta 1, threshold 20), pair.py:81
     const std::vector<float>& c = pe->sd["aapair_to_distcoef.weight"];
-    for (size_t k = 0; k < c.size(); ++k) img[o_coef + k] = c[k] > 20.f ? c[k] : log1pf(expf(c[k]));
+    for (size_t k = 0; k < c.size(); ++k) coef[k] = c[k] > 20.f ? c[k] : log1pf(expf(c[k]));
   }
   auto premul = [&](const std::vector<float>& E, int rows, int col0, size_t off) {      // T[r][o] = sum_c E[r][c] W1[o][col0 + c]
     for (int r = 0; r < rows; ++r)
@@ -834,23 +536,13 @@ extern "C" int abopt_pair_embed_finalize(abopt_pair_embed* pe) {
   };
   premul(pe->sd["aa_pair_embed.weight"], NP, 0, o_taa);
   premul(pe->sd["relpos_embed.weight"], NR, 64, o_trel);
-  auto transpose = [&](const float* Wsrc, int ld, int col0, int K, size_t off) {        // dst[k][o ^ ((k & 3) << 3)] = W[o][col0 + k]; rows beyond K stay zero
-    for (int k = 0; k < K; ++k)
-      for (int o = 0; o < 64; ++o) img[off + (size_t)k * 64 + (o ^ ((k & 3) << 3))] = Wsrc[(size_t)o * ld + col0 + k];     // swizzled
-  };
-  transpose(pe->sd["distance_embed.0.weight"].data(), A2, 0, A2, o_wd1);
-  transpose(pe->sd["distance_embed.2.weight"].data(), 64, 0, 64, o_w64);
-  transpose(W1.data(), K1, 128, 64, o_w64 + 4096);
-  transpose(pe->sd["out_mlp.2.weight"].data(), 64, 0, 64, o_w64 + 2 * 4096);
-  transpose(pe->sd["out_mlp.4.weight"].data(), 64, 0, 64, o_w64 + 3 * 4096);
-  transpose(W1.data(), K1, 192, PE_ANG, o_w1h);
-  // ---- tcgen05 path: pre-swizzled K-major boxes, hi | lo planes
+  // ---- pre-swizzled K-major weight boxes, hi | lo planes
   const int kb1 = (pe->A + 1) / 2;                        // layer-1 K order: [key atom][query atom padded to 16], 2 key atoms per k-block
   const size_t o_box = reserve((size_t)(kb1 + 9) * 4096);
   const size_t o_coefT = reserve((size_t)NP * pe->A * 16);
   for (int r = 0; r < NP; ++r)
     for (int ib = 0; ib < pe->A; ++ib)
-      for (int ia = 0; ia < pe->A; ++ia) img[o_coefT + ((size_t)r * pe->A + ib) * 16 + ia] = img[o_coef + (size_t)r * A2 + ia * pe->A + ib];
+      for (int ia = 0; ia < pe->A; ++ia) img[o_coefT + ((size_t)r * pe->A + ib) * 16 + ia] = coef[(size_t)r * A2 + ia * pe->A + ib];
   auto pack_box = [&](size_t box, auto val) {             // val(k, n) for k in [0, 32), n in [0, 64)
     float* hi = &img[o_box + box * 4096];
     float* lo = hi + 2048;
@@ -900,8 +592,7 @@ extern "C" int abopt_pair_embed_finalize(abopt_pair_embed* pe) {
   if (e != cudaSuccess) return api_fail(ABOPT_ERR_CUDA, std::string("pair-embed weights: ") + cudaGetErrorString(e));
   const float* base = static_cast<const float*>(pe->wbase);
   pe->w.A = pe->A; pe->w.A2 = A2;
-  pe->w.coef = base + o_coef; pe->w.Taa = base + o_taa; pe->w.Trel = base + o_trel; pe->w.Wd1 = base + o_wd1;
-  pe->w.W64 = base + o_w64; pe->w.W1h = base + o_w1h; pe->w.bias = base + o_bias;
+  pe->w.Taa = base + o_taa; pe->w.Trel = base + o_trel; pe->w.bias = base + o_bias;
   pe->w.boxes = base + o_box; pe->w.kb1 = kb1; pe->w.coefT = base + o_coefT;
   memcpy(pe->w.freq, pe->sd["dihedral_embed.freq_bands"].data(), 6 * sizeof(float));
   pe->finalized = true;
@@ -927,12 +618,10 @@ extern "C" int abopt_pair_embed_forward(abopt_pair_embed* pe, int N, int L, int 
   cudaStream_t st = (cudaStream_t)stream;
   {
     ProfScope ps(KK_OTHER, st);
-    static const bool legacy = [] { const char* e = getenv("ABOPT_PAIR_EMBED_MMASYNC"); return e && e[0] == '1'; }();
-    if (legacy) pair_embed_kernel<<<grid, PE_THREADS, pe->smem_bytes, st>>>(pe->w, a);
-    else pair_embed_tc_kernel<<<grid, PT_THREADS, PT_SMEM, st>>>(pe->w, a);
+    pair_embed_tc_kernel<<<grid, PT_THREADS, PT_SMEM, st>>>(pe->w, a);
   }
   cudaError_t e = cudaGetLastError();
   if (cur != pe->device) cudaSetDevice(cur);
-  if (e != cudaSuccess) return api_fail(ABOPT_ERR_CUDA, std::string("pair_embed_kernel: ") + cudaGetErrorString(e));
+  if (e != cudaSuccess) return api_fail(ABOPT_ERR_CUDA, std::string("pair_embed_tc_kernel: ") + cudaGetErrorString(e));
   return ABOPT_OK;
 }

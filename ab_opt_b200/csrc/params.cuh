@@ -32,7 +32,7 @@ struct PairBiasParams {
   float coef[H];
 };
 
-// The same pair-bias weight packed as head PAIRS for the FFMA2 (fma.rn.f32x2) inner loop of pair_stream_kernel:
+// The same pair-bias weight packed as head PAIRS for the FFMA2 (fma.rn.f32x2) inner loop of pair_bias_kernel:
 // w[half][c][k] = (W_b[6 half + 2k][c], W_b[6 half + 2k + 1][c]); by-value kernel parameter -> constant bank ->
 // uniform registers (the head half is warp-uniform in the kernel).
 struct PairBiasPacked {
