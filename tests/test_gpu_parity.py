@@ -140,9 +140,11 @@ def test_transitions_against_reference_fixture(golden_dir, tstep):
 
 
 # ------------------------------------------------------------------------------------------ oracle, more shapes
-@pytest.mark.parametrize('N,L,ragged', [(2, 24, True), (3, 100, True), (1, 300, False), (2, 64, False), (1, 400, True), (1, 512, False)])
+@pytest.mark.parametrize('N,L,ragged', [(2, 24, True), (1, 37, True), (3, 100, True), (1, 300, False), (2, 64, False), (1, 400, True),
+                                        (1, 512, False)])
 def test_block_vs_oracle_shapes(N, L, ragged):
-    """Tile-edge cases: L not a multiple of 64 / 4-row tiles, L > 256 (two-CTA clusters splitting the keys: 5, 7 and 8 chunks per
+    """Tile-edge cases: L not a multiple of 64 / 32 / 8 (short last key chunk, odd number of live rows = a one-row last tile of
+    pair_stream_kernel), L > 256 (two-CTA clusters splitting the keys: 5, 7 and 8 chunks per
     half up to the maximum length 512), ragged masks."""
     W = weights.make_state_dict(seed=5, num_layers=1, flavour='abdesign')
     model = build_model(W, 1, flavour='abdesign')
