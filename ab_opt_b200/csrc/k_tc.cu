@@ -310,15 +310,18 @@ proj_ts_kernel(const float* __restrict__ xg, const __grid_constant__ CUtensorMap
           mbar_wait(&b_full[s], (g / PP_ST) & 1);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t b_hi = smem_u32(smem + s * PP_STAGE), b_lo = b_hi + PP_B_BYTES;
+            const uint32_t b_hi = smem_u32(smem + s * PP_STAGE);      // W_lo box at + PP_B_BYTES
             const uint32_t d_main = tmem_base + PP_TM_ACC + buf * 128, d_small = d_main + 64;
 #pragma unroll
             for (int k = 0; k < G_BK / 8; ++k) {
               const uint32_t ah = tmem_base + PP_TM_A + kb * G_BK + k * 8, al = ah + F;
-              const uint64_t dbh = smem_desc_sw128(b_hi + k * 32), dbl = smem_desc_sw128(b_lo + k * 32);
+              const uint64_t dbh = smem_desc_sw128(b_hi + k * 32);
               const uint32_t acc = (kb == 0 && k == 0) ? 0u : 1u;
-              mma_tf32_ts(d_main, ah, dbh, idesc, acc);
-              mma_tf32_ts(d_small, ah, dbl, idesc, acc);
+              // x_hi . [W_hi | W_lo] -> [main | corrections] as ONE 128-wide instruction: the lo box follows the hi box in the stage
+              // (64 + 64 rows) and the corrections accumulator follows the main one in TMEM.  A 128 x 64 x 8 instruction costs ~45 clk,
+              // a 128 x 128 x 8 one ~77, and this kernel is bound by MMA issue: 60.0 -> 56.3 us per launch.  (48-wide tiles compute 16
+              // columns nobody reads.)
+              mma_tf32_ts(d_main, ah, dbh, idesc_tf32(G_BM, 128), acc);
               mma_tf32_ts(d_small, al, dbh, idesc, 1u);
             }
             mma_commit(&b_empty[s]);
