@@ -590,8 +590,8 @@ def run_pair_embed(args):
                       'clocks': ck, 'gpu_launches': steps,
                       'roofline': {'bound': 'hbm', 'achieved': alg / (ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
                                    'frac': alg / (ms * 1e-3) / 1e9 / peak, 'peak_source': peak_src, 'traffic': None,
-                                   'traffic_note': 'ncu: 1.02 GB written, 5 MB read per launch (profiles/r01_ncu_pair_embed_summary.json)',
-                                   'note': 'not HBM bound: 65 kflop per pair (x3 as 3xTF32 on mma.sync) and one exp per atom pair against 256 B written',
+                                   'traffic_note': 'ncu: 1.02 GB written, 5 MB read per launch (profiles/r02_final_ncu_pair_embed_summary.json)',
+                                   'note': 'not HBM bound: 65 kflop per pair (x3 as 3xTF32 on tcgen05, activations in tensor memory) and one exp per atom pair against 256 B written',
                                    'fp32_equivalent_tflops': flops / (ms * 1e-3) / 1e12},
                       'cpu_baseline': cpu}), flush=True)
 
