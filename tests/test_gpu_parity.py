@@ -177,6 +177,37 @@ def test_block_vs_oracle_shapes(N, L, ragged):
         assert a[~mr].abs().max() == 0 and a.transpose(1, 2)[~mr].abs().max() == 0
 
 
+def test_chunked_attention_passes_equal_whole_batch():
+    """When the attention weights of a batch exceed the 2 GiB cap of the alpha buffer, run_block walks the batch in chunks of
+    complexes (api.cu: chunk_size; ABOPT_CHUNK forces a chunk size).  Every kernel's tiles are per complex, so a chunked pass
+    gives the same bits as the whole-batch pass -- including an uneven last chunk (5 complexes in chunks of 2)."""
+    W = weights.make_state_dict(seed=11, num_layers=2, flavour='abdesign')
+    inp = weights.synthetic_inputs(77, 5, 40, gen_slices=((3, 9),), ragged=True)
+    R, t = G.so3_exp(inp['v']).to(DEV), (inp['p'] / 10.0).to(DEV)
+    ci = cu(inp)
+    outs = []
+    old = os.environ.get('ABOPT_CHUNK')
+    try:
+        for chunk in (None, '2'):
+            if chunk is None:
+                os.environ.pop('ABOPT_CHUNK', None)
+            else:
+                os.environ['ABOPT_CHUNK'] = chunk
+            model = build_model(W, 2, flavour='abdesign')      # a fresh model = a fresh workspace: the chunk size is fixed when it is allocated
+            enc = model.eps_net.encoder
+            alpha, feat = enc.block_taps(0, R, t, ci['res_feat'], ci['pair_feat'], ci['mask_res'])
+            outs.append((alpha.cpu(), feat.cpu(), enc(R, t, ci['res_feat'], ci['pair_feat'], ci['mask_res']).cpu()))
+    finally:
+        if old is None:
+            os.environ.pop('ABOPT_CHUNK', None)
+        else:
+            os.environ['ABOPT_CHUNK'] = old
+    mr = inp['mask_res']
+    assert torch.equal(outs[0][0], outs[1][0]), 'alpha differs between the whole-batch and the chunked pass'
+    assert torch.equal(outs[0][1][mr], outs[1][1][mr]), 'aggregates differ'
+    assert torch.equal(outs[0][2], outs[1][2]), 'encoder output differs'
+
+
 @pytest.mark.parametrize('flavour', ['abdock', 'abdesign'])
 def test_eps_net_vs_oracle(flavour):
     W = weights.make_state_dict(seed=7, num_layers=3, flavour=flavour)
