@@ -291,18 +291,20 @@ void bwd_aggregate(int M, const float* gfeat, const float* feat, const float* R,
 }
 
 // ------------------------------------------------------------------------------------------ pairwise backward, query side
-// One CTA per query row (b, i).  Shared memory: the row block z[b,i,:,:] (L x 64), alpha and d logits of the row (L x 12 each)
+// One CTA per query row (b, i), two CTAs per SM.  Shared memory: the row block z[b,i,:,:] (L x 64), alpha and d logits of the row (L x 12 each)
 // and the row's vectors.  Phases (threads over keys j unless noted):
 //   1  d alpha[j][h] = g_p2n[h] . z[j] + g_node[h] . v[j,h] + g_agg[h] . vg[j,h]                     (ga.py:114-136 backward)
 //      dot[h] = sum_j alpha d alpha
 //   2  d logit[j][h] = alpha (d alpha - dot[h]) sqrt(1/3)  -> global (alpha layout), kept in smem    (softmax, ga.py:11-26,166)
-//      d2[j][h] = |qg_i - kg_j|^2 for d spatial_coef
+//      partial d coef[h] = sum_j dl |qg_i - kg_j|^2 (per thread, block-reduced)
 //   3  threads over outputs: d q[h][d] = sum_j dl k[j,h,d] / sqrt(32);  d qg[h][pc] = 2 c_h (qg_i sum_j dl - sum_j dl kg_j), rotated
-//      to the local frame of residue i;  partial d W_b[h][c] = sum_j dl z[j][c];  partial d coef[h] = sum_j dl d2
+//      to the local frame of residue i;  partial d W_b[h][c] = sum_j dl z[j][c]
 //   4  threads over (j, c):  d z[j][c] (+)= sum_h alpha g_p2n[h][c] + sum_h dl W_b[h][c]
 constexpr int PBQ_THREADS = 256;
 constexpr int PBQ_HP = H + 1;            // row pitch of the per-key [12] arrays in shared memory (13: conflict-free over keys)
-static size_t pbq_smem(int L) { return ((size_t)L * C + 3 * (((size_t)L * PBQ_HP + 3) & ~size_t(3)) + 2 * H * C + H * D + 2 * H * P * 3 + 8 * H + 2 * H + 16) * sizeof(float); }
+// (two [L][13] arrays, not three: with the per-key |qg - kg|^2 kept as well, the 116 KB of a 256-residue row were 576 bytes too many
+// for two CTAs per SM, and this kernel lives on latency hiding: 8 -> 16 warps per SM)
+static size_t pbq_smem(int L) { return ((size_t)L * C + 2 * (((size_t)L * PBQ_HP + 3) & ~size_t(3)) + 2 * H * C + H * D + 2 * H * P * 3 + 8 * H + 2 * H + 16) * sizeof(float); }
 
 __global__ void __launch_bounds__(PBQ_THREADS) pair_bwd_query_kernel(const PairBwdArgs a) {
   extern __shared__ __align__(16) float sm[];
@@ -311,8 +313,7 @@ __global__ void __launch_bounds__(PBQ_THREADS) pair_bwd_query_kernel(const PairB
   const size_t LH = ((size_t)L * PBQ_HP + 3) & ~size_t(3);      // keeps the float4-accessed arrays behind 16-byte aligned
   float* al = zs + (size_t)L * C;              // [L][13]
   float* dl = al + LH;                         // [L][13]  d alpha, then d logits
-  float* d2s = dl + LH;                        // [L][13]
-  float* gp2n = d2s + LH;                      // [12][64]
+  float* gp2n = dl + LH;                       // [12][64]
   float* wb = gp2n + H * C;                    // [12][64]
   float* gnode = wb + H * C;                   // [12][32]
   float* gagg = gnode + H * D;                 // [12][24]  (phase 3: d query points, global frame)
@@ -374,7 +375,10 @@ __global__ void __launch_bounds__(PBQ_THREADS) pair_bwd_query_kernel(const PairB
     dot[tid] = s;
   }
   __syncthreads();
-  // ---- phase 2: d logits (softmax backward), |qg_i - kg_j|^2
+  // ---- phase 2: d logits (softmax backward); partial d coef[h] = sum_j d logit |qg_i - kg_j|^2 (per thread, reduced below)
+  float dcp[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) dcp[h] = 0.f;
   for (int j = tid; j < Lp; j += PBQ_THREADS) {
     if (j >= L) {
 #pragma unroll
@@ -393,19 +397,27 @@ __global__ void __launch_bounds__(PBQ_THREADS) pair_bwd_query_kernel(const PairB
         const float e0 = qgi[h * 24 + c] - k4.x, e1 = qgi[h * 24 + c + 1] - k4.y, e2 = qgi[h * 24 + c + 2] - k4.z, e3 = qgi[h * 24 + c + 3] - k4.w;
         dd += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
       }
-      d2s[j * PBQ_HP + h] = dd;
+      dcp[h] = fmaf(g, dd, dcp[h]);
     }
+  }
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    const float v = wsum(dcp[h]);
+    if (lane == 0) red[warp * H + h] = v;                // (red was last read for dot[], two barriers ago)
   }
   __syncthreads();
   if (tid < H) {
     float s = 0.f;
     for (int j = 0; j < L; ++j) s += dl[j * PBQ_HP + tid];
     sdl[tid] = s;
+    float c = 0.f;
+    for (int w = 0; w < PBQ_THREADS / 32; ++w) c += red[w * H + tid];
+    a.part[(size_t)row * 780 + 768 + tid] = c;
   }
   __syncthreads();
   // ---- phase 3: contractions over the keys, threads over outputs
   float* Grow = a.G + (size_t)row * NPROJ;
-  for (int o = tid; o < H * D + H * P * 3 + H * C + H; o += PBQ_THREADS) {
+  for (int o = tid; o < H * D + H * P * 3 + H * C; o += PBQ_THREADS) {
     if (o < H * D) {                                   // d q[h][d] = sum_j dl k[j,h,d] / sqrt(32)
       const int h = o / D;
       const float* kcol = a.Pm + (size_t)b * L * NPROJ + OFF_K + o;
@@ -418,16 +430,11 @@ __global__ void __launch_bounds__(PBQ_THREADS) pair_bwd_query_kernel(const PairB
       float s = 0.f;
       for (int j = 0; j < L; ++j) s = fmaf(dl[j * PBQ_HP + h], kgcol[(size_t)j * 864], s);
       gagg[e] = 2.f * a.coef[h] * (qgi[e] * sdl[h] - s);
-    } else if (o < H * D + H * P * 3 + H * C) {        // partial d W_b[h][c] = sum_j dl z[j][c]
+    } else {                                           // partial d W_b[h][c] = sum_j dl z[j][c]
       const int e = o - H * D - H * P * 3, h = e / C, c = e - h * C;
       float s = 0.f;
       for (int j = 0; j < L; ++j) s = fmaf(dl[j * PBQ_HP + h], zs[(size_t)j * C + c], s);
       a.part[(size_t)row * 780 + e] = s;
-    } else {                                           // partial d coef[h] = sum_j dl |qg_i - kg_j|^2
-      const int h = o - H * D - H * P * 3 - H * C;
-      float s = 0.f;
-      for (int j = 0; j < L; ++j) s = fmaf(dl[j * PBQ_HP + h], d2s[j * PBQ_HP + h], s);
-      a.part[(size_t)row * 780 + 768 + h] = s;
     }
   }
   __syncthreads();
