@@ -1319,10 +1319,15 @@ static int block_backward(abopt_model* m, TrainWS& T, int l, int N, int L, const
   if (w.NB < N) return fail(ABOPT_ERR_ARG, "backward: the batch does not fit one attention pass (alpha > 2 GiB)");
   // ---- recompute: alpha and the aggregate by the forward kernels, the plain projections, the tail's activations
   int rc = run_block(m, l, N, L, R, t, x, nullptr, z, mask, nullptr, nullptr, nullptr, st); if (rc) return rc;
-  bwd_gemm_nt(M, NPROJ, F, x, F, false, bw.Wcat, F, nullptr, T.Pm, NPROJ, st);
+  // (the two big recompute GEMMs on the tensor cores, 3xTF32 like the forward: x's lo plane is w.xin_lo since run_block; the lo
+  // plane of the aggregate goes through T.gfeat, which is not written before the tail backward below)
+  if (!launch_gemm3x_plain(M, NPROJ, F, x, w.xin_lo, F, bw.Wcat, bw.Wcat_lo, F, T.Pm, NPROJ, nullptr, st))
+    return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (backward: projections)");
   bwd_points_global(M, T.Pm, R, t, T.PG, st);
   const float *W1 = bw.Wmlp, *W2 = bw.Wmlp + F * F, *W3 = bw.Wmlp + 2 * F * F;
-  bwd_gemm_nt(M, F, NFEAT, w.feat, NFEAT, false, bw.Wout, NFEAT, bw.bout, T.t1, F, st);                 // y = out_transform(feat)
+  launch_lo(w.feat, T.gfeat, (size_t)M * NFEAT, st);
+  if (!launch_gemm3x_plain(M, F, NFEAT, w.feat, T.gfeat, NFEAT, bw.Wout, bw.Wout_lo, NFEAT, T.t1, F, bw.bout, st))      // y = out_transform(feat)
+    return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (backward: out_transform)");
   bwd_add_ln_fwd(M, x, T.t1, mask, bw.ln1_g, bw.ln1_b, T.s1, T.h, st);                                  // s1 = x + mask y ; h = LN1
   bwd_gemm_nt(M, F, F, T.h, F, false, W1, F, bw.b1, T.a0, F, st);
   bwd_gemm_nt(M, F, F, T.a0, F, true, W2, F, bw.b2, T.a1, F, st);
