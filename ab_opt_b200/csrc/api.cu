@@ -1352,7 +1352,14 @@ static int block_backward(abopt_model* m, TrainWS& T, int l, int N, int L, const
   bwd_colsum(M, F, T.t1, F, nullptr, 0, grad_of(m, p + "layer_norm_1.gamma"), T.scr, st, 1.f);
   bwd_colsum(M, F, T.a1, F, nullptr, 0, grad_of(m, p + "layer_norm_1.beta"), T.scr, st, 1.f);
   bwd_add_mask(M, F, gx, nullptr, mask, T.t2, st);                                                      // t2 = g_s1 * mask
-  bwd_gemm_nn(M, F, NFEAT, T.t2, F, bw.Wout, NFEAT, T.gfeat, NFEAT, false, st);
+  {
+    // d feat = g_y W_out on the tensor cores: A = g_y (lo plane in the scratch block), B = W_out^T [1824][128] hi | lo
+    float* a_lo = T.scr; float* wt_h = a_lo + (size_t)M * F; float* wt_l = wt_h + (size_t)F * NFEAT;
+    launch_lo(T.t2, a_lo, (size_t)M * F, st);
+    launch_transpose_split(bw.Wout, F, NFEAT, wt_h, wt_l, st);
+    if (!launch_gemm3x_plain(M, NFEAT, F, T.t2, a_lo, F, wt_h, wt_l, F, T.gfeat, NFEAT, nullptr, st))
+      return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (backward: d feat)");
+  }
   bwd_wgrad(M, F, NFEAT, T.t2, F, w.feat, NFEAT, false, grad_of(m, p + "out_transform.weight"), T.scr, T.scr_floats, st);
   bwd_colsum(M, F, T.t2, F, nullptr, 0, grad_of(m, p + "out_transform.bias"), T.scr, st, 1.f);
   // ---- aggregate, softmax, logits (ga.py:81-147)
@@ -1366,7 +1373,16 @@ static int block_backward(abopt_model* m, TrainWS& T, int l, int N, int L, const
   CUDA_TRY(cudaMemcpyAsync(grad_of(m, p + "proj_pair_bias.weight"), T.tmp, H * C * 4, cudaMemcpyDeviceToDevice, st));
   coef_grad_kernel<<<1, 32, 0, st>>>(T.tmp + 768, bw.sc_raw, grad_of(m, p + "spatial_coef"));
   // ---- projections (ga.py:82-83,96-105,122,129-132)
-  bwd_gemm_nn(M, NPROJ, F, T.G, NPROJ, bw.Wcat, F, gx, F, true, st);
+  {
+    // d x += G W_cat on the tensor cores: A = G (its lo plane goes where the plain projections were: they are dead after the pair
+    // backward), B = W_cat^T [128][2016] hi | lo; the product lands in T.t1 and is added to gx
+    float* wt_h = T.scr; float* wt_l = wt_h + (size_t)NPROJ * F;
+    launch_lo(T.G, T.Pm, (size_t)M * NPROJ, st);
+    launch_transpose_split(bw.Wcat, NPROJ, F, wt_h, wt_l, st);
+    if (!launch_gemm3x_plain(M, F, NPROJ, T.G, T.Pm, NPROJ, wt_h, wt_l, NPROJ, T.t1, F, nullptr, st))
+      return fail(ABOPT_ERR_CUDA, "cuTensorMapEncodeTiled failed (backward: d x)");
+    bwd_add_mask(M, F, gx, T.t1, nullptr, gx, st);
+  }
   bwd_wgrad(M, NPROJ, F, T.G, NPROJ, x, F, false, grad_of(m, p + "proj_query.weight"), T.scr, T.scr_floats, st);
   CHECK_LAUNCH();
   return ABOPT_OK;

@@ -210,8 +210,8 @@ __global__ void relu_bwd_kernel(size_t n, float* __restrict__ g, const float* __
   if (i < n && !(a[i] > 0.f)) g[i] = 0.f;
 }
 // out = a (+ b), rows masked to zero where mask == 0 (mask may be null)
-__global__ void add_mask_kernel(int M, int K, const float* __restrict__ a, const float* __restrict__ b, const uint8_t* __restrict__ mask,
-                                float* __restrict__ out) {
+__global__ void add_mask_kernel(int M, int K, const float* a, const float* __restrict__ b, const uint8_t* __restrict__ mask,
+                                float* out) {      // (out may be a: in-place accumulation)
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= (size_t)M * K) return;
   const int r = (int)(i / K);

@@ -630,6 +630,20 @@ void launch_split(const float* in, float* hi, float* lo, size_t n, cudaStream_t 
   split_kernel<<<grid, 256, 0, st>>>(in, hi, lo, n);
 }
 
+// Th[c][r] = W[r][c] (raw fp32 = the tf32 "hi" plane), Tl = its lo plane: a weight as the K-major B operand of an input-gradient GEMM
+__global__ void transpose_split_kernel(const float* __restrict__ W, int R, int Cc, float* __restrict__ Th, float* __restrict__ Tl) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= (size_t)R * Cc) return;
+  const int r = (int)(idx / Cc), c = (int)(idx - (size_t)r * Cc);
+  const float v = W[idx];
+  Th[(size_t)c * R + r] = v;
+  Tl[(size_t)c * R + r] = tf32_lo(v);
+}
+void launch_transpose_split(const float* W, int R, int Cc, float* Th, float* Tl, cudaStream_t st) {
+  ProfScope prof__(KK_OTHER, st);
+  transpose_split_kernel<<<(unsigned)(((size_t)R * Cc + 255) / 256), 256, 0, st>>>(W, R, Cc, Th, Tl);
+}
+
 // D[M][N] = A * B^T (+bias), operands given as hi / lo planes.  K % 32 == 0, N % 4 == 0.
 bool launch_gemm3x_plain(int M, int N, int K, const float* Ah, const float* Al, int lda, const float* Bh, const float* Bl, int ldb,
                          float* D, int ldd, const float* bias, cudaStream_t st) {

@@ -57,6 +57,7 @@ cudaError_t attn_kernels_init();
 cudaError_t tc_init();
 void launch_split(const float* in, float* hi, float* lo, size_t n, cudaStream_t st);
 void launch_lo(const float* in, float* lo, size_t n, cudaStream_t st);
+void launch_transpose_split(const float* W, int R, int Cc, float* Th, float* Tl, cudaStream_t st);
 bool launch_gemm3x_plain(int M, int N, int K, const float* Ah, const float* Al, int lda, const float* Bh, const float* Bl, int ldb,
                          float* D, int ldd, const float* bias, cudaStream_t st);
 
