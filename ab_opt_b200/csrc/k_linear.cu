@@ -1,6 +1,7 @@
 // Small node-feature layers of the hot path on CUDA cores (FP32 FFMA, cp.async pipelined); the big GEMMs are in k_tc.cu.
 //   mixer_kernel  : EpsilonNet input mixer + R = exp(v_t)           dpm_full.py:86-89
 //   heads_kernel  : eps_crd / eps_rot / eps_seq / pRMSD heads + SO(3) update    dpm_full.py:92-110
+#include <cstdlib>
 #include "rowtile.cuh"
 #include "params.cuh"
 #include "kernels.h"
@@ -11,6 +12,8 @@ namespace abopt {
 // rows / count (optional, inside the sampling loop): only the listed rows are evaluated -- everything the mixer reads of a context
 // residue is a loop invariant there (res_feat, its sequence, its frame), so after the first step only the generated rows change.
 // Results go to their place in x_out / x_lo_out / Rbuf / p_norm and, compact (row k of the list), to x_c / x_c_lo.
+// R = rows per warp (rowtile.cuh): a CTA evaluates 8R rows.
+template <int R>
 __global__ void __launch_bounds__(RT_THREADS, 2)
 mixer_kernel(int M, const float* __restrict__ res_feat, const long long* __restrict__ s_t,
              const float* __restrict__ v_t, EpsW w, float* __restrict__ x_out, float* __restrict__ Rbuf,
@@ -19,13 +22,14 @@ mixer_kernel(int M, const float* __restrict__ res_feat, const long long* __restr
              float* __restrict__ x_c, float* __restrict__ x_c_lo) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RowTileSmem& s = *reinterpret_cast<RowTileSmem*>(smem_raw);
-  float* act = reinterpret_cast<float*>(smem_raw + sizeof(RowTileSmem));      // [64][RT_ACT_LD]
-  __shared__ int aa[RT_ROWS];
-  __shared__ int ridx[RT_ROWS];         // residue row of tile row r, -1 = none
-  const int row0 = blockIdx.x * RT_ROWS;
+  constexpr int ROWS = 8 * R;
+  float* act = reinterpret_cast<float*>(smem_raw + sizeof(RowTileSmem));      // [ROWS][RT_ACT_LD]
+  __shared__ int aa[ROWS];
+  __shared__ int ridx[ROWS];            // residue row of tile row r, -1 = none
+  const int row0 = blockIdx.x * ROWS;
   const int nrows = rows ? count[0] : M;
   if (row0 >= nrows) return;
-  if (threadIdx.x < RT_ROWS) {
+  if (threadIdx.x < ROWS) {
     const int k = row0 + threadIdx.x;
     const int r = (k < nrows) ? (rows ? rows[k] : k) : -1;
     ridx[threadIdx.x] = r;
@@ -43,7 +47,7 @@ mixer_kernel(int M, const float* __restrict__ res_feat, const long long* __restr
     }
   }
   __syncthreads();
-  float acc[8][4];
+  float acc[R][4];
   rt_zero(acc);
   // layer 0: [res_feat | embedding(s_t)] (K = 256) -> 128, ReLU
   rt_gemm_globalA(acc, s, [&](int r, int k) -> const float* {
@@ -59,15 +63,15 @@ mixer_kernel(int M, const float* __restrict__ res_feat, const long long* __restr
   rt_add_bias(acc, w.bm2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int row = ridx[warp * 8 + r];
+  for (int r = 0; r < R; ++r) {
+    const int row = ridx[warp * R + r];
     if (row >= 0) {
       const float4 hi = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
       const float4 lo = make_float4(tf32_lo(acc[r][0]), tf32_lo(acc[r][1]), tf32_lo(acc[r][2]), tf32_lo(acc[r][3]));
       *reinterpret_cast<float4*>(x_out + (size_t)row * F + lane * 4) = hi;
       if (x_lo_out != nullptr) *reinterpret_cast<float4*>(x_lo_out + (size_t)row * F + lane * 4) = lo;
       if (x_c != nullptr) {
-        const size_t kc = (size_t)(row0 + warp * 8 + r) * F + lane * 4;
+        const size_t kc = (size_t)(row0 + warp * R + r) * F + lane * 4;
         *reinterpret_cast<float4*>(x_c + kc) = hi;
         *reinterpret_cast<float4*>(x_c_lo + kc) = lo;
       }
@@ -78,10 +82,11 @@ mixer_kernel(int M, const float* __restrict__ res_feat, const long long* __restr
 // ------------------------------------------------------------------------------------------ heads
 constexpr int HD_OUT_LD = 68;      // staged head outputs per row: crd 0-2 | rot 3-5 | seq 6-25 | prmsd 26-65
 
-// One 3-layer head over the 64-row tile.  `in_act` holds the 128 node features; the 3 time-embedding
+// One 3-layer head over the 8R-row tile.  `in_act` holds the 128 node features; the 3 time-embedding
 // inputs enter as a per-row rank-3 correction `ext[r][q]` (q = 0..2) times W0_ext.
-__device__ __forceinline__ void run_head(float (&acc)[8][4], RowTileSmem& s, const float* in_act, float* hid,
-                                         const HeadW& hw, const float (&ext)[8][3]) {
+template <int R>
+__device__ __forceinline__ void run_head(float (&acc)[R][4], RowTileSmem& s, const float* in_act, float* hid,
+                                         const HeadW& hw, const float (&ext)[R][3]) {
   const int lane = threadIdx.x & 31;
   rt_zero(acc);
   rt_gemm_smemA(acc, s, in_act, RT_ACT_LD, hw.W0_t, F);
@@ -90,7 +95,7 @@ __device__ __forceinline__ void run_head(float (&acc)[8][4], RowTileSmem& s, con
   for (int q = 0; q < 3; ++q) {
     const float4 we = *reinterpret_cast<const float4*>(hw.W0_ext + q * F + lane * 4);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = 0; r < R; ++r) {
       acc[r][0] = fmaf(ext[r][q], we.x, acc[r][0]); acc[r][1] = fmaf(ext[r][q], we.y, acc[r][1]);
       acc[r][2] = fmaf(ext[r][q], we.z, acc[r][2]); acc[r][3] = fmaf(ext[r][q], we.w, acc[r][3]);
     }
@@ -112,17 +117,19 @@ __device__ __forceinline__ void run_head(float (&acc)[8][4], RowTileSmem& s, con
 }
 
 // copy output columns [0, n) of the tile into the staging buffer at column offset `off`
-__device__ __forceinline__ void stage_out(const float (&acc)[8][4], float* outs, int off, int n) {
+template <int R>
+__device__ __forceinline__ void stage_out(const float (&acc)[R][4], float* outs, int off, int n) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const int col = lane * 4 + c;
     if (col < n)
 #pragma unroll
-      for (int r = 0; r < 8; ++r) outs[(warp * 8 + r) * HD_OUT_LD + off + col] = acc[r][c];
+      for (int r = 0; r < R; ++r) outs[(warp * R + r) * HD_OUT_LD + off + col] = acc[r][c];
   }
 }
 
+template <int R>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 heads_kernel(int M, int L, const float* __restrict__ x, const float* __restrict__ beta, int beta_stride,
              const float* __restrict__ Rbuf, const float* __restrict__ v_t, const uint8_t* __restrict__ mask_gen,
@@ -132,20 +139,21 @@ heads_kernel(int M, int L, const float* __restrict__ x, const float* __restrict_
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // focus mode: only the `count[0]` rows listed in rows[] are evaluated.  x is either compact (x_compact: row k of x is
   // residue rows[k], the output of a focused last block) or the full tensor; every other tensor is indexed by residue row.
+  constexpr int ROWS = 8 * R;
   if (count) { const int g = count[0]; M = g < M ? g : M; }
-  if ((int)blockIdx.x * RT_ROWS >= M) return;
+  if ((int)blockIdx.x * ROWS >= M) return;
   RowTileSmem& s = *reinterpret_cast<RowTileSmem*>(smem_raw);
-  float* xin = reinterpret_cast<float*>(smem_raw + sizeof(RowTileSmem));      // [64][RT_ACT_LD]
-  float* hid = xin + RT_ROWS * RT_ACT_LD;                                     // [64][RT_ACT_LD]
-  float* outs = hid + RT_ROWS * RT_ACT_LD;                                    // [64][HD_OUT_LD]
-  const int row0 = blockIdx.x * RT_ROWS;
+  float* xin = reinterpret_cast<float*>(smem_raw + sizeof(RowTileSmem));      // [ROWS][RT_ACT_LD]
+  float* hid = xin + ROWS * RT_ACT_LD;                                        // [ROWS][RT_ACT_LD]
+  float* outs = hid + ROWS * RT_ACT_LD;                                       // [ROWS][HD_OUT_LD]
+  const int row0 = blockIdx.x * ROWS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // resident input tile + per-row time embedding (dpm_full.py:92-93)
-  float ext[8][3];
+  float ext[R][3];
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int row = row0 + warp * 8 + r;
+  for (int r = 0; r < R; ++r) {
+    const int row = row0 + warp * R + r;
     float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
     float b = 0.f;
     if (row < M) {
@@ -153,7 +161,7 @@ heads_kernel(int M, int L, const float* __restrict__ x, const float* __restrict_
       xv = *reinterpret_cast<const float4*>(x + (size_t)(x_compact ? row : rr) * F + lane * 4);
       b = beta[(size_t)(rr / L) * beta_stride];
     }
-    *reinterpret_cast<float4*>(xin + (warp * 8 + r) * RT_ACT_LD + lane * 4) = xv;
+    *reinterpret_cast<float4*>(xin + (warp * R + r) * RT_ACT_LD + lane * 4) = xv;
     ext[r][0] = b; ext[r][1] = sinf(b); ext[r][2] = cosf(b);
   }
   __syncthreads();
@@ -162,18 +170,18 @@ heads_kernel(int M, int L, const float* __restrict__ x, const float* __restrict_
   // per-residue epilogues, so they run as separate CTAs (4x the parallelism of one CTA walking all heads; in focus mode
   // only a few row tiles exist)
   const int head = head_lo + blockIdx.y;
-  float acc[8][4];
+  float acc[R][4];
   if (head == 0) { run_head(acc, s, xin, hid, w.crd, ext); stage_out(acc, outs, 0, 3); }
   else if (head == 1) { run_head(acc, s, xin, hid, w.rot, ext); stage_out(acc, outs, 3, 3); }
   else if (head == 2) { run_head(acc, s, xin, hid, w.seq, ext); stage_out(acc, outs, 6, NAA); }
   else {
     // PerResiduePredictor (common/nn.py:164-188): LayerNorm over the 131 inputs, then 3 linears.
-    float g[8][4], gext[8][3];
+    float g[R][4], gext[R][3];
     const float4 lg = *reinterpret_cast<const float4*>(w.prm_ln_g + lane * 4);
     const float4 lb = *reinterpret_cast<const float4*>(w.prm_ln_b + lane * 4);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const float4 xv = *reinterpret_cast<const float4*>(xin + (warp * 8 + r) * RT_ACT_LD + lane * 4);
+    for (int r = 0; r < R; ++r) {
+      const float4 xv = *reinterpret_cast<const float4*>(xin + (warp * R + r) * RT_ACT_LD + lane * 4);
       const float sum = warp_sum(xv.x + xv.y + xv.z + xv.w) + (ext[r][0] + ext[r][1] + ext[r][2]);
       const float mean = sum * (1.f / 131.f);
       const float d0 = xv.x - mean, d1 = xv.y - mean, d2 = xv.z - mean, d3 = xv.w - mean;
@@ -195,7 +203,7 @@ heads_kernel(int M, int L, const float* __restrict__ x, const float* __restrict_
   __syncthreads();
 
   // per-residue epilogue of this head
-  if (threadIdx.x < RT_ROWS) {
+  if (threadIdx.x < ROWS) {
     const int krow = row0 + threadIdx.x;
     if (krow < M) {
       const int row = rows ? rows[krow] : krow;
@@ -313,41 +321,81 @@ void launch_focus_gather(const int* rows, const int* count, const float* x, cons
 }
 
 // ------------------------------------------------------------------------------------------ launchers
-size_t mixer_smem() { return sizeof(RowTileSmem) + RT_ROWS * RT_ACT_LD * sizeof(float); }
-size_t heads_smem() { return sizeof(RowTileSmem) + (2 * RT_ROWS * RT_ACT_LD + RT_ROWS * HD_OUT_LD) * sizeof(float); }
+// Rows per warp (R) of the two row-tile kernels.  Whole-batch launches use R = 8 (64-row tiles, the best FMA : shared-memory
+// ratio).  The launches of the sampling loop that walk a row list (the generated residues: 1 024 rows at C2) are bound by the
+// latency of ONE tile, not by throughput -- 16 tiles of 64 rows leave 132 SMs idle -- so they use smaller tiles on more SMs.
+// The results do not depend on R (rowtile.cuh).  ABOPT_RPW_MIXER / ABOPT_RPW_HEADS (2, 4 or 8; read per call) override the
+// list-launch defaults for A/B measurements.
+constexpr int MIXER_LIST_RPW = 8, HEADS_LIST_RPW = 8;
 
+static int list_rpw(const char* env_name, int dflt) {
+  const char* e = getenv(env_name);
+  if (e == nullptr || e[0] == '\0') return dflt;
+  const int v = atoi(e);
+  return (v == 2 || v == 4 || v == 8) ? v : dflt;
+}
+
+template <int R> static size_t mixer_smem() { return sizeof(RowTileSmem) + 8 * R * RT_ACT_LD * sizeof(float); }
+template <int R> static size_t heads_smem() { return sizeof(RowTileSmem) + (2 * 8 * R * RT_ACT_LD + 8 * R * HD_OUT_LD) * sizeof(float); }
+
+template <int R> static cudaError_t linear_init_r() {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(mixer_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mixer_smem<R>())) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(heads_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_smem<R>())) != cudaSuccess) return e;
+  return cudaSuccess;
+}
 cudaError_t linear_kernels_init() {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(mixer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mixer_smem())) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_smem())) != cudaSuccess) return e;
+  if ((e = linear_init_r<8>()) != cudaSuccess) return e;
+  if ((e = linear_init_r<4>()) != cudaSuccess) return e;
+  if ((e = linear_init_r<2>()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
+template <int R>
+static void mixer_launch_r(int M, const float* res_feat, const long long* s_t, const float* v_t, const EpsW& w, float* x_out,
+                           float* Rbuf, const float* p_ang, float* p_norm, const float* mean, float scale, float* x_lo_out,
+                           cudaStream_t st, const int* rows, const int* count, float* x_c, float* x_c_lo) {
+  mixer_kernel<R><<<(M + 8 * R - 1) / (8 * R), RT_THREADS, mixer_smem<R>(), st>>>(M, res_feat, s_t, v_t, w, x_out, Rbuf, p_ang, p_norm,
+                                                                             mean[0], mean[1], mean[2], scale, x_lo_out, rows, count,
+                                                                             x_c, x_c_lo);
+}
 void launch_mixer(int M, const float* res_feat, const long long* s_t, const float* v_t, const EpsW& w,
                   float* x_out, float* Rbuf, const float* p_ang, float* p_norm, const float* mean, float scale,
                   float* x_lo_out, cudaStream_t st, const int* rows, const int* count, float* x_c, float* x_c_lo) {
   ProfScope prof__(KK_MIXER, st);
-  mixer_kernel<<<(M + RT_ROWS - 1) / RT_ROWS, RT_THREADS, mixer_smem(), st>>>(M, res_feat, s_t, v_t, w, x_out, Rbuf, p_ang, p_norm,
-                                                                           mean[0], mean[1], mean[2], scale, x_lo_out, rows, count,
-                                                                           x_c, x_c_lo);
+  const int R = rows ? list_rpw("ABOPT_RPW_MIXER", MIXER_LIST_RPW) : 8;
+  if (R == 2) mixer_launch_r<2>(M, res_feat, s_t, v_t, w, x_out, Rbuf, p_ang, p_norm, mean, scale, x_lo_out, st, rows, count, x_c, x_c_lo);
+  else if (R == 4) mixer_launch_r<4>(M, res_feat, s_t, v_t, w, x_out, Rbuf, p_ang, p_norm, mean, scale, x_lo_out, st, rows, count, x_c, x_c_lo);
+  else mixer_launch_r<8>(M, res_feat, s_t, v_t, w, x_out, Rbuf, p_ang, p_norm, mean, scale, x_lo_out, st, rows, count, x_c, x_c_lo);
+}
+
+// one launch of `nheads` heads starting at head_lo over the row tiles of M rows (or of the row list)
+template <int R>
+static void heads_launch_r(int nheads, int head_lo, int M, int L, const float* x, const float* beta, int beta_stride, const float* Rbuf,
+                           const float* v_t, const uint8_t* mask_gen, const EpsW& w, float* v_next, float* R_next, float* eps_pos,
+                           float* c_den, float* prmsd_rows, cudaStream_t st, const int* rows, const int* count, int x_compact) {
+  heads_kernel<R><<<dim3((M + 8 * R - 1) / (8 * R), nheads), RT_THREADS, heads_smem<R>(), st>>>(
+      M, L, x, beta, beta_stride, Rbuf, v_t, mask_gen, w, v_next, R_next, eps_pos, c_den, prmsd_rows, rows, count, head_lo, x_compact);
 }
 void launch_heads(int M, int L, const float* x, const float* beta, int beta_stride, const float* Rbuf, const float* v_t,
                   const uint8_t* mask_gen, const EpsW& w, float* v_next, float* R_next, float* eps_pos, float* c_den,
                   float* prmsd_rows, float* prmsd_logits, cudaStream_t st, const int* rows, const int* count, bool x_compact) {
   ProfScope prof__(KK_HEADS, st);
-  const dim3 tiles((M + RT_ROWS - 1) / RT_ROWS);
+  const int R = rows ? list_rpw("ABOPT_RPW_HEADS", HEADS_LIST_RPW) : 8;
+  auto go = [&](int r, int nheads, int head_lo, const int* rws, const int* cnt, int xc) {
+    if (r == 2) heads_launch_r<2>(nheads, head_lo, M, L, x, beta, beta_stride, Rbuf, v_t, mask_gen, w, v_next, R_next, eps_pos, c_den, prmsd_rows, st, rws, cnt, xc);
+    else if (r == 4) heads_launch_r<4>(nheads, head_lo, M, L, x, beta, beta_stride, Rbuf, v_t, mask_gen, w, v_next, R_next, eps_pos, c_den, prmsd_rows, st, rws, cnt, xc);
+    else heads_launch_r<8>(nheads, head_lo, M, L, x, beta, beta_stride, Rbuf, v_t, mask_gen, w, v_next, R_next, eps_pos, c_den, prmsd_rows, st, rws, cnt, xc);
+  };
   if (rows && w.has_prmsd) {
     // the crd / rot / seq heads on the listed (generated) rows only, the pRMSD head on every row (its logits are averaged
     // over all L rows, dpm_full.py:110)
-    heads_kernel<<<dim3(tiles.x, 3), RT_THREADS, heads_smem(), st>>>(M, L, x, beta, beta_stride, Rbuf, v_t, mask_gen, w, v_next, R_next,
-                                                                    eps_pos, c_den, prmsd_rows, rows, count, 0, x_compact ? 1 : 0);
+    go(R, 3, 0, rows, count, x_compact ? 1 : 0);
     count_launch();
-    heads_kernel<<<dim3(tiles.x, 1), RT_THREADS, heads_smem(), st>>>(M, L, x, beta, beta_stride, Rbuf, v_t, mask_gen, w, v_next, R_next,
-                                                                    eps_pos, c_den, prmsd_rows, nullptr, nullptr, 3, 0);
+    go(8, 1, 3, nullptr, nullptr, 0);
   } else {
-    heads_kernel<<<dim3(tiles.x, w.has_prmsd ? 4 : 3), RT_THREADS, heads_smem(), st>>>(M, L, x, beta, beta_stride, Rbuf, v_t, mask_gen, w, v_next,
-                                                                                    R_next, eps_pos, c_den, prmsd_rows, rows, count, 0,
-                                                                                    x_compact ? 1 : 0);
+    go(R, w.has_prmsd ? 4 : 3, 0, rows, count, x_compact ? 1 : 0);
   }
   if (w.has_prmsd && prmsd_logits != nullptr) {
     prmsd_mean_kernel<<<M / L, 64, 0, st>>>(L, w.prmsd_bins, prmsd_rows, prmsd_logits);

@@ -1,6 +1,9 @@
-// Row-tile GEMM machinery: a CTA of 256 threads owns 64 rows x 128 output columns.
-//   thread (warp w, lane l) accumulates rows  w*8 .. w*8+7  and columns  l*4 .. l*4+3,
-//   so a warp holds 8 complete rows and row-wise reductions (LayerNorm) are warp shuffles.
+// Row-tile GEMM machinery: a CTA of 256 threads owns 8*R rows x 128 output columns (R = rows per warp: 8 for the
+// whole-batch launches, fewer for the short row lists of the sampling loop, where the number of CTAs is what matters).
+//   thread (warp w, lane l) accumulates rows  w*R .. w*R+R-1  and columns  l*4 .. l*4+3,
+//   so a warp holds R complete rows and row-wise reductions (LayerNorm) are warp shuffles.
+// R is deduced from the accumulator array.  Every output element is the same chain of FMAs in the same k order whatever R is,
+// so the results do not depend on it.
 // Operand A is row-major in shared memory (rows x k, k contiguous); operand B is a weight stored
 // K-major in global memory (Wt[k][128], i.e. the transpose of nn.Linear.weight, zero-padded to 128
 // columns) streamed through a double-buffered cp.async ring.
@@ -9,7 +12,7 @@
 
 namespace abopt {
 
-constexpr int RT_ROWS = 64;
+constexpr int RT_ROWS = 64;                // rows of the largest tile (R = 8): sizes the staging buffers
 constexpr int RT_COLS = 128;
 constexpr int RT_THREADS = 256;
 constexpr int RT_KC = 32;                  // k-chunk
@@ -22,9 +25,10 @@ struct RowTileSmem {
   float a[2][RT_ROWS * RT_ALD];            // 2 x  9.0 KB
 };
 
-__device__ __forceinline__ void rt_zero(float (&acc)[8][4]) {
+template <int R>
+__device__ __forceinline__ void rt_zero(float (&acc)[R][4]) {
 #pragma unroll
-  for (int r = 0; r < 8; ++r)
+  for (int r = 0; r < R; ++r)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
 }
@@ -43,8 +47,8 @@ __device__ __forceinline__ void rt_load_w(RowTileSmem& s, int buf, const float* 
 }
 
 // inner product over one staged chunk; A rows come from `arow(r)` = pointer to row r's k-chunk
-template <typename ARow>
-__device__ __forceinline__ void rt_mma_chunk(float (&acc)[8][4], const float* __restrict__ wbuf, ARow arow, int kc) {
+template <int R, typename ARow>
+__device__ __forceinline__ void rt_mma_chunk(float (&acc)[R][4], const float* __restrict__ wbuf, ARow arow, int kc) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll 2
   for (int k = 0; k < kc; k += 4) {
@@ -53,8 +57,8 @@ __device__ __forceinline__ void rt_mma_chunk(float (&acc)[8][4], const float* __
     float4 w2 = *reinterpret_cast<const float4*>(&wbuf[(k + 2) * RT_WLD + lane * 4]);
     float4 w3 = *reinterpret_cast<const float4*>(&wbuf[(k + 3) * RT_WLD + lane * 4]);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const float4 a = *reinterpret_cast<const float4*>(arow(warp * 8 + r) + k);
+    for (int r = 0; r < R; ++r) {
+      const float4 a = *reinterpret_cast<const float4*>(arow(warp * R + r) + k);
       acc[r][0] = fmaf(a.x, w0.x, acc[r][0]); acc[r][1] = fmaf(a.x, w0.y, acc[r][1]);
       acc[r][2] = fmaf(a.x, w0.z, acc[r][2]); acc[r][3] = fmaf(a.x, w0.w, acc[r][3]);
       acc[r][0] = fmaf(a.y, w1.x, acc[r][0]); acc[r][1] = fmaf(a.y, w1.y, acc[r][1]);
@@ -67,8 +71,9 @@ __device__ __forceinline__ void rt_mma_chunk(float (&acc)[8][4], const float* __
   }
 }
 
-// acc += Act(64 x K, resident in smem, pitch lda) * Wt[K][128].   K % 4 == 0.
-__device__ __forceinline__ void rt_gemm_smemA(float (&acc)[8][4], RowTileSmem& s, const float* act, int lda,
+// acc += Act(8R x K, resident in smem, pitch lda) * Wt[K][128].   K % 4 == 0.
+template <int R>
+__device__ __forceinline__ void rt_gemm_smemA(float (&acc)[R][4], RowTileSmem& s, const float* act, int lda,
                                               const float* __restrict__ Wt, int K) {
   const int nchunk = (K + RT_KC - 1) / RT_KC;
   rt_load_w(s, 0, Wt, 0, K);
@@ -85,17 +90,18 @@ __device__ __forceinline__ void rt_gemm_smemA(float (&acc)[8][4], RowTileSmem& s
   }
 }
 
-// acc += A(64 x K gathered from global through `src(row, k)` -> pointer to 4 floats, or nullptr for
+// acc += A(8R x K gathered from global through `src(row, k)` -> pointer to 4 floats, or nullptr for
 // zero fill) * Wt[K][128].   K % RT_KC may be nonzero; K % 4 == 0.
-template <typename Src>
-__device__ __forceinline__ void rt_gemm_globalA(float (&acc)[8][4], RowTileSmem& s, Src src,
+template <int R, typename Src>
+__device__ __forceinline__ void rt_gemm_globalA(float (&acc)[R][4], RowTileSmem& s, Src src,
                                                 const float* __restrict__ Wt, int K) {
   const int nchunk = (K + RT_KC - 1) / RT_KC;
   auto load_a = [&](int buf, int k0) {
-    // 64 rows x 32 k = 512 float4 -> 2 per thread
+    // 8R rows x 32 k = 64R float4 -> 2 per thread at R = 8
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < (64 * R + RT_THREADS - 1) / RT_THREADS; ++i) {
       const int f4 = threadIdx.x + i * RT_THREADS;
+      if ((64 * R) % RT_THREADS != 0 && f4 >= 64 * R) break;
       const int r = f4 >> 3, k4 = f4 & 7;
       float* dst = &s.a[buf][r * RT_ALD + k4 * 4];
       const float* g = (k0 + k4 * 4 < K) ? src(r, k0 + k4 * 4) : nullptr;
@@ -119,34 +125,38 @@ __device__ __forceinline__ void rt_gemm_globalA(float (&acc)[8][4], RowTileSmem&
 }
 
 // acc[r][c] += bias[col]
-__device__ __forceinline__ void rt_add_bias(float (&acc)[8][4], const float* __restrict__ bias) {
+template <int R>
+__device__ __forceinline__ void rt_add_bias(float (&acc)[R][4], const float* __restrict__ bias) {
   const int lane = threadIdx.x & 31;
   const float4 b = *reinterpret_cast<const float4*>(bias + lane * 4);
 #pragma unroll
-  for (int r = 0; r < 8; ++r) { acc[r][0] += b.x; acc[r][1] += b.y; acc[r][2] += b.z; acc[r][3] += b.w; }
+  for (int r = 0; r < R; ++r) { acc[r][0] += b.x; acc[r][1] += b.y; acc[r][2] += b.z; acc[r][3] += b.w; }
 }
-__device__ __forceinline__ void rt_relu(float (&acc)[8][4]) {
+template <int R>
+__device__ __forceinline__ void rt_relu(float (&acc)[R][4]) {
 #pragma unroll
-  for (int r = 0; r < 8; ++r)
+  for (int r = 0; r < R; ++r)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[r][c] = fmaxf(acc[r][c], 0.f);
 }
 // write the tile into a resident activation buffer (row-major, pitch lda)
-__device__ __forceinline__ void rt_store_act(const float (&acc)[8][4], float* act, int lda) {
+template <int R>
+__device__ __forceinline__ void rt_store_act(const float (&acc)[R][4], float* act, int lda) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int r = 0; r < 8; ++r)
-    *reinterpret_cast<float4*>(act + (warp * 8 + r) * lda + lane * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+  for (int r = 0; r < R; ++r)
+    *reinterpret_cast<float4*>(act + (warp * R + r) * lda + lane * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
 }
 // Reference LayerNorm over the 128 columns of each row (common/layers.py:146-155): biased variance,
 // eps inside the sqrt.  In place.
-__device__ __forceinline__ void rt_layernorm(float (&v)[8][4], const float* __restrict__ gamma,
+template <int R>
+__device__ __forceinline__ void rt_layernorm(float (&v)[R][4], const float* __restrict__ gamma,
                                              const float* __restrict__ beta, float eps) {
   const int lane = threadIdx.x & 31;
   const float4 g = *reinterpret_cast<const float4*>(gamma + lane * 4);
   const float4 b = *reinterpret_cast<const float4*>(beta + lane * 4);
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
+  for (int r = 0; r < R; ++r) {
     const float mean = warp_sum(v[r][0] + v[r][1] + v[r][2] + v[r][3]) * (1.f / 128.f);
     const float d0 = v[r][0] - mean, d1 = v[r][1] - mean, d2 = v[r][2] - mean, d3 = v[r][3] - mean;
     const float var = warp_sum(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3) * (1.f / 128.f);
