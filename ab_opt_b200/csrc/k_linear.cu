@@ -323,10 +323,11 @@ void launch_focus_gather(const int* rows, const int* count, const float* x, cons
 // ------------------------------------------------------------------------------------------ launchers
 // Rows per warp (R) of the two row-tile kernels.  Whole-batch launches use R = 8 (64-row tiles, the best FMA : shared-memory
 // ratio).  The launches of the sampling loop that walk a row list (the generated residues: 1 024 rows at C2) are bound by the
-// latency of ONE tile, not by throughput -- 16 tiles of 64 rows leave 132 SMs idle -- so they use smaller tiles on more SMs.
-// The results do not depend on R (rowtile.cuh).  ABOPT_RPW_MIXER / ABOPT_RPW_HEADS (2, 4 or 8; read per call) override the
-// list-launch defaults for A/B measurements.
-constexpr int MIXER_LIST_RPW = 8, HEADS_LIST_RPW = 8;
+// latency of ONE tile, not by throughput -- 16 tiles of 64 rows leave 132 SMs idle -- so they use 16-row tiles on more SMs.
+// The results do not depend on R (rowtile.cuh; scripts/ub/rpw_ab.py checks a whole C2 sample bit for bit).  Measured on B200
+// (profiles/r02_rpw_ab.jsonl, per C2 sample of 100 steps): mixer 3.80 / 2.79 / 2.39 ms and heads 5.03 / 4.00 / 3.53 ms at
+// R = 8 / 4 / 2.  ABOPT_RPW_MIXER / ABOPT_RPW_HEADS (2, 4 or 8; read per call) override the list-launch defaults for A/B runs.
+constexpr int MIXER_LIST_RPW = 2, HEADS_LIST_RPW = 2;
 
 static int list_rpw(const char* env_name, int dflt) {
   const char* e = getenv(env_name);
