@@ -20,6 +20,7 @@ static std::vector<ProfRec> g_prof;
 static cudaEvent_t g_prof_open = nullptr;
 void prof_begin(int kind, cudaStream_t st) {
   if (!g_prof_on) return;
+  if (g_prof_open) cudaEventDestroy(g_prof_open);      // a begin without its end: drop the stale event
   cudaEventCreate(&g_prof_open);
   cudaEventRecord(g_prof_open, st);
 }
@@ -185,8 +186,12 @@ extern "C" int abopt_debug_gemm3x(int device, int M, int N, int K, const float* 
   CUDA_TRY(tc_init());
   cudaStream_t st = (cudaStream_t)stream;
   // exactly as the model uses it: the raw fp32 operands serve as the "hi" planes (the tensor core truncates to tf32)
-  float *Al, *Bl;
-  CUDA_TRY(cudaMalloc(&Al, (size_t)M * K * 4)); CUDA_TRY(cudaMalloc(&Bl, (size_t)N * K * 4));
+  float *Al = nullptr, *Bl = nullptr;
+  CUDA_TRY(cudaMalloc(&Al, (size_t)M * K * 4));
+  {
+    const cudaError_t e2 = cudaMalloc(&Bl, (size_t)N * K * 4);
+    if (e2 != cudaSuccess) { cudaFree(Al); return fail(ABOPT_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e2)); }
+  }
   launch_lo(A, Al, (size_t)M * K, st);
   launch_lo(B, Bl, (size_t)N * K, st);
   const bool ok = launch_gemm3x_plain(M, N, K, A, Al, K, B, Bl, K, D, N, bias, st);
@@ -623,6 +628,9 @@ static int check_ready(abopt_model* m, int N, int L, int need_scope = ABOPT_SCOP
   if (N < 1 || L < 1) return fail(ABOPT_ERR_ARG, "N and L must be positive");
   if (L > ABOPT_MAX_L) return fail(ABOPT_ERR_ARG, "L exceeds ABOPT_MAX_L (" + std::to_string(ABOPT_MAX_L) + ")");
   if ((size_t)N * L > (size_t)1 << 30) return fail(ABOPT_ERR_ARG, "N*L too large");
+  // the Philox counters are keyed by the 32-bit row index in the global batch (k_step.cu)
+  if ((unsigned long long)(m->batch_offset + N) * (unsigned long long)L > 0xFFFFFFFFull)
+    return fail(ABOPT_ERR_ARG, "batch offset + N exceeds the 32-bit global row index");
   return ABOPT_OK;
 }
 
@@ -1273,7 +1281,10 @@ static int ensure_train_ws(abopt_model* m, int N, int L, int Lp, TrainWS& t) {
   const int bins = m->cfg.has_prmsd ? m->cfg.prmsd_bins : 1;
   size_t off = 0;
   auto take = [&](size_t floats) { size_t o = off; off = (off + floats * 4 + 255) & ~size_t(255); return o; };
-  const size_t scr_floats = (size_t)64 * NPROJ * F;
+  // scratch: the split weight-gradient partials (64 x NPROJ x F) or, in block_backward, the lo plane of an (M, F) activation
+  // followed by a transposed weight pair (hi | lo) of at most NPROJ x F each -- whichever is larger
+  size_t scr_floats = (size_t)64 * NPROJ * F;
+  if (scr_floats < M * F + (size_t)2 * NPROJ * F) scr_floats = M * F + (size_t)2 * NPROJ * F;
   const size_t o_xs = take(M * F * (m->cfg.num_layers + 1)), o_P = take(M * NPROJ), o_PG = take(M * 864), o_G = take(M * NPROJ),
                o_gf = take(M * NFEAT), o_s1 = take(M * F), o_h = take(M * F), o_a0 = take(M * F), o_a1 = take(M * F), o_s2 = take(M * F),
                o_t1 = take(M * F), o_t2 = take(M * F), o_t3 = take(M * F), o_ga = take(M * 288), o_gl = take((size_t)N * H * L * Lp),
