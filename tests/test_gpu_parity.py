@@ -332,6 +332,32 @@ def test_sample_philox_mode_properties(flavour):
     assert torch.equal(o[0][0].cpu()[~gen], inp['v'][~gen])
 
 
+@pytest.mark.parametrize('flavour', ['abdock', 'abdesign'])
+def test_row_list_tile_size_does_not_change_results(flavour, monkeypatch):
+    """mixer_kernel / heads_kernel walk the generated-row list in tiles of 8 * R rows (R = 2 by default, k_linear.cu); every
+    output element is the same chain of FMAs whatever R is, so whole trajectories agree bit for bit.  33 generated rows: a
+    ragged last tile for every R."""
+    W = weights.make_state_dict(seed=4, num_layers=2, flavour=flavour)
+    model = build_model(W, 2, flavour=flavour, obj='pred_noise')
+    inp = weights.synthetic_inputs(11, 3, 40, gen_slices=((10, 21),), ragged=True)
+    ci = cu(inp)
+    args = (ci['v'], ci['p'], ci['s'], ci['res_feat'], ci['pair_feat'], ci['mask_generate'], ci['mask_res'])
+    runs = {}
+    for r in ('8', '4', '2'):
+        monkeypatch.setenv('ABOPT_RPW_MIXER', r)
+        monkeypatch.setenv('ABOPT_RPW_HEADS', r)
+        torch.manual_seed(5)
+        runs[r] = model.sample(*args)
+    monkeypatch.delenv('ABOPT_RPW_MIXER')
+    monkeypatch.delenv('ABOPT_RPW_HEADS')
+    torch.manual_seed(5)
+    runs['default'] = model.sample(*args)
+    for r in ('4', '2', 'default'):
+        for t in (0, 50):
+            for a, b in zip(runs['8'][t], runs[r][t]):
+                assert torch.equal(a, b), (r, t)
+
+
 def test_sample_host_entry_point():
     import ctypes
     C = ab_opt_b200._capi
