@@ -32,7 +32,10 @@ def pack_results(local):
     int64 tensors travel as two float32 words each (a bit-exact view, not a conversion)."""
     cols = []
     for t in local:
-        flat = t.reshape(t.shape[0], -1).contiguous()
+        per = 1
+        for d in t.shape[1:]:
+            per *= int(d)
+        flat = t.reshape(t.shape[0], per).contiguous()      # (explicit width: an empty shard cannot infer -1)
         if flat.dtype == torch.int64:
             flat = flat.view(torch.float32)
         elif flat.dtype != torch.float32:
@@ -93,6 +96,10 @@ def sample_shard(model, mine, offset, n_total, group=None, seed=None, **kw):
     res_feat, pair_feat, mask_generate, mask_res on the model's device; `offset` = index of mine[0] in the global batch of
     `n_total`): the full T-step loop on the shard, then the ONE packed gather.  Returns (v, p, s) of all complexes."""
     seed = common_seed(model, group, seed, **kw)
+    if mine['v'].shape[0] == 0:
+        # fewer complexes than ranks: this rank has nothing to sample, but it still takes part in the seed broadcast above
+        # and in the gather (zero rows)
+        return gather_results([mine['v'].float(), mine['p'].float(), mine['s'].long()], n_total, group), {}
     traj = model.sample(mine['v'], mine['p'], mine['s'], mine['res_feat'], mine['pair_feat'], mine['mask_generate'],
                         mine['mask_res'], seed=seed, batch_offset=offset, batch_total=n_total, **kw)
     return gather_results([traj[0][0], traj[0][1], traj[0][2]], n_total, group), traj

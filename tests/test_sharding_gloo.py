@@ -62,11 +62,16 @@ def _worker(rank, world, port, n, L, ret):
     a, b = sharding.shard_bounds(n, world, rank)
     assert mine['v'].shape[0] == b - a and torch.equal(mine['s'], batch['s'][a:b])
     got = sharding.sample_sharded(model, **batch)
-    kw = _FakeDPM.calls[-1]                        # the loop call carries the shard's place in the global batch and a common seed
-    assert kw['batch_offset'] == a and kw['batch_total'] == n and isinstance(kw['seed'], int)
+    if b > a:
+        kw = _FakeDPM.calls[-1]                    # the loop call carries the shard's place in the global batch and a common seed
+        assert kw['batch_offset'] == a and kw['batch_total'] == n and isinstance(kw['seed'], int)
+        seed = kw['seed']
+    else:
+        assert not _FakeDPM.calls                  # an empty shard (fewer complexes than ranks) never enters the loop
+        seed = None
     seeds = [None, None]
-    dist.all_gather_object(seeds, kw['seed'])
-    assert seeds[0] == seeds[1]
+    dist.all_gather_object(seeds, seed)
+    assert seeds[0] == seeds[1] or None in seeds
     ref = model.sample(**batch)[0]
     ok = all(torch.equal(x, y) for x, y in zip(got, ref))
     ret[rank] = bool(ok) and got[0].shape[0] == n
@@ -81,4 +86,14 @@ def test_two_rank_gloo_shard_and_gather():
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, 5, 12, ret), nprocs=2, join=True)      # 5 complexes over 2 ranks: uneven shards
+    assert ret[0] and ret[1]
+
+
+def test_two_rank_gloo_fewer_complexes_than_ranks():
+    with socket.socket() as sk:
+        sk.bind(('127.0.0.1', 0))
+        port = sk.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, 1, 9, ret), nprocs=2, join=True)       # 1 complex over 2 ranks: rank 1's shard is empty
     assert ret[0] and ret[1]
