@@ -243,7 +243,8 @@ int abopt_sample_host(abopt_model* m, int N, int L, const float* v, const float*
  *   [0] rot  [1] pos  [2] seq  [3] prmsd (has_prmsd models, else 0)  [4] dist (has_prmsd + obj pred_x0, else 0).
  * Evaluated as the reference evaluates it under torch.no_grad() (validate(), AbDock/train.py:141-149): log_rotation clamps the
  * cosine at -1.  With autograd enabled the reference clamps at -0.999 (modules/common/so3.py:12-17), which changes the noised
- * rotation of residues within 0.045 rad of pi; that variant ships with the backward pass, which is not part of this library yet. */
+ * rotation of residues within 0.045 rad of pi: flag ABOPT_GRAD_SEMANTICS selects that evaluation here, and abopt_loss_backward
+ * (below) always uses it. */
 int abopt_loss_forward(abopt_model* m, int N, int L, const float* v_0, const float* p_0, const int64_t* s_0,
                        const float* res_feat, const float* pair_feat, const uint8_t* mask_generate,
                        const uint8_t* mask_res, uint32_t flags, const int64_t* t, uint64_t seed,
